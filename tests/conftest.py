@@ -1,0 +1,12 @@
+"""pytest configuration: registers the `gpu` marker and puts the repo root on
+sys.path so `oracle` (the CPU checker) and `__graft_entry__` import cleanly."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: test needs a CUDA device (run with -m gpu on a B200)")
