@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""bench.py -- XXZ L=32 Sz=0 H.psi applies/s on B200 (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one H.psi (reference apply_H!, Hamiltonian.jl:211-273) over the
+whole L=32, nup=16 sector (601 080 390 states, f64) with the counter-based
+seeded psi.  `value` is device-resident throughput timed with CUDA events on the
+library's own stream; `e2e` is the same call through the host-buffer entry
+points (pinned H2D of psi, kernel, D2H of out inside the timed region);
+`roofline` compares algorithmic bytes (16 B/state) with the measured HBM copy
+peak; `cpu_baseline` times the CPU oracle port of the reference loop on a
+bounded sample.  With N > 1 the same L=32 vector is sharded by rank range over
+N GPUs (strong scaling): peer shards are read over NVLink, no data collective.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "spindynamics.jl_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "XXZ L=32 Sz=0 H.psi applies/s"
+UNIT = "applies/s"
+SEED = 20261018
+
+
+def comb(n, k):
+    from math import comb as c
+    return c(n, k)
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                    "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                self.samples.append([x.strip() for x in o.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            if len(s) < 6:
+                continue
+            try:
+                sm.append(float(s[0]))
+                mx = float(s[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_applies_per_s(L_sample, reps, L_target=32):
+    """Times the oracle's reference-faithful apply_H! (explicit states[], hash map in
+    place of the Dict, per-term loops, OpenMP over idx) on L_sample and converts to
+    L_target-equivalent applies/s by the state*bond count ratio."""
+    from oracle import oracle as orc
+    m = orc.XXZChain(L_sample, Jxy=1.0, Jz=1.0, hz=0.0, nup=L_sample // 2)
+    n = len(m)
+    psi = orc.fill_seeded(n, SEED)
+    out = np.empty_like(psi)
+    orc.apply_H_(out, psi, m)                                   # warm-up (page faults, caches)
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        orc.apply_H_(out, psi, m)
+        times.append(time.perf_counter() - t0)
+    t = float(np.mean(times))
+    work_sample = n * (L_sample - 1)
+    work_target = comb(L_target, L_target // 2) * (L_target - 1)
+    cores = int(orc.lib().orc_num_threads())
+    return {"value": (work_sample / t) / work_target, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"oracle/oracle.c orc_apply_H_f64 (C/OpenMP restatement of Hamiltonian.jl:211-273; Julia is not "
+                      f"installed) on XXZ L={L_sample} nup={L_sample // 2} ({n} states), {reps} applies, "
+                      f"{t * 1e3:.1f} ms each on {cores} threads; scaled to L={L_target} by states*bonds",
+            "ms_per_sample_apply": t * 1e3}, times
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  Julia is
+    absent from this image, so this is the oracle port (kind "port")."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    L_s = args.cpu_L
+    res, times = cpu_port_applies_per_s(L_s, max(1, args.steps))
+    line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / res["value"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic (counter-based seeded psi)",
+            "config": {"workload": "XXZChain L=32 nup=16 open, f64 H.psi, CPU sample scaled (see cpu_baseline.sample)"},
+            "cpu_baseline": res,
+            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--L", type=int, default=32, help="chain length (default: the metric's L=32)")
+    ap.add_argument("--dtype", default="f64", choices=["f64", "c128"])
+    ap.add_argument("--cpu-L", type=int, default=28, help="chain length of the CPU baseline sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--path", default=None, choices=[None, "tiled", "generic"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import spindyn as sd
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        ctx = sd.Context.from_torch_distributed(local_rank)
+    else:
+        if sd.device_count() < 1:
+            raise SystemExit("bench.py needs a CUDA device: libspindyn_cuda has no CPU fallback")
+        ctx = sd.Context(0)
+    sd.set_default_context(ctx)
+
+    L, nup = args.L, args.L // 2
+    dtype = np.float64 if args.dtype == "f64" else np.complex128
+    esz = 8 if args.dtype == "f64" else 16
+    model = sd.XXZChain(L, Jxy=1.0, Jz=1.0, hz=0.0, nup=nup, ctx=ctx)
+    if args.path:
+        model.set_path(args.path)
+    N = model.dim
+    first, count = model.local_range
+    psi = model.vector(dtype).fill_seeded(SEED, 1.0 / np.sqrt(N / 3.0))      # ||psi|| ~ 1
+    out = model.vector(dtype)
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            dist.barrier()
+
+    for _ in range(max(args.warmup, 0)):
+        sd.apply_H_(out, psi, model)
+    barrier()
+    l0 = ctx.launch_count()
+    with ClockSampler(local_rank) as clk:
+        ctx.timer_start()
+        for _ in range(args.steps):
+            sd.apply_H_(out, psi, model)
+        ms_total = ctx.timer_stop()
+        barrier()
+    launches = ctx.launch_count() - l0
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+    ms_step = ms_total / args.steps
+    value = 1e3 / ms_step
+
+    # end to end through the host-buffer entry points (pinned host memory)
+    e2e = None
+    if not args.no_e2e:
+        hin = sd.PinnedBuffer(count, dtype)
+        hout = sd.PinnedBuffer(count, dtype)
+        hin.array[:] = 0.0
+        psi.to_host(hin.array)
+        lib, check = sd.lib(), sd._lib.check
+
+        def e2e_step():
+            check(lib.sd_vec_upload_async(psi._h, hin._p))
+            check(lib.sd_apply_H(model._h, out._h, psi._h))
+            check(lib.sd_vec_download_async(out._h, hout._p))
+            ctx.sync()
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        ctx.timer_start()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        ms_e2e = ctx.timer_stop()
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        ms_e2e = max(ms_e2e, 0.0)
+        if dist is not None:
+            import torch
+            t = torch.tensor([ms_e2e], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e2e = float(t.item())
+        e2e = {"value": 1e3 / (ms_e2e / args.e2e_steps), "unit": UNIT,
+               "h2d_bytes_per_step": int(N * esz), "d2h_bytes_per_step": int(N * esz),
+               "steps": args.e2e_steps, "ms_per_step": ms_e2e / args.e2e_steps, "wall_ms_per_step": wall / args.e2e_steps,
+               "note": "pinned host psi -> HBM, sd_apply_H, out -> pinned host, all inside the timed region"}
+        checksum = float(np.sum(hout.array[:min(count, 1 << 20)]).real)
+        hin.free()
+        hout.free()
+    else:
+        checksum = None
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        alg_bytes = 2 * esz * N                              # read psi once + write out once
+        # the apply kernel is the only kernel in a step; per-launch time = step time (per GPU: its shard)
+        achieved = alg_bytes / world / (ms_step * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                with open(tpath) as f:
+                    traffic = json.load(f).get(f"apply_L{L}_{args.dtype}_bytes_per_launch")
+            except Exception:
+                traffic = None
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "peak_source": peak_src, "kernel": f"sd_tile_apply_kernel ({model.info['kernel_path']})",
+                    "algorithmic_bytes_per_launch": alg_bytes // world,
+                    "note": "16 B/state f64 (32 c128): one read of psi + one write of out; index math is on the fly"}
+        cpu = None
+        if not args.no_cpu and world == 1:
+            cpu, _ = cpu_port_applies_per_s(args.cpu_L, 4)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": args.dtype, "data": "synthetic (counter-based seeded psi, splitmix64)",
+                "config": {"workload": f"XXZChain L={L} nup={nup} open Jxy=Jz=1 hz=0, {args.dtype} H.psi, N={N} states "
+                                       f"({N * esz / 1e9:.2f} GB per vector)",
+                           "l2": "inputs >> 126 MB L2, no flush needed" if N * esz > 1e9 else "WARNING: fits L2",
+                           "sharding": f"{world} contiguous rank ranges, NVLink peer reads" if world > 1 else "single GPU",
+                           "kernel_path": model.info["kernel_path"], "tile_sites": model.info["tile_sites"]},
+                "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+                "cpu_baseline": cpu, "checksum": checksum}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,1303 @@
+// sd_api.cu -- the C ABI of libspindyn_cuda (include/spindyn.h): contexts,
+// models, device vectors, the H.psi operator and the recurrences that call it.
+// Host code only orchestrates; all vector work runs in the kernels of
+// sd_kernels.cuh.  There is no CPU fallback: without a device every compute
+// entry point returns SD_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/spindyn.h"
+#include "sd_common.h"
+#include "sd_tile.h"
+#include "sd_tile_host.h"
+#include "sd_kernels.cuh"
+
+#define SD_VERSION 100
+
+// ----------------------------------------------------------------- errors
+static thread_local char g_err[512] = "";
+static int sd_fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define SD_CUDA(call)                                                                       \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess)                                                              \
+            return sd_fail(e_ == cudaErrorMemoryAllocation ? SD_ERR_NOMEM : SD_ERR_CUDA,    \
+                           "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define SD_TRY(call)              \
+    do {                          \
+        int r_ = (call);          \
+        if (r_ != SD_OK) return r_; \
+    } while (0)
+#define SD_ARG(cond, ...)                                  \
+    do {                                                   \
+        if (!(cond)) return sd_fail(SD_ERR_ARG, __VA_ARGS__); \
+    } while (0)
+
+// ----------------------------------------------------------------- NCCL (dlopen, only when world > 1)
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSuccess_ = 0 };
+enum { ncclUint8_ = 1, ncclFloat64_ = 8 };   // ncclDataType_t values (nccl.h)
+enum { ncclSum_ = 0 };
+struct SdNccl {
+    void *h = nullptr;
+    int (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+static SdNccl g_nccl;
+static std::mutex g_nccl_mu;
+static int sd_nccl_load() {
+    std::lock_guard<std::mutex> lk(g_nccl_mu);
+    if (g_nccl.h) return SD_OK;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *n : names) {
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) return sd_fail(SD_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define SD_SYM(field, name)                                                   \
+    *(void **)(&g_nccl.field) = dlsym(h, name);                               \
+    if (!g_nccl.field) return sd_fail(SD_ERR_NCCL, "libnccl lacks %s", name);
+    SD_SYM(GetUniqueId, "ncclGetUniqueId")
+    SD_SYM(CommInitRank, "ncclCommInitRank")
+    SD_SYM(CommDestroy, "ncclCommDestroy")
+    SD_SYM(AllReduce, "ncclAllReduce")
+    SD_SYM(AllGather, "ncclAllGather")
+    SD_SYM(GetErrorString, "ncclGetErrorString")
+#undef SD_SYM
+    g_nccl.h = h;
+    return SD_OK;
+}
+#define SD_NCCL(call)                                                                      \
+    do {                                                                                   \
+        int e_ = (call);                                                                   \
+        if (e_ != 0) return sd_fail(SD_ERR_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString(e_)); \
+    } while (0)
+
+// ----------------------------------------------------------------- handles
+#define SD_NSCAL 4096
+struct sd_ctx {
+    int device = 0;
+    int rank = 0, world = 1;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    ncclComm_t comm = nullptr;
+    uint64_t *d_binom = nullptr;
+    double *d_scal = nullptr;       // device scalars [SD_NSCAL]
+    double *h_scal = nullptr;       // pinned mirror
+    double *d_partials = nullptr;
+    size_t partials_cap = 0;        // doubles
+    unsigned char *d_ipc = nullptr; // [world*64] handle exchange buffer
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint64_t launches = 0;
+    std::vector<uint64_t> binom;
+};
+
+struct SdTileDev {
+    bool ok = false;
+    SdTileHost host;
+    uint32_t cap = 0;
+    size_t smem = 0;
+    void *d_perm = nullptr, *d_midcfg = nullptr, *d_urank = nullptr, *d_dmid = nullptr, *d_cls = nullptr;
+    uint64_t keys[SD_MAX_WORLD + 1];
+};
+
+struct sd_model {
+    sd_ctx *ctx = nullptr;
+    int L = 0, k = -1;
+    uint64_t N = 0;
+    std::vector<int> hop_a, hop_b, zz_a, zz_b;
+    std::vector<double> hop_J, zz_J, field;
+    int *d_hop_a = nullptr, *d_hop_b = nullptr, *d_zz_a = nullptr, *d_zz_b = nullptr;
+    double *d_hop_J = nullptr, *d_zz_J = nullptr, *d_field = nullptr;
+    uint64_t *d_linA = nullptr, *d_linB = nullptr;
+    int lin_h = 0;
+    int path = SD_PATH_GENERIC;
+    bool tile_capable = false;
+    int tile_T[2] = {5, 4};
+    SdTileDev tile[2];              // [0]: F64, [1]: C128
+    SdShardMap shards;
+};
+
+struct sd_vec {
+    sd_model *model = nullptr;
+    int dtype = SD_F64, nc = 1;
+    uint64_t local_n = 0;
+    double *d = nullptr;
+    SdVecView view;
+    void *peer[SD_MAX_WORLD];
+    bool owned = true;
+};
+
+struct sd_vecset {
+    std::vector<sd_vec *> v;
+};
+
+static inline unsigned sd_blas_grid(const sd_ctx *c, uint64_t n) {
+    uint64_t g = (n + SD_BLAS_THREADS - 1) / SD_BLAS_THREADS;
+    const uint64_t cap = (uint64_t)c->sm_count * 8;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (unsigned)g;
+}
+static int sd_launch_check(sd_ctx *c, const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return sd_fail(SD_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    c->launches++;
+    return SD_OK;
+}
+static int sd_use(const sd_ctx *c) {
+    SD_CUDA(cudaSetDevice(c->device));
+    return SD_OK;
+}
+static int sd_partials_reserve(sd_ctx *c, size_t doubles) {
+    if (doubles <= c->partials_cap) return SD_OK;
+    if (c->d_partials) { SD_CUDA(cudaStreamSynchronize(c->stream)); SD_CUDA(cudaFree(c->d_partials)); c->d_partials = nullptr; }
+    size_t cap = std::max(doubles, (size_t)1 << 16);
+    SD_CUDA(cudaMalloc(&c->d_partials, cap * sizeof(double)));
+    c->partials_cap = cap;
+    return SD_OK;
+}
+// partials[slot*nparts + i] -> d_scal[slot_out + slot] (+ NCCL sum over ranks)
+static int sd_finish_reduce(sd_ctx *c, unsigned nparts, int slotmask, int slot_out) {
+    sd_reduce_partials_kernel<<<1, 1024, 0, c->stream>>>(c->d_partials, nparts, slotmask, c->d_scal + slot_out);
+    SD_TRY(sd_launch_check(c, "sd_reduce_partials_kernel"));
+    if (c->world > 1)
+        SD_NCCL(g_nccl.AllReduce(c->d_scal + slot_out, c->d_scal + slot_out, SD_NSLOT, ncclFloat64_, ncclSum_,
+                                 c->comm, c->stream));
+    return SD_OK;
+}
+static int sd_fetch(sd_ctx *c, int slot, int n, double *out) {
+    SD_CUDA(cudaMemcpyAsync(c->h_scal + slot, c->d_scal + slot, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SD_CUDA(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < n; ++i) out[i] = c->h_scal[slot + i];
+    return SD_OK;
+}
+// stream-ordered barrier across ranks: peers' earlier kernels have finished
+// before any later kernel of this rank runs.
+static int sd_rank_barrier(sd_ctx *c) {
+    if (c->world <= 1) return SD_OK;
+    SD_NCCL(g_nccl.AllReduce(c->d_scal + SD_NSCAL - 8, c->d_scal + SD_NSCAL - 8, 1, ncclFloat64_, ncclSum_,
+                             c->comm, c->stream));
+    return SD_OK;
+}
+
+// All exported functions get C linkage from their declarations in spindyn.h.
+
+const char *sd_last_error(void) { return g_err; }
+int sd_version(void) { return SD_VERSION; }
+int sd_device_count(int *n) {
+    SD_ARG(n, "n is NULL");
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) { *n = 0; return sd_fail(SD_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+    *n = c;
+    return SD_OK;
+}
+
+// ------------------------------------------------------------------ context
+static int sd_ctx_init(int device, int rank, int world, const void *id128, sd_ctx **out) {
+    SD_ARG(out, "ctx is NULL");
+    *out = nullptr;
+    SD_ARG(world >= 1 && world <= SD_MAX_WORLD, "world must be 1..%d", SD_MAX_WORLD);
+    SD_ARG(rank >= 0 && rank < world, "rank out of range");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return sd_fail(SD_ERR_CUDA, "no CUDA device available (libspindyn_cuda has no CPU fallback): %s",
+                       e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    SD_ARG(device >= 0 && device < ndev, "device %d out of range (0..%d)", device, ndev - 1);
+    sd_ctx *c = new (std::nothrow) sd_ctx;
+    if (!c) return sd_fail(SD_ERR_NOMEM, "out of host memory");
+    c->device = device; c->rank = rank; c->world = world;
+    SD_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SD_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    SD_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    SD_CUDA(cudaEventCreate(&c->ev0));
+    SD_CUDA(cudaEventCreate(&c->ev1));
+    c->binom.assign(SD_BINOM_DIM * SD_BINOM_DIM, 0);
+    sd_fill_binom(c->binom.data());
+    SD_CUDA(cudaMalloc(&c->d_binom, c->binom.size() * sizeof(uint64_t)));
+    SD_CUDA(cudaMemcpy(c->d_binom, c->binom.data(), c->binom.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    SD_CUDA(cudaMalloc(&c->d_scal, SD_NSCAL * sizeof(double)));
+    SD_CUDA(cudaMemset(c->d_scal, 0, SD_NSCAL * sizeof(double)));
+    SD_CUDA(cudaMallocHost(&c->h_scal, SD_NSCAL * sizeof(double)));
+    if (world > 1) {
+        SD_ARG(id128, "id128 is NULL");
+        SD_TRY(sd_nccl_load());
+        ncclUniqueId id;
+        memcpy(&id, id128, sizeof(id));
+        SD_NCCL(g_nccl.CommInitRank(&c->comm, world, id, rank));
+        SD_CUDA(cudaMalloc(&c->d_ipc, (size_t)(world + 1) * 64));
+    }
+    *out = c;
+    return SD_OK;
+}
+int sd_ctx_create(int device, sd_ctx **ctx) { return sd_ctx_init(device, 0, 1, nullptr, ctx); }
+int sd_nccl_unique_id(void *id128) {
+    SD_ARG(id128, "id128 is NULL");
+    SD_TRY(sd_nccl_load());
+    ncclUniqueId id;
+    SD_NCCL(g_nccl.GetUniqueId(&id));
+    memcpy(id128, &id, sizeof(id));
+    return SD_OK;
+}
+int sd_ctx_create_rank(int device, int rank, int world, const void *id128, sd_ctx **ctx) {
+    return sd_ctx_init(device, rank, world, id128, ctx);
+}
+int sd_ctx_free(sd_ctx *c) {
+    if (!c) return SD_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm) g_nccl.CommDestroy(c->comm);
+    cudaFree(c->d_binom); cudaFree(c->d_scal); cudaFreeHost(c->h_scal); cudaFree(c->d_partials); cudaFree(c->d_ipc);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return SD_OK;
+}
+int sd_ctx_sync(sd_ctx *c) {
+    SD_ARG(c, "ctx is NULL");
+    SD_TRY(sd_use(c));
+    SD_CUDA(cudaStreamSynchronize(c->stream));
+    return SD_OK;
+}
+int sd_ctx_rank(const sd_ctx *c, int *rank, int *world) {
+    SD_ARG(c, "ctx is NULL");
+    if (rank) *rank = c->rank;
+    if (world) *world = c->world;
+    return SD_OK;
+}
+int sd_timer_start(sd_ctx *c) {
+    SD_ARG(c, "ctx is NULL");
+    SD_TRY(sd_use(c));
+    SD_CUDA(cudaEventRecord(c->ev0, c->stream));
+    return SD_OK;
+}
+int sd_timer_stop(sd_ctx *c, float *ms) {
+    SD_ARG(c && ms, "NULL argument");
+    SD_TRY(sd_use(c));
+    SD_CUDA(cudaEventRecord(c->ev1, c->stream));
+    SD_CUDA(cudaEventSynchronize(c->ev1));
+    SD_CUDA(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return SD_OK;
+}
+int sd_launch_count(const sd_ctx *c, uint64_t *n) {
+    SD_ARG(c && n, "NULL argument");
+    *n = c->launches;
+    return SD_OK;
+}
+
+// -------------------------------------------------------------------- model
+template <typename T>
+static int sd_to_device(T **dst, const std::vector<T> &src) {
+    *dst = nullptr;
+    const size_t n = std::max<size_t>(src.size(), 1);
+    SD_CUDA(cudaMalloc(dst, n * sizeof(T)));
+    if (!src.empty()) SD_CUDA(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return SD_OK;
+}
+
+static int sd_tile_setup(sd_model *m, int which, int B) {
+    SdTileDev &t = m->tile[which];
+    t.ok = false;
+    const int L = m->L;
+    std::vector<double> Jhop(L, 0.0), Jz(L, 0.0);
+    for (size_t b = 0; b < m->hop_a.size(); ++b) Jhop[m->hop_a[b]] += m->hop_J[b];
+    for (size_t b = 0; b < m->zz_a.size(); ++b) Jz[m->zz_a[b]] += m->zz_J[b];
+    if (!sd_tile_build(L, m->k, B, m->tile_T[which], Jhop.data(), Jz.data(), m->field.data(), t.host)) return SD_OK;
+    const int nc = which + 1;
+    t.cap = t.host.cap_max;
+    t.smem = sd_tile_smem_bytes(nc, t.cap, t.host.P.M);
+    if (t.smem > 227 * 1024) return SD_OK;
+    SD_TRY(sd_to_device((uint16_t **)&t.d_perm, t.host.perm));
+    SD_TRY(sd_to_device((uint16_t **)&t.d_midcfg, t.host.midcfg));
+    SD_TRY(sd_to_device((uint16_t **)&t.d_urank, t.host.urank));
+    SD_TRY(sd_to_device((double **)&t.d_dmid, t.host.dmid));
+    SD_TRY(sd_to_device((uint32_t **)&t.d_cls, t.host.cls_base));
+    SdTileParams &P = t.host.P;
+    P.binom = m->ctx->d_binom;
+    P.perm = (const uint16_t *)t.d_perm;
+    P.midcfg = (const uint16_t *)t.d_midcfg;
+    P.urank = (const uint16_t *)t.d_urank;
+    P.dmid = (const double *)t.d_dmid;
+    P.cls_base = (const uint32_t *)t.d_cls;
+    t.ok = true;
+    return SD_OK;
+}
+
+static int sd_env_int(const char *name, int dflt) {
+    const char *s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+int sd_model_create(sd_ctx *ctx, int L, int nup, const sd_bond *hop, int nhop, const sd_bond *zz, int nzz,
+                    const double *field, sd_model **model) {
+    SD_ARG(ctx && model, "NULL argument");
+    *model = nullptr;
+    // Basis.jl:9-20
+    SD_ARG(L >= 1, "L must be at least 1");
+    SD_ARG(L <= SD_MAX_L, "L must be at most 63 when using UInt64 basis states");
+    SD_ARG(nup >= -1 && nup <= L, "nup must satisfy 0 <= nup <= L");
+    SD_ARG(nhop >= 0 && nzz >= 0 && (nhop == 0 || hop) && (nzz == 0 || zz) && field, "bad bond lists");
+    SD_TRY(sd_use(ctx));
+    sd_model *m = new (std::nothrow) sd_model;
+    if (!m) return sd_fail(SD_ERR_NOMEM, "out of host memory");
+    m->ctx = ctx; m->L = L; m->k = nup;
+    m->N = nup < 0 ? (1ULL << L) : ctx->binom[L * SD_BINOM_DIM + nup];
+    bool all_nn = true;
+    for (int b = 0; b < nhop; ++b) {
+        const int64_t i = hop[b].i, j = hop[b].j;
+        if (i < 1 || i > L || j < 1 || j > L) { delete m; return sd_fail(SD_ERR_ARG, "hopping site outside 1..L"); }
+        if (i == j) continue;                       // bits never differ: the reference skips it
+        const int a = (int)std::min(i, j) - 1, c = (int)std::max(i, j) - 1;
+        m->hop_a.push_back(a); m->hop_b.push_back(c); m->hop_J.push_back(hop[b].J);
+        if (c != a + 1) all_nn = false;
+    }
+    for (int b = 0; b < nzz; ++b) {
+        const int64_t i = zz[b].i, j = zz[b].j;
+        if (i < 1 || i > L || j < 1 || j > L) { delete m; return sd_fail(SD_ERR_ARG, "zz site outside 1..L"); }
+        const int a = (int)std::min(i, j) - 1, c = (int)std::max(i, j) - 1;
+        m->zz_a.push_back(a); m->zz_b.push_back(c); m->zz_J.push_back(zz[b].J);
+        if (c != a + 1) all_nn = false;
+    }
+    m->field.assign(field, field + L);
+    SD_TRY(sd_to_device(&m->d_hop_a, m->hop_a));
+    SD_TRY(sd_to_device(&m->d_hop_b, m->hop_b));
+    SD_TRY(sd_to_device(&m->d_hop_J, m->hop_J));
+    SD_TRY(sd_to_device(&m->d_zz_a, m->zz_a));
+    SD_TRY(sd_to_device(&m->d_zz_b, m->zz_b));
+    SD_TRY(sd_to_device(&m->d_zz_J, m->zz_J));
+    SD_TRY(sd_to_device(&m->d_field, m->field));
+    // two-table ranking for non-nearest-neighbour hops in a sector (L <= 40)
+    bool need_lin = false;
+    for (size_t b = 0; b < m->hop_a.size(); ++b) if (m->hop_b[b] != m->hop_a[b] + 1) need_lin = true;
+    if (nup >= 0 && need_lin && L >= 2 && L <= 40) {
+        const int h = L / 2, g = L - h;
+        const uint64_t *C = ctx->binom.data();
+        std::vector<uint64_t> A((size_t)1 << h, 0), Bt((size_t)1 << g, 0);
+        for (uint64_t lo = 0; lo < (1ULL << h); ++lo) {
+            const int pl = __builtin_popcountll(lo);
+            if (pl > nup || nup - pl > g) continue;
+            uint64_t acc = 0;
+            int rem = nup;                           // set bits at positions >= q
+            for (int q = 0; q < h; ++q) {
+                if ((lo >> q) & 1ULL) --rem;
+                else acc += sd_binom_at(C, SD_BINOM_DIM, L - 1 - q, rem - 1);
+            }
+            A[lo] = acc;
+        }
+        for (uint64_t hi = 0; hi < (1ULL << g); ++hi) {
+            int rem = __builtin_popcountll(hi);
+            if (rem > nup) continue;
+            uint64_t acc = 0;
+            for (int q = 0; q < g; ++q) {
+                if ((hi >> q) & 1ULL) --rem;
+                else acc += sd_binom_at(C, SD_BINOM_DIM, L - 1 - (h + q), rem - 1);
+            }
+            Bt[hi] = acc;
+        }
+        SD_TRY(sd_to_device(&m->d_linA, A));
+        SD_TRY(sd_to_device(&m->d_linB, Bt));
+        m->lin_h = h;
+    }
+    // tiled path: sector basis, every bond nearest-neighbour
+    m->tile_T[0] = sd_env_int("SD_TILE_T", 5);
+    m->tile_T[1] = sd_env_int("SD_TILE_T_C128", 4);
+    m->tile_capable = false;
+    if (nup >= 0 && all_nn && L >= 10 && !sd_env_int("SD_FORCE_GENERIC", 0)) {
+        const int B1 = std::min(L, sd_env_int("SD_TILE_B", 15));
+        const int B2 = std::min(L, sd_env_int("SD_TILE_B_C128", 13));
+        SD_TRY(sd_tile_setup(m, 0, B1));
+        SD_TRY(sd_tile_setup(m, 1, std::min(B1, B2)));
+        m->tile_capable = m->tile[0].ok && m->tile[1].ok;
+    }
+    m->path = m->tile_capable ? SD_PATH_TILED : SD_PATH_GENERIC;
+    // shards: tile-aligned to the coarser (F64) tiling when tiled, plain equal split otherwise
+    uint64_t bounds[SD_MAX_WORLD + 1];
+    if (m->tile_capable) {
+        sd_tile_shard_bounds(m->tile[0].host, ctx->world, bounds, m->tile[0].keys);
+        for (int g = 0; g <= ctx->world; ++g) {
+            uint64_t base = 0;
+            m->tile[1].keys[g] = sd_tile_key_of_rank(m->tile[1].host, bounds[g], &base);
+            if (base != bounds[g]) { delete m; return sd_fail(SD_ERR_UNSUPPORTED, "internal: shard bound not tile aligned"); }
+        }
+    } else {
+        for (int g = 0; g <= ctx->world; ++g)
+            bounds[g] = (g == ctx->world) ? m->N : (uint64_t)(((unsigned __int128)m->N * g) / ctx->world);
+    }
+    m->shards.world = ctx->world; m->shards.rank = ctx->rank;
+    for (int g = 0; g <= SD_MAX_WORLD; ++g) m->shards.start[g] = bounds[std::min(g, ctx->world)];
+    *model = m;
+    return SD_OK;
+}
+
+int sd_model_free(sd_model *m) {
+    if (!m) return SD_OK;
+    cudaSetDevice(m->ctx->device);
+    cudaStreamSynchronize(m->ctx->stream);
+    cudaFree(m->d_hop_a); cudaFree(m->d_hop_b); cudaFree(m->d_hop_J);
+    cudaFree(m->d_zz_a); cudaFree(m->d_zz_b); cudaFree(m->d_zz_J); cudaFree(m->d_field);
+    cudaFree(m->d_linA); cudaFree(m->d_linB);
+    for (int w = 0; w < 2; ++w) {
+        SdTileDev &t = m->tile[w];
+        cudaFree(t.d_perm); cudaFree(t.d_midcfg); cudaFree(t.d_urank); cudaFree(t.d_dmid); cudaFree(t.d_cls);
+    }
+    delete m;
+    return SD_OK;
+}
+int sd_model_dim(const sd_model *m, uint64_t *dim) {
+    SD_ARG(m && dim, "NULL argument");
+    *dim = m->N;
+    return SD_OK;
+}
+int sd_model_local_range(const sd_model *m, uint64_t *first, uint64_t *count) {
+    SD_ARG(m, "NULL argument");
+    const uint64_t a = m->shards.start[m->shards.rank], b = m->shards.start[m->shards.rank + 1];
+    if (first) *first = a;
+    if (count) *count = b - a;
+    return SD_OK;
+}
+int sd_model_shard_bounds(const sd_model *m, int world, uint64_t *bounds) {
+    SD_ARG(m && bounds, "NULL argument");
+    SD_ARG(world >= 1 && world <= SD_MAX_WORLD, "world must be 1..%d", SD_MAX_WORLD);
+    if (m->tile_capable) sd_tile_shard_bounds(m->tile[0].host, world, bounds, nullptr);
+    else
+        for (int g = 0; g <= world; ++g)
+            bounds[g] = (g == world) ? m->N : (uint64_t)(((unsigned __int128)m->N * g) / world);
+    return SD_OK;
+}
+int sd_model_info(const sd_model *m, int *kernel_path, int *tile_sites, int *rank_bits) {
+    SD_ARG(m, "NULL argument");
+    if (kernel_path) *kernel_path = m->path;
+    if (tile_sites) *tile_sites = m->tile_capable ? m->tile[0].host.P.B : 0;
+    if (rank_bits) *rank_bits = (m->N > 0xffffffffULL) ? 64 : 32;
+    return SD_OK;
+}
+int sd_model_set_path(sd_model *m, int kernel_path) {
+    SD_ARG(m, "NULL argument");
+    if (kernel_path == SD_PATH_GENERIC) { m->path = SD_PATH_GENERIC; return SD_OK; }
+    if (kernel_path == SD_PATH_TILED) {
+        if (!m->tile_capable)
+            return sd_fail(SD_ERR_UNSUPPORTED, "model does not qualify for the tiled kernel (sector basis, nearest-neighbour bonds, L >= 10)");
+        m->path = SD_PATH_TILED;
+        return SD_OK;
+    }
+    return sd_fail(SD_ERR_ARG, "unknown kernel path %d", kernel_path);
+}
+
+// -------------------------------------------------------------------- basis
+int sd_unrank(sd_model *m, uint64_t first, uint64_t count, uint64_t *states) {
+    SD_ARG(m && (states || count == 0), "NULL argument");
+    SD_ARG(first <= m->N && count <= m->N - first, "range outside the basis");
+    if (count == 0) return SD_OK;
+    sd_ctx *c = m->ctx;
+    SD_TRY(sd_use(c));
+    uint64_t *d = nullptr;
+    SD_CUDA(cudaMalloc(&d, count * sizeof(uint64_t)));
+    sd_unrank_kernel<<<sd_blas_grid(c, count), SD_BLAS_THREADS, 0, c->stream>>>(m->L, m->k, c->d_binom, first, count, d);
+    int rc = sd_launch_check(c, "sd_unrank_kernel");
+    if (rc == SD_OK) {
+        cudaError_t e = cudaMemcpyAsync(states, d, count * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = sd_fail(SD_ERR_CUDA, "sd_unrank copy: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d);
+    return rc;
+}
+int sd_rank(sd_model *m, const uint64_t *states, uint64_t count, int64_t *idx1) {
+    SD_ARG(m && ((states && idx1) || count == 0), "NULL argument");
+    if (count == 0) return SD_OK;
+    sd_ctx *c = m->ctx;
+    SD_TRY(sd_use(c));
+    uint64_t *ds = nullptr;
+    int64_t *di = nullptr;
+    SD_CUDA(cudaMalloc(&ds, count * sizeof(uint64_t)));
+    cudaError_t e = cudaMalloc(&di, count * sizeof(int64_t));
+    if (e != cudaSuccess) { cudaFree(ds); return sd_fail(SD_ERR_NOMEM, "cudaMalloc: %s", cudaGetErrorString(e)); }
+    int rc = SD_OK;
+    e = cudaMemcpyAsync(ds, states, count * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        sd_rank_kernel<<<sd_blas_grid(c, count), SD_BLAS_THREADS, 0, c->stream>>>(m->L, m->k, c->d_binom, ds, count, di);
+        rc = sd_launch_check(c, "sd_rank_kernel");
+        if (rc == SD_OK) {
+            e = cudaMemcpyAsync(idx1, di, count * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        }
+    }
+    if (rc == SD_OK && e != cudaSuccess) rc = sd_fail(SD_ERR_CUDA, "sd_rank: %s", cudaGetErrorString(e));
+    cudaFree(ds); cudaFree(di);
+    return rc;
+}
+
+// ------------------------------------------------------------------ vectors
+int sd_vec_alloc(sd_model *m, int dtype, sd_vec **vec) {
+    SD_ARG(m && vec, "NULL argument");
+    *vec = nullptr;
+    SD_ARG(dtype == SD_F64 || dtype == SD_C128, "dtype must be SD_F64 or SD_C128");
+    sd_ctx *c = m->ctx;
+    SD_TRY(sd_use(c));
+    sd_vec *v = new (std::nothrow) sd_vec;
+    if (!v) return sd_fail(SD_ERR_NOMEM, "out of host memory");
+    v->model = m; v->dtype = dtype; v->nc = dtype == SD_C128 ? 2 : 1;
+    const uint64_t ls = m->shards.start[c->rank];
+    v->local_n = m->shards.start[c->rank + 1] - ls;
+    for (int g = 0; g < SD_MAX_WORLD; ++g) { v->peer[g] = nullptr; v->view.base[g] = nullptr; }
+    // +2 elements of slack so 16-byte vector accesses at the ends stay inside the allocation
+    const size_t bytes = (size_t)(v->local_n + 2) * v->nc * sizeof(double);
+    cudaError_t e = cudaMalloc(&v->d, bytes);
+    if (e != cudaSuccess) {
+        delete v;
+        return sd_fail(SD_ERR_NOMEM, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    }
+    v->view.base[c->rank] = v->d - (int64_t)ls * v->nc;
+    if (c->world > 1) {
+        // collective: exchange CUDA IPC handles, map every peer shard
+        cudaIpcMemHandle_t hnd;
+        SD_CUDA(cudaIpcGetMemHandle(&hnd, v->d));
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        SD_CUDA(cudaMemcpyAsync(c->d_ipc + (size_t)c->world * 64, &hnd, 64, cudaMemcpyHostToDevice, c->stream));
+        SD_NCCL(g_nccl.AllGather(c->d_ipc + (size_t)c->world * 64, c->d_ipc, 64, ncclUint8_, c->comm, c->stream));
+        std::vector<cudaIpcMemHandle_t> all(c->world);
+        SD_CUDA(cudaMemcpyAsync(all.data(), c->d_ipc, (size_t)c->world * 64, cudaMemcpyDeviceToHost, c->stream));
+        SD_CUDA(cudaStreamSynchronize(c->stream));
+        for (int g = 0; g < c->world; ++g) {
+            if (g == c->rank) continue;
+            void *p = nullptr;
+            SD_CUDA(cudaIpcOpenMemHandle(&p, all[g], cudaIpcMemLazyEnablePeerAccess));
+            v->peer[g] = p;
+            v->view.base[g] = (const double *)p - (int64_t)m->shards.start[g] * v->nc;
+        }
+    }
+    *vec = v;
+    return SD_OK;
+}
+int sd_vec_free(sd_vec *v) {
+    if (!v) return SD_OK;
+    sd_ctx *c = v->model->ctx;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (int g = 0; g < SD_MAX_WORLD; ++g)
+        if (v->peer[g]) cudaIpcCloseMemHandle(v->peer[g]);
+    if (c->world > 1) sd_rank_barrier(c), cudaStreamSynchronize(c->stream);   // peers unmapped before the free
+    if (v->owned) cudaFree(v->d);
+    delete v;
+    return SD_OK;
+}
+int sd_vec_dtype(const sd_vec *v, int *dtype) {
+    SD_ARG(v && dtype, "NULL argument");
+    *dtype = v->dtype;
+    return SD_OK;
+}
+int sd_vec_local_len(const sd_vec *v, uint64_t *n) {
+    SD_ARG(v && n, "NULL argument");
+    *n = v->local_n;
+    return SD_OK;
+}
+static inline size_t sd_vec_bytes(const sd_vec *v) { return (size_t)v->local_n * v->nc * sizeof(double); }
+
+int sd_vec_upload(sd_vec *v, const void *host) {
+    SD_ARG(v && host, "NULL argument");
+    sd_ctx *c = v->model->ctx;
+    SD_TRY(sd_use(c));
+    SD_CUDA(cudaMemcpyAsync(v->d, host, sd_vec_bytes(v), cudaMemcpyHostToDevice, c->stream));
+    SD_CUDA(cudaStreamSynchronize(c->stream));
+    return SD_OK;
+}
+int sd_vec_download(sd_vec *v, void *host) {
+    SD_ARG(v && host, "NULL argument");
+    sd_ctx *c = v->model->ctx;
+    SD_TRY(sd_use(c));
+    SD_CUDA(cudaMemcpyAsync(host, v->d, sd_vec_bytes(v), cudaMemcpyDeviceToHost, c->stream));
+    SD_CUDA(cudaStreamSynchronize(c->stream));
+    return SD_OK;
+}
+int sd_vec_upload_async(sd_vec *v, const void *host) {
+    SD_ARG(v && host, "NULL argument");
+    sd_ctx *c = v->model->ctx;
+    SD_TRY(sd_use(c));
+    SD_CUDA(cudaMemcpyAsync(v->d, host, sd_vec_bytes(v), cudaMemcpyHostToDevice, c->stream));
+    return SD_OK;
+}
+int sd_vec_download_async(sd_vec *v, void *host) {
+    SD_ARG(v && host, "NULL argument");
+    sd_ctx *c = v->model->ctx;
+    SD_TRY(sd_use(c));
+    SD_CUDA(cudaMemcpyAsync(host, v->d, sd_vec_bytes(v), cudaMemcpyDeviceToHost, c->stream));
+    return SD_OK;
+}
+int sd_host_alloc(void **p, uint64_t bytes) {
+    SD_ARG(p, "NULL argument");
+    SD_CUDA(cudaMallocHost(p, bytes ? bytes : 1));
+    return SD_OK;
+}
+int sd_host_free(void *p) {
+    if (p) SD_CUDA(cudaFreeHost(p));
+    return SD_OK;
+}
+int sd_vec_zero(sd_vec *v) {
+    SD_ARG(v, "NULL argument");
+    sd_ctx *c = v->model->ctx;
+    SD_TRY(sd_use(c));
+    SD_CUDA(cudaMemsetAsync(v->d, 0, sd_vec_bytes(v), c->stream));
+    return SD_OK;
+}
+int sd_vec_set_onehot(sd_vec *v, uint64_t idx0) {
+    SD_ARG(v, "NULL argument");
+    SD_ARG(idx0 < v->model->N, "index outside the basis");
+    sd_ctx *c = v->model->ctx;
+    SD_TRY(sd_vec_zero(v));
+    const uint64_t ls = v->model->shards.start[c->rank];
+    if (idx0 >= ls && idx0 < ls + v->local_n) {
+        sd_set_one_kernel<<<1, 1, 0, c->stream>>>(v->d, (idx0 - ls) * v->nc);
+        SD_TRY(sd_launch_check(c, "sd_set_one_kernel"));
+    }
+    return SD_OK;
+}
+int sd_vec_fill_seeded(sd_vec *v, uint64_t seed, double scale) {
+    SD_ARG(v, "NULL argument");
+    sd_ctx *c = v->model->ctx;
+    SD_TRY(sd_use(c));
+    if (v->local_n == 0) return SD_OK;
+    sd_fill_seeded_kernel<<<sd_blas_grid(c, v->local_n), SD_BLAS_THREADS, 0, c->stream>>>(
+        v->d, v->nc, v->model->shards.start[c->rank], v->local_n, seed, scale);
+    return sd_launch_check(c, "sd_fill_seeded_kernel");
+}
+int sd_vec_copy(sd_vec *dst, const sd_vec *src) {
+    SD_ARG(dst && src, "NULL argument");
+    SD_ARG(dst->model == src->model && dst->dtype == src->dtype, "vectors differ in model or dtype");
+    sd_ctx *c = dst->model->ctx;
+    SD_TRY(sd_use(c));
+    if (dst->d != src->d)
+        SD_CUDA(cudaMemcpyAsync(dst->d, src->d, sd_vec_bytes(dst), cudaMemcpyDeviceToDevice, c->stream));
+    return SD_OK;
+}
+int sd_vec_convert(sd_vec *dst, const sd_vec *src) {
+    SD_ARG(dst && src, "NULL argument");
+    SD_ARG(dst->model == src->model, "vectors belong to different models");
+    if (dst->dtype == src->dtype) return sd_vec_copy(dst, src);
+    sd_ctx *c = dst->model->ctx;
+    SD_TRY(sd_use(c));
+    if (dst->local_n == 0) return SD_OK;
+    sd_convert_kernel<<<sd_blas_grid(c, dst->local_n), SD_BLAS_THREADS, 0, c->stream>>>(dst->d, src->d, dst->local_n, src->nc);
+    return sd_launch_check(c, "sd_convert_kernel");
+}
+
+static SdScalar sd_host_scalar(double re, double im) {
+    SdScalar s; s.re = re; s.im = im; s.dev = nullptr; s.dev_mode = 0; return s;
+}
+static SdScalar sd_dev_scalar(const double *p, int mode) {
+    SdScalar s; s.re = 0; s.im = 0; s.dev = p; s.dev_mode = mode; return s;
+}
+
+static int sd_scale_impl(sd_vec *x, SdScalar s) {
+    sd_ctx *c = x->model->ctx;
+    if (x->local_n == 0) return SD_OK;
+    const unsigned g = sd_blas_grid(c, x->local_n);
+    if (x->nc == 2) sd_scale_kernel<2><<<g, SD_BLAS_THREADS, 0, c->stream>>>(x->d, x->local_n, s);
+    else sd_scale_kernel<1><<<g, SD_BLAS_THREADS, 0, c->stream>>>(x->d, x->local_n, s);
+    return sd_launch_check(c, "sd_scale_kernel");
+}
+int sd_vec_scale(sd_vec *x, sd_complex s) {
+    SD_ARG(x, "NULL argument");
+    SD_ARG(x->nc == 2 || s.im == 0.0, "complex scale of a real vector (InexactError)");
+    SD_TRY(sd_use(x->model->ctx));
+    return sd_scale_impl(x, sd_host_scalar(s.re, s.im));
+}
+// y = x / s (s real; device or host scalar)
+static int sd_divide_impl(sd_vec *y, const sd_vec *x, SdScalar s) {
+    sd_ctx *c = y->model->ctx;
+    if (y->local_n == 0) return SD_OK;
+    const unsigned g = sd_blas_grid(c, y->local_n * y->nc);
+    if (y->nc == 2) sd_divide_kernel<2><<<g, SD_BLAS_THREADS, 0, c->stream>>>(y->d, x->d, y->local_n, s);
+    else sd_divide_kernel<1><<<g, SD_BLAS_THREADS, 0, c->stream>>>(y->d, x->d, y->local_n, s);
+    return sd_launch_check(c, "sd_divide_kernel");
+}
+// y += a x [+ b z]; if slot_out >= 0: ||y||^2 -> d_scal[slot_out+3]
+static int sd_axpy_impl(sd_vec *y, SdScalar a, const sd_vec *x, SdScalar b, const sd_vec *z, int slot_out) {
+    sd_ctx *c = y->model->ctx;
+    const unsigned g = sd_blas_grid(c, y->local_n);
+    double *partials = nullptr;
+    if (slot_out >= 0) { SD_TRY(sd_partials_reserve(c, (size_t)SD_NSLOT * g)); partials = c->d_partials; }
+    if (y->nc == 2)
+        sd_axpy_kernel<2><<<g, SD_BLAS_THREADS, 0, c->stream>>>(y->d, y->local_n, a, x->d, b, z ? z->d : nullptr, partials, g);
+    else
+        sd_axpy_kernel<1><<<g, SD_BLAS_THREADS, 0, c->stream>>>(y->d, y->local_n, a, x->d, b, z ? z->d : nullptr, partials, g);
+    SD_TRY(sd_launch_check(c, "sd_axpy_kernel"));
+    if (slot_out >= 0) SD_TRY(sd_finish_reduce(c, g, 8, slot_out));
+    return SD_OK;
+}
+int sd_vec_axpy(sd_vec *y, sd_complex a, const sd_vec *x) {
+    SD_ARG(y && x, "NULL argument");
+    SD_ARG(y->model == x->model && y->dtype == x->dtype, "vectors differ in model or dtype");
+    SD_ARG(y->nc == 2 || a.im == 0.0, "complex axpy into a real vector (InexactError)");
+    SD_TRY(sd_use(y->model->ctx));
+    return sd_axpy_impl(y, sd_host_scalar(a.re, a.im), x, sd_host_scalar(0, 0), nullptr, -1);
+}
+// dot -> d_scal[slot_out + 0,1]
+static int sd_dot_impl(const sd_vec *x, const sd_vec *y, int conj, int slot_out) {
+    sd_ctx *c = x->model->ctx;
+    const unsigned g = sd_blas_grid(c, x->local_n);
+    SD_TRY(sd_partials_reserve(c, (size_t)SD_NSLOT * g));
+    if (x->nc == 2) sd_dot_kernel<2><<<g, SD_BLAS_THREADS, 0, c->stream>>>(x->d, y->d, x->local_n, conj, c->d_partials, g);
+    else sd_dot_kernel<1><<<g, SD_BLAS_THREADS, 0, c->stream>>>(x->d, y->d, x->local_n, conj, c->d_partials, g);
+    SD_TRY(sd_launch_check(c, "sd_dot_kernel"));
+    return sd_finish_reduce(c, g, 3, slot_out);
+}
+int sd_vec_dot(const sd_vec *x, const sd_vec *y, sd_complex *result) {
+    SD_ARG(x && y && result, "NULL argument");
+    SD_ARG(x->model == y->model && x->dtype == y->dtype, "vectors differ in model or dtype");
+    sd_ctx *c = x->model->ctx;
+    SD_TRY(sd_use(c));
+    SD_TRY(sd_dot_impl(x, y, 1, 0));
+    double r[2];
+    SD_TRY(sd_fetch(c, 0, 2, r));
+    result->re = r[0]; result->im = r[1];
+    return SD_OK;
+}
+int sd_vec_dotu(const sd_vec *x, const sd_vec *y, sd_complex *result) {
+    SD_ARG(x && y && result, "NULL argument");
+    SD_ARG(x->model == y->model && x->dtype == y->dtype, "vectors differ in model or dtype");
+    sd_ctx *c = x->model->ctx;
+    SD_TRY(sd_use(c));
+    SD_TRY(sd_dot_impl(x, y, 0, 0));
+    double r[2];
+    SD_TRY(sd_fetch(c, 0, 2, r));
+    result->re = r[0]; result->im = r[1];
+    return SD_OK;
+}
+int sd_vec_norm(const sd_vec *x, double *result) {
+    SD_ARG(x && result, "NULL argument");
+    sd_ctx *c = x->model->ctx;
+    SD_TRY(sd_use(c));
+    SD_TRY(sd_dot_impl(x, x, 1, 0));
+    double r[2];
+    SD_TRY(sd_fetch(c, 0, 2, r));
+    *result = sqrt(r[0]);
+    return SD_OK;
+}
+
+// ----------------------------------------------------------------- operator
+// Launches one apply kernel with the given epilogue; reductions (if any) land
+// in d_scal[slot_out .. slot_out+3].
+static int sd_apply_impl(sd_model *m, sd_vec *out, const sd_vec *psi, SdEpi epi, int slot_out) {
+    sd_ctx *c = m->ctx;
+    SD_ARG(out && psi, "NULL argument");
+    SD_ARG(out->model == m && psi->model == m, "vector does not belong to this model");
+    SD_ARG(out->dtype == psi->dtype, "out and psi differ in element type");
+    SD_ARG(out->d != psi->d, "out must not alias psi");
+    SD_TRY(sd_use(c));
+    SD_TRY(sd_rank_barrier(c));
+    const int nc = psi->nc;
+    const int slotmask = sd_epi_slotmask(epi.red);
+    if (m->path == SD_PATH_TILED) {
+        SdTileDev &t = m->tile[nc - 1];
+        SdTileParams P = t.host.P;
+        P.shards = m->shards;
+        P.key_lo = t.keys[c->rank];
+        P.key_hi = t.keys[c->rank + 1];
+        const uint64_t nkeys = P.key_hi - P.key_lo;
+        if (nkeys == 0) return SD_OK;
+        SD_ARG(nkeys < 0x7fffffffULL, "too many tiles for one launch");
+        if (slotmask) SD_TRY(sd_partials_reserve(c, (size_t)SD_NSLOT * nkeys));
+        epi.partials = c->d_partials;
+        epi.nparts = (unsigned)nkeys;
+        double *out_vbase = out->d - (int64_t)m->shards.start[c->rank] * nc;
+        const int T = m->tile_T[nc - 1];
+#define SD_LAUNCH_TILE(NC_, T_)                                                                             \
+    do {                                                                                                    \
+        static size_t set_smem = 0;                                                                         \
+        if (t.smem > set_smem) {                                                                            \
+            SD_CUDA(cudaFuncSetAttribute(sd_tile_apply_kernel<NC_, T_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem)); \
+            set_smem = t.smem;                                                                              \
+        }                                                                                                   \
+        sd_tile_apply_kernel<NC_, T_><<<(unsigned)nkeys, SD_TILE_THREADS, t.smem, c->stream>>>(P, psi->view, out_vbase, epi, t.cap); \
+    } while (0)
+        if (nc == 1 && T == 5) SD_LAUNCH_TILE(1, 5);
+        else if (nc == 2 && T == 4) SD_LAUNCH_TILE(2, 4);
+        else if (nc == 1 && T == 4) SD_LAUNCH_TILE(1, 4);
+        else if (nc == 1 && T == 6) SD_LAUNCH_TILE(1, 6);
+        else if (nc == 2 && T == 3) SD_LAUNCH_TILE(2, 3);
+        else if (nc == 2 && T == 5) SD_LAUNCH_TILE(2, 5);
+        else return sd_fail(SD_ERR_UNSUPPORTED, "tail size %d not compiled", T);
+#undef SD_LAUNCH_TILE
+        SD_TRY(sd_launch_check(c, "sd_tile_apply_kernel"));
+        if (slotmask) SD_TRY(sd_finish_reduce(c, (unsigned)nkeys, slotmask, slot_out));
+    } else {
+        SdGenericParams G;
+        G.L = m->L; G.k = m->k; G.nhop = (int)m->hop_a.size(); G.nzz = (int)m->zz_a.size(); G.N = m->N;
+        G.hop_a = m->d_hop_a; G.hop_b = m->d_hop_b; G.hop_J = m->d_hop_J;
+        G.zz_a = m->d_zz_a; G.zz_b = m->d_zz_b; G.zz_J = m->d_zz_J; G.field = m->d_field;
+        G.binom = c->d_binom; G.lin_h = m->lin_h; G.linA = m->d_linA; G.linB = m->d_linB;
+        G.shards = m->shards;
+        uint64_t g64 = (psi->local_n + SD_GEN_THREADS - 1) / SD_GEN_THREADS;
+        g64 = std::max<uint64_t>(1, std::min<uint64_t>(g64, (uint64_t)c->sm_count * 16));
+        const unsigned g = (unsigned)g64;
+        if (slotmask) SD_TRY(sd_partials_reserve(c, (size_t)SD_NSLOT * g));
+        epi.partials = c->d_partials;
+        epi.nparts = g;
+        if (nc == 2) sd_generic_apply_kernel<2><<<g, SD_GEN_THREADS, 0, c->stream>>>(G, psi->view, out->d, epi);
+        else sd_generic_apply_kernel<1><<<g, SD_GEN_THREADS, 0, c->stream>>>(G, psi->view, out->d, epi);
+        SD_TRY(sd_launch_check(c, "sd_generic_apply_kernel"));
+        if (slotmask) SD_TRY(sd_finish_reduce(c, g, slotmask, slot_out));
+    }
+    return SD_OK;
+}
+static SdEpi sd_epi_plain(double hscale) {
+    SdEpi e;
+    memset(&e, 0, sizeof(e));
+    e.mode = SD_EPI_PLAIN; e.hscale = hscale; e.a = 1.0; e.b = 0.0;
+    return e;
+}
+
+int sd_apply_H(sd_model *m, sd_vec *out, const sd_vec *psi) {
+    SD_ARG(m, "NULL argument");
+    return sd_apply_impl(m, out, psi, sd_epi_plain(1.0), 0);
+}
+int sd_apply_H_dot(sd_model *m, sd_vec *out, const sd_vec *psi, sd_complex *dot) {
+    SD_ARG(m && dot, "NULL argument");
+    SdEpi e = sd_epi_plain(1.0);
+    e.red = SD_RED_DOT_SELF;
+    SD_TRY(sd_apply_impl(m, out, psi, e, 0));
+    double r[2];
+    SD_TRY(sd_fetch(m->ctx, 0, 2, r));
+    dot->re = r[0]; dot->im = r[1];
+    return SD_OK;
+}
+int sd_apply_rescaled_H(sd_model *m, sd_vec *out, const sd_vec *psi, double a, double b) {
+    SD_ARG(m, "NULL argument");
+    SdEpi e = sd_epi_plain(1.0);
+    e.mode = SD_EPI_RESCALED; e.a = a; e.b = b;
+    return sd_apply_impl(m, out, psi, e, 0);
+}
+static int sd_cheb_step_impl(sd_model *m, sd_vec *vnext, const sd_vec *v, const sd_vec *vprev, double a, double b,
+                             const sd_vec *phi, sd_vec *acc, sd_complex ck, int slot_out) {
+    SD_ARG(vnext && v && vprev, "NULL argument");
+    SD_ARG(vprev->model == m && vprev->dtype == v->dtype, "vprev mismatch");
+    SdEpi e = sd_epi_plain(1.0);
+    e.mode = SD_EPI_CHEB; e.a = a; e.b = b; e.vprev = vprev->d;
+    if (phi) {
+        SD_ARG(phi->model == m && phi->dtype == v->dtype, "phi mismatch");
+        e.red = SD_RED_DOT_PHI | SD_RED_NORM2; e.phi = phi->d;
+    }
+    if (acc) {
+        SD_ARG(acc->model == m && acc->dtype == v->dtype, "acc mismatch");
+        SD_ARG(acc->nc == 2 || ck.im == 0.0, "complex coefficient into a real accumulator (InexactError)");
+        SD_ARG(acc->d != vnext->d && acc->d != v->d, "acc must not alias vnext or v");
+        e.acc = acc->d; e.ck_re = ck.re; e.ck_im = ck.im;
+    }
+    return sd_apply_impl(m, vnext, v, e, slot_out);
+}
+int sd_cheb_step(sd_model *m, sd_vec *vnext, const sd_vec *v, const sd_vec *vprev, double a, double b,
+                 const sd_vec *phi, double *mu, double *norm2, sd_vec *acc, sd_complex ck) {
+    SD_ARG(m, "NULL argument");
+    SD_TRY(sd_cheb_step_impl(m, vnext, v, vprev, a, b, phi, acc, ck, 0));
+    if (phi && (mu || norm2)) {
+        double r[4];
+        SD_TRY(sd_fetch(m->ctx, 0, 4, r));
+        if (mu) *mu = r[2];
+        if (norm2) *norm2 = r[3];
+    }
+    return SD_OK;
+}
+int sd_szq(sd_model *m, sd_vec *phi, const sd_vec *psi0, double q, double *norm2) {
+    SD_ARG(m && phi && psi0, "NULL argument");
+    SD_ARG(phi->model == m && psi0->model == m, "vector does not belong to this model");
+    SD_ARG(phi->dtype == SD_C128, "phi must be SD_C128");
+    SD_ARG(phi->d != psi0->d, "phi must not alias psi0");
+    sd_ctx *c = m->ctx;
+    SD_TRY(sd_use(c));
+    SdSzqParams Z;
+    Z.L = m->L; Z.k = m->k; Z.normfact = 1.0 / sqrt((double)m->L); Z.binom = c->d_binom;
+    for (int r = 0; r < m->L; ++r) { Z.ph_re[r] = cos(q * (double)r); Z.ph_im[r] = sin(q * (double)r); }
+    const unsigned g = sd_blas_grid(c, phi->local_n);
+    double *partials = nullptr;
+    if (norm2) { SD_TRY(sd_partials_reserve(c, (size_t)SD_NSLOT * g)); partials = c->d_partials; }
+    const uint64_t ls = m->shards.start[c->rank];
+    if (psi0->nc == 2) sd_szq_kernel<2><<<g, SD_BLAS_THREADS, 0, c->stream>>>(Z, ls, phi->local_n, psi0->d, phi->d, partials, g);
+    else sd_szq_kernel<1><<<g, SD_BLAS_THREADS, 0, c->stream>>>(Z, ls, phi->local_n, psi0->d, phi->d, partials, g);
+    SD_TRY(sd_launch_check(c, "sd_szq_kernel"));
+    if (norm2) {
+        SD_TRY(sd_finish_reduce(c, g, 8, 0));
+        double r[4];
+        SD_TRY(sd_fetch(c, 0, 4, r));
+        *norm2 = r[3];
+    }
+    return SD_OK;
+}
+int sd_apply_H_host(sd_model *m, int dtype, void *out, const void *psi) {
+    SD_ARG(m && out && psi, "NULL argument");
+    SD_ARG(m->ctx->world == 1, "sd_apply_H_host needs a single-rank context");
+    SD_ARG(out != psi, "out must not alias psi");
+    sd_vec *vi = nullptr, *vo = nullptr;
+    int rc = sd_vec_alloc(m, dtype, &vi);
+    if (rc == SD_OK) rc = sd_vec_alloc(m, dtype, &vo);
+    if (rc == SD_OK) rc = sd_vec_upload_async(vi, psi);
+    if (rc == SD_OK) rc = sd_apply_H(m, vo, vi);
+    if (rc == SD_OK) rc = sd_vec_download(vo, out);
+    sd_vec_free(vi); sd_vec_free(vo);
+    return rc;
+}
+
+// -------------------------------------------------------------- recurrences
+int sd_vecset_free(sd_vecset *s) {
+    if (!s) return SD_OK;
+    for (sd_vec *v : s->v) sd_vec_free(v);
+    delete s;
+    return SD_OK;
+}
+int sd_vecset_size(const sd_vecset *s, int *m) {
+    SD_ARG(s && m, "NULL argument");
+    *m = (int)s->v.size();
+    return SD_OK;
+}
+int sd_vecset_get(sd_vecset *s, int k, sd_vec **vec) {
+    SD_ARG(s && vec, "NULL argument");
+    SD_ARG(k >= 0 && k < (int)s->v.size(), "index outside the vector set");
+    *vec = s->v[k];
+    return SD_OK;
+}
+int sd_lincomb(sd_vecset *s, const sd_complex *y, int mcount, sd_vec *out, double *norm2) {
+    SD_ARG(s && y && out, "NULL argument");
+    SD_ARG(mcount >= 1 && mcount <= (int)s->v.size(), "m outside the vector set");
+    sd_vec *v0 = s->v[0];
+    sd_model *m = v0->model;
+    SD_ARG(out->model == m, "out belongs to a different model");
+    SD_ARG(out->nc >= v0->nc, "cannot combine complex vectors into a real output");
+    for (int j = 0; j < mcount; ++j) {
+        SD_ARG(s->v[j]->d != out->d, "out aliases a member of the set");
+        if (out->nc == 1) SD_ARG(y[j].im == 0.0, "complex coefficient into a real output (InexactError)");
+    }
+    sd_ctx *c = m->ctx;
+    SD_TRY(sd_use(c));
+    SD_ARG(2 * mcount <= 2048, "too many vectors");
+    // coefficients -> device (pinned staging, ordered on the stream)
+    SD_CUDA(cudaStreamSynchronize(c->stream));
+    for (int j = 0; j < mcount; ++j) { c->h_scal[1024 + 2 * j] = y[j].re; c->h_scal[1024 + 2 * j + 1] = y[j].im; }
+    SD_CUDA(cudaMemcpyAsync(c->d_scal + 1024, c->h_scal + 1024, 2 * mcount * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    const unsigned g = sd_blas_grid(c, out->local_n);
+    SD_TRY(sd_partials_reserve(c, (size_t)SD_NSLOT * g));
+    for (int j0 = 0; j0 < mcount; j0 += SD_BDOT_MAX) {
+        const int nb = std::min(SD_BDOT_MAX, mcount - j0);
+        SdPtrBlock pb;
+        for (int j = 0; j < SD_BDOT_MAX; ++j) pb.v[j] = (j < nb) ? s->v[j0 + j]->d : nullptr;
+        const bool last = j0 + nb >= mcount;
+        double *partials = last ? c->d_partials : nullptr;
+        const double *yd = c->d_scal + 1024 + 2 * j0;
+        if (out->nc == 2 && v0->nc == 2)
+            sd_lincomb_kernel<2><<<g, SD_BLAS_THREADS, 0, c->stream>>>(out->d, out->local_n, pb, nb, yd, j0 > 0, partials, g);
+        else if (out->nc == 1)
+            sd_lincomb_kernel<1><<<g, SD_BLAS_THREADS, 0, c->stream>>>(out->d, out->local_n, pb, nb, yd, j0 > 0, partials, g);
+        else
+            sd_lincomb_r2c_kernel<<<g, SD_BLAS_THREADS, 0, c->stream>>>(out->d, out->local_n, pb, nb, yd, j0 > 0, partials, g);
+        SD_TRY(sd_launch_check(c, "sd_lincomb_kernel"));
+    }
+    SD_TRY(sd_finish_reduce(c, g, 8, 0));
+    if (norm2) {
+        double r[4];
+        SD_TRY(sd_fetch(c, 0, 4, r));
+        *norm2 = r[3];
+    }
+    return SD_OK;
+}
+
+struct SdVecGuard {          // frees temporaries on every exit path
+    std::vector<sd_vec *> v;
+    ~SdVecGuard() { for (sd_vec *p : v) sd_vec_free(p); }
+    int make(sd_model *m, int dtype, sd_vec **out) {
+        int rc = sd_vec_alloc(m, dtype, out);
+        if (rc == SD_OK) v.push_back(*out);
+        return rc;
+    }
+    void release(sd_vec *p) { v.erase(std::remove(v.begin(), v.end(), p), v.end()); }
+};
+
+// v <- v0 / ||v0||; returns the norm
+static int sd_normalised_copy(sd_vec *dst, const sd_vec *src, double *norm_out) {
+    sd_ctx *c = dst->model->ctx;
+    SD_TRY(sd_dot_impl(src, src, 1, 0));
+    double r[2];
+    SD_TRY(sd_fetch(c, 0, 2, r));
+    const double nrm = sqrt(r[0]);
+    if (norm_out) *norm_out = nrm;
+    if (nrm == 0.0) return SD_OK;
+    return sd_divide_impl(dst, src, sd_host_scalar(nrm, 0));
+}
+
+int sd_lanczos_extremal(sd_model *m, const sd_vec *v0, int lanc_m, double tol, int negate,
+                        double *alpha, double *beta, int *m_eff) {
+    SD_ARG(m && v0 && alpha && beta && m_eff, "NULL argument");
+    SD_ARG(v0->model == m && v0->dtype == SD_C128, "v0 must be an SD_C128 vector of this model");
+    SD_ARG(lanc_m >= 1, "lanc_m must be >= 1");
+    sd_ctx *c = m->ctx;
+    SD_TRY(sd_use(c));
+    const int mm = (int)std::min<uint64_t>((uint64_t)lanc_m, m->N);          // Lanczos.jl:36
+    SdVecGuard G;
+    sd_vec *vp, *vc, *w;
+    SD_TRY(G.make(m, SD_C128, &vp)); SD_TRY(G.make(m, SD_C128, &vc)); SD_TRY(G.make(m, SD_C128, &w));
+    double n0;
+    SD_TRY(sd_normalised_copy(vp, v0, &n0));                                // :39-40
+    if (n0 == 0.0) return sd_fail(SD_ERR_ZERO_NORM, "starting vector has zero norm");
+    int count = 0;
+    for (int j = 1; j <= mm; ++j) {
+        SdEpi e = sd_epi_plain(negate ? -1.0 : 1.0);
+        e.red = SD_RED_DOT_SELF;
+        SD_TRY(sd_apply_impl(m, w, vp, e, 0));                              // :49-50  alpha = Re dot(v, w)
+        // w -= alpha v [+ beta v_old]                                        :53-60
+        SdScalar sa = sd_dev_scalar(c->d_scal + 0, 4);
+        if (j == 1) SD_TRY(sd_axpy_impl(w, sa, vp, sd_host_scalar(0, 0), nullptr, 4));
+        else SD_TRY(sd_axpy_impl(w, sa, vp, sd_host_scalar(-beta[j - 2], 0), vc, 4));
+        double r[8];
+        SD_TRY(sd_fetch(c, 0, 8, r));
+        alpha[j - 1] = r[0];
+        count = j;
+        if (j < mm) {
+            beta[j - 1] = sqrt(r[7]);                                       // :63
+            if (beta[j - 1] < tol) break;                                   // :65-69
+            std::swap(vp, vc);                                              // :71 roles rotate
+            SD_TRY(sd_divide_impl(vp, w, sd_host_scalar(beta[j - 1], 0)));
+        }
+    }
+    *m_eff = count;
+    return SD_OK;
+}
+
+int sd_lanczos_tridiag(sd_model *m, const sd_vec *v, int lanc_m, double tol, double *alpha, double *beta,
+                       int *m_eff, double *normv) {
+    SD_ARG(m && v && alpha && beta && m_eff && normv, "NULL argument");
+    SD_ARG(v->model == m && v->dtype == SD_C128, "v must be an SD_C128 vector of this model");
+    SD_ARG(lanc_m >= 1, "lanc_m must be >= 1");
+    sd_ctx *c = m->ctx;
+    SD_TRY(sd_use(c));
+    const int mm = (int)std::min<uint64_t>((uint64_t)lanc_m, m->N);          // Lanczos.jl:200
+    SdVecGuard G;
+    sd_vec *vj, *vo, *w;
+    SD_TRY(G.make(m, SD_C128, &vj)); SD_TRY(G.make(m, SD_C128, &vo)); SD_TRY(G.make(m, SD_C128, &w));
+    SD_TRY(sd_normalised_copy(vj, v, normv));                               // :209-213
+    if (*normv == 0.0) return sd_fail(SD_ERR_ZERO_NORM, "starting vector has zero norm");
+    int eff = mm;
+    for (int j = 1; j < mm; ++j) {                                          // :216-235
+        SdEpi e = sd_epi_plain(1.0);
+        e.red = SD_RED_DOT_SELF;
+        SD_TRY(sd_apply_impl(m, w, vj, e, 0));
+        SdScalar sa = sd_dev_scalar(c->d_scal + 0, 4);
+        if (j == 1) SD_TRY(sd_axpy_impl(w, sa, vj, sd_host_scalar(0, 0), nullptr, 4));
+        else SD_TRY(sd_axpy_impl(w, sa, vj, sd_host_scalar(-beta[j - 2], 0), vo, 4));
+        double r[8];
+        SD_TRY(sd_fetch(c, 0, 8, r));
+        alpha[j - 1] = r[0];
+        beta[j - 1] = sqrt(r[7]);
+        if (beta[j - 1] < tol) { eff = j; break; }                          // :228-231
+        std::swap(vj, vo);
+        SD_TRY(sd_divide_impl(vj, w, sd_host_scalar(beta[j - 1], 0)));
+    }
+    if (eff == mm) {                                                        // :237-239
+        SdEpi e = sd_epi_plain(1.0);
+        e.red = SD_RED_DOT_SELF;
+        SD_TRY(sd_apply_impl(m, w, vj, e, 0));
+        double r[2];
+        SD_TRY(sd_fetch(c, 0, 2, r));
+        alpha[mm - 1] = r[0];
+    }
+    *m_eff = eff;
+    return SD_OK;
+}
+
+int sd_lanczos_groundstate(sd_model *m, const sd_vec *v0, int lanc_m, double tol, double orth_tol,
+                           double *alpha, double *beta, int *m_actual, sd_vecset **Vout) {
+    SD_ARG(m && v0 && alpha && beta && m_actual && Vout, "NULL argument");
+    *Vout = nullptr;
+    SD_ARG(v0->model == m && v0->dtype == SD_F64, "v0 must be an SD_F64 vector of this model");
+    SD_ARG(lanc_m >= 1, "lanc_m must be >= 1");
+    sd_ctx *c = m->ctx;
+    SD_TRY(sd_use(c));
+    const int mm = (int)std::min<uint64_t>((uint64_t)lanc_m, m->N);          // Lanczos.jl:97
+    sd_vecset *S = new (std::nothrow) sd_vecset;
+    if (!S) return sd_fail(SD_ERR_NOMEM, "out of host memory");
+    struct SetGuard { sd_vecset *s; ~SetGuard() { if (s) sd_vecset_free(s); } } sg{S};
+    SdVecGuard G;
+    sd_vec *w;
+    SD_TRY(G.make(m, SD_F64, &w));
+    {
+        sd_vec *v1;
+        SD_TRY(sd_vec_alloc(m, SD_F64, &v1));
+        S->v.push_back(v1);
+        double n0;
+        SD_TRY(sd_normalised_copy(v1, v0, &n0));                            // :99-100
+        if (n0 == 0.0) return sd_fail(SD_ERR_ZERO_NORM, "starting vector has zero norm");
+    }
+    int mact = mm;
+    for (int j = 1; j <= mm; ++j) {
+        sd_vec *vj = S->v[j - 1];
+        SD_TRY(sd_apply_impl(m, w, vj, sd_epi_plain(1.0), 0));              // :113
+        for (int k = 1; k < j; ++k) {                                       // :116-122 sequential MGS
+            SD_TRY(sd_dot_impl(S->v[k - 1], w, 1, 8));
+            SD_TRY(sd_axpy_impl(w, sd_dev_scalar(c->d_scal + 8, 4), S->v[k - 1], sd_host_scalar(0, 0), nullptr, -1));
+        }
+        SD_TRY(sd_dot_impl(vj, w, 1, 8));                                   // :124
+        SdScalar sa = sd_dev_scalar(c->d_scal + 8, 4);
+        if (j == 1) SD_TRY(sd_axpy_impl(w, sa, vj, sd_host_scalar(0, 0), nullptr, 12));
+        else SD_TRY(sd_axpy_impl(w, sa, vj, sd_host_scalar(-beta[j - 2], 0), S->v[j - 2], 12));   // :126-130
+        double r[8];
+        SD_TRY(sd_fetch(c, 8, 8, r));
+        alpha[j - 1] = r[0];
+        if (j < mm) {
+            beta[j - 1] = sqrt(r[7]);                                       // :133
+            if (beta[j - 1] < tol) { mact = j; break; }                     // :136-139
+            for (int k = 1; k <= j; ++k) {                                  // :142-153 check pass
+                SD_TRY(sd_dot_impl(S->v[k - 1], w, 1, 8));
+                double d[2];
+                SD_TRY(sd_fetch(c, 8, 2, d));
+                if (fabs(d[0]) / beta[j - 1] > orth_tol) {
+                    SD_TRY(sd_axpy_impl(w, sd_host_scalar(-d[0], 0), S->v[k - 1], sd_host_scalar(0, 0), nullptr, 12));
+                    double nn[4];
+                    SD_TRY(sd_fetch(c, 12, 4, nn));
+                    beta[j - 1] = sqrt(nn[3]);
+                    if (beta[j - 1] < tol) { mact = j; break; }
+                }
+            }
+            sd_vec *vn;
+            SD_TRY(sd_vec_alloc(m, SD_F64, &vn));
+            S->v.push_back(vn);
+            SD_TRY(sd_divide_impl(vn, w, sd_host_scalar(beta[j - 1], 0)));    // :155
+        }
+    }
+    *m_actual = mact;
+    *Vout = S;
+    sg.s = nullptr;
+    return SD_OK;
+}
+
+int sd_kpm_moments(sd_model *m, const sd_vec *phi, int M, double a, double b, double *mu) {
+    SD_ARG(m && phi && mu, "NULL argument");
+    SD_ARG(phi->model == m && phi->dtype == SD_C128, "phi must be an SD_C128 vector of this model");
+    SD_ARG(M >= 1, "M must be >= 1");
+    sd_ctx *c = m->ctx;
+    SD_TRY(sd_use(c));
+    SdVecGuard G;
+    sd_vec *vp, *vc;
+    SD_TRY(G.make(m, SD_C128, &vp)); SD_TRY(G.make(m, SD_C128, &vc));
+    for (int i = 0; i < M; ++i) mu[i] = 0.0;
+    SD_TRY(sd_vec_copy(vp, phi));                                           // KPM_Sqw.jl:100
+    SD_TRY(sd_dot_impl(phi, vp, 1, 0));                                     // :104
+    double r[4];
+    SD_TRY(sd_fetch(c, 0, 2, r));
+    mu[0] = r[0];
+    if (M == 1) return SD_OK;
+    {                                                                       // :106-107
+        SdEpi e = sd_epi_plain(1.0);
+        e.mode = SD_EPI_RESCALED; e.a = a; e.b = b;
+        e.red = SD_RED_DOT_PHI; e.phi = phi->d;
+        SD_TRY(sd_apply_impl(m, vc, vp, e, 0));
+        SD_TRY(sd_fetch(c, 0, 4, r));
+        mu[1] = r[2];
+    }
+    for (int n = 2; n < M; ++n) {                                           // :109-126
+        sd_complex zero = {0, 0};
+        SD_TRY(sd_cheb_step_impl(m, vp, vc, vp, a, b, phi, nullptr, zero, 0));   // v_next overwrites v_prev
+        SD_TRY(sd_fetch(c, 0, 4, r));
+        mu[n] = r[2];
+        const double nv = sqrt(r[3]);
+        if (nv > 1e3) SD_TRY(sd_divide_impl(vp, vp, sd_host_scalar(nv, 0)));   // :118-121
+        std::swap(vp, vc);
+    }
+    return SD_OK;
+}
+
+int sd_krylov_basis(sd_model *m, const sd_vec *psi0, int kry_m, sd_complex *alpha, double *beta, int *m_eff,
+                    double *norm0, sd_vecset **Vout) {
+    SD_ARG(m && psi0 && alpha && beta && m_eff && norm0 && Vout, "NULL argument");
+    *Vout = nullptr;
+    SD_ARG(psi0->model == m, "psi0 belongs to a different model");
+    SD_ARG(kry_m >= 1, "kry_m must be >= 1");
+    sd_ctx *c = m->ctx;
+    SD_TRY(sd_use(c));
+    const int dt = psi0->dtype;
+    sd_vecset *S = new (std::nothrow) sd_vecset;
+    if (!S) return sd_fail(SD_ERR_NOMEM, "out of host memory");
+    struct SetGuard { sd_vecset *s; ~SetGuard() { if (s) sd_vecset_free(s); } } sg{S};
+    SdVecGuard G;
+    sd_vec *w;
+    SD_TRY(G.make(m, dt, &w));
+    sd_vec *v1;
+    SD_TRY(sd_vec_alloc(m, dt, &v1));
+    S->v.push_back(v1);
+    SD_TRY(sd_normalised_copy(v1, psi0, norm0));                            // Krylov.jl:147-150
+    int eff = kry_m;
+    if (*norm0 == 0.0) { *m_eff = 0; *Vout = S; sg.s = nullptr; return SD_OK; }
+    for (int j = 1; j <= kry_m; ++j) {                                      // :153-172
+        sd_vec *vj = S->v[j - 1];
+        SdEpi e = sd_epi_plain(1.0);
+        e.red = SD_RED_DOT_SELF;
+        SD_TRY(sd_apply_impl(m, w, vj, e, 0));                              // alpha_j = dot(V_j, w), complex
+        SdScalar sa = sd_dev_scalar(c->d_scal + 0, 3);
+        if (j == 1) SD_TRY(sd_axpy_impl(w, sa, vj, sd_host_scalar(0, 0), nullptr, 4));
+        else SD_TRY(sd_axpy_impl(w, sa, vj, sd_host_scalar(-beta[j - 2], 0), S->v[j - 2], 4));
+        double r[8];
+        SD_TRY(sd_fetch(c, 0, 8, r));
+        alpha[j - 1].re = r[0]; alpha[j - 1].im = r[1];
+        if (j < kry_m) {
+            beta[j - 1] = sqrt(r[7]);
+            if (fabs(beta[j - 1]) < 1e-14) { eff = j; break; }              // :163-168
+            sd_vec *vn;
+            SD_TRY(sd_vec_alloc(m, dt, &vn));
+            S->v.push_back(vn);
+            SD_TRY(sd_divide_impl(vn, w, sd_host_scalar(beta[j - 1], 0)));
+        }
+    }
+    *m_eff = eff;
+    *Vout = S;
+    sg.s = nullptr;
+    return SD_OK;
+}
+
+int sd_chebyshev_evolve(sd_model *m, const sd_vec *psi0, const sd_complex *cf, int n, double a, double b,
+                        sd_vec *out) {
+    SD_ARG(m && psi0 && cf && out, "NULL argument");
+    SD_ARG(psi0->model == m && out->model == m, "vector belongs to a different model");
+    SD_ARG(psi0->dtype == SD_C128 && out->dtype == SD_C128, "psi0 and out must be SD_C128 (InexactError otherwise)");
+    SD_ARG(n >= 1, "cheb_n must be >= 1");
+    SD_ARG(out->d != psi0->d, "out must not alias psi0");
+    sd_ctx *c = m->ctx;
+    SD_TRY(sd_use(c));
+    SdVecGuard G;
+    sd_vec *vp, *vc;
+    SD_TRY(G.make(m, SD_C128, &vp)); SD_TRY(G.make(m, SD_C128, &vc));
+    SD_TRY(sd_vec_copy(vp, psi0));                                          // Chebyshev.jl:95
+    SD_TRY(sd_apply_rescaled_H(m, vc, vp, a, b));                           // :98
+    SD_TRY(sd_vec_zero(out));                                               // :100-107
+    SD_TRY(sd_axpy_impl(out, sd_host_scalar(cf[0].re, cf[0].im), vp, sd_host_scalar(0, 0), nullptr, -1));
+    if (n >= 2) SD_TRY(sd_axpy_impl(out, sd_host_scalar(cf[1].re, cf[1].im), vc, sd_host_scalar(0, 0), nullptr, -1));
+    for (int k = 2; k < n; ++k) {                                           // :110-121
+        SD_TRY(sd_cheb_step_impl(m, vp, vc, vp, a, b, nullptr, out, cf[k], 0));
+        std::swap(vp, vc);
+    }
+    SD_CUDA(cudaStreamSynchronize(c->stream));
+    return SD_OK;
+}
+

@@ -1,0 +1,586 @@
+"""Python mirror of the reference's operator / solver / public interface for the
+H.psi hot path, on top of libspindyn_cuda.  Same names (Julia `f!` -> `f_`),
+same argument meaning, same error behaviour (ArgumentError -> ValueError), so
+tests/ can read like the reference's own tests.  Citations are file:line under
+/root/reference/src.
+
+Vector arguments may be numpy arrays (host, like Julia Vectors: uploaded,
+processed on the GPU, result downloaded) or `DeviceVector`s (stay in HBM).
+All vector arithmetic runs in CUDA kernels; the host keeps exactly what the
+north star keeps there: random start vectors, m x m tridiagonal eigenproblems,
+Bessel coefficients, kernel damping and spectrum reconstruction.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+
+from ._lib import SdComplex, check, lib
+from .core import Context, DeviceVector, Model, VecSet, _ptr, default_context
+
+# ------------------------------------------------------------------ Basis.jl
+
+
+def _validate_basis_args(L, nup=None):
+    """Basis.jl:9-20."""
+    if not L >= 1:
+        raise ValueError("L must be at least 1")
+    if not L <= 63:
+        raise ValueError("L must be at most 63 when using UInt64 basis states")
+    if nup is not None and not (0 <= nup <= L):
+        raise ValueError("nup must satisfy 0 <= nup <= L")
+
+
+class _RankMap:
+    """Stands in for Dict{UInt64,Int} (Basis.jl:49-52): lookups are computed by
+    ranking on the device instead of hashing."""
+
+    def __init__(self, model: Model):
+        self._m = model
+
+    def __getitem__(self, s):
+        r = int(self._m.rank_of([s])[0])
+        if r == 0:
+            raise KeyError(s)
+        return r
+
+    def get(self, s, default=0):
+        r = int(self._m.rank_of([s])[0])
+        return r if r != 0 else default
+
+    def __contains__(self, s):
+        return int(self._m.rank_of([s])[0]) != 0
+
+    def __len__(self):
+        return self._m.dim
+
+
+def build_full_basis(L: int, ctx: Optional[Context] = None):
+    """Basis.jl:23-34 -> (states, idxmap)."""
+    _validate_basis_args(L)
+    m = Model(L, None, [], np.zeros(L), [], ctx)
+    return m.states, _RankMap(m)
+
+
+def build_sector_basis(L: int, nup: int, ctx: Optional[Context] = None):
+    """Basis.jl:37-53 -> (states, idxmap); states come from the device unranking."""
+    _validate_basis_args(L, nup)
+    m = Model(L, nup, [], np.zeros(L), [], ctx)
+    return m.states, _RankMap(m)
+
+
+# -------------------------------------------------------------- SpinModel.jl
+
+def build_model(L: int, nup=None, hopping=(), onsite_field=None, zz=(), ctx: Optional[Context] = None) -> Model:
+    """SpinModel.jl:23-38."""
+    _validate_basis_args(L, nup)
+    if onsite_field is None:
+        onsite_field = np.zeros(L)
+    return Model(L, nup, list(hopping), onsite_field, list(zz), ctx)
+
+
+def nn_hopping(L: int, J: float):
+    """SpinModel.jl:40-42."""
+    return [(i, i + 1, J) for i in range(1, L)]
+
+
+def long_range_hopping(L: int, J: Callable):
+    """SpinModel.jl:44-46."""
+    return [(i, j, J(i, j)) for i in range(1, L + 1) for j in range(i + 1, L + 1)]
+
+
+def XXZChain(L: int, Jxy=1.0, Jz=1.0, hz=0.0, nup=None, boundary="open", ctx: Optional[Context] = None) -> Model:
+    """SpinModel.jl:63-90."""
+    hopping = [(i, i + 1, float(Jxy) / 2) for i in range(1, L)]
+    zz = [(i, i + 1, float(Jz)) for i in range(1, L)]
+    if boundary == "periodic":
+        if L > 2:
+            hopping.append((L, 1, float(Jxy) / 2))
+            zz.append((L, 1, float(Jz)))
+    elif boundary != "open":
+        raise ValueError("boundary must be :open or :periodic")
+    return build_model(L, nup=nup, hopping=hopping, onsite_field=np.full(L, float(hz)), zz=zz, ctx=ctx)
+
+
+def momenta(model: Model):
+    """SpinModel.jl:97-99."""
+    return 2 * np.pi * np.arange(model.L) / model.L
+
+
+# ------------------------------------------------------------ Hamiltonian.jl
+
+def bit_at(state: int, i: int) -> int:
+    """Hamiltonian.jl:19-21."""
+    return (int(state) >> i) & 1
+
+
+def sz_value(bit: int) -> float:
+    """Hamiltonian.jl:23-25."""
+    return 0.5 if bit == 1 else -0.5
+
+
+def flip_bits(state: int, i: int, j: int) -> int:
+    """Hamiltonian.jl:27-29."""
+    return int(state) ^ (1 << i) ^ (1 << j)
+
+
+def _is_dev(x) -> bool:
+    return isinstance(x, DeviceVector)
+
+
+def _up(model: Model, x, dtype=None) -> DeviceVector:
+    """Host vector -> device (Julia Vector semantics); DeviceVector passes through."""
+    if _is_dev(x):
+        if dtype is not None and x.dtype != np.dtype(dtype):
+            return x.astype(dtype)
+        return x
+    a = np.asarray(x)
+    if dtype is not None:
+        a = a.astype(dtype, copy=False)
+    elif a.dtype not in (np.float64, np.complex128):
+        a = a.astype(np.complex128 if np.iscomplexobj(a) else np.float64)
+    return model.to_device(a)
+
+
+def apply_H_(out, psi, model: Model):
+    """apply_H!(out, psi, model)   Hamiltonian.jl:211-273.  Returns `out`."""
+    if _is_dev(out) and _is_dev(psi):
+        check(lib().sd_apply_H(model._h, out._h, psi._h))
+        return out
+    out_a, psi_a = np.asarray(out), np.asarray(psi)
+    if not (isinstance(out, np.ndarray) and out.flags.c_contiguous and out.flags.writeable):
+        raise TypeError("out must be a writable contiguous numpy array or a DeviceVector")
+    if out_a.shape != psi_a.shape:                                  # @assert length(out) == N
+        raise ValueError("AssertionError: length(out) == N")
+    if out_a.dtype != psi_a.dtype:                                   # `where T` dispatch
+        raise TypeError("MethodError: out and psi must share one element type")
+    if psi_a.shape != (model.dim,):
+        raise ValueError("DimensionMismatch: psi does not match the model basis")
+    psi_c = np.ascontiguousarray(psi_a)
+    from .core import _sd_dtype
+    check(lib().sd_apply_H_host(model._h, _sd_dtype(psi_c.dtype), _ptr(out_a), _ptr(psi_c)))
+    return out
+
+
+def apply_H_neg_(out, psi, model: Model):
+    """The `-H` wrapper estimate_energy_bounds builds (Lanczos.jl:261-265)."""
+    apply_H_(out, psi, model)
+    if _is_dev(out):
+        out.scale(-1.0)
+    else:
+        np.negative(out, out=out)
+    return out
+
+
+def apply_rescaled_H_(out, psi, applyH_, model: Model, a: float, b: float):
+    """apply_rescaled_H!   Hamiltonian.jl:286-301: out = (H psi - b psi)/a."""
+    _require_builtin(applyH_)
+    if _is_dev(out) and _is_dev(psi):
+        check(lib().sd_apply_rescaled_H(model._h, out._h, psi._h, float(a), float(b)))
+        return out
+    if len(out) != len(psi):
+        raise ValueError("AssertionError: length(out) == length(psi)")
+    d_psi = _up(model, psi)
+    d_out = model.vector(d_psi.dtype)
+    check(lib().sd_apply_rescaled_H(model._h, d_out._h, d_psi._h, float(a), float(b)))
+    d_out.to_host(out)
+    return out
+
+
+def Sz_q_vector(model: Model, psi0, q: float, device: bool = False):
+    """Sz_q_vector   Hamiltonian.jl:307-337."""
+    n = model.dim if not _is_dev(psi0) else None
+    if n is not None and len(psi0) != n:
+        raise ValueError("AssertionError: length(psi0) == N")
+    d_psi = _up(model, psi0)
+    phi = model.vector(np.complex128)
+    check(lib().sd_szq(model._h, phi._h, d_psi._h, float(q), None))
+    return phi if (device or _is_dev(psi0)) else phi.to_host()
+
+
+def _require_builtin(applyH_):
+    if applyH_ not in (apply_H_, apply_H_neg_):
+        raise NotImplementedError(
+            "the GPU recurrences run the built-in matrix-free Hamiltonian; pass apply_H_ "
+            "(the reference's public layer hard-codes Hamiltonian.apply_H! the same way, PublicAPI.jl:28,62,70,80)")
+
+
+# ---------------------------------------------------------- InitialStates.jl
+
+def _one_hot(model: Model, s: int, what: str, device: bool = False):
+    idx = int(model.rank_of([s])[0])            # get(idxmap, s, 0) / Int(s)+1
+    if idx == 0:
+        raise ValueError(f"{what} is not contained in the model basis")
+    if device:
+        return model.vector(np.float64).set_onehot(idx - 1)
+    psi0 = np.zeros(model.dim)
+    psi0[idx - 1] = 1.0
+    return psi0
+
+
+def domain_wall_state(model: Model, device: bool = False):
+    """InitialStates.jl:9-34."""
+    nup = model.nup if model.mode == "sector" else int(np.ceil(model.L / 2))
+    s = 0
+    for i in range(nup):
+        s |= 1 << i
+    return _one_hot(model, s, "domain-wall state", device)
+
+
+def neel_state(model: Model, device: bool = False):
+    """InitialStates.jl:40-63."""
+    s = 0
+    for i in range(model.L):
+        if (i + 1) % 2 == 1:
+            s |= 1 << i
+    return _one_hot(model, s, "Neel state", device)
+
+
+def polarized_state(model: Model, up: bool = True, device: bool = False):
+    """InitialStates.jl:70-90."""
+    s = (1 << model.L) - 1 if up else 0
+    return _one_hot(model, s, "requested polarized state", device)
+
+
+def polarized_state_with_flips(model: Model, flips: Sequence[int], device: bool = False):
+    """InitialStates.jl:98-130."""
+    for site in flips:
+        if not 1 <= site <= model.L:
+            raise ValueError(f"flip site {site} is outside the model with L={model.L}")
+    s = (1 << model.L) - 1
+    for site in flips:
+        s ^= 1 << (site - 1)
+    return _one_hot(model, s, "requested flipped polarized state", device)
+
+
+# ---------------------------------------------------------------- Lanczos.jl
+
+def _eigvals_symtri(alpha, beta):
+    from scipy.linalg import eigh_tridiagonal
+    alpha = np.asarray(alpha, dtype=np.float64)
+    beta = np.asarray(beta, dtype=np.float64)
+    if len(alpha) == 1:
+        return alpha.copy()
+    return eigh_tridiagonal(alpha, beta, eigvals_only=True)
+
+
+def _eigen_symtri(alpha, beta):
+    from scipy.linalg import eigh_tridiagonal
+    alpha = np.asarray(alpha, dtype=np.float64)
+    beta = np.asarray(beta, dtype=np.float64)
+    if len(alpha) == 1:
+        return alpha.copy(), np.ones((1, 1))
+    return eigh_tridiagonal(alpha, beta)
+
+
+def randn_complex(rng: np.random.Generator, N: int) -> np.ndarray:
+    """randn(rng, ComplexF64, N): real and imaginary parts N(0, 1/2)."""
+    return (rng.standard_normal(N) + 1j * rng.standard_normal(N)) / np.sqrt(2.0)
+
+
+def _start_vector(model: Model, v0, rng, cplx: bool) -> DeviceVector:
+    """Start vectors stay a host responsibility (Lanczos.jl:39,99 use randn);
+    a DeviceVector or a seed-filled vector avoids the host round trip at large N."""
+    dt = np.complex128 if cplx else np.float64
+    if v0 is not None:
+        return _up(model, v0, dt)
+    if model.ctx.world > 1:
+        raise ValueError("multi-rank runs need an explicit DeviceVector start vector")
+    rng = rng or np.random.default_rng()
+    host = randn_complex(rng, model.dim) if cplx else rng.standard_normal(model.dim)
+    return model.to_device(host)
+
+
+def lanczos_extremal(applyH_, model: Model, lanc_m: int = 100, tol: float = 1e-12,
+                     rng: Optional[np.random.Generator] = None, v0=None):
+    """Lanczos.jl:27-84 -> (Emin, Emax) of the Krylov tridiagonal."""
+    _require_builtin(applyH_)
+    m = min(int(lanc_m), model.dim)
+    d0 = _start_vector(model, v0, rng, True)
+    alpha = np.zeros(m)
+    beta = np.zeros(max(m - 1, 1))
+    meff = ctypes.c_int()
+    check(lib().sd_lanczos_extremal(model._h, d0._h, int(lanc_m), float(tol),
+                                    1 if applyH_ is apply_H_neg_ else 0,
+                                    _ptr(alpha), _ptr(beta), ctypes.byref(meff)))
+    k = meff.value
+    evals = _eigvals_symtri(alpha[:k], beta[:k - 1])
+    return float(evals.min()), float(evals.max())
+
+
+def lanczos_groundstate(applyH_, model: Model, lanc_m: int = 100, tol: float = 1e-12,
+                        orthogonalize_tol: float = 1e-10, rng: Optional[np.random.Generator] = None,
+                        v0=None, device: bool = False, return_tridiag: bool = False):
+    """Lanczos.jl:87-181 -> (Emin, psi_gs).  psi_gs is a numpy array, or a
+    DeviceVector when device=True (needed once N no longer fits the host)."""
+    _require_builtin(applyH_)
+    m = min(int(lanc_m), model.dim)
+    d0 = _start_vector(model, v0, rng, False)
+    alpha = np.zeros(m)
+    beta = np.zeros(max(m - 1, 1))
+    mact = ctypes.c_int()
+    hV = ctypes.c_void_p()
+    check(lib().sd_lanczos_groundstate(model._h, d0._h, int(lanc_m), float(tol), float(orthogonalize_tol),
+                                       _ptr(alpha), _ptr(beta), ctypes.byref(mact), ctypes.byref(hV)))
+    V = VecSet(model, hV, np.float64)
+    ma = mact.value
+    a_act = alpha[:ma]
+    b_act = beta[:min(ma - 1, m - 1)]
+    evals, evecs = _eigen_symtri(a_act, b_act)                      # :164-165
+    idx = int(np.argmin(evals))
+    Emin = float(evals[idx])
+    y = evecs[:, idx]
+    psi = model.vector(np.float64)
+    n2 = V.lincomb(y.astype(np.complex128), psi)                    # :170
+    psi.scale(1.0 / np.sqrt(n2))                                    # :171
+    V.free()
+    res = psi if device else psi.to_host()
+    if return_tridiag:
+        return Emin, res, a_act.copy(), b_act.copy()
+    return Emin, res
+
+
+def lanczos_tridiag(applyH_, model: Model, v, lanc_m: int = 100, tol: float = 1e-12):
+    """Lanczos.jl:196-246 -> (alpha, beta, normv)."""
+    _require_builtin(applyH_)
+    dv = _up(model, v, np.complex128)
+    m = min(int(lanc_m), model.dim)
+    alpha = np.zeros(m)
+    beta = np.zeros(max(m - 1, 1))
+    meff = ctypes.c_int()
+    nv = ctypes.c_double()
+    try:
+        check(lib().sd_lanczos_tridiag(model._h, dv._h, int(lanc_m), float(tol), _ptr(alpha), _ptr(beta),
+                                       ctypes.byref(meff), ctypes.byref(nv)))
+    except Exception as e:
+        from ._lib import ZeroNormError
+        if isinstance(e, ZeroNormError):
+            raise RuntimeError("starting vector has zero norm") from None
+        raise
+    k = meff.value
+    return alpha[:k].copy(), beta[:k - 1].copy(), float(nv.value)
+
+
+def estimate_energy_bounds(applyH_, model: Model, lanc_m: int = 80, rng: Optional[np.random.Generator] = None,
+                           v0=None):
+    """Lanczos.jl:255-271: two extremal runs, on H and on -H."""
+    _require_builtin(applyH_)
+    _, Emax = lanczos_extremal(apply_H_, model, lanc_m=lanc_m, rng=rng, v0=v0)
+    _, Emax_neg = lanczos_extremal(apply_H_neg_, model, lanc_m=lanc_m, rng=rng, v0=v0)
+    return -Emax_neg, Emax
+
+
+# ------------------------------------------------------------- LanczosSqw.jl
+
+def spectral_from_tridiagonal(alpha, beta, norm_phi, E0, w_range, eta=0.05, broaden="lorentz"):
+    """LanczosSqw.jl:18-43 (host: W x m dense work)."""
+    theta, Q = _eigen_symtri(alpha, beta)
+    wts = np.abs(Q[0, :]) ** 2 * norm_phi ** 2
+    w_range = np.asarray(w_range, dtype=np.float64)
+    shifted = w_range[:, None] - (theta - E0)[None, :]
+    if broaden == "lorentz":
+        return ((1 / np.pi) * (eta / (shifted ** 2 + eta ** 2))) @ wts
+    elif broaden == "gauss":
+        return ((1 / (np.sqrt(2 * np.pi) * eta)) * np.exp(-(shifted ** 2) / (2 * eta ** 2))) @ wts
+    raise RuntimeError(f"unknown broadening: {broaden}")
+
+
+def lanczos_sqw(psi0, model: Model, q_list, w_range, lanc_m=200, eta=0.05, broaden="lorentz"):
+    """LanczosSqw.jl:49-80."""
+    psi0c = _up(model, psi0, np.complex128)
+    tmp = model.vector(np.complex128)
+    check(lib().sd_apply_H(model._h, tmp._h, psi0c._h))
+    E0 = psi0c.dotu(tmp).real                                      # :59 dot(conj(psi0c), tmp)
+    S = np.zeros((len(q_list), len(w_range)))
+    phi = model.vector(np.complex128)
+    for iq, q in enumerate(q_list):                                 # :65 (the reference threads over q)
+        n2 = ctypes.c_double()
+        check(lib().sd_szq(model._h, phi._h, psi0c._h, float(q), ctypes.byref(n2)))
+        if n2.value == 0.0:                                         # :69-72
+            continue
+        a, b, nphi = lanczos_tridiag(apply_H_, model, phi, lanc_m=lanc_m)
+        S[iq, :] = spectral_from_tridiagonal(a, b, nphi, E0, w_range, eta=eta, broaden=broaden)
+    return S
+
+
+# ---------------------------------------------------------------- KPM_Sqw.jl
+
+def _rescaling_from_bounds(E_min, E_max):
+    """KPM_Sqw.jl:13-17."""
+    return float((E_max - E_min) / (2 * 0.99)), float((E_max + E_min) / 2)
+
+
+def get_rescaling_params(applyH_, model: Model, lanc_m=80, rng=None):
+    """KPM_Sqw.jl:25-28."""
+    E_min, E_max = estimate_energy_bounds(applyH_, model, lanc_m=lanc_m, rng=rng)
+    return _rescaling_from_bounds(E_min, E_max)
+
+
+def compute_chebyshev_moments(applyH_, phi, M: int, a: float, b: float, model: Model):
+    """KPM_Sqw.jl:95-128: the fused moment loop (one kernel per moment)."""
+    _require_builtin(applyH_)
+    dphi = _up(model, phi, np.complex128)
+    mu = np.zeros(int(M))
+    check(lib().sd_kpm_moments(model._h, dphi._h, int(M), float(a), float(b), _ptr(mu)))
+    return mu
+
+
+def get_kernel(M: int, kernel: str):
+    """KPM_Sqw.jl:131-145."""
+    g = np.ones(M)
+    if kernel == "jackson":
+        n = np.arange(M)
+        g = ((M - n + 1) * np.cos(np.pi * n / (M + 1))
+             + np.sin(np.pi * n / (M + 1)) / np.tan(np.pi / (M + 1))) / (M + 1)
+    elif kernel == "lorentz":
+        lam = 3.0
+        n = np.arange(M)
+        g = np.sinh(lam * (1 - n / M)) / np.sinh(lam)
+    return g
+
+
+def kpm_sw(phi, applyH_, model: Model, w_range, a, b, E0, kpm_m=200, kernel="jackson"):
+    """KPM_Sqw.jl:34-93."""
+    mu = compute_chebyshev_moments(applyH_, phi, kpm_m, a, b, model)
+    mu = mu * get_kernel(kpm_m, kernel)
+    w_range = np.asarray(w_range, dtype=np.float64)
+    x = (w_range + E0 - b) / a
+    S = np.zeros(len(w_range))
+    inside = np.abs(x) < 1.0
+    xi = x[inside]
+    Tm2 = np.ones_like(xi)
+    acc = mu[0] * Tm2
+    if kpm_m >= 2:
+        Tm1 = xi.copy()
+        acc = acc + 2.0 * mu[1] * Tm1
+        for n in range(2, kpm_m):
+            Tn = 2.0 * xi * Tm1 - Tm2
+            acc = acc + 2.0 * mu[n] * Tn
+            Tm2, Tm1 = Tm1, Tn
+    S[inside] = np.maximum(0.0, acc / (a * np.pi * np.sqrt(1.0 - xi ** 2)))
+    return S
+
+
+def kpm_sqw(psi0, model: Model, q_list, w_range, a=None, b=None, kpm_m=200, kernel="jackson", rng=None):
+    """KPM_Sqw.jl:191-256."""
+    psi0c = _up(model, psi0, np.complex128)
+    S = np.zeros((len(q_list), len(w_range)))
+    tmp = model.vector(np.complex128)
+    r = SdComplex()
+    check(lib().sd_apply_H_dot(model._h, tmp._h, psi0c._h, ctypes.byref(r)))    # :207-209 fused E0
+    E0 = float(r.re)
+    if a is None or b is None:
+        a, b = get_rescaling_params(apply_H_, model, rng=rng)
+    phi = model.vector(np.complex128)
+    for iq, q in enumerate(q_list):
+        n2 = ctypes.c_double()
+        check(lib().sd_szq(model._h, phi._h, psi0c._h, float(q), ctypes.byref(n2)))
+        norm_phi = float(np.sqrt(n2.value))
+        if norm_phi == 0:
+            continue
+        phi.scale(1.0 / norm_phi)                                   # :231
+        Sq = kpm_sw(phi, apply_H_, model, w_range, a=a, b=b, E0=E0, kpm_m=kpm_m, kernel=kernel)
+        S[iq, :] = norm_phi ** 2 * Sq
+    return S
+
+
+# ---------------------------------------------------- TimeEvolution/Krylov.jl
+
+def krylov_time_evolve(psi0, dt: float, applyH_, model: Model, kry_m: int = 30, device: bool = False):
+    """Krylov.jl:136-192."""
+    _require_builtin(applyH_)
+    d0 = _up(model, psi0)
+    n = int(kry_m)
+    alpha = np.zeros(n, dtype=np.complex128)
+    beta = np.zeros(max(n - 1, 1))
+    meff = ctypes.c_int()
+    norm0 = ctypes.c_double()
+    hV = ctypes.c_void_p()
+    check(lib().sd_krylov_basis(model._h, d0._h, n, _ptr(alpha), _ptr(beta), ctypes.byref(meff),
+                                ctypes.byref(norm0), ctypes.byref(hV)))
+    V = VecSet(model, hV, d0.dtype)
+    if norm0.value == 0.0:                                          # :148
+        V.free()
+        return d0 if _is_dev(psi0) else np.array(psi0, copy=True)
+    k = meff.value
+    al, be = alpha[:k], beta[:k - 1].astype(np.complex128)
+    TR = np.diag(al) + np.diag(be, 1) + np.diag(be, -1)             # :175
+    if np.array_equal(TR, TR.conj().T):
+        D, Q = np.linalg.eigh(TR)
+    else:
+        D, Q = np.linalg.eig(TR)
+    U_T = Q @ np.diag(np.exp(-1j * D * dt)) @ Q.conj().T            # :180
+    e1 = np.zeros(k, dtype=np.complex128)
+    e1[0] = norm0.value
+    y = U_T @ e1
+    psit = model.vector(np.complex128)
+    n2 = V.lincomb(y, psit)                                         # :185-188
+    psit.scale(1.0 / np.sqrt(n2))                                   # :190
+    V.free()
+    return psit if (device or _is_dev(psi0)) else psit.to_host()
+
+
+# ------------------------------------------------- TimeEvolution/Chebyshev.jl
+
+_MINUS_I_POW = (1.0 + 0j, -1j, -1.0 + 0j, 1j)
+
+
+def chebyshev_coefficients(dt, cheb_n, Ebounds):
+    """Chebyshev.jl:70-79 (host: Bessel functions)."""
+    from scipy.special import jv
+    E_min, E_max = Ebounds
+    a = (E_max - E_min) / (2 * 0.9999)
+    b = (E_max + E_min) / 2
+    phase_factor = np.exp(-1j * b * dt)
+    c = np.empty(cheb_n, dtype=np.complex128)
+    for k in range(cheb_n):
+        c[k] = (2 - (1.0 if k == 0 else 0.0)) * _MINUS_I_POW[k % 4] * jv(k, a * dt) * phase_factor
+    return c, a, b
+
+
+def chebyshev_time_evolve(psi0, dt: float, applyH_, model: Model, cheb_n: int = 100, Ebounds=(-1.0, 1.0),
+                          device: bool = False):
+    """Chebyshev.jl:61-124."""
+    _require_builtin(applyH_)
+    if not cheb_n >= 1:
+        raise ValueError("AssertionError: cheb_n must be >= 1")
+    dt_in = psi0.dtype if _is_dev(psi0) else np.asarray(psi0).dtype
+    if dt_in != np.complex128:
+        raise TypeError("InexactError: real psi0 cannot hold complex Chebyshev sums")
+    c, a, b = chebyshev_coefficients(dt, int(cheb_n), Ebounds)
+    d0 = _up(model, psi0, np.complex128)
+    out = model.vector(np.complex128)
+    check(lib().sd_chebyshev_evolve(model._h, d0._h, _ptr(c), int(cheb_n), float(a), float(b), out._h))
+    return out if (device or _is_dev(psi0)) else out.to_host()
+
+
+# -------------------------------------------------------------- PublicAPI.jl
+
+def groundstate(model: Model, method="lanczos", **kw):
+    """PublicAPI.jl:25-35."""
+    if method == "lanczos":
+        return lanczos_groundstate(apply_H_, model, **kw)
+    raise ValueError(f"unsupported ground-state method: {method}")
+
+
+def time_evolve(model: Model, psi0, t, method="krylov", Ebounds=None, **kw):
+    """PublicAPI.jl:50-88."""
+    if method == "krylov":
+        return krylov_time_evolve(psi0, float(t), apply_H_, model, **kw)
+    elif method == "chebyshev":
+        bounds = estimate_energy_bounds(apply_H_, model) if Ebounds is None else Ebounds
+        return chebyshev_time_evolve(psi0, float(t), apply_H_, model, Ebounds=bounds, **kw)
+    raise ValueError(f"unsupported time-evolution method: {method}")
+
+
+def dynamical_structure_factor(model: Model, psi0, q, w, method="lanczos", **kw):
+    """PublicAPI.jl:122-155."""
+    q_list = np.asarray(q, dtype=np.float64)
+    w_range = np.asarray(w, dtype=np.float64)
+    if method == "lanczos":
+        return lanczos_sqw(psi0, model, q_list, w_range, **kw)
+    elif method == "kpm":
+        return kpm_sqw(psi0, model, q_list, w_range, **kw)
+    raise ValueError(f"unsupported dynamical structure-factor method: {method}")

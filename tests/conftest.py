@@ -1,11 +1,16 @@
-"""pytest configuration: registers the `gpu` marker and puts the repo root on
-sys.path so `oracle` (the CPU checker) and `__graft_entry__` import cleanly."""
+"""pytest configuration: registers the `gpu` marker, puts the repo root (for
+`oracle`, `__graft_entry__`) and the package directory (for `spindyn`) on
+sys.path, and builds the native pieces once per session."""
 import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-if ROOT not in sys.path:
-    sys.path.insert(0, ROOT)
+PKG = os.path.join(ROOT, "spindynamics.jl_b200")
+for p in (ROOT, PKG, os.path.dirname(os.path.abspath(__file__))):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import spindyn as sd  # noqa: E402  (importing needs neither the .so nor a GPU)
 
 
 def pytest_configure(config):
