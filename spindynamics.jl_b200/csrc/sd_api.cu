@@ -120,7 +120,7 @@ struct SdTileDev {
     SdTileHost host;
     uint32_t cap = 0;
     size_t smem = 0;
-    void *d_perm = nullptr, *d_midcfg = nullptr, *d_urank = nullptr, *d_dmid = nullptr, *d_cls = nullptr;
+    void *d_perm = nullptr, *d_items = nullptr, *d_binomM = nullptr;
     uint64_t keys[SD_MAX_WORLD + 1];
 };
 
@@ -137,6 +137,7 @@ struct sd_model {
     int path = SD_PATH_GENERIC;
     bool tile_capable = false;
     int tile_T[2] = {5, 4};
+    int tile_threads = 512;
     SdTileDev tile[2];              // [0]: F64, [1]: C128
     SdShardMap shards;
 };
@@ -307,6 +308,17 @@ int sd_timer_stop(sd_ctx *c, float *ms) {
     SD_CUDA(cudaEventElapsedTime(ms, c->ev0, c->ev1));
     return SD_OK;
 }
+// debug: per-phase cycle sums of the tiled kernel (all zero unless built with -DSD_PHASE_TIMING)
+extern "C" int sd_debug_phase_cycles(sd_ctx *c, uint64_t *out8, int reset) {
+    SD_ARG(c && out8, "NULL argument");
+    SD_TRY(sd_use(c));
+    SD_CUDA(cudaStreamSynchronize(c->stream));
+    unsigned long long h[8];
+    SD_CUDA(cudaMemcpyFromSymbol(h, sd_phase_cycles, sizeof(h)));
+    for (int i = 0; i < 8; ++i) out8[i] = h[i];
+    if (reset) { memset(h, 0, sizeof(h)); SD_CUDA(cudaMemcpyToSymbol(sd_phase_cycles, h, sizeof(h))); }
+    return SD_OK;
+}
 int sd_launch_count(const sd_ctx *c, uint64_t *n) {
     SD_ARG(c && n, "NULL argument");
     *n = c->launches;
@@ -323,6 +335,11 @@ static int sd_to_device(T **dst, const std::vector<T> &src) {
     return SD_OK;
 }
 
+static int sd_env_int(const char *name, int dflt) {
+    const char *s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
 static int sd_tile_setup(sd_model *m, int which, int B) {
     SdTileDev &t = m->tile[which];
     t.ok = false;
@@ -336,24 +353,18 @@ static int sd_tile_setup(sd_model *m, int which, int B) {
     t.smem = sd_tile_smem_bytes(nc, t.cap, t.host.P.M);
     if (t.smem > 227 * 1024) return SD_OK;
     SD_TRY(sd_to_device((uint16_t **)&t.d_perm, t.host.perm));
-    SD_TRY(sd_to_device((uint16_t **)&t.d_midcfg, t.host.midcfg));
-    SD_TRY(sd_to_device((uint16_t **)&t.d_urank, t.host.urank));
-    SD_TRY(sd_to_device((double **)&t.d_dmid, t.host.dmid));
-    SD_TRY(sd_to_device((uint32_t **)&t.d_cls, t.host.cls_base));
+    SD_TRY(sd_to_device((SdItem **)&t.d_items, t.host.items));
+    SD_TRY(sd_to_device((uint16_t **)&t.d_binomM, t.host.binomM));
     SdTileParams &P = t.host.P;
     P.binom = m->ctx->d_binom;
     P.perm = (const uint16_t *)t.d_perm;
-    P.midcfg = (const uint16_t *)t.d_midcfg;
-    P.urank = (const uint16_t *)t.d_urank;
-    P.dmid = (const double *)t.d_dmid;
-    P.cls_base = (const uint32_t *)t.d_cls;
+    P.items = (const SdItem *)t.d_items;
+    P.pf_dist = sd_env_int("SD_PF_DIST", 128);
+    P.binomM = (const uint16_t *)t.d_binomM;
+    // neighbour tiles further away than this are streamed evict-first (they cannot be reused from L2)
+    P.qfar = sd_tile_qfar(L, P.A, t.host.binom.data(), (uint64_t)sd_env_int("SD_FAR_MB", 100) << 20, 8 * nc);
     t.ok = true;
     return SD_OK;
-}
-
-static int sd_env_int(const char *name, int dflt) {
-    const char *s = getenv(name);
-    return (s && *s) ? atoi(s) : dflt;
 }
 
 int sd_model_create(sd_ctx *ctx, int L, int nup, const sd_bond *hop, int nhop, const sd_bond *zz, int nzz,
@@ -427,6 +438,7 @@ int sd_model_create(sd_ctx *ctx, int L, int nup, const sd_bond *hop, int nhop, c
         m->lin_h = h;
     }
     // tiled path: sector basis, every bond nearest-neighbour
+    m->tile_threads = sd_env_int("SD_TILE_THREADS", 512) == 256 ? 256 : 512;
     m->tile_T[0] = sd_env_int("SD_TILE_T", 5);
     m->tile_T[1] = sd_env_int("SD_TILE_T_C128", 4);
     m->tile_capable = false;
@@ -466,7 +478,7 @@ int sd_model_free(sd_model *m) {
     cudaFree(m->d_linA); cudaFree(m->d_linB);
     for (int w = 0; w < 2; ++w) {
         SdTileDev &t = m->tile[w];
-        cudaFree(t.d_perm); cudaFree(t.d_midcfg); cudaFree(t.d_urank); cudaFree(t.d_dmid); cudaFree(t.d_cls);
+        cudaFree(t.d_perm); cudaFree(t.d_items); cudaFree(t.d_binomM);
     }
     delete m;
     return SD_OK;
@@ -829,15 +841,26 @@ static int sd_apply_impl(sd_model *m, sd_vec *out, const sd_vec *psi, SdEpi epi,
         epi.nparts = (unsigned)nkeys;
         double *out_vbase = out->d - (int64_t)m->shards.start[c->rank] * nc;
         const int T = m->tile_T[nc - 1];
-#define SD_LAUNCH_TILE(NC_, T_)                                                                             \
+#define SD_LAUNCH_TILE3(NC_, T_, PLAIN_, NTHR_)                                                             \
     do {                                                                                                    \
         static size_t set_smem = 0;                                                                         \
         if (t.smem > set_smem) {                                                                            \
-            SD_CUDA(cudaFuncSetAttribute(sd_tile_apply_kernel<NC_, T_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem)); \
+            SD_CUDA(cudaFuncSetAttribute(sd_tile_apply_kernel<NC_, T_, PLAIN_, NTHR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem)); \
             set_smem = t.smem;                                                                              \
         }                                                                                                   \
-        sd_tile_apply_kernel<NC_, T_><<<(unsigned)nkeys, SD_TILE_THREADS, t.smem, c->stream>>>(P, psi->view, out_vbase, epi, t.cap); \
+        sd_tile_apply_kernel<NC_, T_, PLAIN_, NTHR_><<<(unsigned)nkeys, NTHR_, t.smem, c->stream>>>(P, psi->view, out_vbase, epi, t.cap); \
     } while (0)
+#define SD_LAUNCH_TILE2(NC_, T_, PLAIN_)                                                                    \
+    do {                                                                                                    \
+        if (m->tile_threads == 256) SD_LAUNCH_TILE3(NC_, T_, PLAIN_, 256);                                  \
+        else SD_LAUNCH_TILE3(NC_, T_, PLAIN_, 512);                                                         \
+    } while (0)
+#define SD_LAUNCH_TILE(NC_, T_)                                                                             \
+    do {                                                                                                    \
+        if (plain) SD_LAUNCH_TILE2(NC_, T_, true);                                                          \
+        else SD_LAUNCH_TILE2(NC_, T_, false);                                                               \
+    } while (0)
+        const bool plain = epi.mode == SD_EPI_PLAIN && epi.red == 0 && !epi.acc && epi.hscale == 1.0;
         if (nc == 1 && T == 5) SD_LAUNCH_TILE(1, 5);
         else if (nc == 2 && T == 4) SD_LAUNCH_TILE(2, 4);
         else if (nc == 1 && T == 4) SD_LAUNCH_TILE(1, 4);
@@ -845,6 +868,8 @@ static int sd_apply_impl(sd_model *m, sd_vec *out, const sd_vec *psi, SdEpi epi,
         else if (nc == 2 && T == 3) SD_LAUNCH_TILE(2, 3);
         else if (nc == 2 && T == 5) SD_LAUNCH_TILE(2, 5);
         else return sd_fail(SD_ERR_UNSUPPORTED, "tail size %d not compiled", T);
+#undef SD_LAUNCH_TILE3
+#undef SD_LAUNCH_TILE2
 #undef SD_LAUNCH_TILE
         SD_TRY(sd_launch_check(c, "sd_tile_apply_kernel"));
         if (slotmask) SD_TRY(sd_finish_reduce(c, (unsigned)nkeys, slotmask, slot_out));

@@ -74,28 +74,56 @@ __global__ void __launch_bounds__(1024) sd_reduce_partials_kernel(const double *
 }
 
 // ------------------------------------------------------------ tiled apply
-// registers: own[] + acc[] take 4*C(T,T/2)*NC; two CTAs per SM only when that fits 64 regs/thread
-template <int NC, int T>
-__global__ void __launch_bounds__(SD_TILE_THREADS, (4 * sd_cbinom(T, T / 2) * NC <= 48) ? 2 : 1)
+// Optional per-phase cycle counters (thread 0 of every CTA), enabled with -DSD_PHASE_TIMING.
+__device__ unsigned long long sd_phase_cycles[8];
+#ifdef SD_PHASE_TIMING
+#define SD_TICK(i)                                                          \
+    do {                                                                    \
+        if (threadIdx.x == 0) {                                             \
+            const long long now_ = clock64();                               \
+            atomicAdd(&sd_phase_cycles[i], (unsigned long long)(now_ - tick_)); \
+            tick_ = now_;                                                   \
+        }                                                                   \
+    } while (0)
+#define SD_TICK_INIT() long long tick_ = clock64()
+#else
+#define SD_TICK(i) ((void)0)
+#define SD_TICK_INIT() ((void)0)
+#endif
+
+// registers: own[] + acc[] take 4*C(T,T/2)*NC; two CTAs per SM only when that fits 64 regs/thread.
+// PLAIN = no fused epilogue (out = H psi): phase 3 is a pure streaming store.
+template <int NC, int T, bool PLAIN, int NTHR>
+__global__ void __launch_bounds__(NTHR, ((4 * sd_cbinom(T, T / 2) * NC <= 48) ? 1024 : 512) / NTHR)
 sd_tile_apply_kernel(const __grid_constant__ SdTileParams P, const __grid_constant__ SdVecView psi,
                      double *out_vbase, const __grid_constant__ SdEpi epi, uint32_t cap) {
     extern __shared__ __align__(16) unsigned char sd_smem[];
     const SdTileView<NC> v = sd_tile_carve<NC>(sd_smem, cap);
     const uint64_t key = P.key_lo + blockIdx.x;
-    sd_tile_phase0a<NC>(P, key, v, threadIdx.x, blockDim.x);
+    SdItem item0;
+    SD_TICK_INIT();
+    // the CTA size is a compile-time constant so element strides become immediates after inlining
+    sd_tile_phase0a<NC>(P, key, v, threadIdx.x, NTHR, item0);
     __syncthreads();
-    if (threadIdx.x == 0) sd_tile_phase0b<NC>(P, key, v, psi);
+    SD_TICK(0);
+    sd_tile_phase0b<NC>(P, key, v, psi, threadIdx.x, NTHR);
     __syncthreads();
-    const int slotmask = sd_epi_slotmask(epi.red);
+    SD_TICK(1);
+    const int slotmask = PLAIN ? 0 : sd_epi_slotmask(epi.red);
     double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
     if (v.hdr->valid) {
-        sd_tile_phase1<NC>(P, v, psi, threadIdx.x, blockDim.x);
+        sd_tile_phase1<NC>(P, v, psi, threadIdx.x, NTHR);
+        SD_TICK(2);                                       // thread 0's own phase-1 time
         __syncthreads();
-        sd_tile_phase2<NC, T>(P, v, threadIdx.x, blockDim.x);
+        SD_TICK(3);                                       // wait for the slowest warp
+        sd_tile_phase2<NC, T>(P, v, threadIdx.x, NTHR, item0);
+        SD_TICK(4);
         __syncthreads();
-        sd_tile_phase3<NC>(P, v, out_vbase, epi, threadIdx.x, blockDim.x, red);
+        SD_TICK(5);
+        sd_tile_phase3<NC, PLAIN>(P, v, out_vbase, epi, threadIdx.x, NTHR, red);
+        SD_TICK(6);
     }
-    if (slotmask) sd_block_reduce_store(red, slotmask, v.hdr->red, epi.partials, epi.nparts, blockIdx.x);
+    if (!PLAIN && slotmask) sd_block_reduce_store(red, slotmask, v.hdr->red, epi.partials, epi.nparts, blockIdx.x);
 }
 
 // ------------------------------------------------------------ generic apply

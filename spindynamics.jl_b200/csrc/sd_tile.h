@@ -20,8 +20,11 @@
 // class) reads conflict-free.
 //
 // Phases (separated by CTA barriers):
-//   0  header: prefix bits, tile base rank, neighbour-tile list        (1 thread)
-//   1  flat, coalesced: own psi -> smem, g = sum_J psi[neighbour tiles] -> smem
+//   0a every thread: one prefix position / bond each (one binomial lookup, all
+//      in flight together); item records of phase 2 are prefetched to registers
+//   0b one thread: ordered sums, neighbour-list compaction
+//   1  flat, coalesced, U elements per thread in flight per neighbour tile:
+//      own psi -> smem, g = sum_J psi[neighbour tiles] -> smem
 //   2  block-mapped: diag + g + tail/mid/crossing hops -> result in smem
 //   3  flat, coalesced: epilogue (rescale / Chebyshev / dots) -> out
 //
@@ -30,43 +33,107 @@
 #pragma once
 #include "sd_common.h"
 
-#define SD_TILE_MAXNB 32
+#define SD_TILE_MAXNB 32      // prefix sites A <= 32
 #define SD_TILE_MAXT 6
+#define SD_TILE_MAXB 19     // suffix sites (tile = up to C(19,9) states would not fit smem anyway)
+#define SD_TILE_U(NC) ((NC) == 1 ? 13 : 6)  // elements per thread per phase-1 warp chunk
+
+#if defined(__CUDA_ARCH__)
+#define SD_ATOMIC_OR(p, v) atomicOr(p, v)
+#define SD_LD_NEAR(p) __ldg(p)
+#define SD_LD_FAR(p) __ldcs(p)
+#define SD_ST_STREAM(p, v) __stcs(p, v)
+// nc doubles (8 or 16 bytes) global -> shared without a register landing zone
+#define SD_CP_ASYNC(dst, src, nc)                                                                   \
+    do {                                                                                            \
+        const unsigned sd_sa_ = (unsigned)__cvta_generic_to_shared(dst);                            \
+        if ((nc) == 1) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sd_sa_), "l"(src) : "memory");  \
+        else asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sd_sa_), "l"(src) : "memory");           \
+    } while (0)
+#define SD_CP_ASYNC_WAIT_ALL() asm volatile("cp.async.wait_all;" ::: "memory")
+// bulk L2 prefetch of [p, p+bytes): address aligned down to 16 B, size rounded up (vectors carry slack)
+#define SD_PREFETCH_L2(p, bytes)                                                                    \
+    do {                                                                                            \
+        const unsigned long long sd_a_ = (unsigned long long)(p);                                   \
+        const unsigned long long sd_b_ = sd_a_ & ~15ULL;                                            \
+        const unsigned sd_n_ = (unsigned)(((sd_a_ - sd_b_) + (bytes) + 15ULL) & ~15ULL);            \
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(sd_b_), "r"(sd_n_) : "memory"); \
+    } while (0)
+#else
+#define SD_ATOMIC_OR(p, v) (*(p) |= (v))
+#define SD_LD_NEAR(p) (*(p))
+#define SD_LD_FAR(p) (*(p))
+#define SD_ST_STREAM(p, v) (*(p) = (v))
+#define SD_CP_ASYNC(dst, src, nc)                          \
+    do {                                                   \
+        for (int sd_c_ = 0; sd_c_ < (nc); ++sd_c_) (dst)[sd_c_] = (src)[sd_c_]; \
+    } while (0)
+#define SD_CP_ASYNC_WAIT_ALL() ((void)0)
+#define SD_PREFETCH_L2(p, bytes) ((void)(p))
+#endif
+
+// One phase-2 work item (a tail block), precomputed per (js, slot) on the host.
+struct alignas(16) SdItem {
+    uint16_t c;        // mid configuration bits; 0xFFFF marks a padding slot
+    uint16_t u;        // class-local index of c
+    uint16_t u2;       // class-local index of the crossing partner (c with its last bit flipped)
+    uint16_t jt;       // tail popcount = class
+    double dmid;       // diag of the mid sites + mid-internal zz
+};
+
+// Per suffix-popcount layout, precomputed on the host.
+struct SdJsInfo {
+    uint32_t cls_base[SD_TILE_MAXT + 2];   // smem element offset of class jt; [T+1] = padded tile size
+    uint32_t nslots;                       // phase-2 slots (classes padded to warps)
+    uint32_t item_off;                     // first SdItem of this js
+    uint32_t perm_off;                     // first perm entry of this js
+    uint32_t size;                         // C(B, js)
+    uint32_t n1;                           // C(B-1, js-1): suffix configurations whose first bit is set
+    uint32_t ncross;                       // C(B-1, js): rank shift of the (1,0)->(0,1) crossing hop
+};
 
 struct SdTileParams {
     int L, k, A, B, M, T;
     uint64_t key_lo;                 // tile key of blockIdx.x == 0
     uint64_t key_hi;                 // one past the last key of this launch
+    int qfar;                        // prefix bonds q < qfar are far streams (shift beyond L2 reach): read evict-first
+    uint32_t hop_mask;               // bit q: Jhop[q] != 0 (q < 32)
     double Jhop[SD_MAX_L];           // hop coefficient of bond p (positions p, p+1)
     double Jz[SD_MAX_L];             // zz coefficient of bond p
     double h[SD_MAX_L + 1];          // field at position p
     double dtail[1 << SD_TILE_MAXT]; // diag of the tail sites + tail-internal zz, by tail bits
     const uint64_t *binom;           // [65*65]
-    const uint16_t *perm;            // [perm_off[js] + l] -> smem element position
-    const uint16_t *midcfg;          // [mid_off[jm] + u] -> mid bits c
-    const uint16_t *urank;           // [c] -> class-local index u
-    const double *dmid;              // [c] -> diag of mid sites + mid-internal zz
-    const uint32_t *cls_base;        // [js*(SD_TILE_MAXT+2) + jt] smem start of class jt; [.. + T+1] = cap
-    uint32_t perm_off[32];           // B <= 30
-    uint32_t mid_off[32];            // M <= 30
+    const uint16_t *perm;            // [perm_off + l] -> smem element position
+    const SdItem *items;             // [item_off + slot]
+    SdJsInfo js[SD_TILE_MAXB + 1];   // per suffix popcount layout (kernel parameter space: no load latency)
+    int pf_dist;                     // L2 prefetch distance in tiles (0 = off)
+    const uint16_t *binomM;          // [(M+1)*(M+1)] C(n, r) for n, r <= M
     SdShardMap shards;
+};
+
+struct SdNbEntry {
+    const double *ptr;               // virtual base: element l of the neighbour tile is ptr[l*NC]
+    double J;
 };
 
 struct SdTileHdr {
     uint64_t base;                   // rank of the tile's first state
     uint32_t size;                   // C(B, js)
-    int js, valid, nnb;
-    uint32_t nslots;
+    int js, valid;
+    int nfar, nfull;                 // nbf[0..nfar) far streams, nbf[nfar..nfull) near streams
+    uint32_t mixed_mask;             // bit q: neighbour range straddles a shard boundary (slow path)
+    uint32_t nslots, item_off, perm_off;
     double dP[2];                    // prefix diag + crossing zz, by first mid bit
     uint32_t cls_base[SD_TILE_MAXT + 2];
-    uint32_t slot_base[SD_TILE_MAXT + 2];
-    uint32_t n_items[SD_TILE_MAXT + 1];
-    int64_t nb_off[SD_TILE_MAXNB];   // rank shift of neighbour tile
-    double nb_J[SD_TILE_MAXNB];
-    uint32_t nb_lo[SD_TILE_MAXNB], nb_hi[SD_TILE_MAXNB];
-    const double *nb_ptr[SD_TILE_MAXNB];  // virtual base if the range sits in one shard, else null
-    uint64_t t_base[SD_TILE_MAXNB];  // phase-0 scratch: per-position rank terms
-    double t_diag[SD_TILE_MAXNB];    //                  per-position diagonal terms
+    SdNbEntry nbf[SD_TILE_MAXNB];    // compacted neighbour tiles of the active prefix-internal bonds
+    SdNbEntry cross;                 // prefix|suffix crossing bond (ptr == null: inactive)
+    // per prefix position q: rank term, diagonal term, rank shift and element range of bond q
+    uint64_t t_base[SD_TILE_MAXNB];
+    double t_diag[SD_TILE_MAXNB];
+    int64_t t_off[SD_TILE_MAXNB];
+    uint32_t t_lo[SD_TILE_MAXNB], t_hi[SD_TILE_MAXNB];
+    uint64_t pf_base[SD_TILE_MAXNB]; // rank terms of the tile that is being prefetched into L2
+    int64_t pf_off[SD_TILE_MAXNB];   // its far-bond shifts
     double red[SD_NSLOT][32];
 };
 
@@ -103,20 +170,34 @@ SD_HD SdTileView<NC> sd_tile_carve(void *smem, uint32_t cap) {
 // prefix bits of tile `key`: keys enumerate prefixes in rank order, bit q of the
 // prefix is the complement of key digit A-1-q ("1 first").
 SD_HD uint64_t sd_tile_prefix_bits(uint64_t key, int A) {
+    if (A == 0) return 0;
+#if defined(__CUDA_ARCH__)
+    return __brevll(~key) >> (64 - A);
+#else
     uint64_t Pb = 0;
     for (int q = 0; q < A; ++q)
         if (!((key >> (A - 1 - q)) & 1ULL)) Pb |= 1ULL << q;
     return Pb;
+#endif
 }
 
 // ---------------------------------------------------------------- phase 0
-// 0a runs on every thread: thread q owns prefix position q and bond q (one
-// binomial lookup each, all in flight together); 0b (one thread) sums the
-// per-position terms in order, compacts the neighbour list and lays out the
-// classes.  A single serial thread doing all of it cost ~35 us per tile.
+// 0a: thread q < A computes the rank / diagonal terms of prefix position q and
+//     the rank shift of bond q; binomM copy and the first phase-2 item prefetch
+//     are spread over the CTA.  0b: thread q < A sums the A rank terms itself
+//     (broadcast smem reads) and writes its own neighbour entry into a slot
+//     computed from the bond-activity mask (popc prefix) -- no serial work.
+//     Far bonds (q < qfar: shift larger than anything L2 can hold) come first.
+SD_HD uint32_t sd_tile_active_mask(const SdTileParams &P, uint64_t Pb) {
+    // bit q: prefix-internal bond q (positions q, q+1) is antiparallel and has J != 0
+    if (P.A < 2) return 0u;
+    const uint64_t m = (Pb ^ (Pb >> 1)) & ((1ULL << (P.A - 1)) - 1);
+    return (uint32_t)m & P.hop_mask;
+}
+
 template <int NC>
 SD_HD void sd_tile_phase0a(const SdTileParams &P, uint64_t key, const SdTileView<NC> &v,
-                           unsigned tid, unsigned nthreads) {
+                           unsigned tid, unsigned nthreads, SdItem &item0) {
     SdTileHdr &H = *v.hdr;
     const int L = P.L, k = P.k, A = P.A, B = P.B, M = P.M, T = P.T;
     const uint64_t *C = P.binom;
@@ -126,10 +207,41 @@ SD_HD void sd_tile_phase0a(const SdTileParams &P, uint64_t key, const SdTileView
     if (tid == 0) {
         H.valid = valid ? 1 : 0;
         H.js = js;
-        H.size = valid ? (uint32_t)sd_binom_at(C, SD_BINOM_DIM, B, js) : 0u;
+        H.mixed_mask = 0;
+    }
+    item0.c = 0xFFFFu;
+    // L2 prefetch for the tile pf_dist keys ahead: lanes 32.. compute its rank terms and far shifts
+    if (P.pf_dist > 0 && tid >= 32 && tid < 32u + (unsigned)A) {
+        const int q = (int)tid - 32;
+        const uint64_t key2 = key + (uint64_t)P.pf_dist;
+        uint64_t tb = 0;
+        int64_t off = 0;
+        if (key2 < P.key_hi) {
+            const uint64_t Pb2 = sd_tile_prefix_bits(key2, A);
+            const int js2 = k - SD_POPC64(Pb2);
+            if (js2 >= 0 && js2 <= B) {
+                const int bit = (int)((Pb2 >> q) & 1ULL);
+                const int below = SD_POPC64(Pb2 & ((1ULL << q) - 1));
+                tb = bit ? 0ULL : sd_binom_at(C, SD_BINOM_DIM, L - 1 - q, k - below - 1);
+                if (q < P.qfar && q + 1 < A) {
+                    const int bn = (int)((Pb2 >> (q + 1)) & 1ULL);
+                    if (bit != bn && P.Jhop[q] != 0.0) {
+                        const uint64_t dl = sd_binom_at(C, SD_BINOM_DIM, L - 2 - q, k - (below + bit + bn));
+                        off = bit ? (int64_t)dl : -(int64_t)dl;
+                    }
+                }
+            }
+        }
+        H.pf_base[q] = tb;
+        H.pf_off[q] = off;
     }
     if (!valid) return;
-    const uint32_t size = (uint32_t)sd_binom_at(C, SD_BINOM_DIM, B, js);
+    const SdJsInfo &I = P.js[js];
+    const uint32_t size = I.size;
+    if (tid < I.nslots) item0 = P.items[I.item_off + tid];   // first phase-2 item: depends on js and tid only
+    if (tid == 0) {
+        H.size = size; H.nslots = I.nslots; H.item_off = I.item_off; H.perm_off = I.perm_off;
+    }
     for (int q = (int)tid; q < A; q += (int)nthreads) {
         const int bit = (int)((Pb >> q) & 1ULL);
         const int below = SD_POPC64(Pb & ((1ULL << q) - 1));             // set bits at positions < q
@@ -138,119 +250,216 @@ SD_HD void sd_tile_phase0a(const SdTileParams &P, uint64_t key, const SdTileView
         H.t_base[q] = bit ? 0ULL : sd_binom_at(C, SD_BINOM_DIM, L - 1 - q, k - below - 1);
         int64_t off = 0;
         uint32_t lo = 0, hi = 0;
-        const double J = P.Jhop[q];
         if (q + 1 < A) {                                                  // prefix-internal bond q
             const int bn = (int)((Pb >> (q + 1)) & 1ULL);
             d += P.Jz[q] * sq * (bn ? 0.5 : -0.5);
-            if (bit != bn && J != 0.0) {
+            if (bit != bn && P.Jhop[q] != 0.0) {
                 const uint64_t dl = sd_binom_at(C, SD_BINOM_DIM, L - 2 - q, k - (below + bit + bn));
                 off = bit ? (int64_t)dl : -(int64_t)dl;
                 hi = size;
             }
-        } else if (J != 0.0) {                                            // prefix|suffix crossing bond
-            const uint32_t n1 = (uint32_t)sd_binom_at(C, SD_BINOM_DIM, B - 1, js - 1);   // first suffix bit = 1
+        } else if (P.Jhop[q] != 0.0) {                                    // prefix|suffix crossing bond
+            const uint32_t n1 = I.n1;                                     // first suffix bit = 1
             if (bit) {                       // (1,0) -> (0,1): states with first suffix bit 0 move up
-                if (n1 < size) { off = (int64_t)sd_binom_at(C, SD_BINOM_DIM, B - 1, js); lo = n1; hi = size; }
+                if (n1 < size) { off = (int64_t)I.ncross; lo = n1; hi = size; }
             } else if (n1 > 0) {             // (0,1) -> (1,0)
                 off = -(int64_t)n1; lo = 0; hi = n1;
             }
         }
         H.t_diag[q] = d;
-        H.nb_off[q] = off; H.nb_J[q] = J; H.nb_lo[q] = lo; H.nb_hi[q] = hi;
+        H.t_off[q] = off; H.t_lo[q] = lo; H.t_hi[q] = hi;
     }
-    for (int i = (int)tid; i < (M + 1) * (M + 1); i += (int)nthreads) {
-        const int nn = i / (M + 1), r = i - nn * (M + 1);
-        v.binomM[i] = (uint16_t)sd_binom_at(C, SD_BINOM_DIM, nn, r);
-    }
-    for (int jt = (int)tid; jt <= T + 1; jt += (int)nthreads) {
-        H.cls_base[jt] = P.cls_base[js * (SD_TILE_MAXT + 2) + jt];
-        if (jt <= T) {
-            const int jm = js - jt;
-            H.n_items[jt] = (jm >= 0 && jm <= M) ? (uint32_t)sd_binom_at(C, SD_BINOM_DIM, M, jm) : 0u;
-        }
-    }
+    for (int i = (int)tid; i < (M + 1) * (M + 1); i += (int)nthreads) v.binomM[i] = P.binomM[i];
+    for (int jt = (int)tid; jt <= T + 1; jt += (int)nthreads) H.cls_base[jt] = I.cls_base[jt];
 }
 
 template <int NC>
 SD_HD void sd_tile_phase0b(const SdTileParams &P, uint64_t key, const SdTileView<NC> &v,
-                           const SdVecView &psi) {
+                           const SdVecView &psi, unsigned tid, unsigned nthreads) {
     SdTileHdr &H = *v.hdr;
-    if (!H.valid) return;
-    const int A = P.A, T = P.T;
-    uint64_t base = 0;
-    double dpre = 0.0;
-    for (int q = 0; q < A; ++q) { base += H.t_base[q]; dpre += H.t_diag[q]; }
-    H.base = base;
-    if (A > 0) {
-        const uint64_t Pb = sd_tile_prefix_bits(key, A);
-        const double sl = ((Pb >> (A - 1)) & 1ULL) ? 0.5 : -0.5;
-        H.dP[0] = dpre + P.Jz[A - 1] * sl * (-0.5);
-        H.dP[1] = dpre + P.Jz[A - 1] * sl * (0.5);
-    } else {
-        H.dP[0] = H.dP[1] = dpre;
-    }
-    int n = 0;
-    const bool single = P.shards.world == 1;
-    for (int q = 0; q < A; ++q) {
-        const uint32_t lo = H.nb_lo[q], hi = H.nb_hi[q];
-        if (hi <= lo) continue;
-        const int64_t off = H.nb_off[q];
-        const double J = H.nb_J[q];
-        const double *ptr;
-        if (single) {
-            ptr = psi.base[0] + (int64_t)NC * ((int64_t)base + off);
-        } else {
-            const uint64_t r0 = (uint64_t)((int64_t)(base + lo) + off);
-            const uint64_t r1 = (uint64_t)((int64_t)(base + hi - 1) + off);
-            const int g0 = sd_owner(P.shards, r0), g1 = sd_owner(P.shards, r1);
-            ptr = (g0 == g1) ? psi.base[g0] + (int64_t)NC * ((int64_t)base + off) : nullptr;
+    const int A = P.A;
+    // L2 prefetch of the own tile and the far neighbour tiles of key + pf_dist (local shard only)
+    if (P.pf_dist > 0 && tid >= 32 && tid <= 32u + (unsigned)P.qfar && tid <= 32u + (unsigned)A) {
+        const uint64_t key2 = key + (uint64_t)P.pf_dist;
+        if (key2 < P.key_hi) {
+            const int js2 = P.k - SD_POPC64(sd_tile_prefix_bits(key2, A));
+            if (js2 >= 0 && js2 <= P.B) {
+                uint64_t base2 = 0;
+                for (int q = 0; q < A; ++q) base2 += H.pf_base[q];
+                const int which = (int)tid - 32;                          // 0..qfar-1: far bond, qfar: own tile
+                const int64_t off = (which < P.qfar && which < A) ? H.pf_off[which] : 0;
+                if (which == P.qfar || off != 0) {
+                    const uint64_t r0 = (uint64_t)((int64_t)base2 + off);
+                    const int g = P.shards.world == 1 ? 0 : sd_owner(P.shards, r0);
+                    if (g == P.shards.rank) SD_PREFETCH_L2(psi.base[g] + (size_t)NC * r0, (size_t)NC * 8 * P.js[js2].size);
+                }
+            }
         }
-        H.nb_off[n] = off; H.nb_J[n] = J; H.nb_lo[n] = lo; H.nb_hi[n] = hi; H.nb_ptr[n] = ptr;
-        ++n;
     }
-    H.nnb = n;
-    uint32_t slot = 0;
-    for (int jt = 0; jt <= T; ++jt) {
-        H.slot_base[jt] = slot;
-        slot += (H.n_items[jt] + 31u) & ~31u;
+    if (!H.valid) return;
+    if ((int)tid >= A && tid != 0) return;
+    uint64_t base = 0;
+    for (int q = 0; q < A; ++q) base += H.t_base[q];
+    const uint64_t Pb = sd_tile_prefix_bits(key, A);
+    const uint32_t act = sd_tile_active_mask(P, Pb);
+    const uint32_t farbits = (P.qfar >= 32) ? ~0u : ((1u << P.qfar) - 1u);
+    const uint32_t act_far = act & farbits, act_near = act & ~farbits;
+    const int nfar = SD_POPC32(act_far);
+    if (tid == 0) {
+        double dpre = 0.0;
+        for (int q = 0; q < A; ++q) dpre += H.t_diag[q];
+        H.base = base;
+        if (A > 0) {
+            const double sl = ((Pb >> (A - 1)) & 1ULL) ? 0.5 : -0.5;
+            H.dP[0] = dpre + P.Jz[A - 1] * sl * (-0.5);
+            H.dP[1] = dpre + P.Jz[A - 1] * sl * (0.5);
+        } else {
+            H.dP[0] = H.dP[1] = dpre;
+        }
+        H.nfar = nfar;
+        H.nfull = nfar + SD_POPC32(act_near);
+        H.cross.ptr = nullptr;
     }
-    H.slot_base[T + 1] = slot;
-    H.nslots = slot;
+    const bool single = P.shards.world == 1;
+    for (int q = (int)tid; q < A; q += (int)nthreads) {
+        const uint32_t lo = H.t_lo[q], hi = H.t_hi[q];
+        if (hi <= lo) continue;
+        const int64_t off = H.t_off[q];
+        int g0 = 0, g1 = 0;
+        if (!single) {
+            g0 = sd_owner(P.shards, (uint64_t)((int64_t)(base + lo) + off));
+            g1 = sd_owner(P.shards, (uint64_t)((int64_t)(base + hi - 1) + off));
+        }
+        SdNbEntry e;
+        e.J = P.Jhop[q];
+        e.ptr = psi.base[g0] + (int64_t)NC * ((int64_t)base + off);
+        if (g0 != g1) {                                  // range straddles a shard boundary: slow path,
+            SD_ATOMIC_OR(&H.mixed_mask, 1u << q);        // the entry stays in its slot with J = 0
+            e.J = 0.0;
+            e.ptr = psi.base[P.shards.rank] + (int64_t)NC * (int64_t)base;
+        }
+        if (q + 1 < A) {
+            const uint32_t below = (1u << q) - 1u;
+            const int slot = ((farbits >> q) & 1u) ? SD_POPC32(act_far & below) : nfar + SD_POPC32(act_near & below);
+            H.nbf[slot] = e;
+        } else {
+            H.cross = e;
+        }
+    }
 }
 
 // ---------------------------------------------------------------- phase 1
+// Warp-blocked mapping: a warp owns 32*U consecutive elements, a thread's U elements are 256 B
+// apart (element l0 + 32 u).  With the obvious CTA-strided mapping (elements 4 KB apart) all of a
+// thread's loads fall into the same L1 set and throughput stops scaling with U; measured on B200
+// (scripts/mb_streams.cu): 10 streams, 32 warps/SM: strided U=7 8.9 ms, U=13 11.0 ms; blocked U=13 7.2 ms.
+// The apply is bound by bytes in flight, so U is as large as the register file allows.
+template <int NC, int CNT, bool FULL, bool FAR>
+SD_HD void sd_tile_gather(double (&g)[CNT][NC], const double *q, double J, const int32_t (&idx)[CNT]) {
+    double t[CNT][NC];
+#pragma unroll
+    for (int u = 0; u < CNT; ++u)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const double *a = FULL ? q + (size_t)NC * 32 * u + c : q + (int64_t)NC * idx[u] + c;
+            t[u][c] = FAR ? SD_LD_FAR(a) : SD_LD_NEAR(a);
+        }
+#pragma unroll
+    for (int u = 0; u < CNT; ++u)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) g[u][c] += J * t[u][c];
+}
+
+// One warp chunk: elements l0 + 32 u, u < CNT.  FULL: every element of every lane is inside the tile
+// (unpredicated loads, immediate offsets); otherwise indices are clamped into the tile and only the
+// stores are predicated.
+template <int NC, int CNT, bool FULL>
+SD_HD void sd_tile_phase1_chunk(const SdTileParams &P, const SdTileView<NC> &v, const SdVecView &psi, uint32_t l0) {
+    const SdTileHdr &H = *v.hdr;
+    const uint32_t size = H.size;
+    int32_t idx[CNT];                                     // element offset relative to l0 (clamped lanes: negative)
+#pragma unroll
+    for (int u = 0; u < CNT; ++u) {
+        const uint32_t l = l0 + 32u * u;
+        idx[u] = FULL ? 32 * u : (int32_t)(l < size ? l : size - 1) - (int32_t)l0;
+    }
+    const uint16_t *perm = P.perm + H.perm_off + l0;
+    uint32_t pos[CNT];
+#pragma unroll
+    for (int u = 0; u < CNT; ++u) pos[u] = perm[idx[u]];
+    {                                                     // own tile: global -> smem (class-major position)
+        const double *own = psi.base[P.shards.rank] + (int64_t)NC * (int64_t)(H.base + l0);
+#pragma unroll
+        for (int u = 0; u < CNT; ++u)
+            if (FULL || l0 + 32u * u < size) SD_CP_ASYNC(v.spsi + (size_t)pos[u] * NC, own + (int64_t)NC * idx[u], NC);
+    }
+    double g[CNT][NC];
+#pragma unroll
+    for (int u = 0; u < CNT; ++u)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) g[u][c] = 0.0;
+    const int nfar = H.nfar, nfull = H.nfull;
+    int i = 0;
+#pragma unroll 1
+    for (; i < nfar; ++i) {
+        const SdNbEntry e = H.nbf[i];
+        sd_tile_gather<NC, CNT, FULL, true>(g, e.ptr + (size_t)NC * l0, e.J, idx);
+    }
+#pragma unroll 1
+    for (; i < nfull; ++i) {
+        const SdNbEntry e = H.nbf[i];
+        sd_tile_gather<NC, CNT, FULL, false>(g, e.ptr + (size_t)NC * l0, e.J, idx);
+    }
+    const SdNbEntry ce = H.cross;                         // prefix|suffix crossing bond: sub-range [lo, hi)
+    if (ce.ptr) {
+        const int qc = P.A - 1;
+        const uint32_t lo = H.t_lo[qc], hi = H.t_hi[qc];
+        const double *q = ce.ptr + (size_t)NC * l0;
+#pragma unroll
+        for (int u = 0; u < CNT; ++u) {
+            const uint32_t l = l0 + 32u * u;
+            if (l >= lo && l < hi) {
+#pragma unroll
+                for (int c = 0; c < NC; ++c) g[u][c] += ce.J * SD_LD_NEAR(q + (size_t)NC * 32 * u + c);
+            }
+        }
+    }
+    for (uint32_t mm = H.mixed_mask; mm; mm &= mm - 1) {  // neighbour range straddles a shard boundary (rare)
+        int qq = 0;
+        while (!((mm >> qq) & 1u)) ++qq;
+        const int64_t off = H.t_off[qq];
+        const double J = P.Jhop[qq];
+        const uint32_t lo = H.t_lo[qq], hi = H.t_hi[qq];
+#pragma unroll
+        for (int u = 0; u < CNT; ++u) {
+            const uint32_t l = l0 + 32u * u;
+            if (l >= lo && l < hi) {
+                const uint64_t r = (uint64_t)((int64_t)(H.base + l) + off);
+                const double *q = psi.base[sd_owner(P.shards, r)] + (size_t)NC * r;
+#pragma unroll
+                for (int c = 0; c < NC; ++c) g[u][c] += J * q[c];
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < CNT; ++u)
+        if (FULL || l0 + 32u * u < size) {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) v.sg[(size_t)pos[u] * NC + c] = g[u][c];
+        }
+}
+
 template <int NC>
 SD_HD void sd_tile_phase1(const SdTileParams &P, const SdTileView<NC> &v, const SdVecView &psi,
                           unsigned tid, unsigned nthreads) {
-    const SdTileHdr &H = *v.hdr;
-    const uint16_t *perm = P.perm + P.perm_off[H.js];
-    const double *own = psi.base[P.shards.rank] + (int64_t)NC * (int64_t)H.base;
-    const int nnb = H.nnb;
-    for (uint32_t l = tid; l < H.size; l += nthreads) {
-        const uint32_t pos = perm[l];
-        double g[NC];
-#pragma unroll
-        for (int c = 0; c < NC; ++c) g[c] = 0.0;
-        for (int i = 0; i < nnb; ++i) {
-            if (l >= H.nb_lo[i] && l < H.nb_hi[i]) {
-                const double *q = H.nb_ptr[i];
-                if (q) {
-                    q += (size_t)NC * l;
-                } else {
-                    const uint64_t r = (uint64_t)((int64_t)(H.base + l) + H.nb_off[i]);
-                    q = psi.base[sd_owner(P.shards, r)] + (size_t)NC * r;
-                }
-                const double J = H.nb_J[i];
-#pragma unroll
-                for (int c = 0; c < NC; ++c) g[c] += J * q[c];
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            v.spsi[(size_t)pos * NC + c] = own[(size_t)l * NC + c];
-            v.sg[(size_t)pos * NC + c] = g[c];
-        }
+    constexpr int U = SD_TILE_U(NC);
+    const uint32_t size = v.hdr->size;
+    const uint32_t lane = tid & 31u, warp = tid >> 5, nwarps = nthreads >> 5;
+    for (uint32_t c0 = warp * 32u * U; c0 < size; c0 += nwarps * 32u * U) {
+        if (c0 + 32u * U <= size) sd_tile_phase1_chunk<NC, U, true>(P, v, psi, c0 + lane);
+        else sd_tile_phase1_chunk<NC, U, false>(P, v, psi, c0 + lane);
     }
+    SD_CP_ASYNC_WAIT_ALL();                               // own-tile copies landed before the CTA barrier
 }
 
 // ---------------------------------------------------------------- phase 2
@@ -294,13 +503,13 @@ struct SdTailInit {
 };
 
 template <int NC, int T, int JT>
-SD_HD void sd_tile_block(const SdTileParams &P, const SdTileView<NC> &v, uint32_t u) {
+SD_HD void sd_tile_block(const SdTileParams &P, const SdTileView<NC> &v, const SdItem &it) {
     constexpr int NT = sd_cbinom(T, JT);
     constexpr int NTP = NT | 1;                      // odd pitch: conflict-free across a warp
     const SdTileHdr &H = *v.hdr;
     const int M = P.M, A = P.A;
-    const int jm = H.js - JT;
-    const unsigned c = P.midcfg[P.mid_off[jm] + u];
+    const unsigned c = it.c;
+    const uint32_t u = it.u;
     const uint32_t cb = H.cls_base[JT];
     const uint32_t pos = cb + u * NTP;
     double own[NT * NC], acc[NT * NC];
@@ -311,7 +520,7 @@ SD_HD void sd_tile_block(const SdTileParams &P, const SdTileView<NC> &v, uint32_
     }
     // diagonal + neighbour-tile sum
     const int c_first = (int)(c & 1u), c_last = (int)((c >> (M - 1)) & 1u);
-    const double dthread = H.dP[c_first] + P.dmid[c];
+    const double dthread = H.dP[c_first] + it.dmid;
     const double qx = P.Jz[A + M - 1] * 0.25;
     const double dx = c_last ? qx : -qx;             // +qx when tail bit 0 equals the last mid bit
     SdTailInit<NC, T, JT, 0>::run(acc, own, v.sg + (size_t)pos * NC, P.dtail, dthread, dx);
@@ -335,23 +544,19 @@ SD_HD void sd_tile_block(const SdTileParams &P, const SdTileView<NC> &v, uint32_
         const double J = P.Jhop[A + M - 1];
         constexpr int n1 = sd_cbinom(T - 1, JT - 1);          // tail configs with first bit 1
         if (c_last) {
-            if constexpr (JT < T && NT - n1 > 0) {                       // our first bit 0 -> partner class JT+1, first part
+            if constexpr (JT < T && NT - n1 > 0) {             // our first bit 0 -> partner class JT+1, first part
                 constexpr int NTP2 = sd_cbinom(T, JT + 1) | 1;
-                const unsigned c2 = c ^ (1u << (M - 1));
-                const uint32_t u2 = P.urank[c2];
-                const double *sp = v.spsi + (size_t)(H.cls_base[JT + 1] + u2 * NTP2) * NC;
+                const double *sp = v.spsi + (size_t)(H.cls_base[JT + 1] + (uint32_t)it.u2 * NTP2) * NC;
 #pragma unroll
                 for (int t = n1; t < NT; ++t)
 #pragma unroll
                     for (int cc = 0; cc < NC; ++cc) acc[t * NC + cc] += J * sp[(t - n1) * NC + cc];
             }
         } else {
-            if constexpr (JT > 0 && n1 > 0) {                            // our first bit 1 -> partner class JT-1, second part
+            if constexpr (JT > 0 && n1 > 0) {                  // our first bit 1 -> partner class JT-1, second part
                 constexpr int NTP2 = sd_cbinom(T, JT - 1) | 1;
                 constexpr int n1p = sd_cbinom(T - 1, JT - 2);
-                const unsigned c2 = c | (1u << (M - 1));
-                const uint32_t u2 = P.urank[c2];
-                const double *sp = v.spsi + (size_t)(H.cls_base[JT - 1] + u2 * NTP2) * NC;
+                const double *sp = v.spsi + (size_t)(H.cls_base[JT - 1] + (uint32_t)it.u2 * NTP2) * NC;
 #pragma unroll
                 for (int t = 0; t < n1; ++t)
 #pragma unroll
@@ -368,44 +573,70 @@ SD_HD void sd_tile_block(const SdTileParams &P, const SdTileView<NC> &v, uint32_
 
 template <int NC, int T, int JT>
 struct SdTileDispatch {
-    static SD_HD void run(const SdTileParams &P, const SdTileView<NC> &v, int jt, uint32_t u) {
-        if (jt == JT) sd_tile_block<NC, T, JT>(P, v, u);
-        else if constexpr (JT > 0) SdTileDispatch<NC, T, JT - 1>::run(P, v, jt, u);
+    static SD_HD void run(const SdTileParams &P, const SdTileView<NC> &v, const SdItem &it) {
+        if (it.jt == JT) sd_tile_block<NC, T, JT>(P, v, it);
+        else if constexpr (JT > 0) SdTileDispatch<NC, T, JT - 1>::run(P, v, it);
     }
 };
 
 template <int NC, int T>
 SD_HD void sd_tile_phase2(const SdTileParams &P, const SdTileView<NC> &v, unsigned tid,
-                          unsigned nthreads) {
+                          unsigned nthreads, const SdItem &item0) {
     const SdTileHdr &H = *v.hdr;
-    for (uint32_t s = tid; s < H.nslots; s += nthreads) {
-        int jt = 0;
-#pragma unroll
-        for (int j = 1; j <= T; ++j) jt += (s >= H.slot_base[j]) ? 1 : 0;
-        const uint32_t u = s - H.slot_base[jt];
-        if (u < H.n_items[jt]) SdTileDispatch<NC, T, T>::run(P, v, jt, u);
+    const uint32_t nslots = H.nslots;
+    const SdItem *items = P.items + H.item_off;
+    SdItem cur = item0;                                   // prefetched in phase 0
+#pragma unroll 1
+    for (uint32_t s = tid; s < nslots; s += nthreads) {
+        SdItem nxt;
+        nxt.c = 0xFFFFu;
+        if (s + nthreads < nslots) nxt = items[s + nthreads];             // lookahead hides the L2 latency
+        if (cur.c != 0xFFFFu) SdTileDispatch<NC, T, T>::run(P, v, cur);
+        cur = nxt;
     }
 }
 
 // ---------------------------------------------------------------- phase 3
-template <int NC>
+template <int NC, bool PLAIN, int CNT, bool FULL>
+SD_HD void sd_tile_phase3_chunk(const SdTileParams &P, const SdTileView<NC> &v, double *out_vbase,
+                                const SdEpi &epi, uint32_t l0, double (&red)[SD_NSLOT]) {
+    const SdTileHdr &H = *v.hdr;
+    const uint32_t size = H.size;
+    const uint16_t *perm = P.perm + H.perm_off + l0;
+    double *o = out_vbase + (int64_t)NC * (int64_t)(H.base + l0);
+    uint32_t pos[CNT];
+#pragma unroll
+    for (int u = 0; u < CNT; ++u) pos[u] = (FULL || l0 + 32u * u < size) ? perm[32 * u] : 0u;
+#pragma unroll
+    for (int u = 0; u < CNT; ++u) {
+        if (!FULL && l0 + 32u * u >= size) continue;
+        SdVal<NC> h;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) h.c[c] = v.sg[(size_t)pos[u] * NC + c];
+        if (PLAIN) {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) SD_ST_STREAM(o + (size_t)NC * 32 * u + c, h.c[c]);
+        } else {
+            SdVal<NC> p;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) p.c[c] = v.spsi[(size_t)pos[u] * NC + c];
+            const uint64_t li = H.base + l0 + 32u * u - P.shards.start[P.shards.rank];
+            const SdVal<NC> r = sd_epilogue<NC>(epi, h, p, li, red);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) o[(size_t)NC * 32 * u + c] = r.c[c];
+        }
+    }
+}
+
+template <int NC, bool PLAIN>
 SD_HD void sd_tile_phase3(const SdTileParams &P, const SdTileView<NC> &v, double *out_vbase,
                           const SdEpi &epi, unsigned tid, unsigned nthreads,
                           double (&red)[SD_NSLOT]) {
-    const SdTileHdr &H = *v.hdr;
-    const uint16_t *perm = P.perm + P.perm_off[H.js];
-    const uint64_t lstart = P.shards.start[P.shards.rank];
-    double *o = out_vbase + (int64_t)NC * (int64_t)H.base;
-    for (uint32_t l = tid; l < H.size; l += nthreads) {
-        const uint32_t pos = perm[l];
-        SdVal<NC> h, p;
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            h.c[c] = v.sg[(size_t)pos * NC + c];
-            p.c[c] = v.spsi[(size_t)pos * NC + c];
-        }
-        const SdVal<NC> r = sd_epilogue<NC>(epi, h, p, H.base + l - lstart, red);
-#pragma unroll
-        for (int c = 0; c < NC; ++c) o[(size_t)l * NC + c] = r.c[c];
+    constexpr int U = 8;
+    const uint32_t size = v.hdr->size;
+    const uint32_t lane = tid & 31u, warp = tid >> 5, nwarps = nthreads >> 5;
+    for (uint32_t c0 = warp * 32u * U; c0 < size; c0 += nwarps * 32u * U) {
+        if (c0 + 32u * U <= size) sd_tile_phase3_chunk<NC, PLAIN, U, true>(P, v, out_vbase, epi, c0 + lane, red);
+        else sd_tile_phase3_chunk<NC, PLAIN, U, false>(P, v, out_vbase, epi, c0 + lane, red);
     }
 }

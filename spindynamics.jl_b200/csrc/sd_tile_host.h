@@ -9,43 +9,59 @@
 struct SdTileHost {
     SdTileParams P;                 // table pointers left null; caller points them at host or device copies
     std::vector<uint64_t> binom;    // [65*65]
-    std::vector<uint16_t> perm, midcfg, urank;
-    std::vector<double> dmid;
-    std::vector<uint32_t> cls_base; // [(B+1)*(SD_TILE_MAXT+2)]
+    std::vector<uint16_t> perm;     // flat suffix index -> smem position, all js concatenated
+    std::vector<SdItem> items;      // phase-2 work items, all js concatenated
+    std::vector<SdJsInfo> jsinfo;   // [B+1]
+    std::vector<uint16_t> binomM;   // [(M+1)*(M+1)]
     uint32_t cap_max = 0;           // largest padded tile, in elements
+    uint32_t nslots_max = 0;
 };
 
 // Jhop/Jz: coefficient of bond p (positions p,p+1), length L-1 (0 if absent); h: length L.
 // Returns false if the split is not representable (then the generic kernel is used).
+// Prefix bonds q < qfar can shift a tile by more than `far_bytes` (their largest shift is
+// C(L-2-q, (L-2-q)/2) elements): such neighbour tiles cannot be reused from L2.
+static inline int sd_tile_qfar(int L, int A, const uint64_t *C, uint64_t far_bytes, int elem_bytes) {
+    int q = 0;
+    while (q + 1 < A && q < 31) {
+        const int n = L - 2 - q;
+        if (C[n * SD_BINOM_DIM + n / 2] * (uint64_t)elem_bytes <= far_bytes) break;
+        ++q;
+    }
+    return q;
+}
+
 static inline bool sd_tile_build(int L, int k, int B, int T, const double *Jhop, const double *Jz,
                                  const double *h, SdTileHost &o) {
-    if (k < 0 || k > L || T < 1 || T > SD_TILE_MAXT || B > L || B - T < 2 || B > 30) return false;
+    if (k < 0 || k > L || T < 1 || T > SD_TILE_MAXT || B > L || B - T < 2 || B > SD_TILE_MAXB) return false;
     const int M = B - T, A = L - B;
-    if (M > 15 || A > SD_TILE_MAXNB - 1) return false;   // u16 mid tables; neighbour list capacity
+    if (M > 15 || A > SD_TILE_MAXNB) return false;       // u16 mid tables; neighbour list capacity
     o.binom.assign(SD_BINOM_DIM * SD_BINOM_DIM, 0);
     sd_fill_binom(o.binom.data());
     const uint64_t *C = o.binom.data();
     SdTileParams &P = o.P;
     std::memset(&P, 0, sizeof(P));
     P.L = L; P.k = k; P.A = A; P.B = B; P.M = M; P.T = T;
+    P.qfar = 0;
+    P.hop_mask = 0;
+    for (int p = 0; p + 1 < L && p < 32; ++p) if (Jhop[p] != 0.0) P.hop_mask |= 1u << p;
     for (int p = 0; p + 1 < L; ++p) { P.Jhop[p] = Jhop[p]; P.Jz[p] = Jz[p]; }
     for (int p = 0; p < L; ++p) P.h[p] = h[p];
     // mid configurations, class-sorted (class = popcount), "1 first" lexicographic inside a class
-    o.midcfg.assign((size_t)1 << M, 0);
-    o.urank.assign((size_t)1 << M, 0);
-    o.dmid.assign((size_t)1 << M, 0.0);
+    std::vector<uint16_t> midcfg((size_t)1 << M, 0), urank((size_t)1 << M, 0);
+    std::vector<uint32_t> mid_off(M + 2, 0);
+    std::vector<double> dmid((size_t)1 << M, 0.0);
     uint32_t off = 0;
     for (int jm = 0; jm <= M; ++jm) {
-        P.mid_off[jm] = off;
+        mid_off[jm] = off;
         const uint32_t n = (uint32_t)C[M * SD_BINOM_DIM + jm];
         for (uint32_t u = 0; u < n; ++u) {
             const unsigned c = (unsigned)sd_unrank_state(u, M, jm, C, SD_BINOM_DIM);
-            o.midcfg[off + u] = (uint16_t)c;
-            o.urank[c] = (uint16_t)u;
+            midcfg[off + u] = (uint16_t)c;
+            urank[c] = (uint16_t)u;
         }
         off += n;
     }
-    P.mid_off[M + 1] = off;
     for (unsigned c = 0; c < (1u << M); ++c) {
         double d = 0.0;
         for (int q = 0; q < M; ++q) {
@@ -53,7 +69,7 @@ static inline bool sd_tile_build(int L, int k, int B, int T, const double *Jhop,
             d += h[A + q] * s;
             if (q + 1 < M) d += Jz[A + q] * s * (((c >> (q + 1)) & 1u) ? 0.5 : -0.5);
         }
-        o.dmid[c] = d;
+        dmid[c] = d;
     }
     for (unsigned t = 0; t < (1u << T); ++t) {
         double d = 0.0;
@@ -64,39 +80,66 @@ static inline bool sd_tile_build(int L, int k, int B, int T, const double *Jhop,
         }
         P.dtail[t] = d;
     }
-    // class-major smem layout per suffix popcount js
-    o.cls_base.assign((size_t)(B + 1) * (SD_TILE_MAXT + 2), 0);
-    o.cap_max = 0;
-    for (int js = 0; js <= B; ++js) {
-        uint32_t run = 0;
-        for (int jt = 0; jt <= T; ++jt) {
-            o.cls_base[js * (SD_TILE_MAXT + 2) + jt] = run;
-            const int jm = js - jt;
-            if (jm >= 0 && jm <= M)
-                run += (uint32_t)C[M * SD_BINOM_DIM + jm] * ((uint32_t)C[T * SD_BINOM_DIM + jt] | 1u);
-        }
-        for (int jt = T + 1; jt < SD_TILE_MAXT + 2; ++jt) o.cls_base[js * (SD_TILE_MAXT + 2) + jt] = run;
-        if (run > o.cap_max) o.cap_max = run;
-    }
-    if (o.cap_max > 65535u) return false;
-    // permutation flat suffix index -> smem position
-    o.perm.assign((size_t)1 << B, 0);
+    // per-js layout: class-major smem offsets, phase-2 slots (classes padded to warps), work items
+    o.jsinfo.assign(B + 1, SdJsInfo());
+    o.items.clear();
+    o.cap_max = 0; o.nslots_max = 0;
     uint32_t poff = 0;
     for (int js = 0; js <= B; ++js) {
-        P.perm_off[js] = poff;
-        const uint32_t n = (uint32_t)C[B * SD_BINOM_DIM + js];
-        for (uint32_t l = 0; l < n; ++l) {
+        SdJsInfo &I = o.jsinfo[js];
+        std::memset(&I, 0, sizeof(I));
+        uint32_t run = 0, slot = 0;
+        I.item_off = (uint32_t)o.items.size();
+        for (int jt = 0; jt <= T; ++jt) {
+            I.cls_base[jt] = run;
+            const int jm = js - jt;
+            if (jm < 0 || jm > M) continue;
+            const uint32_t ni = (uint32_t)C[M * SD_BINOM_DIM + jm];
+            run += ni * ((uint32_t)C[T * SD_BINOM_DIM + jt] | 1u);
+            const uint32_t padded = (ni + 31u) & ~31u;
+            for (uint32_t u = 0; u < padded; ++u) {
+                SdItem it;
+                std::memset(&it, 0, sizeof(it));
+                it.c = 0xFFFFu;
+                if (u < ni) {
+                    const unsigned c = midcfg[mid_off[jm] + u];
+                    it.c = (uint16_t)c; it.u = (uint16_t)u; it.jt = (uint16_t)jt;
+                    it.u2 = urank[c ^ (1u << (M - 1))];
+                    it.dmid = dmid[c];
+                }
+                o.items.push_back(it);
+            }
+            slot += padded;
+        }
+        for (int jt = T + 1; jt < SD_TILE_MAXT + 2; ++jt) I.cls_base[jt] = run;
+        I.nslots = slot;
+        I.size = (uint32_t)C[B * SD_BINOM_DIM + js];
+        I.n1 = js >= 1 ? (uint32_t)C[(B - 1) * SD_BINOM_DIM + js - 1] : 0u;
+        I.ncross = (uint32_t)C[(B - 1) * SD_BINOM_DIM + js];
+        I.perm_off = poff;
+        poff += I.size;
+        if (run > o.cap_max) o.cap_max = run;
+        if (slot > o.nslots_max) o.nslots_max = slot;
+    }
+    if (o.cap_max > 65535u) return false;
+    for (int js = 0; js <= B; ++js) P.js[js] = o.jsinfo[js];
+    o.binomM.assign((size_t)(M + 1) * (M + 1), 0);
+    for (int nn = 0; nn <= M; ++nn)
+        for (int r = 0; r <= nn; ++r) o.binomM[nn * (M + 1) + r] = (uint16_t)C[nn * SD_BINOM_DIM + r];
+    // permutation flat suffix index -> smem position
+    o.perm.assign((size_t)1 << B, 0);
+    for (int js = 0; js <= B; ++js) {
+        const SdJsInfo &I = o.jsinfo[js];
+        for (uint32_t l = 0; l < I.size; ++l) {
             const uint64_t s = sd_unrank_state(l, B, js, C, SD_BINOM_DIM);
             const unsigned c = (unsigned)(s & ((1ULL << M) - 1));
             const unsigned tau = (unsigned)(s >> M);
             const int jt = __builtin_popcount(tau);
             const uint32_t ntp = (uint32_t)C[T * SD_BINOM_DIM + jt] | 1u;
             const uint32_t t = (uint32_t)sd_rank_state(tau, T, jt, C, SD_BINOM_DIM);
-            o.perm[poff + l] = (uint16_t)(o.cls_base[js * (SD_TILE_MAXT + 2) + jt] + o.urank[c] * ntp + t);
+            o.perm[I.perm_off + l] = (uint16_t)(I.cls_base[jt] + urank[c] * ntp + t);
         }
-        poff += n;
     }
-    P.perm_off[B + 1] = poff;
     P.key_lo = 0;
     P.key_hi = 1ULL << A;
     P.shards.world = 1; P.shards.rank = 0;

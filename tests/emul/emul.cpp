@@ -8,6 +8,7 @@
 // sequentially over the threads of one CTA, one CTA (tile) at a time.
 #include <cstdlib>
 #include <cstring>
+#include <array>
 #include <vector>
 #include "../../spindynamics.jl_b200/csrc/sd_tile_host.h"
 
@@ -20,14 +21,18 @@ static void run_tiles(const SdTileHost &th, SdTileParams P, const SdVecView &psi
     for (uint64_t key = P.key_lo; key < P.key_hi; ++key) {
         std::memset(sm, 0xA5, bytes);              // poison: catches reads of unwritten smem
         SdTileView<NC> v = sd_tile_carve<NC>(sm, th.cap_max);
-        for (unsigned tid = 0; tid < nthreads; ++tid) sd_tile_phase0a<NC>(P, key, v, tid, nthreads);
-        sd_tile_phase0b<NC>(P, key, v, psi);
+        std::vector<SdItem> regs(nthreads);        // per-thread register held across phases
+        for (unsigned tid = 0; tid < nthreads; ++tid) sd_tile_phase0a<NC>(P, key, v, tid, nthreads, regs[tid]);
+        for (unsigned tid = 0; tid < nthreads; ++tid) sd_tile_phase0b<NC>(P, key, v, psi, tid, nthreads);
         if (!v.hdr->valid) continue;
         for (unsigned tid = 0; tid < nthreads; ++tid) sd_tile_phase1<NC>(P, v, psi, tid, nthreads);
-        for (unsigned tid = 0; tid < nthreads; ++tid) sd_tile_phase2<NC, T>(P, v, tid, nthreads);
+        for (unsigned tid = 0; tid < nthreads; ++tid)
+            sd_tile_phase2<NC, T>(P, v, tid, nthreads, regs[tid]);
+        const bool plain = epi.mode == SD_EPI_PLAIN && epi.red == 0 && !epi.acc && epi.hscale == 1.0;
         for (unsigned tid = 0; tid < nthreads; ++tid) {
             double red[SD_NSLOT] = {0, 0, 0, 0};
-            sd_tile_phase3<NC>(P, v, out_vbase, epi, tid, nthreads, red);
+            if (plain) sd_tile_phase3<NC, true>(P, v, out_vbase, epi, tid, nthreads, red);
+            else sd_tile_phase3<NC, false>(P, v, out_vbase, epi, tid, nthreads, red);
             for (int s = 0; s < SD_NSLOT; ++s) red_total[s] += red[s];
         }
     }
@@ -43,16 +48,16 @@ int emul_tile_apply(int L, int k, int B, int T, const double *Jhop, const double
                     int NC, const double *psi, double *out, unsigned nthreads, int world, int rank,
                     int mode, int redmask, double hscale, double a, double b, const double *vprev,
                     const double *phi, double *acc, double ck_re, double ck_im, double *red_out,
-                    uint64_t *bounds_out) {
+                    uint64_t *bounds_out, uint64_t far_elems) {
     SdTileHost th;
     if (!sd_tile_build(L, k, B, T, Jhop, Jz, h, th)) return -1;
     SdTileParams P = th.P;
     P.binom = th.binom.data();
     P.perm = th.perm.data();
-    P.midcfg = th.midcfg.data();
-    P.urank = th.urank.data();
-    P.dmid = th.dmid.data();
-    P.cls_base = th.cls_base.data();
+    P.items = th.items.data();
+    P.pf_dist = 3;                                 // exercises the prefetch bookkeeping (no-op on the host)
+    P.binomM = th.binomM.data();
+    P.qfar = sd_tile_qfar(L, P.A, th.binom.data(), far_elems, 8 * NC);
     uint64_t bounds[SD_MAX_WORLD + 1], keys[SD_MAX_WORLD + 1];
     sd_tile_shard_bounds(th, world, bounds, keys);
     P.shards.world = world; P.shards.rank = rank;

@@ -26,7 +26,7 @@ def emul():
     lib.emul_tile_apply.argtypes = ([ctypes.c_int] * 4 + [vp, vp, vp, ctypes.c_int, vp, vp, ctypes.c_uint,
                                     ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                     ctypes.c_double, ctypes.c_double, ctypes.c_double, vp, vp, vp,
-                                    ctypes.c_double, ctypes.c_double, vp, vp])
+                                    ctypes.c_double, ctypes.c_double, vp, vp, ctypes.c_uint64])
     return lib
 
 
@@ -55,7 +55,7 @@ def oracle_apply(L, k, Jhop, Jz, h, psi, NC):
 
 
 def run(lib, L, k, B, T, NC, world, psi, Jhop, Jz, h, nthreads=64, mode=0, red=0, hscale=1.0, a=1.0, b=0.0,
-        vprev=None, phi=None, acc=None, ck=0j):
+        vprev=None, phi=None, acc=None, ck=0j, far=50):
     N = len(psi) // NC
     out = np.full(N * NC, np.nan)
     redsum = np.zeros(4)
@@ -63,7 +63,7 @@ def run(lib, L, k, B, T, NC, world, psi, Jhop, Jz, h, nthreads=64, mode=0, red=0
     for r in range(world):
         redr = np.zeros(4)
         rc = lib.emul_tile_apply(L, k, B, T, P(Jhop), P(Jz), P(h), NC, P(psi), P(out), nthreads, world, r,
-                                 mode, red, hscale, a, b, P(vprev), P(phi), P(acc), ck.real, ck.imag, P(redr), P(bounds))
+                                 mode, red, hscale, a, b, P(vprev), P(phi), P(acc), ck.real, ck.imag, P(redr), P(bounds), far)
         assert rc == 0
         redsum += redr
     return out, redsum, bounds
@@ -142,7 +142,7 @@ def _gloo_worker(rank, world, port, q):
         lib.emul_tile_apply.argtypes = ([ctypes.c_int] * 4 + [vp, vp, vp, ctypes.c_int, vp, vp, ctypes.c_uint,
                                         ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_double, ctypes.c_double, ctypes.c_double, vp, vp, vp,
-                                        ctypes.c_double, ctypes.c_double, vp, vp])
+                                        ctypes.c_double, ctypes.c_double, vp, vp, ctypes.c_uint64])
         L, k, B, T = 16, 8, 11, 5
         Jhop, Jz, h = model_lists(L)
         N = orc.lib().orc_sector_dim(L, k)
@@ -151,7 +151,7 @@ def _gloo_worker(rank, world, port, q):
         red = np.zeros(4)
         bounds = np.zeros(world + 1, dtype=np.uint64)
         rc = lib.emul_tile_apply(L, k, B, T, P(Jhop), P(Jz), P(h), 1, P(psi), P(out), 128, world, rank,
-                                 0, 1, 1.0, 1.0, 0.0, None, None, None, 0.0, 0.0, P(red), P(bounds))
+                                 0, 1, 1.0, 1.0, 0.0, None, None, None, 0.0, 0.0, P(red), P(bounds), 100)
         assert rc == 0
         lo, hi = int(bounds[rank]), int(bounds[rank + 1])
         mine = torch.from_numpy(out[lo:hi].copy())
