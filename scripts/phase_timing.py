@@ -11,15 +11,15 @@ m = sd.XXZChain(Lc, nup=Lc // 2)
 psi = m.vector().fill_seeded(1, 1e-4); out = m.vector()
 lib = sd.lib()
 lib.sd_debug_phase_cycles.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
-buf = np.zeros(8, dtype=np.uint64)
+buf = np.zeros(16, dtype=np.uint64)
 sd.apply_H_(out, psi, m); m.ctx.sync()
 lib.sd_debug_phase_cycles(m.ctx._h, buf.ctypes.data_as(ctypes.c_void_p), 1)
 m.ctx.timer_start()
 for _ in range(3): sd.apply_H_(out, psi, m)
 ms = m.ctx.timer_stop() / 3
 lib.sd_debug_phase_cycles(m.ctx._h, buf.ctypes.data_as(ctypes.c_void_p), 1)
-names = ["0a+bar", "0b+bar", "phase1(thread0)", "bar1 wait", "phase2(thread0)", "bar2 wait", "phase3(thread0)", "-"]
-tot = buf.sum()
+names = ["phase0(thread0)", "bar0 wait", "phase1(thread0)", "bar1 wait", "phase2(thread0)", "bar2 wait", "phase3(thread0)", "-", "p1: perm+cp.async", "p1: far streams", "p1: near streams", "p1: crossing", "p1: cp.async wait", "-", "-", "-"]
+tot = buf[:8].sum()
 ntiles = 1 << (Lc - m.info["tile_sites"])
 print(f"L={Lc} ms/apply={ms:.3f} tiles={ntiles} threads={os.environ.get('SD_TILE_THREADS','512')} B={m.info['tile_sites']}")
 for n, c in zip(names, buf):

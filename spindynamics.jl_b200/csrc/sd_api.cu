@@ -313,9 +313,9 @@ extern "C" int sd_debug_phase_cycles(sd_ctx *c, uint64_t *out8, int reset) {
     SD_ARG(c && out8, "NULL argument");
     SD_TRY(sd_use(c));
     SD_CUDA(cudaStreamSynchronize(c->stream));
-    unsigned long long h[8];
+    unsigned long long h[16];
     SD_CUDA(cudaMemcpyFromSymbol(h, sd_phase_cycles, sizeof(h)));
-    for (int i = 0; i < 8; ++i) out8[i] = h[i];
+    for (int i = 0; i < 16; ++i) out8[i] = h[i];
     if (reset) { memset(h, 0, sizeof(h)); SD_CUDA(cudaMemcpyToSymbol(sd_phase_cycles, h, sizeof(h))); }
     return SD_OK;
 }
@@ -836,9 +836,10 @@ static int sd_apply_impl(sd_model *m, sd_vec *out, const sd_vec *psi, SdEpi epi,
         const uint64_t nkeys = P.key_hi - P.key_lo;
         if (nkeys == 0) return SD_OK;
         SD_ARG(nkeys < 0x7fffffffULL, "too many tiles for one launch");
-        if (slotmask) SD_TRY(sd_partials_reserve(c, (size_t)SD_NSLOT * nkeys));
+        const unsigned grid = (unsigned)nkeys;           // one CTA per tile, in rank order
+        if (slotmask) SD_TRY(sd_partials_reserve(c, (size_t)SD_NSLOT * grid));
         epi.partials = c->d_partials;
-        epi.nparts = (unsigned)nkeys;
+        epi.nparts = grid;
         double *out_vbase = out->d - (int64_t)m->shards.start[c->rank] * nc;
         const int T = m->tile_T[nc - 1];
 #define SD_LAUNCH_TILE3(NC_, T_, PLAIN_, NTHR_)                                                             \
@@ -848,7 +849,7 @@ static int sd_apply_impl(sd_model *m, sd_vec *out, const sd_vec *psi, SdEpi epi,
             SD_CUDA(cudaFuncSetAttribute(sd_tile_apply_kernel<NC_, T_, PLAIN_, NTHR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem)); \
             set_smem = t.smem;                                                                              \
         }                                                                                                   \
-        sd_tile_apply_kernel<NC_, T_, PLAIN_, NTHR_><<<(unsigned)nkeys, NTHR_, t.smem, c->stream>>>(P, psi->view, out_vbase, epi, t.cap); \
+        sd_tile_apply_kernel<NC_, T_, PLAIN_, NTHR_><<<grid, NTHR_, t.smem, c->stream>>>(P, psi->view, out_vbase, epi, t.cap); \
     } while (0)
 #define SD_LAUNCH_TILE2(NC_, T_, PLAIN_)                                                                    \
     do {                                                                                                    \
@@ -872,7 +873,7 @@ static int sd_apply_impl(sd_model *m, sd_vec *out, const sd_vec *psi, SdEpi epi,
 #undef SD_LAUNCH_TILE2
 #undef SD_LAUNCH_TILE
         SD_TRY(sd_launch_check(c, "sd_tile_apply_kernel"));
-        if (slotmask) SD_TRY(sd_finish_reduce(c, (unsigned)nkeys, slotmask, slot_out));
+        if (slotmask) SD_TRY(sd_finish_reduce(c, grid, slotmask, slot_out));
     } else {
         SdGenericParams G;
         G.L = m->L; G.k = m->k; G.nhop = (int)m->hop_a.size(); G.nzz = (int)m->zz_a.size(); G.N = m->N;

@@ -23,7 +23,7 @@ __device__ __forceinline__ double sd_warp_sum(double v) {
 
 // red[] per thread -> partials[slot*nparts + part]; scratch is [SD_NSLOT][32] smem.
 __device__ __forceinline__ void sd_block_reduce_store(double (&red)[SD_NSLOT], int mask,
-                                                      double (*scratch)[32], double *partials,
+                                                      double (*scratch)[16], double *partials,
                                                       unsigned nparts, unsigned part) {
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31u) >> 5;
 #pragma unroll
@@ -75,7 +75,6 @@ __global__ void __launch_bounds__(1024) sd_reduce_partials_kernel(const double *
 
 // ------------------------------------------------------------ tiled apply
 // Optional per-phase cycle counters (thread 0 of every CTA), enabled with -DSD_PHASE_TIMING.
-__device__ unsigned long long sd_phase_cycles[8];
 #ifdef SD_PHASE_TIMING
 #define SD_TICK(i)                                                          \
     do {                                                                    \
@@ -98,32 +97,52 @@ __global__ void __launch_bounds__(NTHR, ((4 * sd_cbinom(T, T / 2) * NC <= 48) ? 
 sd_tile_apply_kernel(const __grid_constant__ SdTileParams P, const __grid_constant__ SdVecView psi,
                      double *out_vbase, const __grid_constant__ SdEpi epi, uint32_t cap) {
     extern __shared__ __align__(16) unsigned char sd_smem[];
+    // One CTA per tile (a persistent variant was measured slower: all CTAs fall into lockstep and
+    // the memory system idles during the compute phases).  The CTA size is a compile-time constant
+    // so element strides become immediates after inlining.
     const SdTileView<NC> v = sd_tile_carve<NC>(sd_smem, cap);
+    SdTileHdr &H = *v.hdr;
+    const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
     const uint64_t key = P.key_lo + blockIdx.x;
-    SdItem item0;
     SD_TICK_INIT();
-    // the CTA size is a compile-time constant so element strides become immediates after inlining
-    sd_tile_phase0a<NC>(P, key, v, threadIdx.x, NTHR, item0);
-    __syncthreads();
+    if (warp == 0) {
+        const SdHdrRegs r = sd_tile_hdr_issue(P, key, lane);
+        sd_tile_hdr_finish<NC>(P, key, H, psi, lane, r);
+    } else if (warp == 1 && P.pf_dist > 0 && key + (uint64_t)P.pf_dist < P.key_hi) {
+        // L2 prefetch of the own tile and far neighbour tiles of the tile pf_dist keys ahead
+        SdTileHdr &Hp = *(SdTileHdr *)((char *)v.hdr + ((sizeof(SdTileHdr) + 15) & ~(size_t)15));
+        const uint64_t key2 = key + (uint64_t)P.pf_dist;
+        const SdHdrRegs r = sd_tile_hdr_issue(P, key2, lane);
+        sd_tile_hdr_finish<NC>(P, key2, Hp, psi, lane, r);
+        __syncwarp();
+        sd_tile_hdr_prefetch<NC>(P, Hp, psi, lane);
+    }
+    for (int i = (int)tid; i < (P.M + 1) * (P.M + 1); i += NTHR) v.binomM[i] = P.binomM[i];
+    // the first phase-2 item of this thread depends on js and tid only: prefetch it now
+    SdItem item0;
+    item0.c = 0xFFFFu;
+    {
+        const int js = P.k - __popcll(sd_tile_prefix_bits(key, P.A));
+        if (js >= 0 && js <= P.B && tid < P.js[js].nslots) item0 = P.items[P.js[js].item_off + tid];
+    }
     SD_TICK(0);
-    sd_tile_phase0b<NC>(P, key, v, psi, threadIdx.x, NTHR);
     __syncthreads();
     SD_TICK(1);
     const int slotmask = PLAIN ? 0 : sd_epi_slotmask(epi.red);
     double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
-    if (v.hdr->valid) {
-        sd_tile_phase1<NC>(P, v, psi, threadIdx.x, NTHR);
+    if (H.valid) {
+        sd_tile_phase1<NC>(P, v, psi, tid, NTHR);
         SD_TICK(2);                                       // thread 0's own phase-1 time
         __syncthreads();
         SD_TICK(3);                                       // wait for the slowest warp
-        sd_tile_phase2<NC, T>(P, v, threadIdx.x, NTHR, item0);
+        sd_tile_phase2<NC, T>(P, v, tid, NTHR, item0);
         SD_TICK(4);
         __syncthreads();
         SD_TICK(5);
-        sd_tile_phase3<NC, PLAIN>(P, v, out_vbase, epi, threadIdx.x, NTHR, red);
+        sd_tile_phase3<NC, PLAIN>(P, v, out_vbase, epi, tid, NTHR, red);
         SD_TICK(6);
     }
-    if (!PLAIN && slotmask) sd_block_reduce_store(red, slotmask, v.hdr->red, epi.partials, epi.nparts, blockIdx.x);
+    if (!PLAIN && slotmask) sd_block_reduce_store(red, slotmask, H.red, epi.partials, epi.nparts, blockIdx.x);
 }
 
 // ------------------------------------------------------------ generic apply
@@ -153,7 +172,7 @@ template <int NC>
 __global__ void __launch_bounds__(SD_GEN_THREADS)
 sd_generic_apply_kernel(const __grid_constant__ SdGenericParams G, const __grid_constant__ SdVecView psi,
                         double *out_local, const __grid_constant__ SdEpi epi) {
-    __shared__ double scratch[SD_NSLOT][32];
+    __shared__ double scratch[SD_NSLOT][16];
     const uint64_t lstart = G.shards.start[G.shards.rank];
     const uint64_t ln = G.shards.start[G.shards.rank + 1] - lstart;
     const bool full = G.k < 0;
@@ -231,7 +250,7 @@ template <int NCIN>
 __global__ void __launch_bounds__(SD_BLAS_THREADS)
 sd_szq_kernel(const __grid_constant__ SdSzqParams Z, uint64_t lstart, uint64_t ln, const double *psi0,
               double *phi, double *partials, unsigned nparts) {
-    __shared__ double scratch[SD_NSLOT][32];
+    __shared__ double scratch[SD_NSLOT][16];
     double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
     for (uint64_t li = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; li < ln;
          li += (uint64_t)gridDim.x * blockDim.x) {
@@ -324,7 +343,7 @@ template <int NC>
 __global__ void __launch_bounds__(SD_BLAS_THREADS)
 sd_axpy_kernel(double *y, uint64_t n, const __grid_constant__ SdScalar a, const double *x,
                const __grid_constant__ SdScalar b, const double *z, double *partials, unsigned nparts) {
-    __shared__ double scratch[SD_NSLOT][32];
+    __shared__ double scratch[SD_NSLOT][16];
     double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
     double ar, ai, br = 0.0, bi = 0.0;
     sd_load_scalar(a, ar, ai);
@@ -355,7 +374,7 @@ sd_axpy_kernel(double *y, uint64_t n, const __grid_constant__ SdScalar a, const 
 template <int NC>
 __global__ void __launch_bounds__(SD_BLAS_THREADS)
 sd_dot_kernel(const double *x, const double *y, uint64_t n, int conj, double *partials, unsigned nparts) {
-    __shared__ double scratch[SD_NSLOT][32];
+    __shared__ double scratch[SD_NSLOT][16];
     double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (uint64_t)gridDim.x * blockDim.x) {
@@ -377,7 +396,7 @@ template <int NC>
 __global__ void __launch_bounds__(SD_BLAS_THREADS)
 sd_lincomb_kernel(double *out, uint64_t n, const __grid_constant__ SdPtrBlock V, int m, const double *y /*dev, (re,im) pairs*/,
                   int accumulate, double *partials, unsigned nparts) {
-    __shared__ double scratch[SD_NSLOT][32];
+    __shared__ double scratch[SD_NSLOT][16];
     double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (uint64_t)gridDim.x * blockDim.x) {
@@ -404,7 +423,7 @@ sd_lincomb_kernel(double *out, uint64_t n, const __grid_constant__ SdPtrBlock V,
 __global__ void __launch_bounds__(SD_BLAS_THREADS)
 sd_lincomb_r2c_kernel(double *out, uint64_t n, const __grid_constant__ SdPtrBlock V, int m, const double *y,
                       int accumulate, double *partials, unsigned nparts) {
-    __shared__ double scratch[SD_NSLOT][32];
+    __shared__ double scratch[SD_NSLOT][16];
     double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (uint64_t)gridDim.x * blockDim.x) {

@@ -36,7 +36,7 @@
 #define SD_TILE_MAXNB 32      // prefix sites A <= 32
 #define SD_TILE_MAXT 6
 #define SD_TILE_MAXB 19     // suffix sites (tile = up to C(19,9) states would not fit smem anyway)
-#define SD_TILE_U(NC) ((NC) == 1 ? 13 : 6)  // elements per thread per phase-1 warp chunk
+#define SD_TILE_U(NC) ((NC) == 1 ? 7 : 3)   // elements per thread per phase-1 warp chunk (x3 tiles in flight)
 
 #if defined(__CUDA_ARCH__)
 #define SD_ATOMIC_OR(p, v) atomicOr(p, v)
@@ -70,6 +70,27 @@
     } while (0)
 #define SD_CP_ASYNC_WAIT_ALL() ((void)0)
 #define SD_PREFETCH_L2(p, bytes) ((void)(p))
+#endif
+
+// optional fine-grained cycle counters inside the phases (thread 0 only; -DSD_PHASE_TIMING)
+#if defined(SD_PHASE_TIMING) && defined(__CUDA_ARCH__)
+__device__ unsigned long long sd_phase_cycles[16];
+#define SD_PTICK_INIT() long long ptick_ = clock64()
+#define SD_PTICK(i)                                                             \
+    do {                                                                        \
+        if (threadIdx.x == 0) {                                                 \
+            const long long now_ = clock64();                                   \
+            atomicAdd(&sd_phase_cycles[i], (unsigned long long)(now_ - ptick_)); \
+            ptick_ = now_;                                                      \
+        }                                                                       \
+    } while (0)
+#elif defined(__CUDACC__)
+__device__ unsigned long long sd_phase_cycles[16];
+#define SD_PTICK_INIT() ((void)0)
+#define SD_PTICK(i) ((void)0)
+#else
+#define SD_PTICK_INIT() ((void)0)
+#define SD_PTICK(i) ((void)0)
 #endif
 
 // One phase-2 work item (a tail block), precomputed per (js, slot) on the host.
@@ -127,14 +148,17 @@ struct SdTileHdr {
     uint32_t cls_base[SD_TILE_MAXT + 2];
     SdNbEntry nbf[SD_TILE_MAXNB];    // compacted neighbour tiles of the active prefix-internal bonds
     SdNbEntry cross;                 // prefix|suffix crossing bond (ptr == null: inactive)
-    // per prefix position q: rank term, diagonal term, rank shift and element range of bond q
-    uint64_t t_base[SD_TILE_MAXNB];
-    double t_diag[SD_TILE_MAXNB];
+    // per prefix position q: rank shift and element range of bond q (crossing bond and slow path)
     int64_t t_off[SD_TILE_MAXNB];
     uint32_t t_lo[SD_TILE_MAXNB], t_hi[SD_TILE_MAXNB];
-    uint64_t pf_base[SD_TILE_MAXNB]; // rank terms of the tile that is being prefetched into L2
-    int64_t pf_off[SD_TILE_MAXNB];   // its far-bond shifts
-    double red[SD_NSLOT][32];
+    double red[SD_NSLOT][16];        // CTA reduction scratch (<= 16 warps)
+};
+
+// Scratch of the host-callable two-step header (sd_tile_phase0a/0b, CPU emulation only; the device
+// keeps these terms in registers of warp 0).
+struct SdTileScratch {
+    uint64_t t_base[SD_TILE_MAXNB];  // per prefix position: rank term
+    double t_diag[SD_TILE_MAXNB];    //                      diagonal term
 };
 
 template <int NC>
@@ -145,9 +169,10 @@ struct SdTileView {
     uint16_t *binomM;                // [(M+1)*(M+1)]
 };
 
+// smem: two headers (current tile / next tile of the persistent loop), psi tile, g/result tile, binomM
 SD_HD size_t sd_tile_smem_bytes(int NC, uint32_t cap, int M) {
     size_t b = sizeof(SdTileHdr);
-    b = (b + 15) & ~(size_t)15;
+    b = 2 * ((b + 15) & ~(size_t)15);
     b += (size_t)2 * cap * NC * sizeof(double);
     b += (size_t)(M + 1) * (M + 1) * sizeof(uint16_t);
     return (b + 15) & ~(size_t)15;
@@ -157,8 +182,8 @@ template <int NC>
 SD_HD SdTileView<NC> sd_tile_carve(void *smem, uint32_t cap) {
     SdTileView<NC> v;
     char *p = (char *)smem;
-    v.hdr = (SdTileHdr *)p;
-    p += (sizeof(SdTileHdr) + 15) & ~(size_t)15;
+    v.hdr = (SdTileHdr *)p;                               // second header follows the first
+    p += 2 * ((sizeof(SdTileHdr) + 15) & ~(size_t)15);
     v.spsi = (double *)p;
     p += (size_t)cap * NC * sizeof(double);
     v.sg = (double *)p;
@@ -197,7 +222,7 @@ SD_HD uint32_t sd_tile_active_mask(const SdTileParams &P, uint64_t Pb) {
 
 template <int NC>
 SD_HD void sd_tile_phase0a(const SdTileParams &P, uint64_t key, const SdTileView<NC> &v,
-                           unsigned tid, unsigned nthreads, SdItem &item0) {
+                           unsigned tid, unsigned nthreads, SdItem &item0, SdTileScratch &X) {
     SdTileHdr &H = *v.hdr;
     const int L = P.L, k = P.k, A = P.A, B = P.B, M = P.M, T = P.T;
     const uint64_t *C = P.binom;
@@ -210,31 +235,6 @@ SD_HD void sd_tile_phase0a(const SdTileParams &P, uint64_t key, const SdTileView
         H.mixed_mask = 0;
     }
     item0.c = 0xFFFFu;
-    // L2 prefetch for the tile pf_dist keys ahead: lanes 32.. compute its rank terms and far shifts
-    if (P.pf_dist > 0 && tid >= 32 && tid < 32u + (unsigned)A) {
-        const int q = (int)tid - 32;
-        const uint64_t key2 = key + (uint64_t)P.pf_dist;
-        uint64_t tb = 0;
-        int64_t off = 0;
-        if (key2 < P.key_hi) {
-            const uint64_t Pb2 = sd_tile_prefix_bits(key2, A);
-            const int js2 = k - SD_POPC64(Pb2);
-            if (js2 >= 0 && js2 <= B) {
-                const int bit = (int)((Pb2 >> q) & 1ULL);
-                const int below = SD_POPC64(Pb2 & ((1ULL << q) - 1));
-                tb = bit ? 0ULL : sd_binom_at(C, SD_BINOM_DIM, L - 1 - q, k - below - 1);
-                if (q < P.qfar && q + 1 < A) {
-                    const int bn = (int)((Pb2 >> (q + 1)) & 1ULL);
-                    if (bit != bn && P.Jhop[q] != 0.0) {
-                        const uint64_t dl = sd_binom_at(C, SD_BINOM_DIM, L - 2 - q, k - (below + bit + bn));
-                        off = bit ? (int64_t)dl : -(int64_t)dl;
-                    }
-                }
-            }
-        }
-        H.pf_base[q] = tb;
-        H.pf_off[q] = off;
-    }
     if (!valid) return;
     const SdJsInfo &I = P.js[js];
     const uint32_t size = I.size;
@@ -247,7 +247,7 @@ SD_HD void sd_tile_phase0a(const SdTileParams &P, uint64_t key, const SdTileView
         const int below = SD_POPC64(Pb & ((1ULL << q) - 1));             // set bits at positions < q
         const double sq = bit ? 0.5 : -0.5;
         double d = P.h[q] * sq;
-        H.t_base[q] = bit ? 0ULL : sd_binom_at(C, SD_BINOM_DIM, L - 1 - q, k - below - 1);
+        X.t_base[q] = bit ? 0ULL : sd_binom_at(C, SD_BINOM_DIM, L - 1 - q, k - below - 1);
         int64_t off = 0;
         uint32_t lo = 0, hi = 0;
         if (q + 1 < A) {                                                  // prefix-internal bond q
@@ -266,7 +266,7 @@ SD_HD void sd_tile_phase0a(const SdTileParams &P, uint64_t key, const SdTileView
                 off = -(int64_t)n1; lo = 0; hi = n1;
             }
         }
-        H.t_diag[q] = d;
+        X.t_diag[q] = d;
         H.t_off[q] = off; H.t_lo[q] = lo; H.t_hi[q] = hi;
     }
     for (int i = (int)tid; i < (M + 1) * (M + 1); i += (int)nthreads) v.binomM[i] = P.binomM[i];
@@ -275,31 +275,13 @@ SD_HD void sd_tile_phase0a(const SdTileParams &P, uint64_t key, const SdTileView
 
 template <int NC>
 SD_HD void sd_tile_phase0b(const SdTileParams &P, uint64_t key, const SdTileView<NC> &v,
-                           const SdVecView &psi, unsigned tid, unsigned nthreads) {
+                           const SdVecView &psi, unsigned tid, unsigned nthreads, const SdTileScratch &X) {
     SdTileHdr &H = *v.hdr;
     const int A = P.A;
-    // L2 prefetch of the own tile and the far neighbour tiles of key + pf_dist (local shard only)
-    if (P.pf_dist > 0 && tid >= 32 && tid <= 32u + (unsigned)P.qfar && tid <= 32u + (unsigned)A) {
-        const uint64_t key2 = key + (uint64_t)P.pf_dist;
-        if (key2 < P.key_hi) {
-            const int js2 = P.k - SD_POPC64(sd_tile_prefix_bits(key2, A));
-            if (js2 >= 0 && js2 <= P.B) {
-                uint64_t base2 = 0;
-                for (int q = 0; q < A; ++q) base2 += H.pf_base[q];
-                const int which = (int)tid - 32;                          // 0..qfar-1: far bond, qfar: own tile
-                const int64_t off = (which < P.qfar && which < A) ? H.pf_off[which] : 0;
-                if (which == P.qfar || off != 0) {
-                    const uint64_t r0 = (uint64_t)((int64_t)base2 + off);
-                    const int g = P.shards.world == 1 ? 0 : sd_owner(P.shards, r0);
-                    if (g == P.shards.rank) SD_PREFETCH_L2(psi.base[g] + (size_t)NC * r0, (size_t)NC * 8 * P.js[js2].size);
-                }
-            }
-        }
-    }
     if (!H.valid) return;
     if ((int)tid >= A && tid != 0) return;
     uint64_t base = 0;
-    for (int q = 0; q < A; ++q) base += H.t_base[q];
+    for (int q = 0; q < A; ++q) base += X.t_base[q];
     const uint64_t Pb = sd_tile_prefix_bits(key, A);
     const uint32_t act = sd_tile_active_mask(P, Pb);
     const uint32_t farbits = (P.qfar >= 32) ? ~0u : ((1u << P.qfar) - 1u);
@@ -307,7 +289,7 @@ SD_HD void sd_tile_phase0b(const SdTileParams &P, uint64_t key, const SdTileView
     const int nfar = SD_POPC32(act_far);
     if (tid == 0) {
         double dpre = 0.0;
-        for (int q = 0; q < A; ++q) dpre += H.t_diag[q];
+        for (int q = 0; q < A; ++q) dpre += X.t_diag[q];
         H.base = base;
         if (A > 0) {
             const double sl = ((Pb >> (A - 1)) & 1ULL) ? 0.5 : -0.5;
@@ -348,15 +330,178 @@ SD_HD void sd_tile_phase0b(const SdTileParams &P, uint64_t key, const SdTileView
     }
 }
 
+#if defined(__CUDACC__)
+// ---------------------------------------------------------------- tile header, device version
+// The kernel is persistent (one CTA walks tiles key, key+grid, ...), so the header of the NEXT tile
+// is computed by warp 0 in two halves around phase 1 of the current tile: sd_tile_hdr_issue starts
+// the two binomial loads of every prefix site, sd_tile_hdr_finish reduces them with shuffles and
+// writes the header.  The L2 latency of the lookups (~2000 cycles under load) hides behind phase 1.
+// Same arithmetic as the host-callable sd_tile_phase0a/0b used by the CPU emulation.
+struct SdHdrRegs {
+    uint64_t tb, dl;                                      // C(L-1-q, .) rank term, C(L-2-q, .) bond shift
+};
+__device__ __forceinline__ uint64_t sd_ldg_u64_pinned(const uint64_t *p) {
+    uint64_t x;
+    asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(x) : "l"(p) : "memory");
+    return x;
+}
+__device__ __forceinline__ uint64_t sd_warp_sum_u64(uint64_t x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+__device__ __forceinline__ double sd_warp_sum_f64(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+
+// warp 0, lane q = prefix position q
+__device__ __forceinline__ SdHdrRegs sd_tile_hdr_issue(const SdTileParams &P, uint64_t key, unsigned lane) {
+    SdHdrRegs r;
+    r.tb = 0; r.dl = 0;
+    const int L = P.L, k = P.k, A = P.A, q = (int)lane;
+    if (q >= A) return r;
+    const uint64_t Pb = sd_tile_prefix_bits(key, A);
+    const int js = k - __popcll(Pb);
+    if (js < 0 || js > P.B) return r;
+    const int bit = (int)((Pb >> q) & 1ULL);
+    const int below = __popcll(Pb & ((1ULL << q) - 1));
+    if (!bit) {
+        const int n = L - 1 - q, rr = k - below - 1;
+        if (rr >= 0 && rr <= n) r.tb = sd_ldg_u64_pinned(P.binom + n * SD_BINOM_DIM + rr);
+    }
+    if (q + 1 < A) {
+        const int bn = (int)((Pb >> (q + 1)) & 1ULL);
+        if (bit != bn && P.Jhop[q] != 0.0) {
+            const int n = L - 2 - q, rr = k - (below + bit + bn);
+            if (rr >= 0 && rr <= n) r.dl = sd_ldg_u64_pinned(P.binom + n * SD_BINOM_DIM + rr);
+        }
+    }
+    return r;
+}
+
+template <int NC>
+__device__ __forceinline__ void sd_tile_hdr_finish(const SdTileParams &P, uint64_t key, SdTileHdr &H,
+                                                   const SdVecView &psi, unsigned lane, const SdHdrRegs &r) {
+    const int k = P.k, A = P.A, B = P.B, T = P.T, q = (int)lane;
+    const uint64_t Pb = sd_tile_prefix_bits(key, A);
+    const int js = k - __popcll(Pb);
+    const bool valid = (js >= 0 && js <= B);
+    if (lane == 0) {
+        H.valid = valid ? 1 : 0;
+        H.js = js;
+        H.mixed_mask = 0;
+    }
+    if (!valid) return;
+    const SdJsInfo &I = P.js[js];
+    const uint32_t size = I.size;
+    if (lane == 0) {
+        H.size = size; H.nslots = I.nslots; H.item_off = I.item_off; H.perm_off = I.perm_off;
+    }
+    if (q <= T + 1) H.cls_base[q] = I.cls_base[q];
+    double d = 0.0;
+    int64_t off = 0;
+    uint32_t lo = 0, hi = 0;
+    if (q < A) {
+        const int bit = (int)((Pb >> q) & 1ULL);
+        const double sq = bit ? 0.5 : -0.5;
+        d = P.h[q] * sq;
+        if (q + 1 < A) {
+            const int bn = (int)((Pb >> (q + 1)) & 1ULL);
+            d += P.Jz[q] * sq * (bn ? 0.5 : -0.5);
+            if (bit != bn && P.Jhop[q] != 0.0) {
+                off = bit ? (int64_t)r.dl : -(int64_t)r.dl;
+                hi = size;
+            }
+        } else if (P.Jhop[q] != 0.0) {
+            const uint32_t n1 = I.n1;
+            if (bit) {
+                if (n1 < size) { off = (int64_t)I.ncross; lo = n1; hi = size; }
+            } else if (n1 > 0) {
+                off = -(int64_t)n1; lo = 0; hi = n1;
+            }
+        }
+        H.t_off[q] = off; H.t_lo[q] = lo; H.t_hi[q] = hi;
+    }
+    const uint64_t base = sd_warp_sum_u64(r.tb);
+    const double dpre = sd_warp_sum_f64(d);
+    const uint32_t act = sd_tile_active_mask(P, Pb);
+    const uint32_t farbits = (P.qfar >= 32) ? ~0u : ((1u << P.qfar) - 1u);
+    const uint32_t act_far = act & farbits, act_near = act & ~farbits;
+    const int nfar = __popc(act_far);
+    if (lane == 0) {
+        H.base = base;
+        if (A > 0) {
+            const double sl = ((Pb >> (A - 1)) & 1ULL) ? 0.5 : -0.5;
+            H.dP[0] = dpre + P.Jz[A - 1] * sl * (-0.5);
+            H.dP[1] = dpre + P.Jz[A - 1] * sl * (0.5);
+        } else {
+            H.dP[0] = H.dP[1] = dpre;
+            H.cross.ptr = nullptr;
+        }
+        H.nfar = nfar;
+        H.nfull = nfar + __popc(act_near);
+    }
+    if (q < A) {
+        SdNbEntry e;
+        e.ptr = nullptr;
+        e.J = P.Jhop[q];
+        if (hi > lo) {
+            int g0 = 0, g1 = 0;
+            if (P.shards.world != 1) {
+                g0 = sd_owner(P.shards, (uint64_t)((int64_t)(base + lo) + off));
+                g1 = sd_owner(P.shards, (uint64_t)((int64_t)(base + hi - 1) + off));
+            }
+            e.ptr = psi.base[g0] + (int64_t)NC * ((int64_t)base + off);
+            if (g0 != g1) {
+                atomicOr(&H.mixed_mask, 1u << q);
+                e.J = 0.0;
+                e.ptr = psi.base[P.shards.rank] + (int64_t)NC * (int64_t)base;
+            }
+        }
+        if (q + 1 < A) {
+            if (hi > lo) {
+                const uint32_t below = (1u << q) - 1u;
+                const int slot = ((farbits >> q) & 1u) ? __popc(act_far & below) : nfar + __popc(act_near & below);
+                H.nbf[slot] = e;
+            }
+        } else {
+            H.cross = e;                                  // ptr == null when the crossing bond is inactive
+        }
+    }
+}
+
+// warp 1: pull the own tile and the far neighbour tiles of an already finished header into L2
+template <int NC>
+__device__ __forceinline__ void sd_tile_hdr_prefetch(const SdTileParams &P, const SdTileHdr &H, const SdVecView &psi,
+                                                     unsigned lane) {
+    if (!H.valid) return;
+    const size_t bytes = (size_t)NC * 8 * H.size;
+    if ((int)lane < H.nfar) {
+        const double *p = H.nbf[lane].ptr;
+        const bool local = (P.shards.world == 1) ||
+            (p >= psi.base[P.shards.rank] + (size_t)NC * P.shards.start[P.shards.rank] &&
+             p < psi.base[P.shards.rank] + (size_t)NC * P.shards.start[P.shards.rank + 1]);
+        if (local) SD_PREFETCH_L2(p, bytes);
+    } else if ((int)lane == H.nfar) {
+        SD_PREFETCH_L2(psi.base[P.shards.rank] + (size_t)NC * H.base, bytes);
+    }
+}
+#endif
+
 // ---------------------------------------------------------------- phase 1
 // Warp-blocked mapping: a warp owns 32*U consecutive elements, a thread's U elements are 256 B
 // apart (element l0 + 32 u).  With the obvious CTA-strided mapping (elements 4 KB apart) all of a
 // thread's loads fall into the same L1 set and throughput stops scaling with U; measured on B200
 // (scripts/mb_streams.cu): 10 streams, 32 warps/SM: strided U=7 8.9 ms, U=13 11.0 ms; blocked U=13 7.2 ms.
-// The apply is bound by bytes in flight, so U is as large as the register file allows.
+//
+// The apply is bound by BYTES IN FLIGHT (Little's law): load destinations are registers and the
+// register file is shared with phase 2, so the partial sums g live in shared memory (where they
+// must end up anyway) and ALL landing registers hold loads: two neighbour tiles x U elements are in
+// flight per thread, then  sg[pos] (+)= J0 t0 + J1 t1.
 template <int NC, int CNT, bool FULL, bool FAR>
-SD_HD void sd_tile_gather(double (&g)[CNT][NC], const double *q, double J, const int32_t (&idx)[CNT]) {
-    double t[CNT][NC];
+SD_HD void sd_tile_issue(double (&t)[CNT][NC], const double *q, const int32_t (&idx)[CNT]) {
 #pragma unroll
     for (int u = 0; u < CNT; ++u)
 #pragma unroll
@@ -364,10 +509,51 @@ SD_HD void sd_tile_gather(double (&g)[CNT][NC], const double *q, double J, const
             const double *a = FULL ? q + (size_t)NC * 32 * u + c : q + (int64_t)NC * idx[u] + c;
             t[u][c] = FAR ? SD_LD_FAR(a) : SD_LD_NEAR(a);
         }
+}
+
+// one round: R neighbour tiles x CNT elements in flight, then sg[pos] (+)= sum_r J_r t_r
+template <int NC, int CNT, bool FULL, bool FAR, int R>
+SD_HD void sd_tile_round(double *sg, const uint32_t (&pos)[CNT], const int32_t (&idx)[CNT], uint32_t ok,
+                         const SdNbEntry *e, uint32_t l0, bool first) {
+    double t[R][CNT][NC];
+    double J[R];
 #pragma unroll
-    for (int u = 0; u < CNT; ++u)
+    for (int r = 0; r < R; ++r) {
+        const SdNbEntry er = e[r];
+        J[r] = er.J;
+        sd_tile_issue<NC, CNT, FULL, FAR>(t[r], er.ptr + (size_t)NC * l0, idx);
+    }
 #pragma unroll
-        for (int c = 0; c < NC; ++c) g[u][c] += J * t[u][c];
+    for (int u = 0; u < CNT; ++u) {
+        if (!FULL && !((ok >> u) & 1u)) continue;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            double s = J[0] * t[0][u][c];
+#pragma unroll
+            for (int r = 1; r < R; ++r) s += J[r] * t[r][u][c];
+            double *d = sg + (size_t)pos[u] * NC + c;
+            *d = first ? s : *d + s;
+        }
+    }
+}
+
+// entries e[0..n) of one cache policy, SD_TILE_EPR per round; `first` = sg not yet initialised
+template <int NC, int CNT, bool FULL, bool FAR>
+SD_HD void sd_tile_stream(double *sg, const uint32_t (&pos)[CNT], const int32_t (&idx)[CNT], uint32_t ok,
+                          const SdNbEntry *e, int n, uint32_t l0, bool &first) {
+    int i = 0;
+#pragma unroll 1
+    for (; i + 3 <= n; i += 3) {
+        sd_tile_round<NC, CNT, FULL, FAR, 3>(sg, pos, idx, ok, e + i, l0, first);
+        first = false;
+    }
+    if (n - i == 2) {
+        sd_tile_round<NC, CNT, FULL, FAR, 2>(sg, pos, idx, ok, e + i, l0, first);
+        first = false;
+    } else if (n - i == 1) {
+        sd_tile_round<NC, CNT, FULL, FAR, 1>(sg, pos, idx, ok, e + i, l0, first);
+        first = false;
+    }
 }
 
 // One warp chunk: elements l0 + 32 u, u < CNT.  FULL: every element of every lane is inside the tile
@@ -378,11 +564,14 @@ SD_HD void sd_tile_phase1_chunk(const SdTileParams &P, const SdTileView<NC> &v, 
     const SdTileHdr &H = *v.hdr;
     const uint32_t size = H.size;
     int32_t idx[CNT];                                     // element offset relative to l0 (clamped lanes: negative)
+    uint32_t ok = 0u;                                     // bit u: element u of this lane exists
 #pragma unroll
     for (int u = 0; u < CNT; ++u) {
         const uint32_t l = l0 + 32u * u;
         idx[u] = FULL ? 32 * u : (int32_t)(l < size ? l : size - 1) - (int32_t)l0;
+        if (FULL || l < size) ok |= 1u << u;
     }
+    SD_PTICK_INIT();
     const uint16_t *perm = P.perm + H.perm_off + l0;
     uint32_t pos[CNT];
 #pragma unroll
@@ -391,24 +580,22 @@ SD_HD void sd_tile_phase1_chunk(const SdTileParams &P, const SdTileView<NC> &v, 
         const double *own = psi.base[P.shards.rank] + (int64_t)NC * (int64_t)(H.base + l0);
 #pragma unroll
         for (int u = 0; u < CNT; ++u)
-            if (FULL || l0 + 32u * u < size) SD_CP_ASYNC(v.spsi + (size_t)pos[u] * NC, own + (int64_t)NC * idx[u], NC);
+            if (FULL || ((ok >> u) & 1u)) SD_CP_ASYNC(v.spsi + (size_t)pos[u] * NC, own + (int64_t)NC * idx[u], NC);
     }
-    double g[CNT][NC];
-#pragma unroll
-    for (int u = 0; u < CNT; ++u)
-#pragma unroll
-        for (int c = 0; c < NC; ++c) g[u][c] = 0.0;
+    SD_PTICK(8);                                          // perm round trip + cp.async issue
+    bool first = true;
     const int nfar = H.nfar, nfull = H.nfull;
-    int i = 0;
-#pragma unroll 1
-    for (; i < nfar; ++i) {
-        const SdNbEntry e = H.nbf[i];
-        sd_tile_gather<NC, CNT, FULL, true>(g, e.ptr + (size_t)NC * l0, e.J, idx);
-    }
-#pragma unroll 1
-    for (; i < nfull; ++i) {
-        const SdNbEntry e = H.nbf[i];
-        sd_tile_gather<NC, CNT, FULL, false>(g, e.ptr + (size_t)NC * l0, e.J, idx);
+    sd_tile_stream<NC, CNT, FULL, true>(v.sg, pos, idx, ok, H.nbf, nfar, l0, first);
+    SD_PTICK(9);                                          // far streams
+    sd_tile_stream<NC, CNT, FULL, false>(v.sg, pos, idx, ok, H.nbf + nfar, nfull - nfar, l0, first);
+    SD_PTICK(10);                                         // near streams
+    if (first) {                                          // no active prefix bond at all
+#pragma unroll
+        for (int u = 0; u < CNT; ++u)
+            if (FULL || ((ok >> u) & 1u)) {
+#pragma unroll
+                for (int c = 0; c < NC; ++c) v.sg[(size_t)pos[u] * NC + c] = 0.0;
+            }
     }
     const SdNbEntry ce = H.cross;                         // prefix|suffix crossing bond: sub-range [lo, hi)
     if (ce.ptr) {
@@ -420,10 +607,12 @@ SD_HD void sd_tile_phase1_chunk(const SdTileParams &P, const SdTileView<NC> &v, 
             const uint32_t l = l0 + 32u * u;
             if (l >= lo && l < hi) {
 #pragma unroll
-                for (int c = 0; c < NC; ++c) g[u][c] += ce.J * SD_LD_NEAR(q + (size_t)NC * 32 * u + c);
+                for (int c = 0; c < NC; ++c)
+                    v.sg[(size_t)pos[u] * NC + c] += ce.J * SD_LD_NEAR(q + (size_t)NC * 32 * u + c);
             }
         }
     }
+    SD_PTICK(11);                                         // crossing bond
     for (uint32_t mm = H.mixed_mask; mm; mm &= mm - 1) {  // neighbour range straddles a shard boundary (rare)
         int qq = 0;
         while (!((mm >> qq) & 1u)) ++qq;
@@ -437,16 +626,10 @@ SD_HD void sd_tile_phase1_chunk(const SdTileParams &P, const SdTileView<NC> &v, 
                 const uint64_t r = (uint64_t)((int64_t)(H.base + l) + off);
                 const double *q = psi.base[sd_owner(P.shards, r)] + (size_t)NC * r;
 #pragma unroll
-                for (int c = 0; c < NC; ++c) g[u][c] += J * q[c];
+                for (int c = 0; c < NC; ++c) v.sg[(size_t)pos[u] * NC + c] += J * q[c];
             }
         }
     }
-#pragma unroll
-    for (int u = 0; u < CNT; ++u)
-        if (FULL || l0 + 32u * u < size) {
-#pragma unroll
-            for (int c = 0; c < NC; ++c) v.sg[(size_t)pos[u] * NC + c] = g[u][c];
-        }
 }
 
 template <int NC>
@@ -459,7 +642,9 @@ SD_HD void sd_tile_phase1(const SdTileParams &P, const SdTileView<NC> &v, const 
         if (c0 + 32u * U <= size) sd_tile_phase1_chunk<NC, U, true>(P, v, psi, c0 + lane);
         else sd_tile_phase1_chunk<NC, U, false>(P, v, psi, c0 + lane);
     }
+    SD_PTICK_INIT();
     SD_CP_ASYNC_WAIT_ALL();                               // own-tile copies landed before the CTA barrier
+    SD_PTICK(12);
 }
 
 // ---------------------------------------------------------------- phase 2

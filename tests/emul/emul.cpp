@@ -22,8 +22,9 @@ static void run_tiles(const SdTileHost &th, SdTileParams P, const SdVecView &psi
         std::memset(sm, 0xA5, bytes);              // poison: catches reads of unwritten smem
         SdTileView<NC> v = sd_tile_carve<NC>(sm, th.cap_max);
         std::vector<SdItem> regs(nthreads);        // per-thread register held across phases
-        for (unsigned tid = 0; tid < nthreads; ++tid) sd_tile_phase0a<NC>(P, key, v, tid, nthreads, regs[tid]);
-        for (unsigned tid = 0; tid < nthreads; ++tid) sd_tile_phase0b<NC>(P, key, v, psi, tid, nthreads);
+        SdTileScratch scratch;
+        for (unsigned tid = 0; tid < nthreads; ++tid) sd_tile_phase0a<NC>(P, key, v, tid, nthreads, regs[tid], scratch);
+        for (unsigned tid = 0; tid < nthreads; ++tid) sd_tile_phase0b<NC>(P, key, v, psi, tid, nthreads, scratch);
         if (!v.hdr->valid) continue;
         for (unsigned tid = 0; tid < nthreads; ++tid) sd_tile_phase1<NC>(P, v, psi, tid, nthreads);
         for (unsigned tid = 0; tid < nthreads; ++tid)
