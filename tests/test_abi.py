@@ -13,7 +13,7 @@ from conftest import ROOT, sd
 def declared_symbols():
     src = open(os.path.join(ROOT, "include", "spindyn.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(sd_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(sd_[A-Za-z0-9_]+)\s*\(", src)))
 
 
 def test_library_loads_and_exports_every_declared_symbol():
