@@ -63,7 +63,8 @@ enum sd_status {
 /* Which apply kernel a model was routed to (sd_model_info). */
 enum sd_kernel_path {
     SD_PATH_GENERIC = 0,    /* one thread per state, arbitrary bond lists, full or sector  */
-    SD_PATH_TILED = 1       /* sector basis, open nearest-neighbour chain: smem-tiled gather */
+    SD_PATH_TILED = 1,      /* sector basis, open nearest-neighbour chain: smem-tiled gather */
+    SD_PATH_BLOCK = 2       /* same models, L >= 16: block-layout vectors, TMA tiles, no staging (default) */
 };
 
 const char *sd_last_error(void);

@@ -21,6 +21,8 @@
 #include "sd_tile.h"
 #include "sd_tile_host.h"
 #include "sd_kernels.cuh"
+#include "sd_blk.h"
+#include "sd_blk_host.h"
 
 #define SD_VERSION 100
 
@@ -113,6 +115,22 @@ struct sd_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint64_t launches = 0;
     std::vector<uint64_t> binom;
+    void *scratch[2] = {nullptr, nullptr};   // rank-ordered staging of block-layout vectors (upload/download/szq)
+    size_t scratch_cap[2] = {0, 0};
+};
+
+struct SdBlkDev {
+    bool ok = false;
+    SdBlkHost host;
+    uint64_t *d_W = nullptr;
+    SdBlkJs *d_js = nullptr;
+    uint16_t *d_units = nullptr;
+    SdBlkItem *d_items = nullptr;
+    double *d_dmid = nullptr;
+    uint64_t pstart[SD_MAX_WORLD + 1];
+    int nbuf[2] = {0, 0};
+    size_t smem[2] = {0, 0};
+    int qfar[2] = {0, 0};
 };
 
 struct SdTileDev {
@@ -140,12 +158,17 @@ struct sd_model {
     int tile_threads = 512;
     SdTileDev tile[2];              // [0]: F64, [1]: C128
     SdShardMap shards;
+    SdBlkDev blk;                   // block-layout kernel (sd_blk.h)
+    bool blk_layout = false;        // vectors of this model are stored in block layout
+    int live_vecs = 0;
 };
 
 struct sd_vec {
     sd_model *model = nullptr;
     int dtype = SD_F64, nc = 1;
-    uint64_t local_n = 0;
+    uint64_t local_n = 0;           // STORED elements of the local shard (block layout: padded)
+    uint64_t logical_n = 0;         // basis states of the local shard
+    int layout = 0;                 // 0: rank order, 1: block layout
     double *d = nullptr;
     SdVecView view;
     void *peer[SD_MAX_WORLD];
@@ -276,6 +299,7 @@ int sd_ctx_free(sd_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm) g_nccl.CommDestroy(c->comm);
     cudaFree(c->d_binom); cudaFree(c->d_scal); cudaFreeHost(c->h_scal); cudaFree(c->d_partials); cudaFree(c->d_ipc);
+    cudaFree(c->scratch[0]); cudaFree(c->scratch[1]);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -367,6 +391,68 @@ static int sd_tile_setup(sd_model *m, int which, int B) {
     return SD_OK;
 }
 
+static int sd_scratch(sd_ctx *c, int which, size_t bytes, double **p) {
+    if (bytes > c->scratch_cap[which]) {
+        if (c->scratch[which]) { SD_CUDA(cudaStreamSynchronize(c->stream)); SD_CUDA(cudaFree(c->scratch[which])); c->scratch[which] = nullptr; c->scratch_cap[which] = 0; }
+        cudaError_t e = cudaMalloc(&c->scratch[which], bytes);
+        if (e != cudaSuccess) return sd_fail(SD_ERR_NOMEM, "cudaMalloc of %zu staging bytes failed: %s", bytes, cudaGetErrorString(e));
+        c->scratch_cap[which] = bytes;
+    }
+    *p = (double *)c->scratch[which];
+    return SD_OK;
+}
+static void sd_scratch_release(sd_ctx *c) {          // staging is only kept while it is small
+    for (int w = 0; w < 2; ++w)
+        if (c->scratch_cap[w] > ((size_t)256 << 20)) {
+            cudaStreamSynchronize(c->stream);
+            cudaFree(c->scratch[w]); c->scratch[w] = nullptr; c->scratch_cap[w] = 0;
+        }
+}
+
+// block-layout kernel tables (sd_blk.h); needs the tiled tables too (same tile keys: B = 15)
+static int sd_blk_setup(sd_model *m) {
+    SdBlkDev &b = m->blk;
+    b.ok = false;
+    const int L = m->L;
+    if (!m->tile_capable || m->tile[0].host.P.B != SD_BLK_B || L - SD_BLK_B < 1) return SD_OK;
+    std::vector<double> Jhop(L + 1, 0.0), Jz(L + 1, 0.0);
+    for (size_t i = 0; i < m->hop_a.size(); ++i) Jhop[m->hop_a[i]] += m->hop_J[i];
+    for (size_t i = 0; i < m->zz_a.size(); ++i) Jz[m->zz_a[i]] += m->zz_J[i];
+    if (!sd_blk_build(L, m->k, Jhop.data(), Jz.data(), m->field.data(), b.host)) return SD_OK;
+    for (int w = 0; w < 2; ++w) {
+        const int nc = w + 1;
+        int nbuf = sd_env_int(w == 0 ? "SD_BLK_NBUF" : "SD_BLK_NBUF_C128", w == 0 ? 3 : 2);
+        for (; nbuf >= 2; --nbuf) {
+            b.smem[w] = sd_blk_smem_carve(nullptr, nullptr, b.host.P.A, L, nbuf, b.host.P.cap, nc);
+            if (b.smem[w] <= 227 * 1024) break;
+        }
+        if (nbuf < 2) return SD_OK;
+        b.nbuf[w] = nbuf;
+        b.qfar[w] = sd_tile_qfar(L, b.host.P.A, b.host.binom.data(), (uint64_t)sd_env_int("SD_FAR_MB", 100) << 20, 8 * nc);
+    }
+    SD_TRY(sd_to_device(&b.d_W, b.host.W));
+    SD_TRY(sd_to_device(&b.d_js, b.host.js));
+    SD_TRY(sd_to_device(&b.d_units, b.host.units));
+    SD_TRY(sd_to_device(&b.d_items, b.host.items));
+    SD_TRY(sd_to_device(&b.d_dmid, b.host.dmid));
+    SdBlkParams &P = b.host.P;
+    P.W = b.d_W; P.js = b.d_js; P.units = b.d_units; P.items = b.d_items; P.dmid = b.d_dmid;
+    b.ok = true;
+    return SD_OK;
+}
+// parameters of a launch on this rank's shard
+static SdBlkParams sd_blk_params(const sd_model *m, int nc) {
+    SdBlkParams P = m->blk.host.P;
+    const sd_ctx *c = m->ctx;
+    P.nbuf = m->blk.nbuf[nc - 1];
+    P.dbg = sd_env_int("SD_BLK_DBG", 0);
+    P.key_lo = m->tile[0].keys[c->rank];
+    P.key_hi = m->tile[0].keys[c->rank + 1];
+    P.shards.world = c->world; P.shards.rank = c->rank;
+    for (int g = 0; g <= SD_MAX_WORLD; ++g) P.shards.pstart[g] = m->blk.pstart[std::min(g, c->world)];
+    return P;
+}
+
 int sd_model_create(sd_ctx *ctx, int L, int nup, const sd_bond *hop, int nhop, const sd_bond *zz, int nzz,
                     const double *field, sd_model **model) {
     SD_ARG(ctx && model, "NULL argument");
@@ -450,6 +536,10 @@ int sd_model_create(sd_ctx *ctx, int L, int nup, const sd_bond *hop, int nhop, c
         m->tile_capable = m->tile[0].ok && m->tile[1].ok;
     }
     m->path = m->tile_capable ? SD_PATH_TILED : SD_PATH_GENERIC;
+    if (m->tile_capable && sd_env_int("SD_BLK", 1)) {
+        SD_TRY(sd_blk_setup(m));
+        if (m->blk.ok) m->path = SD_PATH_BLOCK;
+    }
     // shards: tile-aligned to the coarser (F64) tiling when tiled, plain equal split otherwise
     uint64_t bounds[SD_MAX_WORLD + 1];
     if (m->tile_capable) {
@@ -465,6 +555,9 @@ int sd_model_create(sd_ctx *ctx, int L, int nup, const sd_bond *hop, int nhop, c
     }
     m->shards.world = ctx->world; m->shards.rank = ctx->rank;
     for (int g = 0; g <= SD_MAX_WORLD; ++g) m->shards.start[g] = bounds[std::min(g, ctx->world)];
+    if (m->blk.ok)
+        for (int g = 0; g <= ctx->world; ++g) m->blk.pstart[g] = sd_blk_key_base(m->blk.host, m->tile[0].keys[g]);
+    m->blk_layout = (m->path == SD_PATH_BLOCK);
     *model = m;
     return SD_OK;
 }
@@ -480,6 +573,7 @@ int sd_model_free(sd_model *m) {
         SdTileDev &t = m->tile[w];
         cudaFree(t.d_perm); cudaFree(t.d_items); cudaFree(t.d_binomM);
     }
+    cudaFree(m->blk.d_W); cudaFree(m->blk.d_js); cudaFree(m->blk.d_units); cudaFree(m->blk.d_items); cudaFree(m->blk.d_dmid);
     delete m;
     return SD_OK;
 }
@@ -513,11 +607,22 @@ int sd_model_info(const sd_model *m, int *kernel_path, int *tile_sites, int *ran
 }
 int sd_model_set_path(sd_model *m, int kernel_path) {
     SD_ARG(m, "NULL argument");
-    if (kernel_path == SD_PATH_GENERIC) { m->path = SD_PATH_GENERIC; return SD_OK; }
+    // the block kernel works on block-layout vectors, the other two on rank-ordered ones: the
+    // layout can only change while no vector of the model is alive
+    const bool want_blk = kernel_path == SD_PATH_BLOCK;
+    if (want_blk != m->blk_layout && m->live_vecs > 0)
+        return sd_fail(SD_ERR_UNSUPPORTED, "cannot switch between the block kernel and the rank-ordered kernels while %d vectors of the model are alive", m->live_vecs);
+    if (kernel_path == SD_PATH_GENERIC) { m->path = SD_PATH_GENERIC; m->blk_layout = false; return SD_OK; }
     if (kernel_path == SD_PATH_TILED) {
         if (!m->tile_capable)
             return sd_fail(SD_ERR_UNSUPPORTED, "model does not qualify for the tiled kernel (sector basis, nearest-neighbour bonds, L >= 10)");
-        m->path = SD_PATH_TILED;
+        m->path = SD_PATH_TILED; m->blk_layout = false;
+        return SD_OK;
+    }
+    if (kernel_path == SD_PATH_BLOCK) {
+        if (!m->blk.ok)
+            return sd_fail(SD_ERR_UNSUPPORTED, "model does not qualify for the block kernel (sector basis, nearest-neighbour bonds, L >= 16)");
+        m->path = SD_PATH_BLOCK; m->blk_layout = true;
         return SD_OK;
     }
     return sd_fail(SD_ERR_ARG, "unknown kernel path %d", kernel_path);
@@ -577,8 +682,11 @@ int sd_vec_alloc(sd_model *m, int dtype, sd_vec **vec) {
     sd_vec *v = new (std::nothrow) sd_vec;
     if (!v) return sd_fail(SD_ERR_NOMEM, "out of host memory");
     v->model = m; v->dtype = dtype; v->nc = dtype == SD_C128 ? 2 : 1;
-    const uint64_t ls = m->shards.start[c->rank];
-    v->local_n = m->shards.start[c->rank + 1] - ls;
+    v->layout = m->blk_layout ? 1 : 0;
+    const uint64_t *starts = v->layout ? m->blk.pstart : m->shards.start;
+    const uint64_t ls = starts[c->rank];
+    v->local_n = starts[c->rank + 1] - ls;
+    v->logical_n = m->shards.start[c->rank + 1] - m->shards.start[c->rank];
     for (int g = 0; g < SD_MAX_WORLD; ++g) { v->peer[g] = nullptr; v->view.base[g] = nullptr; }
     // +2 elements of slack so 16-byte vector accesses at the ends stay inside the allocation
     const size_t bytes = (size_t)(v->local_n + 2) * v->nc * sizeof(double);
@@ -587,7 +695,12 @@ int sd_vec_alloc(sd_model *m, int dtype, sd_vec **vec) {
         delete v;
         return sd_fail(SD_ERR_NOMEM, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
     }
+    if (v->layout) {                                  // block layout: padding must be (and stays) zero
+        e = cudaMemsetAsync(v->d, 0, bytes, c->stream);
+        if (e != cudaSuccess) { cudaFree(v->d); delete v; return sd_fail(SD_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e)); }
+    }
     v->view.base[c->rank] = v->d - (int64_t)ls * v->nc;
+    m->live_vecs++;
     if (c->world > 1) {
         // collective: exchange CUDA IPC handles, map every peer shard
         cudaIpcMemHandle_t hnd;
@@ -603,7 +716,7 @@ int sd_vec_alloc(sd_model *m, int dtype, sd_vec **vec) {
             void *p = nullptr;
             SD_CUDA(cudaIpcOpenMemHandle(&p, all[g], cudaIpcMemLazyEnablePeerAccess));
             v->peer[g] = p;
-            v->view.base[g] = (const double *)p - (int64_t)m->shards.start[g] * v->nc;
+            v->view.base[g] = (const double *)p - (int64_t)starts[g] * v->nc;
         }
     }
     *vec = v;
@@ -618,6 +731,7 @@ int sd_vec_free(sd_vec *v) {
         if (v->peer[g]) cudaIpcCloseMemHandle(v->peer[g]);
     if (c->world > 1) sd_rank_barrier(c), cudaStreamSynchronize(c->stream);   // peers unmapped before the free
     if (v->owned) cudaFree(v->d);
+    v->model->live_vecs--;
     delete v;
     return SD_OK;
 }
@@ -628,15 +742,40 @@ int sd_vec_dtype(const sd_vec *v, int *dtype) {
 }
 int sd_vec_local_len(const sd_vec *v, uint64_t *n) {
     SD_ARG(v && n, "NULL argument");
-    *n = v->local_n;
+    *n = v->logical_n;
     return SD_OK;
 }
 static inline size_t sd_vec_bytes(const sd_vec *v) { return (size_t)v->local_n * v->nc * sizeof(double); }
+static inline size_t sd_vec_logical_bytes(const sd_vec *v) { return (size_t)v->logical_n * v->nc * sizeof(double); }
+// block layout <-> rank order on the local shard.  dir 0: blk := rank-ordered (or seeded values), 1: rank-ordered := blk
+static int sd_blk_permute(const sd_vec *v, double *rank_local, int nc_rank, int dir, int seeded, uint64_t seed, double scale) {
+    sd_model *m = v->model;
+    sd_ctx *c = m->ctx;
+    SdBlkParams P = sd_blk_params(m, v->nc);
+    const uint64_t nkeys = P.key_hi - P.key_lo;
+    if (nkeys == 0) return SD_OK;
+    SdBlkPermute Q;
+    Q.dir = dir; Q.nc_blk = v->nc; Q.nc_rank = nc_rank; Q.seeded = seeded; Q.seed = seed; Q.scale = scale;
+    Q.rstart = m->shards.start[c->rank];
+    Q.binom = c->d_binom;
+    const unsigned grid = (unsigned)std::min<uint64_t>(nkeys, (uint64_t)c->sm_count * 16);
+    sd_blk_permute_kernel<<<grid, 256, 0, c->stream>>>(P, Q, v->d, rank_local);
+    return sd_launch_check(c, "sd_blk_permute_kernel");
+}
 
 int sd_vec_upload(sd_vec *v, const void *host) {
     SD_ARG(v && host, "NULL argument");
     sd_ctx *c = v->model->ctx;
     SD_TRY(sd_use(c));
+    if (v->layout) {
+        double *st = nullptr;
+        SD_TRY(sd_scratch(c, 0, sd_vec_logical_bytes(v) + 16, &st));
+        SD_CUDA(cudaMemcpyAsync(st, host, sd_vec_logical_bytes(v), cudaMemcpyHostToDevice, c->stream));
+        SD_TRY(sd_blk_permute(v, st, v->nc, 0, 0, 0, 0.0));
+        SD_CUDA(cudaStreamSynchronize(c->stream));
+        sd_scratch_release(c);
+        return SD_OK;
+    }
     SD_CUDA(cudaMemcpyAsync(v->d, host, sd_vec_bytes(v), cudaMemcpyHostToDevice, c->stream));
     SD_CUDA(cudaStreamSynchronize(c->stream));
     return SD_OK;
@@ -645,6 +784,15 @@ int sd_vec_download(sd_vec *v, void *host) {
     SD_ARG(v && host, "NULL argument");
     sd_ctx *c = v->model->ctx;
     SD_TRY(sd_use(c));
+    if (v->layout) {
+        double *st = nullptr;
+        SD_TRY(sd_scratch(c, 1, sd_vec_logical_bytes(v) + 16, &st));
+        SD_TRY(sd_blk_permute(v, st, v->nc, 1, 0, 0, 0.0));
+        SD_CUDA(cudaMemcpyAsync(host, st, sd_vec_logical_bytes(v), cudaMemcpyDeviceToHost, c->stream));
+        SD_CUDA(cudaStreamSynchronize(c->stream));
+        sd_scratch_release(c);
+        return SD_OK;
+    }
     SD_CUDA(cudaMemcpyAsync(host, v->d, sd_vec_bytes(v), cudaMemcpyDeviceToHost, c->stream));
     SD_CUDA(cudaStreamSynchronize(c->stream));
     return SD_OK;
@@ -653,6 +801,12 @@ int sd_vec_upload_async(sd_vec *v, const void *host) {
     SD_ARG(v && host, "NULL argument");
     sd_ctx *c = v->model->ctx;
     SD_TRY(sd_use(c));
+    if (v->layout) {
+        double *st = nullptr;
+        SD_TRY(sd_scratch(c, 0, sd_vec_logical_bytes(v) + 16, &st));
+        SD_CUDA(cudaMemcpyAsync(st, host, sd_vec_logical_bytes(v), cudaMemcpyHostToDevice, c->stream));
+        return sd_blk_permute(v, st, v->nc, 0, 0, 0, 0.0);
+    }
     SD_CUDA(cudaMemcpyAsync(v->d, host, sd_vec_bytes(v), cudaMemcpyHostToDevice, c->stream));
     return SD_OK;
 }
@@ -660,6 +814,13 @@ int sd_vec_download_async(sd_vec *v, void *host) {
     SD_ARG(v && host, "NULL argument");
     sd_ctx *c = v->model->ctx;
     SD_TRY(sd_use(c));
+    if (v->layout) {
+        double *st = nullptr;
+        SD_TRY(sd_scratch(c, 1, sd_vec_logical_bytes(v) + 16, &st));
+        SD_TRY(sd_blk_permute(v, st, v->nc, 1, 0, 0, 0.0));
+        SD_CUDA(cudaMemcpyAsync(host, st, sd_vec_logical_bytes(v), cudaMemcpyDeviceToHost, c->stream));
+        return SD_OK;
+    }
     SD_CUDA(cudaMemcpyAsync(host, v->d, sd_vec_bytes(v), cudaMemcpyDeviceToHost, c->stream));
     return SD_OK;
 }
@@ -685,8 +846,14 @@ int sd_vec_set_onehot(sd_vec *v, uint64_t idx0) {
     sd_ctx *c = v->model->ctx;
     SD_TRY(sd_vec_zero(v));
     const uint64_t ls = v->model->shards.start[c->rank];
-    if (idx0 >= ls && idx0 < ls + v->local_n) {
-        sd_set_one_kernel<<<1, 1, 0, c->stream>>>(v->d, (idx0 - ls) * v->nc);
+    if (idx0 >= ls && idx0 < ls + v->logical_n) {
+        uint64_t off = idx0 - ls;
+        if (v->layout) {
+            const sd_model *m = v->model;
+            const uint64_t st = sd_unrank_state(idx0, m->L, m->k, c->binom.data(), SD_BINOM_DIM);
+            off = sd_blk_pos_of_state(m->blk.host, st) - m->blk.pstart[c->rank];
+        }
+        sd_set_one_kernel<<<1, 1, 0, c->stream>>>(v->d, off * v->nc);
         SD_TRY(sd_launch_check(c, "sd_set_one_kernel"));
     }
     return SD_OK;
@@ -696,6 +863,7 @@ int sd_vec_fill_seeded(sd_vec *v, uint64_t seed, double scale) {
     sd_ctx *c = v->model->ctx;
     SD_TRY(sd_use(c));
     if (v->local_n == 0) return SD_OK;
+    if (v->layout) return sd_blk_permute(v, nullptr, v->nc, 0, 1, seed, scale);
     sd_fill_seeded_kernel<<<sd_blas_grid(c, v->local_n), SD_BLAS_THREADS, 0, c->stream>>>(
         v->d, v->nc, v->model->shards.start[c->rank], v->local_n, seed, scale);
     return sd_launch_check(c, "sd_fill_seeded_kernel");
@@ -827,7 +995,38 @@ static int sd_apply_impl(sd_model *m, sd_vec *out, const sd_vec *psi, SdEpi epi,
     SD_TRY(sd_rank_barrier(c));
     const int nc = psi->nc;
     const int slotmask = sd_epi_slotmask(epi.red);
-    if (m->path == SD_PATH_TILED) {
+    SD_ARG(out->layout == psi->layout && psi->layout == (m->path == SD_PATH_BLOCK ? 1 : 0),
+           "vector layout does not match the model's kernel path");
+    if (m->path == SD_PATH_BLOCK) {
+        SdBlkParams P = sd_blk_params(m, nc);
+        const uint64_t nkeys = P.key_hi - P.key_lo;
+        if (nkeys == 0) return SD_OK;
+        SD_ARG(nkeys < 0x7fffffffULL, "too many tiles for one launch");
+        const unsigned grid = (unsigned)std::min<uint64_t>(nkeys, (uint64_t)c->sm_count);
+        if (slotmask) {
+            SD_TRY(sd_partials_reserve(c, (size_t)SD_NSLOT * nkeys));
+            SD_CUDA(cudaMemsetAsync(c->d_partials, 0, (size_t)SD_NSLOT * nkeys * sizeof(double), c->stream));
+        }
+        epi.partials = c->d_partials;
+        epi.nparts = (unsigned)nkeys;
+        const size_t smem = m->blk.smem[nc - 1];
+        const int qfar = m->blk.qfar[nc - 1];
+        const bool plain = epi.mode == SD_EPI_PLAIN && epi.red == 0 && !epi.acc && epi.hscale == 1.0;
+#define SD_LAUNCH_BLK(NC_, PLAIN_)                                                                           \
+    do {                                                                                                     \
+        static size_t set_smem = 0;                                                                          \
+        if (smem > set_smem) {                                                                               \
+            SD_CUDA(cudaFuncSetAttribute(sd_blk_apply_kernel<NC_, PLAIN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            set_smem = smem;                                                                                 \
+        }                                                                                                    \
+        sd_blk_apply_kernel<NC_, PLAIN_><<<grid, SD_BLK_THREADS, smem, c->stream>>>(P, psi->view, out->d, epi, qfar); \
+    } while (0)
+        if (nc == 1) { if (plain) SD_LAUNCH_BLK(1, true); else SD_LAUNCH_BLK(1, false); }
+        else { if (plain) SD_LAUNCH_BLK(2, true); else SD_LAUNCH_BLK(2, false); }
+#undef SD_LAUNCH_BLK
+        SD_TRY(sd_launch_check(c, "sd_blk_apply_kernel"));
+        if (slotmask) SD_TRY(sd_finish_reduce(c, (unsigned)nkeys, slotmask, slot_out));
+    } else if (m->path == SD_PATH_TILED) {
         SdTileDev &t = m->tile[nc - 1];
         SdTileParams P = t.host.P;
         P.shards = m->shards;
@@ -881,7 +1080,7 @@ static int sd_apply_impl(sd_model *m, sd_vec *out, const sd_vec *psi, SdEpi epi,
         G.zz_a = m->d_zz_a; G.zz_b = m->d_zz_b; G.zz_J = m->d_zz_J; G.field = m->d_field;
         G.binom = c->d_binom; G.lin_h = m->lin_h; G.linA = m->d_linA; G.linB = m->d_linB;
         G.shards = m->shards;
-        uint64_t g64 = (psi->local_n + SD_GEN_THREADS - 1) / SD_GEN_THREADS;
+        uint64_t g64 = (psi->logical_n + SD_GEN_THREADS - 1) / SD_GEN_THREADS;
         g64 = std::max<uint64_t>(1, std::min<uint64_t>(g64, (uint64_t)c->sm_count * 16));
         const unsigned g = (unsigned)g64;
         if (slotmask) SD_TRY(sd_partials_reserve(c, (size_t)SD_NSLOT * g));
@@ -961,13 +1160,28 @@ int sd_szq(sd_model *m, sd_vec *phi, const sd_vec *psi0, double q, double *norm2
     SdSzqParams Z;
     Z.L = m->L; Z.k = m->k; Z.normfact = 1.0 / sqrt((double)m->L); Z.binom = c->d_binom;
     for (int r = 0; r < m->L; ++r) { Z.ph_re[r] = cos(q * (double)r); Z.ph_im[r] = sin(q * (double)r); }
-    const unsigned g = sd_blas_grid(c, phi->local_n);
+    const unsigned g = sd_blas_grid(c, phi->logical_n);
     double *partials = nullptr;
     if (norm2) { SD_TRY(sd_partials_reserve(c, (size_t)SD_NSLOT * g)); partials = c->d_partials; }
     const uint64_t ls = m->shards.start[c->rank];
-    if (psi0->nc == 2) sd_szq_kernel<2><<<g, SD_BLAS_THREADS, 0, c->stream>>>(Z, ls, phi->local_n, psi0->d, phi->d, partials, g);
-    else sd_szq_kernel<1><<<g, SD_BLAS_THREADS, 0, c->stream>>>(Z, ls, phi->local_n, psi0->d, phi->d, partials, g);
-    SD_TRY(sd_launch_check(c, "sd_szq_kernel"));
+    const double *src = psi0->d;
+    double *dst = phi->d;
+    if (phi->layout) {                               // block layout: the state of an element comes from its rank,
+        double *s0 = nullptr, *s1 = nullptr;         // so run on rank-ordered staging copies (not a hot path)
+        SD_TRY(sd_scratch(c, 0, sd_vec_logical_bytes(psi0) + 16, &s0));
+        SD_TRY(sd_scratch(c, 1, sd_vec_logical_bytes(phi) + 16, &s1));
+        SD_TRY(sd_blk_permute(psi0, s0, psi0->nc, 1, 0, 0, 0.0));
+        src = s0; dst = s1;
+    }
+    if (phi->logical_n > 0) {
+        if (psi0->nc == 2) sd_szq_kernel<2><<<g, SD_BLAS_THREADS, 0, c->stream>>>(Z, ls, phi->logical_n, src, dst, partials, g);
+        else sd_szq_kernel<1><<<g, SD_BLAS_THREADS, 0, c->stream>>>(Z, ls, phi->logical_n, src, dst, partials, g);
+        SD_TRY(sd_launch_check(c, "sd_szq_kernel"));
+    }
+    if (phi->layout) {
+        SD_TRY(sd_blk_permute(phi, dst, 2, 0, 0, 0, 0.0));
+        sd_scratch_release(c);
+    }
     if (norm2) {
         SD_TRY(sd_finish_reduce(c, g, 8, 0));
         double r[4];

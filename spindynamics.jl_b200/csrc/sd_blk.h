@@ -1,0 +1,716 @@
+// sd_blk.h -- the "block layout" H.psi kernel for the sector basis of an open
+// nearest-neighbour chain (reference Hamiltonian.jl:211-273 restricted to the bond
+// lists XXZChain builds, SpinModel.jl:63-90; arbitrary per-bond J/Jz, per-site field).
+//
+// Device vectors of a block-layout model are NOT stored in rank order.  The chain is
+// cut into  prefix (A sites) | mid (M sites) | tail (T sites); a TILE is one prefix
+// configuration (a contiguous rank range of the reference basis, Basis.jl:37-53).
+// Inside a tile the suffix configurations are stored
+//     class-major (class jt = tail popcount), element-major (e = index of the tail
+//     configuration inside its class), mid-configuration fastest (u = index of the mid
+//     configuration among those with js - jt set bits),
+// every (jt, e) row padded to a multiple of 4 elements and every tile to a multiple of
+// 16 elements (padding is zero and stays zero under every linear operation).  With this
+// order
+//   * a hop on a prefix bond maps a whole tile onto another whole tile, element by
+//     element: one thread that owns mid configuration u streams  acc[e] += J psi'[e][u]
+//     with fully coalesced 16-byte loads (lanes = consecutive u), no staging;
+//   * the tile itself is copied verbatim into shared memory by one TMA bulk copy
+//     (cp.async.bulk + mbarrier), so hops on suffix bonds are shared-memory gathers;
+//   * tail-internal hops are register moves fixed at compile time;
+//   * the result is stored straight from registers, again coalesced 16-byte stores.
+// There is no flat phase, no permutation table and no CTA barrier in the steady state:
+// consumer warps pull (tile, unit) work items from a per-tile counter, a producer warp
+// computes tile headers and keeps NBUF tiles in flight.
+//
+// f64: a lane owns two adjacent mid configurations (a double2 = blocks u, u+1).
+// c128: a lane owns one mid configuration (a double2 = re, im).  H is real, so both are
+// "two independent real columns" for everything but the gather addresses.
+#pragma once
+#include "sd_common.h"
+
+#define SD_BLK_M 10
+#define SD_BLK_T 5
+#define SD_BLK_B (SD_BLK_M + SD_BLK_T)
+#define SD_BLK_NCLS (SD_BLK_T + 1)
+#define SD_BLK_MAXA 32
+#define SD_BLK_MAXUNITS 32      // units per tile: sum_jt ceil(pitch/64) <= 17 (f64), sum_jt ceil(pitch/32) <= 32 (c128)
+#define SD_BLK_THREADS 512
+#define SD_BLK_CWARPS 15        // consumer warps; warp 15 is the producer
+
+struct SdBlkCls {
+    uint32_t cb;         // element offset of the class inside the tile
+    uint32_t pitch;      // row pitch (elements) = nblk rounded up to 4
+    uint32_t nblk;       // mid configurations in the class = C(M, js - jt)
+    uint32_t n1;         // of which the first mid bit is set = C(M-1, js - jt - 1)
+    uint32_t item_off;   // first SdBlkItem of the class
+    uint32_t pad_;
+};
+struct SdBlkJs {
+    uint32_t size;       // C(B, js) real elements
+    uint32_t size_pad;   // stored elements (multiple of 16)
+    uint32_t nunits[2];  // units per tile, [0]: f64 (64 blocks per unit), [1]: c128 (32 blocks per unit)
+    SdBlkCls cls[SD_BLK_NCLS];
+};
+// one mid configuration of one class
+struct alignas(16) SdBlkItem {
+    uint8_t nb[12];      // nb[pm]: class-local index of c with mid bits pm, pm+1 swapped; 0xFF = parallel
+    uint16_t c;          // mid configuration bits
+    uint16_t u2x;        // class-local index (in class jt +- 1) of c with its last bit flipped
+};
+
+struct SdBlkShards {
+    int world, rank;
+    uint64_t pstart[SD_MAX_WORLD + 1];   // stored-element offset of each shard (tile aligned)
+};
+
+struct SdBlkParams {
+    int L, k, A;
+    int nbuf;                        // tile buffers in shared memory
+    uint64_t key_lo, key_hi;         // tile keys of this launch (this shard)
+    double Jhop[SD_MAX_L + 1];       // hop coefficient of bond p (positions p, p+1)
+    double Jz[SD_MAX_L + 1];
+    double h[SD_MAX_L + 1];
+    double dtail[1 << SD_BLK_T];     // diag of the tail sites + tail-internal zz, by tail bits
+    const uint64_t *W;               // [A*(A+1)] stored elements of all tiles "1 at q, `below` ones before"
+    const SdBlkJs *js;               // [B+1]
+    const uint16_t *units;           // [2][(B+1)*MAXUNITS]: jt << 8 | unit-in-class, heavy classes first
+    const SdBlkItem *items;
+    const double *dmid;              // [1 << M] diag of the mid sites + mid-internal zz
+    uint32_t cap;                    // largest size_pad
+    int dbg;                         // profiling switches (SD_BLK_DBG): 1 skip prefix streams, 2 skip suffix hops, 4 skip store
+    SdBlkShards shards;
+};
+
+SD_HD int sd_blk_owner(const SdBlkShards &m, uint64_t p) {
+    int g = 0;
+#pragma unroll
+    for (int i = 1; i < SD_MAX_WORLD; ++i) g += (i < m.world && p >= m.pstart[i]) ? 1 : 0;
+    return g;
+}
+
+// prefix bits of tile `key`: keys enumerate prefixes in rank order ("1 first").
+SD_HD uint64_t sd_blk_prefix_bits(uint64_t key, int A) {
+    uint64_t Pb = 0;
+    for (int q = 0; q < A; ++q)
+        if (!((key >> (A - 1 - q)) & 1ULL)) Pb |= 1ULL << q;
+    return Pb;
+}
+
+#if defined(__CUDACC__)
+// ------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ unsigned sd_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sd_mbar_init(uint64_t *b, unsigned cnt) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sd_smem_u32(b)), "r"(cnt) : "memory");
+}
+__device__ __forceinline__ void sd_mbar_expect_tx(uint64_t *b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sd_smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sd_mbar_arrive(uint64_t *b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sd_smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void sd_mbar_wait(uint64_t *b, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "SD_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra SD_DONE_%=;\n"
+        "bra SD_WAIT_%=;\n"
+        "SD_DONE_%=:\n"
+        "}" ::"r"(sd_smem_u32(b)), "r"(parity) : "memory");
+}
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (16-byte aligned, size % 16 == 0)
+__device__ __forceinline__ void sd_bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(sd_smem_u32(dst)), "l"(src), "r"(bytes), "r"(sd_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void sd_bulk_prefetch_l2(const void *src, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ double2 sd_ldg_v2(const double *p) {
+    double2 v;
+    asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double2 sd_ldg_v2_far(const double *p) {
+    double2 v;
+    asm("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void sd_stg_v2(double *p, double2 v) {
+    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+
+// ------------------------------------------------------------------ tile header
+struct SdBlkHdr {
+    uint64_t base;                       // stored-element offset of the tile (global, all shards)
+    int js, jsx;                         // suffix popcount of the tile / of the crossing partner tile
+    int valid;                           // 1: tile, -1: end of this CTA's tile list
+    int nnb, nfar;                       // active prefix-internal bonds; the first nfar are beyond L2 reach
+    int bP;                              // last prefix bit
+    unsigned next_unit;                  // work counter of the consumer warps
+    unsigned done_units;                 // finished units (the warp that finishes the last one sums usum[] in order)
+    unsigned tile_index;                 // key - key_lo (slot of the per-tile partial sums)
+    double dP[2];                        // prefix diag + prefix|mid zz, by first mid bit
+    double Jx;                           // hop coefficient of the prefix|mid bond (0: none)
+    const double *xptr;                  // stored base of the crossing partner tile (component 0)
+    const double *nb_ptr[SD_BLK_MAXA];   // stored bases of the neighbour tiles of the active prefix bonds
+    double nb_J[SD_BLK_MAXA];
+    double usum[SD_NSLOT][SD_BLK_MAXUNITS];   // per-unit reduction results (deterministic: summed in unit order)
+};
+
+// warp-wide: lane q = prefix position q.  W[q*(A+1) + below] lives in shared memory.
+template <int NC>
+__device__ __forceinline__ void sd_blk_make_hdr(const SdBlkParams &P, const uint64_t *W, uint64_t key, SdBlkHdr &H,
+                                                const SdVecView &psi, int qfar, unsigned lane) {
+    const int A = P.A, k = P.k, q = (int)lane;
+    const uint64_t Pb = __brevll(~key) >> (64 - A);               // A >= 1
+    const int js = k - __popcll(Pb);
+    const int bit = (int)((Pb >> q) & 1ULL), bn = (int)((Pb >> (q + 1)) & 1ULL);
+    const int below = __popcll(Pb & ((1ULL << q) - 1ULL));
+    uint64_t term = 0, wq = 0, wn = 0;
+    double d = 0.0;
+    bool act = false;
+    if (q < A) {
+        wq = W[q * (A + 1) + below];
+        if (!bit) term = wq;
+        const double sq = bit ? 0.5 : -0.5;
+        d = P.h[q] * sq;
+        if (q + 1 < A) {
+            d += P.Jz[q] * sq * (bn ? 0.5 : -0.5);
+            act = (bit != bn) && (P.Jhop[q] != 0.0);
+            if (act) wn = W[(q + 1) * (A + 1) + below + 1];
+        }
+    }
+    uint64_t base = term;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) base += __shfl_xor_sync(0xffffffffu, base, o);
+    double dpre = d;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dpre += __shfl_xor_sync(0xffffffffu, dpre, o);
+    const unsigned actmask = __ballot_sync(0xffffffffu, act);
+    const unsigned farmask = (qfar >= 32) ? 0xffffffffu : ((1u << qfar) - 1u);
+    const int nfar = __popc(actmask & farmask);
+    if (act) {
+        // (1,0) -> (0,1): + (W[q][below] - W[q+1][below+1]);  (0,1) -> (1,0): the negative
+        const uint64_t dl = wq - wn;
+        const uint64_t nbase = bit ? base + dl : base - dl;
+        const unsigned lt = (1u << q) - 1u;
+        const int slot = ((farmask >> q) & 1u) ? __popc(actmask & farmask & lt) : nfar + __popc(actmask & ~farmask & lt);
+        H.nb_ptr[slot] = psi.base[sd_blk_owner(P.shards, nbase)] + (size_t)NC * nbase;
+        H.nb_J[slot] = P.Jhop[q];
+    }
+    if (q == A - 1) {                                             // prefix|mid crossing bond
+        const int jsx = bit ? js + 1 : js - 1;
+        const double J = P.Jhop[q];
+        const bool ok = (J != 0.0) && jsx >= 0 && jsx <= SD_BLK_B;
+        const uint64_t nbase = bit ? base + wq : base - wq;
+        H.jsx = jsx;
+        H.Jx = ok ? J : 0.0;
+        H.xptr = ok ? psi.base[sd_blk_owner(P.shards, nbase)] + (size_t)NC * nbase : nullptr;
+        H.bP = bit;
+        const double sl = bit ? 0.5 : -0.5;
+        H.dP[0] = dpre + P.Jz[q] * sl * (-0.5);
+        H.dP[1] = dpre + P.Jz[q] * sl * (0.5);
+    }
+    if (lane == 0) {
+        H.base = base;
+        H.js = js;
+        H.valid = 1;
+        H.nnb = __popc(actmask);
+        H.nfar = nfar;
+        H.next_unit = 0;
+        H.done_units = 0;
+        H.tile_index = (unsigned)(key - P.key_lo);
+    }
+}
+
+// ------------------------------------------------------------------ per-unit body
+// compile-time tables of the tail block of class (T, JT): see sd_common.h
+template <int NT>
+struct SdV2Arr {
+    double2 v[NT];
+};
+
+template <int JT, int t, int q>
+struct SdBlkTailHop {
+    static constexpr int NT = sd_cbinom(SD_BLK_T, JT);
+    static __device__ __forceinline__ void run(double2 (&acc)[NT], const double2 (&own)[NT], const double *Jt) {
+        constexpr unsigned cfg = sd_tail_cfg(SD_BLK_T, JT, t);
+        constexpr bool act = (((cfg >> q) ^ (cfg >> (q + 1))) & 1u) != 0;
+        if constexpr (act) {
+            constexpr int t2 = sd_tail_rank(SD_BLK_T, JT, cfg ^ (3u << q));
+            const double J = Jt[q];
+            acc[t].x += J * own[t2].x;
+            acc[t].y += J * own[t2].y;
+        }
+        if constexpr (q + 2 < SD_BLK_T) SdBlkTailHop<JT, t, q + 1>::run(acc, own, Jt);
+    }
+};
+template <int JT, int t>
+struct SdBlkTailRow {
+    static constexpr int NT = sd_cbinom(SD_BLK_T, JT);
+    static __device__ __forceinline__ void run(double2 (&acc)[NT], const double2 (&own)[NT], const double *Jt,
+                                               const double *dtail, double d0, double d1, double dx0, double dx1) {
+        constexpr unsigned cfg = sd_tail_cfg(SD_BLK_T, JT, t);
+        const double dt = dtail[cfg];
+        // + dx when tail bit 0 equals the last mid bit (dx already carries the sign of the last mid bit)
+        acc[t].x += (d0 + dt + ((cfg & 1u) ? dx0 : -dx0)) * own[t].x;
+        acc[t].y += (d1 + dt + ((cfg & 1u) ? dx1 : -dx1)) * own[t].y;
+        SdBlkTailHop<JT, t, 0>::run(acc, own, Jt);
+        if constexpr (t + 1 < NT) SdBlkTailRow<JT, t + 1>::run(acc, own, Jt, dtail, d0, d1, dx0, dx1);
+    }
+};
+
+struct SdBlkCtx {
+    const SdBlkParams *P;
+    const SdBlkJs *js;          // shared-memory copy [B+1]
+    const double *dmid;         // shared-memory copy [1 << M]
+    const double *dtail;        // shared-memory copy
+    const double *Jhop;         // shared-memory copy [L]
+    double qx;                  // Jz of the mid|tail bond * 0.25
+    double *out_local;          // local shard of out, component 0 of stored element 0
+    uint64_t pstart_local;      // stored-element offset of the local shard
+    const SdEpi *epi;
+};
+
+// One unit: lanes own BPL = 2/NC adjacent mid configurations ub + sb of class JT (all C(T,JT) tail
+// configurations each).  tb = shared-memory copy of the tile.
+template <int NC, int JT, bool PLAIN>
+__device__ __forceinline__ void sd_blk_unit(const SdBlkCtx &X, const SdBlkHdr &H, const double *tb, uint32_t ub,
+                                            double (&red)[SD_NSLOT]) {
+    constexpr int T = SD_BLK_T, M = SD_BLK_M;
+    constexpr int NT = sd_cbinom(T, JT);
+    constexpr int BPL = 2 / NC;
+    const SdBlkParams &P = *X.P;
+    const SdBlkJs &I = X.js[H.js];
+    const SdBlkCls cls = I.cls[JT];
+    if (ub >= cls.pitch) return;
+    const size_t off0 = (size_t)(cls.cb + ub) * NC;
+    const size_t es = (size_t)cls.pitch * NC;
+    // work items of the lane's blocks (L2-resident table), issued before the streams
+    SdBlkItem it[BPL];
+    bool have[BPL];
+#pragma unroll
+    for (int sb = 0; sb < BPL; ++sb) {
+        have[sb] = ub + sb < cls.nblk;
+        const uint4 raw = have[sb] ? __ldg((const uint4 *)(P.items + cls.item_off + ub + sb)) : make_uint4(~0u, ~0u, ~0u, 0u);
+        *(uint4 *)&it[sb] = raw;
+    }
+    double2 acc[NT];
+#pragma unroll
+    for (int e = 0; e < NT; ++e) acc[e] = make_double2(0.0, 0.0);
+    // ---- prefix-internal bonds: whole neighbour tiles, same element order
+    if (!(P.dbg & 1)) {
+        const int nfar = H.nfar, nnb = H.nnb;
+#pragma unroll 1
+        for (int n = 0; n < nfar; ++n) {
+            const double *p = H.nb_ptr[n] + off0;
+            const double J = H.nb_J[n];
+            double2 t[NT];
+#pragma unroll
+            for (int e = 0; e < NT; ++e) t[e] = sd_ldg_v2_far(p + e * es);
+#pragma unroll
+            for (int e = 0; e < NT; ++e) { acc[e].x += J * t[e].x; acc[e].y += J * t[e].y; }
+        }
+#pragma unroll 1
+        for (int n = nfar; n < nnb; ++n) {
+            const double *p = H.nb_ptr[n] + off0;
+            const double J = H.nb_J[n];
+            double2 t[NT];
+#pragma unroll
+            for (int e = 0; e < NT; ++e) t[e] = sd_ldg_v2(p + e * es);
+#pragma unroll
+            for (int e = 0; e < NT; ++e) { acc[e].x += J * t[e].x; acc[e].y += J * t[e].y; }
+        }
+    }
+    // ---- prefix|mid crossing bond: partner tile with js +- 1, same class, uniform block shift
+    if (H.xptr) {
+        const SdBlkCls cx = X.js[H.jsx].cls[JT];
+        const double J = H.Jx;
+#pragma unroll
+        for (int sb = 0; sb < BPL; ++sb) {
+            const uint32_t u = ub + sb;
+            const bool c0 = u < cls.n1;                            // first mid bit (blocks with it set come first)
+            if (have[sb] && (c0 != (bool)H.bP)) {
+                const uint32_t u2 = H.bP ? u - cls.n1 : cx.n1 + u;
+                const double *p = H.xptr + (size_t)(cx.cb + u2) * NC;
+                const size_t xs = (size_t)cx.pitch * NC;
+                if (NC == 2) {
+#pragma unroll
+                    for (int e = 0; e < NT; ++e) {
+                        const double2 t = sd_ldg_v2(p + e * xs);
+                        acc[e].x += J * t.x; acc[e].y += J * t.y;
+                    }
+                } else {
+                    double t[NT];
+#pragma unroll
+                    for (int e = 0; e < NT; ++e) t[e] = __ldg(p + e * xs);
+#pragma unroll
+                    for (int e = 0; e < NT; ++e) { if (sb == 0) acc[e].x += J * t[e]; else acc[e].y += J * t[e]; }
+                }
+            }
+        }
+    }
+    // ---- own block: diagonal + tail-internal hops (registers)
+    {
+        double2 own[NT];
+#pragma unroll
+        for (int e = 0; e < NT; ++e) own[e] = *(const double2 *)(tb + off0 + e * es);
+        double d[2], dx[2];
+#pragma unroll
+        for (int sb = 0; sb < 2; ++sb) {
+            const int s = (NC == 2) ? 0 : sb;
+            const unsigned c = it[s].c & ((1u << M) - 1u);
+            const bool c0 = (ub + s) < cls.n1;
+            d[sb] = H.dP[c0 ? 1 : 0] + X.dmid[c];
+            dx[sb] = ((c >> (M - 1)) & 1u) ? X.qx : -X.qx;
+        }
+        SdBlkTailRow<JT, 0>::run(acc, own, X.Jhop + P.A + M, X.dtail, d[0], d[1], dx[0], dx[1]);
+    }
+    // ---- mid-internal hops: the whole block moves to block nb[pm] of the same class
+    if (!(P.dbg & 2)) {
+        const double *cbp = tb + (size_t)cls.cb * NC;
+#pragma unroll
+        for (int pm = 0; pm + 1 < M; ++pm) {
+            const double J = X.Jhop[P.A + pm];
+#pragma unroll
+            for (int sb = 0; sb < BPL; ++sb) {
+                const unsigned nbu = it[sb].nb[pm];
+                if (nbu != 0xFFu) {
+                    const double *sp = cbp + (size_t)nbu * NC;
+#pragma unroll
+                    for (int e = 0; e < NT; ++e) {
+                        if (NC == 2) {
+                            const double2 t = *(const double2 *)(sp + e * es);
+                            acc[e].x += J * t.x; acc[e].y += J * t.y;
+                        } else {
+                            const double t = sp[e * es];
+                            if (sb == 0) acc[e].x += J * t; else acc[e].y += J * t;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // ---- mid|tail crossing bond
+    {
+        const double J = X.Jhop[P.A + M - 1];
+        constexpr int n1 = sd_cbinom(T - 1, JT - 1);               // tail configurations with first bit 1
+#pragma unroll
+        for (int sb = 0; sb < BPL; ++sb) {
+            if (!have[sb]) continue;
+            const unsigned c = it[sb].c;
+            const unsigned u2 = it[sb].u2x;
+            if ((c >> (M - 1)) & 1u) {
+                if constexpr (JT < T && NT - n1 > 0) {             // tail bit 0 clear -> class JT+1, first part
+                    const SdBlkCls c2 = I.cls[JT + 1];
+                    const double *sp = tb + (size_t)(c2.cb + u2) * NC;
+                    const size_t s2 = (size_t)c2.pitch * NC;
+#pragma unroll
+                    for (int e = n1; e < NT; ++e) {
+                        if (NC == 2) {
+                            const double2 t = *(const double2 *)(sp + (e - n1) * s2);
+                            acc[e].x += J * t.x; acc[e].y += J * t.y;
+                        } else {
+                            const double t = sp[(e - n1) * s2];
+                            if (sb == 0) acc[e].x += J * t; else acc[e].y += J * t;
+                        }
+                    }
+                }
+            } else {
+                if constexpr (JT > 0 && n1 > 0) {                  // tail bit 0 set -> class JT-1, second part
+                    constexpr int n1p = sd_cbinom(T - 1, JT - 2);
+                    const SdBlkCls c2 = I.cls[JT - 1];
+                    const double *sp = tb + (size_t)(c2.cb + u2) * NC;
+                    const size_t s2 = (size_t)c2.pitch * NC;
+#pragma unroll
+                    for (int e = 0; e < n1; ++e) {
+                        if (NC == 2) {
+                            const double2 t = *(const double2 *)(sp + (n1p + e) * s2);
+                            acc[e].x += J * t.x; acc[e].y += J * t.y;
+                        } else {
+                            const double t = sp[(n1p + e) * s2];
+                            if (sb == 0) acc[e].x += J * t; else acc[e].y += J * t;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // ---- epilogue + store
+    const uint64_t li0 = H.base - X.pstart_local + cls.cb + ub;    // local stored element of (e = 0, ub)
+    double *o = X.out_local + (size_t)li0 * NC;
+    if (PLAIN) {
+        if (P.dbg & 4) { if (acc[0].x == 1.2345e300) sd_stg_v2(o, acc[0]); return; }
+#pragma unroll
+        for (int e = 0; e < NT; ++e) sd_stg_v2(o + e * es, acc[e]);
+    } else {
+        const SdEpi &E = *X.epi;
+#pragma unroll
+        for (int e = 0; e < NT; ++e) {
+            const double2 p = *(const double2 *)(tb + off0 + e * es);
+            double2 r;
+            if (NC == 2) {
+                SdVal<2> hh, pp;
+                hh.c[0] = acc[e].x; hh.c[1] = acc[e].y; pp.c[0] = p.x; pp.c[1] = p.y;
+                const SdVal<2> rr = sd_epilogue<2>(E, hh, pp, li0 + (uint64_t)e * cls.pitch, red);
+                r = make_double2(rr.c[0], rr.c[1]);
+            } else {
+                SdVal<1> hh, pp;
+                hh.c[0] = acc[e].x; pp.c[0] = p.x;
+                const SdVal<1> r0 = sd_epilogue<1>(E, hh, pp, li0 + (uint64_t)e * cls.pitch, red);
+                hh.c[0] = acc[e].y; pp.c[0] = p.y;
+                const SdVal<1> r1 = sd_epilogue<1>(E, hh, pp, li0 + (uint64_t)e * cls.pitch + 1, red);
+                r = make_double2(r0.c[0], r1.c[0]);
+            }
+            *(double2 *)(o + e * es) = r;
+        }
+    }
+}
+
+template <int NC, bool PLAIN, int JT>
+struct SdBlkDispatch {
+    static __device__ __forceinline__ void run(const SdBlkCtx &X, const SdBlkHdr &H, const double *tb, int jt, uint32_t ub,
+                                               double (&red)[SD_NSLOT]) {
+        if (jt == JT) sd_blk_unit<NC, JT, PLAIN>(X, H, tb, ub, red);
+        else if constexpr (JT > 0) SdBlkDispatch<NC, PLAIN, JT - 1>::run(X, H, tb, jt, ub, red);
+    }
+};
+
+// shared-memory carve-up
+struct SdBlkSmem {
+    uint64_t *full, *empty;      // [nbuf] mbarriers
+    SdBlkHdr *hdr;               // [nbuf]
+    uint64_t *W;                 // [A*(A+1)]
+    SdBlkJs *js;                 // [B+1]
+    uint16_t *units;             // [(B+1)*MAXUNITS]
+    double *dmid;                // [1 << M]
+    double *dtail;               // [1 << T]
+    double *Jhop;                // [L + 1]
+    double *tiles;               // [nbuf][cap*NC]
+};
+SD_HD size_t sd_blk_smem_carve(SdBlkSmem *s, void *base, int A, int L, int nbuf, uint32_t cap, int NC) {
+    size_t o = 0;
+    auto take = [&](size_t bytes, size_t align) {
+        o = (o + align - 1) & ~(align - 1);
+        const size_t at = o;
+        o += bytes;
+        return at;
+    };
+    const size_t a_full = take(8 * (size_t)nbuf, 8), a_empty = take(8 * (size_t)nbuf, 8);
+    const size_t a_hdr = take(sizeof(SdBlkHdr) * (size_t)nbuf, 16);
+    const size_t a_W = take(8 * (size_t)A * (A + 1) + 8, 8);
+    const size_t a_js = take(sizeof(SdBlkJs) * (SD_BLK_B + 1), 16);
+    const size_t a_units = take(2 * (size_t)(SD_BLK_B + 1) * SD_BLK_MAXUNITS, 4);
+    const size_t a_dmid = take(8 * ((size_t)1 << SD_BLK_M), 16);
+    const size_t a_dtail = take(8 * ((size_t)1 << SD_BLK_T), 16);
+    const size_t a_J = take(8 * (size_t)(L + 1), 16);
+    const size_t a_tiles = take((size_t)nbuf * cap * NC * 8, 128);
+    if (s) {
+        char *b = (char *)base;
+        s->full = (uint64_t *)(b + a_full); s->empty = (uint64_t *)(b + a_empty);
+        s->hdr = (SdBlkHdr *)(b + a_hdr); s->W = (uint64_t *)(b + a_W); s->js = (SdBlkJs *)(b + a_js);
+        s->units = (uint16_t *)(b + a_units); s->dmid = (double *)(b + a_dmid); s->dtail = (double *)(b + a_dtail);
+        s->Jhop = (double *)(b + a_J); s->tiles = (double *)(b + a_tiles);
+    }
+    return (o + 127) & ~(size_t)127;
+}
+
+// ------------------------------------------------------------------ the kernel
+// grid = one persistent CTA per SM; CTA c walks tile keys key_lo + c, + grid, ...
+// partials: [SD_NSLOT][ntiles] per-tile sums (zero-filled by the host before the launch: invalid tiles
+// write nothing); each is the in-order sum of the tile's per-unit sums, so results are run-to-run identical.
+template <int NC, bool PLAIN>
+__global__ void __launch_bounds__(SD_BLK_THREADS, 1)
+sd_blk_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constant__ SdVecView psi, double *out_local,
+                    const __grid_constant__ SdEpi epi, int qfar) {
+    extern __shared__ __align__(128) unsigned char sd_blk_smem[];
+    SdBlkSmem S;
+    sd_blk_smem_carve(&S, sd_blk_smem, P.A, P.L, P.nbuf, P.cap, NC);
+    const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+    const int nbuf = P.nbuf;
+    // ---- one-time setup
+    for (int i = (int)tid; i < P.A * (P.A + 1); i += SD_BLK_THREADS) S.W[i] = P.W[i];
+    {
+        const uint32_t *src = (const uint32_t *)P.js;
+        uint32_t *dst = (uint32_t *)S.js;
+        for (int i = (int)tid; i < (int)(sizeof(SdBlkJs) * (SD_BLK_B + 1) / 4); i += SD_BLK_THREADS) dst[i] = src[i];
+    }
+    for (int i = (int)tid; i < (SD_BLK_B + 1) * SD_BLK_MAXUNITS; i += SD_BLK_THREADS)
+        S.units[i] = P.units[(NC - 1) * (SD_BLK_B + 1) * SD_BLK_MAXUNITS + i];
+    for (int i = (int)tid; i < (1 << SD_BLK_M); i += SD_BLK_THREADS) S.dmid[i] = P.dmid[i];
+    for (int i = (int)tid; i < (1 << SD_BLK_T); i += SD_BLK_THREADS) S.dtail[i] = P.dtail[i];
+    for (int i = (int)tid; i <= P.L; i += SD_BLK_THREADS) S.Jhop[i] = P.Jhop[i];
+    if (tid == 0) {
+        for (int b = 0; b < nbuf; ++b) { sd_mbar_init(&S.full[b], 1); sd_mbar_init(&S.empty[b], SD_BLK_CWARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const size_t tile_doubles = (size_t)P.cap * NC;
+
+    if (warp == SD_BLK_CWARPS) {
+        // ================= producer warp: headers + TMA of the own tiles
+        uint64_t key = P.key_lo + blockIdx.x;
+        for (unsigned i = 0;; ++i) {
+            const int b = (int)(i % (unsigned)nbuf);
+            const unsigned round = i / (unsigned)nbuf;
+            // skip prefixes whose suffix popcount is impossible
+            while (key < P.key_hi) {
+                const uint64_t Pb = __brevll(~key) >> (64 - P.A);
+                const int js = P.k - __popcll(Pb);
+                if (js >= 0 && js <= SD_BLK_B) break;
+                key += gridDim.x;
+            }
+            sd_mbar_wait(&S.empty[b], (round & 1u) ^ 1u);          // consumers released this buffer
+            SdBlkHdr &H = S.hdr[b];
+            if (key >= P.key_hi) {
+                if (lane == 0) { H.valid = -1; }
+                __syncwarp();
+                if (lane == 0) sd_mbar_arrive(&S.full[b]);
+                break;
+            }
+            sd_blk_make_hdr<NC>(P, S.W, key, H, psi, qfar, lane);
+            __syncwarp();
+            const uint32_t bytes = S.js[H.js].size_pad * (uint32_t)(NC * 8);
+            const char *src = (const char *)(psi.base[P.shards.rank] + (size_t)NC * H.base);
+            char *dst = (char *)(S.tiles + (size_t)b * tile_doubles);
+            if (lane == 0) sd_mbar_expect_tx(&S.full[b], bytes);
+            __syncwarp();
+            constexpr uint32_t CH = 8192;
+            for (uint32_t o = lane * CH; o < bytes; o += 32 * CH)
+                sd_bulk_g2s(dst + o, src + o, (bytes - o < CH) ? bytes - o : CH, &S.full[b]);
+            key += gridDim.x;
+        }
+    } else {
+        // ================= consumer warps
+        SdBlkCtx X;
+        X.P = &P; X.js = S.js; X.dmid = S.dmid; X.dtail = S.dtail; X.Jhop = S.Jhop;
+        X.qx = P.Jz[P.A + SD_BLK_M - 1] * 0.25;
+        X.pstart_local = P.shards.pstart[P.shards.rank];
+        X.out_local = out_local;
+        X.epi = &epi;
+        constexpr unsigned UW = 32u * (2 / NC);                    // blocks per unit
+        const int slotmask = PLAIN ? 0 : sd_epi_slotmask(epi.red);
+        for (unsigned i = 0;; ++i) {
+            const int b = (int)(i % (unsigned)nbuf);
+            const unsigned round = i / (unsigned)nbuf;
+            sd_mbar_wait(&S.full[b], round & 1u);
+            SdBlkHdr &H = S.hdr[b];
+            if (H.valid < 0) break;
+            const double *tb = S.tiles + (size_t)b * tile_doubles;
+            const unsigned nunits = S.js[H.js].nunits[NC - 1];
+            const uint16_t *ut = S.units + H.js * SD_BLK_MAXUNITS;
+            for (;;) {
+                unsigned un = 0;
+                if (lane == 0) un = atomicAdd(&H.next_unit, 1u);
+                un = __shfl_sync(0xffffffffu, un, 0);
+                if (un >= nunits) break;
+                const unsigned code = ut[un];
+                const int jt = (int)(code >> 8);
+                const uint32_t ub = (code & 0xFFu) * UW + lane * (2 / NC);
+                double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
+                SdBlkDispatch<NC, PLAIN, SD_BLK_T>::run(X, H, tb, jt, ub, red);
+                if (!PLAIN && slotmask) {
+#pragma unroll
+                    for (int s = 0; s < SD_NSLOT; ++s) {
+                        if (!((slotmask >> s) & 1)) continue;
+                        double w = red[s];
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) w += __shfl_down_sync(0xffffffffu, w, o);
+                        if (lane == 0) H.usum[s][un] = w;
+                    }
+                    if (lane == 0) {
+                        __threadfence_block();
+                        const unsigned done = atomicAdd(&H.done_units, 1u);
+                        if (done + 1 == nunits) {                  // last unit of the tile: ordered sum
+                            __threadfence_block();
+                            for (int s = 0; s < SD_NSLOT; ++s) {
+                                if (!((slotmask >> s) & 1)) continue;
+                                double t = 0.0;
+                                for (unsigned j = 0; j < nunits; ++j) t += ((volatile double *)H.usum[s])[j];
+                                epi.partials[(size_t)s * epi.nparts + H.tile_index] = t;
+                            }
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) sd_mbar_arrive(&S.empty[b]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ layout conversion
+// dir 0: blk[pos] = rankvec[rank]   (scatter a rank-ordered vector into block layout, padding := 0)
+// dir 1: rankvec[rank] = blk[pos]
+// One CTA per tile (grid-stride).  rank_local points at the local shard of the rank-ordered vector
+// (element r - rstart), blk_local at the local shard of the block-layout vector.
+// seeded != 0: dir 0 writes scale*sd_seeded_value(seed (+c), rank) instead of reading rankvec.
+struct SdBlkPermute {
+    int dir, nc_blk, nc_rank, seeded;
+    uint64_t seed;
+    double scale;
+    uint64_t rstart;             // first rank of the local shard
+    const uint64_t *binom;       // [65*65]
+};
+__global__ void __launch_bounds__(256) sd_blk_permute_kernel(const __grid_constant__ SdBlkParams P, SdBlkPermute Q,
+                                                             double *blk_local, double *rank_local) {
+    __shared__ uint64_t s_base[2];
+    const int A = P.A, k = P.k, L = P.L;
+    for (uint64_t key = P.key_lo + blockIdx.x; key < P.key_hi; key += gridDim.x) {
+        const uint64_t Pb = __brevll(~key) >> (64 - A);
+        const int js = k - __popcll(Pb);
+        if (js < 0 || js > SD_BLK_B) continue;                     // uniform over the CTA
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint64_t pb = 0, rb = 0;
+            for (int q = 0; q < A; ++q) {
+                if ((Pb >> q) & 1ULL) continue;
+                const int below = __popcll(Pb & ((1ULL << q) - 1ULL));
+                pb += P.W[q * (A + 1) + below];
+                rb += sd_binom_at(Q.binom, SD_BINOM_DIM, L - 1 - q, k - below - 1);
+            }
+            s_base[0] = pb; s_base[1] = rb;
+        }
+        __syncthreads();
+        const uint64_t pbase = s_base[0] - P.shards.pstart[P.shards.rank], rbase = s_base[1] - Q.rstart;
+        const SdBlkJs &I = P.js[js];
+        for (uint32_t p = threadIdx.x; p < I.size_pad; p += blockDim.x) {
+            int jt = -1;
+            uint32_t rel = 0;
+#pragma unroll
+            for (int j = 0; j < SD_BLK_NCLS; ++j) {
+                const uint32_t len = I.cls[j].pitch * (uint32_t)sd_cbinom(SD_BLK_T, j);
+                if (jt < 0 && p >= I.cls[j].cb && p < I.cls[j].cb + len) { jt = j; rel = p - I.cls[j].cb; }
+            }
+            bool real = jt >= 0;
+            uint32_t e = 0, u = 0;
+            if (real) {
+                e = rel / I.cls[jt].pitch; u = rel % I.cls[jt].pitch;
+                real = u < I.cls[jt].nblk;
+            }
+            double *bp = blk_local + (size_t)(pbase + p) * Q.nc_blk;
+            if (!real) {
+                if (Q.dir == 0) for (int c = 0; c < Q.nc_blk; ++c) bp[c] = 0.0;
+                continue;
+            }
+            const unsigned cm = P.items[I.cls[jt].item_off + u].c;
+            const unsigned tau = sd_tail_cfg(SD_BLK_T, jt, (int)e);
+            const uint64_t suf = (uint64_t)cm | ((uint64_t)tau << SD_BLK_M);
+            const uint64_t lr = sd_rank_state(suf, SD_BLK_B, js, Q.binom, SD_BINOM_DIM);
+            double *rp = rank_local + (size_t)(rbase + lr) * Q.nc_rank;
+            if (Q.dir == 0) {
+                if (Q.seeded) {
+                    for (int c = 0; c < Q.nc_blk; ++c) bp[c] = Q.scale * sd_seeded_value(Q.seed + (uint64_t)c, Q.rstart + rbase + lr);
+                } else {
+                    for (int c = 0; c < Q.nc_blk; ++c) bp[c] = c < Q.nc_rank ? rp[c] : 0.0;
+                }
+            } else {
+                for (int c = 0; c < Q.nc_rank; ++c) rp[c] = c < Q.nc_blk ? bp[c] : 0.0;
+            }
+        }
+    }
+}
+#endif  // __CUDACC__

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "libspindyn_cuda.so")
 
 SD_F64, SD_C128 = 0, 1
-SD_PATH_GENERIC, SD_PATH_TILED = 0, 1
+SD_PATH_GENERIC, SD_PATH_TILED, SD_PATH_BLOCK = 0, 1, 2
 SD_ERR_ARG, SD_ERR_CUDA, SD_ERR_NOMEM, SD_ERR_NCCL, SD_ERR_ZERO_NORM, SD_ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6
 
 

@@ -194,11 +194,13 @@ class Model:
     def info(self):
         p, t, r = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         check(lib().sd_model_info(self._h, ctypes.byref(p), ctypes.byref(t), ctypes.byref(r)))
-        return {"kernel_path": "tiled" if p.value == _lib.SD_PATH_TILED else "generic",
+        return {"kernel_path": {_lib.SD_PATH_TILED: "tiled", _lib.SD_PATH_BLOCK: "block"}.get(p.value, "generic"),
                 "tile_sites": t.value, "rank_bits": r.value}
 
     def set_path(self, path: str) -> None:
-        check(lib().sd_model_set_path(self._h, {"generic": 0, "tiled": 1}[path]))
+        """"block" stores vectors in block layout, "tiled"/"generic" in rank order: switching between
+        the two groups is only possible while no DeviceVector of the model is alive."""
+        check(lib().sd_model_set_path(self._h, {"generic": 0, "tiled": 1, "block": 2}[path]))
 
     # -- vectors ------------------------------------------------------------
     def vector(self, dtype=np.float64) -> "DeviceVector":
