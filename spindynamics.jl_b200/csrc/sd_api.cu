@@ -115,6 +115,7 @@ struct sd_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint64_t launches = 0;
     std::vector<uint64_t> binom;
+    unsigned long long *d_tilectr = nullptr;  // tile counter of the block kernel's dynamic scheduler
     void *scratch[2] = {nullptr, nullptr};   // rank-ordered staging of block-layout vectors (upload/download/szq)
     size_t scratch_cap[2] = {0, 0};
 };
@@ -270,6 +271,7 @@ static int sd_ctx_init(int device, int rank, int world, const void *id128, sd_ct
     SD_CUDA(cudaMalloc(&c->d_scal, SD_NSCAL * sizeof(double)));
     SD_CUDA(cudaMemset(c->d_scal, 0, SD_NSCAL * sizeof(double)));
     SD_CUDA(cudaMallocHost(&c->h_scal, SD_NSCAL * sizeof(double)));
+    SD_CUDA(cudaMalloc(&c->d_tilectr, sizeof(unsigned long long)));
     if (world > 1) {
         SD_ARG(id128, "id128 is NULL");
         SD_TRY(sd_nccl_load());
@@ -299,7 +301,7 @@ int sd_ctx_free(sd_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm) g_nccl.CommDestroy(c->comm);
     cudaFree(c->d_binom); cudaFree(c->d_scal); cudaFreeHost(c->h_scal); cudaFree(c->d_partials); cudaFree(c->d_ipc);
-    cudaFree(c->scratch[0]); cudaFree(c->scratch[1]);
+    cudaFree(c->scratch[0]); cudaFree(c->scratch[1]); cudaFree(c->d_tilectr);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -1009,6 +1011,7 @@ static int sd_apply_impl(sd_model *m, sd_vec *out, const sd_vec *psi, SdEpi epi,
         }
         epi.partials = c->d_partials;
         epi.nparts = (unsigned)nkeys;
+        SD_CUDA(cudaMemsetAsync(c->d_tilectr, 0, sizeof(unsigned long long), c->stream));
         const size_t smem = m->blk.smem[nc - 1];
         const int qfar = m->blk.qfar[nc - 1];
         const bool plain = epi.mode == SD_EPI_PLAIN && epi.red == 0 && !epi.acc && epi.hscale == 1.0;
@@ -1019,7 +1022,7 @@ static int sd_apply_impl(sd_model *m, sd_vec *out, const sd_vec *psi, SdEpi epi,
             SD_CUDA(cudaFuncSetAttribute(sd_blk_apply_kernel<NC_, PLAIN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             set_smem = smem;                                                                                 \
         }                                                                                                    \
-        sd_blk_apply_kernel<NC_, PLAIN_><<<grid, SD_BLK_THREADS, smem, c->stream>>>(P, psi->view, out->d, epi, qfar); \
+        sd_blk_apply_kernel<NC_, PLAIN_><<<grid, SD_BLK_THREADS, smem, c->stream>>>(P, psi->view, out->d, epi, qfar, c->d_tilectr); \
     } while (0)
         if (nc == 1) { if (plain) SD_LAUNCH_BLK(1, true); else SD_LAUNCH_BLK(1, false); }
         else { if (plain) SD_LAUNCH_BLK(2, true); else SD_LAUNCH_BLK(2, false); }

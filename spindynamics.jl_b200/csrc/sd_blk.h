@@ -34,7 +34,7 @@
 #define SD_BLK_B (SD_BLK_M + SD_BLK_T)
 #define SD_BLK_NCLS (SD_BLK_T + 1)
 #define SD_BLK_MAXA 32
-#define SD_BLK_MAXUNITS 32      // units per tile: sum_jt ceil(pitch/64) <= 17 (f64), sum_jt ceil(pitch/32) <= 32 (c128)
+#define SD_BLK_MAXUNITS 64      // work items per tile: (unit, element chunk) pairs; <= 25 (f64), <= 47 (c128)
 #define SD_BLK_THREADS 512
 #define SD_BLK_CWARPS 15        // consumer warps; warp 15 is the producer
 
@@ -155,8 +155,8 @@ struct SdBlkHdr {
     double dP[2];                        // prefix diag + prefix|mid zz, by first mid bit
     double Jx;                           // hop coefficient of the prefix|mid bond (0: none)
     const double *xptr;                  // stored base of the crossing partner tile (component 0)
-    const double *nb_ptr[SD_BLK_MAXA];   // stored bases of the neighbour tiles of the active prefix bonds
-    double nb_J[SD_BLK_MAXA];
+    const double *nb_ptr[SD_BLK_MAXA + 8];   // stored bases of the neighbour tiles of the active prefix bonds
+    double nb_J[SD_BLK_MAXA + 8];        // entries >= nnb: valid pointer, J = 0 (software pipeline overrun)
     double usum[SD_NSLOT][SD_BLK_MAXUNITS];   // per-unit reduction results (deterministic: summed in unit order)
 };
 
@@ -226,18 +226,15 @@ __device__ __forceinline__ void sd_blk_make_hdr(const SdBlkParams &P, const uint
     }
 }
 
-// ------------------------------------------------------------------ per-unit body
-// compile-time tables of the tail block of class (T, JT): see sd_common.h
-template <int NT>
-struct SdV2Arr {
-    double2 v[NT];
-};
-
-template <int JT, int t, int q>
+// ------------------------------------------------------------------ per-item body
+// A work ITEM is (unit, element chunk): lanes own BPL = 2/NC adjacent mid configurations ub + sb of
+// class JT and the EC tail configurations [E0, E0+EC) of each.  Chunks keep the register footprint at
+// acc[EC] + 3 x t[EC] double2, which is what allows THREE neighbour tiles in flight per warp.
+template <int JT, int E0, int EC, int t, int q>
 struct SdBlkTailHop {
     static constexpr int NT = sd_cbinom(SD_BLK_T, JT);
-    static __device__ __forceinline__ void run(double2 (&acc)[NT], const double2 (&own)[NT], const double *Jt) {
-        constexpr unsigned cfg = sd_tail_cfg(SD_BLK_T, JT, t);
+    static __device__ __forceinline__ void run(double2 (&acc)[EC], const double2 (&own)[NT], const double *Jt) {
+        constexpr unsigned cfg = sd_tail_cfg(SD_BLK_T, JT, E0 + t);
         constexpr bool act = (((cfg >> q) ^ (cfg >> (q + 1))) & 1u) != 0;
         if constexpr (act) {
             constexpr int t2 = sd_tail_rank(SD_BLK_T, JT, cfg ^ (3u << q));
@@ -245,21 +242,21 @@ struct SdBlkTailHop {
             acc[t].x += J * own[t2].x;
             acc[t].y += J * own[t2].y;
         }
-        if constexpr (q + 2 < SD_BLK_T) SdBlkTailHop<JT, t, q + 1>::run(acc, own, Jt);
+        if constexpr (q + 2 < SD_BLK_T) SdBlkTailHop<JT, E0, EC, t, q + 1>::run(acc, own, Jt);
     }
 };
-template <int JT, int t>
+template <int JT, int E0, int EC, int t>
 struct SdBlkTailRow {
     static constexpr int NT = sd_cbinom(SD_BLK_T, JT);
-    static __device__ __forceinline__ void run(double2 (&acc)[NT], const double2 (&own)[NT], const double *Jt,
+    static __device__ __forceinline__ void run(double2 (&acc)[EC], const double2 (&own)[NT], const double *Jt,
                                                const double *dtail, double d0, double d1, double dx0, double dx1) {
-        constexpr unsigned cfg = sd_tail_cfg(SD_BLK_T, JT, t);
+        constexpr unsigned cfg = sd_tail_cfg(SD_BLK_T, JT, E0 + t);
         const double dt = dtail[cfg];
         // + dx when tail bit 0 equals the last mid bit (dx already carries the sign of the last mid bit)
-        acc[t].x += (d0 + dt + ((cfg & 1u) ? dx0 : -dx0)) * own[t].x;
-        acc[t].y += (d1 + dt + ((cfg & 1u) ? dx1 : -dx1)) * own[t].y;
-        SdBlkTailHop<JT, t, 0>::run(acc, own, Jt);
-        if constexpr (t + 1 < NT) SdBlkTailRow<JT, t + 1>::run(acc, own, Jt, dtail, d0, d1, dx0, dx1);
+        acc[t].x += (d0 + dt + ((cfg & 1u) ? dx0 : -dx0)) * own[E0 + t].x;
+        acc[t].y += (d1 + dt + ((cfg & 1u) ? dx1 : -dx1)) * own[E0 + t].y;
+        SdBlkTailHop<JT, E0, EC, t, 0>::run(acc, own, Jt);
+        if constexpr (t + 1 < EC) SdBlkTailRow<JT, E0, EC, t + 1>::run(acc, own, Jt, dtail, d0, d1, dx0, dx1);
     }
 };
 
@@ -275,59 +272,73 @@ struct SdBlkCtx {
     const SdEpi *epi;
 };
 
-// One unit: lanes own BPL = 2/NC adjacent mid configurations ub + sb of class JT (all C(T,JT) tail
-// configurations each).  tb = shared-memory copy of the tile.
-template <int NC, int JT, bool PLAIN>
-__device__ __forceinline__ void sd_blk_unit(const SdBlkCtx &X, const SdBlkHdr &H, const double *tb, uint32_t ub,
-                                            double (&red)[SD_NSLOT]) {
+// own block: diagonal + tail-internal hops.  The only part specialised on (class, chunk): the tail
+// configurations are compile-time constants, so tail hops are register moves.
+template <int NC, int JT, int E0, int EC>
+__device__ __forceinline__ void sd_blk_tail(double2 (&acc)[EC], const double *own_ptr, uint32_t es, const double *Jt,
+                                            const double *dtail, double d0, double d1, double dx0, double dx1) {
+    constexpr int NT = sd_cbinom(SD_BLK_T, JT);
+    double2 own[NT];
+#pragma unroll
+    for (int e = 0; e < NT; ++e) own[e] = *(const double2 *)(own_ptr + e * es);
+    SdBlkTailRow<JT, E0, EC, 0>::run(acc, own, Jt, dtail, d0, d1, dx0, dx1);
+}
+
+// One work item: class jt, tail configurations [E0, E0+EC), lanes own BPL = 2/NC adjacent mid
+// configurations ub + sb.  Everything except sd_blk_tail is generic in (jt, E0), which keeps the code
+// small enough for the instruction cache (15 warps run different items at the same time).
+template <int NC, int EC, bool PLAIN>
+__device__ __forceinline__ void sd_blk_item(const SdBlkCtx &X, const SdBlkHdr &H, const double *tb, int jt, int E0,
+                                            uint32_t ub, double (&red)[SD_NSLOT]) {
     constexpr int T = SD_BLK_T, M = SD_BLK_M;
-    constexpr int NT = sd_cbinom(T, JT);
     constexpr int BPL = 2 / NC;
     const SdBlkParams &P = *X.P;
     const SdBlkJs &I = X.js[H.js];
-    const SdBlkCls cls = I.cls[JT];
+    const SdBlkCls cls = I.cls[jt];
     if (ub >= cls.pitch) return;
-    const size_t off0 = (size_t)(cls.cb + ub) * NC;
-    const size_t es = (size_t)cls.pitch * NC;
+    const uint32_t es = cls.pitch * NC;                               // doubles between tail configurations
+    const uint32_t off0 = (cls.cb + ub) * NC;                         // doubles, element (e = 0, ub)
+    const uint32_t offc = off0 + E0 * es;                             // first element of the chunk
     // work items of the lane's blocks (L2-resident table), issued before the streams
-    SdBlkItem it[BPL];
+    uint4 it[BPL];                                                    // SdBlkItem: x,y,z = nb[12]; w = c | u2x << 16
     bool have[BPL];
 #pragma unroll
     for (int sb = 0; sb < BPL; ++sb) {
         have[sb] = ub + sb < cls.nblk;
-        const uint4 raw = have[sb] ? __ldg((const uint4 *)(P.items + cls.item_off + ub + sb)) : make_uint4(~0u, ~0u, ~0u, 0u);
-        *(uint4 *)&it[sb] = raw;
+        it[sb] = have[sb] ? __ldg((const uint4 *)(P.items + cls.item_off + ub + sb)) : make_uint4(~0u, ~0u, ~0u, 0u);
     }
-    double2 acc[NT];
+    double2 acc[EC];
 #pragma unroll
-    for (int e = 0; e < NT; ++e) acc[e] = make_double2(0.0, 0.0);
-    // ---- prefix-internal bonds: whole neighbour tiles, same element order
+    for (int e = 0; e < EC; ++e) acc[e] = make_double2(0.0, 0.0);
+    // ---- prefix-internal bonds: whole neighbour tiles, same element order; three tiles in flight
     if (!(P.dbg & 1)) {
-        const int nfar = H.nfar, nnb = H.nnb;
+        const int nnb = H.nnb;
+        double2 t0[EC], t1[EC], t2[EC];
+#define SD_BLK_LOAD(t_, n_)                                                                   \
+        do {                                                                                  \
+            const bool ok_ = (n_) < nnb;                                                      \
+            const double *p_ = H.nb_ptr[n_] + offc;                                           \
+            _Pragma("unroll") for (int e = 0; e < EC; ++e)                                    \
+                t_[e] = ok_ ? sd_ldg_v2(p_ + e * es) : make_double2(0.0, 0.0);                \
+        } while (0)
+#define SD_BLK_FMA(t_, n_)                                                                    \
+        do {                                                                                  \
+            const double J_ = (n_) < nnb ? H.nb_J[n_] : 0.0;                                  \
+            _Pragma("unroll") for (int e = 0; e < EC; ++e) { acc[e].x += J_ * t_[e].x; acc[e].y += J_ * t_[e].y; } \
+        } while (0)
+        SD_BLK_LOAD(t0, 0); SD_BLK_LOAD(t1, 1); SD_BLK_LOAD(t2, 2);
 #pragma unroll 1
-        for (int n = 0; n < nfar; ++n) {
-            const double *p = H.nb_ptr[n] + off0;
-            const double J = H.nb_J[n];
-            double2 t[NT];
-#pragma unroll
-            for (int e = 0; e < NT; ++e) t[e] = sd_ldg_v2_far(p + e * es);
-#pragma unroll
-            for (int e = 0; e < NT; ++e) { acc[e].x += J * t[e].x; acc[e].y += J * t[e].y; }
+        for (int n = 0; n < nnb; n += 3) {
+            SD_BLK_FMA(t0, n); SD_BLK_LOAD(t0, n + 3);
+            SD_BLK_FMA(t1, n + 1); SD_BLK_LOAD(t1, n + 4);
+            SD_BLK_FMA(t2, n + 2); SD_BLK_LOAD(t2, n + 5);
         }
-#pragma unroll 1
-        for (int n = nfar; n < nnb; ++n) {
-            const double *p = H.nb_ptr[n] + off0;
-            const double J = H.nb_J[n];
-            double2 t[NT];
-#pragma unroll
-            for (int e = 0; e < NT; ++e) t[e] = sd_ldg_v2(p + e * es);
-#pragma unroll
-            for (int e = 0; e < NT; ++e) { acc[e].x += J * t[e].x; acc[e].y += J * t[e].y; }
-        }
+#undef SD_BLK_LOAD
+#undef SD_BLK_FMA
     }
     // ---- prefix|mid crossing bond: partner tile with js +- 1, same class, uniform block shift
     if (H.xptr) {
-        const SdBlkCls cx = X.js[H.jsx].cls[JT];
+        const SdBlkCls cx = X.js[H.jsx].cls[jt];
         const double J = H.Jx;
 #pragma unroll
         for (int sb = 0; sb < BPL; ++sb) {
@@ -335,53 +346,74 @@ __device__ __forceinline__ void sd_blk_unit(const SdBlkCtx &X, const SdBlkHdr &H
             const bool c0 = u < cls.n1;                            // first mid bit (blocks with it set come first)
             if (have[sb] && (c0 != (bool)H.bP)) {
                 const uint32_t u2 = H.bP ? u - cls.n1 : cx.n1 + u;
-                const double *p = H.xptr + (size_t)(cx.cb + u2) * NC;
-                const size_t xs = (size_t)cx.pitch * NC;
+                const uint32_t xs = cx.pitch * NC;
+                const double *p = H.xptr + (size_t)(cx.cb + u2) * NC + (size_t)E0 * xs;
                 if (NC == 2) {
+                    double2 t[EC];
 #pragma unroll
-                    for (int e = 0; e < NT; ++e) {
-                        const double2 t = sd_ldg_v2(p + e * xs);
-                        acc[e].x += J * t.x; acc[e].y += J * t.y;
-                    }
+                    for (int e = 0; e < EC; ++e) t[e] = sd_ldg_v2(p + e * xs);
+#pragma unroll
+                    for (int e = 0; e < EC; ++e) { acc[e].x += J * t[e].x; acc[e].y += J * t[e].y; }
                 } else {
-                    double t[NT];
+                    double t[EC];
 #pragma unroll
-                    for (int e = 0; e < NT; ++e) t[e] = __ldg(p + e * xs);
+                    for (int e = 0; e < EC; ++e) t[e] = __ldg(p + e * xs);
 #pragma unroll
-                    for (int e = 0; e < NT; ++e) { if (sb == 0) acc[e].x += J * t[e]; else acc[e].y += J * t[e]; }
+                    for (int e = 0; e < EC; ++e) { if (sb == 0) acc[e].x += J * t[e]; else acc[e].y += J * t[e]; }
                 }
             }
         }
     }
     // ---- own block: diagonal + tail-internal hops (registers)
     {
-        double2 own[NT];
-#pragma unroll
-        for (int e = 0; e < NT; ++e) own[e] = *(const double2 *)(tb + off0 + e * es);
         double d[2], dx[2];
 #pragma unroll
         for (int sb = 0; sb < 2; ++sb) {
             const int s = (NC == 2) ? 0 : sb;
-            const unsigned c = it[s].c & ((1u << M) - 1u);
+            const unsigned c = it[s].w & ((1u << M) - 1u);
             const bool c0 = (ub + s) < cls.n1;
             d[sb] = H.dP[c0 ? 1 : 0] + X.dmid[c];
             dx[sb] = ((c >> (M - 1)) & 1u) ? X.qx : -X.qx;
         }
-        SdBlkTailRow<JT, 0>::run(acc, own, X.Jhop + P.A + M, X.dtail, d[0], d[1], dx[0], dx[1]);
+        const double *op = tb + off0;
+        const double *Jt = X.Jhop + P.A + M;
+        static_assert(SD_BLK_T == 5, "item chunking is written for T = 5");
+        if constexpr (EC == 1) {
+            if (jt == 0) sd_blk_tail<NC, 0, 0, 1>(acc, op, es, Jt, X.dtail, d[0], d[1], dx[0], dx[1]);
+            else sd_blk_tail<NC, 5, 0, 1>(acc, op, es, Jt, X.dtail, d[0], d[1], dx[0], dx[1]);
+        } else {
+            switch (jt * 2 + (E0 ? 1 : 0)) {
+                case 2: sd_blk_tail<NC, 1, 0, 5>(acc, op, es, Jt, X.dtail, d[0], d[1], dx[0], dx[1]); break;
+                case 4: sd_blk_tail<NC, 2, 0, 5>(acc, op, es, Jt, X.dtail, d[0], d[1], dx[0], dx[1]); break;
+                case 5: sd_blk_tail<NC, 2, 5, 5>(acc, op, es, Jt, X.dtail, d[0], d[1], dx[0], dx[1]); break;
+                case 6: sd_blk_tail<NC, 3, 0, 5>(acc, op, es, Jt, X.dtail, d[0], d[1], dx[0], dx[1]); break;
+                case 7: sd_blk_tail<NC, 3, 5, 5>(acc, op, es, Jt, X.dtail, d[0], d[1], dx[0], dx[1]); break;
+                default: sd_blk_tail<NC, 4, 0, 5>(acc, op, es, Jt, X.dtail, d[0], d[1], dx[0], dx[1]); break;
+            }
+        }
     }
     // ---- mid-internal hops: the whole block moves to block nb[pm] of the same class
     if (!(P.dbg & 2)) {
-        const double *cbp = tb + (size_t)cls.cb * NC;
+        const double *cbp = tb + cls.cb * NC + E0 * es;
+        uint64_t lo[BPL];
+        uint32_t hi[BPL];
 #pragma unroll
+        for (int sb = 0; sb < BPL; ++sb) {
+            lo[sb] = (uint64_t)it[sb].x | ((uint64_t)it[sb].y << 32);
+            hi[sb] = it[sb].z;
+        }
+#pragma unroll 1
         for (int pm = 0; pm + 1 < M; ++pm) {
             const double J = X.Jhop[P.A + pm];
 #pragma unroll
             for (int sb = 0; sb < BPL; ++sb) {
-                const unsigned nbu = it[sb].nb[pm];
+                const unsigned nbu = (unsigned)(lo[sb] & 0xFFu);
+                lo[sb] = (lo[sb] >> 8) | ((uint64_t)hi[sb] << 56);
+                hi[sb] >>= 8;
                 if (nbu != 0xFFu) {
-                    const double *sp = cbp + (size_t)nbu * NC;
+                    const double *sp = cbp + nbu * NC;
 #pragma unroll
-                    for (int e = 0; e < NT; ++e) {
+                    for (int e = 0; e < EC; ++e) {
                         if (NC == 2) {
                             const double2 t = *(const double2 *)(sp + e * es);
                             acc[e].x += J * t.x; acc[e].y += J * t.y;
@@ -394,63 +426,50 @@ __device__ __forceinline__ void sd_blk_unit(const SdBlkCtx &X, const SdBlkHdr &H
             }
         }
     }
-    // ---- mid|tail crossing bond
+    // ---- mid|tail crossing bond.  Tail configurations with bit 0 set come first in a class:
+    // n1 = C(T-1, jt-1) of them.  Last mid bit set & tail bit 0 clear -> class jt+1, row e - n1;
+    // last mid bit clear & tail bit 0 set -> class jt-1, row C(T-1, jt-2) + e.
     {
         const double J = X.Jhop[P.A + M - 1];
-        constexpr int n1 = sd_cbinom(T - 1, JT - 1);               // tail configurations with first bit 1
+        // nibble i of the constant = C(4, i-2) (T = 5)
+        const int n1 = (int)((0x01464100u >> (4 * (jt + 1))) & 0xFu), n1p = (int)((0x01464100u >> (4 * jt)) & 0xFu);
 #pragma unroll
         for (int sb = 0; sb < BPL; ++sb) {
             if (!have[sb]) continue;
-            const unsigned c = it[sb].c;
-            const unsigned u2 = it[sb].u2x;
-            if ((c >> (M - 1)) & 1u) {
-                if constexpr (JT < T && NT - n1 > 0) {             // tail bit 0 clear -> class JT+1, first part
-                    const SdBlkCls c2 = I.cls[JT + 1];
-                    const double *sp = tb + (size_t)(c2.cb + u2) * NC;
-                    const size_t s2 = (size_t)c2.pitch * NC;
+            const bool up = (it[sb].w >> (M - 1)) & 1u;
+            const int jt2 = up ? jt + 1 : jt - 1;
+            if (jt2 < 0 || jt2 > T) continue;
+            const SdBlkCls c2 = I.cls[jt2];
+            const double *sp = tb + (c2.cb + (it[sb].w >> 16)) * NC;
+            const uint32_t s2 = c2.pitch * NC;
+            const int shift = up ? -n1 : n1p;                      // partner row = e + shift
 #pragma unroll
-                    for (int e = n1; e < NT; ++e) {
-                        if (NC == 2) {
-                            const double2 t = *(const double2 *)(sp + (e - n1) * s2);
-                            acc[e].x += J * t.x; acc[e].y += J * t.y;
-                        } else {
-                            const double t = sp[(e - n1) * s2];
-                            if (sb == 0) acc[e].x += J * t; else acc[e].y += J * t;
-                        }
-                    }
-                }
-            } else {
-                if constexpr (JT > 0 && n1 > 0) {                  // tail bit 0 set -> class JT-1, second part
-                    constexpr int n1p = sd_cbinom(T - 1, JT - 2);
-                    const SdBlkCls c2 = I.cls[JT - 1];
-                    const double *sp = tb + (size_t)(c2.cb + u2) * NC;
-                    const size_t s2 = (size_t)c2.pitch * NC;
-#pragma unroll
-                    for (int e = 0; e < n1; ++e) {
-                        if (NC == 2) {
-                            const double2 t = *(const double2 *)(sp + (n1p + e) * s2);
-                            acc[e].x += J * t.x; acc[e].y += J * t.y;
-                        } else {
-                            const double t = sp[(n1p + e) * s2];
-                            if (sb == 0) acc[e].x += J * t; else acc[e].y += J * t;
-                        }
+            for (int e = 0; e < EC; ++e) {
+                const int ee = E0 + e;
+                if (up ? (ee >= n1) : (ee < n1)) {
+                    if (NC == 2) {
+                        const double2 t = *(const double2 *)(sp + (ee + shift) * s2);
+                        acc[e].x += J * t.x; acc[e].y += J * t.y;
+                    } else {
+                        const double t = sp[(ee + shift) * s2];
+                        if (sb == 0) acc[e].x += J * t; else acc[e].y += J * t;
                     }
                 }
             }
         }
     }
     // ---- epilogue + store
-    const uint64_t li0 = H.base - X.pstart_local + cls.cb + ub;    // local stored element of (e = 0, ub)
+    const uint64_t li0 = H.base - X.pstart_local + cls.cb + (uint64_t)E0 * cls.pitch + ub;   // local stored element of (E0, ub)
     double *o = X.out_local + (size_t)li0 * NC;
     if (PLAIN) {
         if (P.dbg & 4) { if (acc[0].x == 1.2345e300) sd_stg_v2(o, acc[0]); return; }
 #pragma unroll
-        for (int e = 0; e < NT; ++e) sd_stg_v2(o + e * es, acc[e]);
+        for (int e = 0; e < EC; ++e) sd_stg_v2(o + e * es, acc[e]);
     } else {
         const SdEpi &E = *X.epi;
 #pragma unroll
-        for (int e = 0; e < NT; ++e) {
-            const double2 p = *(const double2 *)(tb + off0 + e * es);
+        for (int e = 0; e < EC; ++e) {
+            const double2 p = *(const double2 *)(tb + offc + e * es);
             double2 r;
             if (NC == 2) {
                 SdVal<2> hh, pp;
@@ -470,14 +489,14 @@ __device__ __forceinline__ void sd_blk_unit(const SdBlkCtx &X, const SdBlkHdr &H
     }
 }
 
-template <int NC, bool PLAIN, int JT>
-struct SdBlkDispatch {
-    static __device__ __forceinline__ void run(const SdBlkCtx &X, const SdBlkHdr &H, const double *tb, int jt, uint32_t ub,
-                                               double (&red)[SD_NSLOT]) {
-        if (jt == JT) sd_blk_unit<NC, JT, PLAIN>(X, H, tb, ub, red);
-        else if constexpr (JT > 0) SdBlkDispatch<NC, PLAIN, JT - 1>::run(X, H, tb, jt, ub, red);
-    }
-};
+// item code: jt << 12 | chunk << 8 | unit-in-class.  Chunks: NT = 10 -> two of 5; NT = 5 -> one; NT = 1 -> one.
+template <int NC, bool PLAIN>
+__device__ __forceinline__ void sd_blk_dispatch(const SdBlkCtx &X, const SdBlkHdr &H, const double *tb, unsigned code,
+                                                uint32_t ub, double (&red)[SD_NSLOT]) {
+    const int jt = (int)(code >> 12), E0 = ((code >> 8) & 0xFu) ? 5 : 0;
+    if (jt == 0 || jt == SD_BLK_T) sd_blk_item<NC, 1, PLAIN>(X, H, tb, jt, 0, ub, red);
+    else sd_blk_item<NC, 5, PLAIN>(X, H, tb, jt, E0, ub, red);
+}
 
 // shared-memory carve-up
 struct SdBlkSmem {
@@ -519,13 +538,14 @@ SD_HD size_t sd_blk_smem_carve(SdBlkSmem *s, void *base, int A, int L, int nbuf,
 }
 
 // ------------------------------------------------------------------ the kernel
-// grid = one persistent CTA per SM; CTA c walks tile keys key_lo + c, + grid, ...
+// grid = one persistent CTA per SM.  Tiles are handed out in key (= rank) order by a global counter, so
+// the tiles in flight form a tight window and near neighbour tiles are re-used from L2.
 // partials: [SD_NSLOT][ntiles] per-tile sums (zero-filled by the host before the launch: invalid tiles
-// write nothing); each is the in-order sum of the tile's per-unit sums, so results are run-to-run identical.
+// write nothing); each is the in-order sum of the tile's per-item sums, so results are run-to-run identical.
 template <int NC, bool PLAIN>
 __global__ void __launch_bounds__(SD_BLK_THREADS, 1)
 sd_blk_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constant__ SdVecView psi, double *out_local,
-                    const __grid_constant__ SdEpi epi, int qfar) {
+                    const __grid_constant__ SdEpi epi, int qfar, unsigned long long *tile_ctr) {
     extern __shared__ __align__(128) unsigned char sd_blk_smem[];
     SdBlkSmem S;
     sd_blk_smem_carve(&S, sd_blk_smem, P.A, P.L, P.nbuf, P.cap, NC);
@@ -551,17 +571,20 @@ sd_blk_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constant
     const size_t tile_doubles = (size_t)P.cap * NC;
 
     if (warp == SD_BLK_CWARPS) {
-        // ================= producer warp: headers + TMA of the own tiles
-        uint64_t key = P.key_lo + blockIdx.x;
+        // ================= producer warp: tile keys, headers, TMA of the own tiles, L2 prefetch of far tiles
         for (unsigned i = 0;; ++i) {
             const int b = (int)(i % (unsigned)nbuf);
             const unsigned round = i / (unsigned)nbuf;
-            // skip prefixes whose suffix popcount is impossible
-            while (key < P.key_hi) {
+            uint64_t key;
+            for (;;) {                                             // next valid tile of this shard
+                unsigned long long t = 0;
+                if (lane == 0) t = atomicAdd(tile_ctr, 1ULL);
+                t = __shfl_sync(0xffffffffu, t, 0);
+                key = P.key_lo + t;
+                if (key >= P.key_hi) break;
                 const uint64_t Pb = __brevll(~key) >> (64 - P.A);
                 const int js = P.k - __popcll(Pb);
-                if (js >= 0 && js <= SD_BLK_B) break;
-                key += gridDim.x;
+                if (js >= 0 && js <= SD_BLK_B) break;              // else: impossible suffix popcount
             }
             sd_mbar_wait(&S.empty[b], (round & 1u) ^ 1u);          // consumers released this buffer
             SdBlkHdr &H = S.hdr[b];
@@ -581,7 +604,15 @@ sd_blk_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constant
             constexpr uint32_t CH = 8192;
             for (uint32_t o = lane * CH; o < bytes; o += 32 * CH)
                 sd_bulk_g2s(dst + o, src + o, (bytes - o < CH) ? bytes - o : CH, &S.full[b]);
-            key += gridDim.x;
+            if (!(P.dbg & 8)) {                                    // far neighbour tiles: DRAM -> L2 ahead of the consumers
+                const int nfar = H.nfar;
+                if ((int)lane < nfar) {
+                    const double *p = H.nb_ptr[lane];
+                    const double *lo = psi.base[P.shards.rank] + (size_t)NC * P.shards.pstart[P.shards.rank];
+                    const double *hi = psi.base[P.shards.rank] + (size_t)NC * P.shards.pstart[P.shards.rank + 1];
+                    if (p >= lo && p < hi) sd_bulk_prefetch_l2(p, bytes);
+                }
+            }
         }
     } else {
         // ================= consumer warps
@@ -608,10 +639,9 @@ sd_blk_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constant
                 un = __shfl_sync(0xffffffffu, un, 0);
                 if (un >= nunits) break;
                 const unsigned code = ut[un];
-                const int jt = (int)(code >> 8);
                 const uint32_t ub = (code & 0xFFu) * UW + lane * (2 / NC);
                 double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
-                SdBlkDispatch<NC, PLAIN, SD_BLK_T>::run(X, H, tb, jt, ub, red);
+                sd_blk_dispatch<NC, PLAIN>(X, H, tb, code, ub, red);
                 if (!PLAIN && slotmask) {
 #pragma unroll
                     for (int s = 0; s < SD_NSLOT; ++s) {
@@ -624,7 +654,7 @@ sd_blk_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constant
                     if (lane == 0) {
                         __threadfence_block();
                         const unsigned done = atomicAdd(&H.done_units, 1u);
-                        if (done + 1 == nunits) {                  // last unit of the tile: ordered sum
+                        if (done + 1 == nunits) {                  // last item of the tile: ordered sum
                             __threadfence_block();
                             for (int s = 0; s < SD_NSLOT; ++s) {
                                 if (!((slotmask >> s) & 1)) continue;

@@ -12,7 +12,7 @@ struct SdBlkHost {
     std::vector<uint64_t> binom;      // [65*65]
     std::vector<uint64_t> W;          // [A*(A+1)]
     std::vector<SdBlkJs> js;          // [B+1]
-    std::vector<uint16_t> units;      // [2][(B+1)*MAXUNITS]
+    std::vector<uint16_t> units;      // [2][(B+1)*MAXUNITS] item codes jt << 12 | chunk << 8 | unit-in-class
     std::vector<SdBlkItem> items;
     std::vector<double> dmid;         // [1 << M]
     std::vector<uint16_t> urank;      // [1 << M] class-local index of a mid configuration
@@ -112,7 +112,11 @@ static inline bool sd_blk_build(int L, int k, const double *Jhop, const double *
             for (int jt = 0; jt <= T; ++jt) {
                 const SdBlkCls &c = I.cls[jt];
                 const uint32_t nu = (c.pitch + uw - 1) / uw;
-                for (uint32_t j = 0; j < nu; ++j) list.push_back({-(int)C[T * SD_BINOM_DIM + jt], (uint16_t)((jt << 8) | j)});
+                const int nt = (int)C[T * SD_BINOM_DIM + jt];
+                const int nchunk = nt > 5 ? 2 : 1;                // sd_blk_dispatch: NT = 10 -> two chunks of 5
+                for (uint32_t j = 0; j < nu; ++j)
+                    for (int ch = 0; ch < nchunk; ++ch)
+                        list.push_back({-(nt / nchunk), (uint16_t)((jt << 12) | (ch << 8) | j)});
             }
             std::stable_sort(list.begin(), list.end(), [](const auto &a, const auto &b) { return a.first < b.first; });
             if (list.size() > SD_BLK_MAXUNITS) return false;
