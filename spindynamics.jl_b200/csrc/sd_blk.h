@@ -34,7 +34,7 @@
 #define SD_BLK_B (SD_BLK_M + SD_BLK_T)
 #define SD_BLK_NCLS (SD_BLK_T + 1)
 #define SD_BLK_MAXA 32
-#define SD_BLK_MAXUNITS 64      // work items per tile: (unit, element chunk) pairs; <= 25 (f64), <= 47 (c128)
+#define SD_BLK_MAXUNITS 64      // work items per tile: (unit of 32 mid configurations, element chunk); <= 32 (f64), <= 47 (c128)
 #define SD_BLK_THREADS 512
 #define SD_BLK_CWARPS 15        // consumer warps; warp 15 is the producer
 
@@ -49,7 +49,7 @@ struct SdBlkCls {
 struct SdBlkJs {
     uint32_t size;       // C(B, js) real elements
     uint32_t size_pad;   // stored elements (multiple of 16)
-    uint32_t nunits[2];  // units per tile, [0]: f64 (64 blocks per unit), [1]: c128 (32 blocks per unit)
+    uint32_t nunits[2];  // work items per tile, [0]: f64 (one chunk per class), [1]: c128 (classes of 10 in two chunks)
     SdBlkCls cls[SD_BLK_NCLS];
 };
 // one mid configuration of one class
@@ -227,10 +227,27 @@ __device__ __forceinline__ void sd_blk_make_hdr(const SdBlkParams &P, const uint
 }
 
 // ------------------------------------------------------------------ per-item body
-// A work ITEM is (unit, element chunk): lanes own BPL = 2/NC adjacent mid configurations ub + sb of
-// class JT and the EC tail configurations [E0, E0+EC) of each.  Chunks keep the register footprint at
-// acc[EC] + 3 x t[EC] double2, which is what allows THREE neighbour tiles in flight per warp.
-template <int JT, int E0, int EC, int t, int q>
+// A work ITEM is (unit, element chunk): a lane owns ONE mid configuration u = ub + lane of class jt and
+// the EC tail configurations [E0, E0+EC) of it.  Values are held as double2: f64 uses .x only (the .y
+// arithmetic is dead code), c128 is (re, im) -- H is real, so both are plain real columns.
+// Register budget: acc[EC] + 3 x t[EC] values, which is what allows THREE neighbour tiles in flight
+// per warp (f64: EC = 10 -> 20 + 60 registers; c128: EC = 5 -> 20 + 60).
+template <int NC> __device__ __forceinline__ double2 sd_blk_ldg(const double *p) {
+    double2 v;
+    if (NC == 2) asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    else { asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v.x) : "l"(p)); v.y = 0.0; }
+    return v;
+}
+template <int NC> __device__ __forceinline__ double2 sd_blk_lds(const double *p) {
+    if (NC == 2) return *(const double2 *)p;
+    return make_double2(*p, 0.0);
+}
+template <int NC> __device__ __forceinline__ void sd_blk_stg(double *p, double2 v) {
+    if (NC == 2) asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+    else asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(p), "d"(v.x) : "memory");
+}
+
+template <int NC, int JT, int E0, int EC, int t, int q>
 struct SdBlkTailHop {
     static constexpr int NT = sd_cbinom(SD_BLK_T, JT);
     static __device__ __forceinline__ void run(double2 (&acc)[EC], const double2 (&own)[NT], const double *Jt) {
@@ -240,25 +257,36 @@ struct SdBlkTailHop {
             constexpr int t2 = sd_tail_rank(SD_BLK_T, JT, cfg ^ (3u << q));
             const double J = Jt[q];
             acc[t].x += J * own[t2].x;
-            acc[t].y += J * own[t2].y;
+            if (NC == 2) acc[t].y += J * own[t2].y;
         }
-        if constexpr (q + 2 < SD_BLK_T) SdBlkTailHop<JT, E0, EC, t, q + 1>::run(acc, own, Jt);
+        if constexpr (q + 2 < SD_BLK_T) SdBlkTailHop<NC, JT, E0, EC, t, q + 1>::run(acc, own, Jt);
     }
 };
-template <int JT, int E0, int EC, int t>
+template <int NC, int JT, int E0, int EC, int t>
 struct SdBlkTailRow {
     static constexpr int NT = sd_cbinom(SD_BLK_T, JT);
     static __device__ __forceinline__ void run(double2 (&acc)[EC], const double2 (&own)[NT], const double *Jt,
-                                               const double *dtail, double d0, double d1, double dx0, double dx1) {
+                                               const double *dtail, double d0, double dx0) {
         constexpr unsigned cfg = sd_tail_cfg(SD_BLK_T, JT, E0 + t);
-        const double dt = dtail[cfg];
         // + dx when tail bit 0 equals the last mid bit (dx already carries the sign of the last mid bit)
-        acc[t].x += (d0 + dt + ((cfg & 1u) ? dx0 : -dx0)) * own[E0 + t].x;
-        acc[t].y += (d1 + dt + ((cfg & 1u) ? dx1 : -dx1)) * own[E0 + t].y;
-        SdBlkTailHop<JT, E0, EC, t, 0>::run(acc, own, Jt);
-        if constexpr (t + 1 < EC) SdBlkTailRow<JT, E0, EC, t + 1>::run(acc, own, Jt, dtail, d0, d1, dx0, dx1);
+        const double d = d0 + dtail[cfg] + ((cfg & 1u) ? dx0 : -dx0);
+        acc[t].x += d * own[E0 + t].x;
+        if (NC == 2) acc[t].y += d * own[E0 + t].y;
+        SdBlkTailHop<NC, JT, E0, EC, t, 0>::run(acc, own, Jt);
+        if constexpr (t + 1 < EC) SdBlkTailRow<NC, JT, E0, EC, t + 1>::run(acc, own, Jt, dtail, d0, dx0);
     }
 };
+// own block: diagonal + tail-internal hops.  The only part specialised on (class, chunk): the tail
+// configurations are compile-time constants, so tail hops are register moves.
+template <int NC, int JT, int E0, int EC>
+__device__ __forceinline__ void sd_blk_tail(double2 (&acc)[EC], const double *own_ptr, uint32_t es, const double *Jt,
+                                            const double *dtail, double d0, double dx0) {
+    constexpr int NT = sd_cbinom(SD_BLK_T, JT);
+    double2 own[NT];
+#pragma unroll
+    for (int e = 0; e < NT; ++e) own[e] = sd_blk_lds<NC>(own_ptr + e * es);
+    SdBlkTailRow<NC, JT, E0, EC, 0>::run(acc, own, Jt, dtail, d0, dx0);
+}
 
 struct SdBlkCtx {
     const SdBlkParams *P;
@@ -272,41 +300,21 @@ struct SdBlkCtx {
     const SdEpi *epi;
 };
 
-// own block: diagonal + tail-internal hops.  The only part specialised on (class, chunk): the tail
-// configurations are compile-time constants, so tail hops are register moves.
-template <int NC, int JT, int E0, int EC>
-__device__ __forceinline__ void sd_blk_tail(double2 (&acc)[EC], const double *own_ptr, uint32_t es, const double *Jt,
-                                            const double *dtail, double d0, double d1, double dx0, double dx1) {
-    constexpr int NT = sd_cbinom(SD_BLK_T, JT);
-    double2 own[NT];
-#pragma unroll
-    for (int e = 0; e < NT; ++e) own[e] = *(const double2 *)(own_ptr + e * es);
-    SdBlkTailRow<JT, E0, EC, 0>::run(acc, own, Jt, dtail, d0, d1, dx0, dx1);
-}
-
-// One work item: class jt, tail configurations [E0, E0+EC), lanes own BPL = 2/NC adjacent mid
-// configurations ub + sb.  Everything except sd_blk_tail is generic in (jt, E0), which keeps the code
-// small enough for the instruction cache (15 warps run different items at the same time).
+// Everything except sd_blk_tail is generic in (jt, E0), which keeps the code small enough for the
+// instruction cache (15 warps run different items at the same time).
 template <int NC, int EC, bool PLAIN>
 __device__ __forceinline__ void sd_blk_item(const SdBlkCtx &X, const SdBlkHdr &H, const double *tb, int jt, int E0,
-                                            uint32_t ub, double (&red)[SD_NSLOT]) {
+                                            uint32_t u, double (&red)[SD_NSLOT]) {
     constexpr int T = SD_BLK_T, M = SD_BLK_M;
-    constexpr int BPL = 2 / NC;
     const SdBlkParams &P = *X.P;
     const SdBlkJs &I = X.js[H.js];
     const SdBlkCls cls = I.cls[jt];
-    if (ub >= cls.pitch) return;
+    if (u >= cls.nblk) return;
     const uint32_t es = cls.pitch * NC;                               // doubles between tail configurations
-    const uint32_t off0 = (cls.cb + ub) * NC;                         // doubles, element (e = 0, ub)
+    const uint32_t off0 = (cls.cb + u) * NC;                          // doubles, element (e = 0, u)
     const uint32_t offc = off0 + E0 * es;                             // first element of the chunk
-    // work items of the lane's blocks (L2-resident table), issued before the streams
-    uint4 it[BPL];                                                    // SdBlkItem: x,y,z = nb[12]; w = c | u2x << 16
-    bool have[BPL];
-#pragma unroll
-    for (int sb = 0; sb < BPL; ++sb) {
-        have[sb] = ub + sb < cls.nblk;
-        it[sb] = have[sb] ? __ldg((const uint4 *)(P.items + cls.item_off + ub + sb)) : make_uint4(~0u, ~0u, ~0u, 0u);
-    }
+    // the lane's work item (L2-resident table): x,y,z = nb[12]; w = c | u2x << 16
+    const uint4 it = __ldg((const uint4 *)(P.items + cls.item_off + u));
     double2 acc[EC];
 #pragma unroll
     for (int e = 0; e < EC; ++e) acc[e] = make_double2(0.0, 0.0);
@@ -319,12 +327,12 @@ __device__ __forceinline__ void sd_blk_item(const SdBlkCtx &X, const SdBlkHdr &H
             const bool ok_ = (n_) < nnb;                                                      \
             const double *p_ = H.nb_ptr[n_] + offc;                                           \
             _Pragma("unroll") for (int e = 0; e < EC; ++e)                                    \
-                t_[e] = ok_ ? sd_ldg_v2(p_ + e * es) : make_double2(0.0, 0.0);                \
+                t_[e] = ok_ ? sd_blk_ldg<NC>(p_ + e * es) : make_double2(0.0, 0.0);           \
         } while (0)
 #define SD_BLK_FMA(t_, n_)                                                                    \
         do {                                                                                  \
             const double J_ = (n_) < nnb ? H.nb_J[n_] : 0.0;                                  \
-            _Pragma("unroll") for (int e = 0; e < EC; ++e) { acc[e].x += J_ * t_[e].x; acc[e].y += J_ * t_[e].y; } \
+            _Pragma("unroll") for (int e = 0; e < EC; ++e) { acc[e].x += J_ * t_[e].x; if (NC == 2) acc[e].y += J_ * t_[e].y; } \
         } while (0)
         SD_BLK_LOAD(t0, 0); SD_BLK_LOAD(t1, 1); SD_BLK_LOAD(t2, 2);
 #pragma unroll 1
@@ -336,92 +344,64 @@ __device__ __forceinline__ void sd_blk_item(const SdBlkCtx &X, const SdBlkHdr &H
 #undef SD_BLK_LOAD
 #undef SD_BLK_FMA
     }
+    const bool c0 = u < cls.n1;                                       // first mid bit (blocks with it set come first)
     // ---- prefix|mid crossing bond: partner tile with js +- 1, same class, uniform block shift
-    if (H.xptr) {
+    if (H.xptr && (c0 != (bool)H.bP)) {
         const SdBlkCls cx = X.js[H.jsx].cls[jt];
         const double J = H.Jx;
+        const uint32_t u2 = H.bP ? u - cls.n1 : cx.n1 + u;
+        const uint32_t xs = cx.pitch * NC;
+        const double *p = H.xptr + (size_t)(cx.cb + u2) * NC + (size_t)E0 * xs;
+        double2 t[EC];
 #pragma unroll
-        for (int sb = 0; sb < BPL; ++sb) {
-            const uint32_t u = ub + sb;
-            const bool c0 = u < cls.n1;                            // first mid bit (blocks with it set come first)
-            if (have[sb] && (c0 != (bool)H.bP)) {
-                const uint32_t u2 = H.bP ? u - cls.n1 : cx.n1 + u;
-                const uint32_t xs = cx.pitch * NC;
-                const double *p = H.xptr + (size_t)(cx.cb + u2) * NC + (size_t)E0 * xs;
-                if (NC == 2) {
-                    double2 t[EC];
+        for (int e = 0; e < EC; ++e) t[e] = sd_blk_ldg<NC>(p + e * xs);
 #pragma unroll
-                    for (int e = 0; e < EC; ++e) t[e] = sd_ldg_v2(p + e * xs);
-#pragma unroll
-                    for (int e = 0; e < EC; ++e) { acc[e].x += J * t[e].x; acc[e].y += J * t[e].y; }
-                } else {
-                    double t[EC];
-#pragma unroll
-                    for (int e = 0; e < EC; ++e) t[e] = __ldg(p + e * xs);
-#pragma unroll
-                    for (int e = 0; e < EC; ++e) { if (sb == 0) acc[e].x += J * t[e]; else acc[e].y += J * t[e]; }
-                }
-            }
-        }
+        for (int e = 0; e < EC; ++e) { acc[e].x += J * t[e].x; if (NC == 2) acc[e].y += J * t[e].y; }
     }
     // ---- own block: diagonal + tail-internal hops (registers)
+    const unsigned cmid = it.w & ((1u << M) - 1u);
+    const bool clast = (cmid >> (M - 1)) & 1u;
     {
-        double d[2], dx[2];
-#pragma unroll
-        for (int sb = 0; sb < 2; ++sb) {
-            const int s = (NC == 2) ? 0 : sb;
-            const unsigned c = it[s].w & ((1u << M) - 1u);
-            const bool c0 = (ub + s) < cls.n1;
-            d[sb] = H.dP[c0 ? 1 : 0] + X.dmid[c];
-            dx[sb] = ((c >> (M - 1)) & 1u) ? X.qx : -X.qx;
-        }
+        const double d0 = H.dP[c0 ? 1 : 0] + X.dmid[cmid];
+        const double dx0 = clast ? X.qx : -X.qx;
         const double *op = tb + off0;
         const double *Jt = X.Jhop + P.A + M;
         static_assert(SD_BLK_T == 5, "item chunking is written for T = 5");
         if constexpr (EC == 1) {
-            if (jt == 0) sd_blk_tail<NC, 0, 0, 1>(acc, op, es, Jt, X.dtail, d[0], d[1], dx[0], dx[1]);
-            else sd_blk_tail<NC, 5, 0, 1>(acc, op, es, Jt, X.dtail, d[0], d[1], dx[0], dx[1]);
+            if (jt == 0) sd_blk_tail<NC, 0, 0, 1>(acc, op, es, Jt, X.dtail, d0, dx0);
+            else sd_blk_tail<NC, 5, 0, 1>(acc, op, es, Jt, X.dtail, d0, dx0);
+        } else if constexpr (EC == 10) {
+            if (jt == 2) sd_blk_tail<NC, 2, 0, 10>(acc, op, es, Jt, X.dtail, d0, dx0);
+            else sd_blk_tail<NC, 3, 0, 10>(acc, op, es, Jt, X.dtail, d0, dx0);
         } else {
             switch (jt * 2 + (E0 ? 1 : 0)) {
-                case 2: sd_blk_tail<NC, 1, 0, 5>(acc, op, es, Jt, X.dtail, d[0], d[1], dx[0], dx[1]); break;
-                case 4: sd_blk_tail<NC, 2, 0, 5>(acc, op, es, Jt, X.dtail, d[0], d[1], dx[0], dx[1]); break;
-                case 5: sd_blk_tail<NC, 2, 5, 5>(acc, op, es, Jt, X.dtail, d[0], d[1], dx[0], dx[1]); break;
-                case 6: sd_blk_tail<NC, 3, 0, 5>(acc, op, es, Jt, X.dtail, d[0], d[1], dx[0], dx[1]); break;
-                case 7: sd_blk_tail<NC, 3, 5, 5>(acc, op, es, Jt, X.dtail, d[0], d[1], dx[0], dx[1]); break;
-                default: sd_blk_tail<NC, 4, 0, 5>(acc, op, es, Jt, X.dtail, d[0], d[1], dx[0], dx[1]); break;
+                case 2: sd_blk_tail<NC, 1, 0, 5>(acc, op, es, Jt, X.dtail, d0, dx0); break;
+                case 4: sd_blk_tail<NC, 2, 0, 5>(acc, op, es, Jt, X.dtail, d0, dx0); break;
+                case 5: sd_blk_tail<NC, 2, 5, 5>(acc, op, es, Jt, X.dtail, d0, dx0); break;
+                case 6: sd_blk_tail<NC, 3, 0, 5>(acc, op, es, Jt, X.dtail, d0, dx0); break;
+                case 7: sd_blk_tail<NC, 3, 5, 5>(acc, op, es, Jt, X.dtail, d0, dx0); break;
+                default: sd_blk_tail<NC, 4, 0, 5>(acc, op, es, Jt, X.dtail, d0, dx0); break;
             }
         }
     }
     // ---- mid-internal hops: the whole block moves to block nb[pm] of the same class
     if (!(P.dbg & 2)) {
         const double *cbp = tb + cls.cb * NC + E0 * es;
-        uint64_t lo[BPL];
-        uint32_t hi[BPL];
-#pragma unroll
-        for (int sb = 0; sb < BPL; ++sb) {
-            lo[sb] = (uint64_t)it[sb].x | ((uint64_t)it[sb].y << 32);
-            hi[sb] = it[sb].z;
-        }
+        uint64_t lo = (uint64_t)it.x | ((uint64_t)it.y << 32);
+        uint32_t hi = it.z;
 #pragma unroll 1
         for (int pm = 0; pm + 1 < M; ++pm) {
             const double J = X.Jhop[P.A + pm];
+            const unsigned nbu = (unsigned)(lo & 0xFFu);
+            lo = (lo >> 8) | ((uint64_t)hi << 56);
+            hi >>= 8;
+            if (nbu != 0xFFu) {
+                const double *sp = cbp + nbu * NC;
 #pragma unroll
-            for (int sb = 0; sb < BPL; ++sb) {
-                const unsigned nbu = (unsigned)(lo[sb] & 0xFFu);
-                lo[sb] = (lo[sb] >> 8) | ((uint64_t)hi[sb] << 56);
-                hi[sb] >>= 8;
-                if (nbu != 0xFFu) {
-                    const double *sp = cbp + nbu * NC;
-#pragma unroll
-                    for (int e = 0; e < EC; ++e) {
-                        if (NC == 2) {
-                            const double2 t = *(const double2 *)(sp + e * es);
-                            acc[e].x += J * t.x; acc[e].y += J * t.y;
-                        } else {
-                            const double t = sp[e * es];
-                            if (sb == 0) acc[e].x += J * t; else acc[e].y += J * t;
-                        }
-                    }
+                for (int e = 0; e < EC; ++e) {
+                    const double2 t = sd_blk_lds<NC>(sp + e * es);
+                    acc[e].x += J * t.x;
+                    if (NC == 2) acc[e].y += J * t.y;
                 }
             }
         }
@@ -433,69 +413,54 @@ __device__ __forceinline__ void sd_blk_item(const SdBlkCtx &X, const SdBlkHdr &H
         const double J = X.Jhop[P.A + M - 1];
         // nibble i of the constant = C(4, i-2) (T = 5)
         const int n1 = (int)((0x01464100u >> (4 * (jt + 1))) & 0xFu), n1p = (int)((0x01464100u >> (4 * jt)) & 0xFu);
-#pragma unroll
-        for (int sb = 0; sb < BPL; ++sb) {
-            if (!have[sb]) continue;
-            const bool up = (it[sb].w >> (M - 1)) & 1u;
-            const int jt2 = up ? jt + 1 : jt - 1;
-            if (jt2 < 0 || jt2 > T) continue;
+        const int jt2 = clast ? jt + 1 : jt - 1;
+        if (jt2 >= 0 && jt2 <= T) {
             const SdBlkCls c2 = I.cls[jt2];
-            const double *sp = tb + (c2.cb + (it[sb].w >> 16)) * NC;
+            const double *sp = tb + (c2.cb + (it.w >> 16)) * NC;
             const uint32_t s2 = c2.pitch * NC;
-            const int shift = up ? -n1 : n1p;                      // partner row = e + shift
+            const int shift = clast ? -n1 : n1p;                   // partner row = e + shift
 #pragma unroll
             for (int e = 0; e < EC; ++e) {
                 const int ee = E0 + e;
-                if (up ? (ee >= n1) : (ee < n1)) {
-                    if (NC == 2) {
-                        const double2 t = *(const double2 *)(sp + (ee + shift) * s2);
-                        acc[e].x += J * t.x; acc[e].y += J * t.y;
-                    } else {
-                        const double t = sp[(ee + shift) * s2];
-                        if (sb == 0) acc[e].x += J * t; else acc[e].y += J * t;
-                    }
+                if (clast ? (ee >= n1) : (ee < n1)) {
+                    const double2 t = sd_blk_lds<NC>(sp + (ee + shift) * s2);
+                    acc[e].x += J * t.x;
+                    if (NC == 2) acc[e].y += J * t.y;
                 }
             }
         }
     }
     // ---- epilogue + store
-    const uint64_t li0 = H.base - X.pstart_local + cls.cb + (uint64_t)E0 * cls.pitch + ub;   // local stored element of (E0, ub)
+    const uint64_t li0 = H.base - X.pstart_local + cls.cb + (uint64_t)E0 * cls.pitch + u;   // local stored element of (E0, u)
     double *o = X.out_local + (size_t)li0 * NC;
     if (PLAIN) {
-        if (P.dbg & 4) { if (acc[0].x == 1.2345e300) sd_stg_v2(o, acc[0]); return; }
+        if (P.dbg & 4) { if (acc[0].x == 1.2345e300) sd_blk_stg<NC>(o, acc[0]); return; }
 #pragma unroll
-        for (int e = 0; e < EC; ++e) sd_stg_v2(o + e * es, acc[e]);
+        for (int e = 0; e < EC; ++e) sd_blk_stg<NC>(o + e * es, acc[e]);
     } else {
         const SdEpi &E = *X.epi;
 #pragma unroll
         for (int e = 0; e < EC; ++e) {
-            const double2 p = *(const double2 *)(tb + offc + e * es);
-            double2 r;
-            if (NC == 2) {
-                SdVal<2> hh, pp;
-                hh.c[0] = acc[e].x; hh.c[1] = acc[e].y; pp.c[0] = p.x; pp.c[1] = p.y;
-                const SdVal<2> rr = sd_epilogue<2>(E, hh, pp, li0 + (uint64_t)e * cls.pitch, red);
-                r = make_double2(rr.c[0], rr.c[1]);
-            } else {
-                SdVal<1> hh, pp;
-                hh.c[0] = acc[e].x; pp.c[0] = p.x;
-                const SdVal<1> r0 = sd_epilogue<1>(E, hh, pp, li0 + (uint64_t)e * cls.pitch, red);
-                hh.c[0] = acc[e].y; pp.c[0] = p.y;
-                const SdVal<1> r1 = sd_epilogue<1>(E, hh, pp, li0 + (uint64_t)e * cls.pitch + 1, red);
-                r = make_double2(r0.c[0], r1.c[0]);
-            }
-            *(double2 *)(o + e * es) = r;
+            const double2 p = sd_blk_lds<NC>(tb + offc + e * es);
+            SdVal<NC> hh, pp;
+            hh.c[0] = acc[e].x; pp.c[0] = p.x;
+            if (NC == 2) { hh.c[NC - 1] = acc[e].y; pp.c[NC - 1] = p.y; }
+            const SdVal<NC> rr = sd_epilogue<NC>(E, hh, pp, li0 + (uint64_t)e * cls.pitch, red);
+            if (NC == 2) *(double2 *)(o + e * es) = make_double2(rr.c[0], rr.c[NC - 1]);
+            else o[e * es] = rr.c[0];
         }
     }
 }
 
-// item code: jt << 12 | chunk << 8 | unit-in-class.  Chunks: NT = 10 -> two of 5; NT = 5 -> one; NT = 1 -> one.
+// item code: jt << 12 | chunk << 8 | unit-in-class (units of 32 mid configurations).
+// f64: one chunk per class (EC = NT).  c128: NT = 10 -> two chunks of 5.
 template <int NC, bool PLAIN>
 __device__ __forceinline__ void sd_blk_dispatch(const SdBlkCtx &X, const SdBlkHdr &H, const double *tb, unsigned code,
-                                                uint32_t ub, double (&red)[SD_NSLOT]) {
+                                                uint32_t u, double (&red)[SD_NSLOT]) {
     const int jt = (int)(code >> 12), E0 = ((code >> 8) & 0xFu) ? 5 : 0;
-    if (jt == 0 || jt == SD_BLK_T) sd_blk_item<NC, 1, PLAIN>(X, H, tb, jt, 0, ub, red);
-    else sd_blk_item<NC, 5, PLAIN>(X, H, tb, jt, E0, ub, red);
+    if (jt == 0 || jt == SD_BLK_T) sd_blk_item<NC, 1, PLAIN>(X, H, tb, jt, 0, u, red);
+    else if (NC == 1 && (jt == 2 || jt == 3)) sd_blk_item<NC, (NC == 1 ? 10 : 5), PLAIN>(X, H, tb, jt, 0, u, red);
+    else sd_blk_item<NC, 5, PLAIN>(X, H, tb, jt, E0, u, red);
 }
 
 // shared-memory carve-up
@@ -622,7 +587,6 @@ sd_blk_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constant
         X.pstart_local = P.shards.pstart[P.shards.rank];
         X.out_local = out_local;
         X.epi = &epi;
-        constexpr unsigned UW = 32u * (2 / NC);                    // blocks per unit
         const int slotmask = PLAIN ? 0 : sd_epi_slotmask(epi.red);
         for (unsigned i = 0;; ++i) {
             const int b = (int)(i % (unsigned)nbuf);
@@ -639,9 +603,9 @@ sd_blk_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constant
                 un = __shfl_sync(0xffffffffu, un, 0);
                 if (un >= nunits) break;
                 const unsigned code = ut[un];
-                const uint32_t ub = (code & 0xFFu) * UW + lane * (2 / NC);
+                const uint32_t u = (code & 0xFFu) * 32u + lane;      // the lane's mid configuration
                 double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
-                sd_blk_dispatch<NC, PLAIN>(X, H, tb, code, ub, red);
+                sd_blk_dispatch<NC, PLAIN>(X, H, tb, code, u, red);
                 if (!PLAIN && slotmask) {
 #pragma unroll
                     for (int s = 0; s < SD_NSLOT; ++s) {

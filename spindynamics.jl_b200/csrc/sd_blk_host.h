@@ -106,14 +106,14 @@ static inline bool sd_blk_build(int L, int k, const double *Jhop, const double *
         }
         I.size_pad = (run + 15u) & ~15u;
         cap = std::max(cap, I.size_pad);
-        for (int w = 0; w < 2; ++w) {                         // unit lists: w = 0 f64 (64 blocks), 1 c128 (32 blocks)
-            const uint32_t uw = w == 0 ? 64u : 32u;
+        for (int w = 0; w < 2; ++w) {                         // item lists: w = 0 f64, 1 c128 (units of 32 mid configurations)
+            const uint32_t uw = 32u;
             std::vector<std::pair<int, uint16_t>> list;       // (-NT, code): heavy classes first
             for (int jt = 0; jt <= T; ++jt) {
                 const SdBlkCls &c = I.cls[jt];
                 const uint32_t nu = (c.pitch + uw - 1) / uw;
                 const int nt = (int)C[T * SD_BINOM_DIM + jt];
-                const int nchunk = nt > 5 ? 2 : 1;                // sd_blk_dispatch: NT = 10 -> two chunks of 5
+                const int nchunk = (w == 1 && nt > 5) ? 2 : 1;    // sd_blk_dispatch: c128, NT = 10 -> two chunks of 5
                 for (uint32_t j = 0; j < nu; ++j)
                     for (int ch = 0; ch < nchunk; ++ch)
                         list.push_back({-(nt / nchunk), (uint16_t)((jt << 12) | (ch << 8) | j)});
