@@ -128,6 +128,11 @@ __device__ __forceinline__ void sd_bulk_g2s(void *dst, const void *src, unsigned
 __device__ __forceinline__ void sd_bulk_prefetch_l2(const void *src, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void sd_bulk_prefetch_l2_evict_first(const void *src, unsigned bytes) {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(src), "r"(bytes), "l"(pol) : "memory");
+}
 __device__ __forceinline__ double2 sd_ldg_v2(const double *p) {
     double2 v;
     asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
@@ -234,8 +239,18 @@ __device__ __forceinline__ void sd_blk_make_hdr(const SdBlkParams &P, const uint
 // per warp (f64: EC = 10 -> 20 + 60 registers; c128: EC = 5 -> 20 + 60).
 template <int NC> __device__ __forceinline__ double2 sd_blk_ldg(const double *p) {
     double2 v;
-    if (NC == 2) asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-    else { asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v.x) : "l"(p)); v.y = 0.0; }
+    // .cg: cached in L2 only (normal eviction priority); L1::no_allocate loads were measured to be treated
+    // as streaming by L2 as well (+6 GB of DRAM reads per apply at L = 32)
+    if (NC == 2) asm("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    else { asm("ld.global.cg.f64 %0, [%1];" : "=d"(v.x) : "l"(p)); v.y = 0.0; }
+    return v;
+}
+// load with an L2 eviction policy: far tiles (re-use distance beyond L2 reach) are read evict-first so
+// that they do not push near tiles out of L2
+template <int NC> __device__ __forceinline__ double2 sd_blk_ldg_pol(const double *p, uint64_t pol) {
+    double2 v;
+    if (NC == 2) asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+    else { asm("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v.x) : "l"(p), "l"(pol)); v.y = 0.0; }
     return v;
 }
 template <int NC> __device__ __forceinline__ double2 sd_blk_lds(const double *p) {
@@ -294,6 +309,7 @@ struct SdBlkCtx {
     const double *dmid;         // shared-memory copy [1 << M]
     const double *dtail;        // shared-memory copy
     const double *Jhop;         // shared-memory copy [L]
+    uint64_t pol_far, pol_near; // L2 eviction policies of the neighbour-tile loads
     double qx;                  // Jz of the mid|tail bond * 0.25
     double *out_local;          // local shard of out, component 0 of stored element 0
     uint64_t pstart_local;      // stored-element offset of the local shard
@@ -318,46 +334,43 @@ __device__ __forceinline__ void sd_blk_item(const SdBlkCtx &X, const SdBlkHdr &H
     double2 acc[EC];
 #pragma unroll
     for (int e = 0; e < EC; ++e) acc[e] = make_double2(0.0, 0.0);
-    // ---- prefix-internal bonds: whole neighbour tiles, same element order; three tiles in flight
-    if (!(P.dbg & 1)) {
-        const int nnb = H.nnb;
-        double2 t0[EC], t1[EC], t2[EC];
-#define SD_BLK_LOAD(t_, n_)                                                                   \
-        do {                                                                                  \
-            const bool ok_ = (n_) < nnb;                                                      \
-            const double *p_ = H.nb_ptr[n_] + offc;                                           \
-            _Pragma("unroll") for (int e = 0; e < EC; ++e)                                    \
-                t_[e] = ok_ ? sd_blk_ldg<NC>(p_ + e * es) : make_double2(0.0, 0.0);           \
-        } while (0)
-#define SD_BLK_FMA(t_, n_)                                                                    \
-        do {                                                                                  \
-            const double J_ = (n_) < nnb ? H.nb_J[n_] : 0.0;                                  \
-            _Pragma("unroll") for (int e = 0; e < EC; ++e) { acc[e].x += J_ * t_[e].x; if (NC == 2) acc[e].y += J_ * t_[e].y; } \
-        } while (0)
-        SD_BLK_LOAD(t0, 0); SD_BLK_LOAD(t1, 1); SD_BLK_LOAD(t2, 2);
-#pragma unroll 1
-        for (int n = 0; n < nnb; n += 3) {
-            SD_BLK_FMA(t0, n); SD_BLK_LOAD(t0, n + 3);
-            SD_BLK_FMA(t1, n + 1); SD_BLK_LOAD(t1, n + 4);
-            SD_BLK_FMA(t2, n + 2); SD_BLK_LOAD(t2, n + 5);
-        }
-#undef SD_BLK_LOAD
-#undef SD_BLK_FMA
-    }
     const bool c0 = u < cls.n1;                                       // first mid bit (blocks with it set come first)
-    // ---- prefix|mid crossing bond: partner tile with js +- 1, same class, uniform block shift
-    if (H.xptr && (c0 != (bool)H.bP)) {
+    // ---- neighbour-tile streams, software-pipelined three deep and interleaved with the shared-memory
+    // work of the same item (the loads of the next round fly while tail and mid hops run):
+    //   entries 0 .. nnb-1 : prefix-internal bonds, whole neighbour tiles in the same element order
+    //   entry   nnb        : prefix|mid crossing bond (partner tile with js +- 1, same class, uniform
+    //                        block shift), only for lanes whose first mid bit differs from the last prefix bit
+    const int nnb = (P.dbg & 1) ? 0 : H.nnb;
+    const bool hasx = H.xptr != nullptr;
+    const int ntot = nnb + (hasx ? 1 : 0);
+    const double *xp = nullptr;
+    uint32_t xs = 0;
+    bool xlane = false;
+    if (hasx) {
         const SdBlkCls cx = X.js[H.jsx].cls[jt];
-        const double J = H.Jx;
+        xlane = c0 != (bool)H.bP;
         const uint32_t u2 = H.bP ? u - cls.n1 : cx.n1 + u;
-        const uint32_t xs = cx.pitch * NC;
-        const double *p = H.xptr + (size_t)(cx.cb + u2) * NC + (size_t)E0 * xs;
-        double2 t[EC];
-#pragma unroll
-        for (int e = 0; e < EC; ++e) t[e] = sd_blk_ldg<NC>(p + e * xs);
-#pragma unroll
-        for (int e = 0; e < EC; ++e) { acc[e].x += J * t[e].x; if (NC == 2) acc[e].y += J * t[e].y; }
+        xs = cx.pitch * NC;
+        xp = H.xptr + (size_t)(cx.cb + (xlane ? u2 : 0u)) * NC + (size_t)E0 * xs;
     }
+    double2 t0[EC], t1[EC], t2[EC];
+#define SD_BLK_LOAD(t_, n_)                                                                   \
+    do {                                                                                      \
+        const int nn_ = (n_);                                                                 \
+        const bool isx_ = nn_ == nnb;                                                         \
+        const bool ok_ = nn_ < ntot && (!isx_ || xlane);                                      \
+        const double *p_ = isx_ ? xp : H.nb_ptr[nn_] + offc;                                  \
+        const uint32_t st_ = isx_ ? xs : es;                                                  \
+        _Pragma("unroll") for (int e = 0; e < EC; ++e)                                        \
+            t_[e] = ok_ ? sd_blk_ldg<NC>(p_ + e * st_) : make_double2(0.0, 0.0);              \
+    } while (0)
+#define SD_BLK_FMA(t_, n_)                                                                    \
+    do {                                                                                      \
+        const int nn_ = (n_);                                                                 \
+        const double J_ = nn_ < nnb ? H.nb_J[nn_] : (nn_ == nnb && hasx ? H.Jx : 0.0);        \
+        _Pragma("unroll") for (int e = 0; e < EC; ++e) { acc[e].x += J_ * t_[e].x; if (NC == 2) acc[e].y += J_ * t_[e].y; } \
+    } while (0)
+    SD_BLK_LOAD(t0, 0); SD_BLK_LOAD(t1, 1); SD_BLK_LOAD(t2, 2);
     // ---- own block: diagonal + tail-internal hops (registers)
     const unsigned cmid = it.w & ((1u << M) - 1u);
     const bool clast = (cmid >> (M - 1)) & 1u;
@@ -384,28 +397,41 @@ __device__ __forceinline__ void sd_blk_item(const SdBlkCtx &X, const SdBlkHdr &H
             }
         }
     }
-    // ---- mid-internal hops: the whole block moves to block nb[pm] of the same class
-    if (!(P.dbg & 2)) {
-        const double *cbp = tb + cls.cb * NC + E0 * es;
-        uint64_t lo = (uint64_t)it.x | ((uint64_t)it.y << 32);
-        uint32_t hi = it.z;
+    // ---- mid-internal hops (the whole block moves to block nb[pm] of the same class), three bonds per
+    // stream round so that shared-memory gathers overlap the global loads in flight
+    const double *cbp = tb + cls.cb * NC + E0 * es;
+    uint64_t lo = (uint64_t)it.x | ((uint64_t)it.y << 32);
+    uint32_t hi = it.z;
+    int pm = (P.dbg & 2) ? M : 0;
+#define SD_BLK_MID()                                                                          \
+    do {                                                                                      \
+        const double J = X.Jhop[P.A + pm];                                                    \
+        const unsigned nbu = (unsigned)(lo & 0xFFu);                                          \
+        lo = (lo >> 8) | ((uint64_t)hi << 56);                                                \
+        hi >>= 8;                                                                             \
+        ++pm;                                                                                 \
+        if (nbu != 0xFFu) {                                                                   \
+            const double *sp = cbp + nbu * NC;                                                \
+            _Pragma("unroll") for (int e = 0; e < EC; ++e) {                                  \
+                const double2 t = sd_blk_lds<NC>(sp + e * es);                                \
+                acc[e].x += J * t.x;                                                          \
+                if (NC == 2) acc[e].y += J * t.y;                                             \
+            }                                                                                 \
+        }                                                                                     \
+    } while (0)
 #pragma unroll 1
-        for (int pm = 0; pm + 1 < M; ++pm) {
-            const double J = X.Jhop[P.A + pm];
-            const unsigned nbu = (unsigned)(lo & 0xFFu);
-            lo = (lo >> 8) | ((uint64_t)hi << 56);
-            hi >>= 8;
-            if (nbu != 0xFFu) {
-                const double *sp = cbp + nbu * NC;
-#pragma unroll
-                for (int e = 0; e < EC; ++e) {
-                    const double2 t = sd_blk_lds<NC>(sp + e * es);
-                    acc[e].x += J * t.x;
-                    if (NC == 2) acc[e].y += J * t.y;
-                }
-            }
-        }
+    for (int n = 0; n < ntot; n += 3) {
+#pragma unroll 1
+        for (int k = 0; k < 3 && pm + 1 < M; ++k) SD_BLK_MID();
+        SD_BLK_FMA(t0, n); SD_BLK_LOAD(t0, n + 3);
+        SD_BLK_FMA(t1, n + 1); SD_BLK_LOAD(t1, n + 4);
+        SD_BLK_FMA(t2, n + 2); SD_BLK_LOAD(t2, n + 5);
     }
+#pragma unroll 1
+    while (pm + 1 < M) SD_BLK_MID();
+#undef SD_BLK_MID
+#undef SD_BLK_LOAD
+#undef SD_BLK_FMA
     // ---- mid|tail crossing bond.  Tail configurations with bit 0 set come first in a class:
     // n1 = C(T-1, jt-1) of them.  Last mid bit set & tail bit 0 clear -> class jt+1, row e - n1;
     // last mid bit clear & tail bit 0 set -> class jt-1, row C(T-1, jt-2) + e.
@@ -569,13 +595,16 @@ sd_blk_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constant
             constexpr uint32_t CH = 8192;
             for (uint32_t o = lane * CH; o < bytes; o += 32 * CH)
                 sd_bulk_g2s(dst + o, src + o, (bytes - o < CH) ? bytes - o : CH, &S.full[b]);
-            if (!(P.dbg & 8)) {                                    // far neighbour tiles: DRAM -> L2 ahead of the consumers
+            if (P.dbg & 8) {                                       // (off: measured +6 GB of DRAM reads) far neighbour tiles: DRAM -> L2 ahead of the consumers
                 const int nfar = H.nfar;
                 if ((int)lane < nfar) {
                     const double *p = H.nb_ptr[lane];
                     const double *lo = psi.base[P.shards.rank] + (size_t)NC * P.shards.pstart[P.shards.rank];
                     const double *hi = psi.base[P.shards.rank] + (size_t)NC * P.shards.pstart[P.shards.rank + 1];
-                    if (p >= lo && p < hi) sd_bulk_prefetch_l2(p, bytes);
+                    if (p >= lo && p < hi) {
+                        if (P.dbg & 32) sd_bulk_prefetch_l2(p, bytes);
+                        else sd_bulk_prefetch_l2_evict_first(p, bytes);
+                    }
                 }
             }
         }
@@ -584,6 +613,9 @@ sd_blk_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constant
         SdBlkCtx X;
         X.P = &P; X.js = S.js; X.dmid = S.dmid; X.dtail = S.dtail; X.Jhop = S.Jhop;
         X.qx = P.Jz[P.A + SD_BLK_M - 1] * 0.25;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(X.pol_far));
+        if (P.dbg & 64) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(X.pol_near));
+        else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(X.pol_near));
         X.pstart_local = P.shards.pstart[P.shards.rank];
         X.out_local = out_local;
         X.epi = &epi;
