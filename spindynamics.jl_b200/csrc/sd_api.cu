@@ -853,7 +853,7 @@ int sd_vec_set_onehot(sd_vec *v, uint64_t idx0) {
         if (v->layout) {
             const sd_model *m = v->model;
             const uint64_t st = sd_unrank_state(idx0, m->L, m->k, c->binom.data(), SD_BINOM_DIM);
-            off = sd_blk_pos_of_state(m->blk.host, st) - m->blk.pstart[c->rank];
+            off = sd_blk_pos_of_state(m->blk.host, st, v->nc) - m->blk.pstart[c->rank];
         }
         sd_set_one_kernel<<<1, 1, 0, c->stream>>>(v->d, off * v->nc);
         SD_TRY(sd_launch_check(c, "sd_set_one_kernel"));
@@ -886,6 +886,15 @@ int sd_vec_convert(sd_vec *dst, const sd_vec *src) {
     sd_ctx *c = dst->model->ctx;
     SD_TRY(sd_use(c));
     if (dst->local_n == 0) return SD_OK;
+    if (dst->layout || src->layout) {                // f64 and c128 block layouts order a class differently
+        SD_ARG(dst->layout && src->layout, "vectors differ in layout");
+        double *st = nullptr;
+        SD_TRY(sd_scratch(c, 0, sd_vec_logical_bytes(src) + 16, &st));
+        SD_TRY(sd_blk_permute(src, st, src->nc, 1, 0, 0, 0.0));
+        SD_TRY(sd_blk_permute(dst, st, src->nc, 0, 0, 0, 0.0));
+        sd_scratch_release(c);
+        return SD_OK;
+    }
     sd_convert_kernel<<<sd_blas_grid(c, dst->local_n), SD_BLAS_THREADS, 0, c->stream>>>(dst->d, src->d, dst->local_n, src->nc);
     return sd_launch_check(c, "sd_convert_kernel");
 }

@@ -5,13 +5,17 @@
 // Device vectors of a block-layout model are NOT stored in rank order.  The chain is
 // cut into  prefix (A sites) | mid (M sites) | tail (T sites); a TILE is one prefix
 // configuration (a contiguous rank range of the reference basis, Basis.jl:37-53).
-// Inside a tile the suffix configurations are stored
-//     class-major (class jt = tail popcount), element-major (e = index of the tail
-//     configuration inside its class), mid-configuration fastest (u = index of the mid
-//     configuration among those with js - jt set bits),
-// every (jt, e) row padded to a multiple of 4 elements and every tile to a multiple of
-// 16 elements (padding is zero and stays zero under every linear operation).  With this
-// order
+// Inside a tile the suffix configurations are stored class-major (class jt = tail popcount);
+// inside a class, with e = index of the tail configuration in its class (NT = C(T, jt) of them)
+// and u = index of the mid configuration among those with js - jt set bits (row pitch = their
+// number rounded up to 4):
+//     c128:  element (e, u) at  cb + e*pitch + u                       (one 16-byte value)
+//     f64 :  element (e, u) at  cb + (e/2)*2*pitch + 2u + (e & 1)      (pair rows: a 16-byte SLOT
+//            holds tail configurations 2s and 2s+1 of one mid configuration); the last
+//            configuration of an odd class is a plain row at  cb + (NT-1)*pitch + u  (half slot)
+// so that both types move 16-byte slots at  cb*NC + s*2*pitch + 2u  doubles, lanes = consecutive u.
+// Tiles are padded to a multiple of 16 elements; padding is zero and stays zero under every
+// linear operation.  With this order
 //   * a hop on a prefix bond maps a whole tile onto another whole tile, element by
 //     element: one thread that owns mid configuration u streams  acc[e] += J psi'[e][u]
 //     with fully coalesced 16-byte loads (lanes = consecutive u), no staging;
@@ -232,75 +236,91 @@ __device__ __forceinline__ void sd_blk_make_hdr(const SdBlkParams &P, const uint
 }
 
 // ------------------------------------------------------------------ per-item body
-// A work ITEM is (unit, element chunk): a lane owns ONE mid configuration u = ub + lane of class jt and
-// the EC tail configurations [E0, E0+EC) of it.  Values are held as double2: f64 uses .x only (the .y
-// arithmetic is dead code), c128 is (re, im) -- H is real, so both are plain real columns.
-// Register budget: acc[EC] + 3 x t[EC] values, which is what allows THREE neighbour tiles in flight
-// per warp (f64: EC = 10 -> 20 + 60 registers; c128: EC = 5 -> 20 + 60).
-template <int NC> __device__ __forceinline__ double2 sd_blk_ldg(const double *p) {
+// A work ITEM is (unit of 32 mid configurations, slot chunk): a lane owns ONE mid configuration u of
+// class jt.  All data moves as 16-byte SLOTS:
+//   f64 : slot s = tail configurations (2s, 2s+1) of the block  (pair rows, see the layout above)
+//   c128: slot s = tail configuration s, (re, im)
+// H is real, so a slot is two independent real columns for everything but the tail-internal hops and
+// the mid|tail crossing bond, which address single tail configurations.
+// Register budget: acc[EC] + 3 x t[EC] slots (EC <= 5 -> 20 + 60 registers), which is what allows
+// THREE neighbour tiles in flight per warp.
+__device__ __forceinline__ double2 sd_blk_ldg(const double *p) {
     double2 v;
     // .cg: cached in L2 only (normal eviction priority); L1::no_allocate loads were measured to be treated
     // as streaming by L2 as well (+6 GB of DRAM reads per apply at L = 32)
-    if (NC == 2) asm("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-    else { asm("ld.global.cg.f64 %0, [%1];" : "=d"(v.x) : "l"(p)); v.y = 0.0; }
+    asm("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
     return v;
 }
-// load with an L2 eviction policy: far tiles (re-use distance beyond L2 reach) are read evict-first so
-// that they do not push near tiles out of L2
-template <int NC> __device__ __forceinline__ double2 sd_blk_ldg_pol(const double *p, uint64_t pol) {
+__device__ __forceinline__ double2 sd_blk_ldg_half(const double *p) {
     double2 v;
-    if (NC == 2) asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
-    else { asm("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v.x) : "l"(p), "l"(pol)); v.y = 0.0; }
+    asm("ld.global.cg.f64 %0, [%1];" : "=d"(v.x) : "l"(p));
+    v.y = 0.0;
     return v;
 }
-template <int NC> __device__ __forceinline__ double2 sd_blk_lds(const double *p) {
-    if (NC == 2) return *(const double2 *)p;
-    return make_double2(*p, 0.0);
+__device__ __forceinline__ void sd_blk_stg(double *p, double2 v) {
+    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
 }
-template <int NC> __device__ __forceinline__ void sd_blk_stg(double *p, double2 v) {
-    if (NC == 2) asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
-    else asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(p), "d"(v.x) : "memory");
+__device__ __forceinline__ void sd_blk_stg_half(double *p, double v) {
+    asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 
-template <int NC, int JT, int E0, int EC, int t, int q>
+// tail-configuration accessors (e is a compile-time element index relative to the first element of
+// the chunk for acc, absolute for own)
+#define SD_BLK_EL(arr, e, NC_) (*((NC_) == 1 ? (((e) & 1) ? &arr[(e) >> 1].y : &arr[(e) >> 1].x) : &arr[(e)].x))
+
+template <int NC, int JT, int E0, int EC, int NO, int t, int q>
 struct SdBlkTailHop {
-    static constexpr int NT = sd_cbinom(SD_BLK_T, JT);
-    static __device__ __forceinline__ void run(double2 (&acc)[EC], const double2 (&own)[NT], const double *Jt) {
+    static __device__ __forceinline__ void run(double2 (&acc)[EC], const double2 (&own)[NO], const double *Jt) {
         constexpr unsigned cfg = sd_tail_cfg(SD_BLK_T, JT, E0 + t);
         constexpr bool act = (((cfg >> q) ^ (cfg >> (q + 1))) & 1u) != 0;
         if constexpr (act) {
             constexpr int t2 = sd_tail_rank(SD_BLK_T, JT, cfg ^ (3u << q));
             const double J = Jt[q];
-            acc[t].x += J * own[t2].x;
-            if (NC == 2) acc[t].y += J * own[t2].y;
+            if (NC == 1) {
+                SD_BLK_EL(acc, t, 1) += J * ((t2 & 1) ? own[t2 >> 1].y : own[t2 >> 1].x);
+            } else {
+                acc[t].x += J * own[t2].x;
+                acc[t].y += J * own[t2].y;
+            }
         }
-        if constexpr (q + 2 < SD_BLK_T) SdBlkTailHop<NC, JT, E0, EC, t, q + 1>::run(acc, own, Jt);
+        if constexpr (q + 2 < SD_BLK_T) SdBlkTailHop<NC, JT, E0, EC, NO, t, q + 1>::run(acc, own, Jt);
     }
 };
-template <int NC, int JT, int E0, int EC, int t>
+// NE = tail configurations in the chunk
+template <int NC, int JT, int E0, int NE, int EC, int NO, int t>
 struct SdBlkTailRow {
-    static constexpr int NT = sd_cbinom(SD_BLK_T, JT);
-    static __device__ __forceinline__ void run(double2 (&acc)[EC], const double2 (&own)[NT], const double *Jt,
+    static __device__ __forceinline__ void run(double2 (&acc)[EC], const double2 (&own)[NO], const double *Jt,
                                                const double *dtail, double d0, double dx0) {
         constexpr unsigned cfg = sd_tail_cfg(SD_BLK_T, JT, E0 + t);
         // + dx when tail bit 0 equals the last mid bit (dx already carries the sign of the last mid bit)
         const double d = d0 + dtail[cfg] + ((cfg & 1u) ? dx0 : -dx0);
-        acc[t].x += d * own[E0 + t].x;
-        if (NC == 2) acc[t].y += d * own[E0 + t].y;
-        SdBlkTailHop<NC, JT, E0, EC, t, 0>::run(acc, own, Jt);
-        if constexpr (t + 1 < EC) SdBlkTailRow<NC, JT, E0, EC, t + 1>::run(acc, own, Jt, dtail, d0, dx0);
+        if (NC == 1) {
+            SD_BLK_EL(acc, t, 1) += d * (((E0 + t) & 1) ? own[(E0 + t) >> 1].y : own[(E0 + t) >> 1].x);
+        } else {
+            acc[t].x += d * own[E0 + t].x;
+            acc[t].y += d * own[E0 + t].y;
+        }
+        SdBlkTailHop<NC, JT, E0, EC, NO, t, 0>::run(acc, own, Jt);
+        if constexpr (t + 1 < NE) SdBlkTailRow<NC, JT, E0, NE, EC, NO, t + 1>::run(acc, own, Jt, dtail, d0, dx0);
     }
 };
 // own block: diagonal + tail-internal hops.  The only part specialised on (class, chunk): the tail
 // configurations are compile-time constants, so tail hops are register moves.
-template <int NC, int JT, int E0, int EC>
-__device__ __forceinline__ void sd_blk_tail(double2 (&acc)[EC], const double *own_ptr, uint32_t es, const double *Jt,
-                                            const double *dtail, double d0, double dx0) {
+// E0/NE: first tail configuration / number of tail configurations of the chunk (f64: the whole class).
+template <int NC, int JT, int E0, int NE, int EC>
+__device__ __forceinline__ void sd_blk_tail(double2 (&acc)[EC], const double *own_ptr, uint32_t ss, uint32_t u,
+                                            const double *Jt, const double *dtail, double d0, double dx0) {
     constexpr int NT = sd_cbinom(SD_BLK_T, JT);
-    double2 own[NT];
+    constexpr int NO = NC == 1 ? (NT + 1) / 2 : NT;              // slots of the whole block
+    static_assert(NC == 2 || (E0 == 0 && NE == NT && EC == NO), "f64 items cover the whole class");
+    static_assert(NC == 1 || NE == EC, "c128 slots are tail configurations");
+    double2 own[NO];
 #pragma unroll
-    for (int e = 0; e < NT; ++e) own[e] = sd_blk_lds<NC>(own_ptr + e * es);
-    SdBlkTailRow<NC, JT, E0, EC, 0>::run(acc, own, Jt, dtail, d0, dx0);
+    for (int s = 0; s < NO; ++s) {
+        if (NC == 1 && (NT & 1) && s == NO - 1) own[s] = make_double2(own_ptr[s * ss - u], 0.0);   // half slot
+        else own[s] = *(const double2 *)(own_ptr + s * ss);
+    }
+    SdBlkTailRow<NC, JT, E0, NE, EC, NO, 0>::run(acc, own, Jt, dtail, d0, dx0);
 }
 
 struct SdBlkCtx {
@@ -309,31 +329,33 @@ struct SdBlkCtx {
     const double *dmid;         // shared-memory copy [1 << M]
     const double *dtail;        // shared-memory copy
     const double *Jhop;         // shared-memory copy [L]
-    uint64_t pol_far, pol_near; // L2 eviction policies of the neighbour-tile loads
     double qx;                  // Jz of the mid|tail bond * 0.25
     double *out_local;          // local shard of out, component 0 of stored element 0
     uint64_t pstart_local;      // stored-element offset of the local shard
     const SdEpi *epi;
 };
 
-// Everything except sd_blk_tail is generic in (jt, E0), which keeps the code small enough for the
+// Everything except sd_blk_tail is generic in (jt, S0), which keeps the code small enough for the
 // instruction cache (15 warps run different items at the same time).
-template <int NC, int EC, bool PLAIN>
-__device__ __forceinline__ void sd_blk_item(const SdBlkCtx &X, const SdBlkHdr &H, const double *tb, int jt, int E0,
+// S0 = first slot of the chunk (c128, classes of 10: 0 or 5; otherwise 0).
+// HALF: the last slot of the chunk is a half slot (f64 classes with an odd number of tail configurations:
+// the last configuration is stored as a plain row of doubles at cb + (NT-1)*pitch + u).
+template <int NC, int EC, bool HALF, bool PLAIN>
+__device__ __forceinline__ void sd_blk_item(const SdBlkCtx &X, const SdBlkHdr &H, const double *tb, int jt, int S0,
                                             uint32_t u, double (&red)[SD_NSLOT]) {
     constexpr int T = SD_BLK_T, M = SD_BLK_M;
     const SdBlkParams &P = *X.P;
     const SdBlkJs &I = X.js[H.js];
     const SdBlkCls cls = I.cls[jt];
     if (u >= cls.nblk) return;
-    const uint32_t es = cls.pitch * NC;                               // doubles between tail configurations
-    const uint32_t off0 = (cls.cb + u) * NC;                          // doubles, element (e = 0, u)
-    const uint32_t offc = off0 + E0 * es;                             // first element of the chunk
+    const uint32_t ss = 2u * cls.pitch;                               // doubles between slots (both dtypes)
+    const uint32_t off0 = cls.cb * NC + 2u * u;                       // doubles, slot 0 of the block
+    const uint32_t offc = off0 + S0 * ss;                             // first slot of the chunk
     // the lane's work item (L2-resident table): x,y,z = nb[12]; w = c | u2x << 16
     const uint4 it = __ldg((const uint4 *)(P.items + cls.item_off + u));
     double2 acc[EC];
 #pragma unroll
-    for (int e = 0; e < EC; ++e) acc[e] = make_double2(0.0, 0.0);
+    for (int s = 0; s < EC; ++s) acc[s] = make_double2(0.0, 0.0);
     const bool c0 = u < cls.n1;                                       // first mid bit (blocks with it set come first)
     // ---- neighbour-tile streams, software-pipelined three deep and interleaved with the shared-memory
     // work of the same item (the loads of the next round fly while tail and mid hops run):
@@ -344,14 +366,14 @@ __device__ __forceinline__ void sd_blk_item(const SdBlkCtx &X, const SdBlkHdr &H
     const bool hasx = H.xptr != nullptr;
     const int ntot = nnb + (hasx ? 1 : 0);
     const double *xp = nullptr;
-    uint32_t xs = 0;
+    uint32_t xs = 0, xu = 0;
     bool xlane = false;
     if (hasx) {
         const SdBlkCls cx = X.js[H.jsx].cls[jt];
         xlane = c0 != (bool)H.bP;
-        const uint32_t u2 = H.bP ? u - cls.n1 : cx.n1 + u;
-        xs = cx.pitch * NC;
-        xp = H.xptr + (size_t)(cx.cb + (xlane ? u2 : 0u)) * NC + (size_t)E0 * xs;
+        xu = xlane ? (H.bP ? u - cls.n1 : cx.n1 + u) : 0u;
+        xs = 2u * cx.pitch;
+        xp = H.xptr + (size_t)(cx.cb * NC + 2u * xu) + (size_t)S0 * xs;
     }
     double2 t0[EC], t1[EC], t2[EC];
 #define SD_BLK_LOAD(t_, n_)                                                                   \
@@ -360,15 +382,18 @@ __device__ __forceinline__ void sd_blk_item(const SdBlkCtx &X, const SdBlkHdr &H
         const bool isx_ = nn_ == nnb;                                                         \
         const bool ok_ = nn_ < ntot && (!isx_ || xlane);                                      \
         const double *p_ = isx_ ? xp : H.nb_ptr[nn_] + offc;                                  \
-        const uint32_t st_ = isx_ ? xs : es;                                                  \
-        _Pragma("unroll") for (int e = 0; e < EC; ++e)                                        \
-            t_[e] = ok_ ? sd_blk_ldg<NC>(p_ + e * st_) : make_double2(0.0, 0.0);              \
+        const uint32_t st_ = isx_ ? xs : ss;                                                  \
+        _Pragma("unroll") for (int s = 0; s < EC; ++s) {                                      \
+            if (HALF && s == EC - 1)                                                          \
+                t_[s] = ok_ ? sd_blk_ldg_half(p_ + s * st_ - (isx_ ? xu : u)) : make_double2(0.0, 0.0); \
+            else t_[s] = ok_ ? sd_blk_ldg(p_ + s * st_) : make_double2(0.0, 0.0);             \
+        }                                                                                     \
     } while (0)
 #define SD_BLK_FMA(t_, n_)                                                                    \
     do {                                                                                      \
         const int nn_ = (n_);                                                                 \
         const double J_ = nn_ < nnb ? H.nb_J[nn_] : (nn_ == nnb && hasx ? H.Jx : 0.0);        \
-        _Pragma("unroll") for (int e = 0; e < EC; ++e) { acc[e].x += J_ * t_[e].x; if (NC == 2) acc[e].y += J_ * t_[e].y; } \
+        _Pragma("unroll") for (int s = 0; s < EC; ++s) { acc[s].x += J_ * t_[s].x; acc[s].y += J_ * t_[s].y; } \
     } while (0)
     SD_BLK_LOAD(t0, 0); SD_BLK_LOAD(t1, 1); SD_BLK_LOAD(t2, 2);
     // ---- own block: diagonal + tail-internal hops (registers)
@@ -380,26 +405,30 @@ __device__ __forceinline__ void sd_blk_item(const SdBlkCtx &X, const SdBlkHdr &H
         const double *op = tb + off0;
         const double *Jt = X.Jhop + P.A + M;
         static_assert(SD_BLK_T == 5, "item chunking is written for T = 5");
+        static_assert(HALF == (NC == 1 && EC != 5), "half slots: f64 classes of 1 and 5");
         if constexpr (EC == 1) {
-            if (jt == 0) sd_blk_tail<NC, 0, 0, 1>(acc, op, es, Jt, X.dtail, d0, dx0);
-            else sd_blk_tail<NC, 5, 0, 1>(acc, op, es, Jt, X.dtail, d0, dx0);
-        } else if constexpr (EC == 10) {
-            if (jt == 2) sd_blk_tail<NC, 2, 0, 10>(acc, op, es, Jt, X.dtail, d0, dx0);
-            else sd_blk_tail<NC, 3, 0, 10>(acc, op, es, Jt, X.dtail, d0, dx0);
-        } else {
-            switch (jt * 2 + (E0 ? 1 : 0)) {
-                case 2: sd_blk_tail<NC, 1, 0, 5>(acc, op, es, Jt, X.dtail, d0, dx0); break;
-                case 4: sd_blk_tail<NC, 2, 0, 5>(acc, op, es, Jt, X.dtail, d0, dx0); break;
-                case 5: sd_blk_tail<NC, 2, 5, 5>(acc, op, es, Jt, X.dtail, d0, dx0); break;
-                case 6: sd_blk_tail<NC, 3, 0, 5>(acc, op, es, Jt, X.dtail, d0, dx0); break;
-                case 7: sd_blk_tail<NC, 3, 5, 5>(acc, op, es, Jt, X.dtail, d0, dx0); break;
-                default: sd_blk_tail<NC, 4, 0, 5>(acc, op, es, Jt, X.dtail, d0, dx0); break;
+            if (jt == 0) sd_blk_tail<NC, 0, 0, 1, 1>(acc, op, ss, u, Jt, X.dtail, d0, dx0);
+            else sd_blk_tail<NC, 5, 0, 1, 1>(acc, op, ss, u, Jt, X.dtail, d0, dx0);
+        } else if constexpr (EC == 3) {                            // f64, classes of 5 (+1 phantom)
+            if (jt == 1) sd_blk_tail<NC, 1, 0, 5, 3>(acc, op, ss, u, Jt, X.dtail, d0, dx0);
+            else sd_blk_tail<NC, 4, 0, 5, 3>(acc, op, ss, u, Jt, X.dtail, d0, dx0);
+        } else if constexpr (NC == 1) {                            // f64, classes of 10
+            if (jt == 2) sd_blk_tail<NC, 2, 0, 10, 5>(acc, op, ss, u, Jt, X.dtail, d0, dx0);
+            else sd_blk_tail<NC, 3, 0, 10, 5>(acc, op, ss, u, Jt, X.dtail, d0, dx0);
+        } else {                                                   // c128: chunks of 5 tail configurations
+            switch (jt * 2 + (S0 ? 1 : 0)) {
+                case 2: sd_blk_tail<NC, 1, 0, 5, 5>(acc, op, ss, u, Jt, X.dtail, d0, dx0); break;
+                case 4: sd_blk_tail<NC, 2, 0, 5, 5>(acc, op, ss, u, Jt, X.dtail, d0, dx0); break;
+                case 5: sd_blk_tail<NC, 2, 5, 5, 5>(acc, op, ss, u, Jt, X.dtail, d0, dx0); break;
+                case 6: sd_blk_tail<NC, 3, 0, 5, 5>(acc, op, ss, u, Jt, X.dtail, d0, dx0); break;
+                case 7: sd_blk_tail<NC, 3, 5, 5, 5>(acc, op, ss, u, Jt, X.dtail, d0, dx0); break;
+                default: sd_blk_tail<NC, 4, 0, 5, 5>(acc, op, ss, u, Jt, X.dtail, d0, dx0); break;
             }
         }
     }
     // ---- mid-internal hops (the whole block moves to block nb[pm] of the same class), three bonds per
     // stream round so that shared-memory gathers overlap the global loads in flight
-    const double *cbp = tb + cls.cb * NC + E0 * es;
+    const double *cbp = tb + cls.cb * NC + S0 * ss;
     uint64_t lo = (uint64_t)it.x | ((uint64_t)it.y << 32);
     uint32_t hi = it.z;
     int pm = (P.dbg & 2) ? M : 0;
@@ -411,11 +440,15 @@ __device__ __forceinline__ void sd_blk_item(const SdBlkCtx &X, const SdBlkHdr &H
         hi >>= 8;                                                                             \
         ++pm;                                                                                 \
         if (nbu != 0xFFu) {                                                                   \
-            const double *sp = cbp + nbu * NC;                                                \
-            _Pragma("unroll") for (int e = 0; e < EC; ++e) {                                  \
-                const double2 t = sd_blk_lds<NC>(sp + e * es);                                \
-                acc[e].x += J * t.x;                                                          \
-                if (NC == 2) acc[e].y += J * t.y;                                             \
+            const double *sp = cbp + 2u * nbu;                                                \
+            _Pragma("unroll") for (int s = 0; s < EC; ++s) {                                  \
+                if (HALF && s == EC - 1) {                                                    \
+                    acc[s].x += J * sp[s * ss - nbu];                                         \
+                } else {                                                                      \
+                    const double2 t = *(const double2 *)(sp + s * ss);                        \
+                    acc[s].x += J * t.x;                                                      \
+                    acc[s].y += J * t.y;                                                      \
+                }                                                                             \
             }                                                                                 \
         }                                                                                     \
     } while (0)
@@ -432,61 +465,94 @@ __device__ __forceinline__ void sd_blk_item(const SdBlkCtx &X, const SdBlkHdr &H
 #undef SD_BLK_MID
 #undef SD_BLK_LOAD
 #undef SD_BLK_FMA
-    // ---- mid|tail crossing bond.  Tail configurations with bit 0 set come first in a class:
-    // n1 = C(T-1, jt-1) of them.  Last mid bit set & tail bit 0 clear -> class jt+1, row e - n1;
-    // last mid bit clear & tail bit 0 set -> class jt-1, row C(T-1, jt-2) + e.
+    // ---- mid|tail crossing bond, per tail configuration.  Tail configurations with bit 0 set come first
+    // in a class: n1 = C(T-1, jt-1) of them.  Last mid bit set & tail bit 0 clear -> class jt+1,
+    // configuration e - n1; last mid bit clear & tail bit 0 set -> class jt-1, configuration C(T-1, jt-2) + e.
     {
         const double J = X.Jhop[P.A + M - 1];
-        // nibble i of the constant = C(4, i-2) (T = 5)
+        // nibble i of the constant = C(4, i-2) (T = 5); nt = C(5, jt)
         const int n1 = (int)((0x01464100u >> (4 * (jt + 1))) & 0xFu), n1p = (int)((0x01464100u >> (4 * jt)) & 0xFu);
+        const int nt = (int)((0x15AA51u >> (4 * jt)) & 0xFu);
         const int jt2 = clast ? jt + 1 : jt - 1;
         if (jt2 >= 0 && jt2 <= T) {
             const SdBlkCls c2 = I.cls[jt2];
-            const double *sp = tb + (c2.cb + (it.w >> 16)) * NC;
-            const uint32_t s2 = c2.pitch * NC;
-            const int shift = clast ? -n1 : n1p;                   // partner row = e + shift
+            const uint32_t u2x = it.w >> 16;
+            const double *sp = tb + c2.cb * NC + 2u * u2x;             // slot 0 of the partner block
+            const uint32_t s2 = 2u * c2.pitch;
+            const int nt2 = (int)((0x15AA51u >> (4 * jt2)) & 0xFu);
+            const int shift = clast ? -n1 : n1p;                   // partner configuration = e + shift
+            constexpr int NEL = NC == 1 ? 2 * EC : EC;             // tail configurations covered by the chunk
+            const int e0 = NC == 1 ? 0 : S0;
 #pragma unroll
-            for (int e = 0; e < EC; ++e) {
-                const int ee = E0 + e;
-                if (clast ? (ee >= n1) : (ee < n1)) {
-                    const double2 t = sd_blk_lds<NC>(sp + (ee + shift) * s2);
-                    acc[e].x += J * t.x;
-                    if (NC == 2) acc[e].y += J * t.y;
+            for (int e = 0; e < NEL; ++e) {
+                const int ee = e0 + e;
+                if (ee < nt && (clast ? (ee >= n1) : (ee < n1))) {
+                    const int e2 = ee + shift;
+                    if (NC == 1) {
+                        // the last configuration of an odd class is a plain row of doubles
+                        const double t = ((nt2 & 1) && e2 == nt2 - 1) ? sp[(e2 >> 1) * s2 - u2x] : sp[(e2 >> 1) * s2 + (e2 & 1)];
+                        SD_BLK_EL(acc, e, 1) += J * t;
+                    } else {
+                        const double2 t = *(const double2 *)(sp + e2 * s2);
+                        acc[e].x += J * t.x;
+                        acc[e].y += J * t.y;
+                    }
                 }
             }
         }
     }
     // ---- epilogue + store
-    const uint64_t li0 = H.base - X.pstart_local + cls.cb + (uint64_t)E0 * cls.pitch + u;   // local stored element of (E0, u)
-    double *o = X.out_local + (size_t)li0 * NC;
+    const uint64_t ld0 = (H.base - X.pstart_local) * NC + offc;    // doubles from the start of the local shard
+    double *o = X.out_local + ld0;
     if (PLAIN) {
-        if (P.dbg & 4) { if (acc[0].x == 1.2345e300) sd_blk_stg<NC>(o, acc[0]); return; }
+        if (P.dbg & 4) { if (acc[0].x == 1.2345e300) sd_blk_stg(o, acc[0]); return; }
 #pragma unroll
-        for (int e = 0; e < EC; ++e) sd_blk_stg<NC>(o + e * es, acc[e]);
+        for (int s = 0; s < EC; ++s) {
+            if (HALF && s == EC - 1) sd_blk_stg_half(o + s * ss - u, acc[s].x);
+            else sd_blk_stg(o + s * ss, acc[s]);
+        }
     } else {
         const SdEpi &E = *X.epi;
 #pragma unroll
-        for (int e = 0; e < EC; ++e) {
-            const double2 p = sd_blk_lds<NC>(tb + offc + e * es);
-            SdVal<NC> hh, pp;
-            hh.c[0] = acc[e].x; pp.c[0] = p.x;
-            if (NC == 2) { hh.c[NC - 1] = acc[e].y; pp.c[NC - 1] = p.y; }
-            const SdVal<NC> rr = sd_epilogue<NC>(E, hh, pp, li0 + (uint64_t)e * cls.pitch, red);
-            if (NC == 2) *(double2 *)(o + e * es) = make_double2(rr.c[0], rr.c[NC - 1]);
-            else o[e * es] = rr.c[0];
+        for (int s = 0; s < EC; ++s) {
+            if (HALF && s == EC - 1) {
+                const uint64_t ld = ld0 + (uint64_t)s * ss - u;
+                SdVal<1> hh, pp;
+                hh.c[0] = acc[s].x; pp.c[0] = tb[offc + s * ss - u];
+                const SdVal<1> r0 = sd_epilogue<1>(E, hh, pp, ld, red);
+                o[s * ss - u] = r0.c[0];
+                continue;
+            }
+            const double2 p = *(const double2 *)(tb + offc + s * ss);
+            const uint64_t ld = ld0 + (uint64_t)s * ss;
+            double2 r;
+            if (NC == 2) {
+                SdVal<2> hh, pp;
+                hh.c[0] = acc[s].x; hh.c[1] = acc[s].y; pp.c[0] = p.x; pp.c[1] = p.y;
+                const SdVal<2> rr = sd_epilogue<2>(E, hh, pp, ld / 2, red);
+                r = make_double2(rr.c[0], rr.c[1]);
+            } else {
+                SdVal<1> hh, pp;
+                hh.c[0] = acc[s].x; pp.c[0] = p.x;
+                const SdVal<1> r0 = sd_epilogue<1>(E, hh, pp, ld, red);
+                hh.c[0] = acc[s].y; pp.c[0] = p.y;
+                const SdVal<1> r1 = sd_epilogue<1>(E, hh, pp, ld + 1, red);
+                r = make_double2(r0.c[0], r1.c[0]);
+            }
+            *(double2 *)(o + s * ss) = r;
         }
     }
 }
 
 // item code: jt << 12 | chunk << 8 | unit-in-class (units of 32 mid configurations).
-// f64: one chunk per class (EC = NT).  c128: NT = 10 -> two chunks of 5.
+// f64: one chunk per class (1, 3 or 5 slots).  c128: classes of 10 -> two chunks of 5 slots.
 template <int NC, bool PLAIN>
 __device__ __forceinline__ void sd_blk_dispatch(const SdBlkCtx &X, const SdBlkHdr &H, const double *tb, unsigned code,
                                                 uint32_t u, double (&red)[SD_NSLOT]) {
-    const int jt = (int)(code >> 12), E0 = ((code >> 8) & 0xFu) ? 5 : 0;
-    if (jt == 0 || jt == SD_BLK_T) sd_blk_item<NC, 1, PLAIN>(X, H, tb, jt, 0, u, red);
-    else if (NC == 1 && (jt == 2 || jt == 3)) sd_blk_item<NC, (NC == 1 ? 10 : 5), PLAIN>(X, H, tb, jt, 0, u, red);
-    else sd_blk_item<NC, 5, PLAIN>(X, H, tb, jt, E0, u, red);
+    const int jt = (int)(code >> 12), S0 = ((code >> 8) & 0xFu) ? 5 : 0;
+    if (jt == 0 || jt == SD_BLK_T) sd_blk_item<NC, 1, NC == 1, PLAIN>(X, H, tb, jt, 0, u, red);
+    else if (NC == 1 && (jt == 1 || jt == SD_BLK_T - 1)) sd_blk_item<NC, (NC == 1 ? 3 : 5), NC == 1, PLAIN>(X, H, tb, jt, 0, u, red);
+    else sd_blk_item<NC, 5, false, PLAIN>(X, H, tb, jt, S0, u, red);
 }
 
 // shared-memory carve-up
@@ -613,9 +679,6 @@ sd_blk_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constant
         SdBlkCtx X;
         X.P = &P; X.js = S.js; X.dmid = S.dmid; X.dtail = S.dtail; X.Jhop = S.Jhop;
         X.qx = P.Jz[P.A + SD_BLK_M - 1] * 0.25;
-        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(X.pol_far));
-        if (P.dbg & 64) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(X.pol_near));
-        else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(X.pol_near));
         X.pstart_local = P.shards.pstart[P.shards.rank];
         X.out_local = out_local;
         X.epi = &epi;
@@ -714,8 +777,17 @@ __global__ void __launch_bounds__(256) sd_blk_permute_kernel(const __grid_consta
             bool real = jt >= 0;
             uint32_t e = 0, u = 0;
             if (real) {
-                e = rel / I.cls[jt].pitch; u = rel % I.cls[jt].pitch;
-                real = u < I.cls[jt].nblk;
+                const uint32_t pitch = I.cls[jt].pitch;
+                const uint32_t nt = (uint32_t)sd_cbinom(SD_BLK_T, jt);
+                if (Q.nc_blk == 1 && (nt & 1u) && rel >= (nt - 1u) * pitch) {   // f64, odd class: last row is plain
+                    e = nt - 1u; u = rel - (nt - 1u) * pitch;
+                } else if (Q.nc_blk == 1) {                        // f64: pair rows (2s, 2s+1) of double2 per block
+                    const uint32_t pr = rel / (2u * pitch), r2 = rel % (2u * pitch);
+                    u = r2 >> 1; e = 2u * pr + (r2 & 1u);
+                } else {                                           // c128: one row per tail configuration
+                    e = rel / pitch; u = rel % pitch;
+                }
+                real = u < I.cls[jt].nblk && e < (uint32_t)sd_cbinom(SD_BLK_T, jt);
             }
             double *bp = blk_local + (size_t)(pbase + p) * Q.nc_blk;
             if (!real) {

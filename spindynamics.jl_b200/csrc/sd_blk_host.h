@@ -164,8 +164,8 @@ static inline uint64_t sd_blk_key_base(const SdBlkHost &o, uint64_t key) {
     if (key >= (1ULL << o.P.A)) return o.n_store;
     return sd_blk_tile_base(o, sd_blk_prefix_bits(key, o.P.A));
 }
-// stored-element offset of basis state s (popcount k)
-static inline uint64_t sd_blk_pos_of_state(const SdBlkHost &o, uint64_t s) {
+// stored-element offset of basis state s (popcount k) in a vector of nc components per element
+static inline uint64_t sd_blk_pos_of_state(const SdBlkHost &o, uint64_t s, int nc) {
     constexpr int M = SD_BLK_M, T = SD_BLK_T;
     const int A = o.P.A;
     const uint64_t Pb = s & ((1ULL << A) - 1ULL);
@@ -175,5 +175,9 @@ static inline uint64_t sd_blk_pos_of_state(const SdBlkHost &o, uint64_t s) {
     const int js = o.P.k - __builtin_popcountll(Pb);
     const SdBlkCls &cl = o.js[js].cls[jt];
     const uint32_t e = (uint32_t)sd_tail_rank(T, jt, tau);
-    return sd_blk_tile_base(o, Pb) + cl.cb + (uint64_t)e * cl.pitch + o.urank[c];
+    const uint32_t u = o.urank[c];
+    const uint32_t nt = (uint32_t)sd_cbinom(T, jt);
+    if (nc == 1 && (nt & 1u) && e == nt - 1u) return sd_blk_tile_base(o, Pb) + cl.cb + (uint64_t)e * cl.pitch + u;
+    if (nc == 1) return sd_blk_tile_base(o, Pb) + cl.cb + (uint64_t)(e >> 1) * 2u * cl.pitch + 2u * u + (e & 1u);
+    return sd_blk_tile_base(o, Pb) + cl.cb + (uint64_t)e * cl.pitch + u;
 }
