@@ -149,7 +149,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--path", default=None, choices=[None, "tiled", "generic"])
+    ap.add_argument("--path", default=None, choices=[None, "block", "tiled", "generic"])
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -263,7 +263,7 @@ def main():
             except Exception:
                 traffic = None
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "peak_source": peak_src, "kernel": f"sd_tile_apply_kernel ({model.info['kernel_path']})",
+                    "traffic": traffic, "peak_source": peak_src, "kernel": {"block": "sd_blk_apply_kernel", "tiled": "sd_tile_apply_kernel"}.get(model.info["kernel_path"], "sd_generic_apply_kernel"),
                     "algorithmic_bytes_per_launch": alg_bytes // world,
                     "note": "16 B/state f64 (32 c128): one read of psi + one write of out; index math is on the fly"}
         cpu = None

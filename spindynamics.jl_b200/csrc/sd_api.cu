@@ -1248,6 +1248,25 @@ int sd_lincomb(sd_vecset *s, const sd_complex *y, int mcount, sd_vec *out, doubl
     sd_ctx *c = m->ctx;
     SD_TRY(sd_use(c));
     SD_ARG(2 * mcount <= 2048, "too many vectors");
+    if (out->layout && out->nc == 2 && v0->nc == 1) {
+        // the f64 and c128 block layouts order a class differently (pair rows): combine through a
+        // converted copy of each member (Krylov recombination of a real basis, once per solve)
+        sd_vec *tmp = nullptr;
+        SD_TRY(sd_vec_alloc(m, SD_C128, &tmp));
+        int rc = sd_vec_zero(out);
+        for (int j = 0; j < mcount && rc == SD_OK; ++j) {
+            rc = sd_vec_convert(tmp, s->v[j]);
+            if (rc == SD_OK) rc = sd_vec_axpy(out, y[j], tmp);
+        }
+        sd_vec_free(tmp);
+        SD_TRY(rc);
+        if (norm2) {
+            double nrm = 0.0;
+            SD_TRY(sd_vec_norm(out, &nrm));
+            *norm2 = nrm * nrm;
+        }
+        return SD_OK;
+    }
     // coefficients -> device (pinned staging, ordered on the stream)
     SD_CUDA(cudaStreamSynchronize(c->stream));
     for (int j = 0; j < mcount; ++j) { c->h_scal[1024 + 2 * j] = y[j].re; c->h_scal[1024 + 2 * j + 1] = y[j].im; }

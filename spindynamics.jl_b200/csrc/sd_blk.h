@@ -317,7 +317,7 @@ __device__ __forceinline__ void sd_blk_tail(double2 (&acc)[EC], const double *ow
     double2 own[NO];
 #pragma unroll
     for (int s = 0; s < NO; ++s) {
-        if (NC == 1 && (NT & 1) && s == NO - 1) own[s] = make_double2(own_ptr[s * ss - u], 0.0);   // half slot
+        if (NC == 1 && (NT & 1) && s == NO - 1) own[s] = make_double2(*(own_ptr + s * ss - u), 0.0);   // half slot
         else own[s] = *(const double2 *)(own_ptr + s * ss);
     }
     SdBlkTailRow<NC, JT, E0, NE, EC, NO, 0>::run(acc, own, Jt, dtail, d0, dx0);
@@ -443,7 +443,7 @@ __device__ __forceinline__ void sd_blk_item(const SdBlkCtx &X, const SdBlkHdr &H
             const double *sp = cbp + 2u * nbu;                                                \
             _Pragma("unroll") for (int s = 0; s < EC; ++s) {                                  \
                 if (HALF && s == EC - 1) {                                                    \
-                    acc[s].x += J * sp[s * ss - nbu];                                         \
+                    acc[s].x += J * *(sp + s * ss - nbu);                                        \
                 } else {                                                                      \
                     const double2 t = *(const double2 *)(sp + s * ss);                        \
                     acc[s].x += J * t.x;                                                      \
@@ -490,7 +490,7 @@ __device__ __forceinline__ void sd_blk_item(const SdBlkCtx &X, const SdBlkHdr &H
                     const int e2 = ee + shift;
                     if (NC == 1) {
                         // the last configuration of an odd class is a plain row of doubles
-                        const double t = ((nt2 & 1) && e2 == nt2 - 1) ? sp[(e2 >> 1) * s2 - u2x] : sp[(e2 >> 1) * s2 + (e2 & 1)];
+                        const double t = ((nt2 & 1) && e2 == nt2 - 1) ? *(sp + (e2 >> 1) * s2 - u2x) : *(sp + (e2 >> 1) * s2 + (e2 & 1));
                         SD_BLK_EL(acc, e, 1) += J * t;
                     } else {
                         const double2 t = *(const double2 *)(sp + e2 * s2);
@@ -520,7 +520,7 @@ __device__ __forceinline__ void sd_blk_item(const SdBlkCtx &X, const SdBlkHdr &H
                 SdVal<1> hh, pp;
                 hh.c[0] = acc[s].x; pp.c[0] = tb[offc + s * ss - u];
                 const SdVal<1> r0 = sd_epilogue<1>(E, hh, pp, ld, red);
-                o[s * ss - u] = r0.c[0];
+                *(o + s * ss - u) = r0.c[0];                    // pointer arithmetic: s * ss - u alone wraps in u32
                 continue;
             }
             const double2 p = *(const double2 *)(tb + offc + s * ss);

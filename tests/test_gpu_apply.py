@@ -28,6 +28,19 @@ def rand_vec(rng, n, dtype):
     return v.astype(dtype)
 
 
+def paths_of(m):
+    """Every kernel path the model qualifies for ("block" stores vectors in block layout, so a
+    path switch is only legal while no DeviceVector of the model is alive)."""
+    out = []
+    for p in ("block", "tiled", "generic"):
+        try:
+            m.set_path(p)
+            out.append(p)
+        except NotImplementedError:
+            pass
+    return out
+
+
 def both(L, nup=None, Jxy=1.0, Jz=1.0, hz=0.0, boundary="open"):
     return (sd.XXZChain(L, Jxy=Jxy, Jz=Jz, hz=hz, nup=nup, boundary=boundary),
             orc.XXZChain(L, Jxy=Jxy, Jz=Jz, hz=hz, nup=nup, boundary=boundary))
@@ -105,8 +118,7 @@ def test_apply_H_matches_oracle(L, nup, boundary, dtype):
     psi = rand_vec(rng, m.dim, dtype)
     ref = np.empty_like(psi)
     orc.apply_H_(ref, psi, om)
-    paths = ["generic"] + (["tiled"] if m.info["kernel_path"] == "tiled" else [])
-    for path in paths:
+    for path in paths_of(m):
         m.set_path(path)
         out = np.full_like(psi, np.nan)
         assert sd.apply_H_(out, psi, m) is out
@@ -114,7 +126,11 @@ def test_apply_H_matches_oracle(L, nup, boundary, dtype):
 
 
 def test_tiled_path_selected_for_open_chain():
-    assert sd.XXZChain(16, nup=8).info["kernel_path"] == "tiled"
+    assert sd.XXZChain(16, nup=8).info["kernel_path"] == "block"
+    assert sd.XXZChain(14, nup=7).info["kernel_path"] == "tiled"
+    assert paths_of(sd.XXZChain(20, nup=10)) == ["block", "tiled", "generic"]
+    with pytest.raises(NotImplementedError):
+        sd.XXZChain(14, nup=7).set_path("block")
     assert sd.XXZChain(16, nup=8, boundary="periodic").info["kernel_path"] == "generic"
     assert sd.XXZChain(12).info["kernel_path"] == "generic"
     with pytest.raises(NotImplementedError):
@@ -125,21 +141,23 @@ def test_tiled_path_selected_for_open_chain():
 def test_apply_H_random_couplings_and_long_range(dtype):
     """Arbitrary per-bond J / Jz / per-site field (tiled) and long-range lists (generic)."""
     rng = np.random.default_rng(7)
+    for (L, nup, default) in [(14, 6, "tiled"), (17, 8, "block"), (18, 5, "block")]:
+        hop = [(i, i + 1, rng.uniform(0.2, 1.5)) for i in range(1, L)]
+        zz = [(i, i + 1, rng.uniform(-1, 1)) for i in range(1, L)]
+        fld = rng.uniform(-1, 1, L)
+        m = sd.build_model(L, nup=nup, hopping=hop, onsite_field=fld, zz=zz)
+        om = orc.build_model(L, nup=nup, hopping=hop, onsite_field=fld, zz=zz)
+        assert m.info["kernel_path"] == default
+        psi = rand_vec(rng, m.dim, dtype)
+        ref = np.empty_like(psi)
+        orc.apply_H_(ref, psi, om)
+        for path in paths_of(m):
+            m.set_path(path)
+            out = np.empty_like(psi)
+            sd.apply_H_(out, psi, m)
+            assert rel(out, ref) < TOL, (L, nup, path)
     L, nup = 14, 6
-    hop = [(i, i + 1, rng.uniform(0.2, 1.5)) for i in range(1, L)]
-    zz = [(i, i + 1, rng.uniform(-1, 1)) for i in range(1, L)]
     fld = rng.uniform(-1, 1, L)
-    m = sd.build_model(L, nup=nup, hopping=hop, onsite_field=fld, zz=zz)
-    om = orc.build_model(L, nup=nup, hopping=hop, onsite_field=fld, zz=zz)
-    assert m.info["kernel_path"] == "tiled"
-    psi = rand_vec(rng, m.dim, dtype)
-    ref = np.empty_like(psi)
-    orc.apply_H_(ref, psi, om)
-    for path in ("tiled", "generic"):
-        m.set_path(path)
-        out = np.empty_like(psi)
-        sd.apply_H_(out, psi, m)
-        assert rel(out, ref) < TOL
     hop = sd.long_range_hopping(L, lambda i, j: 1.0 / abs(i - j) ** 2)
     zz = [(i, j, 0.5 / abs(i - j)) for i in range(1, L + 1) for j in range(i + 1, L + 1)]
     for nup_ in (nup, None):
@@ -183,10 +201,9 @@ def test_apply_H_argument_errors():
 def test_rescaled_and_cheb_step_fusions(dtype):
     """apply_rescaled_H! (Hamiltonian.jl:286-301) and the fused Chebyshev step
     (KPM_Sqw.jl:111-117, Chebyshev.jl:112-116) against numpy on oracle H.psi."""
-    L, nup = 14, 7
     a, b = 3.7, -0.4
     rng = np.random.default_rng(3)
-    for path in ("tiled", "generic"):
+    for (L, nup, path) in [(14, 7, "tiled"), (14, 7, "generic"), (17, 8, "block"), (16, 9, "block")]:
         m, om = both(L, nup, Jz=0.8)
         m.set_path(path)
         v = rand_vec(rng, m.dim, dtype)
@@ -282,7 +299,7 @@ def test_golden_fixture():
         m = sd.XXZChain(L, Jxy=float(g["Jxy"]), Jz=float(g["Jz"]), hz=float(g["hz"]), nup=nup)
         cplx = kind == "c128"
         psi = orc.fill_seeded(m.dim, int(g["seed"]), cplx=cplx)
-        for path in ("tiled", "generic"):
+        for path in paths_of(m):
             m.set_path(path)
             out = np.empty_like(psi)
             sd.apply_H_(out, psi, m)
@@ -311,10 +328,16 @@ def test_large_sampled_rows_and_linearity(L, nup):
     for r, s in zip(rows[:50], st):
         ref = orc.row_seeded_f64((L, nup, hop, zz, np.zeros(L)), int(s), seed)
         assert abs(out[r] - ref) <= 1e-13 * max(1.0, abs(ref)), (r, out[r], ref)
-    m.set_path("generic")
-    hg = m.vector(np.float64)
-    sd.apply_H_(hg, x, m)
-    assert rel(hg.to_host(), out) < TOL
+    assert m.info["kernel_path"] == "block"
+    del hy, y
+    for path in ("tiled", "generic"):                                # rank-ordered vectors: a second model
+        m2 = sd.XXZChain(L, nup=nup)
+        m2.set_path(path)
+        x2 = m2.vector(np.float64).fill_seeded(seed)
+        hg = m2.vector(np.float64)
+        sd.apply_H_(hg, x2, m2)
+        assert rel(hg.to_host(), out) < TOL, path
+        del x2, hg, m2
 
 
 def om_lists(L, Jxy=1.0, Jz=1.0):
