@@ -994,6 +994,17 @@ int sd_vec_norm(const sd_vec *x, double *result) {
 }
 
 // ----------------------------------------------------------------- operator
+// A rank whose shard holds no tile (fewer tiles than ranks, tiny models only) launches nothing but must
+// still contribute zeros to the cross-rank sum of the fused reductions: every rank calls the same
+// sequence of NCCL collectives.
+static int sd_empty_shard_reduce(sd_ctx *c, int slotmask, int slot_out) {
+    if (!slotmask) return SD_OK;
+    SD_CUDA(cudaMemsetAsync(c->d_scal + slot_out, 0, SD_NSLOT * sizeof(double), c->stream));
+    if (c->world > 1)
+        SD_NCCL(g_nccl.AllReduce(c->d_scal + slot_out, c->d_scal + slot_out, SD_NSLOT, ncclFloat64_, ncclSum_,
+                                 c->comm, c->stream));
+    return SD_OK;
+}
 // Launches one apply kernel with the given epilogue; reductions (if any) land
 // in d_scal[slot_out .. slot_out+3].
 static int sd_apply_impl(sd_model *m, sd_vec *out, const sd_vec *psi, SdEpi epi, int slot_out) {
@@ -1011,7 +1022,7 @@ static int sd_apply_impl(sd_model *m, sd_vec *out, const sd_vec *psi, SdEpi epi,
     if (m->path == SD_PATH_BLOCK) {
         SdBlkParams P = sd_blk_params(m, nc);
         const uint64_t nkeys = P.key_hi - P.key_lo;
-        if (nkeys == 0) return SD_OK;
+        if (nkeys == 0) return sd_empty_shard_reduce(c, slotmask, slot_out);
         SD_ARG(nkeys < 0x7fffffffULL, "too many tiles for one launch");
         const unsigned grid = (unsigned)std::min<uint64_t>(nkeys, (uint64_t)c->sm_count);
         if (slotmask) {
@@ -1045,7 +1056,7 @@ static int sd_apply_impl(sd_model *m, sd_vec *out, const sd_vec *psi, SdEpi epi,
         P.key_lo = t.keys[c->rank];
         P.key_hi = t.keys[c->rank + 1];
         const uint64_t nkeys = P.key_hi - P.key_lo;
-        if (nkeys == 0) return SD_OK;
+        if (nkeys == 0) return sd_empty_shard_reduce(c, slotmask, slot_out);
         SD_ARG(nkeys < 0x7fffffffULL, "too many tiles for one launch");
         const unsigned grid = (unsigned)nkeys;           // one CTA per tile, in rank order
         if (slotmask) SD_TRY(sd_partials_reserve(c, (size_t)SD_NSLOT * grid));
