@@ -101,55 +101,13 @@ SD_HD uint64_t sd_blk_prefix_bits(uint64_t key, int A) {
     return Pb;
 }
 
-#if defined(__CUDACC__)
-// ------------------------------------------------------------------ PTX helpers
-__device__ __forceinline__ unsigned sd_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void sd_mbar_init(uint64_t *b, unsigned cnt) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sd_smem_u32(b)), "r"(cnt) : "memory");
-}
-__device__ __forceinline__ void sd_mbar_expect_tx(uint64_t *b, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sd_smem_u32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void sd_mbar_arrive(uint64_t *b) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sd_smem_u32(b)) : "memory");
-}
-__device__ __forceinline__ void sd_mbar_wait(uint64_t *b, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "SD_WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra SD_DONE_%=;\n"
-        "bra SD_WAIT_%=;\n"
-        "SD_DONE_%=:\n"
-        "}" ::"r"(sd_smem_u32(b)), "r"(parity) : "memory");
-}
-// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (16-byte aligned, size % 16 == 0)
-__device__ __forceinline__ void sd_bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(sd_smem_u32(dst)), "l"(src), "r"(bytes), "r"(sd_smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void sd_bulk_prefetch_l2(const void *src, unsigned bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void sd_bulk_prefetch_l2_evict_first(const void *src, unsigned bytes) {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(src), "r"(bytes), "l"(pol) : "memory");
-}
-__device__ __forceinline__ double2 sd_ldg_v2(const double *p) {
-    double2 v;
-    asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ double2 sd_ldg_v2_far(const double *p) {
-    double2 v;
-    asm("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ void sd_stg_v2(double *p, double2 v) {
-    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
-}
+#if !defined(__CUDACC__)
+// host build (tests/emul/emul_blk.cpp runs the item body on the CPU): the CUDA vector types it uses
+#include <cstring>
+struct alignas(16) double2 { double x, y; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+static inline double2 make_double2(double x, double y) { double2 v; v.x = x; v.y = y; return v; }
+#endif
 
 // ------------------------------------------------------------------ tile header
 struct SdBlkHdr {
@@ -169,44 +127,54 @@ struct SdBlkHdr {
     double usum[SD_NSLOT][SD_BLK_MAXUNITS];   // per-unit reduction results (deterministic: summed in unit order)
 };
 
-// warp-wide: lane q = prefix position q.  W[q*(A+1) + below] lives in shared memory.
-template <int NC>
-__device__ __forceinline__ void sd_blk_make_hdr(const SdBlkParams &P, const uint64_t *W, uint64_t key, SdBlkHdr &H,
-                                                const SdVecView &psi, int qfar, unsigned lane) {
-    const int A = P.A, k = P.k, q = (int)lane;
-    const uint64_t Pb = __brevll(~key) >> (64 - A);               // A >= 1
-    const int js = k - __popcll(Pb);
+// Header of tile `key`, one LANE per prefix position q (the kernel runs it warp-wide and sums with
+// shuffles, tests/emul loops over the lanes).  W[q*(A+1) + below] lives in shared memory.
+SD_HD uint64_t sd_blk_key_prefix(uint64_t key, int A) {
+#if defined(__CUDA_ARCH__)
+    return __brevll(~key) >> (64 - A);                            // A >= 1
+#else
+    return sd_blk_prefix_bits(key, A);
+#endif
+}
+struct SdBlkHdrLane {
+    uint64_t term, wq, wn;       // rank-base contribution; W of this site / of the bond partner
+    double d;                    // diagonal contribution of site q and bond (q, q+1)
+    int bit;
+    bool act;                    // bond (q, q+1) is an active prefix-internal hop
+};
+SD_HD SdBlkHdrLane sd_blk_hdr_lane(const SdBlkParams &P, const uint64_t *W, uint64_t Pb, int q) {
+    const int A = P.A;
+    SdBlkHdrLane l;
     const int bit = (int)((Pb >> q) & 1ULL), bn = (int)((Pb >> (q + 1)) & 1ULL);
-    const int below = __popcll(Pb & ((1ULL << q) - 1ULL));
-    uint64_t term = 0, wq = 0, wn = 0;
-    double d = 0.0;
-    bool act = false;
+    const int below = SD_POPC64(Pb & ((1ULL << q) - 1ULL));
+    l.term = 0; l.wq = 0; l.wn = 0; l.d = 0.0; l.act = false; l.bit = bit;
     if (q < A) {
-        wq = W[q * (A + 1) + below];
-        if (!bit) term = wq;
+        l.wq = W[q * (A + 1) + below];
+        if (!bit) l.term = l.wq;
         const double sq = bit ? 0.5 : -0.5;
-        d = P.h[q] * sq;
+        l.d = P.h[q] * sq;
         if (q + 1 < A) {
-            d += P.Jz[q] * sq * (bn ? 0.5 : -0.5);
-            act = (bit != bn) && (P.Jhop[q] != 0.0);
-            if (act) wn = W[(q + 1) * (A + 1) + below + 1];
+            l.d += P.Jz[q] * sq * (bn ? 0.5 : -0.5);
+            l.act = (bit != bn) && (P.Jhop[q] != 0.0);
+            if (l.act) l.wn = W[(q + 1) * (A + 1) + below + 1];
         }
     }
-    uint64_t base = term;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) base += __shfl_xor_sync(0xffffffffu, base, o);
-    double dpre = d;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) dpre += __shfl_xor_sync(0xffffffffu, dpre, o);
-    const unsigned actmask = __ballot_sync(0xffffffffu, act);
+    return l;
+}
+// second half, after the warp-wide sums base = sum(term), dpre = sum(d), actmask = ballot(act)
+template <int NC>
+SD_HD void sd_blk_hdr_fill(const SdBlkParams &P, const SdBlkHdrLane &l, uint64_t Pb, uint64_t key, uint64_t base, double dpre,
+                           unsigned actmask, int qfar, int q, SdBlkHdr &H, const SdVecView &psi) {
+    const int A = P.A, js = P.k - SD_POPC64(Pb);
+    const int bit = l.bit;
     const unsigned farmask = (qfar >= 32) ? 0xffffffffu : ((1u << qfar) - 1u);
-    const int nfar = __popc(actmask & farmask);
-    if (act) {
+    const int nfar = SD_POPC32(actmask & farmask);
+    if (l.act) {
         // (1,0) -> (0,1): + (W[q][below] - W[q+1][below+1]);  (0,1) -> (1,0): the negative
-        const uint64_t dl = wq - wn;
+        const uint64_t dl = l.wq - l.wn;
         const uint64_t nbase = bit ? base + dl : base - dl;
         const unsigned lt = (1u << q) - 1u;
-        const int slot = ((farmask >> q) & 1u) ? __popc(actmask & farmask & lt) : nfar + __popc(actmask & ~farmask & lt);
+        const int slot = ((farmask >> q) & 1u) ? SD_POPC32(actmask & farmask & lt) : nfar + SD_POPC32(actmask & ~farmask & lt);
         H.nb_ptr[slot] = psi.base[sd_blk_owner(P.shards, nbase)] + (size_t)NC * nbase;
         H.nb_J[slot] = P.Jhop[q];
     }
@@ -214,7 +182,7 @@ __device__ __forceinline__ void sd_blk_make_hdr(const SdBlkParams &P, const uint
         const int jsx = bit ? js + 1 : js - 1;
         const double J = P.Jhop[q];
         const bool ok = (J != 0.0) && jsx >= 0 && jsx <= SD_BLK_B;
-        const uint64_t nbase = bit ? base + wq : base - wq;
+        const uint64_t nbase = bit ? base + l.wq : base - l.wq;
         H.jsx = jsx;
         H.Jx = ok ? J : 0.0;
         H.xptr = ok ? psi.base[sd_blk_owner(P.shards, nbase)] + (size_t)NC * nbase : nullptr;
@@ -223,17 +191,33 @@ __device__ __forceinline__ void sd_blk_make_hdr(const SdBlkParams &P, const uint
         H.dP[0] = dpre + P.Jz[q] * sl * (-0.5);
         H.dP[1] = dpre + P.Jz[q] * sl * (0.5);
     }
-    if (lane == 0) {
+    if (q == 0) {
         H.base = base;
         H.js = js;
         H.valid = 1;
-        H.nnb = __popc(actmask);
+        H.nnb = SD_POPC32(actmask);
         H.nfar = nfar;
         H.next_unit = 0;
         H.done_units = 0;
         H.tile_index = (unsigned)(key - P.key_lo);
     }
 }
+#if defined(__CUDACC__)
+template <int NC>
+__device__ __forceinline__ void sd_blk_make_hdr(const SdBlkParams &P, const uint64_t *W, uint64_t key, SdBlkHdr &H,
+                                                const SdVecView &psi, int qfar, unsigned lane) {
+    const uint64_t Pb = sd_blk_key_prefix(key, P.A);
+    const SdBlkHdrLane l = sd_blk_hdr_lane(P, W, Pb, (int)lane);
+    uint64_t base = l.term;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) base += __shfl_xor_sync(0xffffffffu, base, o);
+    double dpre = l.d;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dpre += __shfl_xor_sync(0xffffffffu, dpre, o);
+    const unsigned actmask = __ballot_sync(0xffffffffu, l.act);
+    sd_blk_hdr_fill<NC>(P, l, Pb, key, base, dpre, actmask, qfar, (int)lane, H, psi);
+}
+#endif
 
 // ------------------------------------------------------------------ per-item body
 // A work ITEM is (unit of 32 mid configurations, slot chunk): a lane owns ONE mid configuration u of
@@ -244,24 +228,51 @@ __device__ __forceinline__ void sd_blk_make_hdr(const SdBlkParams &P, const uint
 // the mid|tail crossing bond, which address single tail configurations.
 // Register budget: acc[EC] + 3 x t[EC] slots (EC <= 5 -> 20 + 60 registers), which is what allows
 // THREE neighbour tiles in flight per warp.
-__device__ __forceinline__ double2 sd_blk_ldg(const double *p) {
+// The body compiles for host and device: tests/emul/emul_blk.cpp runs it on the CPU, lane by lane, against
+// the oracle (index algebra, layout, epilogues, shard ownership without a GPU).
+SD_HD double2 sd_blk_ldg(const double *p) {
     double2 v;
+#if defined(__CUDA_ARCH__)
     // .cg: cached in L2 only (normal eviction priority); L1::no_allocate loads were measured to be treated
     // as streaming by L2 as well (+6 GB of DRAM reads per apply at L = 32)
     asm("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+#else
+    v.x = p[0]; v.y = p[1];
+#endif
     return v;
 }
-__device__ __forceinline__ double2 sd_blk_ldg_half(const double *p) {
+SD_HD double2 sd_blk_ldg_half(const double *p) {
     double2 v;
+#if defined(__CUDA_ARCH__)
     asm("ld.global.cg.f64 %0, [%1];" : "=d"(v.x) : "l"(p));
+#else
+    v.x = p[0];
+#endif
     v.y = 0.0;
     return v;
 }
-__device__ __forceinline__ void sd_blk_stg(double *p, double2 v) {
+SD_HD void sd_blk_stg(double *p, double2 v) {
+#if defined(__CUDA_ARCH__)
     asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+#else
+    p[0] = v.x; p[1] = v.y;
+#endif
 }
-__device__ __forceinline__ void sd_blk_stg_half(double *p, double v) {
+SD_HD void sd_blk_stg_half(double *p, double v) {
+#if defined(__CUDA_ARCH__)
     asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+#else
+    p[0] = v;
+#endif
+}
+SD_HD uint4 sd_blk_ld_item(const SdBlkItem *p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg((const uint4 *)p);
+#else
+    uint4 v;
+    memcpy(&v, p, sizeof(v));
+    return v;
+#endif
 }
 
 // tail-configuration accessors (e is a compile-time element index relative to the first element of
@@ -270,7 +281,7 @@ __device__ __forceinline__ void sd_blk_stg_half(double *p, double v) {
 
 template <int NC, int JT, int E0, int EC, int NO, int t, int q>
 struct SdBlkTailHop {
-    static __device__ __forceinline__ void run(double2 (&acc)[EC], const double2 (&own)[NO], const double *Jt) {
+    static SD_HD void run(double2 (&acc)[EC], const double2 (&own)[NO], const double *Jt) {
         constexpr unsigned cfg = sd_tail_cfg(SD_BLK_T, JT, E0 + t);
         constexpr bool act = (((cfg >> q) ^ (cfg >> (q + 1))) & 1u) != 0;
         if constexpr (act) {
@@ -289,7 +300,7 @@ struct SdBlkTailHop {
 // NE = tail configurations in the chunk
 template <int NC, int JT, int E0, int NE, int EC, int NO, int t>
 struct SdBlkTailRow {
-    static __device__ __forceinline__ void run(double2 (&acc)[EC], const double2 (&own)[NO], const double *Jt,
+    static SD_HD void run(double2 (&acc)[EC], const double2 (&own)[NO], const double *Jt,
                                                const double *dtail, double d0, double dx0) {
         constexpr unsigned cfg = sd_tail_cfg(SD_BLK_T, JT, E0 + t);
         // + dx when tail bit 0 equals the last mid bit (dx already carries the sign of the last mid bit)
@@ -308,7 +319,7 @@ struct SdBlkTailRow {
 // configurations are compile-time constants, so tail hops are register moves.
 // E0/NE: first tail configuration / number of tail configurations of the chunk (f64: the whole class).
 template <int NC, int JT, int E0, int NE, int EC>
-__device__ __forceinline__ void sd_blk_tail(double2 (&acc)[EC], const double *own_ptr, uint32_t ss, uint32_t u,
+SD_HD void sd_blk_tail(double2 (&acc)[EC], const double *own_ptr, uint32_t ss, uint32_t u,
                                             const double *Jt, const double *dtail, double d0, double dx0) {
     constexpr int NT = sd_cbinom(SD_BLK_T, JT);
     constexpr int NO = NC == 1 ? (NT + 1) / 2 : NT;              // slots of the whole block
@@ -341,7 +352,7 @@ struct SdBlkCtx {
 // HALF: the last slot of the chunk is a half slot (f64 classes with an odd number of tail configurations:
 // the last configuration is stored as a plain row of doubles at cb + (NT-1)*pitch + u).
 template <int NC, int EC, bool HALF, bool PLAIN>
-__device__ __forceinline__ void sd_blk_item(const SdBlkCtx &X, const SdBlkHdr &H, const double *tb, int jt, int S0,
+SD_HD void sd_blk_item(const SdBlkCtx &X, const SdBlkHdr &H, const double *tb, int jt, int S0,
                                             uint32_t u, double (&red)[SD_NSLOT]) {
     constexpr int T = SD_BLK_T, M = SD_BLK_M;
     const SdBlkParams &P = *X.P;
@@ -352,7 +363,7 @@ __device__ __forceinline__ void sd_blk_item(const SdBlkCtx &X, const SdBlkHdr &H
     const uint32_t off0 = cls.cb * NC + 2u * u;                       // doubles, slot 0 of the block
     const uint32_t offc = off0 + S0 * ss;                             // first slot of the chunk
     // the lane's work item (L2-resident table): x,y,z = nb[12]; w = c | u2x << 16
-    const uint4 it = __ldg((const uint4 *)(P.items + cls.item_off + u));
+    const uint4 it = sd_blk_ld_item(P.items + cls.item_off + u);
     double2 acc[EC];
 #pragma unroll
     for (int s = 0; s < EC; ++s) acc[s] = make_double2(0.0, 0.0);
@@ -547,7 +558,7 @@ __device__ __forceinline__ void sd_blk_item(const SdBlkCtx &X, const SdBlkHdr &H
 // item code: jt << 12 | chunk << 8 | unit-in-class (units of 32 mid configurations).
 // f64: one chunk per class (1, 3 or 5 slots).  c128: classes of 10 -> two chunks of 5 slots.
 template <int NC, bool PLAIN>
-__device__ __forceinline__ void sd_blk_dispatch(const SdBlkCtx &X, const SdBlkHdr &H, const double *tb, unsigned code,
+SD_HD void sd_blk_dispatch(const SdBlkCtx &X, const SdBlkHdr &H, const double *tb, unsigned code,
                                                 uint32_t u, double (&red)[SD_NSLOT]) {
     const int jt = (int)(code >> 12), S0 = ((code >> 8) & 0xFu) ? 5 : 0;
     if (jt == 0 || jt == SD_BLK_T) sd_blk_item<NC, 1, NC == 1, PLAIN>(X, H, tb, jt, 0, u, red);
@@ -592,6 +603,56 @@ SD_HD size_t sd_blk_smem_carve(SdBlkSmem *s, void *base, int A, int L, int nbuf,
         s->Jhop = (double *)(b + a_J); s->tiles = (double *)(b + a_tiles);
     }
     return (o + 127) & ~(size_t)127;
+}
+
+#if defined(__CUDACC__)
+// ------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ unsigned sd_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sd_mbar_init(uint64_t *b, unsigned cnt) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sd_smem_u32(b)), "r"(cnt) : "memory");
+}
+__device__ __forceinline__ void sd_mbar_expect_tx(uint64_t *b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sd_smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sd_mbar_arrive(uint64_t *b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sd_smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void sd_mbar_wait(uint64_t *b, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "SD_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra SD_DONE_%=;\n"
+        "bra SD_WAIT_%=;\n"
+        "SD_DONE_%=:\n"
+        "}" ::"r"(sd_smem_u32(b)), "r"(parity) : "memory");
+}
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (16-byte aligned, size % 16 == 0)
+__device__ __forceinline__ void sd_bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(sd_smem_u32(dst)), "l"(src), "r"(bytes), "r"(sd_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void sd_bulk_prefetch_l2(const void *src, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sd_bulk_prefetch_l2_evict_first(const void *src, unsigned bytes) {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(src), "r"(bytes), "l"(pol) : "memory");
+}
+__device__ __forceinline__ double2 sd_ldg_v2(const double *p) {
+    double2 v;
+    asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double2 sd_ldg_v2_far(const double *p) {
+    double2 v;
+    asm("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void sd_stg_v2(double *p, double2 v) {
+    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
 }
 
 // ------------------------------------------------------------------ the kernel

@@ -1,0 +1,180 @@
+// emul_blk.cpp -- CPU emulation of the block-layout CUDA kernel (sd_blk.h).
+//
+// TEST INFRASTRUCTURE ONLY.  The product (libspindyn_cuda.so) never loads this; it exists so
+// `pytest -m "not gpu"` can check, in a container without a GPU, everything of the block kernel
+// that is arithmetic rather than plumbing: the padded block layout (f64 pair rows / c128 rows), the
+// tile header (tile bases, neighbour-tile pointers, owner GPU of a neighbour, crossing partner), the
+// item body (prefix streams, tail/mid/crossing hops, diagonal, fused epilogues and their reductions)
+// and the tile-aligned sharding.  It runs the SAME __host__ __device__ functions the kernel runs
+// (sd_blk_hdr_lane / sd_blk_hdr_fill / sd_blk_dispatch), lane by lane, one tile at a time; what it does
+// not cover is the TMA/mbarrier producer-consumer pipeline, which moves bytes but computes nothing.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "../../spindynamics.jl_b200/csrc/sd_tile_host.h"
+#include "../../spindynamics.jl_b200/csrc/sd_blk_host.h"
+
+namespace {
+
+struct AlignedBuf {                      // 128-byte aligned doubles (the kernel moves 16-byte slots)
+    double *p = nullptr;
+    size_t n = 0;
+    void alloc(size_t count, double fill) {
+        n = count;
+        void *q = nullptr;
+        if (posix_memalign(&q, 128, (count + 16) * sizeof(double)) != 0) q = nullptr;
+        p = (double *)q;
+        for (size_t i = 0; i < count + 16; ++i) p[i] = fill;
+    }
+    ~AlignedBuf() { free(p); }
+};
+
+template <int NC, bool PLAIN>
+void run_tiles(const SdBlkHost &bh, const SdBlkParams &P, const SdVecView &psi, double *out_local, const SdEpi &epi,
+               int qfar, double *red_total) {
+    AlignedBuf tile;
+    tile.alloc((size_t)P.cap * NC, NAN);
+    SdBlkCtx X;
+    X.P = &P; X.js = bh.js.data(); X.dmid = bh.dmid.data(); X.dtail = P.dtail; X.Jhop = P.Jhop;
+    X.qx = P.Jz[P.A + SD_BLK_M - 1] * 0.25;
+    X.pstart_local = P.shards.pstart[P.shards.rank];
+    X.out_local = out_local;
+    X.epi = &epi;
+    for (uint64_t key = P.key_lo; key < P.key_hi; ++key) {
+        const uint64_t Pb = sd_blk_key_prefix(key, P.A);
+        const int js = P.k - SD_POPC64(Pb);
+        if (js < 0 || js > SD_BLK_B) continue;                     // impossible suffix popcount
+        // ---- header: what the producer warp computes with shuffles
+        SdBlkHdr H;
+        std::memset(&H, 0, sizeof(H));
+        SdBlkHdrLane lanes[32];
+        uint64_t base = 0;
+        double dpre = 0.0;
+        unsigned actmask = 0;
+        for (int q = 0; q < 32; ++q) {
+            lanes[q] = sd_blk_hdr_lane(P, bh.W.data(), Pb, q);
+            base += lanes[q].term;
+            dpre += lanes[q].d;
+            if (lanes[q].act) actmask |= 1u << q;
+        }
+        for (int q = 0; q < 32; ++q) sd_blk_hdr_fill<NC>(P, lanes[q], Pb, key, base, dpre, actmask, qfar, q, H, psi);
+        // pipeline overrun entries: valid pointer, J = 0 (the kernel never dereferences them: ok_ is false)
+        // ---- own tile -> "shared memory" (the TMA bulk copy); the rest of the buffer stays NaN
+        const uint32_t size_pad = bh.js[H.js].size_pad;
+        for (size_t i = 0; i < (size_t)P.cap * NC; ++i) tile.p[i] = NAN;
+        std::memcpy(tile.p, psi.base[P.shards.rank] + (size_t)NC * H.base, (size_t)size_pad * NC * sizeof(double));
+        // ---- work items in list order, 32 lanes each
+        const unsigned nunits = bh.js[H.js].nunits[NC - 1];
+        const uint16_t *ut = bh.units.data() + ((size_t)(NC - 1) * (SD_BLK_B + 1) + H.js) * SD_BLK_MAXUNITS;
+        for (unsigned un = 0; un < nunits; ++un) {
+            const unsigned code = ut[un];
+            for (unsigned lane = 0; lane < 32; ++lane) {
+                const uint32_t u = (code & 0xFFu) * 32u + lane;
+                double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
+                sd_blk_dispatch<NC, PLAIN>(X, H, tile.p, code, u, red);
+                for (int s = 0; s < SD_NSLOT; ++s) red_total[s] += red[s];
+            }
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+// Runs rank `rank` of `world` of the block kernel over full-length RANK-ORDERED host vectors (the
+// layout conversion the library does in sd_vec_upload/download is done here with sd_blk_pos_of_state).
+// states[N]: the basis in rank order (from the oracle).  psi/out (and vprev/phi/acc) hold NC doubles per
+// state.  out/acc are written for the states of this rank's shard only.
+// Returns 0; -1 model does not qualify; -2 a padding element of out became nonzero; -3 a position
+// collision / out-of-range position in the layout map.
+int emul_blk_apply(int L, int k, const double *Jhop, const double *Jz, const double *h, int NC,
+                   const uint64_t *states, uint64_t N, const double *psi, double *out,
+                   int world, int rank, int mode, int redmask, double hscale, double a, double b,
+                   const double *vprev, const double *phi, double *acc, double ck_re, double ck_im,
+                   double *red_out, uint64_t *bounds_out, uint64_t far_bytes, uint64_t *n_store_out) {
+    SdBlkHost bh;
+    if (!sd_blk_build(L, k, Jhop, Jz, h, bh)) return -1;
+    SdTileHost th;                                                  // shard bounds come from the tiled split (same tile keys)
+    if (!sd_tile_build(L, k, SD_BLK_B, 5, Jhop, Jz, h, th)) return -1;
+    uint64_t bounds[SD_MAX_WORLD + 1], keys[SD_MAX_WORLD + 1];
+    sd_tile_shard_bounds(th, world, bounds, keys);
+    SdBlkParams P = bh.P;
+    P.W = bh.W.data(); P.js = bh.js.data(); P.units = bh.units.data(); P.items = bh.items.data(); P.dmid = bh.dmid.data();
+    P.nbuf = 3; P.dbg = 0;
+    P.key_lo = keys[rank]; P.key_hi = keys[rank + 1];
+    P.shards.world = world; P.shards.rank = rank;
+    uint64_t pstart[SD_MAX_WORLD + 1];
+    for (int g = 0; g <= world; ++g) pstart[g] = sd_blk_key_base(bh, keys[g]);
+    for (int g = 0; g <= SD_MAX_WORLD; ++g) P.shards.pstart[g] = pstart[g < world ? g : world];
+    if (bounds_out) for (int g = 0; g <= world; ++g) bounds_out[g] = bounds[g];
+    if (n_store_out) *n_store_out = bh.n_store;
+    const int qfar = sd_tile_qfar(L, P.A, bh.binom.data(), far_bytes, 8 * NC);
+
+    // ---- layout map: stored position of every basis state, checked to be a bijection onto non-padding slots
+    std::vector<uint64_t> pos(N);
+    {
+        std::vector<unsigned char> used(bh.n_store, 0);
+        for (uint64_t r = 0; r < N; ++r) {
+            const uint64_t p = sd_blk_pos_of_state(bh, states[r], NC);
+            if (p >= bh.n_store || used[p]) return -3;
+            used[p] = 1;
+            pos[r] = p;
+        }
+    }
+    auto to_blk = [&](const double *src, std::vector<AlignedBuf> &shard, SdVecView *view) {
+        shard.clear();
+        shard.resize(world);
+        for (int g = 0; g < world; ++g) {
+            shard[g].alloc((size_t)(pstart[g + 1] - pstart[g]) * NC, 0.0);
+            if (view) view->base[g] = shard[g].p - (int64_t)pstart[g] * NC;
+        }
+        for (uint64_t r = 0; r < N; ++r) {
+            int g = 0;
+            while (g + 1 < world && pos[r] >= pstart[g + 1]) ++g;
+            for (int c = 0; c < NC; ++c) shard[g].p[(pos[r] - pstart[g]) * NC + c] = src[r * NC + c];
+        }
+    };
+    SdVecView view;
+    for (int g = 0; g < SD_MAX_WORLD; ++g) view.base[g] = nullptr;
+    std::vector<AlignedBuf> s_psi, s_prev, s_phi, s_acc;
+    to_blk(psi, s_psi, &view);
+    const size_t nloc = (size_t)(pstart[rank + 1] - pstart[rank]) * NC;
+    AlignedBuf o;
+    o.alloc(nloc, 0.0);                                             // sd_vec_alloc zero-fills block-layout vectors
+    SdEpi epi;
+    std::memset(&epi, 0, sizeof(epi));
+    epi.mode = mode; epi.red = redmask; epi.hscale = hscale; epi.a = a; epi.b = b;
+    epi.ck_re = ck_re; epi.ck_im = ck_im;
+    if (vprev) { to_blk(vprev, s_prev, nullptr); epi.vprev = s_prev[rank].p; }
+    if (phi) { to_blk(phi, s_phi, nullptr); epi.phi = s_phi[rank].p; }
+    if (acc) { to_blk(acc, s_acc, nullptr); epi.acc = s_acc[rank].p; }
+    double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
+    const bool plain = epi.mode == SD_EPI_PLAIN && epi.red == 0 && !epi.acc && epi.hscale == 1.0;
+    if (NC == 1) {
+        if (plain) run_tiles<1, true>(bh, P, view, o.p, epi, qfar, red);
+        else run_tiles<1, false>(bh, P, view, o.p, epi, qfar, red);
+    } else {
+        if (plain) run_tiles<2, true>(bh, P, view, o.p, epi, qfar, red);
+        else run_tiles<2, false>(bh, P, view, o.p, epi, qfar, red);
+    }
+    if (red_out) for (int s = 0; s < SD_NSLOT; ++s) red_out[s] = red[s];
+    // ---- back to rank order; padding must still be zero
+    std::vector<unsigned char> real(nloc / NC, 0);
+    for (uint64_t r = bounds[rank]; r < bounds[rank + 1]; ++r) {
+        const uint64_t lp = pos[r] - pstart[rank];
+        real[lp] = 1;
+        for (int c = 0; c < NC; ++c) {
+            out[r * NC + c] = o.p[lp * NC + c];
+            if (acc) acc[r * NC + c] = s_acc[rank].p[lp * NC + c];
+        }
+    }
+    for (size_t i = 0; i < nloc / NC; ++i)
+        if (!real[i])
+            for (int c = 0; c < NC; ++c)
+                if (o.p[i * NC + c] != 0.0) return -2;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,227 @@
+"""CPU checks of the block-layout kernel (sd_blk.h, the headline H.psi kernel):
+tests/emul/emul_blk.cpp runs the SAME __host__ __device__ functions the CUDA kernel
+runs (tile header lanes, item body, fused epilogue), lane by lane, on block-layout
+copies of the inputs and is compared with the oracle.  Covers the padded f64
+pair-row / c128 row layout (bijection onto non-padding slots, padding stays zero),
+tile bases and neighbour-tile pointers, prefix streams, tail / mid / crossing hops,
+every epilogue mode with its reductions, and tile-aligned sharding over 1..8 ranks
+(including ranks whose shard is empty).  The emulator is test infrastructure; the
+product never loads it."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle.oracle as orc
+from conftest import ROOT
+
+vp = ctypes.c_void_p
+ARGTYPES = ([ctypes.c_int, ctypes.c_int, vp, vp, vp, ctypes.c_int, vp, ctypes.c_uint64, vp, vp,
+             ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+             vp, vp, vp, ctypes.c_double, ctypes.c_double, vp, vp, ctypes.c_uint64, vp])
+
+
+def load():
+    d = os.path.join(ROOT, "tests", "emul")
+    subprocess.check_call(["make", "-C", d], stdout=subprocess.DEVNULL)
+    lib = ctypes.CDLL(os.path.join(d, "libsd_emul_blk.so"))
+    lib.emul_blk_apply.argtypes = ARGTYPES
+    return lib
+
+
+@pytest.fixture(scope="module")
+def emul():
+    return load()
+
+
+def P(a):
+    return a.ctypes.data_as(vp) if a is not None else None
+
+
+def model_lists(L, rng=None):
+    if rng is None:
+        return np.full(L - 1, 0.5), np.ones(L - 1), np.zeros(L)
+    return rng.uniform(0.3, 1.5, L - 1), rng.uniform(-1, 1, L - 1), rng.uniform(-1, 1, L)
+
+
+def oracle_model(L, k, Jhop, Jz, h):
+    hop = [(i + 1, i + 2, Jhop[i]) for i in range(L - 1)]
+    zz = [(i + 1, i + 2, Jz[i]) for i in range(L - 1)]
+    return orc.build_model(L, nup=k, hopping=hop, onsite_field=h, zz=zz)
+
+
+def oracle_apply(m, psi, NC):
+    if NC == 1:
+        ref = np.empty_like(psi)
+        orc.apply_H_(ref, psi, m)
+        return ref
+    pc = psi.view(np.complex128).copy()
+    rf = np.empty_like(pc)
+    orc.apply_H_(rf, pc, m)
+    return rf.view(np.float64).copy()
+
+
+def run(lib, L, k, NC, world, states, psi, Jhop, Jz, h, mode=0, red=0, hscale=1.0, a=1.0, b=0.0,
+        vprev=None, phi=None, acc=None, ck=0j, far_bytes=1 << 20):
+    N = len(states)
+    out = np.full(N * NC, np.nan)
+    redsum = np.zeros(4)
+    bounds = np.zeros(world + 1, dtype=np.uint64)
+    nstore = np.zeros(1, dtype=np.uint64)
+    for r in range(world):
+        redr = np.zeros(4)
+        rc = lib.emul_blk_apply(L, k, P(Jhop), P(Jz), P(h), NC, P(states), N, P(psi), P(out), world, r,
+                                mode, red, hscale, a, b, P(vprev), P(phi), P(acc), ck.real, ck.imag,
+                                P(redr), P(bounds), far_bytes, P(nstore))
+        assert rc == 0, rc
+        redsum += redr
+    return out, redsum, bounds, int(nstore[0])
+
+
+CASES = [(16, 8), (16, 2), (16, 14), (16, 0), (16, 16), (16, 1), (16, 15), (17, 8), (17, 3), (18, 9), (18, 12),
+         (19, 9), (20, 10), (20, 4)]
+
+
+@pytest.mark.parametrize("L,k", CASES)
+@pytest.mark.parametrize("NC", [1, 2])
+def test_block_body_matches_oracle(emul, L, k, NC):
+    rng = np.random.default_rng(L * 1000 + k * 10 + NC)
+    Jhop, Jz, h = model_lists(L, rng)
+    m = oracle_model(L, k, Jhop, Jz, h)
+    states = np.ascontiguousarray(m.states, dtype=np.uint64)
+    N = len(states)
+    psi = rng.standard_normal(N * NC)
+    ref = oracle_apply(m, psi, NC)
+    worlds = (1, 2, 3, 8) if L <= 18 else (1, 4)
+    for world in worlds:
+        out, _, bounds, nstore = run(emul, L, k, NC, world, states, psi, Jhop, Jz, h)
+        assert np.linalg.norm(out - ref) <= 1e-14 * max(1.0, np.linalg.norm(ref)), world
+        assert bounds[0] == 0 and bounds[-1] == N and np.all(np.diff(bounds.astype(np.int64)) >= 0)
+        assert N <= nstore <= 1.25 * N + 64 * (1 << (L - 15))          # padding overhead stays small
+
+
+def test_zero_couplings_on_some_bonds(emul):
+    """J = 0 on a prefix bond, a mid bond, the crossing bonds and a tail bond: inactive bonds are skipped
+    in the header / item tables, not multiplied by zero."""
+    L, k = 18, 9
+    rng = np.random.default_rng(5)
+    Jhop, Jz, h = model_lists(L, rng)
+    for p in (1, 2, 6, 12, 14, 16):
+        Jhop[p] = 0.0
+    m = oracle_model(L, k, Jhop, Jz, h)
+    states = np.ascontiguousarray(m.states, dtype=np.uint64)
+    for NC in (1, 2):
+        psi = rng.standard_normal(len(states) * NC)
+        ref = oracle_apply(m, psi, NC)
+        out, _, _, _ = run(emul, L, k, NC, 2, states, psi, Jhop, Jz, h)
+        assert np.linalg.norm(out - ref) <= 1e-14 * np.linalg.norm(ref)
+
+
+@pytest.mark.parametrize("far_bytes", [0, 1 << 12, 1 << 40])
+def test_far_near_sorting_of_neighbour_tiles_is_only_an_order(emul, far_bytes):
+    L, k = 19, 10
+    rng = np.random.default_rng(2)
+    Jhop, Jz, h = model_lists(L, rng)
+    m = oracle_model(L, k, Jhop, Jz, h)
+    states = np.ascontiguousarray(m.states, dtype=np.uint64)
+    psi = rng.standard_normal(len(states))
+    ref = oracle_apply(m, psi, 1)
+    out, _, _, _ = run(emul, L, k, 1, 1, states, psi, Jhop, Jz, h, far_bytes=far_bytes)
+    assert np.linalg.norm(out - ref) <= 1e-14 * np.linalg.norm(ref)
+
+
+@pytest.mark.parametrize("NC", [1, 2])
+@pytest.mark.parametrize("L,k", [(16, 8), (17, 9), (18, 7)])
+def test_fused_epilogues(emul, L, k, NC):
+    """Every epilogue the recurrences use (Hamiltonian.jl:286-301, KPM_Sqw.jl:111-117,
+    Chebyshev.jl:112-116, Lanczos.jl:50), sharded over 2 ranks."""
+    rng = np.random.default_rng(4 + L)
+    Jhop, Jz, h = model_lists(L, rng)
+    m = oracle_model(L, k, Jhop, Jz, h)
+    states = np.ascontiguousarray(m.states, dtype=np.uint64)
+    N = len(states)
+    v, vprev, phi, acc0 = (rng.standard_normal(N * NC) for _ in range(4))
+    a, b, hs = 2.5, 0.3, -1.0
+    ck = (0.4 - 0.7j) if NC == 2 else (0.4 + 0j)
+    Hv = oracle_apply(m, v, NC)
+    cplx = (lambda x: x.view(np.complex128)) if NC == 2 else (lambda x: x)
+    # apply + <psi, H psi> (Lanczos alpha)
+    out, red, _, _ = run(emul, L, k, NC, 2, states, v, Jhop, Jz, h, red=1)
+    assert np.linalg.norm(out - Hv) <= 1e-14 * np.linalg.norm(Hv)
+    d = np.vdot(cplx(v), cplx(Hv))
+    assert abs(complex(red[0], red[1]) - d) < 1e-10 * max(1.0, abs(d))
+    # rescaled
+    resc = (Hv - b * v) / a
+    out, _, _, _ = run(emul, L, k, NC, 2, states, v, Jhop, Jz, h, mode=1, a=a, b=b)
+    assert np.linalg.norm(out - resc) <= 1e-14 * np.linalg.norm(resc)
+    # Chebyshev step of -H with accumulation and all reductions
+    nxt = 2.0 * ((hs * Hv - b * v) / a) - vprev
+    acc = acc0.copy()
+    out, red, _, _ = run(emul, L, k, NC, 2, states, v, Jhop, Jz, h, mode=2, red=7, hscale=hs, a=a, b=b,
+                         vprev=vprev, phi=phi, acc=acc, ck=ck)
+    assert np.linalg.norm(out - nxt) <= 1e-14 * np.linalg.norm(nxt)
+    assert abs(complex(red[0], red[1]) - np.vdot(cplx(v), cplx(nxt))) < 1e-10
+    assert abs(red[2] - np.vdot(cplx(phi), cplx(nxt)).real) < 1e-10
+    assert abs(red[3] - nxt @ nxt) < 1e-9
+    want = cplx(acc0) + (ck if NC == 2 else ck.real) * cplx(nxt)
+    assert np.linalg.norm(cplx(acc) - want) < 1e-12
+
+
+def _gloo_worker(rank, world, port, q):
+    """world_size-2 gloo run of the sharded block path's host logic: every rank runs the emulated
+    kernel on its own tile-aligned shard (peer shards are separate buffers selected by the owner
+    lookup in the tile header), the shards are gathered and the fused dot is all-reduced."""
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lib = load()
+        L, k = 18, 9
+        Jhop, Jz, h = model_lists(L)
+        m = oracle_model(L, k, Jhop, Jz, h)
+        states = np.ascontiguousarray(m.states, dtype=np.uint64)
+        N = len(states)
+        psi = orc.fill_seeded(N, 99)
+        out = np.zeros(N)
+        red = np.zeros(4)
+        bounds = np.zeros(world + 1, dtype=np.uint64)
+        rc = lib.emul_blk_apply(L, k, P(Jhop), P(Jz), P(h), 1, P(states), N, P(psi), P(out), world, rank,
+                                0, 1, 1.0, 1.0, 0.0, None, None, None, 0.0, 0.0, P(red), P(bounds), 1 << 20, None)
+        assert rc == 0
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        sizes = [int(bounds[g + 1] - bounds[g]) for g in range(world)]
+        parts = [torch.zeros(s, dtype=torch.float64) for s in sizes]
+        for g in range(world):                              # ragged shards: gather by broadcast
+            if g == rank:
+                parts[g] = torch.from_numpy(out[lo:hi].copy())
+            dist.broadcast(parts[g], src=g)
+        full = torch.cat(parts).numpy()
+        dot = torch.tensor([red[0]], dtype=torch.float64)
+        dist.all_reduce(dot)                                # the scalar all-reduce of the Lanczos alpha
+        if rank == 0:
+            ref = oracle_apply(m, psi, 1)
+            q.put((float(np.linalg.norm(full - ref) / np.linalg.norm(ref)), float(abs(dot.item() - psi @ ref)), sizes))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharded_block_apply(emul):
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    err, derr, sizes = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert err < 1e-14 and derr < 1e-9 and sum(sizes) == orc.lib().orc_sector_dim(18, 9) and min(sizes) > 0
