@@ -17,7 +17,7 @@ from oracle import oracle as orc  # noqa: E402
 
 SEED, JXY, JZ, HZ = 20261018, 1.0, 0.75, 0.1
 out = {"seed": SEED, "Jxy": JXY, "Jz": JZ, "hz": HZ}
-for L, nup in [(10, 5), (12, 6), (13, 4), (14, 7)]:
+for L, nup in [(10, 5), (12, 6), (13, 4), (14, 7), (16, 8), (17, 7)]:      # L >= 16: the block-layout kernel's sizes
     m = orc.XXZChain(L, Jxy=JXY, Jz=JZ, hz=HZ, nup=nup)
     for kind, cplx in (("f64", False), ("c128", True)):
         psi = orc.fill_seeded(len(m), SEED, cplx=cplx)

@@ -225,3 +225,25 @@ def test_two_rank_gloo_sharded_block_apply(emul):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert err < 1e-14 and derr < 1e-9 and sum(sizes) == orc.lib().orc_sector_dim(18, 9) and min(sizes) > 0
+
+
+def test_block_body_matches_golden_fixture(emul):
+    """tests/golden/apply_golden.npz holds oracle outputs for the seeded psi at the block kernel's
+    smallest sizes (L = 16, 17); the GPU golden test reads the same file."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "apply_golden.npz"))
+    seen = 0
+    for key in [k for k in g.files if k.startswith("out_")]:
+        _, L, nup, kind = key.split("_")
+        L, nup = int(L), int(nup)
+        if L < 16:
+            continue
+        seen += 1
+        NC = 2 if kind == "c128" else 1
+        Jhop, Jz, h = np.full(L - 1, float(g["Jxy"]) / 2), np.full(L - 1, float(g["Jz"])), np.full(L, float(g["hz"]))
+        om = orc.XXZChain(L, nup=nup)
+        states = np.array(om.states, dtype=np.uint64)
+        psi = orc.fill_seeded(len(states), int(g["seed"]), cplx=NC == 2).view(np.float64).copy()
+        out, _, _, _ = run(emul, L, nup, NC, 2, states, psi, Jhop, Jz, h)
+        ref = np.ascontiguousarray(g[key]).view(np.float64)
+        assert np.linalg.norm(out - ref) <= 1e-14 * np.linalg.norm(ref), key
+    assert seen == 4

@@ -1,0 +1,117 @@
+"""BASELINE.json's configurations at (or near) their full sizes, through size-independent
+properties (the oracle cannot hold these vectors in seconds): sampled rows of H.psi for the
+counter-based psi, Hermiticity, norm / energy conservation and cross-method agreement of the time
+steppers, exact low KPM moments, and ground-state energies pinned by an independent ARPACK run of
+the CPU oracle (tests/golden/energy_golden.json, written by tests/golden/make_energy_golden.py).
+Everything stays device-resident; every call goes through the C ABI."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import oracle.oracle as orc  # noqa: E402
+from conftest import sd  # noqa: E402
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "energy_golden.json")))
+
+
+def energy(m, psi):
+    h = m.vector(psi.dtype)
+    sd.apply_H_(h, psi, m)
+    return psi.dot(h)
+
+
+def test_config4_model_L32_sampled_rows_and_hermiticity():
+    """The headline workload (XXZ L=32 nup=16, 601 080 390 states, f64): 40 rows of H.psi against the
+    oracle's row formula on the regenerated seeded psi, <x,Hy> = <Hx,y>, and the fused <x,Hx>."""
+    L, nup, seed = 32, 16, 20261018
+    m = sd.XXZChain(L, nup=nup)
+    assert m.dim == 601080390 and m.info["kernel_path"] == "block"
+    x = m.vector(np.float64).fill_seeded(seed, 1e-4)
+    y = m.vector(np.float64).fill_seeded(seed + 7, 1e-4)
+    hx, hy = m.vector(np.float64), m.vector(np.float64)
+    sd.apply_H_(hx, x, m)
+    sd.apply_H_(hy, y, m)
+    lhs, rhs = x.dot(hy).real, hx.dot(y).real
+    assert abs(lhs - rhs) < 1e-10 * max(1.0, abs(lhs), x.norm() * hy.norm())
+    del hy, y
+    import ctypes
+    r = sd._lib.SdComplex()
+    h2 = m.vector(np.float64)
+    sd._lib.check(sd.lib().sd_apply_H_dot(m._h, h2._h, x._h, ctypes.byref(r)))
+    xhx = x.dot(hx).real
+    assert abs(r.re - xhx) < 1e-11 * max(1.0, abs(xhx), x.norm() * hx.norm())
+    del h2
+    out = hx.to_host()
+    rng = np.random.default_rng(L)
+    rows = np.unique(np.concatenate([rng.integers(0, m.dim, 36), [0, 1, m.dim - 1, m.dim // 2]]))
+    hop = [(i, i + 1, 0.5) for i in range(1, L)]
+    zz = [(i, i + 1, 1.0) for i in range(1, L)]
+    for r_ in rows:
+        s = int(m.unrank(int(r_), 1)[0])
+        ref = orc.row_seeded_f64((L, nup, hop, zz, np.zeros(L)), s, seed, 1e-4)
+        assert abs(out[r_] - ref) <= 1e-13 * max(1e-4, abs(ref)), (r_, out[r_], ref)
+
+
+def test_config2_L24_krylov_from_neel_full_size():
+    """XXZChain L=24 nup=12 (2 704 156 states), Krylov t=0.5 from the Neel state, complex psi:
+    unit norm, conserved energy <Neel|H|Neel> = -(L-1)/4, agreement with the Chebyshev stepper."""
+    L, t = 24, 0.5
+    m = sd.XXZChain(L, nup=L // 2)
+    assert m.dim == 2704156
+    psi0 = sd.neel_state(m, device=True).astype(np.complex128)
+    pt = sd.krylov_time_evolve(psi0, t, sd.apply_H_, m, kry_m=30, device=True)
+    assert abs(pt.norm() - 1.0) < 1e-10
+    e = energy(m, pt)
+    assert abs(e.real + (L - 1) / 4) < 1e-8 and abs(e.imag) < 1e-10
+    # the spectrum lies in [E0, (L-1)/4]; E0 from the ARPACK golden value
+    bounds = (GOLD["E0"][str(L)] - 0.05, (L - 1) / 4 + 0.05)
+    ct = sd.chebyshev_time_evolve(psi0, t, sd.apply_H_, m, cheb_n=48, Ebounds=bounds, device=True)
+    assert abs(ct.norm() - 1.0) < 1e-9
+    ct.axpy(-1.0, pt)
+    assert ct.norm() < 1e-8
+    # a real (Float64) Neel state must give the same psi(t) (Krylov.jl promotes through the coefficients)
+    pr = sd.krylov_time_evolve(sd.neel_state(m, device=True), t, sd.apply_H_, m, kry_m=30, device=True)
+    pr.axpy(-1.0, pt)
+    assert pr.norm() < 1e-9
+
+
+def test_config3_L28_kpm_1024_moments_full_size():
+    """XXZChain L=28 nup=14 (40 116 600 states), 1024 Chebyshev moments with fused dots (complex phi):
+    mu_0 = |phi|^2, |mu_n| <= mu_0, and mu_1, mu_2 against the unfused rescaled apply + dot kernels."""
+    L, M = 28, 1024
+    m = sd.XXZChain(L, nup=L // 2)
+    assert m.dim == 40116600
+    phi = m.vector(np.complex128).fill_seeded(5)
+    phi.scale(1.0 / phi.norm())
+    Emin, Emax = -0.4432 * L - 0.3, (L - 1) / 4           # E0/L > -0.4432 (Bethe ansatz bulk value -0.44315)
+    a, b = (Emax - Emin) / (2 * 0.99), (Emax + Emin) / 2
+    mu = sd.compute_chebyshev_moments(sd.apply_H_, phi, M, a, b, m)
+    assert mu.shape == (M,) and np.all(np.isfinite(mu))
+    assert abs(mu[0] - 1.0) < 1e-12 and np.all(np.abs(mu) <= 1.0 + 1e-9)
+    w = m.vector(np.complex128)
+    sd.apply_rescaled_H_(w, phi, sd.apply_H_, m, a, b)
+    mu1 = phi.dot(w).real
+    mu2 = 2.0 * w.dot(w).real - 1.0
+    assert abs(mu[1] - mu1) < 1e-12 and abs(mu[2] - mu2) < 1e-11
+    # a seeded random state has its spectral weight in the middle of the band: moments decay
+    assert np.abs(mu[M // 2:]).max() < 0.05
+
+
+@pytest.mark.parametrize("L", [20, 24])
+def test_groundstate_energy_against_arpack_golden(L):
+    """Lanczos ground state (Lanczos.jl:87-181, full reorthogonalisation) on the block kernel vs the
+    ARPACK/oracle value: E0 to 1e-10, Rayleigh quotient and residual of the returned Ritz vector."""
+    m = sd.XXZChain(L, nup=L // 2)
+    v0 = m.vector(np.float64).fill_seeded(3)
+    E0, psi = sd.groundstate(m, lanc_m=120, v0=v0, device=True)
+    assert abs(E0 - GOLD["E0"][str(L)]) < 1e-10, (E0, GOLD["E0"][str(L)])
+    assert abs(psi.norm() - 1.0) < 1e-12
+    h = m.vector(np.float64)
+    sd.apply_H_(h, psi, m)
+    assert abs(psi.dot(h).real - E0) < 1e-10
+    h.axpy(-E0, psi)
+    assert h.norm() < 1e-6

@@ -353,3 +353,19 @@ def test_seeded_row_matches_full_apply():
     for idx in RNG.integers(0, N, 50):
         s = int(m.states[idx])
         assert abs(orc.row_seeded_f64(args, s, seed) - out[idx]) < 1e-14
+
+
+def test_energy_golden_file_agrees_with_the_oracle_lanczos():
+    """tests/golden/energy_golden.json (ARPACK on the oracle matvec, make_energy_golden.py) vs the
+    oracle's own Lanczos.jl restatement at the one size that runs in seconds; pins the fixture that
+    the full-size GPU ground-state tests compare with."""
+    import json
+    import os
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "energy_golden.json")))
+    assert set(g["E0"]) == {"18", "20", "22", "24"} and max(g["residual"].values()) < 1e-12
+    L = 18
+    m = orc.XXZChain(L, nup=L // 2)
+    E0, psi = orc.groundstate(m, lanc_m=90, rng=np.random.default_rng(L))
+    assert abs(E0 - g["E0"][str(L)]) < 1e-10
+    e = np.array([g["E0"][str(x)] for x in (18, 20, 22, 24)])
+    assert np.all(np.abs(np.diff(e, 2)) < 2e-4)          # E0(L) is almost linear in L (bulk energy density)
