@@ -177,4 +177,24 @@ int emul_blk_apply(int L, int k, const double *Jhop, const double *Jz, const dou
     return 0;
 }
 
+// Host-side plan of the sharded block layout at ANY size (no vectors are touched): rank bounds, stored-
+// element bounds and tile-key bounds per rank, total stored elements, largest tile.  Returns 0 or -1.
+int emul_blk_plan(int L, int k, int world, uint64_t *bounds, uint64_t *pstart, uint64_t *keys, uint64_t *n_store,
+                  uint32_t *cap, uint64_t *n_tiles) {
+    SdBlkHost bh;
+    std::vector<double> J(L, 0.5), Jz(L, 1.0), h(L, 0.0);
+    if (!sd_blk_build(L, k, J.data(), Jz.data(), h.data(), bh)) return -1;
+    SdTileHost th;
+    if (!sd_tile_build(L, k, SD_BLK_B, 5, J.data(), Jz.data(), h.data(), th)) return -1;
+    sd_tile_shard_bounds(th, world, bounds, keys);
+    for (int g = 0; g <= world; ++g) pstart[g] = sd_blk_key_base(bh, keys[g]);
+    *n_store = bh.n_store;
+    *cap = bh.P.cap;
+    uint64_t nt = 0;                                               // tiles with a possible suffix popcount
+    for (int x = 0; x <= bh.P.A; ++x)
+        if (k - x >= 0 && k - x <= SD_BLK_B) nt += bh.binom[(size_t)bh.P.A * SD_BINOM_DIM + x];
+    *n_tiles = nt;
+    return 0;
+}
+
 }  // extern "C"

@@ -247,3 +247,27 @@ def test_block_body_matches_golden_fixture(emul):
         ref = np.ascontiguousarray(g[key]).view(np.float64)
         assert np.linalg.norm(out - ref) <= 1e-14 * np.linalg.norm(ref), key
     assert seen == 4
+
+
+@pytest.mark.parametrize("L,k,N", [(32, 16, 601080390), (34, 17, 2333606220), (36, 18, 9075135300), (32, 10, 64512240)])
+def test_shard_plan_at_full_sizes(emul, L, k, N):
+    """Host-side layout/shard plan at BASELINE.json's sizes (L=36: ranks and stored offsets beyond 2^32):
+    bounds are tile aligned and monotone, shards are balanced, padding overhead is small, and the
+    per-rank stored ranges tile the stored vector exactly."""
+    emul.emul_blk_plan.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp]
+    for world in (1, 2, 4, 8):
+        bounds, pstart, keys = (np.zeros(world + 1, dtype=np.uint64) for _ in range(3))
+        nstore, ntiles, cap = np.zeros(1, dtype=np.uint64), np.zeros(1, dtype=np.uint64), np.zeros(1, dtype=np.uint32)
+        assert emul.emul_blk_plan(L, k, world, P(bounds), P(pstart), P(keys), P(nstore), P(cap), P(ntiles)) == 0
+        b, ps, ks = bounds.astype(object), pstart.astype(object), keys.astype(object)
+        assert b[0] == 0 and b[-1] == N and ps[0] == 0 and ps[-1] == int(nstore[0])
+        assert 0 <= ks[0] and ks[-1] <= 1 << (L - 15)                  # the first / last keys may be impossible prefixes
+        assert all(b[g] < b[g + 1] and ps[g] < ps[g + 1] and ks[g] < ks[g + 1] for g in range(world))
+        sizes = [b[g + 1] - b[g] for g in range(world)]
+        assert max(sizes) - min(sizes) <= 2 * 6435                   # a rank boundary moves by at most one tile
+        slack = 1.03 if 2 * k == L else 1.10                          # zero padding of the block layout (1.1-1.2 % at Sz = 0)
+        assert N <= int(nstore[0]) <= slack * N
+        assert all(p % 16 == 0 for p in ps)                           # 128-byte aligned shard bases (TMA needs 16)
+        assert int(cap[0]) == 6480 and int(cap[0]) * 8 * 3 < 227 * 1024
+        stored = [ps[g + 1] - ps[g] for g in range(world)]
+        assert max(stored) <= slack * max(sizes) + 6480
