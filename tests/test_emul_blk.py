@@ -265,8 +265,8 @@ def test_shard_plan_at_full_sizes(emul, L, k, N):
         assert all(b[g] < b[g + 1] and ps[g] < ps[g + 1] and ks[g] < ks[g + 1] for g in range(world))
         sizes = [b[g + 1] - b[g] for g in range(world)]
         assert max(sizes) - min(sizes) <= 2 * 6435                   # a rank boundary moves by at most one tile
-        slack = 1.03 if 2 * k == L else 1.10                          # zero padding of the block layout (1.1-1.2 % at Sz = 0)
-        assert N <= int(nstore[0]) <= slack * N
+        slack = 1.03 if 2 * k == L else 1.15                          # zero padding of the block layout (1.1-1.2 % at Sz = 0)
+        assert N <= int(nstore[0]) <= (slack if 2 * k == L else 1.10) * N
         assert all(p % 16 == 0 for p in ps)                           # 128-byte aligned shard bases (TMA needs 16)
         assert int(cap[0]) == 6480 and int(cap[0]) * 8 * 3 < 227 * 1024
         stored = [ps[g + 1] - ps[g] for g in range(world)]
