@@ -132,6 +132,7 @@ struct SdBlkDev {
     int nbuf[2] = {0, 0};
     size_t smem[2] = {0, 0};
     int qfar[2] = {0, 0};
+    int variant = 0;                // item-body variant of sd_blk_apply_kernel (SD_BLK_VARIANT)
 };
 
 struct SdTileDev {
@@ -432,6 +433,7 @@ static int sd_blk_setup(sd_model *m) {
         b.nbuf[w] = nbuf;
         b.qfar[w] = sd_tile_qfar(L, b.host.P.A, b.host.binom.data(), (uint64_t)sd_env_int("SD_FAR_MB", 100) << 20, 8 * nc);
     }
+    b.variant = sd_env_int("SD_BLK_VARIANT", SD_BLK_DEFAULT_VARIANT) == 1 ? 1 : 0;
     SD_TRY(sd_to_device(&b.d_W, b.host.W));
     SD_TRY(sd_to_device(&b.d_js, b.host.js));
     SD_TRY(sd_to_device(&b.d_units, b.host.units));
@@ -1035,18 +1037,24 @@ static int sd_apply_impl(sd_model *m, sd_vec *out, const sd_vec *psi, SdEpi epi,
         const size_t smem = m->blk.smem[nc - 1];
         const int qfar = m->blk.qfar[nc - 1];
         const bool plain = epi.mode == SD_EPI_PLAIN && epi.red == 0 && !epi.acc && epi.hscale == 1.0;
-#define SD_LAUNCH_BLK(NC_, PLAIN_)                                                                           \
+#define SD_LAUNCH_BLK3(NC_, PLAIN_, V_)                                                                      \
     do {                                                                                                     \
         static size_t set_smem = 0;                                                                          \
         if (smem > set_smem) {                                                                               \
-            SD_CUDA(cudaFuncSetAttribute(sd_blk_apply_kernel<NC_, PLAIN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            SD_CUDA(cudaFuncSetAttribute(sd_blk_apply_kernel<NC_, PLAIN_, V_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             set_smem = smem;                                                                                 \
         }                                                                                                    \
-        sd_blk_apply_kernel<NC_, PLAIN_><<<grid, SD_BLK_THREADS, smem, c->stream>>>(P, psi->view, out->d, epi, qfar, c->d_tilectr); \
+        sd_blk_apply_kernel<NC_, PLAIN_, V_><<<grid, SD_BLK_THREADS, smem, c->stream>>>(P, psi->view, out->d, epi, qfar, c->d_tilectr); \
+    } while (0)
+#define SD_LAUNCH_BLK(NC_, PLAIN_)                                                                           \
+    do {                                                                                                     \
+        if (m->blk.variant == 1) SD_LAUNCH_BLK3(NC_, PLAIN_, 1);                                             \
+        else SD_LAUNCH_BLK3(NC_, PLAIN_, 0);                                                                 \
     } while (0)
         if (nc == 1) { if (plain) SD_LAUNCH_BLK(1, true); else SD_LAUNCH_BLK(1, false); }
         else { if (plain) SD_LAUNCH_BLK(2, true); else SD_LAUNCH_BLK(2, false); }
 #undef SD_LAUNCH_BLK
+#undef SD_LAUNCH_BLK3
         SD_TRY(sd_launch_check(c, "sd_blk_apply_kernel"));
         if (slotmask) SD_TRY(sd_finish_reduce(c, (unsigned)nkeys, slotmask, slot_out));
     } else if (m->path == SD_PATH_TILED) {

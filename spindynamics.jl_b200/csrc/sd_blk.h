@@ -41,6 +41,7 @@
 #define SD_BLK_MAXUNITS 64      // work items per tile: (unit of 32 mid configurations, element chunk); <= 32 (f64), <= 47 (c128)
 #define SD_BLK_THREADS 512
 #define SD_BLK_CWARPS 15        // consumer warps; warp 15 is the producer
+#define SD_BLK_DEFAULT_VARIANT 0   // item-body variant launched by default (SD_BLK_VARIANT overrides); see sd_blk_item
 
 struct SdBlkCls {
     uint32_t cb;         // element offset of the class inside the tile
@@ -115,6 +116,7 @@ struct SdBlkHdr {
     int js, jsx;                         // suffix popcount of the tile / of the crossing partner tile
     int valid;                           // 1: tile, -1: end of this CTA's tile list
     int nnb, nfar;                       // active prefix-internal bonds; the first nfar are beyond L2 reach
+    int ntot;                            // nnb + 1 if the prefix|mid crossing bond is active: entry nnb of nb_ptr / nb_J
     int bP;                              // last prefix bit
     unsigned next_unit;                  // work counter of the consumer warps
     unsigned done_units;                 // finished units (the warp that finishes the last one sums usum[] in order)
@@ -123,7 +125,7 @@ struct SdBlkHdr {
     double Jx;                           // hop coefficient of the prefix|mid bond (0: none)
     const double *xptr;                  // stored base of the crossing partner tile (component 0)
     const double *nb_ptr[SD_BLK_MAXA + 8];   // stored bases of the neighbour tiles of the active prefix bonds
-    double nb_J[SD_BLK_MAXA + 8];        // entries >= nnb: valid pointer, J = 0 (software pipeline overrun)
+    double nb_J[SD_BLK_MAXA + 8];        // entry nnb: the crossing bond (if active); entries ntot .. ntot+5 are 0 (pipeline overrun)
     double usum[SD_NSLOT][SD_BLK_MAXUNITS];   // per-unit reduction results (deterministic: summed in unit order)
 };
 
@@ -186,6 +188,11 @@ SD_HD void sd_blk_hdr_fill(const SdBlkParams &P, const SdBlkHdrLane &l, uint64_t
         H.jsx = jsx;
         H.Jx = ok ? J : 0.0;
         H.xptr = ok ? psi.base[sd_blk_owner(P.shards, nbase)] + (size_t)NC * nbase : nullptr;
+        if (ok) {                                                 // the crossing bond as entry nnb of the stream list
+            const int nnb = SD_POPC32(actmask);
+            H.nb_ptr[nnb] = H.xptr;
+            H.nb_J[nnb] = J;
+        }
         H.bP = bit;
         const double sl = bit ? 0.5 : -0.5;
         H.dP[0] = dpre + P.Jz[q] * sl * (-0.5);
@@ -197,6 +204,13 @@ SD_HD void sd_blk_hdr_fill(const SdBlkParams &P, const SdBlkHdrLane &l, uint64_t
         H.valid = 1;
         H.nnb = SD_POPC32(actmask);
         H.nfar = nfar;
+        {
+            const int bl = (int)((Pb >> (A - 1)) & 1ULL), jsx = bl ? js + 1 : js - 1;
+            const bool okx = (P.Jhop[A - 1] != 0.0) && jsx >= 0 && jsx <= SD_BLK_B;
+            const int ntot = H.nnb + (okx ? 1 : 0);
+            H.ntot = ntot;
+            for (int i = 0; i < 6; ++i) H.nb_J[ntot + i] = 0.0;
+        }
         H.next_unit = 0;
         H.done_units = 0;
         H.tile_index = (unsigned)(key - P.key_lo);
@@ -351,7 +365,10 @@ struct SdBlkCtx {
 // S0 = first slot of the chunk (c128, classes of 10: 0 or 5; otherwise 0).
 // HALF: the last slot of the chunk is a half slot (f64 classes with an odd number of tail configurations:
 // the last configuration is stored as a plain row of doubles at cb + (NT-1)*pitch + u).
-template <int NC, int EC, bool HALF, bool PLAIN>
+// V: body variant.  0 = the round-1 measured body; 1 = lean streams (loads predicated without zero fill,
+// coefficients read from the zero-padded header list, crossing bond as list entry nnb) and mid hops
+// iterated over the item's active-bond mask.  Same arithmetic, different summation interleaving.
+template <int NC, int EC, bool HALF, bool PLAIN, int V>
 SD_HD void sd_blk_item(const SdBlkCtx &X, const SdBlkHdr &H, const double *tb, int jt, int S0,
                                             uint32_t u, double (&red)[SD_NSLOT]) {
     constexpr int T = SD_BLK_T, M = SD_BLK_M;
@@ -373,7 +390,7 @@ SD_HD void sd_blk_item(const SdBlkCtx &X, const SdBlkHdr &H, const double *tb, i
     //   entries 0 .. nnb-1 : prefix-internal bonds, whole neighbour tiles in the same element order
     //   entry   nnb        : prefix|mid crossing bond (partner tile with js +- 1, same class, uniform
     //                        block shift), only for lanes whose first mid bit differs from the last prefix bit
-    const int nnb = (P.dbg & 1) ? 0 : H.nnb;
+    const int nnb = (V == 0 && (P.dbg & 1)) ? 0 : H.nnb;
     const bool hasx = H.xptr != nullptr;
     const int ntot = nnb + (hasx ? 1 : 0);
     const double *xp = nullptr;
@@ -387,6 +404,11 @@ SD_HD void sd_blk_item(const SdBlkCtx &X, const SdBlkHdr &H, const double *tb, i
         xp = H.xptr + (size_t)(cx.cb * NC + 2u * xu) + (size_t)S0 * xs;
     }
     double2 t0[EC], t1[EC], t2[EC];
+    if (V != 0) {
+#pragma unroll
+        for (int s = 0; s < EC; ++s) t0[s] = t1[s] = t2[s] = make_double2(0.0, 0.0);
+    }
+    // V = 0: every load guarded and zero filled, coefficient selected per entry
 #define SD_BLK_LOAD(t_, n_)                                                                   \
     do {                                                                                      \
         const int nn_ = (n_);                                                                 \
@@ -406,7 +428,30 @@ SD_HD void sd_blk_item(const SdBlkCtx &X, const SdBlkHdr &H, const double *tb, i
         const double J_ = nn_ < nnb ? H.nb_J[nn_] : (nn_ == nnb && hasx ? H.Jx : 0.0);        \
         _Pragma("unroll") for (int s = 0; s < EC; ++s) { acc[s].x += J_ * t_[s].x; acc[s].y += J_ * t_[s].y; } \
     } while (0)
-    SD_BLK_LOAD(t0, 0); SD_BLK_LOAD(t1, 1); SD_BLK_LOAD(t2, 2);
+    // V = 1: a load that does not exist leaves its registers alone (zero at first, finite old data later) and
+    // its coefficient is 0: H.nb_J is zero padded behind entry ntot-1, the crossing entry counts only for xlane
+#define SD_BLK_LOAD1(t_, n_)                                                                  \
+    do {                                                                                      \
+        const int nn_ = (n_);                                                                 \
+        const bool isx_ = hasx && nn_ == nnb;                                                 \
+        if (nn_ < ntot && (!isx_ || xlane)) {                                                 \
+            const double *p_ = isx_ ? xp : H.nb_ptr[nn_] + offc;                              \
+            const uint32_t st_ = isx_ ? xs : ss;                                              \
+            _Pragma("unroll") for (int s = 0; s < EC; ++s) {                                  \
+                if (HALF && s == EC - 1) t_[s] = sd_blk_ldg_half(p_ + s * st_ - (isx_ ? xu : u)); \
+                else t_[s] = sd_blk_ldg(p_ + s * st_);                                        \
+            }                                                                                 \
+        }                                                                                     \
+    } while (0)
+#define SD_BLK_FMA1(t_, n_)                                                                   \
+    do {                                                                                      \
+        const int nn_ = (n_);                                                                 \
+        double J_ = H.nb_J[nn_];                                                              \
+        if (hasx && nn_ == nnb && !xlane) J_ = 0.0;                                           \
+        _Pragma("unroll") for (int s = 0; s < EC; ++s) { acc[s].x += J_ * t_[s].x; acc[s].y += J_ * t_[s].y; } \
+    } while (0)
+    if (V == 0) { SD_BLK_LOAD(t0, 0); SD_BLK_LOAD(t1, 1); SD_BLK_LOAD(t2, 2); }
+    else { SD_BLK_LOAD1(t0, 0); SD_BLK_LOAD1(t1, 1); SD_BLK_LOAD1(t2, 2); }
     // ---- own block: diagonal + tail-internal hops (registers)
     const unsigned cmid = it.w & ((1u << M) - 1u);
     const bool clast = (cmid >> (M - 1)) & 1u;
@@ -437,12 +482,26 @@ SD_HD void sd_blk_item(const SdBlkCtx &X, const SdBlkHdr &H, const double *tb, i
             }
         }
     }
-    // ---- mid-internal hops (the whole block moves to block nb[pm] of the same class), three bonds per
+    // ---- mid-internal hops (the whole block moves to block nb[pm] of the same class), a few bonds per
     // stream round so that shared-memory gathers overlap the global loads in flight
     const double *cbp = tb + cls.cb * NC + S0 * ss;
     uint64_t lo = (uint64_t)it.x | ((uint64_t)it.y << 32);
-    uint32_t hi = it.z;
-    int pm = (P.dbg & 2) ? M : 0;
+#define SD_BLK_MID_BODY(J, nbu)                                                               \
+    do {                                                                                      \
+        const double *sp = cbp + 2u * (nbu);                                                  \
+        _Pragma("unroll") for (int s = 0; s < EC; ++s) {                                      \
+            if (HALF && s == EC - 1) {                                                        \
+                acc[s].x += (J) * *(sp + s * ss - (nbu));                                     \
+            } else {                                                                          \
+                const double2 t = *(const double2 *)(sp + s * ss);                            \
+                acc[s].x += (J) * t.x;                                                        \
+                acc[s].y += (J) * t.y;                                                        \
+            }                                                                                 \
+        }                                                                                     \
+    } while (0)
+    if (V == 0) {
+        uint32_t hi = it.z;
+        int pm = (P.dbg & 2) ? M : 0;
 #define SD_BLK_MID()                                                                          \
     do {                                                                                      \
         const double J = X.Jhop[P.A + pm];                                                    \
@@ -450,32 +509,47 @@ SD_HD void sd_blk_item(const SdBlkCtx &X, const SdBlkHdr &H, const double *tb, i
         lo = (lo >> 8) | ((uint64_t)hi << 56);                                                \
         hi >>= 8;                                                                             \
         ++pm;                                                                                 \
-        if (nbu != 0xFFu) {                                                                   \
-            const double *sp = cbp + 2u * nbu;                                                \
-            _Pragma("unroll") for (int s = 0; s < EC; ++s) {                                  \
-                if (HALF && s == EC - 1) {                                                    \
-                    acc[s].x += J * *(sp + s * ss - nbu);                                        \
-                } else {                                                                      \
-                    const double2 t = *(const double2 *)(sp + s * ss);                        \
-                    acc[s].x += J * t.x;                                                      \
-                    acc[s].y += J * t.y;                                                      \
-                }                                                                             \
-            }                                                                                 \
-        }                                                                                     \
+        if (nbu != 0xFFu) SD_BLK_MID_BODY(J, nbu);                                            \
     } while (0)
 #pragma unroll 1
-    for (int n = 0; n < ntot; n += 3) {
+        for (int n = 0; n < ntot; n += 3) {
 #pragma unroll 1
-        for (int k = 0; k < 3 && pm + 1 < M; ++k) SD_BLK_MID();
-        SD_BLK_FMA(t0, n); SD_BLK_LOAD(t0, n + 3);
-        SD_BLK_FMA(t1, n + 1); SD_BLK_LOAD(t1, n + 4);
-        SD_BLK_FMA(t2, n + 2); SD_BLK_LOAD(t2, n + 5);
-    }
+            for (int k = 0; k < 3 && pm + 1 < M; ++k) SD_BLK_MID();
+            SD_BLK_FMA(t0, n); SD_BLK_LOAD(t0, n + 3);
+            SD_BLK_FMA(t1, n + 1); SD_BLK_LOAD(t1, n + 4);
+            SD_BLK_FMA(t2, n + 2); SD_BLK_LOAD(t2, n + 5);
+        }
 #pragma unroll 1
-    while (pm + 1 < M) SD_BLK_MID();
+        while (pm + 1 < M) SD_BLK_MID();
 #undef SD_BLK_MID
+    } else {
+        // active mid bonds of the item: bits of nb[9..10] (sd_blk_build); lowest set bit first
+        uint32_t am = (P.dbg & 2) ? 0u : ((it.z >> 8) & 0xFFFFu);
+#define SD_BLK_MID1()                                                                         \
+    do {                                                                                      \
+        const int pm = SD_POPC32((am & (0u - am)) - 1u);                                      \
+        am &= am - 1u;                                                                        \
+        const unsigned nbu = pm < 8 ? (unsigned)((lo >> (8 * pm)) & 0xFFu) : (it.z & 0xFFu);  \
+        const double J = X.Jhop[P.A + pm];                                                    \
+        SD_BLK_MID_BODY(J, nbu);                                                              \
+    } while (0)
+#pragma unroll 1
+        for (int n = 0; n < ntot; n += 3) {
+#pragma unroll 1
+            for (int k = 0; k < 2 && am != 0u; ++k) SD_BLK_MID1();
+            SD_BLK_FMA1(t0, n); SD_BLK_LOAD1(t0, n + 3);
+            SD_BLK_FMA1(t1, n + 1); SD_BLK_LOAD1(t1, n + 4);
+            SD_BLK_FMA1(t2, n + 2); SD_BLK_LOAD1(t2, n + 5);
+        }
+#pragma unroll 1
+        while (am != 0u) SD_BLK_MID1();
+#undef SD_BLK_MID1
+    }
+#undef SD_BLK_MID_BODY
 #undef SD_BLK_LOAD
 #undef SD_BLK_FMA
+#undef SD_BLK_LOAD1
+#undef SD_BLK_FMA1
     // ---- mid|tail crossing bond, per tail configuration.  Tail configurations with bit 0 set come first
     // in a class: n1 = C(T-1, jt-1) of them.  Last mid bit set & tail bit 0 clear -> class jt+1,
     // configuration e - n1; last mid bit clear & tail bit 0 set -> class jt-1, configuration C(T-1, jt-2) + e.
@@ -557,13 +631,13 @@ SD_HD void sd_blk_item(const SdBlkCtx &X, const SdBlkHdr &H, const double *tb, i
 
 // item code: jt << 12 | chunk << 8 | unit-in-class (units of 32 mid configurations).
 // f64: one chunk per class (1, 3 or 5 slots).  c128: classes of 10 -> two chunks of 5 slots.
-template <int NC, bool PLAIN>
+template <int NC, bool PLAIN, int V>
 SD_HD void sd_blk_dispatch(const SdBlkCtx &X, const SdBlkHdr &H, const double *tb, unsigned code,
                                                 uint32_t u, double (&red)[SD_NSLOT]) {
     const int jt = (int)(code >> 12), S0 = ((code >> 8) & 0xFu) ? 5 : 0;
-    if (jt == 0 || jt == SD_BLK_T) sd_blk_item<NC, 1, NC == 1, PLAIN>(X, H, tb, jt, 0, u, red);
-    else if (NC == 1 && (jt == 1 || jt == SD_BLK_T - 1)) sd_blk_item<NC, (NC == 1 ? 3 : 5), NC == 1, PLAIN>(X, H, tb, jt, 0, u, red);
-    else sd_blk_item<NC, 5, false, PLAIN>(X, H, tb, jt, S0, u, red);
+    if (jt == 0 || jt == SD_BLK_T) sd_blk_item<NC, 1, NC == 1, PLAIN, V>(X, H, tb, jt, 0, u, red);
+    else if (NC == 1 && (jt == 1 || jt == SD_BLK_T - 1)) sd_blk_item<NC, (NC == 1 ? 3 : 5), NC == 1, PLAIN, V>(X, H, tb, jt, 0, u, red);
+    else sd_blk_item<NC, 5, false, PLAIN, V>(X, H, tb, jt, S0, u, red);
 }
 
 // shared-memory carve-up
@@ -660,7 +734,7 @@ __device__ __forceinline__ void sd_stg_v2(double *p, double2 v) {
 // the tiles in flight form a tight window and near neighbour tiles are re-used from L2.
 // partials: [SD_NSLOT][ntiles] per-tile sums (zero-filled by the host before the launch: invalid tiles
 // write nothing); each is the in-order sum of the tile's per-item sums, so results are run-to-run identical.
-template <int NC, bool PLAIN>
+template <int NC, bool PLAIN, int V>
 __global__ void __launch_bounds__(SD_BLK_THREADS, 1)
 sd_blk_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constant__ SdVecView psi, double *out_local,
                     const __grid_constant__ SdEpi epi, int qfar, unsigned long long *tile_ctr) {
@@ -761,7 +835,7 @@ sd_blk_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constant
                 const unsigned code = ut[un];
                 const uint32_t u = (code & 0xFFu) * 32u + lane;      // the lane's mid configuration
                 double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
-                sd_blk_dispatch<NC, PLAIN>(X, H, tb, code, u, red);
+                sd_blk_dispatch<NC, PLAIN, V>(X, H, tb, code, u, red);
                 if (!PLAIN && slotmask) {
 #pragma unroll
                     for (int s = 0; s < SD_NSLOT; ++s) {

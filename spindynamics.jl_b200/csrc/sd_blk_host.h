@@ -73,14 +73,19 @@ static inline bool sd_blk_build(int L, int k, const double *Jhop, const double *
             std::memset(&it, 0xFF, sizeof(it));
             it.c = (uint16_t)c;
             it.u2x = o.urank[c ^ (1u << (M - 1))];
+            unsigned amask = 0;                                // active mid bonds (body variant 1 iterates these)
             for (int pm = 0; pm + 1 < M; ++pm) {
                 const unsigned b0 = (c >> pm) & 1u, b1 = (c >> (pm + 1)) & 1u;
                 if (b0 != b1 && Jhop[A + pm] != 0.0) {
                     const unsigned u2 = o.urank[c ^ (3u << pm)];
                     if (u2 >= 0xFFu) return false;
                     it.nb[pm] = (uint8_t)u2;
+                    amask |= 1u << pm;
                 }
             }
+            static_assert(SD_BLK_M - 1 <= 9, "nb[0..8] partners, nb[9..10] active mask");
+            it.nb[9] = (uint8_t)(amask & 0xFFu);
+            it.nb[10] = (uint8_t)(amask >> 8);
             o.items.push_back(it);
         }
     }

@@ -30,7 +30,7 @@ struct AlignedBuf {                      // 128-byte aligned doubles (the kernel
     ~AlignedBuf() { free(p); }
 };
 
-template <int NC, bool PLAIN>
+template <int NC, bool PLAIN, int V>
 void run_tiles(const SdBlkHost &bh, const SdBlkParams &P, const SdVecView &psi, double *out_local, const SdEpi &epi,
                int qfar, double *red_total) {
     AlignedBuf tile;
@@ -48,6 +48,7 @@ void run_tiles(const SdBlkHost &bh, const SdBlkParams &P, const SdVecView &psi, 
         // ---- header: what the producer warp computes with shuffles
         SdBlkHdr H;
         std::memset(&H, 0, sizeof(H));
+        for (double &j : H.nb_J) j = NAN;                            // entries the header does not write must never be used
         SdBlkHdrLane lanes[32];
         uint64_t base = 0;
         double dpre = 0.0;
@@ -72,7 +73,7 @@ void run_tiles(const SdBlkHost &bh, const SdBlkParams &P, const SdVecView &psi, 
             for (unsigned lane = 0; lane < 32; ++lane) {
                 const uint32_t u = (code & 0xFFu) * 32u + lane;
                 double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
-                sd_blk_dispatch<NC, PLAIN>(X, H, tile.p, code, u, red);
+                sd_blk_dispatch<NC, PLAIN, V>(X, H, tile.p, code, u, red);
                 for (int s = 0; s < SD_NSLOT; ++s) red_total[s] += red[s];
             }
         }
@@ -93,7 +94,7 @@ int emul_blk_apply(int L, int k, const double *Jhop, const double *Jz, const dou
                    const uint64_t *states, uint64_t N, const double *psi, double *out,
                    int world, int rank, int mode, int redmask, double hscale, double a, double b,
                    const double *vprev, const double *phi, double *acc, double ck_re, double ck_im,
-                   double *red_out, uint64_t *bounds_out, uint64_t far_bytes, uint64_t *n_store_out) {
+                   double *red_out, uint64_t *bounds_out, uint64_t far_bytes, uint64_t *n_store_out, int variant) {
     SdBlkHost bh;
     if (!sd_blk_build(L, k, Jhop, Jz, h, bh)) return -1;
     SdTileHost th;                                                  // shard bounds come from the tiled split (same tile keys)
@@ -152,13 +153,11 @@ int emul_blk_apply(int L, int k, const double *Jhop, const double *Jz, const dou
     if (acc) { to_blk(acc, s_acc, nullptr); epi.acc = s_acc[rank].p; }
     double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
     const bool plain = epi.mode == SD_EPI_PLAIN && epi.red == 0 && !epi.acc && epi.hscale == 1.0;
-    if (NC == 1) {
-        if (plain) run_tiles<1, true>(bh, P, view, o.p, epi, qfar, red);
-        else run_tiles<1, false>(bh, P, view, o.p, epi, qfar, red);
-    } else {
-        if (plain) run_tiles<2, true>(bh, P, view, o.p, epi, qfar, red);
-        else run_tiles<2, false>(bh, P, view, o.p, epi, qfar, red);
-    }
+#define RUN(NC_, PLAIN_) do { if (variant == 1) run_tiles<NC_, PLAIN_, 1>(bh, P, view, o.p, epi, qfar, red); \
+                              else run_tiles<NC_, PLAIN_, 0>(bh, P, view, o.p, epi, qfar, red); } while (0)
+    if (NC == 1) { if (plain) RUN(1, true); else RUN(1, false); }
+    else { if (plain) RUN(2, true); else RUN(2, false); }
+#undef RUN
     if (red_out) for (int s = 0; s < SD_NSLOT; ++s) red_out[s] = red[s];
     // ---- back to rank order; padding must still be zero
     std::vector<unsigned char> real(nloc / NC, 0);

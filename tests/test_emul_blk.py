@@ -20,7 +20,7 @@ from conftest import ROOT
 vp = ctypes.c_void_p
 ARGTYPES = ([ctypes.c_int, ctypes.c_int, vp, vp, vp, ctypes.c_int, vp, ctypes.c_uint64, vp, vp,
              ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double,
-             vp, vp, vp, ctypes.c_double, ctypes.c_double, vp, vp, ctypes.c_uint64, vp])
+             vp, vp, vp, ctypes.c_double, ctypes.c_double, vp, vp, ctypes.c_uint64, vp, ctypes.c_int])
 
 
 def load():
@@ -31,8 +31,13 @@ def load():
     return lib
 
 
-@pytest.fixture(scope="module")
-def emul():
+VARIANT = 0          # item-body variant run() uses; the `emul` fixture runs every test with both
+
+
+@pytest.fixture(scope="module", params=[0, 1], ids=["body0", "body1"])
+def emul(request):
+    global VARIANT
+    VARIANT = request.param
     return load()
 
 
@@ -64,7 +69,8 @@ def oracle_apply(m, psi, NC):
 
 
 def run(lib, L, k, NC, world, states, psi, Jhop, Jz, h, mode=0, red=0, hscale=1.0, a=1.0, b=0.0,
-        vprev=None, phi=None, acc=None, ck=0j, far_bytes=1 << 20):
+        vprev=None, phi=None, acc=None, ck=0j, far_bytes=1 << 20, variant=None):
+    variant = VARIANT if variant is None else variant
     N = len(states)
     out = np.full(N * NC, np.nan)
     redsum = np.zeros(4)
@@ -74,7 +80,7 @@ def run(lib, L, k, NC, world, states, psi, Jhop, Jz, h, mode=0, red=0, hscale=1.
         redr = np.zeros(4)
         rc = lib.emul_blk_apply(L, k, P(Jhop), P(Jz), P(h), NC, P(states), N, P(psi), P(out), world, r,
                                 mode, red, hscale, a, b, P(vprev), P(phi), P(acc), ck.real, ck.imag,
-                                P(redr), P(bounds), far_bytes, P(nstore))
+                                P(redr), P(bounds), far_bytes, P(nstore), variant)
         assert rc == 0, rc
         redsum += redr
     return out, redsum, bounds, int(nstore[0])
@@ -189,7 +195,7 @@ def _gloo_worker(rank, world, port, q):
         red = np.zeros(4)
         bounds = np.zeros(world + 1, dtype=np.uint64)
         rc = lib.emul_blk_apply(L, k, P(Jhop), P(Jz), P(h), 1, P(states), N, P(psi), P(out), world, rank,
-                                0, 1, 1.0, 1.0, 0.0, None, None, None, 0.0, 0.0, P(red), P(bounds), 1 << 20, None)
+                                0, 1, 1.0, 1.0, 0.0, None, None, None, 0.0, 0.0, P(red), P(bounds), 1 << 20, None, 0)
         assert rc == 0
         lo, hi = int(bounds[rank]), int(bounds[rank + 1])
         sizes = [int(bounds[g + 1] - bounds[g]) for g in range(world)]
