@@ -67,3 +67,26 @@ def test_host_side_validation_mirrors_reference_errors():
     assert sd.flip_bits(0b0101, 0, 1) == 0b0110
     a, b = sd._rescaling_from_bounds(-3.0, 5.0)                      # test_KPM.jl:32-41
     assert abs((-3.0 - b) / a + 0.99) < 1e-12 and abs((5.0 - b) / a - 0.99) < 1e-12
+
+
+def _header_arg_counts():
+    src = open(os.path.join(ROOT, "include", "spindyn.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(sd_[A-Za-z0-9_]+)\s*\(([^;{}]*?)\)\s*;", src, flags=re.S):
+        args = m.group(2).strip()
+        out[m.group(1)] = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
+    return out
+
+
+def test_julia_binding_matches_the_header():
+    """spindynamics.jl_b200/julia/SpinDynamicsCUDA.jl cannot run here (no julia): check statically that
+    every symbol it ccalls is declared in include/spindyn.h with the same number of arguments."""
+    jl = open(os.path.join(ROOT, "spindynamics.jl_b200", "julia", "SpinDynamicsCUDA.jl")).read()
+    hdr = _header_arg_counts()
+    calls = re.findall(r"ccall\(\(:(sd_[A-Za-z0-9_]+),\s*\w+\),\s*\w+,\s*\(([^)]*)\)", jl)
+    assert len(calls) >= 25
+    for name, argt in calls:
+        assert name in hdr, f"{name} is ccalled from Julia but not declared in include/spindyn.h"
+        n = len([a for a in argt.split(",") if a.strip()])
+        assert n == hdr[name], f"{name}: Julia passes {n} arguments, the header declares {hdr[name]}"
