@@ -48,16 +48,39 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons DURING the timed region.  NVML (nvidia_ml_py) is polled every ~2 ms when it
+    initialises; otherwise `nvidia-smi --query-gpu` (one sample per ~100 ms) as in B200_PROFILING.md."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    NVML_BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
-        self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
+        self.index, self.samples, self._stop, self._t, self.source = index, [], threading.Event(), None, "nvidia-smi"
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(int(index))
+            reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons")
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)); int(reasons(h))      # probe once
+            self._nvml = (pynvml, h, reasons, mx)
+            self.source = "nvml"
+        except Exception:
+            self._nvml = None
 
     def _run(self):
         while not self._stop.is_set():
             try:
+                if self._nvml is not None:
+                    nv, h, reasons, mx = self._nvml
+                    r = int(reasons(h))
+                    self.samples.append([str(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))), str(mx)] +
+                                        ["Active" if r & self.NVML_BITS[n] else "Not Active" for n in self.NAMES])
+                    self._stop.wait(0.002)
+                    continue
                 o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                     "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
                 self.samples.append([x.strip() for x in o.strip().split(",")])
@@ -76,7 +99,6 @@ class ClockSampler:
 
     def summary(self):
         sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for s in self.samples:
             if len(s) < 6:
                 continue
@@ -85,11 +107,11 @@ class ClockSampler:
                 mx = float(s[1])
             except ValueError:
                 continue
-            for n, v in zip(names, s[2:6]):
+            for n, v in zip(self.NAMES, s[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
 
 
 def cpu_port_applies_per_s(L_sample, reps, L_target=32):
