@@ -1,0 +1,150 @@
+"""Tile-granular LRU model of the L2 for the block kernel's neighbour-tile traffic (CPU only).
+
+A tile = one prefix configuration (A = L-15 sites); one H.psi touches, per tile, the tile itself and
+the partner tile of every active prefix bond (+ the prefix|mid crossing partner, half of it).  The model
+replays that access stream for a given TILE ORDER against a byte-weighted LRU of capacity C and reports
+the DRAM read volume, to compare traversal orders before spending GPU time on them.
+
+    python scripts/l2_sim.py [L] [cap_MB ...]
+"""
+import sys
+from collections import OrderedDict
+from math import comb
+
+L = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+caps = [float(x) for x in sys.argv[2:]] or [40, 60, 80, 100, 126]
+k, B = L // 2, 15
+A = L - B
+
+
+def pad(js):
+    if js < 0 or js > B:
+        return 0
+    M, T = 10, 5
+    run = 0
+    for jt in range(T + 1):
+        jm = js - jt
+        if 0 <= jm <= M:
+            run += ((comb(M, jm) + 3) // 4 * 4) * comb(T, jt)
+    return (run + 15) // 16 * 16 * 8          # bytes, f64
+
+
+def tiles_rank_order():
+    """prefix bit patterns in rank order ("1 first", site 0 most significant)."""
+    out = []
+    for key in range(1 << A):
+        Pb = 0
+        for q in range(A):
+            if not (key >> (A - 1 - q)) & 1:
+                Pb |= 1 << q
+        js = k - bin(Pb).count("1")
+        if 0 <= js <= B:
+            out.append(Pb)
+    return out
+
+
+def neighbours(Pb):
+    res = []
+    for q in range(A - 1):
+        if ((Pb >> q) ^ (Pb >> (q + 1))) & 1:
+            res.append((Pb ^ (3 << q), 1.0))
+    x = Pb ^ (1 << (A - 1))                      # crossing partner: about half of its elements are read
+    if 0 <= k - bin(x).count("1") <= B:
+        res.append((x, 0.5))
+    return res
+
+
+def simulate(order, cap_bytes):
+    size = {Pb: pad(k - bin(Pb).count("1")) for Pb in order}
+    lru, used, miss_bytes, hit_bytes = OrderedDict(), 0, 0.0, 0.0
+    def touch(t, frac):
+        nonlocal used, miss_bytes, hit_bytes
+        s = size[t]
+        if t in lru:
+            lru.move_to_end(t)
+            hit_bytes += s * frac
+            return
+        miss_bytes += s * frac
+        lru[t] = s
+        used += s
+        while used > cap_bytes:
+            _, s0 = lru.popitem(last=False)
+            used -= s0
+    for t in order:
+        touch(t, 1.0)
+        for n, f in neighbours(t):
+            touch(n, f)
+    return miss_bytes, hit_bytes
+
+
+def order_by_sites(sig):
+    """tile order with prefix sites listed from most to least significant in `sig` ("1 first" per site)."""
+    base = tiles_rank_order()
+    def keyf(Pb):
+        v = 0
+        for q in sig:
+            v = (v << 1) | (0 if (Pb >> q) & 1 else 1)
+        return v
+    return sorted(base, key=keyf)
+
+
+if __name__ == "__main__":
+    base = tiles_rank_order()
+    N = comb(L, k)
+    tot = sum(pad(k - bin(p).count("1")) for p in base)
+    print(f"L={L}: {len(base)} tiles, stored {tot / 1e9:.3f} GB, logical {N * 8 / 1e9:.3f} GB")
+    orders = {"rank order (sites 0..A-1 most->least significant)": base}
+    r = list(range(A))
+    for split in (4, 5, 6, 7, 8):
+        # middle sites slowest, then the top `split` sites, then the remaining low sites fastest
+        mid = r[split:split + (A - split) // 2]
+        low = r[split + (A - split) // 2:]
+        orders[f"mid {mid[0]}..{mid[-1]} slowest, then top 0..{split - 1}, then low {low[0]}..{low[-1]}"] = order_by_sites(mid + r[:split] + low)
+    orders["reverse significance (site A-1 slowest)"] = order_by_sites(r[::-1])
+    orders["interleave top/low (0,A-1,1,A-2,...)"] = order_by_sites([x for pair in zip(r[:A // 2], r[::-1][:A // 2]) for x in pair] + ([r[A // 2]] if A % 2 else []))
+    print(f"{'order':75s} " + " ".join(f"{c:>7.0f}MB" for c in caps) + "   (DRAM read GB per apply; + write %.2f GB)" % (tot / 1e9))
+    for name, o in orders.items():
+        row = []
+        for c in caps:
+            m, h = simulate(o, c * 1e6)
+            row.append(m / 1e9)
+        print(f"{name:75s} " + " ".join(f"{x:9.2f}" for x in row))
+
+
+def simulate_bypass(order, cap_bytes, qfar):
+    """as simulate(), but partner tiles of prefix bonds q < qfar are streamed past the cache
+    (evict-first / no-allocate): they never hit and never displace anything."""
+    size = {Pb: pad(k - bin(Pb).count("1")) for Pb in order}
+    lru, used, miss = OrderedDict(), 0, 0.0
+    def touch(t, frac):
+        nonlocal used, miss
+        s = size[t]
+        if t in lru:
+            lru.move_to_end(t)
+            return
+        miss += s * frac
+        lru[t] = s
+        used += s
+        while used > cap_bytes:
+            _, s0 = lru.popitem(last=False)
+            used -= s0
+    for t in order:
+        touch(t, 1.0)
+        for q in range(A - 1):
+            if ((t >> q) ^ (t >> (q + 1))) & 1:
+                n = t ^ (3 << q)
+                if q < qfar:
+                    if n in lru:
+                        lru.move_to_end(n)
+                    else:
+                        miss += size[n]
+                else:
+                    touch(n, 1.0)
+        x = t ^ (1 << (A - 1))
+        if x in size:
+            touch(x, 0.5)
+    return miss
+
+
+if __name__ == "__main__" and "--bypass" in sys.argv:
+    pass
