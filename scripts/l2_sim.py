@@ -88,6 +88,35 @@ def order_by_sites(sig):
     return sorted(base, key=keyf)
 
 
+def grouped_greedy_order(e):
+    """The order sd_blk_tile_order (sd_blk_host.h) builds: top e sites slow, popcount groups from full to
+    empty, inside a group a greedy chain of adjacent-swap partners; the other prefix sites in rank order."""
+    e = max(1, min(e, A))
+    def lex(c, n):
+        v = 0
+        for q in range(n):
+            v = (v << 1) | (0 if (c >> q) & 1 else 1)
+        return v
+    slow, nxt = {}, 0
+    for p in range(e, -1, -1):
+        cfgs = sorted([c for c in range(1 << e) if bin(c).count("1") == p], key=lambda c: lex(c, e))
+        left = set(cfgs)
+        cur = cfgs[0]
+        while True:
+            left.discard(cur)
+            slow[cur] = nxt
+            nxt += 1
+            if not left:
+                break
+            for q in range(e - 2, -1, -1):
+                if ((cur >> q) ^ (cur >> (q + 1))) & 1 and (cur ^ (3 << q)) in left:
+                    cur ^= 3 << q
+                    break
+            else:
+                cur = min(left, key=lambda c: lex(c, e))
+    return sorted(tiles_rank_order(), key=lambda Pb: (slow[Pb & ((1 << e) - 1)], lex(Pb >> e, A - e)))
+
+
 if __name__ == "__main__":
     base = tiles_rank_order()
     N = comb(L, k)
@@ -102,7 +131,9 @@ if __name__ == "__main__":
         orders[f"mid {mid[0]}..{mid[-1]} slowest, then top 0..{split - 1}, then low {low[0]}..{low[-1]}"] = order_by_sites(mid + r[:split] + low)
     orders["reverse significance (site A-1 slowest)"] = order_by_sites(r[::-1])
     orders["interleave top/low (0,A-1,1,A-2,...)"] = order_by_sites([x for pair in zip(r[:A // 2], r[::-1][:A // 2]) for x in pair] + ([r[A // 2]] if A % 2 else []))
-    print(f"{'order':75s} " + " ".join(f"{c:>7.0f}MB" for c in caps) + "   (DRAM read GB per apply; + write %.2f GB)" % (tot / 1e9))
+    for e in (10, 12):
+        orders[f"grouped greedy, top {e} sites slow (sd_blk_tile_order, SD_BLK_ORDER=1 SD_BLK_ORDER_E={e})"] = grouped_greedy_order(e)
+    print(f"{'order':75s} "+ " ".join(f"{c:>7.0f}MB" for c in caps) + "   (DRAM read GB per apply; + write %.2f GB)" % (tot / 1e9))
     for name, o in orders.items():
         row = []
         for c in caps:

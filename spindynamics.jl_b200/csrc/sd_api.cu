@@ -133,6 +133,8 @@ struct SdBlkDev {
     size_t smem[2] = {0, 0};
     int qfar[2] = {0, 0};
     int variant = 0;                // item-body variant of sd_blk_apply_kernel (SD_BLK_VARIANT)
+    uint32_t *d_order = nullptr;    // optional L2-friendly tile order of this rank's shard (SD_BLK_ORDER=1)
+    uint32_t norder = 0;
 };
 
 struct SdTileDev {
@@ -450,6 +452,7 @@ static SdBlkParams sd_blk_params(const sd_model *m, int nc) {
     const sd_ctx *c = m->ctx;
     P.nbuf = m->blk.nbuf[nc - 1];
     P.dbg = sd_env_int("SD_BLK_DBG", 0);
+    P.order = m->blk.d_order; P.norder = m->blk.norder;
     P.key_lo = m->tile[0].keys[c->rank];
     P.key_hi = m->tile[0].keys[c->rank + 1];
     P.shards.world = c->world; P.shards.rank = c->rank;
@@ -562,6 +565,15 @@ int sd_model_create(sd_ctx *ctx, int L, int nup, const sd_bond *hop, int nhop, c
     if (m->blk.ok)
         for (int g = 0; g <= ctx->world; ++g) m->blk.pstart[g] = sd_blk_key_base(m->blk.host, m->tile[0].keys[g]);
     m->blk_layout = (m->path == SD_PATH_BLOCK);
+    if (m->blk.ok && sd_env_int("SD_BLK_ORDER", 0)) {               // experimental: L2-friendly tile order (sd_blk_tile_order)
+        std::vector<uint32_t> ord;
+        sd_blk_tile_order(m->blk.host, m->tile[0].keys[ctx->rank], m->tile[0].keys[ctx->rank + 1],
+                          sd_env_int("SD_BLK_ORDER_E", 12), ord);
+        if (!ord.empty()) {
+            SD_TRY(sd_to_device(&m->blk.d_order, ord));
+            m->blk.norder = (uint32_t)ord.size();
+        }
+    }
     *model = m;
     return SD_OK;
 }
@@ -577,6 +589,7 @@ int sd_model_free(sd_model *m) {
         SdTileDev &t = m->tile[w];
         cudaFree(t.d_perm); cudaFree(t.d_items); cudaFree(t.d_binomM);
     }
+    cudaFree(m->blk.d_order);
     cudaFree(m->blk.d_W); cudaFree(m->blk.d_js); cudaFree(m->blk.d_units); cudaFree(m->blk.d_items); cudaFree(m->blk.d_dmid);
     delete m;
     return SD_OK;

@@ -84,6 +84,8 @@ struct SdBlkParams {
     const double *dmid;              // [1 << M] diag of the mid sites + mid-internal zz
     uint32_t cap;                    // largest size_pad
     int dbg;                         // profiling switches (SD_BLK_DBG): 1 skip prefix streams, 2 skip suffix hops, 4 skip store
+    const uint32_t *order;           // optional tile order of this shard (keys, norder of them); nullptr: rank order
+    uint32_t norder;
     SdBlkShards shards;
 };
 
@@ -772,6 +774,10 @@ sd_blk_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constant
                 unsigned long long t = 0;
                 if (lane == 0) t = atomicAdd(tile_ctr, 1ULL);
                 t = __shfl_sync(0xffffffffu, t, 0);
+                if (P.order != nullptr) {                          // explicit tile order (valid tiles only, sd_blk_tile_order)
+                    key = t < (unsigned long long)P.norder ? (uint64_t)P.order[t] : P.key_hi;
+                    break;
+                }
                 key = P.key_lo + t;
                 if (key >= P.key_hi) break;
                 const uint64_t Pb = __brevll(~key) >> (64 - P.A);

@@ -186,3 +186,60 @@ static inline uint64_t sd_blk_pos_of_state(const SdBlkHost &o, uint64_t s, int n
     if (nc == 1) return sd_blk_tile_base(o, Pb) + cl.cb + (uint64_t)(e >> 1) * 2u * cl.pitch + 2u * u + (e & 1u);
     return sd_blk_tile_base(o, Pb) + cl.cb + (uint64_t)e * cl.pitch + u;
 }
+
+// L2-friendly tile order of the keys [key_lo, key_hi) (scripts/l2_sim.py, "grouped, greedy chain"): the top e
+// prefix sites are the slow index, visited popcount group by popcount group and, inside a group, along a chain in
+// which consecutive configurations are adjacent-swap partners whenever possible (so the partner tiles of one
+// far bond were read a moment ago and are still in L2); the remaining prefix sites run in rank order.  Under a
+// 63 MB LRU the model predicts 18.3 GB of DRAM reads per L = 32 apply instead of 22.8 GB in rank order.
+// Any order is correct (tiles are independent); only valid tiles are listed.
+static inline void sd_blk_tile_order(const SdBlkHost &o, uint64_t key_lo, uint64_t key_hi, int e, std::vector<uint32_t> &out) {
+    const int A = o.P.A, k = o.P.k;
+    if (e > A) e = A;
+    if (e < 1) e = 1;
+    const unsigned ne = 1u << e;
+    auto lex = [&](unsigned c) {                                    // "1 first" lexicographic key of a top configuration
+        unsigned v = 0;
+        for (int q = 0; q < e; ++q) v = (v << 1) | (((c >> q) & 1u) ? 0u : 1u);
+        return v;
+    };
+    std::vector<uint32_t> slow(ne, 0);                              // visiting position of a top configuration
+    uint32_t next_pos = 0;
+    for (int p = e; p >= 0; --p) {
+        std::vector<unsigned> cfgs;
+        for (unsigned c = 0; c < ne; ++c) if (__builtin_popcount(c) == p) cfgs.push_back(c);
+        std::sort(cfgs.begin(), cfgs.end(), [&](unsigned a, unsigned b) { return lex(a) < lex(b); });
+        std::vector<unsigned char> left(ne, 0);
+        for (unsigned c : cfgs) left[c] = 1;
+        size_t nleft = cfgs.size(), scan = 0;
+        unsigned cur = cfgs[0];
+        for (;;) {
+            left[cur] = 0; --nleft;
+            slow[cur] = next_pos++;
+            if (nleft == 0) break;
+            bool found = false;
+            for (int q = e - 2; q >= 0 && !found; --q)
+                if (((cur >> q) ^ (cur >> (q + 1))) & 1u) {
+                    const unsigned n = cur ^ (3u << q);
+                    if (left[n]) { cur = n; found = true; }
+                }
+            if (!found) {                                           // chain ends: lexicographically first unvisited
+                while (!left[cfgs[scan]]) ++scan;
+                cur = cfgs[scan];
+            }
+        }
+    }
+    std::vector<std::pair<uint64_t, uint32_t>> keyed;
+    keyed.reserve((size_t)(key_hi - key_lo));
+    for (uint64_t key = key_lo; key < key_hi; ++key) {
+        const uint64_t Pb = sd_blk_prefix_bits(key, A);
+        const int js = k - __builtin_popcountll(Pb);
+        if (js < 0 || js > SD_BLK_B) continue;
+        const unsigned top = (unsigned)(Pb & (ne - 1u));
+        const uint64_t low = key & ((1ULL << (A - e)) - 1ULL);       // the low prefix sites are the low key bits (rank order)
+        keyed.push_back({((uint64_t)slow[top] << (A - e)) | low, (uint32_t)key});
+    }
+    std::sort(keyed.begin(), keyed.end());
+    out.resize(keyed.size());
+    for (size_t i = 0; i < keyed.size(); ++i) out[i] = keyed[i].second;
+}

@@ -277,3 +277,37 @@ def test_shard_plan_at_full_sizes(emul, L, k, N):
         assert int(cap[0]) == 6480 and int(cap[0]) * 8 * 3 < 227 * 1024
         stored = [ps[g + 1] - ps[g] for g in range(world)]
         assert max(stored) <= slack * max(sizes) + 6480
+
+
+@pytest.mark.parametrize("L,k,e,world", [(24, 12, 5, 1), (26, 13, 12, 1), (28, 14, 12, 4), (20, 10, 3, 2)])
+def test_optional_tile_order_is_a_permutation_of_the_shards_valid_tiles(emul, L, k, e, world):
+    """sd_blk_tile_order (SD_BLK_ORDER=1): every valid tile key of the shard exactly once; equal to the
+    python model of the same order that scripts/l2_sim.py evaluates."""
+    emul.emul_blk_order.argtypes = [ctypes.c_int] * 5 + [vp, ctypes.c_long, vp, vp]
+    emul.emul_blk_order.restype = ctypes.c_long
+    A = L - 15
+    allkeys = []
+    for rank in range(world):
+        out = np.zeros(1 << A, dtype=np.uint32)
+        lo, hi = np.zeros(1, dtype=np.uint64), np.zeros(1, dtype=np.uint64)
+        n = emul.emul_blk_order(L, k, world, rank, e, P(out), len(out), P(lo), P(hi))
+        assert n >= 0
+        keys = out[:n].astype(np.int64)
+        valid = [key for key in range(int(lo[0]), int(hi[0]))
+                 if 0 <= k - (A - bin(key).count("1")) <= 15]          # key bit = NOT prefix bit
+        assert sorted(keys.tolist()) == valid
+        allkeys.append(keys)
+    if world == 1:
+        import importlib.util
+        import sys
+        argv = sys.argv
+        sys.argv = ["l2_sim", str(L)]
+        try:
+            spec = importlib.util.spec_from_file_location("l2_sim", os.path.join(ROOT, "scripts", "l2_sim.py"))
+            sim = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(sim)
+        finally:
+            sys.argv = argv
+        ref = sim.grouped_greedy_order(e)                              # prefix bit patterns
+        ref_keys = [sum((0 if (Pb >> q) & 1 else 1) << (A - 1 - q) for q in range(A)) for Pb in ref]
+        assert ref_keys == allkeys[0].tolist()
