@@ -117,6 +117,37 @@ def grouped_greedy_order(e):
     return sorted(tiles_rank_order(), key=lambda Pb: (slow[Pb & ((1 << e) - 1)], lex(Pb >> e, A - e)))
 
 
+def bfs_order(e):
+    """mode 2 of sd_blk_tile_order: breadth-first order of every popcount group of the top-e adjacent-swap graph."""
+    from collections import deque
+    e = max(1, min(e, A, 24))
+    def lex(c, n):
+        v = 0
+        for q in range(n):
+            v = (v << 1) | (0 if (c >> q) & 1 else 1)
+        return v
+    slow, nxt = {}, 0
+    for p in range(e, -1, -1):
+        cfgs = sorted([c for c in range(1 << e) if bin(c).count("1") == p], key=lambda c: lex(c, e))
+        seen = set()
+        for start in cfgs:
+            if start in seen:
+                continue
+            dq = deque([start])
+            seen.add(start)
+            while dq:
+                c = dq.popleft()
+                slow[c] = nxt
+                nxt += 1
+                for q in range(e - 2, -1, -1):
+                    if ((c >> q) ^ (c >> (q + 1))) & 1:
+                        n = c ^ (3 << q)
+                        if n not in seen:
+                            seen.add(n)
+                            dq.append(n)
+    return sorted(tiles_rank_order(), key=lambda Pb: (slow[Pb & ((1 << e) - 1)], lex(Pb >> e, A - e)))
+
+
 if __name__ == "__main__":
     base = tiles_rank_order()
     N = comb(L, k)
@@ -133,6 +164,8 @@ if __name__ == "__main__":
     orders["interleave top/low (0,A-1,1,A-2,...)"] = order_by_sites([x for pair in zip(r[:A // 2], r[::-1][:A // 2]) for x in pair] + ([r[A // 2]] if A % 2 else []))
     for e in (10, 12):
         orders[f"grouped greedy, top {e} sites slow (sd_blk_tile_order, SD_BLK_ORDER=1 SD_BLK_ORDER_E={e})"] = grouped_greedy_order(e)
+    for e in (12, 14, A - 1):
+        orders[f"breadth-first, top {e} sites slow (SD_BLK_ORDER=2 SD_BLK_ORDER_E={e})"] = bfs_order(e)
     print(f"{'order':75s} "+ " ".join(f"{c:>7.0f}MB" for c in caps) + "   (DRAM read GB per apply; + write %.2f GB)" % (tot / 1e9))
     for name, o in orders.items():
         row = []

@@ -567,8 +567,9 @@ int sd_model_create(sd_ctx *ctx, int L, int nup, const sd_bond *hop, int nhop, c
     m->blk_layout = (m->path == SD_PATH_BLOCK);
     if (m->blk.ok && sd_env_int("SD_BLK_ORDER", 0)) {               // experimental: L2-friendly tile order (sd_blk_tile_order)
         std::vector<uint32_t> ord;
+        const int omode = sd_env_int("SD_BLK_ORDER", 0) == 2 ? 2 : 1;   // 1: greedy chain (e = 12), 2: breadth-first (e = A - 1)
         sd_blk_tile_order(m->blk.host, m->tile[0].keys[ctx->rank], m->tile[0].keys[ctx->rank + 1],
-                          sd_env_int("SD_BLK_ORDER_E", 12), ord);
+                          sd_env_int("SD_BLK_ORDER_E", omode == 2 ? m->blk.host.P.A - 1 : 12), ord, omode);
         if (!ord.empty()) {
             SD_TRY(sd_to_device(&m->blk.d_order, ord));
             m->blk.norder = (uint32_t)ord.size();

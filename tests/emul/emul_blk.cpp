@@ -198,7 +198,7 @@ int emul_blk_plan(int L, int k, int world, uint64_t *bounds, uint64_t *pstart, u
 
 // The optional L2-friendly tile order of rank `rank` (sd_blk_tile_order).  Returns the number of keys written
 // (<= cap), or -1.
-long emul_blk_order(int L, int k, int world, int rank, int e, uint32_t *out, long cap, uint64_t *key_lo, uint64_t *key_hi) {
+long emul_blk_order(int L, int k, int world, int rank, int e, uint32_t *out, long cap, uint64_t *key_lo, uint64_t *key_hi, int mode) {
     SdBlkHost bh;
     std::vector<double> J(L, 0.5), Jz(L, 1.0), h(L, 0.0);
     if (!sd_blk_build(L, k, J.data(), Jz.data(), h.data(), bh)) return -1;
@@ -207,7 +207,7 @@ long emul_blk_order(int L, int k, int world, int rank, int e, uint32_t *out, lon
     uint64_t bounds[SD_MAX_WORLD + 1], keys[SD_MAX_WORLD + 1];
     sd_tile_shard_bounds(th, world, bounds, keys);
     std::vector<uint32_t> ord;
-    sd_blk_tile_order(bh, keys[rank], keys[rank + 1], e, ord);
+    sd_blk_tile_order(bh, keys[rank], keys[rank + 1], e, ord, mode);
     if ((long)ord.size() > cap) return -1;
     for (size_t i = 0; i < ord.size(); ++i) out[i] = ord[i];
     *key_lo = keys[rank]; *key_hi = keys[rank + 1];

@@ -279,18 +279,19 @@ def test_shard_plan_at_full_sizes(emul, L, k, N):
         assert max(stored) <= slack * max(sizes) + 6480
 
 
-@pytest.mark.parametrize("L,k,e,world", [(24, 12, 5, 1), (26, 13, 12, 1), (28, 14, 12, 4), (20, 10, 3, 2)])
-def test_optional_tile_order_is_a_permutation_of_the_shards_valid_tiles(emul, L, k, e, world):
-    """sd_blk_tile_order (SD_BLK_ORDER=1): every valid tile key of the shard exactly once; equal to the
-    python model of the same order that scripts/l2_sim.py evaluates."""
-    emul.emul_blk_order.argtypes = [ctypes.c_int] * 5 + [vp, ctypes.c_long, vp, vp]
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("L,k,e,world", [(24, 12, 5, 1), (26, 13, 12, 1), (28, 14, 12, 4), (20, 10, 3, 2), (26, 13, 10, 1)])
+def test_optional_tile_order_is_a_permutation_of_the_shards_valid_tiles(emul, L, k, e, world, mode):
+    """sd_blk_tile_order (SD_BLK_ORDER=1 greedy chain, =2 breadth-first): every valid tile key of the shard
+    exactly once; equal to the python model of the same order that scripts/l2_sim.py evaluates."""
+    emul.emul_blk_order.argtypes = [ctypes.c_int] * 5 + [vp, ctypes.c_long, vp, vp, ctypes.c_int]
     emul.emul_blk_order.restype = ctypes.c_long
     A = L - 15
     allkeys = []
     for rank in range(world):
         out = np.zeros(1 << A, dtype=np.uint32)
         lo, hi = np.zeros(1, dtype=np.uint64), np.zeros(1, dtype=np.uint64)
-        n = emul.emul_blk_order(L, k, world, rank, e, P(out), len(out), P(lo), P(hi))
+        n = emul.emul_blk_order(L, k, world, rank, e, P(out), len(out), P(lo), P(hi), mode)
         assert n >= 0
         keys = out[:n].astype(np.int64)
         valid = [key for key in range(int(lo[0]), int(hi[0]))
@@ -308,6 +309,6 @@ def test_optional_tile_order_is_a_permutation_of_the_shards_valid_tiles(emul, L,
             spec.loader.exec_module(sim)
         finally:
             sys.argv = argv
-        ref = sim.grouped_greedy_order(e)                              # prefix bit patterns
+        ref = sim.grouped_greedy_order(e) if mode == 1 else sim.bfs_order(e)     # prefix bit patterns
         ref_keys = [sum((0 if (Pb >> q) & 1 else 1) << (A - 1 - q) for q in range(A)) for Pb in ref]
         assert ref_keys == allkeys[0].tolist()
