@@ -278,7 +278,7 @@ def main():
         achieved = alg_bytes / world / (ms_step * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath) and world == 1:          # the ncu capture is of the single-GPU launch
             try:
                 with open(tpath) as f:
                     traffic = json.load(f).get(f"apply_L{L}_{args.dtype}_bytes_per_launch")
