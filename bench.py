@@ -278,14 +278,18 @@ def main():
         achieved = alg_bytes / world / (ms_step * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath) and world == 1:          # the ncu capture is of the single-GPU launch
+        knobs = {k: v for k, v in os.environ.items() if k.startswith("SD_BLK") or k in ("SD_FAR_MB", "SD_FORCE_GENERIC")}
+        kname = {"block": "sd_blk_apply_kernel", "tiled": "sd_tile_apply_kernel"}.get(model.info["kernel_path"], "sd_generic_apply_kernel")
+        if kname == "sd_blk_apply_kernel" and args.dtype == "f64" and knobs.get("SD_BLK_RING", "0") not in ("0", ""):
+            kname = "sd_blkr_apply_kernel"                   # experimental ring variant (sd_blkr.h)
+        if os.path.exists(tpath) and world == 1 and not knobs:   # the ncu capture is of the default single-GPU launch
             try:
                 with open(tpath) as f:
                     traffic = json.load(f).get(f"apply_L{L}_{args.dtype}_bytes_per_launch")
             except Exception:
                 traffic = None
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "peak_source": peak_src, "kernel": {"block": "sd_blk_apply_kernel", "tiled": "sd_tile_apply_kernel"}.get(model.info["kernel_path"], "sd_generic_apply_kernel"),
+                    "traffic": traffic, "peak_source": peak_src, "kernel": kname,
                     "algorithmic_bytes_per_launch": alg_bytes // world,
                     "note": "16 B/state f64 (32 c128): one read of psi + one write of out; index math is on the fly"}
         cpu = None
@@ -298,7 +302,8 @@ def main():
                                        f"({N * esz / 1e9:.2f} GB per vector)",
                            "l2": "inputs >> 126 MB L2, no flush needed" if N * esz > 1e9 else "WARNING: fits L2",
                            "sharding": f"{world} contiguous rank ranges, NVLink peer reads" if world > 1 else "single GPU",
-                           "kernel_path": model.info["kernel_path"], "tile_sites": model.info["tile_sites"]},
+                           "kernel_path": model.info["kernel_path"], "tile_sites": model.info["tile_sites"],
+                           **({"env_knobs": knobs} if knobs else {})},
                 "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
                 "cpu_baseline": cpu, "checksum": checksum}
         print(json.dumps(line), flush=True)

@@ -23,6 +23,8 @@
 #include "sd_kernels.cuh"
 #include "sd_blk.h"
 #include "sd_blk_host.h"
+#include "sd_blkr.h"
+#include "sd_blkr_host.h"
 
 #define SD_VERSION 100
 
@@ -135,6 +137,9 @@ struct SdBlkDev {
     int variant = 0;                // item-body variant of sd_blk_apply_kernel (SD_BLK_VARIANT)
     uint32_t *d_order = nullptr;    // optional L2-friendly tile order of this rank's shard (SD_BLK_ORDER=1)
     uint32_t norder = 0;
+    bool ring = false;              // f64 applies run sd_blkr_apply_kernel (SD_BLK_RING=1; sd_blkr.h)
+    SdBlkrWarp *d_rw = nullptr;     // [(B+1)*15] item -> consumer warp packing of the ring kernel
+    size_t ring_smem = 0;
 };
 
 struct SdTileDev {
@@ -436,6 +441,15 @@ static int sd_blk_setup(sd_model *m) {
         b.qfar[w] = sd_tile_qfar(L, b.host.P.A, b.host.binom.data(), (uint64_t)sd_env_int("SD_FAR_MB", 100) << 20, 8 * nc);
     }
     b.variant = sd_env_int("SD_BLK_VARIANT", SD_BLK_DEFAULT_VARIANT) == 1 ? 1 : 0;
+    b.ring = false;
+    if (sd_env_int("SD_BLK_RING", 0)) {                             // experimental: ring kernel for f64 (sd_blkr.h)
+        std::vector<SdBlkrWarp> rw;
+        b.ring_smem = sd_blkr_smem_carve(nullptr, nullptr, b.host.P.A, L, b.host.P.cap);
+        if (sd_blkr_build(b.host, rw) && b.ring_smem <= 227 * 1024) {
+            SD_TRY(sd_to_device(&b.d_rw, rw));
+            b.ring = true;
+        }
+    }
     SD_TRY(sd_to_device(&b.d_W, b.host.W));
     SD_TRY(sd_to_device(&b.d_js, b.host.js));
     SD_TRY(sd_to_device(&b.d_units, b.host.units));
@@ -590,7 +604,7 @@ int sd_model_free(sd_model *m) {
         SdTileDev &t = m->tile[w];
         cudaFree(t.d_perm); cudaFree(t.d_items); cudaFree(t.d_binomM);
     }
-    cudaFree(m->blk.d_order);
+    cudaFree(m->blk.d_order); cudaFree(m->blk.d_rw);
     cudaFree(m->blk.d_W); cudaFree(m->blk.d_js); cudaFree(m->blk.d_units); cudaFree(m->blk.d_items); cudaFree(m->blk.d_dmid);
     delete m;
     return SD_OK;
@@ -1065,8 +1079,20 @@ static int sd_apply_impl(sd_model *m, sd_vec *out, const sd_vec *psi, SdEpi epi,
         if (m->blk.variant == 1) SD_LAUNCH_BLK3(NC_, PLAIN_, 1);                                             \
         else SD_LAUNCH_BLK3(NC_, PLAIN_, 0);                                                                 \
     } while (0)
-        if (nc == 1) { if (plain) SD_LAUNCH_BLK(1, true); else SD_LAUNCH_BLK(1, false); }
+#define SD_LAUNCH_RING(PLAIN_)                                                                               \
+    do {                                                                                                     \
+        static size_t set_smem = 0;                                                                          \
+        const size_t rsmem = m->blk.ring_smem;                                                               \
+        if (rsmem > set_smem) {                                                                              \
+            SD_CUDA(cudaFuncSetAttribute(sd_blkr_apply_kernel<PLAIN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem)); \
+            set_smem = rsmem;                                                                                \
+        }                                                                                                    \
+        sd_blkr_apply_kernel<PLAIN_><<<grid, SD_BLK_THREADS, rsmem, c->stream>>>(P, psi->view, out->d, epi, qfar, c->d_tilectr, m->blk.d_rw); \
+    } while (0)
+        if (nc == 1 && m->blk.ring) { if (plain) SD_LAUNCH_RING(true); else SD_LAUNCH_RING(false); }
+        else if (nc == 1) { if (plain) SD_LAUNCH_BLK(1, true); else SD_LAUNCH_BLK(1, false); }
         else { if (plain) SD_LAUNCH_BLK(2, true); else SD_LAUNCH_BLK(2, false); }
+#undef SD_LAUNCH_RING
 #undef SD_LAUNCH_BLK
 #undef SD_LAUNCH_BLK3
         SD_TRY(sd_launch_check(c, "sd_blk_apply_kernel"));

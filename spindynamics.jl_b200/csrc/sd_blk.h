@@ -166,9 +166,10 @@ SD_HD SdBlkHdrLane sd_blk_hdr_lane(const SdBlkParams &P, const uint64_t *W, uint
     return l;
 }
 // second half, after the warp-wide sums base = sum(term), dpre = sum(d), actmask = ballot(act)
-template <int NC>
+// HDR: SdBlkHdr, or the ring kernel's smaller SdBlkrHdr (sd_blkr.h: same fields, one usum entry per consumer warp)
+template <int NC, class HDR = SdBlkHdr>
 SD_HD void sd_blk_hdr_fill(const SdBlkParams &P, const SdBlkHdrLane &l, uint64_t Pb, uint64_t key, uint64_t base, double dpre,
-                           unsigned actmask, int qfar, int q, SdBlkHdr &H, const SdVecView &psi) {
+                           unsigned actmask, int qfar, int q, HDR &H, const SdVecView &psi) {
     const int A = P.A, js = P.k - SD_POPC64(Pb);
     const int bit = l.bit;
     const unsigned farmask = (qfar >= 32) ? 0xffffffffu : ((1u << qfar) - 1u);
@@ -219,8 +220,8 @@ SD_HD void sd_blk_hdr_fill(const SdBlkParams &P, const SdBlkHdrLane &l, uint64_t
     }
 }
 #if defined(__CUDACC__)
-template <int NC>
-__device__ __forceinline__ void sd_blk_make_hdr(const SdBlkParams &P, const uint64_t *W, uint64_t key, SdBlkHdr &H,
+template <int NC, class HDR = SdBlkHdr>
+__device__ __forceinline__ void sd_blk_make_hdr(const SdBlkParams &P, const uint64_t *W, uint64_t key, HDR &H,
                                                 const SdVecView &psi, int qfar, unsigned lane) {
     const uint64_t Pb = sd_blk_key_prefix(key, P.A);
     const SdBlkHdrLane l = sd_blk_hdr_lane(P, W, Pb, (int)lane);
@@ -231,7 +232,7 @@ __device__ __forceinline__ void sd_blk_make_hdr(const SdBlkParams &P, const uint
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dpre += __shfl_xor_sync(0xffffffffu, dpre, o);
     const unsigned actmask = __ballot_sync(0xffffffffu, l.act);
-    sd_blk_hdr_fill<NC>(P, l, Pb, key, base, dpre, actmask, qfar, (int)lane, H, psi);
+    sd_blk_hdr_fill<NC, HDR>(P, l, Pb, key, base, dpre, actmask, qfar, (int)lane, H, psi);
 }
 #endif
 

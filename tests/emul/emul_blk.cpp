@@ -14,6 +14,7 @@
 #include <vector>
 #include "../../spindynamics.jl_b200/csrc/sd_tile_host.h"
 #include "../../spindynamics.jl_b200/csrc/sd_blk_host.h"
+#include "../../spindynamics.jl_b200/csrc/sd_blkr_host.h"
 
 namespace {
 
@@ -78,6 +79,82 @@ void run_tiles(const SdBlkHost &bh, const SdBlkParams &P, const SdVecView &psi, 
             }
         }
     }
+}
+
+// Ring variant (sd_blkr.h, f64): per tile the header, then for every consumer warp and lane the SAME functions the
+// kernel runs -- sd_blkr_begin, sd_blkr_stream once per ring entry (the "TMA copy" of a neighbour tile is a memcpy
+// into a NaN-filled buffer of the ring-slot size), sd_blkr_own on the tile itself.  Per-warp reduction sums are added
+// in warp order, as the last warp of a tile does.
+template <bool PLAIN>
+int run_tiles_ring(const SdBlkHost &bh, const SdBlkParams &P, const SdVecView &psi, double *out_local, const SdEpi &epi,
+                   int qfar, double *red_total) {
+    std::vector<SdBlkrWarp> rw;
+    if (!sd_blkr_build(bh, rw)) return -4;
+    if (sd_blkr_smem_carve(nullptr, nullptr, P.A, P.L, P.cap) > 227 * 1024) return -5;
+    {   // every item of every suffix popcount exactly once
+        for (int js = 0; js <= SD_BLK_B; ++js) {
+            std::vector<int> seen(SD_BLK_NCLS * 64, 0);
+            auto mark = [&](uint16_t c) { if (c != SD_BLKR_NONE) ++seen[(c >> 12) * 64 + (c & 0xFFF)]; };
+            for (int w = 0; w < SD_BLK_CWARPS; ++w) {
+                const SdBlkrWarp &x = rw[(size_t)js * SD_BLK_CWARPS + w];
+                mark(x.a); mark(x.b[0]); mark(x.b[1]); mark(x.b[2]);
+            }
+            for (int jt = 0; jt <= SD_BLK_T; ++jt) {
+                const uint32_t nu = (bh.js[js].cls[jt].nblk + 31u) / 32u;
+                for (uint32_t j = 0; j < 64; ++j)
+                    if (seen[jt * 64 + j] != (j < nu ? 1 : 0)) return -6;
+            }
+        }
+    }
+    SdBlkCtx X;
+    X.P = &P; X.js = bh.js.data(); X.dmid = bh.dmid.data(); X.dtail = P.dtail; X.Jhop = P.Jhop;
+    X.qx = P.Jz[P.A + SD_BLK_M - 1] * 0.25;
+    X.pstart_local = P.shards.pstart[P.shards.rank];
+    X.out_local = out_local;
+    X.epi = &epi;
+    std::vector<AlignedBuf> ring(SD_BLK_MAXA + 2);
+    for (auto &b : ring) b.alloc(P.cap, NAN);
+    for (uint64_t key = P.key_lo; key < P.key_hi; ++key) {
+        const uint64_t Pb = sd_blk_key_prefix(key, P.A);
+        const int js = P.k - SD_POPC64(Pb);
+        if (js < 0 || js > SD_BLK_B) continue;
+        SdBlkrHdr H;
+        std::memset(&H, 0, sizeof(H));
+        for (double &j : H.nb_J) j = NAN;
+        SdBlkHdrLane lanes[32];
+        uint64_t base = 0;
+        double dpre = 0.0;
+        unsigned actmask = 0;
+        for (int q = 0; q < 32; ++q) {
+            lanes[q] = sd_blk_hdr_lane(P, bh.W.data(), Pb, q);
+            base += lanes[q].term;
+            dpre += lanes[q].d;
+            if (lanes[q].act) actmask |= 1u << q;
+        }
+        for (int q = 0; q < 32; ++q) sd_blk_hdr_fill<1, SdBlkrHdr>(P, lanes[q], Pb, key, base, dpre, actmask, qfar, q, H, psi);
+        // ---- the ring entries of this tile, as the producer warp issues them
+        const int ntot = H.ntot;
+        for (int n = 0; n <= ntot; ++n) {
+            const double *src = n == ntot ? psi.base[P.shards.rank] + H.base : H.nb_ptr[n];
+            const uint32_t elems = (n < ntot && n == H.nnb) ? bh.js[H.jsx].size_pad : bh.js[H.js].size_pad;
+            if (elems > P.cap) return -7;
+            for (size_t i = 0; i < P.cap; ++i) ring[n].p[i] = NAN;
+            std::memcpy(ring[n].p, src, (size_t)elems * sizeof(double));
+        }
+        double wsum[SD_NSLOT][SD_BLK_CWARPS] = {};
+        for (unsigned w = 0; w < SD_BLK_CWARPS; ++w)
+            for (unsigned lane = 0; lane < 32; ++lane) {
+                SdBlkrLane Ln;
+                sd_blkr_begin(Ln, bh.js[H.js], rw[(size_t)H.js * SD_BLK_CWARPS + w], lane);
+                for (int n = 0; n < ntot; ++n) sd_blkr_stream(Ln, bh.js.data(), H, ring[n].p, n);
+                double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
+                sd_blkr_own<PLAIN>(Ln, X, H, ring[ntot].p, red);
+                for (int s = 0; s < SD_NSLOT; ++s) wsum[s][w] += red[s];
+            }
+        for (int s = 0; s < SD_NSLOT; ++s)
+            for (unsigned w = 0; w < SD_BLK_CWARPS; ++w) red_total[s] += wsum[s][w];
+    }
+    return 0;
 }
 
 }  // namespace
@@ -155,7 +232,11 @@ int emul_blk_apply(int L, int k, const double *Jhop, const double *Jz, const dou
     const bool plain = epi.mode == SD_EPI_PLAIN && epi.red == 0 && !epi.acc && epi.hscale == 1.0;
 #define RUN(NC_, PLAIN_) do { if (variant == 1) run_tiles<NC_, PLAIN_, 1>(bh, P, view, o.p, epi, qfar, red); \
                               else run_tiles<NC_, PLAIN_, 0>(bh, P, view, o.p, epi, qfar, red); } while (0)
-    if (NC == 1) { if (plain) RUN(1, true); else RUN(1, false); }
+    if (variant == 2) {                                             // ring kernel: f64 only
+        if (NC != 1) return -1;
+        const int rc = plain ? run_tiles_ring<true>(bh, P, view, o.p, epi, qfar, red) : run_tiles_ring<false>(bh, P, view, o.p, epi, qfar, red);
+        if (rc != 0) return rc;
+    } else if (NC == 1) { if (plain) RUN(1, true); else RUN(1, false); }
     else { if (plain) RUN(2, true); else RUN(2, false); }
 #undef RUN
     if (red_out) for (int s = 0; s < SD_NSLOT; ++s) red_out[s] = red[s];
@@ -193,6 +274,30 @@ int emul_blk_plan(int L, int k, int world, uint64_t *bounds, uint64_t *pstart, u
     for (int x = 0; x <= bh.P.A; ++x)
         if (k - x >= 0 && k - x <= SD_BLK_B) nt += bh.binom[(size_t)bh.P.A * SD_BINOM_DIM + x];
     *n_tiles = nt;
+    return 0;
+}
+
+// Host-side plan of the ring kernel (sd_blkr.h) at any size: dynamic shared memory of a CTA and, per suffix popcount
+// js, the total accumulator slots of a tile and the largest number any consumer warp holds.  Returns 0, -1 (model
+// does not qualify) or -4 (some suffix popcount cannot be packed).
+int emul_blkr_plan(int L, int k, uint64_t *smem_bytes, uint32_t *slots_total, uint32_t *slots_max) {
+    SdBlkHost bh;
+    std::vector<double> J(L, 0.5), Jz(L, 1.0), h(L, 0.0);
+    if (!sd_blk_build(L, k, J.data(), Jz.data(), h.data(), bh)) return -1;
+    std::vector<SdBlkrWarp> rw;
+    if (!sd_blkr_build(bh, rw)) return -4;
+    *smem_bytes = sd_blkr_smem_carve(nullptr, nullptr, bh.P.A, L, bh.P.cap);
+    for (int js = 0; js <= SD_BLK_B; ++js) {
+        slots_total[js] = 0; slots_max[js] = 0;
+        for (int w = 0; w < SD_BLK_CWARPS; ++w) {
+            const SdBlkrWarp &x = rw[(size_t)js * SD_BLK_CWARPS + w];
+            uint32_t n = 0;
+            if (x.a != SD_BLKR_NONE) n += sd_blkr_ec(x.a >> 12);
+            for (int i = 0; i < 3; ++i) if (x.b[i] != SD_BLKR_NONE) n += sd_blkr_ec(x.b[i] >> 12);
+            slots_total[js] += n;
+            if (n > slots_max[js]) slots_max[js] = n;
+        }
+    }
     return 0;
 }
 

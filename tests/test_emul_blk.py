@@ -8,6 +8,7 @@ every epilogue mode with its reductions, and tile-aligned sharding over 1..8 ran
 (including ranks whose shard is empty).  The emulator is test infrastructure; the
 product never loads it."""
 import ctypes
+import math
 import os
 import subprocess
 
@@ -31,10 +32,11 @@ def load():
     return lib
 
 
-VARIANT = 0          # item-body variant run() uses; the `emul` fixture runs every test with both
+VARIANT = 0          # kernel variant run() uses; the `emul` fixture runs every test with each:
+#                      0 / 1 = item bodies of sd_blk_apply_kernel, 2 = the ring kernel (sd_blkr.h, f64 only)
 
 
-@pytest.fixture(scope="module", params=[0, 1], ids=["body0", "body1"])
+@pytest.fixture(scope="module", params=[0, 1, 2], ids=["body0", "body1", "ring"])
 def emul(request):
     global VARIANT
     VARIANT = request.param
@@ -71,6 +73,8 @@ def oracle_apply(m, psi, NC):
 def run(lib, L, k, NC, world, states, psi, Jhop, Jz, h, mode=0, red=0, hscale=1.0, a=1.0, b=0.0,
         vprev=None, phi=None, acc=None, ck=0j, far_bytes=1 << 20, variant=None):
     variant = VARIANT if variant is None else variant
+    if variant == 2 and NC == 2:
+        pytest.skip("the ring kernel is f64 only")
     N = len(states)
     out = np.full(N * NC, np.nan)
     redsum = np.zeros(4)
@@ -118,7 +122,7 @@ def test_zero_couplings_on_some_bonds(emul):
         Jhop[p] = 0.0
     m = oracle_model(L, k, Jhop, Jz, h)
     states = np.ascontiguousarray(m.states, dtype=np.uint64)
-    for NC in (1, 2):
+    for NC in (1, 2) if VARIANT != 2 else (1,):
         psi = rng.standard_normal(len(states) * NC)
         ref = oracle_apply(m, psi, NC)
         out, _, _, _ = run(emul, L, k, NC, 2, states, psi, Jhop, Jz, h)
@@ -245,6 +249,8 @@ def test_block_body_matches_golden_fixture(emul):
             continue
         seen += 1
         NC = 2 if kind == "c128" else 1
+        if VARIANT == 2 and NC == 2:
+            continue
         Jhop, Jz, h = np.full(L - 1, float(g["Jxy"]) / 2), np.full(L - 1, float(g["Jz"])), np.full(L, float(g["hz"]))
         om = orc.XXZChain(L, nup=nup)
         states = np.array(om.states, dtype=np.uint64)
@@ -312,3 +318,22 @@ def test_optional_tile_order_is_a_permutation_of_the_shards_valid_tiles(emul, L,
         ref = sim.grouped_greedy_order(e) if mode == 1 else sim.bfs_order(e)     # prefix bit patterns
         ref_keys = [sum((0 if (Pb >> q) & 1 else 1) << (A - 1 - q) for q in range(A)) for Pb in ref]
         assert ref_keys == allkeys[0].tolist()
+
+
+@pytest.mark.parametrize("L,k", [(32, 16), (34, 17), (36, 18), (32, 10), (24, 12), (16, 8)])
+def test_ring_kernel_plan_at_full_sizes(L, k):
+    """sd_blkr.h at BASELINE.json's sizes: the four-slot ring plus tables fits the 227 KB of dynamic shared memory of
+    an sm_100 CTA, every suffix popcount packs into the 15 consumer warps (8 accumulator slots each), and at the
+    heavy suffix popcounts of an Sz = 0 chain the packing is balanced (114 slots: 7 or 8 per warp)."""
+    lib = load()
+    lib.emul_blkr_plan.argtypes = [ctypes.c_int, ctypes.c_int, vp, vp, vp]
+    smem = np.zeros(1, dtype=np.uint64)
+    tot, mx = np.zeros(16, dtype=np.uint32), np.zeros(16, dtype=np.uint32)
+    assert lib.emul_blkr_plan(L, k, P(smem), P(tot), P(mx)) == 0
+    assert int(smem[0]) <= 227 * 1024
+    assert mx.max() <= 8
+    for js in range(16):
+        lo, hi = max(0, js - 5), min(10, js)                        # mid popcounts of the classes jt = 0..5
+        want = sum(-(-math.comb(10, js - jt) // 32) * ((math.comb(5, jt) + 1) // 2) for jt in range(6) if lo <= js - jt <= hi)
+        assert int(tot[js]) == want
+    assert int(tot[7]) == 114 and int(tot[8]) == 114 and int(mx[7]) == 8 and int(mx[8]) == 8
