@@ -18,7 +18,8 @@ import SpecialFunctions: besselj
 export GPUModel, GPUVector, XXZChain, build_model, momenta, nn_hopping, long_range_hopping,
        build_sector_basis, build_full_basis, apply_H!, apply_rescaled_H!, Sz_q_vector,
        lanczos_extremal, lanczos_groundstate, lanczos_tridiag, estimate_energy_bounds,
-       lanczos_sqw, kpm_sqw, krylov_time_evolve, chebyshev_time_evolve,
+       lanczos_sqw, kpm_sqw, krylov_time_evolve, krylov_time_evolve!, KrylovWorkspace, chebyshev_time_evolve,
+       ChebyshevWorkspace,
        groundstate, time_evolve, dynamical_structure_factor, neel_state
 
 const lib = get(ENV, "SPINDYN_CUDA_LIB", "libspindyn_cuda")
@@ -292,9 +293,29 @@ function krylov_time_evolve(ψ0, dt::Float64, ::typeof(apply_H!), m::GPUModel; k
     device ? ψt : download(ψt)
 end
 
+# Krylov.jl:25-118: the in-place twin.  The Krylov basis is device-resident inside the library for one call, so the
+# workspace only carries the sizes the reference asserts on.
+struct KrylovWorkspace; n::Int; m::Int; end
+function krylov_time_evolve!(ψ_out::Vector{ComplexF64}, ψ_in::Vector{ComplexF64}, dt::Float64, f::typeof(apply_H!),
+                             m::GPUModel, ws::KrylovWorkspace; kry_m::Int=30)
+    @assert length(ψ_out) == length(ψ_in)
+    @assert ws.m ≥ kry_m
+    if norm(ψ_in) == 0
+        copyto!(ψ_out, ψ_in); return ψ_out
+    end
+    copyto!(ψ_out, krylov_time_evolve(ψ_in, dt, f, m; kry_m=kry_m))
+    return nothing
+end
+
+# Chebyshev.jl:19-36: ϕ_prev/ϕ_curr/ϕ_next/ψ_t live on the device inside sd_chebyshev_evolve; N is kept for the size check
+struct ChebyshevWorkspace{T<:Number}; N::Int; end
+ChebyshevWorkspace{T}(ψ::AbstractVector) where T = ChebyshevWorkspace{T}(length(ψ))
+ChebyshevWorkspace(ψ::AbstractVector{T}) where T<:Number = ChebyshevWorkspace{T}(length(ψ))
+
 function chebyshev_time_evolve(ψ0, dt::Float64, ::typeof(apply_H!), m::GPUModel; cheb_n::Int=100,
-                               Ebounds::Tuple{Float64,Float64}=(-1.0, 1.0), device::Bool=false)
+                               Ebounds::Tuple{Float64,Float64}=(-1.0, 1.0), device::Bool=false, workspace=nothing)
     @assert cheb_n >= 1 "cheb_n must be >= 1"
+    workspace === nothing || @assert workspace.N == length(ψ0) "Workspace size mismatch"
     Emin, Emax = Ebounds; a = (Emax - Emin) / (2 * 0.9999); b = (Emax + Emin) / 2           # Chebyshev.jl:70-79
     c = [(2 - (k == 0)) * (-1im)^k * besselj(k, a * dt) * exp(-1im * b * dt) for k in 0:cheb_n-1]
     d0 = ondevice(m, ψ0); d0 isa GPUVector{ComplexF64} || throw(InexactError(:chebyshev_time_evolve, ComplexF64, 0))

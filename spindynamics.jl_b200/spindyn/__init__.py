@@ -9,7 +9,8 @@ from .api import (XXZChain, Sz_q_vector, apply_H_, apply_H_neg_, apply_rescaled_
                   build_model, build_sector_basis, chebyshev_coefficients, chebyshev_time_evolve,
                   compute_chebyshev_moments, domain_wall_state, dynamical_structure_factor,
                   estimate_energy_bounds, flip_bits, get_kernel, get_rescaling_params, groundstate,
-                  kpm_sqw, kpm_sw, krylov_time_evolve, lanczos_extremal, lanczos_groundstate, lanczos_sqw,
+                  kpm_sqw, kpm_sw, krylov_time_evolve, krylov_time_evolve_, KrylovWorkspace, ChebyshevWorkspace,
+                  lanczos_extremal, lanczos_groundstate, lanczos_sqw,
                   lanczos_tridiag, long_range_hopping, momenta, neel_state, nn_hopping, polarized_state,
                   polarized_state_with_flips, randn_complex, spectral_from_tridiagonal, sz_value,
                   time_evolve, _rescaling_from_bounds)

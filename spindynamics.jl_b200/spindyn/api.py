@@ -522,7 +522,48 @@ def krylov_time_evolve(psi0, dt: float, applyH_, model: Model, kry_m: int = 30, 
     return psit if (device or _is_dev(psi0)) else psit.to_host()
 
 
+class KrylovWorkspace:
+    """Krylov.jl:25-40.  The reference preallocates m basis vectors + w on the host; on the GPU path the basis is
+    device-resident and owned by the library for the duration of one call (sd_krylov_basis -> sd_vecset), so the
+    workspace only carries the sizes the reference asserts on (`length(ws.V) >= kry_m`)."""
+
+    def __init__(self, n: int, m: int):
+        self.n, self.m = int(n), int(m)
+        self.alpha = np.zeros(self.m, dtype=np.complex128)
+        self.beta = np.zeros(max(self.m - 1, 0), dtype=np.complex128)
+
+
+def krylov_time_evolve_(psi_out, psi_in, dt: float, applyH_, model: Model, ws: KrylovWorkspace, kry_m: int = 30):
+    """krylov_time_evolve!(psi_out, psi_in, dt, applyH!, model, ws; kry_m)   Krylov.jl:55-118: the in-place twin
+    (untested upstream), routed to the same device routine as krylov_time_evolve.  Returns None; psi_out is
+    returned when psi_in has zero norm, as upstream does (:69-72)."""
+    cplx = (lambda x: (x.dtype if _is_dev(x) else np.asarray(x).dtype) == np.complex128)
+    if not (cplx(psi_out) and cplx(psi_in)):
+        raise TypeError("MethodError: krylov_time_evolve! takes Vector{ComplexF64}")
+    if len(psi_out) != len(psi_in):
+        raise ValueError("AssertionError: length(psi_out) == n")
+    if ws.m < int(kry_m):
+        raise ValueError("AssertionError: length(ws.V) >= kry_m")
+    res = krylov_time_evolve(psi_in, float(dt), applyH_, model, kry_m=int(kry_m), device=_is_dev(psi_out))
+    zero = res is psi_in or (not _is_dev(psi_in) and not _is_dev(res) and not np.any(res))
+    if _is_dev(psi_out):
+        if res is not psi_out:
+            psi_out.copy_from(res if _is_dev(res) else model.to_device(np.asarray(res, dtype=np.complex128)))
+    else:
+        psi_out[:] = res.to_host() if _is_dev(res) else res
+    return psi_out if zero else None
+
+
 # ------------------------------------------------- TimeEvolution/Chebyshev.jl
+
+class ChebyshevWorkspace:
+    """Chebyshev.jl:19-36.  phi_prev / phi_curr / phi_next / psi_t live on the device inside
+    sd_chebyshev_evolve (`w` is unused upstream as well); the workspace keeps N for the size check (:86)."""
+
+    def __init__(self, N_or_psi, dtype=np.complex128):
+        self.N = int(N_or_psi) if np.isscalar(N_or_psi) else len(N_or_psi)
+        self.dtype = np.dtype(dtype)
+
 
 _MINUS_I_POW = (1.0 + 0j, -1j, -1.0 + 0j, 1j)
 
@@ -541,11 +582,13 @@ def chebyshev_coefficients(dt, cheb_n, Ebounds):
 
 
 def chebyshev_time_evolve(psi0, dt: float, applyH_, model: Model, cheb_n: int = 100, Ebounds=(-1.0, 1.0),
-                          device: bool = False):
+                          device: bool = False, workspace: Optional[ChebyshevWorkspace] = None):
     """Chebyshev.jl:61-124."""
     _require_builtin(applyH_)
     if not cheb_n >= 1:
         raise ValueError("AssertionError: cheb_n must be >= 1")
+    if workspace is not None and workspace.N != len(psi0):
+        raise ValueError("AssertionError: Workspace size mismatch")             # :86
     dt_in = psi0.dtype if _is_dev(psi0) else np.asarray(psi0).dtype
     if dt_in != np.complex128:
         raise TypeError("InexactError: real psi0 cannot hold complex Chebyshev sums")

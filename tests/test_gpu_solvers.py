@@ -250,3 +250,30 @@ def test_config2_krylov_from_neel_device_resident():
     pt = sd.krylov_time_evolve(psi0, 0.5, sd.apply_H_, m, kry_m=30)
     ref = orc.krylov_time_evolve(orc.neel_state(om).astype(np.complex128), 0.5, orc.apply_H_, om, kry_m=30)
     assert np.linalg.norm(pt.to_host() - ref) < 1e-9
+
+
+def test_inplace_krylov_and_workspaces():
+    """krylov_time_evolve! / KrylovWorkspace (Krylov.jl:25-118) and ChebyshevWorkspace (Chebyshev.jl:19-36,83-87):
+    same psi(t) as the out-of-place entry points, the reference's size assertions, zero-norm early return."""
+    L = 10
+    m, om = sd.XXZChain(L, nup=5), orc.XXZChain(L, nup=5)
+    rng = np.random.default_rng(8)
+    psi0 = sd.randn_complex(rng, m.dim)
+    psi0 /= np.linalg.norm(psi0)
+    ref = orc.krylov_time_evolve(psi0, 0.3, orc.apply_H_, om, kry_m=20)
+    ws = sd.KrylovWorkspace(m.dim, 20)
+    out = np.zeros(m.dim, dtype=np.complex128)
+    assert sd.krylov_time_evolve_(out, psi0, 0.3, sd.apply_H_, m, ws, kry_m=20) is None
+    assert np.linalg.norm(out - ref) < 1e-9
+    with pytest.raises(ValueError):
+        sd.krylov_time_evolve_(out, psi0, 0.3, sd.apply_H_, m, sd.KrylovWorkspace(m.dim, 5), kry_m=20)
+    with pytest.raises(ValueError):
+        sd.krylov_time_evolve_(np.zeros(3, dtype=np.complex128), psi0, 0.3, sd.apply_H_, m, ws, kry_m=20)
+    z = np.zeros(m.dim, dtype=np.complex128)
+    assert sd.krylov_time_evolve_(out, z, 0.3, sd.apply_H_, m, ws, kry_m=20) is out and not np.any(out)
+    cw = sd.ChebyshevWorkspace(psi0)
+    a = sd.chebyshev_time_evolve(psi0, 0.2, sd.apply_H_, m, cheb_n=40, Ebounds=(-5.0, 3.0), workspace=cw)
+    b = sd.chebyshev_time_evolve(psi0, 0.2, sd.apply_H_, m, cheb_n=40, Ebounds=(-5.0, 3.0))
+    assert np.array_equal(a, b)
+    with pytest.raises(ValueError):
+        sd.chebyshev_time_evolve(psi0, 0.2, sd.apply_H_, m, cheb_n=40, Ebounds=(-5.0, 3.0), workspace=sd.ChebyshevWorkspace(3))

@@ -1,0 +1,55 @@
+"""Host-side logic of the Python mirror that needs no GPU: argument checks that mirror the reference's assertions
+(raised before any library call) and the in-place wrappers, with the device routine replaced by a stub."""
+import numpy as np
+import pytest
+
+from conftest import sd
+from spindyn import api
+
+
+class _M:
+    dim = 4
+
+
+def test_inplace_krylov_wrapper_logic(monkeypatch):
+    """krylov_time_evolve! (Krylov.jl:55-118): size assertions, None on success, psi_out on the zero-norm early
+    return (:69-72), ComplexF64-only method."""
+    def fake(psi0, dt, applyH_, model, kry_m=30, device=False):
+        if not np.any(psi0):
+            return np.array(psi0, copy=True)
+        return psi0 * np.exp(-1j * dt)
+
+    monkeypatch.setattr(api, "krylov_time_evolve", fake)
+    out, psi = np.zeros(4, dtype=complex), np.arange(4) + 0j
+    ws = sd.KrylovWorkspace(4, 20)
+    assert api.krylov_time_evolve_(out, psi, 0.3, sd.apply_H_, _M(), ws, kry_m=20) is None
+    assert np.allclose(out, psi * np.exp(-0.3j))
+    assert api.krylov_time_evolve_(out, np.zeros(4, dtype=complex), 0.3, sd.apply_H_, _M(), ws, kry_m=20) is out
+    assert not np.any(out)
+    with pytest.raises(ValueError):
+        api.krylov_time_evolve_(np.zeros(3, dtype=complex), psi, 0.3, sd.apply_H_, _M(), ws, kry_m=20)
+    with pytest.raises(ValueError):
+        api.krylov_time_evolve_(out, psi, 0.3, sd.apply_H_, _M(), sd.KrylovWorkspace(4, 5), kry_m=20)
+    with pytest.raises(TypeError):
+        api.krylov_time_evolve_(np.zeros(4), psi, 0.3, sd.apply_H_, _M(), ws)
+
+
+def test_chebyshev_argument_checks_precede_the_library():
+    """Chebyshev.jl:66 (`cheb_n >= 1`), :86 (workspace size), and the callback restriction of the GPU path."""
+    psi = np.arange(4) + 0j
+    with pytest.raises(ValueError):
+        sd.chebyshev_time_evolve(psi, 0.1, sd.apply_H_, _M(), cheb_n=0)
+    with pytest.raises(ValueError):
+        sd.chebyshev_time_evolve(psi, 0.1, sd.apply_H_, _M(), cheb_n=5, workspace=sd.ChebyshevWorkspace(3))
+    with pytest.raises(NotImplementedError):
+        sd.chebyshev_time_evolve(psi, 0.1, lambda o, p, m: o, _M(), cheb_n=5)
+    assert sd.ChebyshevWorkspace(psi).N == 4 and sd.ChebyshevWorkspace(7).N == 7
+
+
+def test_chebyshev_coefficients_match_the_reference_formula():
+    """Chebyshev.jl:70-79: a = (Emax-Emin)/(2*0.9999), b = (Emax+Emin)/2, c_k = (2-delta_k0)(-i)^k J_k(a dt) e^{-i b dt}."""
+    from scipy.special import jv
+    c, a, b = sd.chebyshev_coefficients(0.3, 6, (-0.75, 0.25))
+    assert abs(a - 1.0 / (2 * 0.9999)) < 1e-15 and abs(b + 0.25) < 1e-15
+    want = [(1 if k == 0 else 2) * (-1j) ** k * jv(k, a * 0.3) * np.exp(-1j * b * 0.3) for k in range(6)]
+    assert np.allclose(c, want, rtol=0, atol=1e-15)
