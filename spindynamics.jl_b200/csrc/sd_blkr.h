@@ -342,6 +342,40 @@ SD_HD void sd_blkr_own(SdBlkrLane &S, const SdBlkCtx &X, const SdBlkrHdr &H, con
     else if (S.jtB[2] == SD_BLK_T) sd_blkr_own_at<7, SD_BLK_T, PLAIN>(S, X, H, tb, S.uB[2], red);
 }
 
+// The crossing entry only needs, of every slot row of the partner tile, the blocks whose first mid bit is the
+// opposite of the tile's last prefix bit: a contiguous range of each row (blocks with the first mid bit set come first
+// in a class).  Piece i = (class jt, slot row s) in class-major order, i < SD_BLKR_NPIECE; returns false if the piece is
+// empty.  off / len in doubles from the start of the partner tile, both even (TMA bulk copies move 16-byte units: the
+// plain last row of an odd class is widened by at most one element on either side, inside the padded row).
+#define SD_BLKR_NPIECE 18            // sum over jt of (C(5, jt) + 1) / 2
+SD_HD bool sd_blkr_cross_piece(const SdBlkJs *jstab, int js, int jsx, int bP, int i, uint32_t *off, uint32_t *len) {
+    int jt = 0, s = i;
+#pragma unroll
+    for (int j = 0; j <= SD_BLK_T; ++j) {
+        const int ec = sd_blkr_ec(j);
+        if (jt == j && s >= ec) { s -= ec; jt = j + 1; }
+    }
+    if (jt > SD_BLK_T) return false;
+    const SdBlkCls c = jstab[js].cls[jt];
+    const SdBlkCls cx = jstab[jsx].cls[jt];
+    if (c.nblk == 0u || cx.nblk == 0u) return false;
+    // bP: lanes with the first mid bit clear (u >= n1) read partner blocks [0, nblk - n1); else lanes u < n1 read [cx.n1, cx.n1 + n1)
+    uint32_t x0 = bP ? 0u : cx.n1;
+    uint32_t x1 = bP ? c.nblk - c.n1 : cx.n1 + c.n1;
+    if (x1 <= x0) return false;
+    const int ec = sd_blkr_ec(jt);
+    const bool half = s == ec - 1 && ec != 5;                      // f64: classes of 1 and 5 end in a plain row
+    if (half) {
+        x0 &= ~1u; x1 = (x1 + 1u) & ~1u;
+        *off = cx.cb + (uint32_t)(2 * ec - 2) * cx.pitch + x0;
+        *len = x1 - x0;
+    } else {
+        *off = cx.cb + (uint32_t)s * 2u * cx.pitch + 2u * x0;
+        *len = 2u * (x1 - x0);
+    }
+    return true;
+}
+
 // shared-memory carve-up of the ring kernel
 struct SdBlkrSmem {
     uint64_t *full, *empty;      // [NB] mbarriers
@@ -479,6 +513,20 @@ sd_blkr_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constan
                     if (n == nnb) bytes = S.js[H.jsx].size_pad * 8u;     // crossing partner: another suffix popcount
                 }
                 char *dst = (char *)(S.ring + (size_t)slot * P.cap);
+                if (n < ntot && n == nnb && !(P.dbg & 16)) {           // crossing partner: only the row ranges the lanes read
+                    uint32_t off = 0, len = 0;
+                    const bool have = (int)lane < SD_BLKR_NPIECE && sd_blkr_cross_piece(S.js, H.js, H.jsx, H.bP, (int)lane, &off, &len);
+                    uint32_t tot = have ? len * 8u : 0u;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+                    if (lane == 0) {
+                        if (tot) sd_mbar_expect_tx(&S.full[slot], tot);
+                        else sd_mbar_arrive(&S.full[slot]);          // nothing to read: an empty entry
+                    }
+                    __syncwarp();
+                    if (have) sd_bulk_g2s(dst + (size_t)off * 8u, src + (size_t)off * 8u, len * 8u, &S.full[slot]);
+                    continue;
+                }
                 if (lane == 0) sd_mbar_expect_tx(&S.full[slot], bytes);
                 __syncwarp();
                 constexpr uint32_t CH = 8192;

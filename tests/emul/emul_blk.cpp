@@ -139,6 +139,17 @@ int run_tiles_ring(const SdBlkHost &bh, const SdBlkParams &P, const SdVecView &p
             const uint32_t elems = (n < ntot && n == H.nnb) ? bh.js[H.jsx].size_pad : bh.js[H.js].size_pad;
             if (elems > P.cap) return -7;
             for (size_t i = 0; i < P.cap; ++i) ring[n].p[i] = NAN;
+            if (n < ntot && n == H.nnb) {                             // crossing partner: the row ranges only, the rest stays NaN
+                static_assert(SD_BLKR_NPIECE <= 32, "one piece per producer lane");
+                for (int i = 0; i < 32; ++i) {
+                    uint32_t off = 0, len = 0;
+                    if (i < SD_BLKR_NPIECE && sd_blkr_cross_piece(bh.js.data(), H.js, H.jsx, H.bP, i, &off, &len)) {
+                        if ((off & 1u) || (len & 1u) || len == 0u || off + len > elems) return -8;   // 16-byte units inside the tile
+                        std::memcpy(ring[n].p + off, src + off, (size_t)len * sizeof(double));
+                    }
+                }
+                continue;
+            }
             std::memcpy(ring[n].p, src, (size_t)elems * sizeof(double));
         }
         double wsum[SD_NSLOT][SD_BLK_CWARPS] = {};
