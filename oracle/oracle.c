@@ -221,6 +221,49 @@ void orc_apply_H_f64(const orc_model *m, double *out, const double *psi) {
     }
 }
 
+/* NOT the reference's algorithm: the "second, stronger CPU baseline" of BASELINE.md.  Same loop as above for the
+ * sector basis, but the Dict probe `get(idxmap, new_state, 0)` (:260) is replaced by combinatorial ranking of the
+ * flipped state (orc_rank_closed_form's sum, evaluated incrementally: a hop that swaps bits a < b of the state moves
+ * the rank by a sum of binomials over the positions a..b), so no hash table is touched.  Used only by bench.py as a
+ * reported figure and checked against orc_apply_H_f64 in tests/test_oracle.py. */
+void orc_apply_H_f64_ranked(const orc_model *m, double *out, const double *psi) {
+    const int L = m->L;
+    if (m->nup < 0) { orc_apply_H_f64(m, out, psi); return; }
+    uint64_t C[65][65];
+    for (int n = 0; n < 65; ++n)
+        for (int r = 0; r < 65; ++r) C[n][r] = (r > n) ? 0 : binom_u64(n, r);
+    const int64_t N = (int64_t)m->N;
+#pragma omp parallel for schedule(static)
+    for (int64_t idx = 0; idx < N; ++idx) {
+        const uint64_t state = m->states[idx];
+        double diag = 0.0;
+        for (int i = 1; i <= L; ++i) diag += m->field[i - 1] * sz_value(bit_at(state, i - 1));
+        for (int b = 0; b < m->nzz; ++b) {
+            const orc_bond *z = &m->zz[b];
+            diag += z->J * sz_value(bit_at(state, (int)z->i - 1)) * sz_value(bit_at(state, (int)z->j - 1));
+        }
+        double value = diag * psi[idx];
+        for (int b = 0; b < m->nhop; ++b) {
+            const orc_bond *h = &m->hop[b];
+            int pa = (int)h->i - 1, pb = (int)h->j - 1;
+            if (pa > pb) { int t = pa; pa = pb; pb = t; }
+            const uint64_t ba = bit_at(state, pa), bb = bit_at(state, pb);
+            if (ba == bb) continue;
+            /* rank = sum over clear bits q of C(L-1-q, rem(q)-1), rem(q) = set bits at positions >= q (of the
+             * remaining ones); only positions pa..pb change their contribution */
+            const uint64_t ns = flip_bits(state, pa, pb);
+            int rem_old = __builtin_popcountll(state >> pa), rem_new = __builtin_popcountll(ns >> pa);
+            int64_t delta = 0;
+            for (int q = pa; q <= pb; ++q) {
+                if ((state >> q) & 1ULL) --rem_old; else if (rem_old > 0) delta -= (int64_t)C[L - 1 - q][rem_old - 1];
+                if ((ns >> q) & 1ULL) --rem_new; else if (rem_new > 0) delta += (int64_t)C[L - 1 - q][rem_new - 1];
+            }
+            value += h->J * psi[idx + delta];
+        }
+        out[idx] = value;
+    }
+}
+
 /* Hamiltonian.jl:211-273, T = ComplexF64 (interleaved re,im). */
 void orc_apply_H_c128(const orc_model *m, double *out, const double *psi) {
     const int L = m->L;

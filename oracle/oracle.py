@@ -67,6 +67,7 @@ def lib():
         L.orc_rank.argtypes = [vp, vp, u64, vp]
         L.orc_apply_H_f64.argtypes = [vp, vp, vp]
         L.orc_apply_H_c128.argtypes = [vp, vp, vp]
+        L.orc_apply_H_f64_ranked.argtypes = [vp, vp, vp]
         L.orc_apply_rescaled_H.argtypes = [vp, vp, vp, dbl, dbl, ctypes.c_int]
         L.orc_szq.argtypes = [vp, vp, vp, ctypes.c_int, dbl]
         L.orc_fill_seeded.argtypes = [vp, u64, u64, u64, ctypes.c_int]
@@ -229,6 +230,15 @@ def apply_H_(out: np.ndarray, psi: np.ndarray, model: Model) -> np.ndarray:
         lib().orc_apply_H_c128(model._c, _ptr(out), _ptr(psi))
     else:
         raise TypeError(psi.dtype)
+    return out
+
+
+def apply_H_ranked_(out: np.ndarray, psi: np.ndarray, model: Model) -> np.ndarray:
+    """NOT the reference's algorithm: apply_H! with the Dict probe replaced by combinatorial ranking
+    (oracle.c orc_apply_H_f64_ranked) -- the second, stronger CPU baseline bench.py reports."""
+    assert out.shape == psi.shape and psi.dtype == np.float64 and out.dtype == np.float64
+    assert out.flags.c_contiguous and psi.flags.c_contiguous and psi.shape[0] == len(model)
+    lib().orc_apply_H_f64_ranked(model._c, _ptr(out), _ptr(psi))
     return out
 
 

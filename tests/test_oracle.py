@@ -369,3 +369,22 @@ def test_energy_golden_file_agrees_with_the_oracle_lanczos():
     assert abs(E0 - g["E0"][str(L)]) < 1e-10
     e = np.array([g["E0"][str(x)] for x in (18, 20, 22, 24)])
     assert np.all(np.abs(np.diff(e, 2)) < 2e-4)          # E0(L) is almost linear in L (bulk energy density)
+
+
+@pytest.mark.parametrize("L,nup,boundary", [(12, 6, "open"), (13, 4, "open"), (10, 5, "periodic"), (9, None, "open"), (8, 0, "open")])
+def test_ranked_cpu_baseline_equals_the_reference_loop(L, nup, boundary):
+    """bench.py's second CPU figure (combinatorial ranking instead of the Dict probe) computes the
+    same H.psi as the reference-faithful loop, also for long-range hops."""
+    rng = np.random.default_rng(L)
+    m = orc.XXZChain(L, Jxy=0.8, Jz=1.1, hz=0.3, nup=nup, boundary=boundary)
+    psi = rng.standard_normal(len(m))
+    a, b = np.empty_like(psi), np.empty_like(psi)
+    orc.apply_H_(a, psi, m)
+    orc.apply_H_ranked_(b, psi, m)
+    assert np.array_equal(a, b)
+    if nup is not None and 0 < nup < L:
+        hop = [(1, L, 0.4), (2, 5, -0.7), (L - 1, 3, 0.2)] + [(i, i + 1, 0.5) for i in range(1, L)]
+        m2 = orc.build_model(L, nup=nup, hopping=hop, onsite_field=np.zeros(L), zz=[])
+        orc.apply_H_(a, psi, m2)
+        orc.apply_H_ranked_(b, psi, m2)
+        assert np.array_equal(a, b)
