@@ -170,6 +170,12 @@ int sd_cheb_step(sd_model *model, sd_vec *vnext, const sd_vec *v, const sd_vec *
 /* Sz_q_vector: phi = L^-1/2 sum_r e^{iqr} s_r psi0 (phi C128, psi0 F64 or C128),
  * *norm2 = ||phi||^2 if non-NULL               Hamiltonian.jl:307-337 */
 int sd_szq(sd_model *model, sd_vec *phi, const sd_vec *psi0, double q, double *norm2);
+/* Observables.jl:14-109 on a device-resident vector, summed over ranks:
+ *   mags[i] = sum |psi|^2 s_i                      magnetization_per_site (:14-37)
+ *   zz[r]   = sum_i sum |psi|^2 s_i s_{(i+r) mod L}  the cyclic diagonals of SzSz (:48-93); the caller forms
+ *   C_r = (zz[r] - sum_i mags[i] mags[(i+r) mod L]) / L  (connected_correlations) and its FFT (structure_factor_Sq).
+ * mags and zz are host arrays of L doubles. */
+int sd_vec_observables(const sd_vec *psi, double *mags, double *zz);
 /* Host-pointer convenience backing apply_H!(::Vector, ::Vector, ::Model): H2D,
  * apply, D2H, synchronous.  Whole-basis vectors; world must be 1. */
 int sd_apply_H_host(sd_model *model, int dtype, void *out, const void *psi);

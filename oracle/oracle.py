@@ -540,6 +540,42 @@ def estimate_energy_bounds(applyH_, model: Model, lanc_m: int = 80,
     return -Emax_neg, Emax
 
 
+# ------------------------------------------------------------ Observables.jl
+
+def _sz_table(model: Model) -> np.ndarray:
+    """sz_value(bit_at(state, i)) for every state and site: [N, L]."""
+    st = np.array(model.states, dtype=np.uint64)
+    return np.where((st[:, None] >> np.arange(model.L, dtype=np.uint64)[None, :]) & np.uint64(1) == 1, 0.5, -0.5)
+
+
+def magnetization_per_site(psi: np.ndarray, model: Model) -> np.ndarray:
+    """Observables.jl:14-37: mags[i] = sum_idx abs2(psi[idx]) * sz_value(bit_at(state, i))."""
+    return (np.abs(psi) ** 2) @ _sz_table(model)
+
+
+def connected_correlations(psi: np.ndarray, model: Model) -> np.ndarray:
+    """Observables.jl:43-95: the full SzSz matrix and S_i, then C_r = (1/L) sum_i SzSz[i, mod1(i+r, L)] - S_i[i] S_i[j]."""
+    L = model.L
+    sz = _sz_table(model)
+    amp2 = np.abs(psi) ** 2
+    S_i = amp2 @ sz                                        # :64
+    SzSz = sz.T @ (amp2[:, None] * sz)                     # :65-67
+    C_r = np.zeros(L)
+    for r in range(L):                                     # :84-92
+        tmp = 0.0
+        for i in range(L):
+            j = (i + r) % L                                # mod1(i+r, L) with 1-based i
+            tmp += SzSz[i, j] - S_i[i] * S_i[j]
+        C_r[r] = tmp / L
+    return C_r
+
+
+def structure_factor_Sq(psi: np.ndarray, model: Model) -> dict:
+    """Observables.jl:101-109."""
+    S_q = np.fft.fft(connected_correlations(psi, model))
+    return {2 * np.pi * n / model.L: float(S_q[n].real) for n in range(model.L)}
+
+
 # ------------------------------------------------------------- LanczosSqw.jl
 
 def spectral_from_tridiagonal(alpha, beta, norm_phi, E0, w_range, eta=0.05, broaden="lorentz"):
@@ -775,6 +811,11 @@ def time_evolve(model, psi0, t, method="krylov", Ebounds=None, **kw):
         bounds = estimate_energy_bounds(apply_H_, model) if Ebounds is None else Ebounds
         return chebyshev_time_evolve(psi0, float(t), apply_H_, model, Ebounds=bounds, **kw)
     raise ValueError(f"unsupported time-evolution method: {method}")
+
+
+def structure_factor(model, psi):
+    """PublicAPI.jl:94-106."""
+    return structure_factor_Sq(psi, model)
 
 
 def dynamical_structure_factor(model, psi0, q, w, method="lanczos", **kw):

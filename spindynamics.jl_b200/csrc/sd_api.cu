@@ -25,6 +25,7 @@
 #include "sd_blk_host.h"
 #include "sd_blkr.h"
 #include "sd_blkr_host.h"
+#include "sd_obs.h"
 
 #define SD_VERSION 100
 
@@ -1259,6 +1260,38 @@ int sd_szq(sd_model *m, sd_vec *phi, const sd_vec *psi0, double q, double *norm2
         SD_TRY(sd_fetch(c, 0, 4, r));
         *norm2 = r[3];
     }
+    return SD_OK;
+}
+// Observables.jl:14-109 on a device-resident vector: mags[L], zz[L] (see sd_obs.h); summed over ranks.
+#define SD_OBS_SLOT 1024                                               // d_scal[1024 .. 1151]
+int sd_vec_observables(const sd_vec *psi, double *mags, double *zz) {
+    SD_ARG(psi && mags && zz, "NULL argument");
+    sd_model *m = psi->model;
+    sd_ctx *c = m->ctx;
+    SD_ARG(m->L <= 63, "L must be at most 63");
+    SD_TRY(sd_use(c));
+    const double *src = psi->d;
+    if (psi->layout) {                               // block layout: run on a rank-ordered staging copy (not a hot path)
+        double *s0 = nullptr;
+        SD_TRY(sd_scratch(c, 0, sd_vec_logical_bytes(psi) + 16, &s0));
+        SD_TRY(sd_blk_permute(psi, s0, psi->nc, 1, 0, 0, 0.0));
+        src = s0;
+    }
+    const unsigned g = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((psi->logical_n + 255) / 256, (uint64_t)c->sm_count * 4));
+    const unsigned nwarps = g * (256 / 32);
+    SD_TRY(sd_partials_reserve(c, (size_t)nwarps * 128));
+    const uint64_t ls = m->shards.start[c->rank];
+    if (psi->nc == 2) sd_obs_kernel<2><<<g, 256, 0, c->stream>>>(m->L, m->k, c->d_binom, ls, psi->logical_n, src, c->d_partials);
+    else sd_obs_kernel<1><<<g, 256, 0, c->stream>>>(m->L, m->k, c->d_binom, ls, psi->logical_n, src, c->d_partials);
+    SD_TRY(sd_launch_check(c, "sd_obs_kernel"));
+    sd_obs_reduce_kernel<<<1, 128, 0, c->stream>>>(c->d_partials, nwarps, c->d_scal + SD_OBS_SLOT);
+    SD_TRY(sd_launch_check(c, "sd_obs_reduce_kernel"));
+    if (c->world > 1)
+        SD_NCCL(g_nccl.AllReduce(c->d_scal + SD_OBS_SLOT, c->d_scal + SD_OBS_SLOT, 128, ncclFloat64_, ncclSum_, c->comm, c->stream));
+    double r[128];
+    SD_TRY(sd_fetch(c, SD_OBS_SLOT, 128, r));
+    if (psi->layout) sd_scratch_release(c);
+    for (int i = 0; i < m->L; ++i) { mags[i] = r[i]; zz[i] = r[64 + i]; }
     return SD_OK;
 }
 int sd_apply_H_host(sd_model *m, int dtype, void *out, const void *psi) {

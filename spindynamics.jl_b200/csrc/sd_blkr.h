@@ -439,6 +439,15 @@ __device__ __forceinline__ void sd_blkr_wait(uint64_t *b, unsigned parity) {
     }
 }
 
+// bulk copy with an L2 evict-first hint: partner tiles of the far prefix bonds (entries n < nfar in rank order) miss
+// L2 anyway and are not needed again soon, so they should not push the near tiles out (SD_BLK_DBG & 32, unmeasured)
+__device__ __forceinline__ void sd_bulk_g2s_evict_first(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(sd_smem_u32(dst)), "l"(src), "r"(bytes), "r"(sd_smem_u32(bar)), "l"(pol) : "memory");
+}
+
 // grid = one persistent CTA per SM; tiles are handed out by a global counter (rank order, or the optional order table).
 // partials: [SD_NSLOT][ntiles] per-tile sums, zero-filled by the host; each is the sum, in warp order, of the tile's
 // per-warp sums, and the item -> warp assignment is a fixed table, so results are run-to-run identical.
@@ -530,8 +539,13 @@ sd_blkr_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constan
                 if (lane == 0) sd_mbar_expect_tx(&S.full[slot], bytes);
                 __syncwarp();
                 constexpr uint32_t CH = 8192;
-                for (uint32_t o = lane * CH; o < bytes; o += 32 * CH)
-                    sd_bulk_g2s(dst + o, src + o, (bytes - o < CH) ? bytes - o : CH, &S.full[slot]);
+                if ((P.dbg & 32) && n < H.nfar) {
+                    for (uint32_t o = lane * CH; o < bytes; o += 32 * CH)
+                        sd_bulk_g2s_evict_first(dst + o, src + o, (bytes - o < CH) ? bytes - o : CH, &S.full[slot]);
+                } else {
+                    for (uint32_t o = lane * CH; o < bytes; o += 32 * CH)
+                        sd_bulk_g2s(dst + o, src + o, (bytes - o < CH) ? bytes - o : CH, &S.full[slot]);
+                }
             }
         }
     } else {

@@ -20,7 +20,8 @@ export GPUModel, GPUVector, XXZChain, build_model, momenta, nn_hopping, long_ran
        lanczos_extremal, lanczos_groundstate, lanczos_tridiag, estimate_energy_bounds,
        lanczos_sqw, kpm_sqw, krylov_time_evolve, krylov_time_evolve!, KrylovWorkspace, chebyshev_time_evolve,
        ChebyshevWorkspace,
-       groundstate, time_evolve, dynamical_structure_factor, neel_state
+       groundstate, time_evolve, dynamical_structure_factor, neel_state,
+       magnetization_per_site, connected_correlations, structure_factor_Sq, structure_factor
 
 const lib = get(ENV, "SPINDYN_CUDA_LIB", "libspindyn_cuda")
 const SD_F64, SD_C128 = Cint(0), Cint(1)
@@ -339,6 +340,23 @@ function dynamical_structure_factor(m::GPUModel, ψ0, q, ω; method::Symbol=:lan
     method === :kpm && return kpm_sqw(ψ0, m, Float64.(q), Float64.(ω); kw...)
     throw(ArgumentError("unsupported dynamical structure-factor method: $method"))
 end
+
+# ------------------------------------------------------------------ Observables.jl:14-109 (ψ may stay on the device)
+function observables(ψ, m::GPUModel)
+    d = ondevice(m, ψ); mags = zeros(m.L); zz = zeros(m.L)
+    check(ccall((:sd_vec_observables, lib), Cint, (Handle, Ptr{Float64}, Ptr{Float64}), d.h, mags, zz))
+    mags, zz
+end
+magnetization_per_site(ψ, m::GPUModel) = observables(ψ, m)[1]
+function connected_correlations(ψ, m::GPUModel)
+    mags, zz = observables(ψ, m); L = m.L
+    [(zz[r+1] - sum(mags[i] * mags[mod1(i + r, L)] for i in 1:L)) / L for r in 0:L-1]
+end
+function structure_factor_Sq(ψ, m::GPUModel)                       # Observables.jl:101-109 (naive DFT: L numbers)
+    C = connected_correlations(ψ, m); L = m.L
+    Dict(2π * (n - 1) / L => real(sum(C[r+1] * exp(-2π * im * (n - 1) * r / L) for r in 0:L-1)) for n in 1:L)
+end
+structure_factor(m::GPUModel, ψ) = structure_factor_Sq(ψ, m)       # PublicAPI.jl:94-106
 
 # InitialStates.jl:40-63 through sd_rank (no idxmap)
 function neel_state(m::GPUModel)

@@ -1,6 +1,6 @@
 """spindyn -- Python host mirror of SpinDynamics.jl's H.psi hot path on top of
 libspindyn_cuda (B200, sm_100a).  Re-exports the reference's export list for
-this path (SpinDynamics.jl:1-75); out-of-scope exports (Observables,
+this path (SpinDynamics.jl:1-75); out-of-scope exports (
 create_spin_operator, site-resolved KPM) stay in the Julia package."""
 from ._lib import LIB_PATH, SIGNATURES, OTHER_SYMBOLS, SpinDynError, ZeroNormError, lib
 from .core import (Context, DeviceVector, Model, PinnedBuffer, VecSet, default_context, device_count,
@@ -10,7 +10,8 @@ from .api import (XXZChain, Sz_q_vector, apply_H_, apply_H_neg_, apply_rescaled_
                   compute_chebyshev_moments, domain_wall_state, dynamical_structure_factor,
                   estimate_energy_bounds, flip_bits, get_kernel, get_rescaling_params, groundstate,
                   kpm_sqw, kpm_sw, krylov_time_evolve, krylov_time_evolve_, KrylovWorkspace, ChebyshevWorkspace,
-                  lanczos_extremal, lanczos_groundstate, lanczos_sqw,
+                  lanczos_extremal, lanczos_groundstate, lanczos_sqw, magnetization_per_site,
+                  connected_correlations, structure_factor_Sq, structure_factor,
                   lanczos_tridiag, long_range_hopping, momenta, neel_state, nn_hopping, polarized_state,
                   polarized_state_with_flips, randn_complex, spectral_from_tridiagonal, sz_value,
                   time_evolve, _rescaling_from_bounds)

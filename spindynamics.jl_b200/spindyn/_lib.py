@@ -89,6 +89,7 @@ SIGNATURES = {
     "sd_cheb_step": [_vp, _vp, _vp, _vp, _d, _d, _vp, _P(_d), _P(_d), _vp, SdComplex],
     "sd_szq": [_vp, _vp, _vp, _d, _P(_d)],
     "sd_apply_H_host": [_vp, _i, _vp, _vp],
+    "sd_vec_observables": [_vp, _vp, _vp],
     "sd_vecset_free": [_vp],
     "sd_vecset_size": [_vp, _P(_i)],
     "sd_vecset_get": [_vp, _i, _P(_vp)],

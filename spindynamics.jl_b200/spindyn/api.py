@@ -255,6 +255,34 @@ def polarized_state_with_flips(model: Model, flips: Sequence[int], device: bool 
     return _one_hot(model, s, "requested flipped polarized state", device)
 
 
+# ------------------------------------------------------------ Observables.jl
+
+def _observables(psi, model: Model):
+    d = _up(model, psi)
+    mags, zz = np.zeros(model.L), np.zeros(model.L)
+    check(lib().sd_vec_observables(d._h, _ptr(mags), _ptr(zz)))
+    return mags, zz
+
+
+def magnetization_per_site(psi, model: Model) -> np.ndarray:
+    """magnetization_per_site(psi, model)   Observables.jl:14-37; psi may be a DeviceVector (nothing is downloaded)."""
+    return _observables(psi, model)[0]
+
+
+def connected_correlations(psi, model: Model) -> np.ndarray:
+    """connected_correlations(psi, model)   Observables.jl:43-95:
+    C_r = (1/L) sum_i <S_i S_{mod1(i+r,L)}> - <S_i><S_{mod1(i+r,L)}>, r = 0..L-1."""
+    mags, zz = _observables(psi, model)
+    L = model.L
+    return np.array([(zz[r] - float(np.dot(mags, np.roll(mags, -r)))) / L for r in range(L)])
+
+
+def structure_factor_Sq(psi, model: Model) -> dict:
+    """structure_factor_Sq(psi, model)   Observables.jl:101-109: {q_n: Re fft(C_r)[n]}, q_n = 2 pi n / L."""
+    S_q = np.fft.fft(connected_correlations(psi, model))
+    return {2 * np.pi * n / model.L: float(S_q[n].real) for n in range(model.L)}
+
+
 # ---------------------------------------------------------------- Lanczos.jl
 
 def _eigvals_symtri(alpha, beta):
@@ -616,6 +644,11 @@ def time_evolve(model: Model, psi0, t, method="krylov", Ebounds=None, **kw):
         bounds = estimate_energy_bounds(apply_H_, model) if Ebounds is None else Ebounds
         return chebyshev_time_evolve(psi0, float(t), apply_H_, model, Ebounds=bounds, **kw)
     raise ValueError(f"unsupported time-evolution method: {method}")
+
+
+def structure_factor(model: Model, psi):
+    """structure_factor(model, psi)   PublicAPI.jl:94-106."""
+    return structure_factor_Sq(psi, model)
 
 
 def dynamical_structure_factor(model: Model, psi0, q, w, method="lanczos", **kw):
