@@ -205,6 +205,12 @@ int sd_lanczos_groundstate(sd_model *model, const sd_vec *v0, int lanc_m, double
  * beta[m_eff-1], normv.  SD_ERR_ZERO_NORM mirrors :210-212. */
 int sd_lanczos_tridiag(sd_model *model, const sd_vec *v, int lanc_m, double tol,
                        double *alpha, double *beta, int *m_eff, double *normv);
+/* Memory-lean ground state (an extension, not a reference function): the plain three-term
+ * Lanczos recurrence on three work vectors instead of the N x m basis of Lanczos.jl:104, run twice from the same v0.
+ * Pass 1 (y == NULL; out, norm2 unused): alpha[lanc_m], beta[lanc_m], *m_eff.  Pass 2 (y[m_eff] = lowest
+ * eigenvector of the tridiagonal matrix, lanc_m = m_eff of pass 1): out = sum_j y[j] v_j, *norm2 = ||out||^2. */
+int sd_lanczos_lean(sd_model *model, const sd_vec *v0_f64, int lanc_m, double tol, double *alpha, double *beta,
+                    int *m_eff, const double *y, sd_vec *out, double *norm2);
 /* compute_chebyshev_moments (KPM_Sqw.jl:95-128): mu[M], phi C128. */
 int sd_kpm_moments(sd_model *model, const sd_vec *phi, int M, double a, double b, double *mu);
 /* krylov_time_evolve's basis build (Krylov.jl:136-173): alpha complex (the

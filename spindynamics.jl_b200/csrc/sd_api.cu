@@ -1556,6 +1556,64 @@ int sd_lanczos_groundstate(sd_model *m, const sd_vec *v0, int lanc_m, double tol
     return SD_OK;
 }
 
+// Memory-lean ground state: NOT a reference function.  lanczos_groundstate (Lanczos.jl:87-181) keeps
+// the N x m basis V (481 GB at L = 32, m = 100) for full reorthogonalisation and for the Ritz vector V*y.  This is the
+// plain three-term recurrence on three work vectors, run twice from the same v0:
+//   pass 1 (y == NULL): alpha[0 .. m_eff-1], beta[0 .. m_eff-2] (apply with the fused <v,Hv>, axpy with the fused ||w||^2);
+//   pass 2 (y != NULL): the SAME kernels in the same order with the stored alpha / beta as host scalars -- the
+//       regenerated v_j are bit-identical to pass 1 -- accumulating out = sum_{j < m_eff} y[j] v_j; *norm2 = ||out||^2.
+// Without reorthogonalisation converged Ritz values reappear as copies, which leaves the lowest Ritz value and the
+// direction of V*y alone; callers gate on E0 against the faithful path (tests: 1e-10).
+int sd_lanczos_lean(sd_model *m, const sd_vec *v0, int lanc_m, double tol, double *alpha, double *beta, int *m_eff,
+                    const double *y, sd_vec *out, double *norm2) {
+    SD_ARG(m && v0 && alpha && beta && m_eff, "NULL argument");
+    SD_ARG(v0->model == m && v0->dtype == SD_F64, "v0 must be an SD_F64 vector of this model");
+    SD_ARG(lanc_m >= 1, "lanc_m must be >= 1");
+    SD_ARG(!y || (out && norm2 && out->model == m && out->dtype == SD_F64 && out->d != v0->d), "pass 2 needs y, an SD_F64 out and norm2");
+    sd_ctx *c = m->ctx;
+    SD_TRY(sd_use(c));
+    const int mm = (int)std::min<uint64_t>((uint64_t)lanc_m, m->N);
+    SdVecGuard G;
+    sd_vec *vj, *vo, *w;
+    SD_TRY(G.make(m, SD_F64, &vj)); SD_TRY(G.make(m, SD_F64, &vo)); SD_TRY(G.make(m, SD_F64, &w));
+    double n0;
+    SD_TRY(sd_normalised_copy(vj, v0, &n0));
+    if (n0 == 0.0) return sd_fail(SD_ERR_ZERO_NORM, "starting vector has zero norm");
+    if (y) {
+        SD_TRY(sd_vec_zero(out));
+        SD_TRY(sd_axpy_impl(out, sd_host_scalar(y[0], 0), vj, sd_host_scalar(0, 0), nullptr, -1));
+    }
+    int eff = mm;
+    for (int j = 1; j <= mm; ++j) {
+        if (y && j == mm) break;                                             // pass 2 needs v_1 .. v_mm only
+        SdEpi e = sd_epi_plain(1.0);
+        e.red = SD_RED_DOT_SELF;
+        SD_TRY(sd_apply_impl(m, w, vj, e, 0));                               // w = H v_j, <v_j, w> -> d_scal[0]
+        const SdScalar sa = y ? sd_host_scalar(-alpha[j - 1], 0) : sd_dev_scalar(c->d_scal + 0, 4);
+        if (j == 1) SD_TRY(sd_axpy_impl(w, sa, vj, sd_host_scalar(0, 0), nullptr, 4));
+        else SD_TRY(sd_axpy_impl(w, sa, vj, sd_host_scalar(-beta[j - 2], 0), vo, 4));
+        if (!y) {
+            double r[8];
+            SD_TRY(sd_fetch(c, 0, 8, r));
+            alpha[j - 1] = r[0];
+            if (j == mm) break;
+            beta[j - 1] = sqrt(r[7]);
+            if (beta[j - 1] < tol) { eff = j; break; }
+        }
+        std::swap(vj, vo);
+        SD_TRY(sd_divide_impl(vj, w, sd_host_scalar(beta[j - 1], 0)));       // v_{j+1} = w / beta_j
+        if (y) SD_TRY(sd_axpy_impl(out, sd_host_scalar(y[j], 0), vj, sd_host_scalar(0, 0), nullptr, -1));
+    }
+    *m_eff = eff;
+    if (y) {
+        SD_TRY(sd_dot_impl(out, out, 1, 0));
+        double r[2];
+        SD_TRY(sd_fetch(c, 0, 2, r));
+        *norm2 = r[0];
+    }
+    return SD_OK;
+}
+
 int sd_kpm_moments(sd_model *m, const sd_vec *phi, int M, double a, double b, double *mu) {
     SD_ARG(m && phi && mu, "NULL argument");
     SD_ARG(phi->model == m && phi->dtype == SD_C128, "phi must be an SD_C128 vector of this model");

@@ -17,7 +17,7 @@ import SpecialFunctions: besselj
 
 export GPUModel, GPUVector, XXZChain, build_model, momenta, nn_hopping, long_range_hopping,
        build_sector_basis, build_full_basis, apply_H!, apply_rescaled_H!, Sz_q_vector,
-       lanczos_extremal, lanczos_groundstate, lanczos_tridiag, estimate_energy_bounds,
+       lanczos_extremal, lanczos_groundstate, lanczos_groundstate_lean, lanczos_tridiag, estimate_energy_bounds,
        lanczos_sqw, kpm_sqw, krylov_time_evolve, krylov_time_evolve!, KrylovWorkspace, chebyshev_time_evolve,
        ChebyshevWorkspace,
        groundstate, time_evolve, dynamical_structure_factor, neel_state,
@@ -200,6 +200,26 @@ function lanczos_groundstate(::typeof(apply_H!), m::GPUModel; lanc_m::Int=100, t
     check(ccall((:sd_lincomb, lib), Cint, (Handle, Ptr{ComplexF64}, Cint, Handle, Ref{Float64}), V[], y, ma, ψ.h, n2))
     scale!(ψ, 1 / sqrt(n2[]))
     ccall((:sd_vecset_free, lib), Cint, (Handle,), V[])
+    F.values[i], (device ? ψ : download(ψ))
+end
+
+# Extension (SURVEY 8f-3, not in the reference): ground state on three device vectors instead of the N x m basis --
+# the three-term recurrence twice from the same v0, pass 2 accumulating the Ritz vector (sd_lanczos_lean).
+function lanczos_groundstate_lean(::typeof(apply_H!), m::GPUModel; lanc_m::Int=100, tol::Float64=1e-12,
+                                  rng::AbstractRNG=Random.default_rng(), v0=nothing, device::Bool=false)
+    mm = min(lanc_m, m.dim)
+    d0 = v0 === nothing ? upload(m, randn(rng, Float64, m.dim)) : ondevice(m, v0)
+    α = zeros(mm); β = zeros(max(mm, 1)); meff = Ref{Cint}()
+    check(ccall((:sd_lanczos_lean, lib), Cint,
+        (Handle, Handle, Cint, Float64, Ptr{Float64}, Ptr{Float64}, Ref{Cint}, Ptr{Float64}, Handle, Ptr{Float64}),
+        m.h, d0.h, mm, tol, α, β, meff, C_NULL, C_NULL, C_NULL))
+    k = meff[]
+    F = eigen(SymTridiagonal(α[1:k], β[1:k-1])); i = argmin(F.values); y = Float64.(F.vectors[:, i])
+    ψ = GPUVector{Float64}(m); n2 = Ref{Float64}()
+    check(ccall((:sd_lanczos_lean, lib), Cint,
+        (Handle, Handle, Cint, Float64, Ptr{Float64}, Ptr{Float64}, Ref{Cint}, Ptr{Float64}, Handle, Ref{Float64}),
+        m.h, d0.h, k, tol, α, β, meff, y, ψ.h, n2))
+    scale!(ψ, 1 / sqrt(n2[]))
     F.values[i], (device ? ψ : download(ψ))
 end
 

@@ -10,7 +10,7 @@ from .api import (XXZChain, Sz_q_vector, apply_H_, apply_H_neg_, apply_rescaled_
                   compute_chebyshev_moments, domain_wall_state, dynamical_structure_factor,
                   estimate_energy_bounds, flip_bits, get_kernel, get_rescaling_params, groundstate,
                   kpm_sqw, kpm_sw, krylov_time_evolve, krylov_time_evolve_, KrylovWorkspace, ChebyshevWorkspace,
-                  lanczos_extremal, lanczos_groundstate, lanczos_sqw, magnetization_per_site,
+                  lanczos_extremal, lanczos_groundstate, lanczos_groundstate_lean, lanczos_sqw, magnetization_per_site,
                   connected_correlations, structure_factor_Sq, structure_factor,
                   lanczos_tridiag, long_range_hopping, momenta, neel_state, nn_hopping, polarized_state,
                   polarized_state_with_flips, randn_complex, spectral_from_tridiagonal, sz_value,

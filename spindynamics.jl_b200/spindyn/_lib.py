@@ -97,6 +97,7 @@ SIGNATURES = {
     "sd_lanczos_extremal": [_vp, _vp, _i, _d, _i, _vp, _vp, _P(_i)],
     "sd_lanczos_groundstate": [_vp, _vp, _i, _d, _d, _vp, _vp, _P(_i), _P(_vp)],
     "sd_lanczos_tridiag": [_vp, _vp, _i, _d, _vp, _vp, _P(_i), _P(_d)],
+    "sd_lanczos_lean": [_vp, _vp, _i, _d, _vp, _vp, _P(_i), _vp, _vp, _P(_d)],
     "sd_kpm_moments": [_vp, _vp, _i, _d, _d, _vp],
     "sd_krylov_basis": [_vp, _vp, _i, _vp, _vp, _P(_i), _P(_d), _P(_vp)],
     "sd_chebyshev_evolve": [_vp, _vp, _vp, _i, _d, _d, _vp],

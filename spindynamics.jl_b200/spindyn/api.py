@@ -370,6 +370,31 @@ def lanczos_groundstate(applyH_, model: Model, lanc_m: int = 100, tol: float = 1
     return Emin, res
 
 
+def lanczos_groundstate_lean(applyH_, model: Model, lanc_m: int = 100, tol: float = 1e-12,
+                             rng: Optional[np.random.Generator] = None, v0=None, device: bool = False,
+                             return_tridiag: bool = False):
+    """Memory-lean ground state -- an EXTENSION, not a reference function.  lanczos_groundstate
+    keeps the N x m basis (Lanczos.jl:104: 481 GB at L = 32, m = 100); this runs the plain three-term recurrence on
+    three device vectors twice from the same start vector: pass 1 for (alpha, beta), pass 2 to accumulate the Ritz
+    vector V*y (sd_lanczos_lean).  Same return convention as lanczos_groundstate: (Emin, psi_gs), ||psi_gs|| = 1."""
+    _require_builtin(applyH_)
+    m = min(int(lanc_m), model.dim)
+    d0 = _start_vector(model, v0, rng, False)
+    alpha, beta = np.zeros(m), np.zeros(max(m, 1))
+    meff = ctypes.c_int()
+    check(lib().sd_lanczos_lean(model._h, d0._h, m, float(tol), _ptr(alpha), _ptr(beta), ctypes.byref(meff), None, None, None))
+    k = meff.value
+    theta, Q = _eigen_symtri(alpha[:k], beta[:k - 1])
+    y = np.ascontiguousarray(Q[:, 0], dtype=np.float64)
+    psi = model.vector(np.float64)
+    n2 = ctypes.c_double()
+    check(lib().sd_lanczos_lean(model._h, d0._h, k, float(tol), _ptr(alpha), _ptr(beta), ctypes.byref(meff), _ptr(y),
+                                psi._h, ctypes.byref(n2)))
+    psi.scale(1.0 / np.sqrt(n2.value))
+    res = psi if (device or _is_dev(v0)) else psi.to_host()
+    return (float(theta[0]), res, alpha[:k].copy(), beta[:k - 1].copy()) if return_tridiag else (float(theta[0]), res)
+
+
 def lanczos_tridiag(applyH_, model: Model, v, lanc_m: int = 100, tol: float = 1e-12):
     """Lanczos.jl:196-246 -> (alpha, beta, normv)."""
     _require_builtin(applyH_)
@@ -633,6 +658,8 @@ def groundstate(model: Model, method="lanczos", **kw):
     """PublicAPI.jl:25-35."""
     if method == "lanczos":
         return lanczos_groundstate(apply_H_, model, **kw)
+    if method == "lanczos_lean":                       # extension: three work vectors instead of the N x m basis
+        return lanczos_groundstate_lean(apply_H_, model, **kw)
     raise ValueError(f"unsupported ground-state method: {method}")
 
 
