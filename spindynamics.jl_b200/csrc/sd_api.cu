@@ -1263,7 +1263,7 @@ int sd_szq(sd_model *m, sd_vec *phi, const sd_vec *psi0, double q, double *norm2
     return SD_OK;
 }
 // Observables.jl:14-109 on a device-resident vector: mags[L], zz[L] (see sd_obs.h); summed over ranks.
-#define SD_OBS_SLOT 1024                                               // d_scal[1024 .. 1151]
+#define SD_OBS_SLOT 3584                                               // d_scal[3584 .. 3711] (sd_lincomb stages coefficients at 1024 .. 3071)
 int sd_vec_observables(const sd_vec *psi, double *mags, double *zz) {
     SD_ARG(psi && mags && zz, "NULL argument");
     sd_model *m = psi->model;
