@@ -376,6 +376,28 @@ SD_HD bool sd_blkr_cross_piece(const SdBlkJs *jstab, int js, int jsx, int bP, in
     return true;
 }
 
+// The bulk copies of ring entry n of a tile (n < ntot: neighbour entries, n == ntot: the tile itself), as producer
+// LANE `lane` issues them: copy number i (i = 0, 1, ...) of that lane moves len bytes from src + off to slot + off.
+// Returns false when the lane has no copy number i.  The kernel's producer warp and tests/emul walk the same list.
+// Whole tiles go in 8 KB chunks dealt round robin to the lanes; the crossing entry is one row range per lane.
+#define SD_BLKR_CHUNK 8192u
+SD_HD bool sd_blkr_copy(const SdBlkJs *jstab, const SdBlkrHdr &H, const double *own_src, int dbg, int n, int ntot,
+                        unsigned lane, unsigned i, const char **src, uint32_t *off, uint32_t *len) {
+    const bool cross = n < ntot && n == H.nnb;
+    *src = (const char *)(n == ntot ? own_src : H.nb_ptr[n]);
+    if (cross && !(dbg & 16)) {
+        uint32_t o = 0, l = 0;
+        if (i != 0u || lane >= (unsigned)SD_BLKR_NPIECE || !sd_blkr_cross_piece(jstab, H.js, H.jsx, H.bP, (int)lane, &o, &l)) return false;
+        *off = o * 8u; *len = l * 8u;
+        return true;
+    }
+    const uint32_t bytes = jstab[cross ? H.jsx : H.js].size_pad * 8u;
+    const uint32_t o = (lane + 32u * i) * SD_BLKR_CHUNK;
+    if (o >= bytes) return false;
+    *off = o; *len = (bytes - o < SD_BLKR_CHUNK) ? bytes - o : SD_BLKR_CHUNK;
+    return true;
+}
+
 // shared-memory carve-up of the ring kernel
 struct SdBlkrSmem {
     uint64_t *full, *empty;      // [NB] mbarriers
@@ -509,42 +531,29 @@ sd_blkr_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constan
             sd_blk_make_hdr<1, SdBlkrHdr>(P, S.W, key, H, psi, qfar, lane);
             __syncwarp();
             const int ntot = nostream ? 0 : H.ntot;
-            const int nnb = H.nnb;
-            const uint32_t own_bytes = S.js[H.js].size_pad * 8u;
+            const double *own_src = psi.base[P.shards.rank] + H.base;
             for (int n = 0; n <= ntot; ++n, ++e) {
                 const unsigned slot = e & (NB - 1);
                 if (n > 0) sd_blkr_wait(&S.empty[slot], ((e / NB) & 1u) ^ 1u);
-                const char *src;
-                uint32_t bytes = own_bytes;
-                if (n == ntot) src = (const char *)(psi.base[P.shards.rank] + H.base);
-                else {
-                    src = (const char *)H.nb_ptr[n];
-                    if (n == nnb) bytes = S.js[H.jsx].size_pad * 8u;     // crossing partner: another suffix popcount
-                }
                 char *dst = (char *)(S.ring + (size_t)slot * P.cap);
-                if (n < ntot && n == nnb && !(P.dbg & 16)) {           // crossing partner: only the row ranges the lanes read
-                    uint32_t off = 0, len = 0;
-                    const bool have = (int)lane < SD_BLKR_NPIECE && sd_blkr_cross_piece(S.js, H.js, H.jsx, H.bP, (int)lane, &off, &len);
-                    uint32_t tot = have ? len * 8u : 0u;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-                    if (lane == 0) {
-                        if (tot) sd_mbar_expect_tx(&S.full[slot], tot);
-                        else sd_mbar_arrive(&S.full[slot]);          // nothing to read: an empty entry
-                    }
-                    __syncwarp();
-                    if (have) sd_bulk_g2s(dst + (size_t)off * 8u, src + (size_t)off * 8u, len * 8u, &S.full[slot]);
-                    continue;
+                // the lane's copies of this entry (sd_blkr_copy); the transaction count is their byte total
+                uint32_t tot = 0;
+                {
+                    const char *src; uint32_t off, len;
+                    for (unsigned i = 0; sd_blkr_copy(S.js, H, own_src, P.dbg, n, ntot, lane, i, &src, &off, &len); ++i) tot += len;
                 }
-                if (lane == 0) sd_mbar_expect_tx(&S.full[slot], bytes);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+                if (lane == 0) {
+                    if (tot) sd_mbar_expect_tx(&S.full[slot], tot);
+                    else sd_mbar_arrive(&S.full[slot]);              // nothing to read: an empty entry
+                }
                 __syncwarp();
-                constexpr uint32_t CH = 8192;
-                if ((P.dbg & 32) && n < H.nfar) {
-                    for (uint32_t o = lane * CH; o < bytes; o += 32 * CH)
-                        sd_bulk_g2s_evict_first(dst + o, src + o, (bytes - o < CH) ? bytes - o : CH, &S.full[slot]);
-                } else {
-                    for (uint32_t o = lane * CH; o < bytes; o += 32 * CH)
-                        sd_bulk_g2s(dst + o, src + o, (bytes - o < CH) ? bytes - o : CH, &S.full[slot]);
+                const bool evict_first = (P.dbg & 32) && n < H.nfar;
+                const char *src; uint32_t off, len;
+                for (unsigned i = 0; sd_blkr_copy(S.js, H, own_src, P.dbg, n, ntot, lane, i, &src, &off, &len); ++i) {
+                    if (evict_first) sd_bulk_g2s_evict_first(dst + off, src + off, len, &S.full[slot]);
+                    else sd_bulk_g2s(dst + off, src + off, len, &S.full[slot]);
                 }
             }
         }

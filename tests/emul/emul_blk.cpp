@@ -135,22 +135,16 @@ int run_tiles_ring(const SdBlkHost &bh, const SdBlkParams &P, const SdVecView &p
         // ---- the ring entries of this tile, as the producer warp issues them
         const int ntot = H.ntot;
         for (int n = 0; n <= ntot; ++n) {
-            const double *src = n == ntot ? psi.base[P.shards.rank] + H.base : H.nb_ptr[n];
             const uint32_t elems = (n < ntot && n == H.nnb) ? bh.js[H.jsx].size_pad : bh.js[H.js].size_pad;
             if (elems > P.cap) return -7;
-            for (size_t i = 0; i < P.cap; ++i) ring[n].p[i] = NAN;
-            if (n < ntot && n == H.nnb) {                             // crossing partner: the row ranges only, the rest stays NaN
-                static_assert(SD_BLKR_NPIECE <= 32, "one piece per producer lane");
-                for (int i = 0; i < 32; ++i) {
-                    uint32_t off = 0, len = 0;
-                    if (i < SD_BLKR_NPIECE && sd_blkr_cross_piece(bh.js.data(), H.js, H.jsx, H.bP, i, &off, &len)) {
-                        if ((off & 1u) || (len & 1u) || len == 0u || off + len > elems) return -8;   // 16-byte units inside the tile
-                        std::memcpy(ring[n].p + off, src + off, (size_t)len * sizeof(double));
-                    }
+            for (size_t i = 0; i < P.cap; ++i) ring[n].p[i] = NAN;   // what no copy writes stays NaN
+            for (unsigned lane = 0; lane < 32; ++lane) {             // the producer warp's bulk copies (sd_blkr_copy)
+                const char *src; uint32_t off, len;
+                for (unsigned i = 0; sd_blkr_copy(bh.js.data(), H, psi.base[P.shards.rank] + H.base, P.dbg, n, ntot, lane, i, &src, &off, &len); ++i) {
+                    if ((off & 15u) || (len & 15u) || len == 0u || (size_t)off + len > (size_t)elems * 8u) return -8;   // TMA: 16-byte units inside the tile
+                    std::memcpy((char *)ring[n].p + off, src + off, len);
                 }
-                continue;
             }
-            std::memcpy(ring[n].p, src, (size_t)elems * sizeof(double));
         }
         double wsum[SD_NSLOT][SD_BLK_CWARPS] = {};
         for (unsigned w = 0; w < SD_BLK_CWARPS; ++w)
@@ -192,6 +186,7 @@ int emul_blk_apply(int L, int k, const double *Jhop, const double *Jz, const dou
     SdBlkParams P = bh.P;
     P.W = bh.W.data(); P.js = bh.js.data(); P.units = bh.units.data(); P.items = bh.items.data(); P.dmid = bh.dmid.data();
     P.nbuf = 3; P.dbg = 0;
+    if (variant == 3) { variant = 2; P.dbg = 16; }                   // ring kernel copying the whole crossing partner tile
     P.key_lo = keys[rank]; P.key_hi = keys[rank + 1];
     P.shards.world = world; P.shards.rank = rank;
     uint64_t pstart[SD_MAX_WORLD + 1];

@@ -36,7 +36,7 @@ VARIANT = 0          # kernel variant run() uses; the `emul` fixture runs every 
 #                      0 / 1 = item bodies of sd_blk_apply_kernel, 2 = the ring kernel (sd_blkr.h, f64 only)
 
 
-@pytest.fixture(scope="module", params=[0, 1, 2], ids=["body0", "body1", "ring"])
+@pytest.fixture(scope="module", params=[0, 1, 2, 3], ids=["body0", "body1", "ring", "ring_fullx"])
 def emul(request):
     global VARIANT
     VARIANT = request.param
@@ -73,7 +73,7 @@ def oracle_apply(m, psi, NC):
 def run(lib, L, k, NC, world, states, psi, Jhop, Jz, h, mode=0, red=0, hscale=1.0, a=1.0, b=0.0,
         vprev=None, phi=None, acc=None, ck=0j, far_bytes=1 << 20, variant=None):
     variant = VARIANT if variant is None else variant
-    if variant == 2 and NC == 2:
+    if variant >= 2 and NC == 2:
         pytest.skip("the ring kernel is f64 only")
     N = len(states)
     out = np.full(N * NC, np.nan)
@@ -122,7 +122,7 @@ def test_zero_couplings_on_some_bonds(emul):
         Jhop[p] = 0.0
     m = oracle_model(L, k, Jhop, Jz, h)
     states = np.ascontiguousarray(m.states, dtype=np.uint64)
-    for NC in (1, 2) if VARIANT != 2 else (1,):
+    for NC in (1, 2) if VARIANT < 2 else (1,):
         psi = rng.standard_normal(len(states) * NC)
         ref = oracle_apply(m, psi, NC)
         out, _, _, _ = run(emul, L, k, NC, 2, states, psi, Jhop, Jz, h)
@@ -249,7 +249,7 @@ def test_block_body_matches_golden_fixture(emul):
             continue
         seen += 1
         NC = 2 if kind == "c128" else 1
-        if VARIANT == 2 and NC == 2:
+        if VARIANT >= 2 and NC == 2:
             continue
         Jhop, Jz, h = np.full(L - 1, float(g["Jxy"]) / 2), np.full(L - 1, float(g["Jz"])), np.full(L, float(g["hz"]))
         om = orc.XXZChain(L, nup=nup)
