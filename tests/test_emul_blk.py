@@ -112,6 +112,20 @@ def test_block_body_matches_oracle(emul, L, k, NC):
         assert N <= nstore <= 1.25 * N + 64 * (1 << (L - 15))          # padding overhead stays small
 
 
+@pytest.mark.parametrize("L,k", [(22, 11), (24, 12), (24, 9)])
+def test_block_body_longer_prefix(emul, L, k):
+    """L = 22, 24 (7 / 9 prefix sites: up to 8 prefix-bond partner tiles + the crossing partner per tile), f64, 1 and 5 ranks."""
+    rng = np.random.default_rng(L)
+    Jhop, Jz, h = model_lists(L, rng)
+    m = oracle_model(L, k, Jhop, Jz, h)
+    states = np.ascontiguousarray(m.states, dtype=np.uint64)
+    psi = rng.standard_normal(len(states))
+    ref = oracle_apply(m, psi, 1)
+    for world in (1, 5):
+        out, _, _, _ = run(emul, L, k, 1, world, states, psi, Jhop, Jz, h)
+        assert np.linalg.norm(out - ref) <= 1e-14 * np.linalg.norm(ref), world
+
+
 def test_zero_couplings_on_some_bonds(emul):
     """J = 0 on a prefix bond, a mid bond, the crossing bonds and a tail bond: inactive bonds are skipped
     in the header / item tables, not multiplied by zero."""
