@@ -16,5 +16,5 @@ for far in 0 100000; do
 done
 cat $O/blkdbg_${TAG}.txt
 P="python bench.py --steps 3 --warmup 2 --no-cpu --no-e2e"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:sd_blk_apply -s 2 -c 1 -o $O/prof_${TAG} -f $P > $O/ncu_full_${TAG}.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:sd_blkr?_apply -s 2 -c 1 -o $O/prof_${TAG} -f $P > $O/ncu_full_${TAG}.log 2>&1
 tail -2 $O/ncu_full_${TAG}.log

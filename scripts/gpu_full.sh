@@ -11,5 +11,5 @@ timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_ref
 BENCH="python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e"
 timeout 300 $BENCH > $O/plain_${TAG}.log 2>&1 &&
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file $O/launches_${TAG}.csv $BENCH > $O/ncu_list_${TAG}.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:sd_blk_apply -s 3 -c 1 -o $O/prof_${TAG} -f $BENCH > $O/ncu_full_${TAG}.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:sd_blkr?_apply -s 3 -c 1 -o $O/prof_${TAG} -f $BENCH > $O/ncu_full_${TAG}.log 2>&1
 tail -n 2 $O/smoke_${TAG}.log $O/pytest_${TAG}.log $O/bench_ref_${TAG}.log; head -c 2500 $O/bench_${TAG}.log
