@@ -440,8 +440,39 @@ def spectral_from_tridiagonal(alpha, beta, norm_phi, E0, w_range, eta=0.05, broa
     raise RuntimeError(f"unknown broadening: {broaden}")
 
 
-def lanczos_sqw(psi0, model: Model, q_list, w_range, lanc_m=200, eta=0.05, broaden="lorentz"):
-    """LanczosSqw.jl:49-80."""
+def _q_parallel(fn, psi0, model: Model, q_list, q_threads: int, **kw):
+    """The reference runs the q-loop of lanczos_sqw / kpm_sqw under Threads.@threads (LanczosSqw.jl:65,
+    KPM_Sqw.jl:218).  Same structure here: `q_threads` host threads, each with its OWN context (stream + scratch) and
+    its own copy of the model and of psi0 on the same GPU, take a contiguous share of q_list, so the small kernels of
+    different momenta overlap on the device (at L = 16 one apply fills 2 of 148 SMs).  Every q is computed by exactly
+    the kernels of the sequential loop, so the result is bit-identical to q_threads = 1.  Single-GPU contexts only."""
+    from concurrent.futures import ThreadPoolExecutor
+    if model.ctx.world != 1:
+        raise ValueError("q_threads > 1 needs a single-GPU context")
+    host = psi0.to_host() if _is_dev(psi0) else np.asarray(psi0)
+    q_list = list(q_list)
+    nt = max(1, min(int(q_threads), len(q_list)))
+    shares = [q_list[len(q_list) * t // nt: len(q_list) * (t + 1) // nt] for t in range(nt)]
+
+    def work(qs):
+        ctx = Context(model.ctx.device)
+        m = None
+        try:
+            m = Model(model.L, model.nup, model.hopping_list, model.onsite_field, model.zz_list, ctx=ctx)
+            return fn(host, m, qs, q_threads=1, **kw)
+        finally:
+            del m                                                    # vectors of fn are gone; model before its context
+            ctx.close()
+
+    with ThreadPoolExecutor(max_workers=nt) as ex:
+        parts = list(ex.map(work, shares))
+    return np.concatenate(parts, axis=0)
+
+
+def lanczos_sqw(psi0, model: Model, q_list, w_range, lanc_m=200, eta=0.05, broaden="lorentz", q_threads: int = 1):
+    """LanczosSqw.jl:49-80.  q_threads > 1: the q-loop on that many host threads / contexts (see _q_parallel)."""
+    if q_threads > 1 and len(q_list) > 1:
+        return _q_parallel(lanczos_sqw, psi0, model, q_list, q_threads, w_range=w_range, lanc_m=lanc_m, eta=eta, broaden=broaden)
     psi0c = _up(model, psi0, np.complex128)
     tmp = model.vector(np.complex128)
     check(lib().sd_apply_H(model._h, tmp._h, psi0c._h))
@@ -516,8 +547,12 @@ def kpm_sw(phi, applyH_, model: Model, w_range, a, b, E0, kpm_m=200, kernel="jac
     return S
 
 
-def kpm_sqw(psi0, model: Model, q_list, w_range, a=None, b=None, kpm_m=200, kernel="jackson", rng=None):
-    """KPM_Sqw.jl:191-256."""
+def kpm_sqw(psi0, model: Model, q_list, w_range, a=None, b=None, kpm_m=200, kernel="jackson", rng=None, q_threads: int = 1):
+    """KPM_Sqw.jl:191-256.  q_threads > 1: the q-loop on that many host threads / contexts (see _q_parallel)."""
+    if q_threads > 1 and len(q_list) > 1:
+        if a is None or b is None:                                  # :211-215 once, not per thread
+            a, b = get_rescaling_params(apply_H_, model, rng=rng)
+        return _q_parallel(kpm_sqw, psi0, model, q_list, q_threads, w_range=w_range, a=a, b=b, kpm_m=kpm_m, kernel=kernel)
     psi0c = _up(model, psi0, np.complex128)
     S = np.zeros((len(q_list), len(w_range)))
     tmp = model.vector(np.complex128)

@@ -53,3 +53,42 @@ def test_chebyshev_coefficients_match_the_reference_formula():
     assert abs(a - 1.0 / (2 * 0.9999)) < 1e-15 and abs(b + 0.25) < 1e-15
     want = [(1 if k == 0 else 2) * (-1j) ** k * jv(k, a * 0.3) * np.exp(-1j * b * 0.3) for k in range(6)]
     assert np.allclose(c, want, rtol=0, atol=1e-15)
+
+
+def test_threaded_q_loop_partitions_q_in_order(monkeypatch):
+    """_q_parallel (the reference's Threads.@threads q-loop, LanczosSqw.jl:65 / KPM_Sqw.jl:218): contiguous shares of
+    q_list, one context + model copy per thread, rows concatenated in q order, context closed after its model."""
+    events = []
+
+    class Ctx:
+        device, world = 0, 1
+
+        def __init__(self, d=0):
+            events.append("ctx")
+
+        def close(self):
+            events.append("close")
+
+    class Mdl:
+        def __init__(self, L, nup, h, f, z, ctx=None):
+            self.L, self.nup, self.hopping_list, self.onsite_field, self.zz_list, self.ctx = L, nup, h, f, z, ctx or Ctx()
+
+        def __del__(self):
+            events.append("model_del")
+
+    monkeypatch.setattr(api, "Context", Ctx)
+    monkeypatch.setattr(api, "Model", Mdl)
+
+    def fn(psi, m, qs, q_threads=1, **kw):
+        assert q_threads == 1 and isinstance(psi, np.ndarray)
+        return np.array([[q * 10 + kw["x"]] for q in qs])
+
+    m = Mdl(4, 2, [], [0.0] * 4, [])
+    events.clear()
+    out = api._q_parallel(fn, np.zeros(3), m, [0, 1, 2, 3, 4, 5, 6], 3, x=1)
+    assert out.ravel().tolist() == [1, 11, 21, 31, 41, 51, 61]
+    assert events.count("ctx") == 3 and events.count("close") == 3 and events.count("model_del") == 3
+    for i, e in enumerate(events):
+        if e == "close":
+            assert "model_del" in events[:i]
+    assert api._q_parallel(fn, np.zeros(3), m, [5], 8, x=2).ravel().tolist() == [52]
