@@ -13,7 +13,9 @@ timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -n 5 | tee $O/pytest
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -n 2 | tee $O/smoke_${TAG}.txt
 timeout 300 python bench.py > $O/bench_${TAG}.log 2>&1; tail -n 1 $O/bench_${TAG}.log
 echo "== ring kernel parity" | tee $O/ring_${TAG}.txt
-SD_BLK_RING=1 timeout 300 python scripts/ring_check.py 28 32 2>&1 | tail -n 25 | tee -a $O/ring_${TAG}.txt
+# diagnostic watchdog first (SD_BLK_DBG=64: a stuck barrier wait ends the launch with a record of where, instead of a trap)
+SD_BLK_RING=1 SD_BLK_DBG=64 timeout 300 python scripts/ring_check.py 2>&1 | tail -n 25 | tee -a $O/ring_${TAG}.txt
+SD_BLK_RING=1 timeout 300 python scripts/ring_check.py 28 32 2>&1 | tail -n 8 | tee -a $O/ring_${TAG}.txt
 SD_BLK_RING=1 SD_BLK_ORDER=2 timeout 300 python scripts/ring_check.py 32 2>&1 | tail -n 3 | tee -a $O/ring_${TAG}.txt
 SD_BLK_RING=1 SD_TEST_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_gpu_apply.py tests/test_gpu_solvers.py -m gpu -x -q 2>&1 | tail -n 3 | tee -a $O/ring_${TAG}.txt
 bash scripts/gpu_blk_ncu2.sh ${TAG} "SD_BLK_RING=0" "SD_BLK_RING=1" "SD_BLK_RING=1 SD_BLK_ORDER=2" "SD_BLK_ORDER=2" "SD_BLK_ORDER=1" \

@@ -280,7 +280,7 @@ static int sd_ctx_init(int device, int rank, int world, const void *id128, sd_ct
     SD_CUDA(cudaMalloc(&c->d_scal, SD_NSCAL * sizeof(double)));
     SD_CUDA(cudaMemset(c->d_scal, 0, SD_NSCAL * sizeof(double)));
     SD_CUDA(cudaMallocHost(&c->h_scal, SD_NSCAL * sizeof(double)));
-    SD_CUDA(cudaMalloc(&c->d_tilectr, sizeof(unsigned long long)));
+    SD_CUDA(cudaMalloc(&c->d_tilectr, 16 * sizeof(unsigned long long)));   // [0] tile counter, [1..6] ring-kernel watchdog record
     if (world > 1) {
         SD_ARG(id128, "id128 is NULL");
         SD_TRY(sd_nccl_load());
@@ -1062,7 +1062,7 @@ static int sd_apply_impl(sd_model *m, sd_vec *out, const sd_vec *psi, SdEpi epi,
         }
         epi.partials = c->d_partials;
         epi.nparts = (unsigned)nkeys;
-        SD_CUDA(cudaMemsetAsync(c->d_tilectr, 0, sizeof(unsigned long long), c->stream));
+        SD_CUDA(cudaMemsetAsync(c->d_tilectr, 0, 16 * sizeof(unsigned long long), c->stream));
         const size_t smem = m->blk.smem[nc - 1];
         const int qfar = m->blk.qfar[nc - 1];
         const bool plain = epi.mode == SD_EPI_PLAIN && epi.red == 0 && !epi.acc && epi.hscale == 1.0;
@@ -1097,6 +1097,15 @@ static int sd_apply_impl(sd_model *m, sd_vec *out, const sd_vec *psi, SdEpi epi,
 #undef SD_LAUNCH_BLK
 #undef SD_LAUNCH_BLK3
         SD_TRY(sd_launch_check(c, "sd_blk_apply_kernel"));
+        if (nc == 1 && m->blk.ring && (P.dbg & 64)) {                 // diagnostic mode of the ring kernel's watchdog
+            unsigned long long rec[8] = {0};
+            SD_CUDA(cudaMemcpyAsync(rec, c->d_tilectr, sizeof(rec), cudaMemcpyDeviceToHost, c->stream));
+            SD_CUDA(cudaStreamSynchronize(c->stream));
+            if (rec[1] != 0)
+                return sd_fail(SD_ERR_CUDA, "ring kernel watchdog: CTA %llu warp %llu stuck at entry %llu (wait tag %llu: 1/2 producer on empty, "
+                               "3/4/5 consumer on full), tile number %llu of the CTA; tiles handed out: %llu of %llu",
+                               rec[2], rec[3], rec[4], rec[5], rec[6], rec[0], (unsigned long long)nkeys);
+        }
         if (slotmask) SD_TRY(sd_finish_reduce(c, (unsigned)nkeys, slotmask, slot_out));
     } else if (m->path == SD_PATH_TILED) {
         SdTileDev &t = m->tile[nc - 1];

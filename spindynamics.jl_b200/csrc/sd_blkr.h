@@ -438,10 +438,14 @@ SD_HD size_t sd_blkr_smem_carve(SdBlkrSmem *s, void *base, int A, int L, uint32_
 }
 
 #if defined(__CUDACC__)
-// mbarrier wait with a watchdog: a protocol error traps (the launch fails with an error the host reports) instead of
-// hanging the GPU.  The clock is read once per 256 failed polls; 2^32 cycles are about two seconds, a thousand times
-// the longest legitimate wait.
-__device__ __forceinline__ void sd_blkr_wait(uint64_t *b, unsigned parity) {
+// mbarrier wait with a watchdog: a protocol error ends the launch instead of hanging the GPU.  The clock is read once
+// per 256 failed polls; 2^32 cycles are about two seconds, a thousand times the longest legitimate wait.  Default: trap
+// (the launch fails with an error the host reports).  Diagnostic mode (SD_BLK_DBG & 64): the first warp to time out
+// records where it was stuck in ctr[2..6] (CTA, warp, entry number, tag of the wait, tile number) and raises the abort
+// flag ctr[1]; every wait loop polls the flag and returns false, every caller returns, the kernel ends normally and
+// the host turns the record into an error message (sd_apply_impl).
+__device__ __forceinline__ bool sd_blkr_wait(uint64_t *b, unsigned parity, unsigned long long *ctr, int diag,
+                                             unsigned tag, unsigned e, unsigned t) {
     const unsigned addr = sd_smem_u32(b);
     long long t0 = 0;
     for (unsigned spins = 1;; ++spins) {
@@ -452,11 +456,19 @@ __device__ __forceinline__ void sd_blkr_wait(uint64_t *b, unsigned parity) {
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
             "selp.u32 %0, 1, 0, p;\n"
             "}" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-        if (ok) return;
+        if (ok) return true;
         if ((spins & 255u) == 0u) {
+            if (diag && *(volatile unsigned long long *)(ctr + 1) != 0ULL) return false;
             const long long now = clock64();
             if (t0 == 0) t0 = now;
-            else if (now - t0 > (1LL << 32)) __trap();
+            else if (now - t0 > (1LL << 32)) {
+                if (!diag) __trap();
+                if (atomicCAS(ctr + 1, 0ULL, 1ULL) == 0ULL) {
+                    ctr[2] = blockIdx.x; ctr[3] = threadIdx.x >> 5; ctr[4] = e; ctr[5] = tag; ctr[6] = t;
+                    __threadfence();
+                }
+                return false;
+            }
         }
     }
 }
@@ -500,6 +512,7 @@ sd_blkr_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constan
     }
     __syncthreads();
     const bool nostream = (P.dbg & 1) != 0;
+    const int diag = P.dbg & 64;
 
     if (warp == SD_BLK_CWARPS) {
         // ================= producer warp: tile keys, headers, TMA of neighbour tiles and own tiles into the ring
@@ -520,7 +533,7 @@ sd_blkr_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constan
                 const int js = P.k - __popcll(Pb);
                 if (js >= 0 && js <= SD_BLK_B) break;
             }
-            sd_blkr_wait(&S.empty[e & (NB - 1)], ((e / NB) & 1u) ^ 1u);   // first entry of the tile: see the protocol above
+            if (!sd_blkr_wait(&S.empty[e & (NB - 1)], ((e / NB) & 1u) ^ 1u, tile_ctr, diag, 1u, e, t)) return;   // first entry of the tile: see the protocol above
             SdBlkrHdr &H = S.hdr[t & (NB - 1)];
             if (key >= P.key_hi) {
                 if (lane == 0) H.valid = -1;
@@ -534,7 +547,7 @@ sd_blkr_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constan
             const double *own_src = psi.base[P.shards.rank] + H.base;
             for (int n = 0; n <= ntot; ++n, ++e) {
                 const unsigned slot = e & (NB - 1);
-                if (n > 0) sd_blkr_wait(&S.empty[slot], ((e / NB) & 1u) ^ 1u);
+                if (n > 0 && !sd_blkr_wait(&S.empty[slot], ((e / NB) & 1u) ^ 1u, tile_ctr, diag, 2u, e, t)) return;
                 char *dst = (char *)(S.ring + (size_t)slot * P.cap);
                 // the lane's copies of this entry (sd_blkr_copy); the transaction count is their byte total
                 uint32_t tot = 0;
@@ -568,7 +581,7 @@ sd_blkr_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constan
         const int slotmask = PLAIN ? 0 : sd_epi_slotmask(epi.red);
         unsigned e = 0;
         for (unsigned t = 0;; ++t) {
-            sd_blkr_wait(&S.full[e & (NB - 1)], (e / NB) & 1u);
+            if (!sd_blkr_wait(&S.full[e & (NB - 1)], (e / NB) & 1u, tile_ctr, diag, 3u, e, t)) return;
             SdBlkrHdr &H = S.hdr[t & (NB - 1)];
             if (H.valid < 0) break;
             SdBlkrLane Ln;
@@ -576,13 +589,13 @@ sd_blkr_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constan
             const int ntot = nostream ? 0 : H.ntot;
             for (int n = 0; n < ntot; ++n, ++e) {
                 const unsigned slot = e & (NB - 1);
-                if (n > 0) sd_blkr_wait(&S.full[slot], (e / NB) & 1u);
+                if (n > 0 && !sd_blkr_wait(&S.full[slot], (e / NB) & 1u, tile_ctr, diag, 4u, e, t)) return;
                 sd_blkr_stream(Ln, S.js, H, S.ring + (size_t)slot * P.cap, n);
                 __syncwarp();
                 if (lane == 0) sd_mbar_arrive(&S.empty[slot]);
             }
             const unsigned slot = e & (NB - 1);
-            if (ntot > 0) sd_blkr_wait(&S.full[slot], (e / NB) & 1u);
+            if (ntot > 0 && !sd_blkr_wait(&S.full[slot], (e / NB) & 1u, tile_ctr, diag, 5u, e, t)) return;
             double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
             sd_blkr_own<PLAIN>(Ln, X, H, S.ring + (size_t)slot * P.cap, red);
             if (!PLAIN && slotmask) {
