@@ -181,3 +181,14 @@ static inline void sd_tile_shard_bounds(const SdTileHost &o, int world, uint64_t
         if (keys) keys[g] = key;
     }
 }
+
+// The same with given cut positions: cum[g] = basis rank at which shard g starts (cum[0] = 0, cum[world] = N,
+// non-decreasing); every cut is moved down to the base of the tile that holds it.
+static inline void sd_tile_shard_bounds_at(const SdTileHost &o, int world, const uint64_t *cum, uint64_t *bounds, uint64_t *keys) {
+    for (int g = 0; g <= world; ++g) {
+        uint64_t base = 0;
+        const uint64_t key = sd_tile_key_of_rank(o, cum[g], &base);
+        bounds[g] = base;
+        if (keys) keys[g] = key;
+    }
+}

@@ -15,6 +15,7 @@
 #include "../../spindynamics.jl_b200/csrc/sd_tile_host.h"
 #include "../../spindynamics.jl_b200/csrc/sd_blk_host.h"
 #include "../../spindynamics.jl_b200/csrc/sd_blkr_host.h"
+#include "../../spindynamics.jl_b200/csrc/sd_halo_host.h"
 
 namespace {
 
@@ -304,6 +305,75 @@ int emul_blkr_plan(int L, int k, uint64_t *smem_bytes, uint32_t *slots_total, ui
             if (n > slots_max[js]) slots_max[js] = n;
         }
     }
+    return 0;
+}
+
+// Halo-mirror plan of rank `rank` (sd_halo_host.h) at any size, checked: every remote partner tile of every tile header
+// of chunk j lies inside the segments of chunks 0..j; segments are disjoint, inside their peer's shard and tile aligned
+// (multiples of 16 elements).  stats: [0] segments, [1] remote stored elements, [2] local stored elements, [3] peers used,
+// [4] largest number of segments in one chunk.  Returns 0, -1 (model), -2 (plan failed), -3 (coverage), -4 (segment shape).
+int emul_halo_plan(int L, int k, int world, int rank, int nchunks, uint64_t *stats) {
+    SdBlkHost bh;
+    std::vector<double> J(L, 0.5), Jz(L, 1.0), h(L, 0.0);
+    if (!sd_blk_build(L, k, J.data(), Jz.data(), h.data(), bh)) return -1;
+    SdTileHost th;
+    if (!sd_tile_build(L, k, SD_BLK_B, 5, J.data(), Jz.data(), h.data(), th)) return -1;
+    uint64_t bounds[SD_MAX_WORLD + 1], keys[SD_MAX_WORLD + 1];
+    sd_tile_shard_bounds(th, world, bounds, keys);
+    SdBlkParams P = bh.P;
+    P.W = bh.W.data(); P.js = bh.js.data(); P.units = bh.units.data(); P.items = bh.items.data(); P.dmid = bh.dmid.data();
+    P.key_lo = keys[rank]; P.key_hi = keys[rank + 1];
+    P.shards.world = world; P.shards.rank = rank;
+    for (int g = 0; g <= SD_MAX_WORLD; ++g) P.shards.pstart[g] = sd_blk_key_base(bh, keys[g < world ? g : world]);
+    const int qfar = sd_tile_qfar(L, P.A, bh.binom.data(), (uint64_t)100 << 20, 8);
+    SdHaloPlan plan;
+    if (!sd_halo_plan(bh, P, nchunks, qfar, plan)) return -2;
+    if ((int)plan.chunk_key.size() != nchunks + 1 || plan.chunk_key.front() != P.key_lo || plan.chunk_key.back() != P.key_hi) return -2;
+    std::vector<std::pair<uint64_t, uint64_t>> have[SD_MAX_WORLD];
+    uint64_t nseg = 0, maxseg = 0, total = 0;
+    for (int j = 0; j < nchunks; ++j) {
+        if (plan.chunk_key[j] > plan.chunk_key[j + 1]) return -2;
+        maxseg = std::max<uint64_t>(maxseg, plan.segs[j].size());
+        for (const SdHaloSeg &s : plan.segs[j]) {
+            if (s.peer == rank || s.peer < 0 || s.peer >= world || s.lo >= s.hi || (s.lo & 15u) || (s.hi & 15u)) return -4;
+            if (s.lo < P.shards.pstart[s.peer] || s.hi > P.shards.pstart[s.peer + 1]) return -4;
+            for (auto [lo, hi] : have[s.peer]) if (s.lo < hi && lo < s.hi) return -4;             // disjoint from everything before
+            have[s.peer].push_back({s.lo, s.hi});
+            ++nseg; total += s.hi - s.lo;
+        }
+        for (int g = 0; g < world; ++g) sd_halo_merge(have[g]);
+        std::vector<SdHaloSeg> raw;
+        for (uint64_t key = plan.chunk_key[j]; key < plan.chunk_key[j + 1]; ++key) sd_halo_tile_remotes(bh, P, key, qfar, raw);
+        for (const SdHaloSeg &r : raw) {
+            bool ok = false;
+            for (auto [lo, hi] : have[r.peer]) if (lo <= r.lo && r.hi <= hi) { ok = true; break; }
+            if (!ok) return -3;
+        }
+    }
+    if (total != plan.remote_elems) return -4;
+    uint64_t peers = 0;
+    for (int g = 0; g < world; ++g) {
+        if (have[g] != plan.need[g]) return -4;
+        if (!have[g].empty()) ++peers;
+    }
+    stats[0] = nseg; stats[1] = total; stats[2] = P.shards.pstart[rank + 1] - P.shards.pstart[rank]; stats[3] = peers; stats[4] = maxseg;
+    return 0;
+}
+
+// Remote-volume-weighted shard bounds (sd_halo_balance): bounds / keys [world + 1], cost[2] (largest per-rank time with
+// equal shards / with the returned bounds, in local-element units), per_rank[world] times at the returned bounds.
+int emul_halo_balance(int L, int k, int world, double remote_cost, int iters, uint64_t *bounds, uint64_t *keys, double *cost, double *per_rank) {
+    SdBlkHost bh;
+    std::vector<double> J(L, 0.5), Jz(L, 1.0), h(L, 0.0);
+    if (!sd_blk_build(L, k, J.data(), Jz.data(), h.data(), bh)) return -1;
+    SdTileHost th;
+    if (!sd_tile_build(L, k, SD_BLK_B, 5, J.data(), Jz.data(), h.data(), th)) return -1;
+    const int qfar = sd_tile_qfar(L, bh.P.A, bh.binom.data(), (uint64_t)100 << 20, 8);
+    if (!sd_halo_balance(bh, th, world, qfar, remote_cost, iters, bounds, keys, cost)) return -2;
+    double tmax = 0.0;
+    std::vector<double> t;
+    if (!sd_halo_rank_cost(bh, keys, world, qfar, remote_cost, &tmax, &t)) return -2;
+    for (int g = 0; g < world; ++g) per_rank[g] = t[g];
     return 0;
 }
 

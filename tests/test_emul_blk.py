@@ -351,3 +351,47 @@ def test_ring_kernel_plan_at_full_sizes(L, k):
         want = sum(-(-math.comb(10, js - jt) // 32) * ((math.comb(5, jt) + 1) // 2) for jt in range(6) if lo <= js - jt <= hi)
         assert int(tot[js]) == want
     assert int(tot[7]) == 114 and int(tot[8]) == 114 and int(mx[7]) == 8 and int(mx[8]) == 8
+
+
+@pytest.mark.parametrize("L,k,world,chunks", [(20, 10, 2, 4), (22, 11, 3, 5), (24, 12, 4, 8), (26, 9, 8, 3), (28, 14, 8, 8), (32, 16, 8, 8),
+                                              (32, 16, 2, 8), (36, 18, 8, 16)])
+def test_halo_mirror_plan(L, k, world, chunks):
+    """sd_halo_host.h (SD_HALO=1): for every rank, the peer ranges the copy engines bring in for chunk j cover every
+    remote partner tile the tile headers of chunks 0..j point at (same header code as the kernel), segments are
+    disjoint, tile aligned and inside their peer's shard; a handful of large segments per rank.  At half filling the
+    busiest rank pulls 0.5 shards at 2 ranks, 1.5 at 4 and 2.5 at 8 (the ranks whose top prefix bits are 101 / 010 have
+    both top bonds active plus half of the third), the average over ranks is about 0.5 / 1.0 / 1.5."""
+    lib = load()
+    lib.emul_halo_plan.argtypes = [ctypes.c_int] * 5 + [vp]
+    ratios = []
+    for rank in (range(world) if L <= 28 else sorted({0, world // 2, world - 1})):
+        st = np.zeros(8, dtype=np.uint64)
+        assert lib.emul_halo_plan(L, k, world, rank, chunks, P(st)) == 0, rank
+        nseg, remote, local, peers, maxseg = (int(x) for x in st[:5])
+        assert local > 0 and 1 <= peers <= world - 1 and nseg <= 8 * chunks and maxseg <= 12
+        ratios.append(remote / local)
+    if 2 * k == L and world in (2, 4, 8) and L <= 28:
+        want_max, want_avg = {2: (0.5, 0.5), 4: (1.5, 1.0), 8: (2.5, 1.5)}[world]
+        assert abs(max(ratios) - want_max) < 0.1 and abs(np.mean(ratios) - want_avg) < 0.1
+
+
+@pytest.mark.parametrize("L,k,world", [(24, 12, 8), (28, 14, 8), (28, 14, 4), (26, 10, 8)])
+def test_remote_weighted_shard_bounds(L, k, world):
+    """sd_halo_balance (SD_SHARD_BALANCE=1): cut positions weighted by remote volume.  Bounds stay tile aligned and
+    monotone, no rank gets slower than the slowest rank of the equal split, and at 8 ranks of a half-filled chain the
+    largest per-rank time max(local, 0.7 * remote) drops by about a third (1.77 -> 1.19 shares: the 101 / 010 ranks
+    get half-size shards)."""
+    lib = load()
+    lib.emul_halo_balance.argtypes = [ctypes.c_int] * 3 + [ctypes.c_double, ctypes.c_int, vp, vp, vp, vp]
+    b, kk = np.zeros(world + 1, dtype=np.uint64), np.zeros(world + 1, dtype=np.uint64)
+    cost, per = np.zeros(2), np.zeros(world)
+    assert lib.emul_halo_balance(L, k, world, 0.7, 8, P(b), P(kk), P(cost), P(per)) == 0
+    N = math.comb(L, k)
+    bb, kb = b.astype(object), kk.astype(object)
+    assert bb[0] == 0 and bb[-1] == N and all(bb[g] < bb[g + 1] and kb[g] < kb[g + 1] for g in range(world))
+    assert cost[1] <= cost[0] * (1 + 1e-12) and abs(per.max() - cost[1]) <= 1e-9 * cost[1]
+    share = N / world
+    if 2 * k == L and world == 8:
+        assert 1.7 < cost[0] / share < 1.85 and cost[1] / share < 1.3
+        sizes = np.diff(b.astype(np.float64)) / share
+        assert sizes[2] < 0.7 and sizes[5] < 0.7 and sizes[0] > 1.05
