@@ -184,9 +184,16 @@ int emul_blk_apply(int L, int k, const double *Jhop, const double *Jz, const dou
     if (!sd_tile_build(L, k, SD_BLK_B, 5, Jhop, Jz, h, th)) return -1;
     uint64_t bounds[SD_MAX_WORLD + 1], keys[SD_MAX_WORLD + 1];
     sd_tile_shard_bounds(th, world, bounds, keys);
+    if (variant & 512) {
+        double cost[2];
+        if (!sd_halo_balance(bh, th, world, sd_tile_qfar(L, bh.P.A, bh.binom.data(), far_bytes, 8 * NC), 0.7, 5, bounds, keys, cost)) return -9;
+    }
     SdBlkParams P = bh.P;
     P.W = bh.W.data(); P.js = bh.js.data(); P.units = bh.units.data(); P.items = bh.items.data(); P.dmid = bh.dmid.data();
     P.nbuf = 3; P.dbg = 0;
+    const bool halo = (variant & 256) != 0;                          // + 256: through the halo mirror (sd_halo_host.h), 3 chunks
+    const bool balance = (variant & 512) != 0;                       // + 512: remote-volume-weighted shard bounds (sd_halo_balance)
+    variant &= 255;
     if (variant == 3) { variant = 2; P.dbg = 16; }                   // ring kernel copying the whole crossing partner tile
     P.key_lo = keys[rank]; P.key_hi = keys[rank + 1];
     P.shards.world = world; P.shards.rank = rank;
@@ -239,12 +246,36 @@ int emul_blk_apply(int L, int k, const double *Jhop, const double *Jz, const dou
     const bool plain = epi.mode == SD_EPI_PLAIN && epi.red == 0 && !epi.acc && epi.hscale == 1.0;
 #define RUN(NC_, PLAIN_) do { if (variant == 1) run_tiles<NC_, PLAIN_, 1>(bh, P, view, o.p, epi, qfar, red); \
                               else run_tiles<NC_, PLAIN_, 0>(bh, P, view, o.p, epi, qfar, red); } while (0)
-    if (variant == 2) {                                             // ring kernel: f64 only
-        if (NC != 1) return -1;
-        const int rc = plain ? run_tiles_ring<true>(bh, P, view, o.p, epi, qfar, red) : run_tiles_ring<false>(bh, P, view, o.p, epi, qfar, red);
-        if (rc != 0) return rc;
-    } else if (NC == 1) { if (plain) RUN(1, true); else RUN(1, false); }
-    else { if (plain) RUN(2, true); else RUN(2, false); }
+    // halo mirror: the peers' shards are replaced by NaN-filled mirrors that only hold what the plan copies, chunk by
+    // chunk, before the tiles of that chunk run (what sd_apply_blk_halo does with the copy engines and one event per chunk)
+    SdHaloPlan plan;
+    std::vector<AlignedBuf> mirror(world);
+    int nchunks = 1;
+    if (halo && world > 1) {
+        nchunks = 3;
+        if (!sd_halo_plan(bh, P, nchunks, qfar, plan)) return -9;
+        for (int g = 0; g < world; ++g) {
+            if (g == rank) continue;
+            mirror[g].alloc((size_t)(pstart[g + 1] - pstart[g]) * NC, NAN);
+            view.base[g] = mirror[g].p - (int64_t)pstart[g] * NC;
+        }
+    }
+    const uint64_t klo_all = P.key_lo, khi_all = P.key_hi;
+    for (int j = 0; j < nchunks; ++j) {
+        if (halo && world > 1) {
+            for (const SdHaloSeg &sg : plan.segs[j])
+                std::memcpy(mirror[sg.peer].p + (sg.lo - pstart[sg.peer]) * NC, s_psi[sg.peer].p + (sg.lo - pstart[sg.peer]) * NC,
+                            (size_t)(sg.hi - sg.lo) * NC * sizeof(double));
+            P.key_lo = plan.chunk_key[j]; P.key_hi = plan.chunk_key[j + 1];
+        }
+        if (variant == 2) {                                         // ring kernel: f64 only
+            if (NC != 1) return -1;
+            const int rc = plain ? run_tiles_ring<true>(bh, P, view, o.p, epi, qfar, red) : run_tiles_ring<false>(bh, P, view, o.p, epi, qfar, red);
+            if (rc != 0) return rc;
+        } else if (NC == 1) { if (plain) RUN(1, true); else RUN(1, false); }
+        else { if (plain) RUN(2, true); else RUN(2, false); }
+    }
+    P.key_lo = klo_all; P.key_hi = khi_all;
 #undef RUN
     if (red_out) for (int s = 0; s < SD_NSLOT; ++s) red_out[s] = red[s];
     // ---- back to rank order; padding must still be zero

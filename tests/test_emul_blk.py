@@ -73,7 +73,7 @@ def oracle_apply(m, psi, NC):
 def run(lib, L, k, NC, world, states, psi, Jhop, Jz, h, mode=0, red=0, hscale=1.0, a=1.0, b=0.0,
         vprev=None, phi=None, acc=None, ck=0j, far_bytes=1 << 20, variant=None):
     variant = VARIANT if variant is None else variant
-    if variant >= 2 and NC == 2:
+    if (variant & 255) >= 2 and NC == 2:
         pytest.skip("the ring kernel is f64 only")
     N = len(states)
     out = np.full(N * NC, np.nan)
@@ -395,3 +395,31 @@ def test_remote_weighted_shard_bounds(L, k, world):
         assert 1.7 < cost[0] / share < 1.85 and cost[1] / share < 1.3
         sizes = np.diff(b.astype(np.float64)) / share
         assert sizes[2] < 0.7 and sizes[5] < 0.7 and sizes[0] > 1.05
+
+
+@pytest.mark.parametrize("variant", [256 + 0, 256 + 2, 256 + 512 + 0, 256 + 512 + 2, 512 + 1], ids=["halo", "halo_ring", "halo_bal", "halo_bal_ring", "bal_body1"])
+@pytest.mark.parametrize("L,k,world", [(18, 9, 2), (20, 10, 4), (20, 10, 8), (22, 11, 8), (20, 6, 5)])
+def test_sharded_apply_through_the_halo_mirror(variant, L, k, world):
+    """SD_HALO=1 / SD_SHARD_BALANCE=1 end to end on the CPU: every rank runs the emulated kernel on NaN-filled mirrors of
+    its peers' shards that hold only what the halo plan copies, chunk by chunk, before that chunk's tiles run -- a partner
+    tile the plan missed would put NaN into the result -- with equal and with remote-weighted shard bounds, including the
+    fused epilogue with all reductions."""
+    lib = load()
+    rng = np.random.default_rng(L + world)
+    Jhop, Jz, h = model_lists(L, rng)
+    m = oracle_model(L, k, Jhop, Jz, h)
+    states = np.ascontiguousarray(m.states, dtype=np.uint64)
+    N = len(states)
+    for NC in ((1,) if (variant & 255) >= 2 else (1, 2)):
+        psi, vprev, phi = (rng.standard_normal(N * NC) for _ in range(3))
+        ref = oracle_apply(m, psi, NC)
+        out, _, bounds, _ = run(lib, L, k, NC, world, states, psi, Jhop, Jz, h, variant=variant)
+        assert np.linalg.norm(out - ref) <= 1e-14 * np.linalg.norm(ref)
+        assert bounds[0] == 0 and bounds[-1] == N and np.all(np.diff(bounds.astype(np.int64)) >= 0)
+        a, b = 2.5, 0.3
+        nxt = 2.0 * ((ref - b * psi) / a) - vprev
+        out, red, _, _ = run(lib, L, k, NC, world, states, psi, Jhop, Jz, h, mode=2, red=7, a=a, b=b, vprev=vprev, phi=phi, variant=variant)
+        cplx = (lambda x: x.view(np.complex128)) if NC == 2 else (lambda x: x)
+        assert np.linalg.norm(out - nxt) <= 1e-14 * np.linalg.norm(nxt)
+        assert abs(complex(red[0], red[1]) - np.vdot(cplx(psi), cplx(nxt))) < 1e-9
+        assert abs(red[2] - np.vdot(cplx(phi), cplx(nxt)).real) < 1e-9 and abs(red[3] - nxt @ nxt) < 1e-8
