@@ -622,6 +622,10 @@ int sd_model_create(sd_ctx *ctx, int L, int nup, const sd_bond *hop, int nhop, c
     if (m->tile_capable && sd_env_int("SD_BLK", 1)) {
         SD_TRY(sd_blk_setup(m));
         if (m->blk.ok) m->path = SD_PATH_BLOCK;
+        // A chain of L = 16 .. 21 has 2 .. 64 tiles, i.e. that many CTAs on 148 SMs; below SD_BLK_MIN_TILES prefixes the
+        // model starts on the one-thread-per-state kernel instead (0 = off, the measured default; round-2 A/B).
+        const int min_tiles = sd_env_int("SD_BLK_MIN_TILES", 0);
+        if (m->blk.ok && min_tiles > 0 && (1ULL << m->blk.host.P.A) < (uint64_t)min_tiles) m->path = SD_PATH_GENERIC;
     }
     // shards: tile-aligned to the coarser (F64) tiling when tiled, plain equal split otherwise
     uint64_t bounds[SD_MAX_WORLD + 1];
