@@ -12,6 +12,8 @@ nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > $
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -n 5 | tee $O/pytest_${TAG}.txt
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -n 2 | tee $O/smoke_${TAG}.txt
 timeout 300 python bench.py > $O/bench_${TAG}.log 2>&1; tail -n 1 $O/bench_${TAG}.log
+# L2 -> SM throughput of this GPU (DESIGN 4.1a argues from ~6300 B/clk = 12.2 TB/s; measure it)
+nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o scripts/mb_l2cap scripts/mb_l2cap.cu 2> /dev/null && timeout 120 scripts/mb_l2cap 2>&1 | tee $O/l2cap_${TAG}.txt | tail -n 12
 echo "== ring kernel parity" | tee $O/ring_${TAG}.txt
 # diagnostic watchdog first (SD_BLK_DBG=64: a stuck barrier wait ends the launch with a record of where, instead of a trap)
 SD_BLK_RING=1 SD_BLK_DBG=64 timeout 300 python scripts/ring_check.py 2>&1 | tail -n 25 | tee -a $O/ring_${TAG}.txt
