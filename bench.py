@@ -180,6 +180,9 @@ def main():
     ap.add_argument("--cpu-L", type=int, default=28, help="chain length of the CPU baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-solve", action="store_true", help="skip the end-to-end Lanczos solve leg")
+    ap.add_argument("--solve-m", type=int, default=30)
+    ap.add_argument("--solve-multi", action="store_true", help="run the solve leg on N > 1 ranks too (off until verified on a GPU box)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--path", default=None, choices=[None, "block", "tiled", "generic"])
     args = ap.parse_args()
@@ -281,6 +284,26 @@ def main():
     else:
         checksum = None
 
+    # end-to-end solve on the same model (north star: "end-to-end solve time"): 30 steps of the memory-lean Lanczos
+    # ground state (three work vectors; the reference's N x m basis does not fit one GPU beyond m = 33 at L = 32),
+    # after everything the contract needs has been measured; a failure here is recorded, not fatal
+    solve = None
+    if not args.no_solve and not args.no_e2e and args.dtype == "f64" and (world == 1 or args.solve_multi):
+        try:
+            hin = hout = None
+            psi.fill_seeded(SEED + 1, 1.0)
+            barrier()
+            t0 = time.perf_counter()
+            E0, gs = sd.lanczos_groundstate_lean(sd.apply_H_, model, lanc_m=args.solve_m, v0=psi, device=True)
+            barrier()
+            wall = time.perf_counter() - t0
+            solve = {"what": f"lanczos_groundstate_lean lanc_m={args.solve_m} (2 x {args.solve_m} H.psi + BLAS-1, device-resident, "
+                             f"3 work vectors), seeded start vector", "ms": wall * 1e3, "E_ritz": float(E0),
+                     "ritz_norm": float(gs.norm())}
+            del gs
+        except Exception as exc:                                   # noqa: BLE001
+            solve = {"error": repr(exc)[:300]}
+
     if rank == 0:
         peak, peak_src = measured_peak()
         alg_bytes = 2 * esz * N                              # read psi once + write out once
@@ -315,7 +338,7 @@ def main():
                            "kernel_path": model.info["kernel_path"], "tile_sites": model.info["tile_sites"],
                            **({"env_knobs": knobs} if knobs else {})},
                 "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-                "cpu_baseline": cpu, "checksum": checksum}
+                "cpu_baseline": cpu, "checksum": checksum, "solve": solve}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
