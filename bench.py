@@ -327,7 +327,7 @@ def main():
         achieved = alg_bytes / world / (ms_step * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        knobs = {k: v for k, v in os.environ.items() if k.startswith("SD_BLK") or k in ("SD_FAR_MB", "SD_FORCE_GENERIC")}
+        knobs = {k: v for k, v in os.environ.items() if k.startswith(("SD_BLK", "SD_HALO", "SD_SHARD")) or k in ("SD_FAR_MB", "SD_FORCE_GENERIC")}
         kname = {"block": "sd_blk_apply_kernel", "tiled": "sd_tile_apply_kernel"}.get(model.info["kernel_path"], "sd_generic_apply_kernel")
         if kname == "sd_blk_apply_kernel" and args.dtype == "f64" and knobs.get("SD_BLK_RING", "0") not in ("0", ""):
             kname = "sd_blkr_apply_kernel"                   # experimental ring variant (sd_blkr.h)
