@@ -21,4 +21,4 @@ SD_BLK_RING=1 timeout 300 python scripts/ring_check.py 28 32 2>&1 | tail -n 8 | 
 SD_BLK_RING=1 SD_BLK_ORDER=2 timeout 300 python scripts/ring_check.py 32 2>&1 | tail -n 3 | tee -a $O/ring_${TAG}.txt
 SD_BLK_RING=1 SD_TEST_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_gpu_apply.py tests/test_gpu_solvers.py -m gpu -x -q 2>&1 | tail -n 3 | tee -a $O/ring_${TAG}.txt
 bash scripts/gpu_blk_ncu2.sh ${TAG} "SD_BLK_RING=0" "SD_BLK_RING=1" "SD_BLK_RING=1 SD_BLK_ORDER=2" "SD_BLK_ORDER=2" "SD_BLK_ORDER=1" \
-     "SD_BLK_VARIANT=1" "SD_BLK_ORDER=2 SD_BLK_VARIANT=1" "SD_BLK_RING=1 SD_BLK_DBG=1" "SD_BLK_RING=1 SD_BLK_DBG=3" "SD_BLK_RING=1 SD_BLK_ORDER=2 SD_BLK_ORDER_E=14" "SD_BLK_RING=1 SD_BLK_DBG=16" "SD_BLK_RING=1 SD_BLK_DBG=32"
+     "SD_BLK_VARIANT=1" "SD_BLK_ORDER=2 SD_BLK_VARIANT=1" "SD_BLK_RING=1 SD_BLK_DBG=1" "SD_BLK_RING=1 SD_BLK_DBG=3" "SD_BLK_RING=1 SD_BLK_ORDER=2 SD_BLK_ORDER_E=14" "SD_BLK_RING=1 SD_BLK_DBG=16" "SD_BLK_RING=1 SD_BLK_DBG=32" "SD_BLK_RING=1 SD_BLKR_DIRECT=2" "SD_BLK_RING=1 SD_BLKR_DIRECT=4" "SD_BLK_RING=1 SD_BLKR_DIRECT=4 SD_BLK_ORDER=2"

@@ -198,6 +198,7 @@ struct SdBlkDev {
     } halo;
     bool ring = false;              // f64 applies run sd_blkr_apply_kernel (SD_BLK_RING=1; sd_blkr.h)
     SdBlkrWarp *d_rw = nullptr;     // [(B+1)*15] item -> consumer warp packing of the ring kernel
+    int ring_direct = 0;            // nearest prefix entries per tile read straight from L2 by the consumers (SD_BLKR_DIRECT)
     size_t ring_smem = 0;
 };
 
@@ -507,6 +508,7 @@ static int sd_blk_setup(sd_model *m) {
         if (sd_blkr_build(b.host, rw) && b.ring_smem <= 227 * 1024) {
             SD_TRY(sd_to_device(&b.d_rw, rw));
             b.ring = true;
+            b.ring_direct = std::max(0, std::min(SD_BLK_MAXA, sd_env_int("SD_BLKR_DIRECT", 0)));
         }
     }
     SD_TRY(sd_to_device(&b.d_W, b.host.W));
@@ -1207,10 +1209,10 @@ static int sd_blk_launch_range(sd_model *m, int nc, const SdBlkParams &P, const 
         const size_t rsmem = m->blk.ring_smem;
         if (plain) {
             SD_CUDA(cudaFuncSetAttribute(sd_blkr_apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
-            sd_blkr_apply_kernel<true><<<grid, SD_BLK_THREADS, rsmem, c->stream>>>(P, view, out_local, epi, qfar, c->d_tilectr, m->blk.d_rw);
+            sd_blkr_apply_kernel<true><<<grid, SD_BLK_THREADS, rsmem, c->stream>>>(P, view, out_local, epi, qfar, c->d_tilectr, m->blk.d_rw, m->blk.ring_direct);
         } else {
             SD_CUDA(cudaFuncSetAttribute(sd_blkr_apply_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
-            sd_blkr_apply_kernel<false><<<grid, SD_BLK_THREADS, rsmem, c->stream>>>(P, view, out_local, epi, qfar, c->d_tilectr, m->blk.d_rw);
+            sd_blkr_apply_kernel<false><<<grid, SD_BLK_THREADS, rsmem, c->stream>>>(P, view, out_local, epi, qfar, c->d_tilectr, m->blk.d_rw, m->blk.ring_direct);
         }
         return sd_launch_check(c, "sd_blkr_apply_kernel");
     }
@@ -1332,7 +1334,7 @@ static int sd_apply_impl(sd_model *m, sd_vec *out, const sd_vec *psi, SdEpi epi,
             SD_CUDA(cudaFuncSetAttribute(sd_blkr_apply_kernel<PLAIN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem)); \
             set_smem = rsmem;                                                                                \
         }                                                                                                    \
-        sd_blkr_apply_kernel<PLAIN_><<<grid, SD_BLK_THREADS, rsmem, c->stream>>>(P, psi->view, out->d, epi, qfar, c->d_tilectr, m->blk.d_rw); \
+        sd_blkr_apply_kernel<PLAIN_><<<grid, SD_BLK_THREADS, rsmem, c->stream>>>(P, psi->view, out->d, epi, qfar, c->d_tilectr, m->blk.d_rw, m->blk.ring_direct); \
     } while (0)
         if (nc == 1 && m->blk.ring) { if (plain) SD_LAUNCH_RING(true); else SD_LAUNCH_RING(false); }
         else if (nc == 1) { if (plain) SD_LAUNCH_BLK(1, true); else SD_LAUNCH_BLK(1, false); }

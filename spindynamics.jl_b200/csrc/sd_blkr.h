@@ -154,6 +154,42 @@ SD_HD void sd_blkr_stream(SdBlkrLane &S, const SdBlkJs *jstab, const SdBlkrHdr &
 #undef SD_BLKR_CROSS
 }
 
+// The same for a partner tile read straight from global memory / L2 (no ring slot): the `ndirect` nearest prefix
+// entries of a tile (the last ones of the far-first list, most likely L2 hits) can bypass shared memory, which takes
+// their bytes off the shared-memory port (TMA write + LDS) at the price of global-load latency in the consumer warps
+// once per tile, while the ring entries of the tile are already in flight (SD_BLKR_DIRECT, unmeasured).
+template <int O, int EC, bool HALF>
+SD_HD void sd_blkr_axpy_g(SdBlkrLane &S, const double *g, uint32_t base, uint32_t ss, uint32_t u, double J) {
+    double2 t[EC];
+#pragma unroll
+    for (int s = 0; s < EC; ++s) {
+        if (HALF && s == EC - 1) t[s] = sd_blk_ldg_half(g + base + s * ss - u);
+        else t[s] = sd_blk_ldg(g + base + s * ss);
+    }
+#pragma unroll
+    for (int s = 0; s < EC; ++s) {
+        S.acc[O + s].x += J * t[s].x;
+        if (!(HALF && s == EC - 1)) S.acc[O + s].y += J * t[s].y;
+    }
+}
+SD_HD void sd_blkr_stream_direct(SdBlkrLane &S, const SdBlkrHdr &H, int n) {
+    const double J = H.nb_J[n];
+    const double *g = H.nb_ptr[n];
+    if (S.ecA == 5) sd_blkr_axpy_g<0, 5, false>(S, g, S.baseA, S.ssA, S.uA, J);
+    else if (S.ecA == 3) sd_blkr_axpy_g<0, 3, true>(S, g, S.baseA, S.ssA, S.uA, J);
+    else if (S.ecA == 1) sd_blkr_axpy_g<0, 1, true>(S, g, S.baseA, S.ssA, S.uA, J);
+    if (S.ecB0 == 3) sd_blkr_axpy_g<5, 3, true>(S, g, S.baseB[0], S.ssB, S.uB[0], J);
+    else if (S.ecB0 == 1) sd_blkr_axpy_g<5, 1, true>(S, g, S.baseB[0], 0u, S.uB[0], J);
+    if (S.jtB[1] >= 0) sd_blkr_axpy_g<6, 1, true>(S, g, S.baseB[1], 0u, S.uB[1], J);
+    if (S.jtB[2] >= 0) sd_blkr_axpy_g<7, 1, true>(S, g, S.baseB[2], 0u, S.uB[2], J);
+}
+// ring entries of a tile: prefix entries [0, nring), then the crossing entry (if any), then the tile itself;
+// prefix entries [nring, nnb) are read directly by the consumers
+SD_HD int sd_blkr_nring(const SdBlkrHdr &H, int ndirect) {
+    const int nd = ndirect < H.nnb ? ndirect : H.nnb;
+    return H.nnb - (nd > 0 ? nd : 0);
+}
+
 // ---- own tile.  Everything that depends on the class JT (tail popcount) is resolved at compile time: the tail
 // configurations of the class, which of them hop where inside the tail, and which of them cross the mid|tail bond.
 template <int JT, int e, int q>
@@ -383,6 +419,7 @@ SD_HD bool sd_blkr_cross_piece(const SdBlkJs *jstab, int js, int jsx, int bP, in
 #define SD_BLKR_CHUNK 8192u
 SD_HD bool sd_blkr_copy(const SdBlkJs *jstab, const SdBlkrHdr &H, const double *own_src, int dbg, int n, int ntot,
                         unsigned lane, unsigned i, const char **src, uint32_t *off, uint32_t *len) {
+    // n: index into the header's entry list (n == ntot: the tile itself); the caller skips the direct entries
     const bool cross = n < ntot && n == H.nnb;
     *src = (const char *)(n == ntot ? own_src : H.nb_ptr[n]);
     if (cross && !(dbg & 16)) {
@@ -488,7 +525,8 @@ __device__ __forceinline__ void sd_bulk_g2s_evict_first(void *dst, const void *s
 template <bool PLAIN>
 __global__ void __launch_bounds__(SD_BLK_THREADS, 1)
 sd_blkr_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constant__ SdVecView psi, double *out_local,
-                     const __grid_constant__ SdEpi epi, int qfar, unsigned long long *tile_ctr, const SdBlkrWarp *rwtab) {
+                     const __grid_constant__ SdEpi epi, int qfar, unsigned long long *tile_ctr, const SdBlkrWarp *rwtab,
+                     int ndirect) {
     extern __shared__ __align__(128) unsigned char sd_blkr_smem[];
     SdBlkrSmem S;
     sd_blkr_smem_carve(&S, sd_blkr_smem, P.A, P.L, P.cap);
@@ -544,10 +582,14 @@ sd_blkr_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constan
             sd_blk_make_hdr<1, SdBlkrHdr>(P, S.W, key, H, psi, qfar, lane);
             __syncwarp();
             const int ntot = nostream ? 0 : H.ntot;
+            const int nring = sd_blkr_nring(H, ndirect), nnb = H.nnb;
             const double *own_src = psi.base[P.shards.rank] + H.base;
-            for (int n = 0; n <= ntot; ++n, ++e) {
+            bool first = true;
+            for (int n = 0; n <= ntot; ++n) {
+                if (n >= nring && n < nnb && n < ntot) continue;    // read directly by the consumers
                 const unsigned slot = e & (NB - 1);
-                if (n > 0 && !sd_blkr_wait(&S.empty[slot], ((e / NB) & 1u) ^ 1u, tile_ctr, diag, 2u, e, t)) return;
+                if (!first && !sd_blkr_wait(&S.empty[slot], ((e / NB) & 1u) ^ 1u, tile_ctr, diag, 2u, e, t)) return;
+                first = false;
                 char *dst = (char *)(S.ring + (size_t)slot * P.cap);
                 // the lane's copies of this entry (sd_blkr_copy); the transaction count is their byte total
                 uint32_t tot = 0;
@@ -568,6 +610,7 @@ sd_blkr_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constan
                     if (evict_first) sd_bulk_g2s_evict_first(dst + off, src + off, len, &S.full[slot]);
                     else sd_bulk_g2s(dst + off, src + off, len, &S.full[slot]);
                 }
+                ++e;
             }
         }
     } else {
@@ -587,15 +630,21 @@ sd_blkr_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constan
             SdBlkrLane Ln;
             sd_blkr_begin(Ln, S.js[H.js], S.rw[H.js * SD_BLK_CWARPS + warp], lane);
             const int ntot = nostream ? 0 : H.ntot;
-            for (int n = 0; n < ntot; ++n, ++e) {
+            const int nring = sd_blkr_nring(H, ndirect), nnb = H.nnb;
+            for (int n = nring; n < nnb && n < ntot; ++n) sd_blkr_stream_direct(Ln, H, n);   // while the ring entries fly
+            bool first = true;
+            for (int n = 0; n < ntot; ++n) {
+                if (n >= nring && n < nnb) continue;
                 const unsigned slot = e & (NB - 1);
-                if (n > 0 && !sd_blkr_wait(&S.full[slot], (e / NB) & 1u, tile_ctr, diag, 4u, e, t)) return;
+                if (!first && !sd_blkr_wait(&S.full[slot], (e / NB) & 1u, tile_ctr, diag, 4u, e, t)) return;
+                first = false;
                 sd_blkr_stream(Ln, S.js, H, S.ring + (size_t)slot * P.cap, n);
                 __syncwarp();
                 if (lane == 0) sd_mbar_arrive(&S.empty[slot]);
+                ++e;
             }
             const unsigned slot = e & (NB - 1);
-            if (ntot > 0 && !sd_blkr_wait(&S.full[slot], (e / NB) & 1u, tile_ctr, diag, 5u, e, t)) return;
+            if (!first && !sd_blkr_wait(&S.full[slot], (e / NB) & 1u, tile_ctr, diag, 5u, e, t)) return;
             double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
             sd_blkr_own<PLAIN>(Ln, X, H, S.ring + (size_t)slot * P.cap, red);
             if (!PLAIN && slotmask) {

@@ -88,7 +88,7 @@ void run_tiles(const SdBlkHost &bh, const SdBlkParams &P, const SdVecView &psi, 
 // in warp order, as the last warp of a tile does.
 template <bool PLAIN>
 int run_tiles_ring(const SdBlkHost &bh, const SdBlkParams &P, const SdVecView &psi, double *out_local, const SdEpi &epi,
-                   int qfar, double *red_total) {
+                   int qfar, double *red_total, int ndirect = 0) {
     std::vector<SdBlkrWarp> rw;
     if (!sd_blkr_build(bh, rw)) return -4;
     if (sd_blkr_smem_carve(nullptr, nullptr, P.A, P.L, P.cap) > 227 * 1024) return -5;
@@ -135,7 +135,9 @@ int run_tiles_ring(const SdBlkHost &bh, const SdBlkParams &P, const SdVecView &p
         for (int q = 0; q < 32; ++q) sd_blk_hdr_fill<1, SdBlkrHdr>(P, lanes[q], Pb, key, base, dpre, actmask, qfar, q, H, psi);
         // ---- the ring entries of this tile, as the producer warp issues them
         const int ntot = H.ntot;
+        const int nring = sd_blkr_nring(H, ndirect);
         for (int n = 0; n <= ntot; ++n) {
+            if (n >= nring && n < H.nnb && n < ntot) { for (size_t i = 0; i < P.cap; ++i) ring[n].p[i] = NAN; continue; }   // no ring slot
             const uint32_t elems = (n < ntot && n == H.nnb) ? bh.js[H.jsx].size_pad : bh.js[H.js].size_pad;
             if (elems > P.cap) return -7;
             for (size_t i = 0; i < P.cap; ++i) ring[n].p[i] = NAN;   // what no copy writes stays NaN
@@ -152,7 +154,11 @@ int run_tiles_ring(const SdBlkHost &bh, const SdBlkParams &P, const SdVecView &p
             for (unsigned lane = 0; lane < 32; ++lane) {
                 SdBlkrLane Ln;
                 sd_blkr_begin(Ln, bh.js[H.js], rw[(size_t)H.js * SD_BLK_CWARPS + w], lane);
-                for (int n = 0; n < ntot; ++n) sd_blkr_stream(Ln, bh.js.data(), H, ring[n].p, n);
+                for (int n = nring; n < H.nnb && n < ntot; ++n) sd_blkr_stream_direct(Ln, H, n);
+                for (int n = 0; n < ntot; ++n) {
+                    if (n >= nring && n < H.nnb) continue;
+                    sd_blkr_stream(Ln, bh.js.data(), H, ring[n].p, n);
+                }
                 double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
                 sd_blkr_own<PLAIN>(Ln, X, H, ring[ntot].p, red);
                 for (int s = 0; s < SD_NSLOT; ++s) wsum[s][w] += red[s];
@@ -193,6 +199,7 @@ int emul_blk_apply(int L, int k, const double *Jhop, const double *Jz, const dou
     P.nbuf = 3; P.dbg = 0;
     const bool halo = (variant & 256) != 0;                          // + 256: through the halo mirror (sd_halo_host.h), 3 chunks
     const bool balance = (variant & 512) != 0;                       // + 512: remote-volume-weighted shard bounds (sd_halo_balance)
+    const int ndirect = (variant >> 12) & 15;                         // + 4096 * n: n nearest prefix entries read directly (ring kernel)
     variant &= 255;
     if (variant == 3) { variant = 2; P.dbg = 16; }                   // ring kernel copying the whole crossing partner tile
     P.key_lo = keys[rank]; P.key_hi = keys[rank + 1];
@@ -270,7 +277,7 @@ int emul_blk_apply(int L, int k, const double *Jhop, const double *Jz, const dou
         }
         if (variant == 2) {                                         // ring kernel: f64 only
             if (NC != 1) return -1;
-            const int rc = plain ? run_tiles_ring<true>(bh, P, view, o.p, epi, qfar, red) : run_tiles_ring<false>(bh, P, view, o.p, epi, qfar, red);
+            const int rc = plain ? run_tiles_ring<true>(bh, P, view, o.p, epi, qfar, red, ndirect) : run_tiles_ring<false>(bh, P, view, o.p, epi, qfar, red, ndirect);
             if (rc != 0) return rc;
         } else if (NC == 1) { if (plain) RUN(1, true); else RUN(1, false); }
         else { if (plain) RUN(2, true); else RUN(2, false); }

@@ -423,3 +423,24 @@ def test_sharded_apply_through_the_halo_mirror(variant, L, k, world):
         assert np.linalg.norm(out - nxt) <= 1e-14 * np.linalg.norm(nxt)
         assert abs(complex(red[0], red[1]) - np.vdot(cplx(psi), cplx(nxt))) < 1e-9
         assert abs(red[2] - np.vdot(cplx(phi), cplx(nxt)).real) < 1e-9 and abs(red[3] - nxt @ nxt) < 1e-8
+
+
+@pytest.mark.parametrize("ndirect", [1, 3, 15])
+@pytest.mark.parametrize("L,k,world", [(18, 9, 1), (20, 10, 3), (22, 11, 1), (24, 12, 2)])
+def test_ring_kernel_with_direct_near_entries(ndirect, L, k, world):
+    """SD_BLKR_DIRECT=n: the n nearest prefix entries of a tile bypass the ring (consumers read them from global memory),
+    the remaining entries keep the ring protocol; any n (also n >= the number of prefix entries: crossing + own only)."""
+    lib = load()
+    rng = np.random.default_rng(L + ndirect)
+    Jhop, Jz, h = model_lists(L, rng)
+    m = oracle_model(L, k, Jhop, Jz, h)
+    states = np.ascontiguousarray(m.states, dtype=np.uint64)
+    psi, vprev = rng.standard_normal(len(states)), rng.standard_normal(len(states))
+    ref = oracle_apply(m, psi, 1)
+    for base in (2, 3, 2 + 256):
+        out, _, _, _ = run(lib, L, k, 1, world, states, psi, Jhop, Jz, h, variant=base + 4096 * ndirect)
+        assert np.linalg.norm(out - ref) <= 1e-14 * np.linalg.norm(ref), base
+    nxt = 2.0 * ((ref - 0.3 * psi) / 2.5) - vprev
+    out, red, _, _ = run(lib, L, k, 1, world, states, psi, Jhop, Jz, h, mode=2, red=5, a=2.5, b=0.3, vprev=vprev, variant=2 + 4096 * ndirect)
+    assert np.linalg.norm(out - nxt) <= 1e-14 * np.linalg.norm(nxt)
+    assert abs(red[0] - psi @ nxt) < 1e-13 * (nxt @ nxt) and abs(red[3] - nxt @ nxt) < 1e-13 * (nxt @ nxt)
