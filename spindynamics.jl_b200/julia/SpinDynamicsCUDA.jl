@@ -20,7 +20,8 @@ export GPUModel, GPUVector, XXZChain, build_model, momenta, nn_hopping, long_ran
        lanczos_extremal, lanczos_groundstate, lanczos_groundstate_lean, lanczos_tridiag, estimate_energy_bounds,
        lanczos_sqw, kpm_sqw, krylov_time_evolve, krylov_time_evolve!, KrylovWorkspace, chebyshev_time_evolve,
        ChebyshevWorkspace,
-       groundstate, time_evolve, dynamical_structure_factor, neel_state,
+       groundstate, time_evolve, dynamical_structure_factor, neel_state, domain_wall_state, polarized_state,
+       polarized_state_with_flips,
        magnetization_per_site, connected_correlations, structure_factor_Sq, structure_factor
 
 const lib = get(ENV, "SPINDYN_CUDA_LIB", "libspindyn_cuda")
@@ -378,12 +379,30 @@ function structure_factor_Sq(ψ, m::GPUModel)                       # Observable
 end
 structure_factor(m::GPUModel, ψ) = structure_factor_Sq(ψ, m)       # PublicAPI.jl:94-106
 
-# InitialStates.jl:40-63 through sd_rank (no idxmap)
-function neel_state(m::GPUModel)
-    s = UInt64(0); for i in 1:m.L; isodd(i) && (s |= UInt64(1) << (i - 1)); end
+# InitialStates.jl through sd_rank (get(idxmap, s, 0) / Int(s)+1 without a Dict); host Vector{Float64} like the reference
+function onehot(m::GPUModel, s::UInt64, what::String)
     idx = rank_of(m, UInt64[s])[1]
-    idx == 0 && throw(ArgumentError("Neel state is not contained in the model basis"))
+    idx == 0 && throw(ArgumentError("$what is not contained in the model basis"))
     ψ = zeros(m.dim); ψ[idx] = 1.0; ψ
+end
+function domain_wall_state(m::GPUModel)                             # InitialStates.jl:9-34
+    nup = m.nup === nothing ? Int(ceil(m.L / 2)) : m.nup
+    s = UInt64(0); for i in 0:nup-1; s |= UInt64(1) << i; end
+    onehot(m, s, "domain-wall state")
+end
+function neel_state(m::GPUModel)                                    # :40-63
+    s = UInt64(0); for i in 1:m.L; isodd(i) && (s |= UInt64(1) << (i - 1)); end
+    onehot(m, s, "Neel state")
+end
+polarized_state(m::GPUModel; up::Bool=true) =                       # :70-90
+    onehot(m, up ? (UInt64(1) << m.L) - UInt64(1) : UInt64(0), "requested polarized state")
+function polarized_state_with_flips(m::GPUModel, flips::Vector{Int})   # :97-130
+    for site in flips
+        1 <= site <= m.L || throw(ArgumentError("flip site $site is outside the model with L=$(m.L)"))
+    end
+    s = (UInt64(1) << m.L) - UInt64(1)
+    for site in flips; s ⊻= UInt64(1) << (site - 1); end
+    onehot(m, s, "requested flipped polarized state")
 end
 
 end # module
