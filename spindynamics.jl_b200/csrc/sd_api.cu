@@ -26,6 +26,7 @@
 #include "sd_blkr.h"
 #include "sd_blkr_host.h"
 #include "sd_obs.h"
+#include "sd_bdot.cuh"
 #include "sd_halo_host.h"
 #include <cuda.h>          // driver-API types only; the functions are resolved with dlopen (virtual memory management of the halo mirror)
 
@@ -1770,6 +1771,7 @@ int sd_lanczos_groundstate(sd_model *m, const sd_vec *v0, int lanc_m, double tol
         if (n0 == 0.0) return sd_fail(SD_ERR_ZERO_NORM, "starting vector has zero norm");
     }
     int mact = mm;
+    const bool batch_check = sd_env_int("SD_BATCH_CHECK", 0) != 0;
     for (int j = 1; j <= mm; ++j) {
         sd_vec *vj = S->v[j - 1];
         SD_TRY(sd_apply_impl(m, w, vj, sd_epi_plain(1.0), 0));              // :113
@@ -1787,7 +1789,43 @@ int sd_lanczos_groundstate(sd_model *m, const sd_vec *v0, int lanc_m, double tol
         if (j < mm) {
             beta[j - 1] = sqrt(r[7]);                                       // :133
             if (beta[j - 1] < tol) { mact = j; break; }                     // :136-139
-            for (int k = 1; k <= j; ++k) {                                  // :142-153 check pass
+            // :142-153 check pass.  SD_BATCH_CHECK=1: the overlaps are taken eight at a time and fetched once
+            // (sd_bdot.cuh); an overlap above the tolerance is corrected exactly as below and the pass resumes behind it
+            // with the modified w and beta -- the same sequence of operations as the one-at-a-time loop.
+            int kfirst = 1;
+            while (batch_check && kfirst <= j) {
+                const int cnt = j - kfirst + 1;
+                const unsigned g = sd_blas_grid(c, w->local_n);
+                SD_TRY(sd_partials_reserve(c, (size_t)SD_BDOT_MAX * g));
+                std::vector<double> d((size_t)cnt, 0.0);
+                for (int k0 = 0; k0 < cnt; k0 += SD_BDOT_MAX) {
+                    const int nb = std::min(SD_BDOT_MAX, cnt - k0);
+                    SdPtrBlock pb;
+                    for (int t = 0; t < SD_BDOT_MAX; ++t) pb.v[t] = (t < nb) ? S->v[kfirst - 1 + k0 + t]->d : nullptr;
+                    sd_bdot_f64_kernel<<<g, SD_BLAS_THREADS, 0, c->stream>>>(w->local_n, pb, nb, w->d, c->d_partials, g);
+                    SD_TRY(sd_launch_check(c, "sd_bdot_f64_kernel"));
+                    sd_bdot_reduce_kernel<<<1, SD_BDOT_MAX * 32, 0, c->stream>>>(c->d_partials, g, nb, c->d_scal + 2048 + (k0 % 1024));
+                    SD_TRY(sd_launch_check(c, "sd_bdot_reduce_kernel"));
+                    if (c->world > 1)
+                        SD_NCCL(g_nccl.AllReduce(c->d_scal + 2048 + (k0 % 1024), c->d_scal + 2048 + (k0 % 1024), nb, ncclFloat64_, ncclSum_, c->comm, c->stream));
+                    if ((k0 + SD_BDOT_MAX) % 1024 == 0 || k0 + SD_BDOT_MAX >= cnt) {       // drain the staged block of results
+                        const int base = (k0 / 1024) * 1024, have = std::min(cnt - base, 1024);
+                        SD_TRY(sd_fetch(c, 2048, have, d.data() + base));
+                    }
+                }
+                int viol = -1;
+                for (int t = 0; t < cnt && viol < 0; ++t)
+                    if (fabs(d[t]) / beta[j - 1] > orth_tol) viol = t;
+                if (viol < 0) { kfirst = j + 1; break; }
+                const int k = kfirst + viol;
+                SD_TRY(sd_axpy_impl(w, sd_host_scalar(-d[viol], 0), S->v[k - 1], sd_host_scalar(0, 0), nullptr, 12));
+                double nn[4];
+                SD_TRY(sd_fetch(c, 12, 4, nn));
+                beta[j - 1] = sqrt(nn[3]);
+                if (beta[j - 1] < tol) { mact = j; kfirst = j + 1; break; }   // like the loop below: leaves the check pass only
+                kfirst = k + 1;
+            }
+            for (int k = kfirst; k <= j; ++k) {                             // one at a time (the default)
                 SD_TRY(sd_dot_impl(S->v[k - 1], w, 1, 8));
                 double d[2];
                 SD_TRY(sd_fetch(c, 8, 2, d));

@@ -48,3 +48,19 @@ def test_lean_breakdown():
     assert len(a) < 40 and abs(E + 3.374932598687896) < 1e-10 and abs(abs(psi @ gs) - 1) < 1e-10
     with pytest.raises(sd.ZeroNormError):
         sd.lanczos_groundstate_lean(sd.apply_H_, m, v0=np.zeros(m.dim))
+
+
+@pytest.mark.parametrize("L,nup,lanc_m", [(10, 5, 80), (16, 8, 100), (12, 6, 150)])
+def test_batched_check_pass_equals_one_at_a_time(monkeypatch, L, nup, lanc_m):
+    """SD_BATCH_CHECK=1 (sd_bdot.cuh): the check pass of the full reorthogonalisation (Lanczos.jl:142-153) with the
+    overlaps taken eight at a time and fetched once -- same E0, same Ritz vector, same tridiagonal matrix as the
+    one-at-a-time loop (the two differ only in the summation order of the final reduction of each overlap)."""
+    m = sd.XXZChain(L, nup=nup)
+    v0 = np.random.default_rng(L).standard_normal(m.dim)
+    monkeypatch.delenv("SD_BATCH_CHECK", raising=False)
+    E_a, psi_a, al_a, be_a = sd.lanczos_groundstate(sd.apply_H_, m, lanc_m=lanc_m, v0=v0, return_tridiag=True)
+    monkeypatch.setenv("SD_BATCH_CHECK", "1")
+    E_b, psi_b, al_b, be_b = sd.lanczos_groundstate(sd.apply_H_, m, lanc_m=lanc_m, v0=v0, return_tridiag=True)
+    assert abs(E_a - E_b) < 1e-12 and len(al_a) == len(al_b)
+    assert np.allclose(al_a, al_b, atol=1e-9) and np.allclose(be_a, be_b, atol=1e-9)
+    assert min(np.linalg.norm(psi_a - psi_b), np.linalg.norm(psi_a + psi_b)) < 1e-7
