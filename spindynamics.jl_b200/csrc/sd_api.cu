@@ -53,6 +53,7 @@ static int sd_fail(int code, const char *fmt, ...) {
         int r_ = (call);          \
         if (r_ != SD_OK) return r_; \
     } while (0)
+#define SD_LOCK(ctxptr) std::lock_guard<std::recursive_mutex> sd_ctx_lock_((ctxptr)->mu)
 #define SD_ARG(cond, ...)                                  \
     do {                                                   \
         if (!(cond)) return sd_fail(SD_ERR_ARG, __VA_ARGS__); \
@@ -147,6 +148,11 @@ static int sd_drv_load() {
     } while (0)
 
 struct sd_ctx {
+    // Threading contract: calls on one context serialise.  Every entry point that touches the context's
+    // stream or scratch state takes this lock (recursive: entry points call each other), so the reference's
+    // Threads.@threads q-loops stay correct when they share a context -- they become sequential device work; for
+    // concurrency use one context per host thread (spindyn's q_threads).
+    mutable std::recursive_mutex mu;
     int device = 0;
     int rank = 0, world = 1;
     int sm_count = 148;
@@ -379,7 +385,7 @@ int sd_ctx_free(sd_ctx *c) {
 }
 int sd_ctx_sync(sd_ctx *c) {
     SD_ARG(c, "ctx is NULL");
-    SD_TRY(sd_use(c));
+    SD_LOCK(c); SD_TRY(sd_use(c));
     SD_CUDA(cudaStreamSynchronize(c->stream));
     return SD_OK;
 }
@@ -391,13 +397,13 @@ int sd_ctx_rank(const sd_ctx *c, int *rank, int *world) {
 }
 int sd_timer_start(sd_ctx *c) {
     SD_ARG(c, "ctx is NULL");
-    SD_TRY(sd_use(c));
+    SD_LOCK(c); SD_TRY(sd_use(c));
     SD_CUDA(cudaEventRecord(c->ev0, c->stream));
     return SD_OK;
 }
 int sd_timer_stop(sd_ctx *c, float *ms) {
     SD_ARG(c && ms, "NULL argument");
-    SD_TRY(sd_use(c));
+    SD_LOCK(c); SD_TRY(sd_use(c));
     SD_CUDA(cudaEventRecord(c->ev1, c->stream));
     SD_CUDA(cudaEventSynchronize(c->ev1));
     SD_CUDA(cudaEventElapsedTime(ms, c->ev0, c->ev1));
@@ -406,7 +412,7 @@ int sd_timer_stop(sd_ctx *c, float *ms) {
 // debug: per-phase cycle sums of the tiled kernel (all zero unless built with -DSD_PHASE_TIMING)
 extern "C" int sd_debug_phase_cycles(sd_ctx *c, uint64_t *out8, int reset) {
     SD_ARG(c && out8, "NULL argument");
-    SD_TRY(sd_use(c));
+    SD_LOCK(c); SD_TRY(sd_use(c));
     SD_CUDA(cudaStreamSynchronize(c->stream));
     unsigned long long h[16];
     SD_CUDA(cudaMemcpyFromSymbol(h, sd_phase_cycles, sizeof(h)));
@@ -548,7 +554,7 @@ int sd_model_create(sd_ctx *ctx, int L, int nup, const sd_bond *hop, int nhop, c
     SD_ARG(L <= SD_MAX_L, "L must be at most 63 when using UInt64 basis states");
     SD_ARG(nup >= -1 && nup <= L, "nup must satisfy 0 <= nup <= L");
     SD_ARG(nhop >= 0 && nzz >= 0 && (nhop == 0 || hop) && (nzz == 0 || zz) && field, "bad bond lists");
-    SD_TRY(sd_use(ctx));
+    SD_LOCK(ctx); SD_TRY(sd_use(ctx));
     sd_model *m = new (std::nothrow) sd_model;
     if (!m) return sd_fail(SD_ERR_NOMEM, "out of host memory");
     m->ctx = ctx; m->L = L; m->k = nup;
@@ -752,7 +758,7 @@ int sd_unrank(sd_model *m, uint64_t first, uint64_t count, uint64_t *states) {
     SD_ARG(first <= m->N && count <= m->N - first, "range outside the basis");
     if (count == 0) return SD_OK;
     sd_ctx *c = m->ctx;
-    SD_TRY(sd_use(c));
+    SD_LOCK(c); SD_TRY(sd_use(c));
     uint64_t *d = nullptr;
     SD_CUDA(cudaMalloc(&d, count * sizeof(uint64_t)));
     sd_unrank_kernel<<<sd_blas_grid(c, count), SD_BLAS_THREADS, 0, c->stream>>>(m->L, m->k, c->d_binom, first, count, d);
@@ -769,7 +775,7 @@ int sd_rank(sd_model *m, const uint64_t *states, uint64_t count, int64_t *idx1) 
     SD_ARG(m && ((states && idx1) || count == 0), "NULL argument");
     if (count == 0) return SD_OK;
     sd_ctx *c = m->ctx;
-    SD_TRY(sd_use(c));
+    SD_LOCK(c); SD_TRY(sd_use(c));
     uint64_t *ds = nullptr;
     int64_t *di = nullptr;
     SD_CUDA(cudaMalloc(&ds, count * sizeof(uint64_t)));
@@ -796,7 +802,7 @@ int sd_vec_alloc(sd_model *m, int dtype, sd_vec **vec) {
     *vec = nullptr;
     SD_ARG(dtype == SD_F64 || dtype == SD_C128, "dtype must be SD_F64 or SD_C128");
     sd_ctx *c = m->ctx;
-    SD_TRY(sd_use(c));
+    SD_LOCK(c); SD_TRY(sd_use(c));
     sd_vec *v = new (std::nothrow) sd_vec;
     if (!v) return sd_fail(SD_ERR_NOMEM, "out of host memory");
     v->model = m; v->dtype = dtype; v->nc = dtype == SD_C128 ? 2 : 1;
@@ -884,7 +890,7 @@ static int sd_blk_permute(const sd_vec *v, double *rank_local, int nc_rank, int 
 int sd_vec_upload(sd_vec *v, const void *host) {
     SD_ARG(v && host, "NULL argument");
     sd_ctx *c = v->model->ctx;
-    SD_TRY(sd_use(c));
+    SD_LOCK(c); SD_TRY(sd_use(c));
     if (v->layout) {
         double *st = nullptr;
         SD_TRY(sd_scratch(c, 0, sd_vec_logical_bytes(v) + 16, &st));
@@ -901,7 +907,7 @@ int sd_vec_upload(sd_vec *v, const void *host) {
 int sd_vec_download(sd_vec *v, void *host) {
     SD_ARG(v && host, "NULL argument");
     sd_ctx *c = v->model->ctx;
-    SD_TRY(sd_use(c));
+    SD_LOCK(c); SD_TRY(sd_use(c));
     if (v->layout) {
         double *st = nullptr;
         SD_TRY(sd_scratch(c, 1, sd_vec_logical_bytes(v) + 16, &st));
@@ -918,7 +924,7 @@ int sd_vec_download(sd_vec *v, void *host) {
 int sd_vec_upload_async(sd_vec *v, const void *host) {
     SD_ARG(v && host, "NULL argument");
     sd_ctx *c = v->model->ctx;
-    SD_TRY(sd_use(c));
+    SD_LOCK(c); SD_TRY(sd_use(c));
     if (v->layout) {
         double *st = nullptr;
         SD_TRY(sd_scratch(c, 0, sd_vec_logical_bytes(v) + 16, &st));
@@ -931,7 +937,7 @@ int sd_vec_upload_async(sd_vec *v, const void *host) {
 int sd_vec_download_async(sd_vec *v, void *host) {
     SD_ARG(v && host, "NULL argument");
     sd_ctx *c = v->model->ctx;
-    SD_TRY(sd_use(c));
+    SD_LOCK(c); SD_TRY(sd_use(c));
     if (v->layout) {
         double *st = nullptr;
         SD_TRY(sd_scratch(c, 1, sd_vec_logical_bytes(v) + 16, &st));
@@ -954,7 +960,7 @@ int sd_host_free(void *p) {
 int sd_vec_zero(sd_vec *v) {
     SD_ARG(v, "NULL argument");
     sd_ctx *c = v->model->ctx;
-    SD_TRY(sd_use(c));
+    SD_LOCK(c); SD_TRY(sd_use(c));
     SD_CUDA(cudaMemsetAsync(v->d, 0, sd_vec_bytes(v), c->stream));
     return SD_OK;
 }
@@ -979,7 +985,7 @@ int sd_vec_set_onehot(sd_vec *v, uint64_t idx0) {
 int sd_vec_fill_seeded(sd_vec *v, uint64_t seed, double scale) {
     SD_ARG(v, "NULL argument");
     sd_ctx *c = v->model->ctx;
-    SD_TRY(sd_use(c));
+    SD_LOCK(c); SD_TRY(sd_use(c));
     if (v->local_n == 0) return SD_OK;
     if (v->layout) return sd_blk_permute(v, nullptr, v->nc, 0, 1, seed, scale);
     sd_fill_seeded_kernel<<<sd_blas_grid(c, v->local_n), SD_BLAS_THREADS, 0, c->stream>>>(
@@ -990,7 +996,7 @@ int sd_vec_copy(sd_vec *dst, const sd_vec *src) {
     SD_ARG(dst && src, "NULL argument");
     SD_ARG(dst->model == src->model && dst->dtype == src->dtype, "vectors differ in model or dtype");
     sd_ctx *c = dst->model->ctx;
-    SD_TRY(sd_use(c));
+    SD_LOCK(c); SD_TRY(sd_use(c));
     if (dst->d != src->d)
         SD_CUDA(cudaMemcpyAsync(dst->d, src->d, sd_vec_bytes(dst), cudaMemcpyDeviceToDevice, c->stream));
     return SD_OK;
@@ -1000,7 +1006,7 @@ int sd_vec_convert(sd_vec *dst, const sd_vec *src) {
     SD_ARG(dst->model == src->model, "vectors belong to different models");
     if (dst->dtype == src->dtype) return sd_vec_copy(dst, src);
     sd_ctx *c = dst->model->ctx;
-    SD_TRY(sd_use(c));
+    SD_LOCK(c); SD_TRY(sd_use(c));
     if (dst->local_n == 0) return SD_OK;
     if (dst->layout || src->layout) {                // f64 and c128 block layouts order a class differently
         SD_ARG(dst->layout && src->layout, "vectors differ in layout");
@@ -1033,7 +1039,7 @@ static int sd_scale_impl(sd_vec *x, SdScalar s) {
 int sd_vec_scale(sd_vec *x, sd_complex s) {
     SD_ARG(x, "NULL argument");
     SD_ARG(x->nc == 2 || s.im == 0.0, "complex scale of a real vector (InexactError)");
-    SD_TRY(sd_use(x->model->ctx));
+    SD_LOCK(x->model->ctx); SD_TRY(sd_use(x->model->ctx));
     return sd_scale_impl(x, sd_host_scalar(s.re, s.im));
 }
 // y = x / s (s real; device or host scalar)
@@ -1063,7 +1069,7 @@ int sd_vec_axpy(sd_vec *y, sd_complex a, const sd_vec *x) {
     SD_ARG(y && x, "NULL argument");
     SD_ARG(y->model == x->model && y->dtype == x->dtype, "vectors differ in model or dtype");
     SD_ARG(y->nc == 2 || a.im == 0.0, "complex axpy into a real vector (InexactError)");
-    SD_TRY(sd_use(y->model->ctx));
+    SD_LOCK(y->model->ctx); SD_TRY(sd_use(y->model->ctx));
     return sd_axpy_impl(y, sd_host_scalar(a.re, a.im), x, sd_host_scalar(0, 0), nullptr, -1);
 }
 // dot -> d_scal[slot_out + 0,1]
@@ -1080,7 +1086,7 @@ int sd_vec_dot(const sd_vec *x, const sd_vec *y, sd_complex *result) {
     SD_ARG(x && y && result, "NULL argument");
     SD_ARG(x->model == y->model && x->dtype == y->dtype, "vectors differ in model or dtype");
     sd_ctx *c = x->model->ctx;
-    SD_TRY(sd_use(c));
+    SD_LOCK(c); SD_TRY(sd_use(c));
     SD_TRY(sd_dot_impl(x, y, 1, 0));
     double r[2];
     SD_TRY(sd_fetch(c, 0, 2, r));
@@ -1091,7 +1097,7 @@ int sd_vec_dotu(const sd_vec *x, const sd_vec *y, sd_complex *result) {
     SD_ARG(x && y && result, "NULL argument");
     SD_ARG(x->model == y->model && x->dtype == y->dtype, "vectors differ in model or dtype");
     sd_ctx *c = x->model->ctx;
-    SD_TRY(sd_use(c));
+    SD_LOCK(c); SD_TRY(sd_use(c));
     SD_TRY(sd_dot_impl(x, y, 0, 0));
     double r[2];
     SD_TRY(sd_fetch(c, 0, 2, r));
@@ -1101,7 +1107,7 @@ int sd_vec_dotu(const sd_vec *x, const sd_vec *y, sd_complex *result) {
 int sd_vec_norm(const sd_vec *x, double *result) {
     SD_ARG(x && result, "NULL argument");
     sd_ctx *c = x->model->ctx;
-    SD_TRY(sd_use(c));
+    SD_LOCK(c); SD_TRY(sd_use(c));
     SD_TRY(sd_dot_impl(x, x, 1, 0));
     double r[2];
     SD_TRY(sd_fetch(c, 0, 2, r));
@@ -1290,7 +1296,7 @@ static int sd_apply_impl(sd_model *m, sd_vec *out, const sd_vec *psi, SdEpi epi,
     SD_ARG(out->model == m && psi->model == m, "vector does not belong to this model");
     SD_ARG(out->dtype == psi->dtype, "out and psi differ in element type");
     SD_ARG(out->d != psi->d, "out must not alias psi");
-    SD_TRY(sd_use(c));
+    SD_LOCK(c); SD_TRY(sd_use(c));
     SD_TRY(sd_rank_barrier(c));
     const int nc = psi->nc;
     const int slotmask = sd_epi_slotmask(epi.red);
@@ -1484,7 +1490,7 @@ int sd_szq(sd_model *m, sd_vec *phi, const sd_vec *psi0, double q, double *norm2
     SD_ARG(phi->dtype == SD_C128, "phi must be SD_C128");
     SD_ARG(phi->d != psi0->d, "phi must not alias psi0");
     sd_ctx *c = m->ctx;
-    SD_TRY(sd_use(c));
+    SD_LOCK(c); SD_TRY(sd_use(c));
     SdSzqParams Z;
     Z.L = m->L; Z.k = m->k; Z.normfact = 1.0 / sqrt((double)m->L); Z.binom = c->d_binom;
     for (int r = 0; r < m->L; ++r) { Z.ph_re[r] = cos(q * (double)r); Z.ph_im[r] = sin(q * (double)r); }
@@ -1525,7 +1531,7 @@ int sd_vec_observables(const sd_vec *psi, double *mags, double *zz) {
     sd_model *m = psi->model;
     sd_ctx *c = m->ctx;
     SD_ARG(m->L <= 63, "L must be at most 63");
-    SD_TRY(sd_use(c));
+    SD_LOCK(c); SD_TRY(sd_use(c));
     const double *src = psi->d;
     if (psi->layout) {                               // block layout: run on a rank-ordered staging copy (not a hot path)
         double *s0 = nullptr;
@@ -1594,7 +1600,7 @@ int sd_lincomb(sd_vecset *s, const sd_complex *y, int mcount, sd_vec *out, doubl
         if (out->nc == 1) SD_ARG(y[j].im == 0.0, "complex coefficient into a real output (InexactError)");
     }
     sd_ctx *c = m->ctx;
-    SD_TRY(sd_use(c));
+    SD_LOCK(c); SD_TRY(sd_use(c));
     SD_ARG(2 * mcount <= 2048, "too many vectors");
     if (out->layout && out->nc == 2 && v0->nc == 1) {
         // the f64 and c128 block layouts order a class differently (pair rows): combine through a
@@ -1674,7 +1680,7 @@ int sd_lanczos_extremal(sd_model *m, const sd_vec *v0, int lanc_m, double tol, i
     SD_ARG(v0->model == m && v0->dtype == SD_C128, "v0 must be an SD_C128 vector of this model");
     SD_ARG(lanc_m >= 1, "lanc_m must be >= 1");
     sd_ctx *c = m->ctx;
-    SD_TRY(sd_use(c));
+    SD_LOCK(c); SD_TRY(sd_use(c));
     const int mm = (int)std::min<uint64_t>((uint64_t)lanc_m, m->N);          // Lanczos.jl:36
     SdVecGuard G;
     sd_vec *vp, *vc, *w;
@@ -1712,7 +1718,7 @@ int sd_lanczos_tridiag(sd_model *m, const sd_vec *v, int lanc_m, double tol, dou
     SD_ARG(v->model == m && v->dtype == SD_C128, "v must be an SD_C128 vector of this model");
     SD_ARG(lanc_m >= 1, "lanc_m must be >= 1");
     sd_ctx *c = m->ctx;
-    SD_TRY(sd_use(c));
+    SD_LOCK(c); SD_TRY(sd_use(c));
     const int mm = (int)std::min<uint64_t>((uint64_t)lanc_m, m->N);          // Lanczos.jl:200
     SdVecGuard G;
     sd_vec *vj, *vo, *w;
@@ -1754,7 +1760,7 @@ int sd_lanczos_groundstate(sd_model *m, const sd_vec *v0, int lanc_m, double tol
     SD_ARG(v0->model == m && v0->dtype == SD_F64, "v0 must be an SD_F64 vector of this model");
     SD_ARG(lanc_m >= 1, "lanc_m must be >= 1");
     sd_ctx *c = m->ctx;
-    SD_TRY(sd_use(c));
+    SD_LOCK(c); SD_TRY(sd_use(c));
     const int mm = (int)std::min<uint64_t>((uint64_t)lanc_m, m->N);          // Lanczos.jl:97
     sd_vecset *S = new (std::nothrow) sd_vecset;
     if (!S) return sd_fail(SD_ERR_NOMEM, "out of host memory");
@@ -1864,7 +1870,7 @@ int sd_lanczos_lean(sd_model *m, const sd_vec *v0, int lanc_m, double tol, doubl
     SD_ARG(lanc_m >= 1, "lanc_m must be >= 1");
     SD_ARG(!y || (out && norm2 && out->model == m && out->dtype == SD_F64 && out->d != v0->d), "pass 2 needs y, an SD_F64 out and norm2");
     sd_ctx *c = m->ctx;
-    SD_TRY(sd_use(c));
+    SD_LOCK(c); SD_TRY(sd_use(c));
     const int mm = (int)std::min<uint64_t>((uint64_t)lanc_m, m->N);
     SdVecGuard G;
     sd_vec *vj, *vo, *w;
@@ -1912,7 +1918,7 @@ int sd_kpm_moments(sd_model *m, const sd_vec *phi, int M, double a, double b, do
     SD_ARG(phi->model == m && phi->dtype == SD_C128, "phi must be an SD_C128 vector of this model");
     SD_ARG(M >= 1, "M must be >= 1");
     sd_ctx *c = m->ctx;
-    SD_TRY(sd_use(c));
+    SD_LOCK(c); SD_TRY(sd_use(c));
     SdVecGuard G;
     sd_vec *vp, *vc;
     SD_TRY(G.make(m, SD_C128, &vp)); SD_TRY(G.make(m, SD_C128, &vc));
@@ -1950,7 +1956,7 @@ int sd_krylov_basis(sd_model *m, const sd_vec *psi0, int kry_m, sd_complex *alph
     SD_ARG(psi0->model == m, "psi0 belongs to a different model");
     SD_ARG(kry_m >= 1, "kry_m must be >= 1");
     sd_ctx *c = m->ctx;
-    SD_TRY(sd_use(c));
+    SD_LOCK(c); SD_TRY(sd_use(c));
     const int dt = psi0->dtype;
     sd_vecset *S = new (std::nothrow) sd_vecset;
     if (!S) return sd_fail(SD_ERR_NOMEM, "out of host memory");
@@ -1998,7 +2004,7 @@ int sd_chebyshev_evolve(sd_model *m, const sd_vec *psi0, const sd_complex *cf, i
     SD_ARG(n >= 1, "cheb_n must be >= 1");
     SD_ARG(out->d != psi0->d, "out must not alias psi0");
     sd_ctx *c = m->ctx;
-    SD_TRY(sd_use(c));
+    SD_LOCK(c); SD_TRY(sd_use(c));
     SdVecGuard G;
     sd_vec *vp, *vc;
     SD_TRY(G.make(m, SD_C128, &vp)); SD_TRY(G.make(m, SD_C128, &vc));
