@@ -27,7 +27,7 @@ ARGTYPES = ([ctypes.c_int, ctypes.c_int, vp, vp, vp, ctypes.c_int, vp, ctypes.c_
 def load():
     d = os.path.join(ROOT, "tests", "emul")
     subprocess.check_call(["make", "-C", d], stdout=subprocess.DEVNULL)
-    lib = ctypes.CDLL(os.path.join(d, "libsd_emul_blk.so"))
+    lib = ctypes.CDLL(os.environ.get("SD_EMUL_BLK_LIB") or os.path.join(d, "libsd_emul_blk.so"))   # SD_EMUL_BLK_LIB: the ASan build (make asan)
     lib.emul_blk_apply.argtypes = ARGTYPES
     return lib
 
