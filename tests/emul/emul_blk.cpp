@@ -12,6 +12,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#include <atomic>
+#include <thread>
+#include <chrono>
 #include "../../spindynamics.jl_b200/csrc/sd_tile_host.h"
 #include "../../spindynamics.jl_b200/csrc/sd_blk_host.h"
 #include "../../spindynamics.jl_b200/csrc/sd_blkr_host.h"
@@ -169,6 +172,183 @@ int run_tiles_ring(const SdBlkHost &bh, const SdBlkParams &P, const SdVecView &p
     return 0;
 }
 
+// ---- threaded run of the ring kernel's protocol: one host thread per warp (1 producer + 15 consumers), a real ring of
+// SD_BLKR_NB buffers and headers that are REUSED, mbarriers modelled with atomics (pending arrivals + transaction bytes
+// + phase, try_wait on the phase parity).  The two loops below mirror the producer / consumer loops of
+// sd_blkr_apply_kernel statement by statement (same entry numbering, slot = e % NB, parity = (e / NB) & 1, header of the
+// CTA's t-th tile in hdr[t % NB] written after the wait on empty[] of the tile's first entry); everything they call is the
+// kernel's own __host__ __device__ code.  A slot or header that is reused too early shows up as a wrong result (the
+// producer scribbles NaN over a slot before refilling it) or as a ThreadSanitizer report.
+struct HostBar {
+    std::atomic<uint64_t> state{0};                                  // phase << 40 | pending << 32 | tx (tx as uint32 two's complement)
+    uint32_t count = 1;
+    void init(uint32_t c) { count = c; state.store((uint64_t)c << 32, std::memory_order_release); }
+    static uint64_t pack(uint64_t phase, uint32_t pending, uint32_t tx) { return (phase << 40) | ((uint64_t)(pending & 0xFFu) << 32) | tx; }
+    void update(int dpending, int32_t dtx) {
+        uint64_t o = state.load(std::memory_order_acquire), n;
+        do {
+            uint64_t phase = o >> 40;
+            uint32_t pending = (uint32_t)((o >> 32) & 0xFFu), tx = (uint32_t)o;
+            pending = (uint32_t)((int)pending + dpending);
+            tx = (uint32_t)((int32_t)tx + dtx);
+            if (pending == 0 && tx == 0) { ++phase; pending = count; }
+            n = pack(phase, pending, tx);
+        } while (!state.compare_exchange_weak(o, n, std::memory_order_acq_rel));
+    }
+    void arrive() { update(-1, 0); }
+    void arrive_expect_tx(uint32_t bytes) { update(-1, (int32_t)bytes); }
+    void complete_tx(uint32_t bytes) { update(0, -(int32_t)bytes); }
+    bool try_wait(unsigned parity) const { return ((state.load(std::memory_order_acquire) >> 40) & 1u) != parity; }
+};
+static bool host_wait(const HostBar &b, unsigned parity, std::atomic<int> &abort_flag) {
+    for (unsigned spins = 0; !b.try_wait(parity); ++spins) {
+        if (abort_flag.load(std::memory_order_relaxed)) return false;
+        if ((spins & 1023u) == 1023u) std::this_thread::yield();
+        if (spins > (1u << 28)) { abort_flag.store(1); return false; }       // deadlock watchdog
+    }
+    return true;
+}
+
+template <bool PLAIN>
+int run_tiles_ring_threaded(const SdBlkHost &bh, const SdBlkParams &P, const SdVecView &psi, double *out_local, const SdEpi &epi,
+                            int qfar, double *red_total, int ndirect) {
+    constexpr unsigned NB = SD_BLKR_NB;
+    std::vector<SdBlkrWarp> rw;
+    if (!sd_blkr_build(bh, rw)) return -4;
+    std::vector<AlignedBuf> ring(NB);
+    for (auto &b : ring) b.alloc(P.cap, NAN);
+    std::vector<SdBlkrHdr> hdr(NB);
+    HostBar full[NB], empty[NB];
+    for (unsigned b = 0; b < NB; ++b) { full[b].init(1); empty[b].init(SD_BLK_CWARPS); }
+    std::atomic<uint64_t> tile_ctr{0};
+    std::atomic<int> abort_flag{0};
+    const bool nostream = (P.dbg & 1) != 0;
+    std::vector<std::vector<double>> partial;                         // [tile][slot]: per-tile sums, added in tile order afterwards
+    partial.assign((size_t)(P.key_hi - P.key_lo), std::vector<double>(SD_NSLOT, 0.0));
+
+    auto producer = [&]() {
+        unsigned e = 0;
+        for (unsigned t = 0;; ++t) {
+            uint64_t key;
+            for (;;) {
+                const uint64_t c = tile_ctr.fetch_add(1);
+                key = P.key_lo + c;
+                if (key >= P.key_hi) break;
+                const uint64_t Pb = sd_blk_key_prefix(key, P.A);
+                const int js = P.k - SD_POPC64(Pb);
+                if (js >= 0 && js <= SD_BLK_B) break;
+            }
+            if (!host_wait(empty[e & (NB - 1)], ((e / NB) & 1u) ^ 1u, abort_flag)) return;
+            SdBlkrHdr &H = hdr[t & (NB - 1)];
+            if (key >= P.key_hi) {
+                H.valid = -1;
+                full[e & (NB - 1)].arrive();
+                break;
+            }
+            {   // sd_blk_make_hdr, lane by lane
+                const uint64_t Pb = sd_blk_key_prefix(key, P.A);
+                SdBlkHdrLane lanes[32];
+                uint64_t base = 0;
+                double dpre = 0.0;
+                unsigned actmask = 0;
+                for (int q = 0; q < 32; ++q) {
+                    lanes[q] = sd_blk_hdr_lane(P, bh.W.data(), Pb, q);
+                    base += lanes[q].term; dpre += lanes[q].d;
+                    if (lanes[q].act) actmask |= 1u << q;
+                }
+                for (int q = 0; q < 32; ++q) sd_blk_hdr_fill<1, SdBlkrHdr>(P, lanes[q], Pb, key, base, dpre, actmask, qfar, q, H, psi);
+            }
+            const int ntot = nostream ? 0 : H.ntot;
+            const int nring = sd_blkr_nring(H, ndirect), nnb = H.nnb;
+            const double *own_src = psi.base[P.shards.rank] + H.base;
+            bool first = true;
+            for (int n = 0; n <= ntot; ++n) {
+                if (n >= nring && n < nnb && n < ntot) continue;
+                const unsigned slot = e & (NB - 1);
+                if (!first && !host_wait(empty[slot], ((e / NB) & 1u) ^ 1u, abort_flag)) return;
+                first = false;
+                char *dst = (char *)ring[slot].p;
+                for (size_t i = 0; i < P.cap; ++i) ring[slot].p[i] = NAN;      // a consumer still reading this slot would see NaN
+                uint32_t tot = 0;
+                for (unsigned lane = 0; lane < 32; ++lane) {
+                    const char *src; uint32_t off, len;
+                    for (unsigned i = 0; sd_blkr_copy(bh.js.data(), H, own_src, P.dbg, n, ntot, lane, i, &src, &off, &len); ++i) tot += len;
+                }
+                if (tot) full[slot].arrive_expect_tx(tot); else full[slot].arrive();
+                for (unsigned lane = 0; lane < 32; ++lane) {
+                    const char *src; uint32_t off, len;
+                    for (unsigned i = 0; sd_blkr_copy(bh.js.data(), H, own_src, P.dbg, n, ntot, lane, i, &src, &off, &len); ++i) {
+                        std::memcpy(dst + off, src + off, len);
+                        full[slot].complete_tx(len);
+                    }
+                }
+                ++e;
+            }
+        }
+    };
+    std::vector<std::atomic<unsigned>> done(NB);
+    for (auto &d : done) d.store(0);
+    std::vector<std::vector<double>> usum(NB, std::vector<double>(SD_NSLOT * 16, 0.0));
+    auto consumer = [&](unsigned warp) {
+        SdBlkCtx X;
+        X.P = &P; X.js = bh.js.data(); X.dmid = bh.dmid.data(); X.dtail = P.dtail; X.Jhop = P.Jhop;
+        X.qx = P.Jz[P.A + SD_BLK_M - 1] * 0.25;
+        X.pstart_local = P.shards.pstart[P.shards.rank];
+        X.out_local = out_local;
+        X.epi = &epi;
+        unsigned e = 0;
+        for (unsigned t = 0;; ++t) {
+            if (!host_wait(full[e & (NB - 1)], (e / NB) & 1u, abort_flag)) return;
+            SdBlkrHdr &H = hdr[t & (NB - 1)];
+            if (H.valid < 0) break;
+            SdBlkrLane Ln[32];
+            for (unsigned lane = 0; lane < 32; ++lane) sd_blkr_begin(Ln[lane], bh.js[H.js], rw[(size_t)H.js * SD_BLK_CWARPS + warp], lane);
+            const int ntot = nostream ? 0 : H.ntot;
+            const int nring = sd_blkr_nring(H, ndirect), nnb = H.nnb;
+            for (int n = nring; n < nnb && n < ntot; ++n)
+                for (unsigned lane = 0; lane < 32; ++lane) sd_blkr_stream_direct(Ln[lane], H, n);
+            bool first = true;
+            for (int n = 0; n < ntot; ++n) {
+                if (n >= nring && n < nnb) continue;
+                const unsigned slot = e & (NB - 1);
+                if (!first && !host_wait(full[slot], (e / NB) & 1u, abort_flag)) return;
+                first = false;
+                for (unsigned lane = 0; lane < 32; ++lane) sd_blkr_stream(Ln[lane], bh.js.data(), H, ring[slot].p, n);
+                empty[slot].arrive();
+                ++e;
+            }
+            const unsigned slot = e & (NB - 1);
+            if (!first && !host_wait(full[slot], (e / NB) & 1u, abort_flag)) return;
+            double wred[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
+            for (unsigned lane = 0; lane < 32; ++lane) {
+                double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
+                sd_blkr_own<PLAIN>(Ln[lane], X, H, ring[slot].p, red);
+                for (int s = 0; s < SD_NSLOT; ++s) wred[s] += red[s];
+            }
+            const unsigned h = t & (NB - 1);
+            for (int s = 0; s < SD_NSLOT; ++s) usum[h][s * 16 + warp] = wred[s];
+            if (done[h].fetch_add(1, std::memory_order_acq_rel) + 1 == SD_BLK_CWARPS) {   // last warp of the tile: sum in warp order
+                for (int s = 0; s < SD_NSLOT; ++s) {
+                    double tsum = 0.0;
+                    for (unsigned j = 0; j < SD_BLK_CWARPS; ++j) tsum += usum[h][s * 16 + j];
+                    partial[H.tile_index][s] = tsum;
+                }
+                done[h].store(0, std::memory_order_release);                              // the kernel: the producer zeroes it with the next header
+            }
+            empty[slot].arrive();
+            ++e;
+        }
+    };
+    std::vector<std::thread> th;
+    th.emplace_back(producer);
+    for (unsigned w = 0; w < SD_BLK_CWARPS; ++w) th.emplace_back(consumer, w);
+    for (auto &x : th) x.join();
+    if (abort_flag.load()) return -10;                                // deadlock
+    for (auto &p : partial)
+        for (int s = 0; s < SD_NSLOT; ++s) red_total[s] += p[s];
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -199,6 +379,7 @@ int emul_blk_apply(int L, int k, const double *Jhop, const double *Jz, const dou
     P.nbuf = 3; P.dbg = 0;
     const bool halo = (variant & 256) != 0;                          // + 256: through the halo mirror (sd_halo_host.h), 3 chunks
     const bool balance = (variant & 512) != 0;                       // + 512: remote-volume-weighted shard bounds (sd_halo_balance)
+    const bool threaded = (variant & 1024) != 0;                     // + 1024: ring kernel as 16 host threads on a real, reused ring
     const int ndirect = (variant >> 12) & 15;                         // + 4096 * n: n nearest prefix entries read directly (ring kernel)
     variant &= 255;
     if (variant == 3) { variant = 2; P.dbg = 16; }                   // ring kernel copying the whole crossing partner tile
@@ -277,7 +458,8 @@ int emul_blk_apply(int L, int k, const double *Jhop, const double *Jz, const dou
         }
         if (variant == 2) {                                         // ring kernel: f64 only
             if (NC != 1) return -1;
-            const int rc = plain ? run_tiles_ring<true>(bh, P, view, o.p, epi, qfar, red, ndirect) : run_tiles_ring<false>(bh, P, view, o.p, epi, qfar, red, ndirect);
+            const int rc = threaded ? (plain ? run_tiles_ring_threaded<true>(bh, P, view, o.p, epi, qfar, red, ndirect) : run_tiles_ring_threaded<false>(bh, P, view, o.p, epi, qfar, red, ndirect))
+                                    : (plain ? run_tiles_ring<true>(bh, P, view, o.p, epi, qfar, red, ndirect) : run_tiles_ring<false>(bh, P, view, o.p, epi, qfar, red, ndirect));
             if (rc != 0) return rc;
         } else if (NC == 1) { if (plain) RUN(1, true); else RUN(1, false); }
         else { if (plain) RUN(2, true); else RUN(2, false); }

@@ -444,3 +444,29 @@ def test_ring_kernel_with_direct_near_entries(ndirect, L, k, world):
     out, red, _, _ = run(lib, L, k, 1, world, states, psi, Jhop, Jz, h, mode=2, red=5, a=2.5, b=0.3, vprev=vprev, variant=2 + 4096 * ndirect)
     assert np.linalg.norm(out - nxt) <= 1e-14 * np.linalg.norm(nxt)
     assert abs(red[0] - psi @ nxt) < 1e-13 * (nxt @ nxt) and abs(red[3] - nxt @ nxt) < 1e-13 * (nxt @ nxt)
+
+
+@pytest.mark.parametrize("ndirect", [0, 2])
+@pytest.mark.parametrize("L,k,world", [(16, 8, 1), (18, 9, 2), (20, 10, 1), (21, 8, 3)])
+def test_ring_protocol_with_real_threads_and_a_reused_ring(ndirect, L, k, world):
+    """The ring kernel as 16 host threads (1 producer + 15 consumer "warps") on a real ring of 4 buffers and 4 headers
+    that are reused, mbarriers modelled with atomics; the two loops mirror the kernel's statement by statement and call
+    the kernel's own host/device code.  The producer scribbles NaN over a slot before it refills it, so a slot or header
+    reused too early corrupts the result; a deadlock is reported (-10).  Also run under ThreadSanitizer (make tsan)."""
+    lib = load()
+    rng = np.random.default_rng(L + ndirect)
+    Jhop, Jz, h = model_lists(L, rng)
+    m = oracle_model(L, k, Jhop, Jz, h)
+    states = np.ascontiguousarray(m.states, dtype=np.uint64)
+    psi, vprev, phi = (rng.standard_normal(len(states)) for _ in range(3))
+    ref = oracle_apply(m, psi, 1)
+    variant = 2 + 1024 + 4096 * ndirect
+    for rep in range(3):                                             # thread interleavings differ from run to run
+        out, _, _, _ = run(lib, L, k, 1, world, states, psi, Jhop, Jz, h, variant=variant)
+        assert np.linalg.norm(out - ref) <= 1e-14 * np.linalg.norm(ref)
+    nxt = 2.0 * ((ref - 0.3 * psi) / 2.5) - vprev
+    out, red, _, _ = run(lib, L, k, 1, world, states, psi, Jhop, Jz, h, mode=2, red=7, a=2.5, b=0.3, vprev=vprev, phi=phi, variant=variant)
+    assert np.linalg.norm(out - nxt) <= 1e-14 * np.linalg.norm(nxt)
+    assert abs(red[0] - psi @ nxt) < 1e-12 * (nxt @ nxt) and abs(red[2] - phi @ nxt) < 1e-12 * (nxt @ nxt) and abs(red[3] - nxt @ nxt) < 1e-12 * (nxt @ nxt)
+    out2, red2, _, _ = run(lib, L, k, 1, world, states, psi, Jhop, Jz, h, mode=2, red=7, a=2.5, b=0.3, vprev=vprev, phi=phi, variant=variant)
+    assert np.array_equal(out, out2) and np.array_equal(red, red2)   # deterministic whatever the interleaving
