@@ -1170,14 +1170,11 @@ static int sd_halo_mirror(sd_model *m, int nc) {
     const size_t esz = (size_t)nc * sizeof(double);
     for (int g = 0; g < c->world; ++g) {
         if (g == c->rank || H.plan.need[g].empty()) continue;
-        const uint64_t p0 = m->blk.pstart[g], p1 = m->blk.pstart[g + 1];
-        const size_t vsz = (((size_t)(p1 - p0 + 2) * esz + gran - 1) / gran) * gran;
+        size_t vsz = 0;
+        std::vector<std::pair<uint64_t, uint64_t>> runs;               // byte ranges, granularity aligned (sd_halo_mirror_runs)
+        sd_halo_mirror_runs(H.plan, m->blk.pstart, g, esz, gran, &vsz, runs);
         SD_DRV(g_drv.MemAddressReserve(&M.va[g], vsz, gran, 0, 0));
         M.va_size[g] = vsz;
-        std::vector<std::pair<uint64_t, uint64_t>> runs;               // byte ranges, granularity aligned
-        for (auto [lo, hi] : H.plan.need[g])
-            runs.push_back({((lo - p0) * esz / gran) * gran, std::min<uint64_t>(vsz, (((hi - p0) * esz + gran - 1) / gran) * gran)});
-        sd_halo_merge(runs);
         for (auto [b0, b1] : runs) {
             CUmemGenericAllocationHandle h;
             SD_DRV(g_drv.MemCreate(&h, (size_t)(b1 - b0), &prop, 0));

@@ -132,6 +132,19 @@ static inline bool sd_halo_plan(const SdBlkHost &bh, const SdBlkParams &P, int n
     return true;
 }
 
+// Byte layout of the mirror of peer g (sd_halo_mirror in sd_api.cu): the virtual range covers the peer's whole shard
+// (vsz bytes, a multiple of the allocation granularity), physical memory is mapped under `runs` only: the needed element
+// ranges converted to bytes (esz = bytes per element) and rounded out to the granularity, merged.
+static inline void sd_halo_mirror_runs(const SdHaloPlan &plan, const uint64_t *pstart, int g, size_t esz, size_t gran,
+                                       size_t *vsz, std::vector<std::pair<uint64_t, uint64_t>> &runs) {
+    const uint64_t p0 = pstart[g], p1 = pstart[g + 1];
+    *vsz = (((size_t)(p1 - p0 + 2) * esz + gran - 1) / gran) * gran;
+    runs.clear();
+    for (auto [lo, hi] : plan.need[g])
+        runs.push_back({((lo - p0) * esz / gran) * gran, std::min<uint64_t>(*vsz, (((hi - p0) * esz + gran - 1) / gran) * gran)});
+    sd_halo_merge(runs);
+}
+
 // ---- shards weighted by their remote volume (SD_SHARD_BALANCE=1)
 // Equal rank ranges leave the ranks whose top prefix bits are 101 / 010 with 2.5 shards of inbound NVLink traffic at 8
 // ranks while the edge ranks pull 0.5.  With transfers overlapped (halo mirror) a rank's apply time is

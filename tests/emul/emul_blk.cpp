@@ -577,6 +577,32 @@ int emul_halo_plan(int L, int k, int world, int rank, int nchunks, uint64_t *sta
         if (!have[g].empty()) ++peers;
     }
     stats[0] = nseg; stats[1] = total; stats[2] = P.shards.pstart[rank + 1] - P.shards.pstart[rank]; stats[3] = peers; stats[4] = maxseg;
+    // mirror mapping (sd_halo_mirror_runs): every segment's bytes lie inside one mapped, granularity-aligned run of its peer
+    uint64_t mapped = 0;
+    for (int nc = 1; nc <= 2; ++nc) {
+        const size_t esz = (size_t)nc * 8, gran = (size_t)2 << 20;
+        for (int g = 0; g < world; ++g) {
+            if (g == rank || plan.need[g].empty()) continue;
+            size_t vsz = 0;
+            std::vector<std::pair<uint64_t, uint64_t>> runs;
+            sd_halo_mirror_runs(plan, P.shards.pstart, g, esz, gran, &vsz, runs);
+            if (vsz % gran || vsz < (P.shards.pstart[g + 1] - P.shards.pstart[g]) * esz) return -5;
+            for (size_t i = 0; i < runs.size(); ++i) {
+                if (runs[i].first % gran || runs[i].second % gran || runs[i].first >= runs[i].second || runs[i].second > vsz) return -5;
+                if (i && runs[i].first <= runs[i - 1].second) return -5;                            // merged
+                if (nc == 1) mapped += runs[i].second - runs[i].first;
+            }
+            for (int j = 0; j < nchunks; ++j)
+                for (const SdHaloSeg &sg : plan.segs[j]) {
+                    if (sg.peer != g) continue;
+                    const uint64_t b0 = (sg.lo - P.shards.pstart[g]) * esz, b1 = (sg.hi - P.shards.pstart[g]) * esz;
+                    bool ok = false;
+                    for (auto [r0, r1] : runs) if (r0 <= b0 && b1 <= r1) { ok = true; break; }
+                    if (!ok) return -5;
+                }
+        }
+    }
+    stats[5] = mapped;                                                 // bytes of physical mirror memory for f64 vectors
     return 0;
 }
 

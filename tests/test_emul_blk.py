@@ -368,6 +368,7 @@ def test_halo_mirror_plan(L, k, world, chunks):
         st = np.zeros(8, dtype=np.uint64)
         assert lib.emul_halo_plan(L, k, world, rank, chunks, P(st)) == 0, rank
         nseg, remote, local, peers, maxseg = (int(x) for x in st[:5])
+        assert remote * 8 <= int(st[5]) <= remote * 8 + 2 * nseg * (2 << 20)      # mirror memory: the ranges rounded out to 2 MB
         assert local > 0 and 1 <= peers <= world - 1 and nseg <= 8 * chunks and maxseg <= 12
         ratios.append(remote / local)
     if 2 * k == L and world in (2, 4, 8) and L <= 28:
