@@ -90,3 +90,11 @@ def test_julia_binding_matches_the_header():
         assert name in hdr, f"{name} is ccalled from Julia but not declared in include/spindyn.h"
         n = len([a for a in argt.split(",") if a.strip()])
         assert n == hdr[name], f"{name}: Julia passes {n} arguments, the header declares {hdr[name]}"
+
+
+def test_ctypes_signatures_have_the_headers_argument_counts():
+    """Every entry of spindyn._lib.SIGNATURES lists as many argument types as include/spindyn.h declares parameters."""
+    hdr = _header_arg_counts()
+    for name, argtypes in sd.SIGNATURES.items():
+        assert name in hdr, name
+        assert len(argtypes) == hdr[name], f"{name}: ctypes binds {len(argtypes)} arguments, the header declares {hdr[name]}"
