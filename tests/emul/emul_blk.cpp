@@ -378,7 +378,7 @@ int emul_blk_apply(int L, int k, const double *Jhop, const double *Jz, const dou
     P.W = bh.W.data(); P.js = bh.js.data(); P.units = bh.units.data(); P.items = bh.items.data(); P.dmid = bh.dmid.data();
     P.nbuf = 3; P.dbg = 0;
     const bool halo = (variant & 256) != 0;                          // + 256: through the halo mirror (sd_halo_host.h), 3 chunks
-    const bool balance = (variant & 512) != 0;                       // + 512: remote-volume-weighted shard bounds (sd_halo_balance)
+    // + 512: remote-volume-weighted shard bounds (sd_halo_balance), applied above where the bounds are computed
     const bool threaded = (variant & 1024) != 0;                     // + 1024: ring kernel as 16 host threads on a real, reused ring
     const int ndirect = (variant >> 12) & 15;                         // + 4096 * n: n nearest prefix entries read directly (ring kernel)
     variant &= 255;
