@@ -1,12 +1,12 @@
 #!/bin/bash
 # time + dram bytes of the block kernel under env settings. Usage: gpu_blk_ncu2.sh <tag> "ENV..." ...
 TAG=$1; shift; O=gpurun_out; mkdir -p $O
-B="python bench.py --steps 10 --warmup 3 --no-cpu --no-e2e"
-P="python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e"
+B="python bench.py --steps 10 --warmup 3 --no-cpu --no-e2e --no-solve"
+P="python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e --no-solve"
 M=dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct,l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed,sm__inst_executed.avg.per_cycle_elapsed,smsp__inst_executed.sum
 for e in "$@"; do
   r=$(env $e timeout 200 $B 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'])" 2>&1 | tail -1)
-  env $e timeout 600 ncu --metrics $M --clock-control none -k regex:sd_blkr?_apply -s 1 -c 1 --csv --log-file $O/n2.csv $P > /dev/null 2>&1
+  env $e timeout 600 ncu --metrics $M --clock-control none -k regex:sd_blkl?_apply -s 1 -c 1 --csv --log-file $O/n2.csv $P > /dev/null 2>&1
   d=$(python - <<PY
 import csv
 rows=[r for r in csv.reader(open("$O/n2.csv")) if len(r)>10]

@@ -23,8 +23,7 @@
 #include "sd_kernels.cuh"
 #include "sd_blk.h"
 #include "sd_blk_host.h"
-#include "sd_blkr.h"
-#include "sd_blkr_host.h"
+#include "sd_blkl.h"
 #include "sd_obs.h"
 #include "sd_bdot.cuh"
 #include "sd_halo_host.h"
@@ -184,8 +183,10 @@ struct SdBlkDev {
     int nbuf[2] = {0, 0};
     size_t smem[2] = {0, 0};
     int qfar[2] = {0, 0};
-    int variant = 0;                // item-body variant of sd_blk_apply_kernel (SD_BLK_VARIANT)
-    uint32_t *d_order = nullptr;    // optional L2-friendly tile order of this rank's shard (SD_BLK_ORDER=1)
+    int kernel = 1;                 // 1: sd_blkl_apply_kernel (lean, default); 0: sd_blk_apply_kernel (round-1 body; SD_BLK_KERNEL=0)
+    int threads = 640;              // CTA size of the lean kernel (SD_BLKL_THREADS = 512 | 640 | 768)
+    int dbg = 0;                    // profiling switches of the round-1 body (SD_BLK_DBG), read once at model creation
+    uint32_t *d_order = nullptr;    // breadth-first tile order of this rank's shard (vectors larger than the L2)
     uint32_t norder = 0;
     // halo mirror of sharded applies (SD_HALO=1, sd_halo_host.h): chunked copy-engine prefetch of the peer ranges the
     // tile headers point at into a sparse local mapping with the peers' own offsets
@@ -203,10 +204,6 @@ struct SdBlkDev {
         cudaEvent_t ev_ready = nullptr;
         std::vector<cudaEvent_t> ev;
     } halo;
-    bool ring = false;              // f64 applies run sd_blkr_apply_kernel (SD_BLK_RING=1; sd_blkr.h)
-    SdBlkrWarp *d_rw = nullptr;     // [(B+1)*15] item -> consumer warp packing of the ring kernel
-    int ring_direct = 0;            // nearest prefix entries per tile read straight from L2 by the consumers (SD_BLKR_DIRECT)
-    size_t ring_smem = 0;
 };
 
 struct SdTileDev {
@@ -346,7 +343,7 @@ static int sd_ctx_init(int device, int rank, int world, const void *id128, sd_ct
     SD_CUDA(cudaMalloc(&c->d_scal, SD_NSCAL * sizeof(double)));
     SD_CUDA(cudaMemset(c->d_scal, 0, SD_NSCAL * sizeof(double)));
     SD_CUDA(cudaMallocHost(&c->h_scal, SD_NSCAL * sizeof(double)));
-    SD_CUDA(cudaMalloc(&c->d_tilectr, 16 * sizeof(unsigned long long)));   // [0] tile counter, [1..6] ring-kernel watchdog record
+    SD_CUDA(cudaMalloc(&c->d_tilectr, 16 * sizeof(unsigned long long)));   // [0]: tile counter of the block kernels' dynamic scheduler
     if (world > 1) {
         SD_ARG(id128, "id128 is NULL");
         SD_TRY(sd_nccl_load());
@@ -496,27 +493,22 @@ static int sd_blk_setup(sd_model *m) {
     for (size_t i = 0; i < m->hop_a.size(); ++i) Jhop[m->hop_a[i]] += m->hop_J[i];
     for (size_t i = 0; i < m->zz_a.size(); ++i) Jz[m->zz_a[i]] += m->zz_J[i];
     if (!sd_blk_build(L, m->k, Jhop.data(), Jz.data(), m->field.data(), b.host)) return SD_OK;
+    b.kernel = sd_env_int("SD_BLK_KERNEL", 1) ? 1 : 0;
+    b.threads = sd_env_int("SD_BLKL_THREADS", 640);
+    if (b.threads != 512 && b.threads != 768) b.threads = 640;
+    b.dbg = sd_env_int("SD_BLK_DBG", 0);
     for (int w = 0; w < 2; ++w) {
         const int nc = w + 1;
-        int nbuf = sd_env_int(w == 0 ? "SD_BLK_NBUF" : "SD_BLK_NBUF_C128", w == 0 ? 3 : 2);
+        int nbuf = w == 0 ? 3 : 2;
         for (; nbuf >= 2; --nbuf) {
-            b.smem[w] = sd_blk_smem_carve(nullptr, nullptr, b.host.P.A, L, nbuf, b.host.P.cap, nc);
-            if (b.smem[w] <= 227 * 1024) break;
+            // lean kernel: the tile buffers are the dynamic part, tables and headers are static (sizeof(SdBlkShared))
+            b.smem[w] = b.kernel ? (size_t)nbuf * b.host.P.cap * nc * sizeof(double)
+                                 : sd_blk_smem_carve(nullptr, nullptr, b.host.P.A, L, nbuf, b.host.P.cap, nc);
+            if (b.smem[w] + (b.kernel ? sizeof(SdBlkShared) + 128 : 0) <= 227 * 1024) break;
         }
         if (nbuf < 2) return SD_OK;
         b.nbuf[w] = nbuf;
         b.qfar[w] = sd_tile_qfar(L, b.host.P.A, b.host.binom.data(), (uint64_t)sd_env_int("SD_FAR_MB", 100) << 20, 8 * nc);
-    }
-    b.variant = sd_env_int("SD_BLK_VARIANT", SD_BLK_DEFAULT_VARIANT) == 1 ? 1 : 0;
-    b.ring = false;
-    if (sd_env_int("SD_BLK_RING", 0)) {                             // experimental: ring kernel for f64 (sd_blkr.h)
-        std::vector<SdBlkrWarp> rw;
-        b.ring_smem = sd_blkr_smem_carve(nullptr, nullptr, b.host.P.A, L, b.host.P.cap);
-        if (sd_blkr_build(b.host, rw) && b.ring_smem <= 227 * 1024) {
-            SD_TRY(sd_to_device(&b.d_rw, rw));
-            b.ring = true;
-            b.ring_direct = std::max(0, std::min(SD_BLK_MAXA, sd_env_int("SD_BLKR_DIRECT", 0)));
-        }
     }
     SD_TRY(sd_to_device(&b.d_W, b.host.W));
     SD_TRY(sd_to_device(&b.d_js, b.host.js));
@@ -533,7 +525,7 @@ static SdBlkParams sd_blk_params(const sd_model *m, int nc) {
     SdBlkParams P = m->blk.host.P;
     const sd_ctx *c = m->ctx;
     P.nbuf = m->blk.nbuf[nc - 1];
-    P.dbg = sd_env_int("SD_BLK_DBG", 0);
+    P.dbg = m->blk.dbg;
     P.order = m->blk.d_order; P.norder = m->blk.norder;
     P.key_lo = m->tile[0].keys[c->rank];
     P.key_hi = m->tile[0].keys[c->rank + 1];
@@ -664,11 +656,11 @@ int sd_model_create(sd_ctx *ctx, int L, int nup, const sd_bond *hop, int nhop, c
     if (m->blk.ok)
         for (int g = 0; g <= ctx->world; ++g) m->blk.pstart[g] = sd_blk_key_base(m->blk.host, m->tile[0].keys[g]);
     m->blk_layout = (m->path == SD_PATH_BLOCK);
-    if (m->blk.ok && sd_env_int("SD_BLK_ORDER", 0)) {               // experimental: L2-friendly tile order (sd_blk_tile_order)
+    // Breadth-first tile order (sd_blk_tile_order) once a vector no longer fits the L2: measured 14.7 GB instead of 22.4 GB
+    // of DRAM reads per L = 32 apply (profiles/round2_a_ab.txt).  SD_BLK_ORDER=0 keeps rank order (A/B only).
+    if (m->blk.ok && m->blk.host.n_store * sizeof(double) > ((size_t)48 << 20) && sd_env_int("SD_BLK_ORDER", 2) != 0) {
         std::vector<uint32_t> ord;
-        const int omode = sd_env_int("SD_BLK_ORDER", 0) == 2 ? 2 : 1;   // 1: greedy chain (e = 12), 2: breadth-first (e = A - 1)
-        sd_blk_tile_order(m->blk.host, m->tile[0].keys[ctx->rank], m->tile[0].keys[ctx->rank + 1],
-                          sd_env_int("SD_BLK_ORDER_E", omode == 2 ? m->blk.host.P.A - 1 : 12), ord, omode);
+        sd_blk_tile_order(m->blk.host, m->tile[0].keys[ctx->rank], m->tile[0].keys[ctx->rank + 1], m->blk.host.P.A - 1, ord);
         if (!ord.empty()) {
             SD_TRY(sd_to_device(&m->blk.d_order, ord));
             m->blk.norder = (uint32_t)ord.size();
@@ -694,7 +686,7 @@ int sd_model_free(sd_model *m) {
         cudaFree(t.d_perm); cudaFree(t.d_items); cudaFree(t.d_binomM);
     }
     if (m->blk.halo.on || m->blk.halo.copy_stream) sd_halo_free(m);
-    cudaFree(m->blk.d_order); cudaFree(m->blk.d_rw);
+    cudaFree(m->blk.d_order);
     cudaFree(m->blk.d_W); cudaFree(m->blk.d_js); cudaFree(m->blk.d_units); cudaFree(m->blk.d_items); cudaFree(m->blk.d_dmid);
     delete m;
     return SD_OK;
@@ -1200,7 +1192,7 @@ static void sd_halo_free(sd_model *m) {
     if (H.copy_stream) cudaStreamDestroy(H.copy_stream);
     H.ev_ready = nullptr; H.copy_stream = nullptr; H.on = false;
 }
-// one launch of the block kernel (standard or ring, the model's item-body variant) over the tile keys of P
+// one launch of the block-layout apply over the tile keys [P.key_lo, P.key_hi) (or P.order)
 static int sd_blk_launch_range(sd_model *m, int nc, const SdBlkParams &P, const SdVecView &view, double *out_local,
                                const SdEpi &epi, bool plain) {
     sd_ctx *c = m->ctx;
@@ -1209,31 +1201,27 @@ static int sd_blk_launch_range(sd_model *m, int nc, const SdBlkParams &P, const 
     const unsigned grid = (unsigned)std::min<uint64_t>(nkeys, (uint64_t)c->sm_count);
     SD_CUDA(cudaMemsetAsync(c->d_tilectr, 0, 16 * sizeof(unsigned long long), c->stream));
     const int qfar = m->blk.qfar[nc - 1];
-    if (nc == 1 && m->blk.ring) {
-        const size_t rsmem = m->blk.ring_smem;
-        if (plain) {
-            SD_CUDA(cudaFuncSetAttribute(sd_blkr_apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
-            sd_blkr_apply_kernel<true><<<grid, SD_BLK_THREADS, rsmem, c->stream>>>(P, view, out_local, epi, qfar, c->d_tilectr, m->blk.d_rw, m->blk.ring_direct);
-        } else {
-            SD_CUDA(cudaFuncSetAttribute(sd_blkr_apply_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
-            sd_blkr_apply_kernel<false><<<grid, SD_BLK_THREADS, rsmem, c->stream>>>(P, view, out_local, epi, qfar, c->d_tilectr, m->blk.d_rw, m->blk.ring_direct);
-        }
-        return sd_launch_check(c, "sd_blkr_apply_kernel");
-    }
     const size_t smem = m->blk.smem[nc - 1];
-#define SD_HL(NC_, PLAIN_, V_)                                                                               \
+    // the shared-memory attribute is per device and cheap to set: no process-global "already set" cache
+#define SD_HL(KERNEL_, THREADS_)                                                                             \
     do {                                                                                                     \
-        SD_CUDA(cudaFuncSetAttribute(sd_blk_apply_kernel<NC_, PLAIN_, V_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        sd_blk_apply_kernel<NC_, PLAIN_, V_><<<grid, SD_BLK_THREADS, smem, c->stream>>>(P, view, out_local, epi, qfar, c->d_tilectr); \
+        SD_CUDA(cudaFuncSetAttribute(KERNEL_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+        KERNEL_<<<grid, THREADS_, smem, c->stream>>>(P, view, out_local, epi, qfar, c->d_tilectr);           \
     } while (0)
-    const int v1 = m->blk.variant == 1;
-    if (nc == 1) {
-        if (plain) { if (v1) SD_HL(1, true, 1); else SD_HL(1, true, 0); }
-        else { if (v1) SD_HL(1, false, 1); else SD_HL(1, false, 0); }
-    } else {
-        if (plain) { if (v1) SD_HL(2, true, 1); else SD_HL(2, true, 0); }
-        else { if (v1) SD_HL(2, false, 1); else SD_HL(2, false, 0); }
+#define SD_HL_LEAN(NC_, PLAIN_)                                                                              \
+    do {                                                                                                     \
+        if (m->blk.threads == 512) SD_HL((sd_blkl_apply_kernel<NC_, PLAIN_, 512>), 512);                     \
+        else if (m->blk.threads == 768) SD_HL((sd_blkl_apply_kernel<NC_, PLAIN_, 768>), 768);                \
+        else SD_HL((sd_blkl_apply_kernel<NC_, PLAIN_, 640>), 640);                                           \
+    } while (0)
+    if (m->blk.kernel) {
+        if (nc == 1) { if (plain) SD_HL_LEAN(1, true); else SD_HL_LEAN(1, false); }
+        else { if (plain) SD_HL_LEAN(2, true); else SD_HL_LEAN(2, false); }
+        return sd_launch_check(c, "sd_blkl_apply_kernel");
     }
+    if (nc == 1) { if (plain) SD_HL((sd_blk_apply_kernel<1, true, 0>), SD_BLK_THREADS); else SD_HL((sd_blk_apply_kernel<1, false, 0>), SD_BLK_THREADS); }
+    else { if (plain) SD_HL((sd_blk_apply_kernel<2, true, 0>), SD_BLK_THREADS); else SD_HL((sd_blk_apply_kernel<2, false, 0>), SD_BLK_THREADS); }
+#undef SD_HL_LEAN
 #undef SD_HL
     return sd_launch_check(c, "sd_blk_apply_kernel");
 }
@@ -1312,50 +1300,8 @@ static int sd_apply_impl(sd_model *m, sd_vec *out, const sd_vec *psi, SdEpi epi,
         }
         epi.partials = c->d_partials;
         epi.nparts = (unsigned)nkeys;
-        SD_CUDA(cudaMemsetAsync(c->d_tilectr, 0, 16 * sizeof(unsigned long long), c->stream));
-        const size_t smem = m->blk.smem[nc - 1];
-        const int qfar = m->blk.qfar[nc - 1];
         const bool plain = epi.mode == SD_EPI_PLAIN && epi.red == 0 && !epi.acc && epi.hscale == 1.0;
-#define SD_LAUNCH_BLK3(NC_, PLAIN_, V_)                                                                      \
-    do {                                                                                                     \
-        static size_t set_smem = 0;                                                                          \
-        if (smem > set_smem) {                                                                               \
-            SD_CUDA(cudaFuncSetAttribute(sd_blk_apply_kernel<NC_, PLAIN_, V_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            set_smem = smem;                                                                                 \
-        }                                                                                                    \
-        sd_blk_apply_kernel<NC_, PLAIN_, V_><<<grid, SD_BLK_THREADS, smem, c->stream>>>(P, psi->view, out->d, epi, qfar, c->d_tilectr); \
-    } while (0)
-#define SD_LAUNCH_BLK(NC_, PLAIN_)                                                                           \
-    do {                                                                                                     \
-        if (m->blk.variant == 1) SD_LAUNCH_BLK3(NC_, PLAIN_, 1);                                             \
-        else SD_LAUNCH_BLK3(NC_, PLAIN_, 0);                                                                 \
-    } while (0)
-#define SD_LAUNCH_RING(PLAIN_)                                                                               \
-    do {                                                                                                     \
-        static size_t set_smem = 0;                                                                          \
-        const size_t rsmem = m->blk.ring_smem;                                                               \
-        if (rsmem > set_smem) {                                                                              \
-            SD_CUDA(cudaFuncSetAttribute(sd_blkr_apply_kernel<PLAIN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem)); \
-            set_smem = rsmem;                                                                                \
-        }                                                                                                    \
-        sd_blkr_apply_kernel<PLAIN_><<<grid, SD_BLK_THREADS, rsmem, c->stream>>>(P, psi->view, out->d, epi, qfar, c->d_tilectr, m->blk.d_rw, m->blk.ring_direct); \
-    } while (0)
-        if (nc == 1 && m->blk.ring) { if (plain) SD_LAUNCH_RING(true); else SD_LAUNCH_RING(false); }
-        else if (nc == 1) { if (plain) SD_LAUNCH_BLK(1, true); else SD_LAUNCH_BLK(1, false); }
-        else { if (plain) SD_LAUNCH_BLK(2, true); else SD_LAUNCH_BLK(2, false); }
-#undef SD_LAUNCH_RING
-#undef SD_LAUNCH_BLK
-#undef SD_LAUNCH_BLK3
-        SD_TRY(sd_launch_check(c, "sd_blk_apply_kernel"));
-        if (nc == 1 && m->blk.ring && (P.dbg & 64)) {                 // diagnostic mode of the ring kernel's watchdog
-            unsigned long long rec[8] = {0};
-            SD_CUDA(cudaMemcpyAsync(rec, c->d_tilectr, sizeof(rec), cudaMemcpyDeviceToHost, c->stream));
-            SD_CUDA(cudaStreamSynchronize(c->stream));
-            if (rec[1] != 0)
-                return sd_fail(SD_ERR_CUDA, "ring kernel watchdog: CTA %llu warp %llu stuck at entry %llu (wait tag %llu: 1/2 producer on empty, "
-                               "3/4/5 consumer on full), tile number %llu of the CTA; tiles handed out: %llu of %llu",
-                               rec[2], rec[3], rec[4], rec[5], rec[6], rec[0], (unsigned long long)nkeys);
-        }
+        SD_TRY(sd_blk_launch_range(m, nc, P, psi->view, out->d, epi, plain));
         if (slotmask) SD_TRY(sd_finish_reduce(c, (unsigned)nkeys, slotmask, slot_out));
     } else if (m->path == SD_PATH_TILED) {
         SdTileDev &t = m->tile[nc - 1];

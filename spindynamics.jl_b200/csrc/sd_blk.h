@@ -40,6 +40,9 @@
 #define SD_BLK_MAXA 32
 #define SD_BLK_MAXUNITS 64      // work items per tile: (unit of 32 mid configurations, element chunk); <= 32 (f64), <= 47 (c128)
 #define SD_BLK_THREADS 512
+#ifndef SD_BLK_LB
+#define SD_BLK_LB SD_BLK_THREADS
+#endif
 #define SD_BLK_CWARPS 15        // consumer warps; warp 15 is the producer
 #define SD_BLK_DEFAULT_VARIANT 0   // item-body variant launched by default (SD_BLK_VARIANT overrides); see sd_blk_item
 
@@ -361,7 +364,19 @@ struct SdBlkCtx {
     double *out_local;          // local shard of out, component 0 of stored element 0
     uint64_t pstart_local;      // stored-element offset of the local shard
     const SdEpi *epi;
+    const SdBlkItem *items;     // = P->items (the lean body does not touch P)
+    int A;
 };
+SD_HD void sd_blk_ctx_init(SdBlkCtx &X, const SdBlkParams &P, const SdBlkJs *js, const double *dmid, const double *dtail,
+                           const double *Jhop, double *out_local, const SdEpi *epi) {
+    X.P = &P; X.js = js; X.dmid = dmid; X.dtail = dtail; X.Jhop = Jhop;
+    X.qx = P.Jz[P.A + SD_BLK_M - 1] * 0.25;
+    X.pstart_local = P.shards.pstart[P.shards.rank];
+    X.out_local = out_local;
+    X.epi = epi;
+    X.items = P.items;
+    X.A = P.A;
+}
 
 // Everything except sd_blk_tail is generic in (jt, S0), which keeps the code small enough for the
 // instruction cache (15 warps run different items at the same time).
@@ -393,7 +408,7 @@ SD_HD void sd_blk_item(const SdBlkCtx &X, const SdBlkHdr &H, const double *tb, i
     //   entries 0 .. nnb-1 : prefix-internal bonds, whole neighbour tiles in the same element order
     //   entry   nnb        : prefix|mid crossing bond (partner tile with js +- 1, same class, uniform
     //                        block shift), only for lanes whose first mid bit differs from the last prefix bit
-    const int nnb = (V == 0 && (P.dbg & 1)) ? 0 : H.nnb;
+    const int nnb = (P.dbg & 1) ? 0 : H.nnb;
     const bool hasx = H.xptr != nullptr;
     const int ntot = nnb + (hasx ? 1 : 0);
     const double *xp = nullptr;
@@ -407,10 +422,6 @@ SD_HD void sd_blk_item(const SdBlkCtx &X, const SdBlkHdr &H, const double *tb, i
         xp = H.xptr + (size_t)(cx.cb * NC + 2u * xu) + (size_t)S0 * xs;
     }
     double2 t0[EC], t1[EC], t2[EC];
-    if (V != 0) {
-#pragma unroll
-        for (int s = 0; s < EC; ++s) t0[s] = t1[s] = t2[s] = make_double2(0.0, 0.0);
-    }
     // V = 0: every load guarded and zero filled, coefficient selected per entry
 #define SD_BLK_LOAD(t_, n_)                                                                   \
     do {                                                                                      \
@@ -431,30 +442,7 @@ SD_HD void sd_blk_item(const SdBlkCtx &X, const SdBlkHdr &H, const double *tb, i
         const double J_ = nn_ < nnb ? H.nb_J[nn_] : (nn_ == nnb && hasx ? H.Jx : 0.0);        \
         _Pragma("unroll") for (int s = 0; s < EC; ++s) { acc[s].x += J_ * t_[s].x; acc[s].y += J_ * t_[s].y; } \
     } while (0)
-    // V = 1: a load that does not exist leaves its registers alone (zero at first, finite old data later) and
-    // its coefficient is 0: H.nb_J is zero padded behind entry ntot-1, the crossing entry counts only for xlane
-#define SD_BLK_LOAD1(t_, n_)                                                                  \
-    do {                                                                                      \
-        const int nn_ = (n_);                                                                 \
-        const bool isx_ = hasx && nn_ == nnb;                                                 \
-        if (nn_ < ntot && (!isx_ || xlane)) {                                                 \
-            const double *p_ = isx_ ? xp : H.nb_ptr[nn_] + offc;                              \
-            const uint32_t st_ = isx_ ? xs : ss;                                              \
-            _Pragma("unroll") for (int s = 0; s < EC; ++s) {                                  \
-                if (HALF && s == EC - 1) t_[s] = sd_blk_ldg_half(p_ + s * st_ - (isx_ ? xu : u)); \
-                else t_[s] = sd_blk_ldg(p_ + s * st_);                                        \
-            }                                                                                 \
-        }                                                                                     \
-    } while (0)
-#define SD_BLK_FMA1(t_, n_)                                                                   \
-    do {                                                                                      \
-        const int nn_ = (n_);                                                                 \
-        double J_ = H.nb_J[nn_];                                                              \
-        if (hasx && nn_ == nnb && !xlane) J_ = 0.0;                                           \
-        _Pragma("unroll") for (int s = 0; s < EC; ++s) { acc[s].x += J_ * t_[s].x; acc[s].y += J_ * t_[s].y; } \
-    } while (0)
-    if (V == 0) { SD_BLK_LOAD(t0, 0); SD_BLK_LOAD(t1, 1); SD_BLK_LOAD(t2, 2); }
-    else { SD_BLK_LOAD1(t0, 0); SD_BLK_LOAD1(t1, 1); SD_BLK_LOAD1(t2, 2); }
+    SD_BLK_LOAD(t0, 0); SD_BLK_LOAD(t1, 1); SD_BLK_LOAD(t2, 2);
     // ---- own block: diagonal + tail-internal hops (registers)
     const unsigned cmid = it.w & ((1u << M) - 1u);
     const bool clast = (cmid >> (M - 1)) & 1u;
@@ -502,7 +490,7 @@ SD_HD void sd_blk_item(const SdBlkCtx &X, const SdBlkHdr &H, const double *tb, i
             }                                                                                 \
         }                                                                                     \
     } while (0)
-    if (V == 0) {
+    {
         uint32_t hi = it.z;
         int pm = (P.dbg & 2) ? M : 0;
 #define SD_BLK_MID()                                                                          \
@@ -525,34 +513,10 @@ SD_HD void sd_blk_item(const SdBlkCtx &X, const SdBlkHdr &H, const double *tb, i
 #pragma unroll 1
         while (pm + 1 < M) SD_BLK_MID();
 #undef SD_BLK_MID
-    } else {
-        // active mid bonds of the item: bits of nb[9..10] (sd_blk_build); lowest set bit first
-        uint32_t am = (P.dbg & 2) ? 0u : ((it.z >> 8) & 0xFFFFu);
-#define SD_BLK_MID1()                                                                         \
-    do {                                                                                      \
-        const int pm = SD_POPC32((am & (0u - am)) - 1u);                                      \
-        am &= am - 1u;                                                                        \
-        const unsigned nbu = pm < 8 ? (unsigned)((lo >> (8 * pm)) & 0xFFu) : (it.z & 0xFFu);  \
-        const double J = X.Jhop[P.A + pm];                                                    \
-        SD_BLK_MID_BODY(J, nbu);                                                              \
-    } while (0)
-#pragma unroll 1
-        for (int n = 0; n < ntot; n += 3) {
-#pragma unroll 1
-            for (int k = 0; k < 2 && am != 0u; ++k) SD_BLK_MID1();
-            SD_BLK_FMA1(t0, n); SD_BLK_LOAD1(t0, n + 3);
-            SD_BLK_FMA1(t1, n + 1); SD_BLK_LOAD1(t1, n + 4);
-            SD_BLK_FMA1(t2, n + 2); SD_BLK_LOAD1(t2, n + 5);
-        }
-#pragma unroll 1
-        while (am != 0u) SD_BLK_MID1();
-#undef SD_BLK_MID1
     }
 #undef SD_BLK_MID_BODY
 #undef SD_BLK_LOAD
 #undef SD_BLK_FMA
-#undef SD_BLK_LOAD1
-#undef SD_BLK_FMA1
     // ---- mid|tail crossing bond, per tail configuration.  Tail configurations with bit 0 set come first
     // in a class: n1 = C(T-1, jt-1) of them.  Last mid bit set & tail bit 0 clear -> class jt+1,
     // configuration e - n1; last mid bit clear & tail bit 0 set -> class jt-1, configuration C(T-1, jt-2) + e.
@@ -733,6 +697,95 @@ __device__ __forceinline__ void sd_stg_v2(double *p, double2 v) {
 }
 
 // ------------------------------------------------------------------ the kernel
+// one-time setup of a CTA: tables -> shared memory, mbarriers
+template <int NC>
+__device__ __forceinline__ void sd_blk_cta_setup(const SdBlkParams &P, const SdBlkSmem &S, unsigned tid, unsigned nthr, unsigned ncons) {
+    for (int i = (int)tid; i < P.A * (P.A + 1); i += nthr) S.W[i] = P.W[i];
+    {
+        const uint32_t *src = (const uint32_t *)P.js;
+        uint32_t *dst = (uint32_t *)S.js;
+        for (int i = (int)tid; i < (int)(sizeof(SdBlkJs) * (SD_BLK_B + 1) / 4); i += nthr) dst[i] = src[i];
+    }
+    for (int i = (int)tid; i < (SD_BLK_B + 1) * SD_BLK_MAXUNITS; i += nthr)
+        S.units[i] = P.units[(NC - 1) * (SD_BLK_B + 1) * SD_BLK_MAXUNITS + i];
+    for (int i = (int)tid; i < (1 << SD_BLK_M); i += nthr) S.dmid[i] = P.dmid[i];
+    for (int i = (int)tid; i < (1 << SD_BLK_T); i += nthr) S.dtail[i] = P.dtail[i];
+    for (int i = (int)tid; i <= P.L; i += nthr) S.Jhop[i] = P.Jhop[i];
+    if (tid == 0) {
+        for (int b = 0; b < P.nbuf; ++b) { sd_mbar_init(&S.full[b], 1); sd_mbar_init(&S.empty[b], ncons); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+}
+// producer warp: tile keys from the global counter, tile headers, TMA of the own tiles
+template <int NC>
+__device__ __forceinline__ void sd_blk_producer(const SdBlkParams &P, const SdBlkSmem &S, const SdVecView &psi, int qfar,
+                                                unsigned long long *tile_ctr, unsigned lane) {
+    const int nbuf = P.nbuf;
+    const size_t tile_doubles = (size_t)P.cap * NC;
+    for (unsigned i = 0;; ++i) {
+        const int b = (int)(i % (unsigned)nbuf);
+        const unsigned round = i / (unsigned)nbuf;
+        uint64_t key;
+        for (;;) {                                             // next valid tile of this shard
+            unsigned long long t = 0;
+            if (lane == 0) t = atomicAdd(tile_ctr, 1ULL);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            if (P.order != nullptr) {                          // explicit tile order (valid tiles only, sd_blk_tile_order)
+                key = t < (unsigned long long)P.norder ? (uint64_t)P.order[t] : P.key_hi;
+                break;
+            }
+            key = P.key_lo + t;
+            if (key >= P.key_hi) break;
+            const uint64_t Pb = __brevll(~key) >> (64 - P.A);
+            const int js = P.k - __popcll(Pb);
+            if (js >= 0 && js <= SD_BLK_B) break;              // else: impossible suffix popcount
+        }
+        sd_mbar_wait(&S.empty[b], (round & 1u) ^ 1u);          // consumers released this buffer
+        SdBlkHdr &H = S.hdr[b];
+        if (key >= P.key_hi) {
+            if (lane == 0) { H.valid = -1; }
+            __syncwarp();
+            if (lane == 0) sd_mbar_arrive(&S.full[b]);
+            break;
+        }
+        sd_blk_make_hdr<NC>(P, S.W, key, H, psi, qfar, lane);
+        __syncwarp();
+        const uint32_t bytes = S.js[H.js].size_pad * (uint32_t)(NC * 8);
+        const char *src = (const char *)(psi.base[P.shards.rank] + (size_t)NC * H.base);
+        char *dst = (char *)(S.tiles + (size_t)b * tile_doubles);
+        if (lane == 0) sd_mbar_expect_tx(&S.full[b], bytes);
+        __syncwarp();
+        constexpr uint32_t CH = 8192;
+        for (uint32_t o = lane * CH; o < bytes; o += 32 * CH)
+            sd_bulk_g2s(dst + o, src + o, (bytes - o < CH) ? bytes - o : CH, &S.full[b]);
+    }
+}
+// per-item tail of a consumer warp: warp sums of the fused reductions, ordered per-tile sum by the last item
+__device__ __forceinline__ void sd_blk_item_reduce(SdBlkHdr &H, const SdEpi &epi, int slotmask, unsigned un, unsigned nunits,
+                                                   const double (&red)[SD_NSLOT], unsigned lane) {
+#pragma unroll
+    for (int s = 0; s < SD_NSLOT; ++s) {
+        if (!((slotmask >> s) & 1)) continue;
+        double w = red[s];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) w += __shfl_down_sync(0xffffffffu, w, o);
+        if (lane == 0) H.usum[s][un] = w;
+    }
+    if (lane == 0) {
+        __threadfence_block();
+        const unsigned done = atomicAdd(&H.done_units, 1u);
+        if (done + 1 == nunits) {                              // last item of the tile: ordered sum
+            __threadfence_block();
+            for (int s = 0; s < SD_NSLOT; ++s) {
+                if (!((slotmask >> s) & 1)) continue;
+                double t = 0.0;
+                for (unsigned j = 0; j < nunits; ++j) t += ((volatile double *)H.usum[s])[j];
+                epi.partials[(size_t)s * epi.nparts + H.tile_index] = t;
+            }
+        }
+    }
+}
+
 // grid = one persistent CTA per SM.  Tiles are handed out in key (= rank) order by a global counter, so
 // the tiles in flight form a tight window and near neighbour tiles are re-used from L2.
 // partials: [SD_NSLOT][ntiles] per-tile sums (zero-filled by the host before the launch: invalid tiles
@@ -746,84 +799,15 @@ sd_blk_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constant
     sd_blk_smem_carve(&S, sd_blk_smem, P.A, P.L, P.nbuf, P.cap, NC);
     const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
     const int nbuf = P.nbuf;
-    // ---- one-time setup
-    for (int i = (int)tid; i < P.A * (P.A + 1); i += SD_BLK_THREADS) S.W[i] = P.W[i];
-    {
-        const uint32_t *src = (const uint32_t *)P.js;
-        uint32_t *dst = (uint32_t *)S.js;
-        for (int i = (int)tid; i < (int)(sizeof(SdBlkJs) * (SD_BLK_B + 1) / 4); i += SD_BLK_THREADS) dst[i] = src[i];
-    }
-    for (int i = (int)tid; i < (SD_BLK_B + 1) * SD_BLK_MAXUNITS; i += SD_BLK_THREADS)
-        S.units[i] = P.units[(NC - 1) * (SD_BLK_B + 1) * SD_BLK_MAXUNITS + i];
-    for (int i = (int)tid; i < (1 << SD_BLK_M); i += SD_BLK_THREADS) S.dmid[i] = P.dmid[i];
-    for (int i = (int)tid; i < (1 << SD_BLK_T); i += SD_BLK_THREADS) S.dtail[i] = P.dtail[i];
-    for (int i = (int)tid; i <= P.L; i += SD_BLK_THREADS) S.Jhop[i] = P.Jhop[i];
-    if (tid == 0) {
-        for (int b = 0; b < nbuf; ++b) { sd_mbar_init(&S.full[b], 1); sd_mbar_init(&S.empty[b], SD_BLK_CWARPS); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
+    sd_blk_cta_setup<NC>(P, S, tid, SD_BLK_THREADS, SD_BLK_CWARPS);
     __syncthreads();
     const size_t tile_doubles = (size_t)P.cap * NC;
-
     if (warp == SD_BLK_CWARPS) {
-        // ================= producer warp: tile keys, headers, TMA of the own tiles, L2 prefetch of far tiles
-        for (unsigned i = 0;; ++i) {
-            const int b = (int)(i % (unsigned)nbuf);
-            const unsigned round = i / (unsigned)nbuf;
-            uint64_t key;
-            for (;;) {                                             // next valid tile of this shard
-                unsigned long long t = 0;
-                if (lane == 0) t = atomicAdd(tile_ctr, 1ULL);
-                t = __shfl_sync(0xffffffffu, t, 0);
-                if (P.order != nullptr) {                          // explicit tile order (valid tiles only, sd_blk_tile_order)
-                    key = t < (unsigned long long)P.norder ? (uint64_t)P.order[t] : P.key_hi;
-                    break;
-                }
-                key = P.key_lo + t;
-                if (key >= P.key_hi) break;
-                const uint64_t Pb = __brevll(~key) >> (64 - P.A);
-                const int js = P.k - __popcll(Pb);
-                if (js >= 0 && js <= SD_BLK_B) break;              // else: impossible suffix popcount
-            }
-            sd_mbar_wait(&S.empty[b], (round & 1u) ^ 1u);          // consumers released this buffer
-            SdBlkHdr &H = S.hdr[b];
-            if (key >= P.key_hi) {
-                if (lane == 0) { H.valid = -1; }
-                __syncwarp();
-                if (lane == 0) sd_mbar_arrive(&S.full[b]);
-                break;
-            }
-            sd_blk_make_hdr<NC>(P, S.W, key, H, psi, qfar, lane);
-            __syncwarp();
-            const uint32_t bytes = S.js[H.js].size_pad * (uint32_t)(NC * 8);
-            const char *src = (const char *)(psi.base[P.shards.rank] + (size_t)NC * H.base);
-            char *dst = (char *)(S.tiles + (size_t)b * tile_doubles);
-            if (lane == 0) sd_mbar_expect_tx(&S.full[b], bytes);
-            __syncwarp();
-            constexpr uint32_t CH = 8192;
-            for (uint32_t o = lane * CH; o < bytes; o += 32 * CH)
-                sd_bulk_g2s(dst + o, src + o, (bytes - o < CH) ? bytes - o : CH, &S.full[b]);
-            if (P.dbg & 8) {                                       // (off: measured +6 GB of DRAM reads) far neighbour tiles: DRAM -> L2 ahead of the consumers
-                const int nfar = H.nfar;
-                if ((int)lane < nfar) {
-                    const double *p = H.nb_ptr[lane];
-                    const double *lo = psi.base[P.shards.rank] + (size_t)NC * P.shards.pstart[P.shards.rank];
-                    const double *hi = psi.base[P.shards.rank] + (size_t)NC * P.shards.pstart[P.shards.rank + 1];
-                    if (p >= lo && p < hi) {
-                        if (P.dbg & 32) sd_bulk_prefetch_l2(p, bytes);
-                        else sd_bulk_prefetch_l2_evict_first(p, bytes);
-                    }
-                }
-            }
-        }
+        sd_blk_producer<NC>(P, S, psi, qfar, tile_ctr, lane);
     } else {
         // ================= consumer warps
         SdBlkCtx X;
-        X.P = &P; X.js = S.js; X.dmid = S.dmid; X.dtail = S.dtail; X.Jhop = S.Jhop;
-        X.qx = P.Jz[P.A + SD_BLK_M - 1] * 0.25;
-        X.pstart_local = P.shards.pstart[P.shards.rank];
-        X.out_local = out_local;
-        X.epi = &epi;
+        sd_blk_ctx_init(X, P, S.js, S.dmid, S.dtail, S.Jhop, out_local, &epi);
         const int slotmask = PLAIN ? 0 : sd_epi_slotmask(epi.red);
         for (unsigned i = 0;; ++i) {
             const int b = (int)(i % (unsigned)nbuf);
@@ -843,29 +827,7 @@ sd_blk_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constant
                 const uint32_t u = (code & 0xFFu) * 32u + lane;      // the lane's mid configuration
                 double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
                 sd_blk_dispatch<NC, PLAIN, V>(X, H, tb, code, u, red);
-                if (!PLAIN && slotmask) {
-#pragma unroll
-                    for (int s = 0; s < SD_NSLOT; ++s) {
-                        if (!((slotmask >> s) & 1)) continue;
-                        double w = red[s];
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) w += __shfl_down_sync(0xffffffffu, w, o);
-                        if (lane == 0) H.usum[s][un] = w;
-                    }
-                    if (lane == 0) {
-                        __threadfence_block();
-                        const unsigned done = atomicAdd(&H.done_units, 1u);
-                        if (done + 1 == nunits) {                  // last item of the tile: ordered sum
-                            __threadfence_block();
-                            for (int s = 0; s < SD_NSLOT; ++s) {
-                                if (!((slotmask >> s) & 1)) continue;
-                                double t = 0.0;
-                                for (unsigned j = 0; j < nunits; ++j) t += ((volatile double *)H.usum[s])[j];
-                                epi.partials[(size_t)s * epi.nparts + H.tile_index] = t;
-                            }
-                        }
-                    }
-                }
+                if (!PLAIN && slotmask) sd_blk_item_reduce(H, epi, slotmask, un, nunits, red, lane);
             }
             __syncwarp();
             if (lane == 0) sd_mbar_arrive(&S.empty[b]);

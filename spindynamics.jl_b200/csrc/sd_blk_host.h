@@ -187,14 +187,13 @@ static inline uint64_t sd_blk_pos_of_state(const SdBlkHost &o, uint64_t s, int n
     return sd_blk_tile_base(o, Pb) + cl.cb + (uint64_t)e * cl.pitch + u;
 }
 
-// L2-friendly tile order of the keys [key_lo, key_hi) (scripts/l2_sim.py, "grouped, greedy chain"): the top e
-// prefix sites are the slow index, visited popcount group by popcount group and, inside a group, along a chain in
-// which consecutive configurations are adjacent-swap partners whenever possible (so the partner tiles of one
-// far bond were read a moment ago and are still in L2); the remaining prefix sites run in rank order.  Under a
-// 63 MB LRU the model predicts 18.3 GB of DRAM reads per L = 32 apply instead of 22.8 GB in rank order.
-// Any order is correct (tiles are independent); only valid tiles are listed.
-static inline void sd_blk_tile_order(const SdBlkHost &o, uint64_t key_lo, uint64_t key_hi, int e, std::vector<uint32_t> &out,
-                                     int mode = 1) {
+// L2-friendly tile order of the keys [key_lo, key_hi): breadth-first (Cuthill-McKee) order of each popcount group of
+// the adjacent-swap graph on the top e prefix sites (the slow index; the remaining prefix sites run in rank order).
+// Every bond partner of a configuration then lies in the same or a neighbouring BFS level, i.e. within about two
+// level widths of the traversal, so most partner tiles are still in L2 when they are needed.  Model (scripts/l2_sim.py,
+// 63 MB LRU, e = 16): 13.5 GB of DRAM reads per L = 32 apply against 22.8 GB in rank order; measured on B200: 14.7 GB
+// against 22.4 GB (profiles/round2_a_ab.txt).  Any order is correct (tiles are independent); only valid tiles are listed.
+static inline void sd_blk_tile_order(const SdBlkHost &o, uint64_t key_lo, uint64_t key_hi, int e, std::vector<uint32_t> &out) {
     const int A = o.P.A, k = o.P.k;
     if (e > A) e = A;
     if (e > 24) e = 24;
@@ -207,11 +206,7 @@ static inline void sd_blk_tile_order(const SdBlkHost &o, uint64_t key_lo, uint64
     };
     std::vector<uint32_t> slow(ne, 0);                              // visiting position of a top configuration
     uint32_t next_pos = 0;
-    // mode 2: breadth-first (Cuthill-McKee) order of each popcount group of the adjacent-swap graph.  Every
-    // bond partner of a configuration then lies in the same or a neighbouring BFS level, i.e. within about two
-    // level widths of the traversal, so nearly all partner tiles are still in L2 (model: 13.5 GB of DRAM reads per
-    // L = 32 apply at a 63 MB cache with e = 16, against 22.8 GB in rank order; better at every cache size >= 15 MB).
-    for (int p = e; mode == 2 && p >= 0; --p) {
+    for (int p = e; p >= 0; --p) {
         std::vector<unsigned> cfgs;
         for (unsigned c = 0; c < ne; ++c) if (__builtin_popcount(c) == p) cfgs.push_back(c);
         std::sort(cfgs.begin(), cfgs.end(), [&](unsigned a, unsigned b) { return lex(a) < lex(b); });
@@ -230,30 +225,6 @@ static inline void sd_blk_tile_order(const SdBlkHost &o, uint64_t key_lo, uint64
                         const unsigned n = c ^ (3u << q);
                         if (!seen[n]) { seen[n] = 1; queue.push_back(n); }
                     }
-            }
-        }
-    }
-    for (int p = e; mode != 2 && p >= 0; --p) {
-        std::vector<unsigned> cfgs;
-        for (unsigned c = 0; c < ne; ++c) if (__builtin_popcount(c) == p) cfgs.push_back(c);
-        std::sort(cfgs.begin(), cfgs.end(), [&](unsigned a, unsigned b) { return lex(a) < lex(b); });
-        std::vector<unsigned char> left(ne, 0);
-        for (unsigned c : cfgs) left[c] = 1;
-        size_t nleft = cfgs.size(), scan = 0;
-        unsigned cur = cfgs[0];
-        for (;;) {
-            left[cur] = 0; --nleft;
-            slow[cur] = next_pos++;
-            if (nleft == 0) break;
-            bool found = false;
-            for (int q = e - 2; q >= 0 && !found; --q)
-                if (((cur >> q) ^ (cur >> (q + 1))) & 1u) {
-                    const unsigned n = cur ^ (3u << q);
-                    if (left[n]) { cur = n; found = true; }
-                }
-            if (!found) {                                           // chain ends: lexicographically first unvisited
-                while (!left[cfgs[scan]]) ++scan;
-                cur = cfgs[scan];
             }
         }
     }

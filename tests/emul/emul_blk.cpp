@@ -12,12 +12,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
-#include <atomic>
-#include <thread>
-#include <chrono>
 #include "../../spindynamics.jl_b200/csrc/sd_tile_host.h"
 #include "../../spindynamics.jl_b200/csrc/sd_blk_host.h"
-#include "../../spindynamics.jl_b200/csrc/sd_blkr_host.h"
+#include "../../spindynamics.jl_b200/csrc/sd_blkl.h"
 #include "../../spindynamics.jl_b200/csrc/sd_halo_host.h"
 
 namespace {
@@ -41,11 +38,14 @@ void run_tiles(const SdBlkHost &bh, const SdBlkParams &P, const SdVecView &psi, 
     AlignedBuf tile;
     tile.alloc((size_t)P.cap * NC, NAN);
     SdBlkCtx X;
-    X.P = &P; X.js = bh.js.data(); X.dmid = bh.dmid.data(); X.dtail = P.dtail; X.Jhop = P.Jhop;
-    X.qx = P.Jz[P.A + SD_BLK_M - 1] * 0.25;
-    X.pstart_local = P.shards.pstart[P.shards.rank];
-    X.out_local = out_local;
-    X.epi = &epi;
+    sd_blk_ctx_init(X, P, bh.js.data(), bh.dmid.data(), P.dtail, P.Jhop, out_local, &epi);
+    if (V == 1) {                                                   // lean kernel: tables + context in the static block SD_SH
+        std::memcpy(SD_SH.js, bh.js.data(), sizeof(SdBlkJs) * (SD_BLK_B + 1));
+        std::memcpy(SD_SH.dmid, bh.dmid.data(), sizeof(double) << SD_BLK_M);
+        std::memcpy(SD_SH.dtail, P.dtail, sizeof(double) << SD_BLK_T);
+        std::memcpy(SD_SH.Jhop, P.Jhop, sizeof(double) * (SD_MAX_L + 1));
+        sd_blkl_ctx_init(P, out_local, epi);
+    }
     for (uint64_t key = P.key_lo; key < P.key_hi; ++key) {
         const uint64_t Pb = sd_blk_key_prefix(key, P.A);
         const int js = P.k - SD_POPC64(Pb);
@@ -78,275 +78,12 @@ void run_tiles(const SdBlkHost &bh, const SdBlkParams &P, const SdVecView &psi, 
             for (unsigned lane = 0; lane < 32; ++lane) {
                 const uint32_t u = (code & 0xFFu) * 32u + lane;
                 double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
-                sd_blk_dispatch<NC, PLAIN, V>(X, H, tile.p, code, u, red);
+                if (V == 1) sd_blkl_dispatch<NC, PLAIN>(H, tile.p, code, u, red);
+                else sd_blk_dispatch<NC, PLAIN, 0>(X, H, tile.p, code, u, red);
                 for (int s = 0; s < SD_NSLOT; ++s) red_total[s] += red[s];
             }
         }
     }
-}
-
-// Ring variant (sd_blkr.h, f64): per tile the header, then for every consumer warp and lane the SAME functions the
-// kernel runs -- sd_blkr_begin, sd_blkr_stream once per ring entry (the "TMA copy" of a neighbour tile is a memcpy
-// into a NaN-filled buffer of the ring-slot size), sd_blkr_own on the tile itself.  Per-warp reduction sums are added
-// in warp order, as the last warp of a tile does.
-template <bool PLAIN>
-int run_tiles_ring(const SdBlkHost &bh, const SdBlkParams &P, const SdVecView &psi, double *out_local, const SdEpi &epi,
-                   int qfar, double *red_total, int ndirect = 0) {
-    std::vector<SdBlkrWarp> rw;
-    if (!sd_blkr_build(bh, rw)) return -4;
-    if (sd_blkr_smem_carve(nullptr, nullptr, P.A, P.L, P.cap) > 227 * 1024) return -5;
-    {   // every item of every suffix popcount exactly once
-        for (int js = 0; js <= SD_BLK_B; ++js) {
-            std::vector<int> seen(SD_BLK_NCLS * 64, 0);
-            auto mark = [&](uint16_t c) { if (c != SD_BLKR_NONE) ++seen[(c >> 12) * 64 + (c & 0xFFF)]; };
-            for (int w = 0; w < SD_BLK_CWARPS; ++w) {
-                const SdBlkrWarp &x = rw[(size_t)js * SD_BLK_CWARPS + w];
-                mark(x.a); mark(x.b[0]); mark(x.b[1]); mark(x.b[2]);
-            }
-            for (int jt = 0; jt <= SD_BLK_T; ++jt) {
-                const uint32_t nu = (bh.js[js].cls[jt].nblk + 31u) / 32u;
-                for (uint32_t j = 0; j < 64; ++j)
-                    if (seen[jt * 64 + j] != (j < nu ? 1 : 0)) return -6;
-            }
-        }
-    }
-    SdBlkCtx X;
-    X.P = &P; X.js = bh.js.data(); X.dmid = bh.dmid.data(); X.dtail = P.dtail; X.Jhop = P.Jhop;
-    X.qx = P.Jz[P.A + SD_BLK_M - 1] * 0.25;
-    X.pstart_local = P.shards.pstart[P.shards.rank];
-    X.out_local = out_local;
-    X.epi = &epi;
-    std::vector<AlignedBuf> ring(SD_BLK_MAXA + 2);
-    for (auto &b : ring) b.alloc(P.cap, NAN);
-    for (uint64_t key = P.key_lo; key < P.key_hi; ++key) {
-        const uint64_t Pb = sd_blk_key_prefix(key, P.A);
-        const int js = P.k - SD_POPC64(Pb);
-        if (js < 0 || js > SD_BLK_B) continue;
-        SdBlkrHdr H;
-        std::memset(&H, 0, sizeof(H));
-        for (double &j : H.nb_J) j = NAN;
-        SdBlkHdrLane lanes[32];
-        uint64_t base = 0;
-        double dpre = 0.0;
-        unsigned actmask = 0;
-        for (int q = 0; q < 32; ++q) {
-            lanes[q] = sd_blk_hdr_lane(P, bh.W.data(), Pb, q);
-            base += lanes[q].term;
-            dpre += lanes[q].d;
-            if (lanes[q].act) actmask |= 1u << q;
-        }
-        for (int q = 0; q < 32; ++q) sd_blk_hdr_fill<1, SdBlkrHdr>(P, lanes[q], Pb, key, base, dpre, actmask, qfar, q, H, psi);
-        // ---- the ring entries of this tile, as the producer warp issues them
-        const int ntot = H.ntot;
-        const int nring = sd_blkr_nring(H, ndirect);
-        for (int n = 0; n <= ntot; ++n) {
-            if (n >= nring && n < H.nnb && n < ntot) { for (size_t i = 0; i < P.cap; ++i) ring[n].p[i] = NAN; continue; }   // no ring slot
-            const uint32_t elems = (n < ntot && n == H.nnb) ? bh.js[H.jsx].size_pad : bh.js[H.js].size_pad;
-            if (elems > P.cap) return -7;
-            for (size_t i = 0; i < P.cap; ++i) ring[n].p[i] = NAN;   // what no copy writes stays NaN
-            for (unsigned lane = 0; lane < 32; ++lane) {             // the producer warp's bulk copies (sd_blkr_copy)
-                const char *src; uint32_t off, len;
-                for (unsigned i = 0; sd_blkr_copy(bh.js.data(), H, psi.base[P.shards.rank] + H.base, P.dbg, n, ntot, lane, i, &src, &off, &len); ++i) {
-                    if ((off & 15u) || (len & 15u) || len == 0u || (size_t)off + len > (size_t)elems * 8u) return -8;   // TMA: 16-byte units inside the tile
-                    std::memcpy((char *)ring[n].p + off, src + off, len);
-                }
-            }
-        }
-        double wsum[SD_NSLOT][SD_BLK_CWARPS] = {};
-        for (unsigned w = 0; w < SD_BLK_CWARPS; ++w)
-            for (unsigned lane = 0; lane < 32; ++lane) {
-                SdBlkrLane Ln;
-                sd_blkr_begin(Ln, bh.js[H.js], rw[(size_t)H.js * SD_BLK_CWARPS + w], lane);
-                for (int n = nring; n < H.nnb && n < ntot; ++n) sd_blkr_stream_direct(Ln, H, n);
-                for (int n = 0; n < ntot; ++n) {
-                    if (n >= nring && n < H.nnb) continue;
-                    sd_blkr_stream(Ln, bh.js.data(), H, ring[n].p, n);
-                }
-                double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
-                sd_blkr_own<PLAIN>(Ln, X, H, ring[ntot].p, red);
-                for (int s = 0; s < SD_NSLOT; ++s) wsum[s][w] += red[s];
-            }
-        for (int s = 0; s < SD_NSLOT; ++s)
-            for (unsigned w = 0; w < SD_BLK_CWARPS; ++w) red_total[s] += wsum[s][w];
-    }
-    return 0;
-}
-
-// ---- threaded run of the ring kernel's protocol: one host thread per warp (1 producer + 15 consumers), a real ring of
-// SD_BLKR_NB buffers and headers that are REUSED, mbarriers modelled with atomics (pending arrivals + transaction bytes
-// + phase, try_wait on the phase parity).  The two loops below mirror the producer / consumer loops of
-// sd_blkr_apply_kernel statement by statement (same entry numbering, slot = e % NB, parity = (e / NB) & 1, header of the
-// CTA's t-th tile in hdr[t % NB] written after the wait on empty[] of the tile's first entry); everything they call is the
-// kernel's own __host__ __device__ code.  A slot or header that is reused too early shows up as a wrong result (the
-// producer scribbles NaN over a slot before refilling it) or as a ThreadSanitizer report.
-struct HostBar {
-    std::atomic<uint64_t> state{0};                                  // phase << 40 | pending << 32 | tx (tx as uint32 two's complement)
-    uint32_t count = 1;
-    void init(uint32_t c) { count = c; state.store((uint64_t)c << 32, std::memory_order_release); }
-    static uint64_t pack(uint64_t phase, uint32_t pending, uint32_t tx) { return (phase << 40) | ((uint64_t)(pending & 0xFFu) << 32) | tx; }
-    void update(int dpending, int32_t dtx) {
-        uint64_t o = state.load(std::memory_order_acquire), n;
-        do {
-            uint64_t phase = o >> 40;
-            uint32_t pending = (uint32_t)((o >> 32) & 0xFFu), tx = (uint32_t)o;
-            pending = (uint32_t)((int)pending + dpending);
-            tx = (uint32_t)((int32_t)tx + dtx);
-            if (pending == 0 && tx == 0) { ++phase; pending = count; }
-            n = pack(phase, pending, tx);
-        } while (!state.compare_exchange_weak(o, n, std::memory_order_acq_rel));
-    }
-    void arrive() { update(-1, 0); }
-    void arrive_expect_tx(uint32_t bytes) { update(-1, (int32_t)bytes); }
-    void complete_tx(uint32_t bytes) { update(0, -(int32_t)bytes); }
-    bool try_wait(unsigned parity) const { return ((state.load(std::memory_order_acquire) >> 40) & 1u) != parity; }
-};
-static bool host_wait(const HostBar &b, unsigned parity, std::atomic<int> &abort_flag) {
-    for (unsigned spins = 0; !b.try_wait(parity); ++spins) {
-        if (abort_flag.load(std::memory_order_relaxed)) return false;
-        if ((spins & 1023u) == 1023u) std::this_thread::yield();
-        if (spins > (1u << 28)) { abort_flag.store(1); return false; }       // deadlock watchdog
-    }
-    return true;
-}
-
-template <bool PLAIN>
-int run_tiles_ring_threaded(const SdBlkHost &bh, const SdBlkParams &P, const SdVecView &psi, double *out_local, const SdEpi &epi,
-                            int qfar, double *red_total, int ndirect) {
-    constexpr unsigned NB = SD_BLKR_NB;
-    std::vector<SdBlkrWarp> rw;
-    if (!sd_blkr_build(bh, rw)) return -4;
-    std::vector<AlignedBuf> ring(NB);
-    for (auto &b : ring) b.alloc(P.cap, NAN);
-    std::vector<SdBlkrHdr> hdr(NB);
-    HostBar full[NB], empty[NB];
-    for (unsigned b = 0; b < NB; ++b) { full[b].init(1); empty[b].init(SD_BLK_CWARPS); }
-    std::atomic<uint64_t> tile_ctr{0};
-    std::atomic<int> abort_flag{0};
-    const bool nostream = (P.dbg & 1) != 0;
-    std::vector<std::vector<double>> partial;                         // [tile][slot]: per-tile sums, added in tile order afterwards
-    partial.assign((size_t)(P.key_hi - P.key_lo), std::vector<double>(SD_NSLOT, 0.0));
-
-    auto producer = [&]() {
-        unsigned e = 0;
-        for (unsigned t = 0;; ++t) {
-            uint64_t key;
-            for (;;) {
-                const uint64_t c = tile_ctr.fetch_add(1);
-                key = P.key_lo + c;
-                if (key >= P.key_hi) break;
-                const uint64_t Pb = sd_blk_key_prefix(key, P.A);
-                const int js = P.k - SD_POPC64(Pb);
-                if (js >= 0 && js <= SD_BLK_B) break;
-            }
-            if (!host_wait(empty[e & (NB - 1)], ((e / NB) & 1u) ^ 1u, abort_flag)) return;
-            SdBlkrHdr &H = hdr[t & (NB - 1)];
-            if (key >= P.key_hi) {
-                H.valid = -1;
-                full[e & (NB - 1)].arrive();
-                break;
-            }
-            {   // sd_blk_make_hdr, lane by lane
-                const uint64_t Pb = sd_blk_key_prefix(key, P.A);
-                SdBlkHdrLane lanes[32];
-                uint64_t base = 0;
-                double dpre = 0.0;
-                unsigned actmask = 0;
-                for (int q = 0; q < 32; ++q) {
-                    lanes[q] = sd_blk_hdr_lane(P, bh.W.data(), Pb, q);
-                    base += lanes[q].term; dpre += lanes[q].d;
-                    if (lanes[q].act) actmask |= 1u << q;
-                }
-                for (int q = 0; q < 32; ++q) sd_blk_hdr_fill<1, SdBlkrHdr>(P, lanes[q], Pb, key, base, dpre, actmask, qfar, q, H, psi);
-            }
-            const int ntot = nostream ? 0 : H.ntot;
-            const int nring = sd_blkr_nring(H, ndirect), nnb = H.nnb;
-            const double *own_src = psi.base[P.shards.rank] + H.base;
-            bool first = true;
-            for (int n = 0; n <= ntot; ++n) {
-                if (n >= nring && n < nnb && n < ntot) continue;
-                const unsigned slot = e & (NB - 1);
-                if (!first && !host_wait(empty[slot], ((e / NB) & 1u) ^ 1u, abort_flag)) return;
-                first = false;
-                char *dst = (char *)ring[slot].p;
-                for (size_t i = 0; i < P.cap; ++i) ring[slot].p[i] = NAN;      // a consumer still reading this slot would see NaN
-                uint32_t tot = 0;
-                for (unsigned lane = 0; lane < 32; ++lane) {
-                    const char *src; uint32_t off, len;
-                    for (unsigned i = 0; sd_blkr_copy(bh.js.data(), H, own_src, P.dbg, n, ntot, lane, i, &src, &off, &len); ++i) tot += len;
-                }
-                if (tot) full[slot].arrive_expect_tx(tot); else full[slot].arrive();
-                for (unsigned lane = 0; lane < 32; ++lane) {
-                    const char *src; uint32_t off, len;
-                    for (unsigned i = 0; sd_blkr_copy(bh.js.data(), H, own_src, P.dbg, n, ntot, lane, i, &src, &off, &len); ++i) {
-                        std::memcpy(dst + off, src + off, len);
-                        full[slot].complete_tx(len);
-                    }
-                }
-                ++e;
-            }
-        }
-    };
-    std::vector<std::atomic<unsigned>> done(NB);
-    for (auto &d : done) d.store(0);
-    std::vector<std::vector<double>> usum(NB, std::vector<double>(SD_NSLOT * 16, 0.0));
-    auto consumer = [&](unsigned warp) {
-        SdBlkCtx X;
-        X.P = &P; X.js = bh.js.data(); X.dmid = bh.dmid.data(); X.dtail = P.dtail; X.Jhop = P.Jhop;
-        X.qx = P.Jz[P.A + SD_BLK_M - 1] * 0.25;
-        X.pstart_local = P.shards.pstart[P.shards.rank];
-        X.out_local = out_local;
-        X.epi = &epi;
-        unsigned e = 0;
-        for (unsigned t = 0;; ++t) {
-            if (!host_wait(full[e & (NB - 1)], (e / NB) & 1u, abort_flag)) return;
-            SdBlkrHdr &H = hdr[t & (NB - 1)];
-            if (H.valid < 0) break;
-            SdBlkrLane Ln[32];
-            for (unsigned lane = 0; lane < 32; ++lane) sd_blkr_begin(Ln[lane], bh.js[H.js], rw[(size_t)H.js * SD_BLK_CWARPS + warp], lane);
-            const int ntot = nostream ? 0 : H.ntot;
-            const int nring = sd_blkr_nring(H, ndirect), nnb = H.nnb;
-            for (int n = nring; n < nnb && n < ntot; ++n)
-                for (unsigned lane = 0; lane < 32; ++lane) sd_blkr_stream_direct(Ln[lane], H, n);
-            bool first = true;
-            for (int n = 0; n < ntot; ++n) {
-                if (n >= nring && n < nnb) continue;
-                const unsigned slot = e & (NB - 1);
-                if (!first && !host_wait(full[slot], (e / NB) & 1u, abort_flag)) return;
-                first = false;
-                for (unsigned lane = 0; lane < 32; ++lane) sd_blkr_stream(Ln[lane], bh.js.data(), H, ring[slot].p, n);
-                empty[slot].arrive();
-                ++e;
-            }
-            const unsigned slot = e & (NB - 1);
-            if (!first && !host_wait(full[slot], (e / NB) & 1u, abort_flag)) return;
-            double wred[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
-            for (unsigned lane = 0; lane < 32; ++lane) {
-                double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
-                sd_blkr_own<PLAIN>(Ln[lane], X, H, ring[slot].p, red);
-                for (int s = 0; s < SD_NSLOT; ++s) wred[s] += red[s];
-            }
-            const unsigned h = t & (NB - 1);
-            for (int s = 0; s < SD_NSLOT; ++s) usum[h][s * 16 + warp] = wred[s];
-            if (done[h].fetch_add(1, std::memory_order_acq_rel) + 1 == SD_BLK_CWARPS) {   // last warp of the tile: sum in warp order
-                for (int s = 0; s < SD_NSLOT; ++s) {
-                    double tsum = 0.0;
-                    for (unsigned j = 0; j < SD_BLK_CWARPS; ++j) tsum += usum[h][s * 16 + j];
-                    partial[H.tile_index][s] = tsum;
-                }
-                done[h].store(0, std::memory_order_release);                              // the kernel: the producer zeroes it with the next header
-            }
-            empty[slot].arrive();
-            ++e;
-        }
-    };
-    std::vector<std::thread> th;
-    th.emplace_back(producer);
-    for (unsigned w = 0; w < SD_BLK_CWARPS; ++w) th.emplace_back(consumer, w);
-    for (auto &x : th) x.join();
-    if (abort_flag.load()) return -10;                                // deadlock
-    for (auto &p : partial)
-        for (int s = 0; s < SD_NSLOT; ++s) red_total[s] += p[s];
-    return 0;
 }
 
 }  // namespace
@@ -379,10 +116,7 @@ int emul_blk_apply(int L, int k, const double *Jhop, const double *Jz, const dou
     P.nbuf = 3; P.dbg = 0;
     const bool halo = (variant & 256) != 0;                          // + 256: through the halo mirror (sd_halo_host.h), 3 chunks
     // + 512: remote-volume-weighted shard bounds (sd_halo_balance), applied above where the bounds are computed
-    const bool threaded = (variant & 1024) != 0;                     // + 1024: ring kernel as 16 host threads on a real, reused ring
-    const int ndirect = (variant >> 12) & 15;                         // + 4096 * n: n nearest prefix entries read directly (ring kernel)
-    variant &= 255;
-    if (variant == 3) { variant = 2; P.dbg = 16; }                   // ring kernel copying the whole crossing partner tile
+    variant &= 255;                                                  // 0: round-1 item body (sd_blk.h), 1: lean kernel (sd_blkl.h)
     P.key_lo = keys[rank]; P.key_hi = keys[rank + 1];
     P.shards.world = world; P.shards.rank = rank;
     uint64_t pstart[SD_MAX_WORLD + 1];
@@ -456,12 +190,7 @@ int emul_blk_apply(int L, int k, const double *Jhop, const double *Jz, const dou
                             (size_t)(sg.hi - sg.lo) * NC * sizeof(double));
             P.key_lo = plan.chunk_key[j]; P.key_hi = plan.chunk_key[j + 1];
         }
-        if (variant == 2) {                                         // ring kernel: f64 only
-            if (NC != 1) return -1;
-            const int rc = threaded ? (plain ? run_tiles_ring_threaded<true>(bh, P, view, o.p, epi, qfar, red, ndirect) : run_tiles_ring_threaded<false>(bh, P, view, o.p, epi, qfar, red, ndirect))
-                                    : (plain ? run_tiles_ring<true>(bh, P, view, o.p, epi, qfar, red, ndirect) : run_tiles_ring<false>(bh, P, view, o.p, epi, qfar, red, ndirect));
-            if (rc != 0) return rc;
-        } else if (NC == 1) { if (plain) RUN(1, true); else RUN(1, false); }
+        if (NC == 1) { if (plain) RUN(1, true); else RUN(1, false); }
         else { if (plain) RUN(2, true); else RUN(2, false); }
     }
     P.key_lo = klo_all; P.key_hi = khi_all;
@@ -501,30 +230,6 @@ int emul_blk_plan(int L, int k, int world, uint64_t *bounds, uint64_t *pstart, u
     for (int x = 0; x <= bh.P.A; ++x)
         if (k - x >= 0 && k - x <= SD_BLK_B) nt += bh.binom[(size_t)bh.P.A * SD_BINOM_DIM + x];
     *n_tiles = nt;
-    return 0;
-}
-
-// Host-side plan of the ring kernel (sd_blkr.h) at any size: dynamic shared memory of a CTA and, per suffix popcount
-// js, the total accumulator slots of a tile and the largest number any consumer warp holds.  Returns 0, -1 (model
-// does not qualify) or -4 (some suffix popcount cannot be packed).
-int emul_blkr_plan(int L, int k, uint64_t *smem_bytes, uint32_t *slots_total, uint32_t *slots_max) {
-    SdBlkHost bh;
-    std::vector<double> J(L, 0.5), Jz(L, 1.0), h(L, 0.0);
-    if (!sd_blk_build(L, k, J.data(), Jz.data(), h.data(), bh)) return -1;
-    std::vector<SdBlkrWarp> rw;
-    if (!sd_blkr_build(bh, rw)) return -4;
-    *smem_bytes = sd_blkr_smem_carve(nullptr, nullptr, bh.P.A, L, bh.P.cap);
-    for (int js = 0; js <= SD_BLK_B; ++js) {
-        slots_total[js] = 0; slots_max[js] = 0;
-        for (int w = 0; w < SD_BLK_CWARPS; ++w) {
-            const SdBlkrWarp &x = rw[(size_t)js * SD_BLK_CWARPS + w];
-            uint32_t n = 0;
-            if (x.a != SD_BLKR_NONE) n += sd_blkr_ec(x.a >> 12);
-            for (int i = 0; i < 3; ++i) if (x.b[i] != SD_BLKR_NONE) n += sd_blkr_ec(x.b[i] >> 12);
-            slots_total[js] += n;
-            if (n > slots_max[js]) slots_max[js] = n;
-        }
-    }
     return 0;
 }
 
@@ -625,7 +330,7 @@ int emul_halo_balance(int L, int k, int world, double remote_cost, int iters, ui
 
 // The optional L2-friendly tile order of rank `rank` (sd_blk_tile_order).  Returns the number of keys written
 // (<= cap), or -1.
-long emul_blk_order(int L, int k, int world, int rank, int e, uint32_t *out, long cap, uint64_t *key_lo, uint64_t *key_hi, int mode) {
+long emul_blk_order(int L, int k, int world, int rank, int e, uint32_t *out, long cap, uint64_t *key_lo, uint64_t *key_hi) {
     SdBlkHost bh;
     std::vector<double> J(L, 0.5), Jz(L, 1.0), h(L, 0.0);
     if (!sd_blk_build(L, k, J.data(), Jz.data(), h.data(), bh)) return -1;
@@ -634,7 +339,7 @@ long emul_blk_order(int L, int k, int world, int rank, int e, uint32_t *out, lon
     uint64_t bounds[SD_MAX_WORLD + 1], keys[SD_MAX_WORLD + 1];
     sd_tile_shard_bounds(th, world, bounds, keys);
     std::vector<uint32_t> ord;
-    sd_blk_tile_order(bh, keys[rank], keys[rank + 1], e, ord, mode);
+    sd_blk_tile_order(bh, keys[rank], keys[rank + 1], e, ord);
     if ((long)ord.size() > cap) return -1;
     for (size_t i = 0; i < ord.size(); ++i) out[i] = ord[i];
     *key_lo = keys[rank]; *key_hi = keys[rank + 1];

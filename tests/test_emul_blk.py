@@ -33,10 +33,10 @@ def load():
 
 
 VARIANT = 0          # kernel variant run() uses; the `emul` fixture runs every test with each:
-#                      0 / 1 = item bodies of sd_blk_apply_kernel, 2 = the ring kernel (sd_blkr.h, f64 only)
+#                      1 = the lean kernel's item body (sd_blkl.h, the default), 0 = the round-1 body (sd_blk.h)
 
 
-@pytest.fixture(scope="module", params=[0, 1, 2, 3], ids=["body0", "body1", "ring", "ring_fullx"])
+@pytest.fixture(scope="module", params=[1, 0], ids=["lean", "body0"])
 def emul(request):
     global VARIANT
     VARIANT = request.param
@@ -73,8 +73,6 @@ def oracle_apply(m, psi, NC):
 def run(lib, L, k, NC, world, states, psi, Jhop, Jz, h, mode=0, red=0, hscale=1.0, a=1.0, b=0.0,
         vprev=None, phi=None, acc=None, ck=0j, far_bytes=1 << 20, variant=None):
     variant = VARIANT if variant is None else variant
-    if (variant & 255) >= 2 and NC == 2:
-        pytest.skip("the ring kernel is f64 only")
     N = len(states)
     out = np.full(N * NC, np.nan)
     redsum = np.zeros(4)
@@ -299,19 +297,18 @@ def test_shard_plan_at_full_sizes(emul, L, k, N):
         assert max(stored) <= slack * max(sizes) + 6480
 
 
-@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("L,k,e,world", [(24, 12, 5, 1), (26, 13, 12, 1), (28, 14, 12, 4), (20, 10, 3, 2), (26, 13, 10, 1)])
-def test_optional_tile_order_is_a_permutation_of_the_shards_valid_tiles(emul, L, k, e, world, mode):
-    """sd_blk_tile_order (SD_BLK_ORDER=1 greedy chain, =2 breadth-first): every valid tile key of the shard
-    exactly once; equal to the python model of the same order that scripts/l2_sim.py evaluates."""
-    emul.emul_blk_order.argtypes = [ctypes.c_int] * 5 + [vp, ctypes.c_long, vp, vp, ctypes.c_int]
+def test_tile_order_is_a_permutation_of_the_shards_valid_tiles(emul, L, k, e, world):
+    """sd_blk_tile_order (breadth-first order of the popcount groups, the default for vectors beyond the L2): every valid
+    tile key of the shard exactly once; equal to the python model of the same order that scripts/l2_sim.py evaluates."""
+    emul.emul_blk_order.argtypes = [ctypes.c_int] * 5 + [vp, ctypes.c_long, vp, vp]
     emul.emul_blk_order.restype = ctypes.c_long
     A = L - 15
     allkeys = []
     for rank in range(world):
         out = np.zeros(1 << A, dtype=np.uint32)
         lo, hi = np.zeros(1, dtype=np.uint64), np.zeros(1, dtype=np.uint64)
-        n = emul.emul_blk_order(L, k, world, rank, e, P(out), len(out), P(lo), P(hi), mode)
+        n = emul.emul_blk_order(L, k, world, rank, e, P(out), len(out), P(lo), P(hi))
         assert n >= 0
         keys = out[:n].astype(np.int64)
         valid = [key for key in range(int(lo[0]), int(hi[0]))
@@ -329,28 +326,9 @@ def test_optional_tile_order_is_a_permutation_of_the_shards_valid_tiles(emul, L,
             spec.loader.exec_module(sim)
         finally:
             sys.argv = argv
-        ref = sim.grouped_greedy_order(e) if mode == 1 else sim.bfs_order(e)     # prefix bit patterns
+        ref = sim.bfs_order(e)                                          # prefix bit patterns
         ref_keys = [sum((0 if (Pb >> q) & 1 else 1) << (A - 1 - q) for q in range(A)) for Pb in ref]
         assert ref_keys == allkeys[0].tolist()
-
-
-@pytest.mark.parametrize("L,k", [(32, 16), (34, 17), (36, 18), (32, 10), (24, 12), (16, 8)])
-def test_ring_kernel_plan_at_full_sizes(L, k):
-    """sd_blkr.h at BASELINE.json's sizes: the four-slot ring plus tables fits the 227 KB of dynamic shared memory of
-    an sm_100 CTA, every suffix popcount packs into the 15 consumer warps (8 accumulator slots each), and at the
-    heavy suffix popcounts of an Sz = 0 chain the packing is balanced (114 slots: 7 or 8 per warp)."""
-    lib = load()
-    lib.emul_blkr_plan.argtypes = [ctypes.c_int, ctypes.c_int, vp, vp, vp]
-    smem = np.zeros(1, dtype=np.uint64)
-    tot, mx = np.zeros(16, dtype=np.uint32), np.zeros(16, dtype=np.uint32)
-    assert lib.emul_blkr_plan(L, k, P(smem), P(tot), P(mx)) == 0
-    assert int(smem[0]) <= 227 * 1024
-    assert mx.max() <= 8
-    for js in range(16):
-        lo, hi = max(0, js - 5), min(10, js)                        # mid popcounts of the classes jt = 0..5
-        want = sum(-(-math.comb(10, js - jt) // 32) * ((math.comb(5, jt) + 1) // 2) for jt in range(6) if lo <= js - jt <= hi)
-        assert int(tot[js]) == want
-    assert int(tot[7]) == 114 and int(tot[8]) == 114 and int(mx[7]) == 8 and int(mx[8]) == 8
 
 
 @pytest.mark.parametrize("L,k,world,chunks", [(20, 10, 2, 4), (22, 11, 3, 5), (24, 12, 4, 8), (26, 9, 8, 3), (28, 14, 8, 8), (32, 16, 8, 8),
@@ -398,7 +376,7 @@ def test_remote_weighted_shard_bounds(L, k, world):
         assert sizes[2] < 0.7 and sizes[5] < 0.7 and sizes[0] > 1.05
 
 
-@pytest.mark.parametrize("variant", [256 + 0, 256 + 2, 256 + 512 + 0, 256 + 512 + 2, 512 + 1], ids=["halo", "halo_ring", "halo_bal", "halo_bal_ring", "bal_body1"])
+@pytest.mark.parametrize("variant", [256 + 1, 256 + 0, 256 + 512 + 1, 512 + 1], ids=["halo", "halo_body0", "halo_bal", "bal"])
 @pytest.mark.parametrize("L,k,world", [(18, 9, 2), (20, 10, 4), (20, 10, 8), (22, 11, 8), (20, 6, 5)])
 def test_sharded_apply_through_the_halo_mirror(variant, L, k, world):
     """SD_HALO=1 / SD_SHARD_BALANCE=1 end to end on the CPU: every rank runs the emulated kernel on NaN-filled mirrors of
@@ -411,7 +389,7 @@ def test_sharded_apply_through_the_halo_mirror(variant, L, k, world):
     m = oracle_model(L, k, Jhop, Jz, h)
     states = np.ascontiguousarray(m.states, dtype=np.uint64)
     N = len(states)
-    for NC in ((1,) if (variant & 255) >= 2 else (1, 2)):
+    for NC in (1, 2):
         psi, vprev, phi = (rng.standard_normal(N * NC) for _ in range(3))
         ref = oracle_apply(m, psi, NC)
         out, _, bounds, _ = run(lib, L, k, NC, world, states, psi, Jhop, Jz, h, variant=variant)
@@ -424,50 +402,3 @@ def test_sharded_apply_through_the_halo_mirror(variant, L, k, world):
         assert np.linalg.norm(out - nxt) <= 1e-14 * np.linalg.norm(nxt)
         assert abs(complex(red[0], red[1]) - np.vdot(cplx(psi), cplx(nxt))) < 1e-9
         assert abs(red[2] - np.vdot(cplx(phi), cplx(nxt)).real) < 1e-9 and abs(red[3] - nxt @ nxt) < 1e-8
-
-
-@pytest.mark.parametrize("ndirect", [1, 3, 15])
-@pytest.mark.parametrize("L,k,world", [(18, 9, 1), (20, 10, 3), (22, 11, 1), (24, 12, 2)])
-def test_ring_kernel_with_direct_near_entries(ndirect, L, k, world):
-    """SD_BLKR_DIRECT=n: the n nearest prefix entries of a tile bypass the ring (consumers read them from global memory),
-    the remaining entries keep the ring protocol; any n (also n >= the number of prefix entries: crossing + own only)."""
-    lib = load()
-    rng = np.random.default_rng(L + ndirect)
-    Jhop, Jz, h = model_lists(L, rng)
-    m = oracle_model(L, k, Jhop, Jz, h)
-    states = np.ascontiguousarray(m.states, dtype=np.uint64)
-    psi, vprev = rng.standard_normal(len(states)), rng.standard_normal(len(states))
-    ref = oracle_apply(m, psi, 1)
-    for base in (2, 3, 2 + 256):
-        out, _, _, _ = run(lib, L, k, 1, world, states, psi, Jhop, Jz, h, variant=base + 4096 * ndirect)
-        assert np.linalg.norm(out - ref) <= 1e-14 * np.linalg.norm(ref), base
-    nxt = 2.0 * ((ref - 0.3 * psi) / 2.5) - vprev
-    out, red, _, _ = run(lib, L, k, 1, world, states, psi, Jhop, Jz, h, mode=2, red=5, a=2.5, b=0.3, vprev=vprev, variant=2 + 4096 * ndirect)
-    assert np.linalg.norm(out - nxt) <= 1e-14 * np.linalg.norm(nxt)
-    assert abs(red[0] - psi @ nxt) < 1e-13 * (nxt @ nxt) and abs(red[3] - nxt @ nxt) < 1e-13 * (nxt @ nxt)
-
-
-@pytest.mark.parametrize("ndirect", [0, 2])
-@pytest.mark.parametrize("L,k,world", [(16, 8, 1), (18, 9, 2), (20, 10, 1), (21, 8, 3)])
-def test_ring_protocol_with_real_threads_and_a_reused_ring(ndirect, L, k, world):
-    """The ring kernel as 16 host threads (1 producer + 15 consumer "warps") on a real ring of 4 buffers and 4 headers
-    that are reused, mbarriers modelled with atomics; the two loops mirror the kernel's statement by statement and call
-    the kernel's own host/device code.  The producer scribbles NaN over a slot before it refills it, so a slot or header
-    reused too early corrupts the result; a deadlock is reported (-10).  Also run under ThreadSanitizer (make tsan)."""
-    lib = load()
-    rng = np.random.default_rng(L + ndirect)
-    Jhop, Jz, h = model_lists(L, rng)
-    m = oracle_model(L, k, Jhop, Jz, h)
-    states = np.ascontiguousarray(m.states, dtype=np.uint64)
-    psi, vprev, phi = (rng.standard_normal(len(states)) for _ in range(3))
-    ref = oracle_apply(m, psi, 1)
-    variant = 2 + 1024 + 4096 * ndirect
-    for rep in range(3):                                             # thread interleavings differ from run to run
-        out, _, _, _ = run(lib, L, k, 1, world, states, psi, Jhop, Jz, h, variant=variant)
-        assert np.linalg.norm(out - ref) <= 1e-14 * np.linalg.norm(ref)
-    nxt = 2.0 * ((ref - 0.3 * psi) / 2.5) - vprev
-    out, red, _, _ = run(lib, L, k, 1, world, states, psi, Jhop, Jz, h, mode=2, red=7, a=2.5, b=0.3, vprev=vprev, phi=phi, variant=variant)
-    assert np.linalg.norm(out - nxt) <= 1e-14 * np.linalg.norm(nxt)
-    assert abs(red[0] - psi @ nxt) < 1e-12 * (nxt @ nxt) and abs(red[2] - phi @ nxt) < 1e-12 * (nxt @ nxt) and abs(red[3] - nxt @ nxt) < 1e-12 * (nxt @ nxt)
-    out2, red2, _, _ = run(lib, L, k, 1, world, states, psi, Jhop, Jz, h, mode=2, red=7, a=2.5, b=0.3, vprev=vprev, phi=phi, variant=variant)
-    assert np.array_equal(out, out2) and np.array_equal(red, red2)   # deterministic whatever the interleaving
