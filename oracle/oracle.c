@@ -62,17 +62,26 @@ static inline uint64_t flip_bits(uint64_t s, int i, int j) {
     return s ^ (1ULL << i) ^ (1ULL << j);
 }
 
+/* The table stands in for Julia's Dict{UInt64,Int}: Base.Dict keeps its slot count a power of two and grows when
+ * more than 2/3 of the slots are in use, so N keys occupy the smallest power of two >= 1.5 N slots (17 bytes per slot
+ * there, 16 here).  L = 32, nup = 16: 2^30 slots = 17 GB.  Large bases are inserted by all OpenMP threads (compare-
+ * and-swap on the key slot); the result does not depend on the insertion order because keys are unique. */
 static void map_build(orc_model *m) {
     uint64_t cap = 16;
-    while (cap < 2 * m->N) cap <<= 1;
+    while (2 * cap < 3 * m->N) cap <<= 1;
     m->cap_mask = cap - 1;
     m->keys = (uint64_t *)calloc(cap, sizeof(uint64_t));
     m->vals = (int64_t *)malloc(cap * sizeof(int64_t));
-    for (uint64_t i = 0; i < m->N; ++i) {           /* Basis.jl:49-52, idxmap[s] = i */
+    const int64_t N = (int64_t)m->N;
+#pragma omp parallel for schedule(static) if (N > (1 << 22))
+    for (int64_t i = 0; i < N; ++i) {               /* Basis.jl:49-52, idxmap[s] = i */
         uint64_t s = m->states[i];
         uint64_t h = mix64(s) & m->cap_mask;
-        while (m->keys[h]) h = (h + 1) & m->cap_mask;
-        m->keys[h] = s + 1;
+        for (;;) {
+            uint64_t expect = 0;
+            if (__atomic_compare_exchange_n(&m->keys[h], &expect, s + 1, 0, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) break;
+            h = (h + 1) & m->cap_mask;
+        }
         m->vals[h] = (int64_t)i + 1;
     }
 }
@@ -112,8 +121,44 @@ uint64_t orc_sector_dim(int L, int nup) { return binom_u64(L, nup); }
  * site i sets bit i-1, states pushed in iteration order.  Combinatorics.jl
  * yields the k-subsets in lexicographic order of their ascending site lists.
  * out must hold binomial(L,nup) entries. */
+static void sector_basis_range(int L, int nup, uint64_t first, uint64_t count, uint64_t *out) {
+    /* the `first`-th combination (0-based) of combinations(1:L, nup), then `count` successors in iteration order */
+    int c[64];
+    uint64_t idx = first;
+    int prev = 0;
+    for (int i = 0; i < nup; ++i) {
+        int v = prev + 1;
+        for (;; ++v) {
+            uint64_t below = binom_u64(L - v, nup - 1 - i);        /* combinations whose i-th site is v */
+            if (idx < below) break;
+            idx -= below;
+        }
+        c[i] = v; prev = v;
+    }
+    for (uint64_t n = 0; n < count; ++n) {
+        uint64_t s = 0;
+        for (int i = 0; i < nup; ++i) s |= 1ULL << (c[i] - 1);
+        out[n] = s;
+        int i = nup - 1;
+        while (i >= 0 && c[i] == L - nup + i + 1) --i;
+        if (i < 0) break;
+        ++c[i];
+        for (int j = i + 1; j < nup; ++j) c[j] = c[j - 1] + 1;
+    }
+}
 int orc_build_sector_basis(int L, int nup, uint64_t *out) {
     if (orc_validate_basis_args(L, nup) || nup < 0) return -1;
+    const uint64_t N = binom_u64(L, nup);
+    if (N > (1u << 22)) {              /* same enumeration, cut into chunks that start at an unranked combination */
+        const int64_t nchunk = 1024;
+#pragma omp parallel for schedule(dynamic)
+        for (int64_t ch = 0; ch < nchunk; ++ch) {
+            const uint64_t lo = (uint64_t)(((unsigned __int128)N * (uint64_t)ch) / (uint64_t)nchunk);
+            const uint64_t hi = (uint64_t)(((unsigned __int128)N * (uint64_t)(ch + 1)) / (uint64_t)nchunk);
+            if (hi > lo) sector_basis_range(L, nup, lo, hi - lo, out + lo);
+        }
+        return 0;
+    }
     int c[64];
     for (int i = 0; i < nup; ++i) c[i] = i + 1;      /* first combination 1..k */
     uint64_t n = 0;
@@ -175,6 +220,14 @@ void orc_rank(const orc_model *m, const uint64_t *s, uint64_t n, int64_t *idx1) 
     for (uint64_t i = 0; i < n; ++i) idx1[i] = map_get(m, s[i]);
 }
 
+/* bench.py: the OpenMP team is set explicitly (torchrun exports OMP_NUM_THREADS=1 to its children) */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

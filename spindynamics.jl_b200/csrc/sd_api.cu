@@ -183,9 +183,7 @@ struct SdBlkDev {
     int nbuf[2] = {0, 0};
     size_t smem[2] = {0, 0};
     int qfar[2] = {0, 0};
-    int kernel = 1;                 // 1: sd_blkl_apply_kernel (lean, default); 0: sd_blk_apply_kernel (round-1 body; SD_BLK_KERNEL=0)
-    int threads = 640;              // CTA size of the lean kernel (SD_BLKL_THREADS = 512 | 640 | 768)
-    int dbg = 0;                    // profiling switches of the round-1 body (SD_BLK_DBG), read once at model creation
+    int threads = 768;              // CTA size of sd_blkl_apply_kernel (SD_BLKL_THREADS = 512 | 640 | 768, read once at model creation)
     uint32_t *d_order = nullptr;    // breadth-first tile order of this rank's shard (vectors larger than the L2)
     uint32_t norder = 0;
     // halo mirror of sharded applies (SD_HALO=1, sd_halo_host.h): chunked copy-engine prefetch of the peer ranges the
@@ -493,18 +491,15 @@ static int sd_blk_setup(sd_model *m) {
     for (size_t i = 0; i < m->hop_a.size(); ++i) Jhop[m->hop_a[i]] += m->hop_J[i];
     for (size_t i = 0; i < m->zz_a.size(); ++i) Jz[m->zz_a[i]] += m->zz_J[i];
     if (!sd_blk_build(L, m->k, Jhop.data(), Jz.data(), m->field.data(), b.host)) return SD_OK;
-    b.kernel = sd_env_int("SD_BLK_KERNEL", 1) ? 1 : 0;
-    b.threads = sd_env_int("SD_BLKL_THREADS", 640);
-    if (b.threads != 512 && b.threads != 768) b.threads = 640;
-    b.dbg = sd_env_int("SD_BLK_DBG", 0);
+    b.threads = sd_env_int("SD_BLKL_THREADS", 768);
+    if (b.threads != 512 && b.threads != 640) b.threads = 768;
     for (int w = 0; w < 2; ++w) {
         const int nc = w + 1;
         int nbuf = w == 0 ? 3 : 2;
         for (; nbuf >= 2; --nbuf) {
-            // lean kernel: the tile buffers are the dynamic part, tables and headers are static (sizeof(SdBlkShared))
-            b.smem[w] = b.kernel ? (size_t)nbuf * b.host.P.cap * nc * sizeof(double)
-                                 : sd_blk_smem_carve(nullptr, nullptr, b.host.P.A, L, nbuf, b.host.P.cap, nc);
-            if (b.smem[w] + (b.kernel ? sizeof(SdBlkShared) + 128 : 0) <= 227 * 1024) break;
+            // the tile buffers are the dynamic part; tables, headers and context are static (sizeof(SdBlkShared))
+            b.smem[w] = (size_t)nbuf * b.host.P.cap * nc * sizeof(double);
+            if (b.smem[w] + sizeof(SdBlkShared) + 128 <= 227 * 1024) break;
         }
         if (nbuf < 2) return SD_OK;
         b.nbuf[w] = nbuf;
@@ -525,7 +520,6 @@ static SdBlkParams sd_blk_params(const sd_model *m, int nc) {
     SdBlkParams P = m->blk.host.P;
     const sd_ctx *c = m->ctx;
     P.nbuf = m->blk.nbuf[nc - 1];
-    P.dbg = m->blk.dbg;
     P.order = m->blk.d_order; P.norder = m->blk.norder;
     P.key_lo = m->tile[0].keys[c->rank];
     P.key_hi = m->tile[0].keys[c->rank + 1];
@@ -1214,16 +1208,11 @@ static int sd_blk_launch_range(sd_model *m, int nc, const SdBlkParams &P, const 
         else if (m->blk.threads == 768) SD_HL((sd_blkl_apply_kernel<NC_, PLAIN_, 768>), 768);                \
         else SD_HL((sd_blkl_apply_kernel<NC_, PLAIN_, 640>), 640);                                           \
     } while (0)
-    if (m->blk.kernel) {
-        if (nc == 1) { if (plain) SD_HL_LEAN(1, true); else SD_HL_LEAN(1, false); }
-        else { if (plain) SD_HL_LEAN(2, true); else SD_HL_LEAN(2, false); }
-        return sd_launch_check(c, "sd_blkl_apply_kernel");
-    }
-    if (nc == 1) { if (plain) SD_HL((sd_blk_apply_kernel<1, true, 0>), SD_BLK_THREADS); else SD_HL((sd_blk_apply_kernel<1, false, 0>), SD_BLK_THREADS); }
-    else { if (plain) SD_HL((sd_blk_apply_kernel<2, true, 0>), SD_BLK_THREADS); else SD_HL((sd_blk_apply_kernel<2, false, 0>), SD_BLK_THREADS); }
+    if (nc == 1) { if (plain) SD_HL_LEAN(1, true); else SD_HL_LEAN(1, false); }
+    else { if (plain) SD_HL_LEAN(2, true); else SD_HL_LEAN(2, false); }
 #undef SD_HL_LEAN
 #undef SD_HL
-    return sd_launch_check(c, "sd_blk_apply_kernel");
+    return sd_launch_check(c, "sd_blkl_apply_kernel");
 }
 // Sharded block-layout apply through the halo mirror: the copy engines bring the peer ranges of chunk j into the
 // mirror while the kernel of chunk j-1 runs; every kernel read is local.  The caller has issued the rank barrier, so the

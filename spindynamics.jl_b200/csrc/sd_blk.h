@@ -26,6 +26,8 @@
 // There is no flat phase, no permutation table and no CTA barrier in the steady state:
 // consumer warps pull (tile, unit) work items from a per-tile counter, a producer warp
 // computes tile headers and keeps NBUF tiles in flight.
+// This file holds the layout, the tables, the tile header, the producer warp and the layout-conversion kernel;
+// the apply kernel itself (consumer warps, item body) is sd_blkl.h.
 //
 // f64: a lane owns two adjacent mid configurations (a double2 = blocks u, u+1).
 // c128: a lane owns one mid configuration (a double2 = re, im).  H is real, so both are
@@ -39,13 +41,6 @@
 #define SD_BLK_NCLS (SD_BLK_T + 1)
 #define SD_BLK_MAXA 32
 #define SD_BLK_MAXUNITS 64      // work items per tile: (unit of 32 mid configurations, element chunk); <= 32 (f64), <= 47 (c128)
-#define SD_BLK_THREADS 512
-#ifndef SD_BLK_LB
-#define SD_BLK_LB SD_BLK_THREADS
-#endif
-#define SD_BLK_CWARPS 15        // consumer warps; warp 15 is the producer
-#define SD_BLK_DEFAULT_VARIANT 0   // item-body variant launched by default (SD_BLK_VARIANT overrides); see sd_blk_item
-
 struct SdBlkCls {
     uint32_t cb;         // element offset of the class inside the tile
     uint32_t pitch;      // row pitch (elements) = nblk rounded up to 4
@@ -80,13 +75,15 @@ struct SdBlkParams {
     double Jz[SD_MAX_L + 1];
     double h[SD_MAX_L + 1];
     double dtail[1 << SD_BLK_T];     // diag of the tail sites + tail-internal zz, by tail bits
+    double Jmid[SD_BLK_M];           // = Jhop[A + pm]: mid bonds pm = 0 .. M-2, [M-1] the mid|tail bond (constant-bank operands)
+    double Jtail[SD_BLK_T];          // = Jhop[A + M + q]: tail bonds
+    double qx;                       // Jz of the mid|tail bond * 0.25
     const uint64_t *W;               // [A*(A+1)] stored elements of all tiles "1 at q, `below` ones before"
     const SdBlkJs *js;               // [B+1]
     const uint16_t *units;           // [2][(B+1)*MAXUNITS]: jt << 8 | unit-in-class, heavy classes first
     const SdBlkItem *items;
-    const double *dmid;              // [1 << M] diag of the mid sites + mid-internal zz
+    const double *dmid;              // [1 << M] diag of the mid sites + mid-internal zz, in ITEM order (same index as items[])
     uint32_t cap;                    // largest size_pad
-    int dbg;                         // profiling switches (SD_BLK_DBG): 1 skip prefix streams, 2 skip suffix hops, 4 skip store
     const uint32_t *order;           // optional tile order of this shard (keys, norder of them); nullptr: rank order
     uint32_t norder;
     SdBlkShards shards;
@@ -116,12 +113,16 @@ static inline double2 make_double2(double x, double y) { double2 v; v.x = x; v.y
 #endif
 
 // ------------------------------------------------------------------ tile header
-struct SdBlkHdr {
+struct alignas(16) SdBlkEnt {
+    const double *p;                     // stored base of the neighbour tile (component 0)
+    double J;                            // hop coefficient of the bond
+};
+struct alignas(16) SdBlkHdr {
     uint64_t base;                       // stored-element offset of the tile (global, all shards)
     int js, jsx;                         // suffix popcount of the tile / of the crossing partner tile
     int valid;                           // 1: tile, -1: end of this CTA's tile list
     int nnb, nfar;                       // active prefix-internal bonds; the first nfar are beyond L2 reach
-    int ntot;                            // nnb + 1 if the prefix|mid crossing bond is active: entry nnb of nb_ptr / nb_J
+    int ntot;                            // nnb + 1 if the prefix|mid crossing bond is active: entry nnb of nb[]
     int bP;                              // last prefix bit
     unsigned next_unit;                  // work counter of the consumer warps
     unsigned done_units;                 // finished units (the warp that finishes the last one sums usum[] in order)
@@ -129,8 +130,7 @@ struct SdBlkHdr {
     double dP[2];                        // prefix diag + prefix|mid zz, by first mid bit
     double Jx;                           // hop coefficient of the prefix|mid bond (0: none)
     const double *xptr;                  // stored base of the crossing partner tile (component 0)
-    const double *nb_ptr[SD_BLK_MAXA + 8];   // stored bases of the neighbour tiles of the active prefix bonds
-    double nb_J[SD_BLK_MAXA + 8];        // entry nnb: the crossing bond (if active); entries ntot .. ntot+5 are 0 (pipeline overrun)
+    SdBlkEnt nb[SD_BLK_MAXA + 1];        // neighbour tiles of the active prefix bonds (one LDS.128 per entry); entry nnb: the crossing bond (if active)
     double usum[SD_NSLOT][SD_BLK_MAXUNITS];   // per-unit reduction results (deterministic: summed in unit order)
 };
 
@@ -169,7 +169,6 @@ SD_HD SdBlkHdrLane sd_blk_hdr_lane(const SdBlkParams &P, const uint64_t *W, uint
     return l;
 }
 // second half, after the warp-wide sums base = sum(term), dpre = sum(d), actmask = ballot(act)
-// HDR: SdBlkHdr, or the ring kernel's smaller SdBlkrHdr (sd_blkr.h: same fields, one usum entry per consumer warp)
 template <int NC, class HDR = SdBlkHdr>
 SD_HD void sd_blk_hdr_fill(const SdBlkParams &P, const SdBlkHdrLane &l, uint64_t Pb, uint64_t key, uint64_t base, double dpre,
                            unsigned actmask, int qfar, int q, HDR &H, const SdVecView &psi) {
@@ -183,8 +182,8 @@ SD_HD void sd_blk_hdr_fill(const SdBlkParams &P, const SdBlkHdrLane &l, uint64_t
         const uint64_t nbase = bit ? base + dl : base - dl;
         const unsigned lt = (1u << q) - 1u;
         const int slot = ((farmask >> q) & 1u) ? SD_POPC32(actmask & farmask & lt) : nfar + SD_POPC32(actmask & ~farmask & lt);
-        H.nb_ptr[slot] = psi.base[sd_blk_owner(P.shards, nbase)] + (size_t)NC * nbase;
-        H.nb_J[slot] = P.Jhop[q];
+        H.nb[slot].p = psi.base[sd_blk_owner(P.shards, nbase)] + (size_t)NC * nbase;
+        H.nb[slot].J = P.Jhop[q];
     }
     if (q == A - 1) {                                             // prefix|mid crossing bond
         const int jsx = bit ? js + 1 : js - 1;
@@ -196,8 +195,8 @@ SD_HD void sd_blk_hdr_fill(const SdBlkParams &P, const SdBlkHdrLane &l, uint64_t
         H.xptr = ok ? psi.base[sd_blk_owner(P.shards, nbase)] + (size_t)NC * nbase : nullptr;
         if (ok) {                                                 // the crossing bond as entry nnb of the stream list
             const int nnb = SD_POPC32(actmask);
-            H.nb_ptr[nnb] = H.xptr;
-            H.nb_J[nnb] = J;
+            H.nb[nnb].p = H.xptr;
+            H.nb[nnb].J = J;
         }
         H.bP = bit;
         const double sl = bit ? 0.5 : -0.5;
@@ -215,7 +214,6 @@ SD_HD void sd_blk_hdr_fill(const SdBlkParams &P, const SdBlkHdrLane &l, uint64_t
             const bool okx = (P.Jhop[A - 1] != 0.0) && jsx >= 0 && jsx <= SD_BLK_B;
             const int ntot = H.nnb + (okx ? 1 : 0);
             H.ntot = ntot;
-            for (int i = 0; i < 6; ++i) H.nb_J[ntot + i] = 0.0;
         }
         H.next_unit = 0;
         H.done_units = 0;
@@ -246,9 +244,8 @@ __device__ __forceinline__ void sd_blk_make_hdr(const SdBlkParams &P, const uint
 //   c128: slot s = tail configuration s, (re, im)
 // H is real, so a slot is two independent real columns for everything but the tail-internal hops and
 // the mid|tail crossing bond, which address single tail configurations.
-// Register budget: acc[EC] + 3 x t[EC] slots (EC <= 5 -> 20 + 60 registers), which is what allows
-// THREE neighbour tiles in flight per warp.
-// The body compiles for host and device: tests/emul/emul_blk.cpp runs it on the CPU, lane by lane, against
+// The helpers below are shared by the item body of sd_blkl.h.
+// Everything compiles for host and device: tests/emul/emul_blk.cpp runs it on the CPU, lane by lane, against
 // the oracle (index algebra, layout, epilogues, shard ownership without a GPU).
 SD_HD double2 sd_blk_ldg(const double *p) {
     double2 v;
@@ -354,297 +351,14 @@ SD_HD void sd_blk_tail(double2 (&acc)[EC], const double *own_ptr, uint32_t ss, u
     SdBlkTailRow<NC, JT, E0, NE, EC, NO, 0>::run(acc, own, Jt, dtail, d0, dx0);
 }
 
-struct SdBlkCtx {
-    const SdBlkParams *P;
-    const SdBlkJs *js;          // shared-memory copy [B+1]
-    const double *dmid;         // shared-memory copy [1 << M]
-    const double *dtail;        // shared-memory copy
-    const double *Jhop;         // shared-memory copy [L]
-    double qx;                  // Jz of the mid|tail bond * 0.25
-    double *out_local;          // local shard of out, component 0 of stored element 0
-    uint64_t pstart_local;      // stored-element offset of the local shard
-    const SdEpi *epi;
-    const SdBlkItem *items;     // = P->items (the lean body does not touch P)
-    int A;
-};
-SD_HD void sd_blk_ctx_init(SdBlkCtx &X, const SdBlkParams &P, const SdBlkJs *js, const double *dmid, const double *dtail,
-                           const double *Jhop, double *out_local, const SdEpi *epi) {
-    X.P = &P; X.js = js; X.dmid = dmid; X.dtail = dtail; X.Jhop = Jhop;
-    X.qx = P.Jz[P.A + SD_BLK_M - 1] * 0.25;
-    X.pstart_local = P.shards.pstart[P.shards.rank];
-    X.out_local = out_local;
-    X.epi = epi;
-    X.items = P.items;
-    X.A = P.A;
-}
-
-// Everything except sd_blk_tail is generic in (jt, S0), which keeps the code small enough for the
-// instruction cache (15 warps run different items at the same time).
-// S0 = first slot of the chunk (c128, classes of 10: 0 or 5; otherwise 0).
-// HALF: the last slot of the chunk is a half slot (f64 classes with an odd number of tail configurations:
-// the last configuration is stored as a plain row of doubles at cb + (NT-1)*pitch + u).
-// V: body variant.  0 = the round-1 measured body; 1 = lean streams (loads predicated without zero fill,
-// coefficients read from the zero-padded header list, crossing bond as list entry nnb) and mid hops
-// iterated over the item's active-bond mask.  Same arithmetic, different summation interleaving.
-template <int NC, int EC, bool HALF, bool PLAIN, int V>
-SD_HD void sd_blk_item(const SdBlkCtx &X, const SdBlkHdr &H, const double *tb, int jt, int S0,
-                                            uint32_t u, double (&red)[SD_NSLOT]) {
-    constexpr int T = SD_BLK_T, M = SD_BLK_M;
-    const SdBlkParams &P = *X.P;
-    const SdBlkJs &I = X.js[H.js];
-    const SdBlkCls cls = I.cls[jt];
-    if (u >= cls.nblk) return;
-    const uint32_t ss = 2u * cls.pitch;                               // doubles between slots (both dtypes)
-    const uint32_t off0 = cls.cb * NC + 2u * u;                       // doubles, slot 0 of the block
-    const uint32_t offc = off0 + S0 * ss;                             // first slot of the chunk
-    // the lane's work item (L2-resident table): x,y,z = nb[12]; w = c | u2x << 16
-    const uint4 it = sd_blk_ld_item(P.items + cls.item_off + u);
-    double2 acc[EC];
-#pragma unroll
-    for (int s = 0; s < EC; ++s) acc[s] = make_double2(0.0, 0.0);
-    const bool c0 = u < cls.n1;                                       // first mid bit (blocks with it set come first)
-    // ---- neighbour-tile streams, software-pipelined three deep and interleaved with the shared-memory
-    // work of the same item (the loads of the next round fly while tail and mid hops run):
-    //   entries 0 .. nnb-1 : prefix-internal bonds, whole neighbour tiles in the same element order
-    //   entry   nnb        : prefix|mid crossing bond (partner tile with js +- 1, same class, uniform
-    //                        block shift), only for lanes whose first mid bit differs from the last prefix bit
-    const int nnb = (P.dbg & 1) ? 0 : H.nnb;
-    const bool hasx = H.xptr != nullptr;
-    const int ntot = nnb + (hasx ? 1 : 0);
-    const double *xp = nullptr;
-    uint32_t xs = 0, xu = 0;
-    bool xlane = false;
-    if (hasx) {
-        const SdBlkCls cx = X.js[H.jsx].cls[jt];
-        xlane = c0 != (bool)H.bP;
-        xu = xlane ? (H.bP ? u - cls.n1 : cx.n1 + u) : 0u;
-        xs = 2u * cx.pitch;
-        xp = H.xptr + (size_t)(cx.cb * NC + 2u * xu) + (size_t)S0 * xs;
-    }
-    double2 t0[EC], t1[EC], t2[EC];
-    // V = 0: every load guarded and zero filled, coefficient selected per entry
-#define SD_BLK_LOAD(t_, n_)                                                                   \
-    do {                                                                                      \
-        const int nn_ = (n_);                                                                 \
-        const bool isx_ = nn_ == nnb;                                                         \
-        const bool ok_ = nn_ < ntot && (!isx_ || xlane);                                      \
-        const double *p_ = isx_ ? xp : H.nb_ptr[nn_] + offc;                                  \
-        const uint32_t st_ = isx_ ? xs : ss;                                                  \
-        _Pragma("unroll") for (int s = 0; s < EC; ++s) {                                      \
-            if (HALF && s == EC - 1)                                                          \
-                t_[s] = ok_ ? sd_blk_ldg_half(p_ + s * st_ - (isx_ ? xu : u)) : make_double2(0.0, 0.0); \
-            else t_[s] = ok_ ? sd_blk_ldg(p_ + s * st_) : make_double2(0.0, 0.0);             \
-        }                                                                                     \
-    } while (0)
-#define SD_BLK_FMA(t_, n_)                                                                    \
-    do {                                                                                      \
-        const int nn_ = (n_);                                                                 \
-        const double J_ = nn_ < nnb ? H.nb_J[nn_] : (nn_ == nnb && hasx ? H.Jx : 0.0);        \
-        _Pragma("unroll") for (int s = 0; s < EC; ++s) { acc[s].x += J_ * t_[s].x; acc[s].y += J_ * t_[s].y; } \
-    } while (0)
-    SD_BLK_LOAD(t0, 0); SD_BLK_LOAD(t1, 1); SD_BLK_LOAD(t2, 2);
-    // ---- own block: diagonal + tail-internal hops (registers)
-    const unsigned cmid = it.w & ((1u << M) - 1u);
-    const bool clast = (cmid >> (M - 1)) & 1u;
-    {
-        const double d0 = H.dP[c0 ? 1 : 0] + X.dmid[cmid];
-        const double dx0 = clast ? X.qx : -X.qx;
-        const double *op = tb + off0;
-        const double *Jt = X.Jhop + P.A + M;
-        static_assert(SD_BLK_T == 5, "item chunking is written for T = 5");
-        static_assert(HALF == (NC == 1 && EC != 5), "half slots: f64 classes of 1 and 5");
-        if constexpr (EC == 1) {
-            if (jt == 0) sd_blk_tail<NC, 0, 0, 1, 1>(acc, op, ss, u, Jt, X.dtail, d0, dx0);
-            else sd_blk_tail<NC, 5, 0, 1, 1>(acc, op, ss, u, Jt, X.dtail, d0, dx0);
-        } else if constexpr (EC == 3) {                            // f64, classes of 5 (+1 phantom)
-            if (jt == 1) sd_blk_tail<NC, 1, 0, 5, 3>(acc, op, ss, u, Jt, X.dtail, d0, dx0);
-            else sd_blk_tail<NC, 4, 0, 5, 3>(acc, op, ss, u, Jt, X.dtail, d0, dx0);
-        } else if constexpr (NC == 1) {                            // f64, classes of 10
-            if (jt == 2) sd_blk_tail<NC, 2, 0, 10, 5>(acc, op, ss, u, Jt, X.dtail, d0, dx0);
-            else sd_blk_tail<NC, 3, 0, 10, 5>(acc, op, ss, u, Jt, X.dtail, d0, dx0);
-        } else {                                                   // c128: chunks of 5 tail configurations
-            switch (jt * 2 + (S0 ? 1 : 0)) {
-                case 2: sd_blk_tail<NC, 1, 0, 5, 5>(acc, op, ss, u, Jt, X.dtail, d0, dx0); break;
-                case 4: sd_blk_tail<NC, 2, 0, 5, 5>(acc, op, ss, u, Jt, X.dtail, d0, dx0); break;
-                case 5: sd_blk_tail<NC, 2, 5, 5, 5>(acc, op, ss, u, Jt, X.dtail, d0, dx0); break;
-                case 6: sd_blk_tail<NC, 3, 0, 5, 5>(acc, op, ss, u, Jt, X.dtail, d0, dx0); break;
-                case 7: sd_blk_tail<NC, 3, 5, 5, 5>(acc, op, ss, u, Jt, X.dtail, d0, dx0); break;
-                default: sd_blk_tail<NC, 4, 0, 5, 5>(acc, op, ss, u, Jt, X.dtail, d0, dx0); break;
-            }
-        }
-    }
-    // ---- mid-internal hops (the whole block moves to block nb[pm] of the same class), a few bonds per
-    // stream round so that shared-memory gathers overlap the global loads in flight
-    const double *cbp = tb + cls.cb * NC + S0 * ss;
-    uint64_t lo = (uint64_t)it.x | ((uint64_t)it.y << 32);
-#define SD_BLK_MID_BODY(J, nbu)                                                               \
-    do {                                                                                      \
-        const double *sp = cbp + 2u * (nbu);                                                  \
-        _Pragma("unroll") for (int s = 0; s < EC; ++s) {                                      \
-            if (HALF && s == EC - 1) {                                                        \
-                acc[s].x += (J) * *(sp + s * ss - (nbu));                                     \
-            } else {                                                                          \
-                const double2 t = *(const double2 *)(sp + s * ss);                            \
-                acc[s].x += (J) * t.x;                                                        \
-                acc[s].y += (J) * t.y;                                                        \
-            }                                                                                 \
-        }                                                                                     \
-    } while (0)
-    {
-        uint32_t hi = it.z;
-        int pm = (P.dbg & 2) ? M : 0;
-#define SD_BLK_MID()                                                                          \
-    do {                                                                                      \
-        const double J = X.Jhop[P.A + pm];                                                    \
-        const unsigned nbu = (unsigned)(lo & 0xFFu);                                          \
-        lo = (lo >> 8) | ((uint64_t)hi << 56);                                                \
-        hi >>= 8;                                                                             \
-        ++pm;                                                                                 \
-        if (nbu != 0xFFu) SD_BLK_MID_BODY(J, nbu);                                            \
-    } while (0)
-#pragma unroll 1
-        for (int n = 0; n < ntot; n += 3) {
-#pragma unroll 1
-            for (int k = 0; k < 3 && pm + 1 < M; ++k) SD_BLK_MID();
-            SD_BLK_FMA(t0, n); SD_BLK_LOAD(t0, n + 3);
-            SD_BLK_FMA(t1, n + 1); SD_BLK_LOAD(t1, n + 4);
-            SD_BLK_FMA(t2, n + 2); SD_BLK_LOAD(t2, n + 5);
-        }
-#pragma unroll 1
-        while (pm + 1 < M) SD_BLK_MID();
-#undef SD_BLK_MID
-    }
-#undef SD_BLK_MID_BODY
-#undef SD_BLK_LOAD
-#undef SD_BLK_FMA
-    // ---- mid|tail crossing bond, per tail configuration.  Tail configurations with bit 0 set come first
-    // in a class: n1 = C(T-1, jt-1) of them.  Last mid bit set & tail bit 0 clear -> class jt+1,
-    // configuration e - n1; last mid bit clear & tail bit 0 set -> class jt-1, configuration C(T-1, jt-2) + e.
-    {
-        const double J = X.Jhop[P.A + M - 1];
-        // nibble i of the constant = C(4, i-2) (T = 5); nt = C(5, jt)
-        const int n1 = (int)((0x01464100u >> (4 * (jt + 1))) & 0xFu), n1p = (int)((0x01464100u >> (4 * jt)) & 0xFu);
-        const int nt = (int)((0x15AA51u >> (4 * jt)) & 0xFu);
-        const int jt2 = clast ? jt + 1 : jt - 1;
-        if (jt2 >= 0 && jt2 <= T) {
-            const SdBlkCls c2 = I.cls[jt2];
-            const uint32_t u2x = it.w >> 16;
-            const double *sp = tb + c2.cb * NC + 2u * u2x;             // slot 0 of the partner block
-            const uint32_t s2 = 2u * c2.pitch;
-            const int nt2 = (int)((0x15AA51u >> (4 * jt2)) & 0xFu);
-            const int shift = clast ? -n1 : n1p;                   // partner configuration = e + shift
-            constexpr int NEL = NC == 1 ? 2 * EC : EC;             // tail configurations covered by the chunk
-            const int e0 = NC == 1 ? 0 : S0;
-#pragma unroll
-            for (int e = 0; e < NEL; ++e) {
-                const int ee = e0 + e;
-                if (ee < nt && (clast ? (ee >= n1) : (ee < n1))) {
-                    const int e2 = ee + shift;
-                    if (NC == 1) {
-                        // the last configuration of an odd class is a plain row of doubles
-                        const double t = ((nt2 & 1) && e2 == nt2 - 1) ? *(sp + (e2 >> 1) * s2 - u2x) : *(sp + (e2 >> 1) * s2 + (e2 & 1));
-                        SD_BLK_EL(acc, e, 1) += J * t;
-                    } else {
-                        const double2 t = *(const double2 *)(sp + e2 * s2);
-                        acc[e].x += J * t.x;
-                        acc[e].y += J * t.y;
-                    }
-                }
-            }
-        }
-    }
-    // ---- epilogue + store
-    const uint64_t ld0 = (H.base - X.pstart_local) * NC + offc;    // doubles from the start of the local shard
-    double *o = X.out_local + ld0;
-    if (PLAIN) {
-        if (P.dbg & 4) { if (acc[0].x == 1.2345e300) sd_blk_stg(o, acc[0]); return; }
-#pragma unroll
-        for (int s = 0; s < EC; ++s) {
-            if (HALF && s == EC - 1) sd_blk_stg_half(o + s * ss - u, acc[s].x);
-            else sd_blk_stg(o + s * ss, acc[s]);
-        }
-    } else {
-        const SdEpi &E = *X.epi;
-#pragma unroll
-        for (int s = 0; s < EC; ++s) {
-            if (HALF && s == EC - 1) {
-                const uint64_t ld = ld0 + (uint64_t)s * ss - u;
-                SdVal<1> hh, pp;
-                hh.c[0] = acc[s].x; pp.c[0] = tb[offc + s * ss - u];
-                const SdVal<1> r0 = sd_epilogue<1>(E, hh, pp, ld, red);
-                *(o + s * ss - u) = r0.c[0];                    // pointer arithmetic: s * ss - u alone wraps in u32
-                continue;
-            }
-            const double2 p = *(const double2 *)(tb + offc + s * ss);
-            const uint64_t ld = ld0 + (uint64_t)s * ss;
-            double2 r;
-            if (NC == 2) {
-                SdVal<2> hh, pp;
-                hh.c[0] = acc[s].x; hh.c[1] = acc[s].y; pp.c[0] = p.x; pp.c[1] = p.y;
-                const SdVal<2> rr = sd_epilogue<2>(E, hh, pp, ld / 2, red);
-                r = make_double2(rr.c[0], rr.c[1]);
-            } else {
-                SdVal<1> hh, pp;
-                hh.c[0] = acc[s].x; pp.c[0] = p.x;
-                const SdVal<1> r0 = sd_epilogue<1>(E, hh, pp, ld, red);
-                hh.c[0] = acc[s].y; pp.c[0] = p.y;
-                const SdVal<1> r1 = sd_epilogue<1>(E, hh, pp, ld + 1, red);
-                r = make_double2(r0.c[0], r1.c[0]);
-            }
-            *(double2 *)(o + s * ss) = r;
-        }
-    }
-}
-
-// item code: jt << 12 | chunk << 8 | unit-in-class (units of 32 mid configurations).
-// f64: one chunk per class (1, 3 or 5 slots).  c128: classes of 10 -> two chunks of 5 slots.
-template <int NC, bool PLAIN, int V>
-SD_HD void sd_blk_dispatch(const SdBlkCtx &X, const SdBlkHdr &H, const double *tb, unsigned code,
-                                                uint32_t u, double (&red)[SD_NSLOT]) {
-    const int jt = (int)(code >> 12), S0 = ((code >> 8) & 0xFu) ? 5 : 0;
-    if (jt == 0 || jt == SD_BLK_T) sd_blk_item<NC, 1, NC == 1, PLAIN, V>(X, H, tb, jt, 0, u, red);
-    else if (NC == 1 && (jt == 1 || jt == SD_BLK_T - 1)) sd_blk_item<NC, (NC == 1 ? 3 : 5), NC == 1, PLAIN, V>(X, H, tb, jt, 0, u, red);
-    else sd_blk_item<NC, 5, false, PLAIN, V>(X, H, tb, jt, S0, u, red);
-}
-
-// shared-memory carve-up
+// the producer warp's view of the CTA's shared memory
 struct SdBlkSmem {
     uint64_t *full, *empty;      // [nbuf] mbarriers
     SdBlkHdr *hdr;               // [nbuf]
-    uint64_t *W;                 // [A*(A+1)]
-    SdBlkJs *js;                 // [B+1]
-    uint16_t *units;             // [(B+1)*MAXUNITS]
-    double *dmid;                // [1 << M]
-    double *dtail;               // [1 << T]
-    double *Jhop;                // [L + 1]
+    const uint64_t *W;           // [A*(A+1)] (global memory, L2 resident)
+    const SdBlkJs *js;           // [B+1]
     double *tiles;               // [nbuf][cap*NC]
 };
-SD_HD size_t sd_blk_smem_carve(SdBlkSmem *s, void *base, int A, int L, int nbuf, uint32_t cap, int NC) {
-    size_t o = 0;
-    auto take = [&](size_t bytes, size_t align) {
-        o = (o + align - 1) & ~(align - 1);
-        const size_t at = o;
-        o += bytes;
-        return at;
-    };
-    const size_t a_full = take(8 * (size_t)nbuf, 8), a_empty = take(8 * (size_t)nbuf, 8);
-    const size_t a_hdr = take(sizeof(SdBlkHdr) * (size_t)nbuf, 16);
-    const size_t a_W = take(8 * (size_t)A * (A + 1) + 8, 8);
-    const size_t a_js = take(sizeof(SdBlkJs) * (SD_BLK_B + 1), 16);
-    const size_t a_units = take(2 * (size_t)(SD_BLK_B + 1) * SD_BLK_MAXUNITS, 4);
-    const size_t a_dmid = take(8 * ((size_t)1 << SD_BLK_M), 16);
-    const size_t a_dtail = take(8 * ((size_t)1 << SD_BLK_T), 16);
-    const size_t a_J = take(8 * (size_t)(L + 1), 16);
-    const size_t a_tiles = take((size_t)nbuf * cap * NC * 8, 128);
-    if (s) {
-        char *b = (char *)base;
-        s->full = (uint64_t *)(b + a_full); s->empty = (uint64_t *)(b + a_empty);
-        s->hdr = (SdBlkHdr *)(b + a_hdr); s->W = (uint64_t *)(b + a_W); s->js = (SdBlkJs *)(b + a_js);
-        s->units = (uint16_t *)(b + a_units); s->dmid = (double *)(b + a_dmid); s->dtail = (double *)(b + a_dtail);
-        s->Jhop = (double *)(b + a_J); s->tiles = (double *)(b + a_tiles);
-    }
-    return (o + 127) & ~(size_t)127;
-}
 
 #if defined(__CUDACC__)
 // ------------------------------------------------------------------ PTX helpers
@@ -674,48 +388,7 @@ __device__ __forceinline__ void sd_bulk_g2s(void *dst, const void *src, unsigned
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(sd_smem_u32(dst)), "l"(src), "r"(bytes), "r"(sd_smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void sd_bulk_prefetch_l2(const void *src, unsigned bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void sd_bulk_prefetch_l2_evict_first(const void *src, unsigned bytes) {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(src), "r"(bytes), "l"(pol) : "memory");
-}
-__device__ __forceinline__ double2 sd_ldg_v2(const double *p) {
-    double2 v;
-    asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ double2 sd_ldg_v2_far(const double *p) {
-    double2 v;
-    asm("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ void sd_stg_v2(double *p, double2 v) {
-    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
-}
-
-// ------------------------------------------------------------------ the kernel
-// one-time setup of a CTA: tables -> shared memory, mbarriers
-template <int NC>
-__device__ __forceinline__ void sd_blk_cta_setup(const SdBlkParams &P, const SdBlkSmem &S, unsigned tid, unsigned nthr, unsigned ncons) {
-    for (int i = (int)tid; i < P.A * (P.A + 1); i += nthr) S.W[i] = P.W[i];
-    {
-        const uint32_t *src = (const uint32_t *)P.js;
-        uint32_t *dst = (uint32_t *)S.js;
-        for (int i = (int)tid; i < (int)(sizeof(SdBlkJs) * (SD_BLK_B + 1) / 4); i += nthr) dst[i] = src[i];
-    }
-    for (int i = (int)tid; i < (SD_BLK_B + 1) * SD_BLK_MAXUNITS; i += nthr)
-        S.units[i] = P.units[(NC - 1) * (SD_BLK_B + 1) * SD_BLK_MAXUNITS + i];
-    for (int i = (int)tid; i < (1 << SD_BLK_M); i += nthr) S.dmid[i] = P.dmid[i];
-    for (int i = (int)tid; i < (1 << SD_BLK_T); i += nthr) S.dtail[i] = P.dtail[i];
-    for (int i = (int)tid; i <= P.L; i += nthr) S.Jhop[i] = P.Jhop[i];
-    if (tid == 0) {
-        for (int b = 0; b < P.nbuf; ++b) { sd_mbar_init(&S.full[b], 1); sd_mbar_init(&S.empty[b], ncons); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-}
+// ------------------------------------------------------------------ producer warp and reduction tail (kernel: sd_blkl.h)
 // producer warp: tile keys from the global counter, tile headers, TMA of the own tiles
 template <int NC>
 __device__ __forceinline__ void sd_blk_producer(const SdBlkParams &P, const SdBlkSmem &S, const SdVecView &psi, int qfar,
@@ -782,55 +455,6 @@ __device__ __forceinline__ void sd_blk_item_reduce(SdBlkHdr &H, const SdEpi &epi
                 for (unsigned j = 0; j < nunits; ++j) t += ((volatile double *)H.usum[s])[j];
                 epi.partials[(size_t)s * epi.nparts + H.tile_index] = t;
             }
-        }
-    }
-}
-
-// grid = one persistent CTA per SM.  Tiles are handed out in key (= rank) order by a global counter, so
-// the tiles in flight form a tight window and near neighbour tiles are re-used from L2.
-// partials: [SD_NSLOT][ntiles] per-tile sums (zero-filled by the host before the launch: invalid tiles
-// write nothing); each is the in-order sum of the tile's per-item sums, so results are run-to-run identical.
-template <int NC, bool PLAIN, int V>
-__global__ void __launch_bounds__(SD_BLK_THREADS, 1)
-sd_blk_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constant__ SdVecView psi, double *out_local,
-                    const __grid_constant__ SdEpi epi, int qfar, unsigned long long *tile_ctr) {
-    extern __shared__ __align__(128) unsigned char sd_blk_smem[];
-    SdBlkSmem S;
-    sd_blk_smem_carve(&S, sd_blk_smem, P.A, P.L, P.nbuf, P.cap, NC);
-    const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
-    const int nbuf = P.nbuf;
-    sd_blk_cta_setup<NC>(P, S, tid, SD_BLK_THREADS, SD_BLK_CWARPS);
-    __syncthreads();
-    const size_t tile_doubles = (size_t)P.cap * NC;
-    if (warp == SD_BLK_CWARPS) {
-        sd_blk_producer<NC>(P, S, psi, qfar, tile_ctr, lane);
-    } else {
-        // ================= consumer warps
-        SdBlkCtx X;
-        sd_blk_ctx_init(X, P, S.js, S.dmid, S.dtail, S.Jhop, out_local, &epi);
-        const int slotmask = PLAIN ? 0 : sd_epi_slotmask(epi.red);
-        for (unsigned i = 0;; ++i) {
-            const int b = (int)(i % (unsigned)nbuf);
-            const unsigned round = i / (unsigned)nbuf;
-            sd_mbar_wait(&S.full[b], round & 1u);
-            SdBlkHdr &H = S.hdr[b];
-            if (H.valid < 0) break;
-            const double *tb = S.tiles + (size_t)b * tile_doubles;
-            const unsigned nunits = S.js[H.js].nunits[NC - 1];
-            const uint16_t *ut = S.units + H.js * SD_BLK_MAXUNITS;
-            for (;;) {
-                unsigned un = 0;
-                if (lane == 0) un = atomicAdd(&H.next_unit, 1u);
-                un = __shfl_sync(0xffffffffu, un, 0);
-                if (un >= nunits) break;
-                const unsigned code = ut[un];
-                const uint32_t u = (code & 0xFFu) * 32u + lane;      // the lane's mid configuration
-                double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
-                sd_blk_dispatch<NC, PLAIN, V>(X, H, tb, code, u, red);
-                if (!PLAIN && slotmask) sd_blk_item_reduce(H, epi, slotmask, un, nunits, red, lane);
-            }
-            __syncwarp();
-            if (lane == 0) sd_mbar_arrive(&S.empty[b]);
         }
     }
 }

@@ -14,7 +14,7 @@ struct SdBlkHost {
     std::vector<SdBlkJs> js;          // [B+1]
     std::vector<uint16_t> units;      // [2][(B+1)*MAXUNITS] item codes jt << 12 | chunk << 8 | unit-in-class
     std::vector<SdBlkItem> items;
-    std::vector<double> dmid;         // [1 << M]
+    std::vector<double> dmid;         // [1 << M], in item order (dmid[item index])
     std::vector<uint16_t> urank;      // [1 << M] class-local index of a mid configuration
     uint64_t n_store = 0;             // stored elements of the whole vector (all shards)
 };
@@ -43,7 +43,7 @@ static inline bool sd_blk_build(int L, int k, const double *Jhop, const double *
             o.urank[c] = (uint16_t)u;
         }
     }
-    o.dmid.assign((size_t)1 << M, 0.0);
+    std::vector<double> dmid_cfg((size_t)1 << M, 0.0);             // by mid configuration bits; stored in item order below
     for (unsigned c = 0; c < (1u << M); ++c) {
         double d = 0.0;
         for (int q = 0; q < M; ++q) {
@@ -51,8 +51,11 @@ static inline bool sd_blk_build(int L, int k, const double *Jhop, const double *
             d += h[A + q] * s;
             if (q + 1 < M) d += Jz[A + q] * s * (((c >> (q + 1)) & 1u) ? 0.5 : -0.5);
         }
-        o.dmid[c] = d;
+        dmid_cfg[c] = d;
     }
+    for (int q = 0; q < M; ++q) P.Jmid[q] = Jhop[A + q];             // [M-1]: the mid|tail bond
+    for (int q = 0; q + 1 < T; ++q) P.Jtail[q] = Jhop[A + M + q];
+    P.qx = Jz[A + M - 1] * 0.25;
     for (unsigned t = 0; t < (1u << T); ++t) {
         double d = 0.0;
         for (int q = 0; q < T; ++q) {
@@ -65,6 +68,7 @@ static inline bool sd_blk_build(int L, int k, const double *Jhop, const double *
     // work items: one list per mid popcount jm (shared by every (js, jt) with js - jt == jm)
     std::vector<uint32_t> item_off(M + 1, 0);
     o.items.clear();
+    o.dmid.clear();
     for (int jm = 0; jm <= M; ++jm) {
         item_off[jm] = (uint32_t)o.items.size();
         for (uint32_t u = 0; u < midcfg[jm].size(); ++u) {
@@ -87,6 +91,7 @@ static inline bool sd_blk_build(int L, int k, const double *Jhop, const double *
             it.nb[9] = (uint8_t)(amask & 0xFFu);
             it.nb[10] = (uint8_t)(amask >> 8);
             o.items.push_back(it);
+            o.dmid.push_back(dmid_cfg[c]);
         }
     }
     // per-js class layout

@@ -24,17 +24,17 @@ struct SdBlkShared {
     SdBlkHdr hdr[SD_BLKL_NBUF];
     SdBlkJs js[SD_BLK_B + 1];
     uint16_t units[(SD_BLK_B + 1) * SD_BLK_MAXUNITS];
-    double dmid[1 << SD_BLK_M];
-    double dtail[1 << SD_BLK_T];
-    double Jhop[SD_MAX_L + 1];
+    double dmid[1 << SD_BLK_M];  // diagonal of the mid sites, in item order: lanes = consecutive u read consecutive entries
     // per-launch context
     SdEpi epi;
-    double qx;                  // Jz of the mid|tail bond * 0.25
     double *out_local;          // local shard of out, component 0 of stored element 0
     uint64_t pstart_local;      // stored-element offset of the local shard
     const SdBlkItem *items;
-    int A;
 };
+// Model constants that are the same for every lane of a warp (mid / tail hop coefficients, tail diagonal, qx) are NOT in
+// shared memory: they are members of the __grid_constant__ kernel parameter P and reach the FP64 pipe as constant-bank
+// operands.  A warp-uniform LDS costs a full 128-byte wavefront of the LSU data pipe, which is this kernel's scarcest
+// resource (profiles/round2_b_apply_full.txt: 71 % busy, 12 % of it uniform table reads).
 #if defined(__CUDACC__)
 __shared__ SdBlkShared sd_blkl_sh;
 #define SD_SH sd_blkl_sh
@@ -47,15 +47,13 @@ static SdBlkShared sd_blkl_sh;
 // fills the context part of SD_SH (device: one thread, before the CTA barrier; host: the emulation)
 SD_BLKL_FN void sd_blkl_ctx_init(const SdBlkParams &P, double *out_local, const SdEpi &epi) {
     SD_SH.epi = epi;
-    SD_SH.qx = P.Jz[P.A + SD_BLK_M - 1] * 0.25;
     SD_SH.out_local = out_local;
     SD_SH.pstart_local = P.shards.pstart[P.shards.rank];
     SD_SH.items = P.items;
-    SD_SH.A = P.A;
 }
 
 template <int NC, int JT, int S0, bool PLAIN>
-SD_BLKL_FN void sd_blkl_item(const SdBlkHdr &H, const double *tb, uint32_t u, double (&red)[SD_NSLOT]) {
+SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdBlkHdr &H, const double *tb, uint32_t u, double (&red)[SD_NSLOT]) {
     constexpr int T = SD_BLK_T, M = SD_BLK_M;
     constexpr int NT = sd_cbinom(T, JT);
     constexpr int NO = NC == 1 ? (NT + 1) / 2 : NT;                  // slots of the whole block
@@ -104,39 +102,36 @@ SD_BLKL_FN void sd_blkl_item(const SdBlkHdr &H, const double *tb, uint32_t u, do
         }
     }
     // ---- prefix-internal bonds: whole neighbour tiles in the same element order
-    if (nnb > 0) SD_LEAN_LOAD(t0, H.nb_ptr[0]);
+    SdBlkEnt e0 = H.nb[0], e1;                                       // {tile base, J}: one LDS.128 per entry
+    if (nnb > 0) SD_LEAN_LOAD(t0, e0.p);
     if (xl) SD_LEAN_FMA(t1, H.Jx);
     int n = 0;
 #pragma unroll 1
     while (n + 1 < nnb) {
-        SD_LEAN_LOAD(t1, H.nb_ptr[n + 1]);
-        SD_LEAN_FMA(t0, H.nb_J[n]);
-        if (n + 2 < nnb) SD_LEAN_LOAD(t0, H.nb_ptr[n + 2]);
-        SD_LEAN_FMA(t1, H.nb_J[n + 1]);
+        e1 = H.nb[n + 1];
+        SD_LEAN_LOAD(t1, e1.p);
+        SD_LEAN_FMA(t0, e0.J);
+        if (n + 2 < nnb) { e0 = H.nb[n + 2]; SD_LEAN_LOAD(t0, e0.p); }
+        SD_LEAN_FMA(t1, e1.J);
         n += 2;
     }
-    if (n < nnb) SD_LEAN_FMA(t0, H.nb_J[n]);
+    if (n < nnb) SD_LEAN_FMA(t0, e0.J);
 #undef SD_LEAN_LOAD
 #undef SD_LEAN_FMA
     // ---- own block: diagonal + tail-internal hops (registers, compile-time permutation)
     const uint4 it = sd_blk_ld_item(SD_SH.items + cls.item_off + u);     // x,y,z = nb[12]; w = c | u2x << 16
     const unsigned cmid = it.w & ((1u << M) - 1u);
     const bool clast = (cmid >> (M - 1)) & 1u;
-    sd_blk_tail<NC, JT, E0, NE, EC>(acc, tb + off0, ss, u, SD_SH.Jhop + SD_SH.A + M, SD_SH.dtail, H.dP[c0 ? 1 : 0] + SD_SH.dmid[cmid],
-                                    clast ? SD_SH.qx : -SD_SH.qx);
+    sd_blk_tail<NC, JT, E0, NE, EC>(acc, tb + off0, ss, u, P.Jtail, P.dtail, H.dP[c0 ? 1 : 0] + SD_SH.dmid[cls.item_off + u],
+                                    clast ? P.qx : -P.qx);
     // ---- mid-internal hops: the whole block moves to block nb[pm] of the same class
     {
         const double *cbp = tb + cls.cb * NC + (uint32_t)S0 * ss;
-        const double *Jm = SD_SH.Jhop + SD_SH.A;
-        uint64_t lo = (uint64_t)it.x | ((uint64_t)it.y << 32);
-        uint32_t hi = it.z;
-#pragma unroll 1
-        for (int pm = 0; pm + 1 < M; ++pm) {
-            const unsigned nbu = (unsigned)(lo & 0xFFu);
-            lo = (lo >> 8) | ((uint64_t)hi << 56);
-            hi >>= 8;
+#pragma unroll
+        for (int pm = 0; pm + 1 < M; ++pm) {                          // fully unrolled: byte extract and J are compile-time selected
+            const unsigned nbu = ((pm < 4 ? it.x : (pm < 8 ? it.y : it.z)) >> (8 * (pm & 3))) & 0xFFu;
             if (nbu != 0xFFu) {
-                const double J = Jm[pm];
+                const double J = P.Jmid[pm];
                 const double *sp = cbp + 2u * nbu;
 #pragma unroll
                 for (int s = 0; s < EC; ++s) {
@@ -156,7 +151,7 @@ SD_BLKL_FN void sd_blkl_item(const SdBlkHdr &H, const double *tb, uint32_t u, do
     // clear & tail bit 0 set -> class JT-1, configuration C(T-1, JT-2) + e.  u2x: the block with the last mid bit flipped.
     {
         constexpr int n1 = sd_cbinom(T - 1, JT - 1);
-        const double J = SD_SH.Jhop[SD_SH.A + M - 1];
+        const double J = P.Jmid[M - 1];
         const uint32_t u2x = it.w >> 16;
 #define SD_LEAN_CROSS(JT2_, ELO_, EHI_, SHIFT_)                                               \
     do {                                                                                      \
@@ -231,21 +226,21 @@ SD_BLKL_FN void sd_blkl_item(const SdBlkHdr &H, const double *tb, uint32_t u, do
     }
 }
 template <int NC, bool PLAIN>
-SD_BLKL_FN void sd_blkl_dispatch(const SdBlkHdr &H, const double *tb, unsigned code, uint32_t u,
+SD_BLKL_FN void sd_blkl_dispatch(const SdBlkParams &P, const SdBlkHdr &H, const double *tb, unsigned code, uint32_t u,
                                 double (&red)[SD_NSLOT]) {
     const int jt = (int)(code >> 12);
     const bool hi = ((code >> 8) & 0xFu) != 0;                       // c128, classes of 10: second chunk of five
     switch (jt) {
-        case 0: sd_blkl_item<NC, 0, 0, PLAIN>(H, tb, u, red); break;
-        case 1: sd_blkl_item<NC, 1, 0, PLAIN>(H, tb, u, red); break;
+        case 0: sd_blkl_item<NC, 0, 0, PLAIN>(P, H, tb, u, red); break;
+        case 1: sd_blkl_item<NC, 1, 0, PLAIN>(P, H, tb, u, red); break;
         case 2:
-            if constexpr (NC == 2) { if (hi) { sd_blkl_item<NC, 2, 5, PLAIN>(H, tb, u, red); break; } }
-            sd_blkl_item<NC, 2, 0, PLAIN>(H, tb, u, red); break;
+            if constexpr (NC == 2) { if (hi) { sd_blkl_item<NC, 2, 5, PLAIN>(P, H, tb, u, red); break; } }
+            sd_blkl_item<NC, 2, 0, PLAIN>(P, H, tb, u, red); break;
         case 3:
-            if constexpr (NC == 2) { if (hi) { sd_blkl_item<NC, 3, 5, PLAIN>(H, tb, u, red); break; } }
-            sd_blkl_item<NC, 3, 0, PLAIN>(H, tb, u, red); break;
-        case 4: sd_blkl_item<NC, 4, 0, PLAIN>(H, tb, u, red); break;
-        default: sd_blkl_item<NC, 5, 0, PLAIN>(H, tb, u, red); break;
+            if constexpr (NC == 2) { if (hi) { sd_blkl_item<NC, 3, 5, PLAIN>(P, H, tb, u, red); break; } }
+            sd_blkl_item<NC, 3, 0, PLAIN>(P, H, tb, u, red); break;
+        case 4: sd_blkl_item<NC, 4, 0, PLAIN>(P, H, tb, u, red); break;
+        default: sd_blkl_item<NC, 5, 0, PLAIN>(P, H, tb, u, red); break;
     }
 }
 
@@ -269,8 +264,6 @@ sd_blkl_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constan
     for (int i = (int)tid; i < (SD_BLK_B + 1) * SD_BLK_MAXUNITS; i += NTHR)
         SD_SH.units[i] = P.units[(NC - 1) * (SD_BLK_B + 1) * SD_BLK_MAXUNITS + i];
     for (int i = (int)tid; i < (1 << SD_BLK_M); i += NTHR) SD_SH.dmid[i] = P.dmid[i];
-    for (int i = (int)tid; i < (1 << SD_BLK_T); i += NTHR) SD_SH.dtail[i] = P.dtail[i];
-    for (int i = (int)tid; i <= P.L; i += NTHR) SD_SH.Jhop[i] = P.Jhop[i];
     if (tid == 0) {
         sd_blkl_ctx_init(P, out_local, epi);
         for (unsigned b = 0; b < nbuf; ++b) { sd_mbar_init(&SD_SH.full[b], 1); sd_mbar_init(&SD_SH.empty[b], NCONS); }
@@ -280,8 +273,7 @@ sd_blkl_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constan
     const unsigned tile_doubles = P.cap * NC;
     if (warp == NCONS) {
         SdBlkSmem S;
-        S.full = SD_SH.full; S.empty = SD_SH.empty; S.hdr = SD_SH.hdr; S.W = const_cast<uint64_t *>(P.W);   // W: read from L2
-        S.js = SD_SH.js; S.units = SD_SH.units; S.dmid = SD_SH.dmid; S.dtail = SD_SH.dtail; S.Jhop = SD_SH.Jhop;
+        S.full = SD_SH.full; S.empty = SD_SH.empty; S.hdr = SD_SH.hdr; S.W = P.W; S.js = SD_SH.js;
         S.tiles = (double *)sd_blk_smem;
         sd_blk_producer<NC>(P, S, psi, qfar, tile_ctr, lane);
     } else {
@@ -301,7 +293,7 @@ sd_blkl_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constan
                 const unsigned code = SD_SH.units[H.js * SD_BLK_MAXUNITS + un];
                 const uint32_t u = (code & 0xFFu) * 32u + lane;      // the lane's mid configuration
                 double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
-                sd_blkl_dispatch<NC, PLAIN>(H, tb, code, u, red);
+                sd_blkl_dispatch<NC, PLAIN>(P, H, tb, code, u, red);
                 if (!PLAIN && slotmask) sd_blk_item_reduce(H, epi, slotmask, un, nunits, red, lane);
             }
             __syncwarp();

@@ -54,7 +54,7 @@ static inline void sd_halo_tile_remotes(const SdBlkHost &bh, const SdBlkParams &
     }
     for (int q = 0; q < 32; ++q) sd_blk_hdr_fill<1>(P, lanes[q], Pb, key, base, dpre, actmask, qfar, q, H, fake);
     for (int n = 0; n < H.ntot; ++n) {
-        const uint64_t v = (uint64_t)(uintptr_t)H.nb_ptr[n];
+        const uint64_t v = (uint64_t)(uintptr_t)H.nb[n].p;
         const int g = (int)(v >> 56) - 1;
         const uint64_t nbase = (v & ((1ULL << 56) - 1ULL)) / sizeof(double);
         if (g == P.shards.rank) continue;

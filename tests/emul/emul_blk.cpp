@@ -32,20 +32,15 @@ struct AlignedBuf {                      // 128-byte aligned doubles (the kernel
     ~AlignedBuf() { free(p); }
 };
 
-template <int NC, bool PLAIN, int V>
+template <int NC, bool PLAIN>
 void run_tiles(const SdBlkHost &bh, const SdBlkParams &P, const SdVecView &psi, double *out_local, const SdEpi &epi,
                int qfar, double *red_total) {
     AlignedBuf tile;
     tile.alloc((size_t)P.cap * NC, NAN);
-    SdBlkCtx X;
-    sd_blk_ctx_init(X, P, bh.js.data(), bh.dmid.data(), P.dtail, P.Jhop, out_local, &epi);
-    if (V == 1) {                                                   // lean kernel: tables + context in the static block SD_SH
-        std::memcpy(SD_SH.js, bh.js.data(), sizeof(SdBlkJs) * (SD_BLK_B + 1));
-        std::memcpy(SD_SH.dmid, bh.dmid.data(), sizeof(double) << SD_BLK_M);
-        std::memcpy(SD_SH.dtail, P.dtail, sizeof(double) << SD_BLK_T);
-        std::memcpy(SD_SH.Jhop, P.Jhop, sizeof(double) * (SD_MAX_L + 1));
-        sd_blkl_ctx_init(P, out_local, epi);
-    }
+    // tables + context of the kernel's static shared-memory block SD_SH
+    std::memcpy(SD_SH.js, bh.js.data(), sizeof(SdBlkJs) * (SD_BLK_B + 1));
+    std::memcpy(SD_SH.dmid, bh.dmid.data(), sizeof(double) << SD_BLK_M);
+    sd_blkl_ctx_init(P, out_local, epi);
     for (uint64_t key = P.key_lo; key < P.key_hi; ++key) {
         const uint64_t Pb = sd_blk_key_prefix(key, P.A);
         const int js = P.k - SD_POPC64(Pb);
@@ -53,7 +48,7 @@ void run_tiles(const SdBlkHost &bh, const SdBlkParams &P, const SdVecView &psi, 
         // ---- header: what the producer warp computes with shuffles
         SdBlkHdr H;
         std::memset(&H, 0, sizeof(H));
-        for (double &j : H.nb_J) j = NAN;                            // entries the header does not write must never be used
+        for (SdBlkEnt &e : H.nb) { e.p = nullptr; e.J = NAN; }       // entries the header does not write must never be used
         SdBlkHdrLane lanes[32];
         uint64_t base = 0;
         double dpre = 0.0;
@@ -78,8 +73,7 @@ void run_tiles(const SdBlkHost &bh, const SdBlkParams &P, const SdVecView &psi, 
             for (unsigned lane = 0; lane < 32; ++lane) {
                 const uint32_t u = (code & 0xFFu) * 32u + lane;
                 double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
-                if (V == 1) sd_blkl_dispatch<NC, PLAIN>(H, tile.p, code, u, red);
-                else sd_blk_dispatch<NC, PLAIN, 0>(X, H, tile.p, code, u, red);
+                sd_blkl_dispatch<NC, PLAIN>(P, H, tile.p, code, u, red);
                 for (int s = 0; s < SD_NSLOT; ++s) red_total[s] += red[s];
             }
         }
@@ -113,10 +107,9 @@ int emul_blk_apply(int L, int k, const double *Jhop, const double *Jz, const dou
     }
     SdBlkParams P = bh.P;
     P.W = bh.W.data(); P.js = bh.js.data(); P.units = bh.units.data(); P.items = bh.items.data(); P.dmid = bh.dmid.data();
-    P.nbuf = 3; P.dbg = 0;
+    P.nbuf = 3;
     const bool halo = (variant & 256) != 0;                          // + 256: through the halo mirror (sd_halo_host.h), 3 chunks
     // + 512: remote-volume-weighted shard bounds (sd_halo_balance), applied above where the bounds are computed
-    variant &= 255;                                                  // 0: round-1 item body (sd_blk.h), 1: lean kernel (sd_blkl.h)
     P.key_lo = keys[rank]; P.key_hi = keys[rank + 1];
     P.shards.world = world; P.shards.rank = rank;
     uint64_t pstart[SD_MAX_WORLD + 1];
@@ -166,8 +159,7 @@ int emul_blk_apply(int L, int k, const double *Jhop, const double *Jz, const dou
     if (acc) { to_blk(acc, s_acc, nullptr); epi.acc = s_acc[rank].p; }
     double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
     const bool plain = epi.mode == SD_EPI_PLAIN && epi.red == 0 && !epi.acc && epi.hscale == 1.0;
-#define RUN(NC_, PLAIN_) do { if (variant == 1) run_tiles<NC_, PLAIN_, 1>(bh, P, view, o.p, epi, qfar, red); \
-                              else run_tiles<NC_, PLAIN_, 0>(bh, P, view, o.p, epi, qfar, red); } while (0)
+#define RUN(NC_, PLAIN_) run_tiles<NC_, PLAIN_>(bh, P, view, o.p, epi, qfar, red)
     // halo mirror: the peers' shards are replaced by NaN-filled mirrors that only hold what the plan copies, chunk by
     // chunk, before the tiles of that chunk run (what sd_apply_blk_halo does with the copy engines and one event per chunk)
     SdHaloPlan plan;

@@ -32,14 +32,11 @@ def load():
     return lib
 
 
-VARIANT = 0          # kernel variant run() uses; the `emul` fixture runs every test with each:
-#                      1 = the lean kernel's item body (sd_blkl.h, the default), 0 = the round-1 body (sd_blk.h)
+VARIANT = 0          # flags of emul_blk_apply: + 256 through the halo mirror, + 512 remote-weighted shard bounds
 
 
-@pytest.fixture(scope="module", params=[1, 0], ids=["lean", "body0"])
-def emul(request):
-    global VARIANT
-    VARIANT = request.param
+@pytest.fixture(scope="module")
+def emul():
     return load()
 
 
@@ -376,7 +373,7 @@ def test_remote_weighted_shard_bounds(L, k, world):
         assert sizes[2] < 0.7 and sizes[5] < 0.7 and sizes[0] > 1.05
 
 
-@pytest.mark.parametrize("variant", [256 + 1, 256 + 0, 256 + 512 + 1, 512 + 1], ids=["halo", "halo_body0", "halo_bal", "bal"])
+@pytest.mark.parametrize("variant", [256, 256 + 512, 512], ids=["halo", "halo_bal", "bal"])
 @pytest.mark.parametrize("L,k,world", [(18, 9, 2), (20, 10, 4), (20, 10, 8), (22, 11, 8), (20, 6, 5)])
 def test_sharded_apply_through_the_halo_mirror(variant, L, k, world):
     """SD_HALO=1 / SD_SHARD_BALANCE=1 end to end on the CPU: every rank runs the emulated kernel on NaN-filled mirrors of
