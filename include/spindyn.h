@@ -82,6 +82,13 @@ int sd_nccl_unique_id(void *id128);
 int sd_ctx_create_rank(int device, int rank, int world, const void *id128, sd_ctx **ctx);
 int sd_ctx_free(sd_ctx *ctx);
 int sd_ctx_sync(sd_ctx *ctx);
+/* Multi-rank contract (world > 1): every rank makes the same library calls in the same order (SPMD).  Collective
+ * calls are sd_model_create, sd_vec_alloc, sd_ctx_collect, every call that returns a reduced scalar, and the solvers
+ * built on them.  sd_vec_free is NOT collective (finalizers may call it at any time): the local shard stays allocated
+ * until every rank has freed the same vector and a later sd_vec_alloc / sd_ctx_collect has told the peers.  The
+ * library orders peer reads against writes itself (it tracks which vectors were written or gathered since the last
+ * collective and inserts a stream-ordered barrier where needed); callers never synchronise ranks by hand. */
+int sd_ctx_collect(sd_ctx *ctx);
 int sd_ctx_rank(const sd_ctx *ctx, int *rank, int *world);
 /* CUDA-event stopwatch on the context's stream (bench.py uses it so the timed
  * region is measured on the stream the kernels are launched on). */
@@ -121,8 +128,8 @@ int sd_unrank(sd_model *model, uint64_t first, uint64_t count, uint64_t *states)
 int sd_rank(sd_model *model, const uint64_t *states, uint64_t count, int64_t *idx1);
 
 /* ------------------------------------------------------------------ vectors */
-int sd_vec_alloc(sd_model *model, int dtype, sd_vec **vec);
-int sd_vec_free(sd_vec *vec);
+int sd_vec_alloc(sd_model *model, int dtype, sd_vec **vec);   /* collective when world > 1 */
+int sd_vec_free(sd_vec *vec);                                 /* local; see the multi-rank contract above */
 int sd_vec_dtype(const sd_vec *vec, int *dtype);
 int sd_vec_local_len(const sd_vec *vec, uint64_t *n);
 int sd_vec_upload(sd_vec *vec, const void *host);       /* local shard, synchronous   */

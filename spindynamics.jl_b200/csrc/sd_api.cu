@@ -162,13 +162,27 @@ struct sd_ctx {
     double *h_scal = nullptr;       // pinned mirror
     double *d_partials = nullptr;
     size_t partials_cap = 0;        // doubles
-    unsigned char *d_ipc = nullptr; // [world*64] handle exchange buffer
+    unsigned char *d_ipc = nullptr; // [(world + 1) * 128] exchange buffer of sd_exchange
+    std::vector<unsigned char> h_ipc;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint64_t launches = 0;
     std::vector<uint64_t> binom;
     unsigned long long *d_tilectr = nullptr;  // tile counter of the block kernel's dynamic scheduler
     void *scratch[2] = {nullptr, nullptr};   // rank-ordered staging of block-layout vectors (upload/download/szq)
     size_t scratch_cap[2] = {0, 0};
+    // ---- cross-rank ordering of sharded vectors (world > 1).  Every rank makes the same API calls in the same order
+    // (SPMD), vector ids are handed out by the collective sd_vec_alloc, so these sets evolve identically on all ranks and
+    // the barriers they trigger pair up.  Both are emptied by every collective (all ranks' earlier kernels have finished).
+    std::vector<uint64_t> dirty_ids;         // vectors written since the last collective: peers must not gather them yet
+    std::vector<uint64_t> read_ids;          // vectors an apply gathered from since the last collective: peers may still read the local shard
+    uint64_t next_vec_id = 1;
+    // ---- deferred release of IPC-exported shards (world > 1): sd_vec_free is LOCAL (finalizers run at different times
+    // on different ranks); a shard is cudaFree'd once every rank has announced the free of that vector id, which the
+    // ranks tell each other inside the next collective sd_vec_alloc / sd_ctx_collect.
+    struct Dead { uint64_t id; double *d; };
+    std::vector<Dead> dead;                  // local shards waiting for the peers to unmap them
+    std::vector<uint64_t> outbox;            // locally freed ids not yet announced
+    std::vector<std::pair<uint64_t, int>> freed_count;   // id -> ranks that announced it
 };
 
 struct SdBlkDev {
@@ -183,7 +197,7 @@ struct SdBlkDev {
     int nbuf[2] = {0, 0};
     size_t smem[2] = {0, 0};
     int qfar[2] = {0, 0};
-    int threads = 768;              // CTA size of sd_blkl_apply_kernel (SD_BLKL_THREADS = 512 | 640 | 768, read once at model creation)
+    int threads = 640;              // CTA size of sd_blkl_apply_kernel (SD_BLKL_THREADS = 512 | 640 | 768, read once at model creation)
     uint32_t *d_order = nullptr;    // breadth-first tile order of this rank's shard (vectors larger than the L2)
     uint32_t norder = 0;
     // halo mirror of sharded applies (SD_HALO=1, sd_halo_host.h): chunked copy-engine prefetch of the peer ranges the
@@ -232,6 +246,7 @@ struct sd_model {
     SdBlkDev blk;                   // block-layout kernel (sd_blk.h)
     bool blk_layout = false;        // vectors of this model are stored in block layout
     int live_vecs = 0;
+    bool free_pending = false;      // sd_model_free was called while vectors were alive
 };
 
 struct sd_vec {
@@ -240,6 +255,7 @@ struct sd_vec {
     uint64_t local_n = 0;           // STORED elements of the local shard (block layout: padded)
     uint64_t logical_n = 0;         // basis states of the local shard
     int layout = 0;                 // 0: rank order, 1: block layout
+    uint64_t id = 0;                // collective allocation number (same on every rank)
     double *d = nullptr;
     SdVecView view;
     void *peer[SD_MAX_WORLD];
@@ -275,13 +291,16 @@ static int sd_partials_reserve(sd_ctx *c, size_t doubles) {
     c->partials_cap = cap;
     return SD_OK;
 }
+static inline void sd_collective_done(sd_ctx *c) { c->dirty_ids.clear(); c->read_ids.clear(); }
 // partials[slot*nparts + i] -> d_scal[slot_out + slot] (+ NCCL sum over ranks)
 static int sd_finish_reduce(sd_ctx *c, unsigned nparts, int slotmask, int slot_out) {
     sd_reduce_partials_kernel<<<1, 1024, 0, c->stream>>>(c->d_partials, nparts, slotmask, c->d_scal + slot_out);
     SD_TRY(sd_launch_check(c, "sd_reduce_partials_kernel"));
-    if (c->world > 1)
+    if (c->world > 1) {
         SD_NCCL(g_nccl.AllReduce(c->d_scal + slot_out, c->d_scal + slot_out, SD_NSLOT, ncclFloat64_, ncclSum_,
                                  c->comm, c->stream));
+        sd_collective_done(c);
+    }
     return SD_OK;
 }
 static int sd_fetch(sd_ctx *c, int slot, int n, double *out) {
@@ -296,6 +315,30 @@ static int sd_rank_barrier(sd_ctx *c) {
     if (c->world <= 1) return SD_OK;
     SD_NCCL(g_nccl.AllReduce(c->d_scal + SD_NSCAL - 8, c->d_scal + SD_NSCAL - 8, 1, ncclFloat64_, ncclSum_,
                              c->comm, c->stream));
+    sd_collective_done(c);
+    return SD_OK;
+}
+static inline bool sd_id_in(const std::vector<uint64_t> &v, uint64_t id) {
+    for (uint64_t x : v) if (x == id) return true;
+    return false;
+}
+// Call before launching anything that WRITES v: if a peer may still be gathering v (an apply read it since the last
+// collective), wait for the peers first; then v counts as not yet visible to the peers.
+static int sd_before_write(sd_ctx *c, const sd_vec *v) {
+    if (c->world <= 1) return SD_OK;
+    if (sd_id_in(c->read_ids, v->id)) SD_TRY(sd_rank_barrier(c));
+    if (!sd_id_in(c->dirty_ids, v->id)) c->dirty_ids.push_back(v->id);
+    return SD_OK;
+}
+// Call before an apply gathers psi from the peers' shards and writes out (and acc): psi must be complete everywhere
+// (not written since the last collective) and nobody may still be reading out / acc.
+static int sd_before_apply(sd_ctx *c, const sd_vec *out, const sd_vec *psi, const sd_vec *acc) {
+    if (c->world <= 1) return SD_OK;
+    if (sd_id_in(c->dirty_ids, psi->id) || sd_id_in(c->read_ids, out->id) || (acc && sd_id_in(c->read_ids, acc->id)))
+        SD_TRY(sd_rank_barrier(c));
+    if (!sd_id_in(c->read_ids, psi->id)) c->read_ids.push_back(psi->id);
+    if (!sd_id_in(c->dirty_ids, out->id)) c->dirty_ids.push_back(out->id);
+    if (acc && !sd_id_in(c->dirty_ids, acc->id)) c->dirty_ids.push_back(acc->id);
     return SD_OK;
 }
 
@@ -348,7 +391,7 @@ static int sd_ctx_init(int device, int rank, int world, const void *id128, sd_ct
         ncclUniqueId id;
         memcpy(&id, id128, sizeof(id));
         SD_NCCL(g_nccl.CommInitRank(&c->comm, world, id, rank));
-        SD_CUDA(cudaMalloc(&c->d_ipc, (size_t)(world + 1) * 64));
+        SD_CUDA(cudaMalloc(&c->d_ipc, (size_t)(world + 1) * 128));
     }
     *out = c;
     return SD_OK;
@@ -491,8 +534,8 @@ static int sd_blk_setup(sd_model *m) {
     for (size_t i = 0; i < m->hop_a.size(); ++i) Jhop[m->hop_a[i]] += m->hop_J[i];
     for (size_t i = 0; i < m->zz_a.size(); ++i) Jz[m->zz_a[i]] += m->zz_J[i];
     if (!sd_blk_build(L, m->k, Jhop.data(), Jz.data(), m->field.data(), b.host)) return SD_OK;
-    b.threads = sd_env_int("SD_BLKL_THREADS", 768);
-    if (b.threads != 512 && b.threads != 640) b.threads = 768;
+    b.threads = sd_env_int("SD_BLKL_THREADS", 640);
+    if (b.threads != 512 && b.threads != 768) b.threads = 640;
     for (int w = 0; w < 2; ++w) {
         const int nc = w + 1;
         int nbuf = w == 0 ? 3 : 2;
@@ -668,8 +711,14 @@ int sd_model_create(sd_ctx *ctx, int L, int nup, const sd_bond *hop, int nhop, c
     return SD_OK;
 }
 
+// Finalizer order is unspecified (Julia, Python shutdown): a model that still has live vectors is only marked and
+// released by the sd_vec_free of its last vector.
 int sd_model_free(sd_model *m) {
     if (!m) return SD_OK;
+    {
+        SD_LOCK(m->ctx);
+        if (m->live_vecs > 0) { m->free_pending = true; return SD_OK; }
+    }
     cudaSetDevice(m->ctx->device);
     cudaStreamSynchronize(m->ctx->stream);
     cudaFree(m->d_hop_a); cudaFree(m->d_hop_b); cudaFree(m->d_hop_J);
@@ -783,6 +832,46 @@ int sd_rank(sd_model *m, const uint64_t *states, uint64_t count, int64_t *idx1) 
 }
 
 // ------------------------------------------------------------------ vectors
+// One all-gather of 128 bytes per rank: [0,64) the IPC handle of *dptr (zeros if dptr is null), [64,120) up to 7 vector
+// ids this rank has freed since its last announcement, [120,128) how many more it still has to announce.  Every rank
+// counts the announcements; a shard is released when all ranks have freed its vector.
+static int sd_exchange(sd_ctx *c, double **dptr) {
+    unsigned char mine[128];
+    memset(mine, 0, sizeof(mine));
+    if (dptr) {
+        cudaIpcMemHandle_t hnd;
+        SD_CUDA(cudaIpcGetMemHandle(&hnd, *dptr));
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        memcpy(mine, &hnd, 64);
+    }
+    const size_t nsend = std::min<size_t>(7, c->outbox.size());
+    for (size_t i = 0; i < nsend; ++i) memcpy(mine + 64 + 8 * i, &c->outbox[i], 8);
+    c->outbox.erase(c->outbox.begin(), c->outbox.begin() + nsend);
+    const uint64_t pending = c->outbox.size();
+    memcpy(mine + 120, &pending, 8);
+    unsigned char *d_mine = c->d_ipc + (size_t)c->world * 128;
+    SD_CUDA(cudaMemcpyAsync(d_mine, mine, 128, cudaMemcpyHostToDevice, c->stream));
+    SD_NCCL(g_nccl.AllGather(d_mine, c->d_ipc, 128, ncclUint8_, c->comm, c->stream));
+    sd_collective_done(c);
+    c->h_ipc.resize((size_t)c->world * 128);
+    SD_CUDA(cudaMemcpyAsync(c->h_ipc.data(), c->d_ipc, (size_t)c->world * 128, cudaMemcpyDeviceToHost, c->stream));
+    SD_CUDA(cudaStreamSynchronize(c->stream));
+    for (int g = 0; g < c->world; ++g)
+        for (int i = 0; i < 7; ++i) {
+            uint64_t id;
+            memcpy(&id, c->h_ipc.data() + (size_t)g * 128 + 64 + 8 * i, 8);
+            if (!id) continue;
+            size_t k = 0;
+            while (k < c->freed_count.size() && c->freed_count[k].first != id) ++k;
+            if (k == c->freed_count.size()) c->freed_count.push_back({id, 0});
+            if (++c->freed_count[k].second == c->world) {            // every rank has unmapped it: release the local shard
+                for (size_t j = 0; j < c->dead.size(); ++j)
+                    if (c->dead[j].id == id) { cudaFree(c->dead[j].d); c->dead.erase(c->dead.begin() + j); break; }
+                c->freed_count.erase(c->freed_count.begin() + k);
+            }
+        }
+    return SD_OK;
+}
 int sd_vec_alloc(sd_model *m, int dtype, sd_vec **vec) {
     SD_ARG(m && vec, "NULL argument");
     *vec = nullptr;
@@ -810,21 +899,17 @@ int sd_vec_alloc(sd_model *m, int dtype, sd_vec **vec) {
         if (e != cudaSuccess) { cudaFree(v->d); delete v; return sd_fail(SD_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e)); }
     }
     v->view.base[c->rank] = v->d - (int64_t)ls * v->nc;
+    v->id = c->next_vec_id++;
     m->live_vecs++;
     if (c->world > 1) {
-        // collective: exchange CUDA IPC handles, map every peer shard
-        cudaIpcMemHandle_t hnd;
-        SD_CUDA(cudaIpcGetMemHandle(&hnd, v->d));
-        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-        SD_CUDA(cudaMemcpyAsync(c->d_ipc + (size_t)c->world * 64, &hnd, 64, cudaMemcpyHostToDevice, c->stream));
-        SD_NCCL(g_nccl.AllGather(c->d_ipc + (size_t)c->world * 64, c->d_ipc, 64, ncclUint8_, c->comm, c->stream));
-        std::vector<cudaIpcMemHandle_t> all(c->world);
-        SD_CUDA(cudaMemcpyAsync(all.data(), c->d_ipc, (size_t)c->world * 64, cudaMemcpyDeviceToHost, c->stream));
-        SD_CUDA(cudaStreamSynchronize(c->stream));
+        // collective: exchange CUDA IPC handles (64 bytes) and up to 7 locally freed vector ids (64 bytes), map every peer shard
+        SD_TRY(sd_exchange(c, &v->d));
         for (int g = 0; g < c->world; ++g) {
             if (g == c->rank) continue;
+            cudaIpcMemHandle_t hnd;
+            memcpy(&hnd, c->h_ipc.data() + (size_t)g * 128, 64);
             void *p = nullptr;
-            SD_CUDA(cudaIpcOpenMemHandle(&p, all[g], cudaIpcMemLazyEnablePeerAccess));
+            SD_CUDA(cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess));
             v->peer[g] = p;
             v->view.base[g] = (const double *)p - (int64_t)starts[g] * v->nc;
         }
@@ -832,17 +917,45 @@ int sd_vec_alloc(sd_model *m, int dtype, sd_vec **vec) {
     *vec = v;
     return SD_OK;
 }
+// Not collective.  With world > 1 the local shard stays allocated (peers may still have it mapped and may still read
+// it) until every rank has freed the same vector and said so in a later collective (sd_vec_alloc / sd_ctx_collect);
+// finalizers may therefore call this at any time and in any order.
 int sd_vec_free(sd_vec *v) {
     if (!v) return SD_OK;
     sd_ctx *c = v->model->ctx;
+    SD_LOCK(c);
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (int g = 0; g < SD_MAX_WORLD; ++g)
         if (v->peer[g]) cudaIpcCloseMemHandle(v->peer[g]);
-    if (c->world > 1) sd_rank_barrier(c), cudaStreamSynchronize(c->stream);   // peers unmapped before the free
-    if (v->owned) cudaFree(v->d);
-    v->model->live_vecs--;
+    if (c->world > 1) {
+        c->outbox.push_back(v->id);
+        if (v->owned) c->dead.push_back({v->id, v->d});
+    } else if (v->owned) {
+        cudaFree(v->d);
+    }
+    sd_model *m = v->model;
+    const bool last = --m->live_vecs == 0 && m->free_pending;
     delete v;
+    if (last) { m->free_pending = false; return sd_model_free(m); }   // the lock is recursive
+    return SD_OK;
+}
+// Collective (world > 1): announces locally freed vectors until every rank's list is empty and releases the shards
+// that all ranks have freed.  sd_vec_alloc does one round of the same exchange; call this to return memory earlier.
+int sd_ctx_collect(sd_ctx *c) {
+    SD_ARG(c, "ctx is NULL");
+    SD_LOCK(c); SD_TRY(sd_use(c));
+    if (c->world <= 1) return SD_OK;
+    for (;;) {
+        SD_TRY(sd_exchange(c, nullptr));
+        bool more = false;
+        for (int g = 0; g < c->world; ++g) {
+            uint64_t pending;
+            memcpy(&pending, c->h_ipc.data() + (size_t)g * 128 + 120, 8);
+            if (pending) more = true;
+        }
+        if (!more) break;
+    }
     return SD_OK;
 }
 int sd_vec_dtype(const sd_vec *v, int *dtype) {
@@ -877,6 +990,7 @@ int sd_vec_upload(sd_vec *v, const void *host) {
     SD_ARG(v && host, "NULL argument");
     sd_ctx *c = v->model->ctx;
     SD_LOCK(c); SD_TRY(sd_use(c));
+    SD_TRY(sd_before_write(c, v));
     if (v->layout) {
         double *st = nullptr;
         SD_TRY(sd_scratch(c, 0, sd_vec_logical_bytes(v) + 16, &st));
@@ -911,6 +1025,7 @@ int sd_vec_upload_async(sd_vec *v, const void *host) {
     SD_ARG(v && host, "NULL argument");
     sd_ctx *c = v->model->ctx;
     SD_LOCK(c); SD_TRY(sd_use(c));
+    SD_TRY(sd_before_write(c, v));
     if (v->layout) {
         double *st = nullptr;
         SD_TRY(sd_scratch(c, 0, sd_vec_logical_bytes(v) + 16, &st));
@@ -947,6 +1062,7 @@ int sd_vec_zero(sd_vec *v) {
     SD_ARG(v, "NULL argument");
     sd_ctx *c = v->model->ctx;
     SD_LOCK(c); SD_TRY(sd_use(c));
+    SD_TRY(sd_before_write(c, v));
     SD_CUDA(cudaMemsetAsync(v->d, 0, sd_vec_bytes(v), c->stream));
     return SD_OK;
 }
@@ -954,6 +1070,7 @@ int sd_vec_set_onehot(sd_vec *v, uint64_t idx0) {
     SD_ARG(v, "NULL argument");
     SD_ARG(idx0 < v->model->N, "index outside the basis");
     sd_ctx *c = v->model->ctx;
+    SD_LOCK(c);
     SD_TRY(sd_vec_zero(v));
     const uint64_t ls = v->model->shards.start[c->rank];
     if (idx0 >= ls && idx0 < ls + v->logical_n) {
@@ -972,6 +1089,7 @@ int sd_vec_fill_seeded(sd_vec *v, uint64_t seed, double scale) {
     SD_ARG(v, "NULL argument");
     sd_ctx *c = v->model->ctx;
     SD_LOCK(c); SD_TRY(sd_use(c));
+    SD_TRY(sd_before_write(c, v));
     if (v->local_n == 0) return SD_OK;
     if (v->layout) return sd_blk_permute(v, nullptr, v->nc, 0, 1, seed, scale);
     sd_fill_seeded_kernel<<<sd_blas_grid(c, v->local_n), SD_BLAS_THREADS, 0, c->stream>>>(
@@ -983,8 +1101,10 @@ int sd_vec_copy(sd_vec *dst, const sd_vec *src) {
     SD_ARG(dst->model == src->model && dst->dtype == src->dtype, "vectors differ in model or dtype");
     sd_ctx *c = dst->model->ctx;
     SD_LOCK(c); SD_TRY(sd_use(c));
-    if (dst->d != src->d)
+    if (dst->d != src->d) {
+        SD_TRY(sd_before_write(c, dst));
         SD_CUDA(cudaMemcpyAsync(dst->d, src->d, sd_vec_bytes(dst), cudaMemcpyDeviceToDevice, c->stream));
+    }
     return SD_OK;
 }
 int sd_vec_convert(sd_vec *dst, const sd_vec *src) {
@@ -993,6 +1113,7 @@ int sd_vec_convert(sd_vec *dst, const sd_vec *src) {
     if (dst->dtype == src->dtype) return sd_vec_copy(dst, src);
     sd_ctx *c = dst->model->ctx;
     SD_LOCK(c); SD_TRY(sd_use(c));
+    SD_TRY(sd_before_write(c, dst));
     if (dst->local_n == 0) return SD_OK;
     if (dst->layout || src->layout) {                // f64 and c128 block layouts order a class differently
         SD_ARG(dst->layout && src->layout, "vectors differ in layout");
@@ -1016,6 +1137,7 @@ static SdScalar sd_dev_scalar(const double *p, int mode) {
 
 static int sd_scale_impl(sd_vec *x, SdScalar s) {
     sd_ctx *c = x->model->ctx;
+    SD_TRY(sd_before_write(c, x));
     if (x->local_n == 0) return SD_OK;
     const unsigned g = sd_blas_grid(c, x->local_n);
     if (x->nc == 2) sd_scale_kernel<2><<<g, SD_BLAS_THREADS, 0, c->stream>>>(x->d, x->local_n, s);
@@ -1031,6 +1153,7 @@ int sd_vec_scale(sd_vec *x, sd_complex s) {
 // y = x / s (s real; device or host scalar)
 static int sd_divide_impl(sd_vec *y, const sd_vec *x, SdScalar s) {
     sd_ctx *c = y->model->ctx;
+    SD_TRY(sd_before_write(c, y));
     if (y->local_n == 0) return SD_OK;
     const unsigned g = sd_blas_grid(c, y->local_n * y->nc);
     if (y->nc == 2) sd_divide_kernel<2><<<g, SD_BLAS_THREADS, 0, c->stream>>>(y->d, x->d, y->local_n, s);
@@ -1040,6 +1163,7 @@ static int sd_divide_impl(sd_vec *y, const sd_vec *x, SdScalar s) {
 // y += a x [+ b z]; if slot_out >= 0: ||y||^2 -> d_scal[slot_out+3]
 static int sd_axpy_impl(sd_vec *y, SdScalar a, const sd_vec *x, SdScalar b, const sd_vec *z, int slot_out) {
     sd_ctx *c = y->model->ctx;
+    SD_TRY(sd_before_write(c, y));
     const unsigned g = sd_blas_grid(c, y->local_n);
     double *partials = nullptr;
     if (slot_out >= 0) { SD_TRY(sd_partials_reserve(c, (size_t)SD_NSLOT * g)); partials = c->d_partials; }
@@ -1108,9 +1232,11 @@ int sd_vec_norm(const sd_vec *x, double *result) {
 static int sd_empty_shard_reduce(sd_ctx *c, int slotmask, int slot_out) {
     if (!slotmask) return SD_OK;
     SD_CUDA(cudaMemsetAsync(c->d_scal + slot_out, 0, SD_NSLOT * sizeof(double), c->stream));
-    if (c->world > 1)
+    if (c->world > 1) {
         SD_NCCL(g_nccl.AllReduce(c->d_scal + slot_out, c->d_scal + slot_out, SD_NSLOT, ncclFloat64_, ncclSum_,
                                  c->comm, c->stream));
+        sd_collective_done(c);
+    }
     return SD_OK;
 }
 // ----------------------------------------------------------------- halo mirror (SD_HALO=1; sd_halo_host.h)
@@ -1264,14 +1390,14 @@ static int sd_apply_blk_halo(sd_model *m, sd_vec *out, const sd_vec *psi, SdEpi 
 
 // Launches one apply kernel with the given epilogue; reductions (if any) land
 // in d_scal[slot_out .. slot_out+3].
-static int sd_apply_impl(sd_model *m, sd_vec *out, const sd_vec *psi, SdEpi epi, int slot_out) {
+static int sd_apply_impl(sd_model *m, sd_vec *out, const sd_vec *psi, SdEpi epi, int slot_out, const sd_vec *acc = nullptr) {
     sd_ctx *c = m->ctx;
     SD_ARG(out && psi, "NULL argument");
     SD_ARG(out->model == m && psi->model == m, "vector does not belong to this model");
     SD_ARG(out->dtype == psi->dtype, "out and psi differ in element type");
     SD_ARG(out->d != psi->d, "out must not alias psi");
     SD_LOCK(c); SD_TRY(sd_use(c));
-    SD_TRY(sd_rank_barrier(c));
+    SD_TRY(sd_before_apply(c, out, psi, acc));
     const int nc = psi->nc;
     const int slotmask = sd_epi_slotmask(epi.red);
     SD_ARG(out->layout == psi->layout && psi->layout == (m->path == SD_PATH_BLOCK ? 1 : 0),
@@ -1402,7 +1528,7 @@ static int sd_cheb_step_impl(sd_model *m, sd_vec *vnext, const sd_vec *v, const 
         SD_ARG(acc->d != vnext->d && acc->d != v->d, "acc must not alias vnext or v");
         e.acc = acc->d; e.ck_re = ck.re; e.ck_im = ck.im;
     }
-    return sd_apply_impl(m, vnext, v, e, slot_out);
+    return sd_apply_impl(m, vnext, v, e, slot_out, acc);
 }
 int sd_cheb_step(sd_model *m, sd_vec *vnext, const sd_vec *v, const sd_vec *vprev, double a, double b,
                  const sd_vec *phi, double *mu, double *norm2, sd_vec *acc, sd_complex ck) {
@@ -1423,6 +1549,7 @@ int sd_szq(sd_model *m, sd_vec *phi, const sd_vec *psi0, double q, double *norm2
     SD_ARG(phi->d != psi0->d, "phi must not alias psi0");
     sd_ctx *c = m->ctx;
     SD_LOCK(c); SD_TRY(sd_use(c));
+    SD_TRY(sd_before_write(c, phi));
     SdSzqParams Z;
     Z.L = m->L; Z.k = m->k; Z.normfact = 1.0 / sqrt((double)m->L); Z.binom = c->d_binom;
     for (int r = 0; r < m->L; ++r) { Z.ph_re[r] = cos(q * (double)r); Z.ph_im[r] = sin(q * (double)r); }
@@ -1443,6 +1570,8 @@ int sd_szq(sd_model *m, sd_vec *phi, const sd_vec *psi0, double q, double *norm2
         if (psi0->nc == 2) sd_szq_kernel<2><<<g, SD_BLAS_THREADS, 0, c->stream>>>(Z, ls, phi->logical_n, src, dst, partials, g);
         else sd_szq_kernel<1><<<g, SD_BLAS_THREADS, 0, c->stream>>>(Z, ls, phi->logical_n, src, dst, partials, g);
         SD_TRY(sd_launch_check(c, "sd_szq_kernel"));
+    } else if (partials) {                           // empty shard: contribute zeros to the cross-rank sum
+        SD_CUDA(cudaMemsetAsync(partials, 0, (size_t)SD_NSLOT * g * sizeof(double), c->stream));
     }
     if (phi->layout) {
         SD_TRY(sd_blk_permute(phi, dst, 2, 0, 0, 0, 0.0));
@@ -1481,7 +1610,7 @@ int sd_vec_observables(const sd_vec *psi, double *mags, double *zz) {
     sd_obs_reduce_kernel<<<1, 128, 0, c->stream>>>(c->d_partials, nwarps, c->d_scal + SD_OBS_SLOT);
     SD_TRY(sd_launch_check(c, "sd_obs_reduce_kernel"));
     if (c->world > 1)
-        SD_NCCL(g_nccl.AllReduce(c->d_scal + SD_OBS_SLOT, c->d_scal + SD_OBS_SLOT, 128, ncclFloat64_, ncclSum_, c->comm, c->stream));
+        { SD_NCCL(g_nccl.AllReduce(c->d_scal + SD_OBS_SLOT, c->d_scal + SD_OBS_SLOT, 128, ncclFloat64_, ncclSum_, c->comm, c->stream)); sd_collective_done(c); }
     double r[128];
     SD_TRY(sd_fetch(c, SD_OBS_SLOT, 128, r));
     if (psi->layout) sd_scratch_release(c);
@@ -1553,6 +1682,7 @@ int sd_lincomb(sd_vecset *s, const sd_complex *y, int mcount, sd_vec *out, doubl
         }
         return SD_OK;
     }
+    SD_TRY(sd_before_write(c, out));
     // coefficients -> device (pinned staging, ordered on the stream)
     SD_CUDA(cudaStreamSynchronize(c->stream));
     for (int j = 0; j < mcount; ++j) { c->h_scal[1024 + 2 * j] = y[j].re; c->h_scal[1024 + 2 * j + 1] = y[j].im; }
@@ -1744,8 +1874,10 @@ int sd_lanczos_groundstate(sd_model *m, const sd_vec *v0, int lanc_m, double tol
                     SD_TRY(sd_launch_check(c, "sd_bdot_f64_kernel"));
                     sd_bdot_reduce_kernel<<<1, SD_BDOT_MAX * 32, 0, c->stream>>>(c->d_partials, g, nb, c->d_scal + 2048 + (k0 % 1024));
                     SD_TRY(sd_launch_check(c, "sd_bdot_reduce_kernel"));
-                    if (c->world > 1)
+                    if (c->world > 1) {
                         SD_NCCL(g_nccl.AllReduce(c->d_scal + 2048 + (k0 % 1024), c->d_scal + 2048 + (k0 % 1024), nb, ncclFloat64_, ncclSum_, c->comm, c->stream));
+                        sd_collective_done(c);
+                    }
                     if ((k0 + SD_BDOT_MAX) % 1024 == 0 || k0 + SD_BDOT_MAX >= cnt) {       // drain the staged block of results
                         const int base = (k0 / 1024) * 1024, have = std::min(cnt - base, 1024);
                         SD_TRY(sd_fetch(c, 2048, have, d.data() + base));

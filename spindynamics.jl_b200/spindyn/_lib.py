@@ -50,6 +50,7 @@ SIGNATURES = {
     "sd_ctx_create_rank": [_i, _i, _i, _vp, _P(_vp)],
     "sd_ctx_free": [_vp],
     "sd_ctx_sync": [_vp],
+    "sd_ctx_collect": [_vp],
     "sd_ctx_rank": [_vp, _P(_i), _P(_i)],
     "sd_timer_start": [_vp],
     "sd_timer_stop": [_vp, _P(ctypes.c_float)],

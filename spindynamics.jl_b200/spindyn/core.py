@@ -82,6 +82,10 @@ class Context:
     def sync(self) -> None:
         check(lib().sd_ctx_sync(self._h))
 
+    def collect(self) -> None:
+        """Collective (world > 1): release the shards of vectors that every rank has freed (sd_ctx_collect)."""
+        check(lib().sd_ctx_collect(self._h))
+
     def timer_start(self) -> None:
         check(lib().sd_timer_start(self._h))
 
