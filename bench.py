@@ -114,17 +114,43 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
 
 
-def cpu_port_applies_per_s(L_sample, reps, L_target=32):
-    """Times the oracle's reference-faithful apply_H! (explicit states[], hash map in
-    place of the Dict, per-term loops, OpenMP over idx) on L_sample and converts to
-    L_target-equivalent applies/s by the state*bond count ratio."""
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def mem_available_gb():
+    try:
+        with open("/proc/meminfo") as f:
+            for ln in f:
+                if ln.startswith("MemAvailable:"):
+                    return int(ln.split()[1]) / 1e6
+    except Exception:
+        pass
+    return 0.0
+
+
+def cpu_reference(L_sample, reps, L_target=32, ranked=True, warm=True):
+    """Times the oracle's reference-faithful apply_H! (explicit states[], open-addressing table in place of the Dict
+    with Julia's load factor, per-term loops, OpenMP over idx) on XXZ L_sample at ALL host threads: the team is set
+    explicitly because torchrun exports OMP_NUM_THREADS=1 to its children.  1 warm-up apply, then `reps` timed ones.
+    value = applies/s of the L_target problem: measured directly when L_sample == L_target (same_config), otherwise
+    converted by the states*bonds ratio and labelled as such."""
     from oracle import oracle as orc
+    nthr = host_threads()
+    orc.lib().orc_set_num_threads(nthr)
+    t_build = time.perf_counter()
     m = orc.XXZChain(L_sample, Jxy=1.0, Jz=1.0, hz=0.0, nup=L_sample // 2)
     n = len(m)
     psi = orc.fill_seeded(n, SEED)
     out = np.empty_like(psi)
-    orc.apply_H_(out, psi, m)                                   # warm-up (page faults, caches)
-    times = []
+    t_build = time.perf_counter() - t_build
+    out[:] = 0.0                                                # page faults of out are not the algorithm's
+    if warm:
+        orc.apply_H_(out, psi, m)                               # warm-up (skipped at L >= 30: an apply takes ~1 min and the
+    times = []                                                  # working set is 100x every cache, so there is nothing to warm)
     for _ in range(reps):
         t0 = time.perf_counter()
         orc.apply_H_(out, psi, m)
@@ -133,21 +159,48 @@ def cpu_port_applies_per_s(L_sample, reps, L_target=32):
     work_sample = n * (L_sample - 1)
     work_target = comb(L_target, L_target // 2) * (L_target - 1)
     cores = int(orc.lib().orc_num_threads())
-    # second, stronger CPU figure: same loop, Dict probe replaced by combinatorial ranking
-    orc.apply_H_ranked_(out, psi, m)
-    tr = []
-    for _ in range(max(1, reps // 2)):
+    same = L_sample == L_target
+    res = {"value": (work_sample / t) / work_target, "unit": UNIT, "cores": cores, "kind": "port", "same_config": same,
+           "sample": f"oracle/oracle.c orc_apply_H_f64 (C/OpenMP restatement of Hamiltonian.jl:211-273; Julia is not "
+                     f"installed) on XXZ L={L_sample} nup={L_sample // 2} ({n} states), {1 if warm else 0} warm-up + {reps} timed applies, "
+                     f"{t * 1e3:.1f} ms each on {cores} threads (basis + table built in {t_build:.0f} s, untimed)"
+                     + ("" if same else f"; converted to L={L_target} by states*bonds"),
+           "ms_per_sample_apply": t * 1e3, "host_threads_available": nthr}
+    if ranked:
+        # second, stronger CPU figure: same loop, Dict probe replaced by combinatorial ranking
+        orc.apply_H_ranked_(out, psi, m)
         t0 = time.perf_counter()
         orc.apply_H_ranked_(out, psi, m)
-        tr.append(time.perf_counter() - t0)
-    t_ranked = float(np.mean(tr))
-    return {"value": (work_sample / t) / work_target, "unit": UNIT, "cores": cores, "kind": "port",
-            "ranked_value": (work_sample / t_ranked) / work_target,
-            "ranked_note": f"same loop with combinatorial ranking instead of the hash-map probe (not the reference's algorithm): {t_ranked * 1e3:.1f} ms per L={L_sample} apply",
-            "sample": f"oracle/oracle.c orc_apply_H_f64 (C/OpenMP restatement of Hamiltonian.jl:211-273; Julia is not "
-                      f"installed) on XXZ L={L_sample} nup={L_sample // 2} ({n} states), {reps} applies, "
-                      f"{t * 1e3:.1f} ms each on {cores} threads; scaled to L={L_target} by states*bonds",
-            "ms_per_sample_apply": t * 1e3}, times
+        t_ranked = time.perf_counter() - t0
+        res["ranked_value"] = (work_sample / t_ranked) / work_target
+        res["ranked_note"] = (f"same loop with combinatorial ranking instead of the hash-map probe (not the reference's "
+                              f"algorithm): {t_ranked * 1e3:.1f} ms per L={L_sample} apply")
+    return res, times
+
+
+def sampled_row_parity(model, out, scale, first, count, nrows, rank, cplx=False):
+    """max over sampled rows r of this rank's shard of |out[r] - (H psi)[r]| / max(|(H psi)[r]|, scale), with (H psi)[r]
+    from the oracle's row formula (oracle.c orc_row_seeded_f64 restates Hamiltonian.jl:223-269 for one state and
+    regenerates psi from the counter).  Checker only: nothing here is timed."""
+    from oracle import oracle as orc
+    L, nup = model.L, model.nup
+    if count == 0:
+        return {"rows": 0, "max_rel_err": 0.0, "what": "sampled rows of H.psi vs oracle row formula"}
+    rng = np.random.default_rng(1234 + rank)
+    rows = np.unique(np.concatenate([rng.integers(first, first + count, max(nrows - 3, 1)),
+                                     [first, first + count - 1, first + count // 2]])).astype(np.uint64)
+    got, present = out.get(rows)
+    assert present.all()
+    hop = [(i, i + 1, 0.5) for i in range(1, L)]
+    zz = [(i, i + 1, 1.0) for i in range(1, L)]
+    worst = 0.0
+    for r, g in zip(rows, got):
+        state = int(model.unrank(int(r), 1)[0])
+        ref = orc.row_seeded_f64((L, nup, hop, zz, np.zeros(L)), state, SEED, scale)
+        if cplx:                                                 # H is real: the imaginary part is the row of the psi seeded with SEED + 1
+            ref = complex(ref, orc.row_seeded_f64((L, nup, hop, zz, np.zeros(L)), state, SEED + 1, scale))
+        worst = max(worst, abs(complex(g) - ref) / max(abs(ref), scale))
+    return {"rows": int(len(rows)), "max_rel_err": worst, "what": "sampled rows of H.psi vs oracle row formula"}
 
 
 def run_solve(args):
@@ -169,18 +222,35 @@ def run_solve(args):
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path.  Julia is
-    absent from this image, so this is the oracle port (kind "port")."""
+    """--impl reference: the reference's CPU implementation of the path on the bench's own configuration.  Julia is
+    absent from this image, so this is the oracle port (kind "port"), on all host threads.  The L = 32 problem itself is
+    run when the host has the memory (states 4.8 GB + table 17.2 GB + two vectors 9.6 GB); the number of timed applies
+    does not depend on --steps (a CPU apply takes about a minute): 2 timed applies."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    L_s = args.cpu_L
-    res, times = cpu_port_applies_per_s(L_s, max(1, args.steps))
+    L_t = args.L
+    need_gb = {32: 40.0, 30: 12.0}
+    avail = mem_available_gb()
+    L_s = L_t
+    if args.cpu_L_ref:
+        L_s = args.cpu_L_ref
+    else:
+        for cand in (L_t, 30, 28):
+            if cand <= L_t and avail >= need_gb.get(cand, 4.0):
+                L_s = cand
+                break
+    reps = 2 if L_s >= 30 else 5
+    res, times = cpu_reference(L_s, reps, L_target=L_t, ranked=False, warm=L_s < 30)
     line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / res["value"],
+            "steps": reps, "warmup": 1 if L_s < 30 else 0, "ms_per_step": 1e3 / res["value"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic (counter-based seeded psi)",
-            "config": {"workload": "XXZChain L=32 nup=16 open, f64 H.psi, CPU sample scaled (see cpu_baseline.sample)"},
+            "config": {"workload": f"XXZChain L={L_t} nup={L_t // 2} open Jxy=Jz=1 hz=0, f64 H.psi on the host CPU"
+                                   + ("" if res["same_config"] else f" (sample L={L_s}, converted; host MemAvailable {avail:.0f} GB)"),
+                       "requested_steps": args.steps, "requested_warmup": args.warmup,
+                       "note": "a CPU apply takes about a minute: 2 timed applies whatever --steps says"},
+            "same_config": res["same_config"],
             "cpu_baseline": res,
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -195,9 +265,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--L", type=int, default=32, help="chain length (default: the metric's L=32)")
     ap.add_argument("--dtype", default="f64", choices=["f64", "c128"])
-    ap.add_argument("--cpu-L", type=int, default=28, help="chain length of the CPU baseline sample")
+    ap.add_argument("--cpu-L", type=int, default=28, help="chain length of the bounded cpu_baseline sample of the GPU arm")
+    ap.add_argument("--cpu-L-ref", type=int, default=0, help="--impl reference: force the chain length (default: L itself if the host has the memory)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the sampled-row check of H.psi against the oracle")
+    ap.add_argument("--parity-rows", type=int, default=48, help="sampled rows per rank")
     ap.add_argument("--no-solve", action="store_true", help="skip the end-to-end Lanczos solve leg")
     ap.add_argument("--solve-m", type=int, default=30)
     ap.add_argument("--solve-only", action="store_true", help="(internal) run only the solve leg and print {\"solve\": ...}")
@@ -234,7 +307,8 @@ def main():
         model.set_path(args.path)
     N = model.dim
     first, count = model.local_range
-    psi = model.vector(dtype).fill_seeded(SEED, 1.0 / np.sqrt(N / 3.0))      # ||psi|| ~ 1
+    psi_scale = 1.0 / np.sqrt(N / 3.0)
+    psi = model.vector(dtype).fill_seeded(SEED, psi_scale)                   # ||psi|| ~ 1
     out = model.vector(dtype)
 
     def barrier():
@@ -264,9 +338,25 @@ def main():
     ms_step = ms_total / args.steps
     value = 1e3 / ms_step
 
+    # parity of what was just timed: sampled rows of out = H psi on every rank against the oracle's row formula (the
+    # oracle regenerates the counter-based psi, so this works at sizes no host can hold).  Outside the timed region.
+    parity = None
+    if not args.no_parity:
+        parity = sampled_row_parity(model, out, psi_scale, first, count, args.parity_rows, rank, args.dtype == "c128")
+        if dist is not None:
+            import torch
+            t = torch.tensor([parity["max_rel_err"]], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            r = torch.tensor([parity["rows"]], device="cuda", dtype=torch.int64)
+            dist.all_reduce(r, op=dist.ReduceOp.SUM)
+            parity = {**parity, "max_rel_err": float(t.item()), "rows": int(r.item()), "ranks": world}
+        parity["ok"] = bool(parity["max_rel_err"] <= 1e-13)
+
     # end to end through the host-buffer entry points (pinned host memory)
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and 2 * count * esz > (24 << 30):
+        e2e = {"skipped": f"2 x {count * esz / 1e9:.1f} GB of pinned host memory per rank"}
+    elif not args.no_e2e:
         hin = sd.PinnedBuffer(count, dtype)
         hout = sd.PinnedBuffer(count, dtype)
         hin.array[:] = 0.0
@@ -343,7 +433,7 @@ def main():
                     "note": "16 B/state f64 (32 c128): one read of psi + one write of out; index math is on the fly"}
         cpu = None
         if not args.no_cpu and world == 1:
-            cpu, _ = cpu_port_applies_per_s(args.cpu_L, 4)
+            cpu, _ = cpu_reference(args.cpu_L, 4, L_target=L)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": args.dtype, "data": "synthetic (counter-based seeded psi, splitmix64)",
@@ -354,7 +444,7 @@ def main():
                            "kernel_path": model.info["kernel_path"], "tile_sites": model.info["tile_sites"],
                            **({"env_knobs": knobs} if knobs else {})},
                 "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-                "cpu_baseline": cpu, "checksum": checksum, "solve": solve}
+                "parity": parity, "cpu_baseline": cpu, "checksum": checksum, "solve": solve}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

@@ -138,6 +138,10 @@ int sd_vec_upload_async(sd_vec *vec, const void *pinned_host);
 int sd_vec_download_async(sd_vec *vec, void *pinned_host);
 int sd_vec_zero(sd_vec *vec);
 int sd_vec_set_onehot(sd_vec *vec, uint64_t idx0);      /* InitialStates.jl one-hot   */
+/* out[i] = vec[idx0[i]] (0-based basis ranks) for the ranks the local shard holds (present[i] = 1), untouched
+ * otherwise (present[i] = 0); host output, any layout.  The Julia side's getindex on a device vector, and how
+ * bench.py samples rows of H.psi at sizes nobody can download (count <= 65536). */
+int sd_vec_get(sd_vec *vec, const uint64_t *idx0, uint64_t count, void *out, unsigned char *present);
 /* psi[r] = 2*u(splitmix64(seed ^ r)) - 1 (re: seed, im: seed+1), then * scale.
  * Counter-based bench/test input; oracle.c:seeded_value is the same formula. */
 int sd_vec_fill_seeded(sd_vec *vec, uint64_t seed, double scale);

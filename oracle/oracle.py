@@ -78,6 +78,8 @@ def lib():
         L.orc_row_seeded_f64.argtypes = [ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, vp,
                                          ctypes.c_int, vp, u64, u64, dbl]
         L.orc_num_threads.restype = ctypes.c_int
+        L.orc_set_num_threads.argtypes = [ctypes.c_int]
+        L.orc_set_num_threads.restype = None
         L.orc_sector_dim.restype = u64
         L.orc_sector_dim.argtypes = [ctypes.c_int, ctypes.c_int]
         _LIB = L

@@ -1085,6 +1085,49 @@ int sd_vec_set_onehot(sd_vec *v, uint64_t idx0) {
     }
     return SD_OK;
 }
+// Elements of a (possibly sharded, possibly block-layout) vector by basis rank: out[i] = v[idx0[i]] for the ranks this
+// shard holds (present[i] = 1), untouched otherwise (present[i] = 0).  Host output; meant for a few sampled rows.
+int sd_vec_get(sd_vec *v, const uint64_t *idx0, uint64_t count, void *out, unsigned char *present) {
+    SD_ARG(v && idx0 && out && present, "NULL argument");
+    SD_ARG(count <= 65536, "at most 65536 elements per call");
+    sd_model *m = v->model;
+    sd_ctx *c = m->ctx;
+    SD_LOCK(c); SD_TRY(sd_use(c));
+    const uint64_t ls = m->shards.start[c->rank];
+    std::vector<uint64_t> off;
+    std::vector<uint64_t> where;
+    for (uint64_t i = 0; i < count; ++i) {
+        SD_ARG(idx0[i] < m->N, "index outside the basis");
+        present[i] = (idx0[i] >= ls && idx0[i] < ls + v->logical_n) ? 1 : 0;
+        if (!present[i]) continue;
+        uint64_t o = idx0[i] - ls;
+        if (v->layout) {
+            const uint64_t st = sd_unrank_state(idx0[i], m->L, m->k, c->binom.data(), SD_BINOM_DIM);
+            o = sd_blk_pos_of_state(m->blk.host, st, v->nc) - m->blk.pstart[c->rank];
+        }
+        off.push_back(o);
+        where.push_back(i);
+    }
+    if (off.empty()) return SD_OK;
+    uint64_t *d_off = nullptr;
+    double *d_out = nullptr;
+    SD_CUDA(cudaMalloc(&d_off, off.size() * sizeof(uint64_t)));
+    cudaError_t e = cudaMalloc(&d_out, off.size() * v->nc * sizeof(double));
+    if (e != cudaSuccess) { cudaFree(d_off); return sd_fail(SD_ERR_NOMEM, "cudaMalloc: %s", cudaGetErrorString(e)); }
+    std::vector<double> h(off.size() * v->nc);
+    e = cudaMemcpyAsync(d_off, off.data(), off.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        sd_gather_kernel<<<(unsigned)((off.size() + 127) / 128), 128, 0, c->stream>>>(v->d, d_off, (unsigned)off.size(), v->nc, d_out);
+        c->launches++;
+        e = cudaMemcpyAsync(h.data(), d_out, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_off); cudaFree(d_out);
+    if (e != cudaSuccess) return sd_fail(SD_ERR_CUDA, "sd_vec_get: %s", cudaGetErrorString(e));
+    for (size_t j = 0; j < where.size(); ++j)
+        for (int cc = 0; cc < v->nc; ++cc) ((double *)out)[where[j] * v->nc + cc] = h[j * v->nc + cc];
+    return SD_OK;
+}
 int sd_vec_fill_seeded(sd_vec *v, uint64_t seed, double scale) {
     SD_ARG(v, "NULL argument");
     sd_ctx *c = v->model->ctx;

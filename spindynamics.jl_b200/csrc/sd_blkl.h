@@ -79,20 +79,59 @@ SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdBlkHdr &H, const doub
         _Pragma("unroll") for (int s = 0; s < EC; ++s)                                        \
             t_[s] = (HALF && s == EC - 1) ? sd_blk_ldg_half(q_ + o[s]) : sd_blk_ldg(q_ + o[s]); \
     } while (0)
+#define SD_LEAN_LOAD_R(t_, p_)        /* tile on another GPU (prefetched into L1 above) */      \
+    do {                                                                                      \
+        const double *q_ = (p_);                                                              \
+        _Pragma("unroll") for (int s = 0; s < EC; ++s)                                        \
+            t_[s] = (HALF && s == EC - 1) ? sd_blk_ldg_ca_half(q_ + o[s]) : sd_blk_ldg_ca(q_ + o[s]); \
+    } while (0)
+#define SD_LEAN_LOADN(t_, p_, n_) do { if ((n_) < nloc) SD_LEAN_LOAD(t_, p_); else SD_LEAN_LOAD_R(t_, p_); } while (0)
 #define SD_LEAN_FMA(t_, J_)                                                                   \
     do {                                                                                      \
         const double j_ = (J_);                                                               \
         _Pragma("unroll") for (int s = 0; s < EC; ++s) { acc[s].x += j_ * t_[s].x; acc[s].y += j_ * t_[s].y; } \
     } while (0)
-    // Order of the phases: the loads of a stream entry are issued BEFORE a shared-memory phase and consumed after it, so
-    // that tail, mid and crossing work run under the L2 / DRAM latency of the first three stream rounds (round 2 profile
-    // of the straight order: 53 % of the stall samples were long-scoreboard waits in the stream loop).
-    //   load e0 | own block + tail hops | mid hops | use e0, load e1, load X (prefix|mid crossing partner) |
-    //   mid|tail crossing | use X, load e2 | two-deep loop over the remaining entries | epilogue
+    // ---- prefix|mid crossing bond: partner tile with js +- 1, same class, uniform block shift; only the lanes whose
+    // first mid bit differs from the last prefix bit
     const bool c0 = u < cls.n1;                                      // first mid bit (blocks with it set come first)
-    const int nnb = H.nnb;
-    SdBlkEnt ea = H.nb[0], eb;                                       // {tile base, J}: one LDS.128 per entry
-    if (nnb > 0) SD_LEAN_LOAD(t0, ea.p);
+    const int nnb = H.nnb, nloc = H.nloc;
+    for (int n = nloc; n < nnb; ++n) {                                // sharded runs only: NVLink latency starts now
+        const double *q_ = H.nb[n].p;
+#pragma unroll
+        for (int s = 0; s < EC; ++s) sd_blk_prefetch_l1(q_ + o[s]);
+    }
+    bool xl = false;
+    if (H.xptr != nullptr) {
+        xl = c0 != (bool)H.bP;
+        if (xl) {
+            const SdBlkCls cx = SD_SH.js[H.jsx].cls[JT];
+            const uint32_t xu = H.bP ? u - cls.n1 : cx.n1 + u;
+            const uint32_t xs = 2u * cx.pitch;
+            const double *xp = H.xptr + (cx.cb * NC + 2u * xu);
+#pragma unroll
+            for (int s = 0; s < EC; ++s)
+                t1[s] = (HALF && s == EC - 1) ? sd_blk_ldg_half(xp + (uint32_t)(S0 + s) * xs - xu) : sd_blk_ldg(xp + (uint32_t)(S0 + s) * xs);
+        }
+    }
+    // ---- prefix-internal bonds: whole neighbour tiles in the same element order
+    SdBlkEnt e0 = H.nb[0], e1;                                       // {tile base, J}: one LDS.128 per entry
+    if (nnb > 0) SD_LEAN_LOADN(t0, e0.p, 0);
+    if (xl) SD_LEAN_FMA(t1, H.Jx);
+    int n = 0;
+#pragma unroll 1
+    while (n + 1 < nnb) {
+        e1 = H.nb[n + 1];
+        SD_LEAN_LOADN(t1, e1.p, n + 1);
+        SD_LEAN_FMA(t0, e0.J);
+        if (n + 2 < nnb) { e0 = H.nb[n + 2]; SD_LEAN_LOADN(t0, e0.p, n + 2); }
+        SD_LEAN_FMA(t1, e1.J);
+        n += 2;
+    }
+    if (n < nnb) SD_LEAN_FMA(t0, e0.J);
+#undef SD_LEAN_LOAD
+#undef SD_LEAN_LOAD_R
+#undef SD_LEAN_LOADN
+#undef SD_LEAN_FMA
     // ---- own block: diagonal + tail-internal hops (registers, compile-time permutation)
     const uint4 it = sd_blk_ld_item(SD_SH.items + cls.item_off + u);     // x,y,z = nb[12]; w = c | u2x << 16
     const unsigned cmid = it.w & ((1u << M) - 1u);
@@ -119,23 +158,6 @@ SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdBlkHdr &H, const doub
                     }
                 }
             }
-        }
-    }
-    if (nnb > 0) SD_LEAN_FMA(t0, ea.J);
-    if (nnb > 1) { ea = H.nb[1]; SD_LEAN_LOAD(t0, ea.p); }
-    // ---- prefix|mid crossing bond: partner tile with js +- 1, same class, uniform block shift; only the lanes whose
-    // first mid bit differs from the last prefix bit
-    bool xl = false;
-    if (H.xptr != nullptr) {
-        xl = c0 != (bool)H.bP;
-        if (xl) {
-            const SdBlkCls cx = SD_SH.js[H.jsx].cls[JT];
-            const uint32_t xu = H.bP ? u - cls.n1 : cx.n1 + u;
-            const uint32_t xs = 2u * cx.pitch;
-            const double *xp = H.xptr + (cx.cb * NC + 2u * xu);
-#pragma unroll
-            for (int s = 0; s < EC; ++s)
-                t1[s] = (HALF && s == EC - 1) ? sd_blk_ldg_half(xp + (uint32_t)(S0 + s) * xs - xu) : sd_blk_ldg(xp + (uint32_t)(S0 + s) * xs);
         }
     }
     // ---- mid|tail crossing bond, per tail configuration.  Tail configurations with bit 0 set come first in a
@@ -177,21 +199,6 @@ SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdBlkHdr &H, const doub
         }
 #undef SD_LEAN_CROSS
     }
-    // ---- rest of the stream entries (prefix-internal bonds: whole neighbour tiles in the same element order)
-    if (xl) SD_LEAN_FMA(t1, H.Jx);
-    if (nnb > 2) { eb = H.nb[2]; SD_LEAN_LOAD(t1, eb.p); }
-    // invariant: t0 = entry n, t1 = entry n + 1 (those that exist) are in flight
-#pragma unroll 1
-    for (int n = 1; n < nnb; n += 2) {
-        SD_LEAN_FMA(t0, ea.J);
-        if (n + 2 < nnb) { ea = H.nb[n + 2]; SD_LEAN_LOAD(t0, ea.p); }
-        if (n + 1 < nnb) {
-            SD_LEAN_FMA(t1, eb.J);
-            if (n + 3 < nnb) { eb = H.nb[n + 3]; SD_LEAN_LOAD(t1, eb.p); }
-        }
-    }
-#undef SD_LEAN_LOAD
-#undef SD_LEAN_FMA
     // ---- epilogue + store
     const uint64_t ld0 = (H.base - SD_SH.pstart_local) * NC;              // doubles from the start of the local shard
     double *ob = SD_SH.out_local + ld0;

@@ -42,17 +42,7 @@ static inline void sd_halo_tile_remotes(const SdBlkHost &bh, const SdBlkParams &
     for (int g = 0; g < SD_MAX_WORLD; ++g) fake.base[g] = (const double *)(uintptr_t)((uint64_t)(g + 1) << 56);
     SdBlkHdr H;
     std::memset(&H, 0, sizeof(H));
-    SdBlkHdrLane lanes[32];
-    uint64_t base = 0;
-    double dpre = 0.0;
-    unsigned actmask = 0;
-    for (int q = 0; q < 32; ++q) {
-        lanes[q] = sd_blk_hdr_lane(P, bh.W.data(), Pb, q);
-        base += lanes[q].term;
-        dpre += lanes[q].d;
-        if (lanes[q].act) actmask |= 1u << q;
-    }
-    for (int q = 0; q < 32; ++q) sd_blk_hdr_fill<1>(P, lanes[q], Pb, key, base, dpre, actmask, qfar, q, H, fake);
+    sd_blk_hdr_host<1>(P, bh.W.data(), key, qfar, fake, H);
     for (int n = 0; n < H.ntot; ++n) {
         const uint64_t v = (uint64_t)(uintptr_t)H.nb[n].p;
         const int g = (int)(v >> 56) - 1;

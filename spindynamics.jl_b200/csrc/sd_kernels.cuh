@@ -285,6 +285,11 @@ __global__ void sd_fill_seeded_kernel(double *v, int nc, uint64_t first, uint64_
 }
 
 __global__ void sd_set_one_kernel(double *v, uint64_t off) { v[off] = 1.0; }
+// out[i*nc + c] = v[off[i]*nc + c]  (sd_vec_get: a handful of elements by stored offset)
+__global__ void sd_gather_kernel(const double *v, const uint64_t *off, unsigned n, int nc, double *out) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) for (int c = 0; c < nc; ++c) out[(size_t)i * nc + c] = v[off[i] * nc + c];
+}
 
 // y = ComplexF64.(x) (nc_in=1 -> nc_out=2) or real part (2 -> 1)
 __global__ void sd_convert_kernel(double *y, const double *x, uint64_t n, int nc_in) {

@@ -74,6 +74,7 @@ SIGNATURES = {
     "sd_vec_download_async": [_vp, _vp],
     "sd_vec_zero": [_vp],
     "sd_vec_set_onehot": [_vp, _u64],
+    "sd_vec_get": [_vp, _vp, _u64, _vp, _vp],
     "sd_vec_fill_seeded": [_vp, _u64, _d],
     "sd_vec_copy": [_vp, _vp],
     "sd_vec_convert": [_vp, _vp],

@@ -283,6 +283,14 @@ class DeviceVector:
         check(lib().sd_vec_set_onehot(self._h, int(idx0)))
         return self
 
+    def get(self, idx0):
+        """Elements by 0-based basis rank: (values, present) -- present[i] is False for ranks another shard holds."""
+        idx = np.ascontiguousarray(idx0, dtype=np.uint64)
+        out = np.zeros(len(idx), dtype=self.dtype)
+        present = np.zeros(len(idx), dtype=np.uint8)
+        check(lib().sd_vec_get(self._h, _ptr(idx), len(idx), _ptr(out), _ptr(present)))
+        return out, present.astype(bool)
+
     def fill_seeded(self, seed: int, scale: float = 1.0):
         check(lib().sd_vec_fill_seeded(self._h, int(seed), float(scale)))
         return self

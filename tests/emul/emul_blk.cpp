@@ -49,17 +49,7 @@ void run_tiles(const SdBlkHost &bh, const SdBlkParams &P, const SdVecView &psi, 
         SdBlkHdr H;
         std::memset(&H, 0, sizeof(H));
         for (SdBlkEnt &e : H.nb) { e.p = nullptr; e.J = NAN; }       // entries the header does not write must never be used
-        SdBlkHdrLane lanes[32];
-        uint64_t base = 0;
-        double dpre = 0.0;
-        unsigned actmask = 0;
-        for (int q = 0; q < 32; ++q) {
-            lanes[q] = sd_blk_hdr_lane(P, bh.W.data(), Pb, q);
-            base += lanes[q].term;
-            dpre += lanes[q].d;
-            if (lanes[q].act) actmask |= 1u << q;
-        }
-        for (int q = 0; q < 32; ++q) sd_blk_hdr_fill<NC>(P, lanes[q], Pb, key, base, dpre, actmask, qfar, q, H, psi);
+        sd_blk_hdr_host<NC>(P, bh.W.data(), key, qfar, psi, H);
         // pipeline overrun entries: valid pointer, J = 0 (the kernel never dereferences them: ok_ is false)
         // ---- own tile -> "shared memory" (the TMA bulk copy); the rest of the buffer stays NaN
         const uint32_t size_pad = bh.js[H.js].size_pad;
