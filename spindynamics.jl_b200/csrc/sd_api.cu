@@ -106,6 +106,8 @@ static int sd_nccl_load() {
 
 // ----------------------------------------------------------------- handles
 #define SD_NSCAL 4096
+#define SD_HIST 4096                  // d_scal[SD_HIST + 8 j ..]: reductions of Lanczos step j (kept on the device, fetched in blocks)
+#define SD_HIST_MAX 4096             // steps
 // ----------------------------------------------------------------- CUDA driver API (dlopen, only for SD_HALO=1)
 struct SdDrv {
     void *h = nullptr;
@@ -381,9 +383,9 @@ static int sd_ctx_init(int device, int rank, int world, const void *id128, sd_ct
     sd_fill_binom(c->binom.data());
     SD_CUDA(cudaMalloc(&c->d_binom, c->binom.size() * sizeof(uint64_t)));
     SD_CUDA(cudaMemcpy(c->d_binom, c->binom.data(), c->binom.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
-    SD_CUDA(cudaMalloc(&c->d_scal, SD_NSCAL * sizeof(double)));
-    SD_CUDA(cudaMemset(c->d_scal, 0, SD_NSCAL * sizeof(double)));
-    SD_CUDA(cudaMallocHost(&c->h_scal, SD_NSCAL * sizeof(double)));
+    SD_CUDA(cudaMalloc(&c->d_scal, (SD_NSCAL + 8 * (SD_HIST_MAX + 2)) * sizeof(double)));
+    SD_CUDA(cudaMemset(c->d_scal, 0, (SD_NSCAL + 8 * (SD_HIST_MAX + 2)) * sizeof(double)));
+    SD_CUDA(cudaMallocHost(&c->h_scal, (SD_NSCAL + 8 * (SD_HIST_MAX + 2)) * sizeof(double)));
     SD_CUDA(cudaMalloc(&c->d_tilectr, 16 * sizeof(unsigned long long)));   // [0]: tile counter of the block kernels' dynamic scheduler
     if (world > 1) {
         SD_ARG(id128, "id128 is NULL");
@@ -1402,7 +1404,7 @@ static int sd_apply_blk_halo(sd_model *m, sd_vec *out, const sd_vec *psi, SdEpi 
         SD_TRY(sd_partials_reserve(c, (size_t)SD_NSLOT * nkeys));
         SD_CUDA(cudaMemsetAsync(c->d_partials, 0, (size_t)SD_NSLOT * nkeys * sizeof(double), c->stream));
     }
-    const bool plain = epi.mode == SD_EPI_PLAIN && epi.red == 0 && !epi.acc && epi.hscale == 1.0;
+    const bool plain = epi.mode == SD_EPI_PLAIN && epi.red == 0 && !epi.acc && epi.hscale == 1.0 && !epi.hscale_dev;
     SdVecView view = psi->view;
     for (int g = 0; g < c->world; ++g)
         if (g != c->rank && M.va[g]) view.base[g] = (const double *)M.va[g] - (int64_t)m->blk.pstart[g] * nc;
@@ -1458,7 +1460,7 @@ static int sd_apply_impl(sd_model *m, sd_vec *out, const sd_vec *psi, SdEpi epi,
         }
         epi.partials = c->d_partials;
         epi.nparts = (unsigned)nkeys;
-        const bool plain = epi.mode == SD_EPI_PLAIN && epi.red == 0 && !epi.acc && epi.hscale == 1.0;
+        const bool plain = epi.mode == SD_EPI_PLAIN && epi.red == 0 && !epi.acc && epi.hscale == 1.0 && !epi.hscale_dev;
         SD_TRY(sd_blk_launch_range(m, nc, P, psi->view, out->d, epi, plain));
         if (slotmask) SD_TRY(sd_finish_reduce(c, (unsigned)nkeys, slotmask, slot_out));
     } else if (m->path == SD_PATH_TILED) {
@@ -1495,7 +1497,7 @@ static int sd_apply_impl(sd_model *m, sd_vec *out, const sd_vec *psi, SdEpi epi,
         if (plain) SD_LAUNCH_TILE2(NC_, T_, true);                                                          \
         else SD_LAUNCH_TILE2(NC_, T_, false);                                                               \
     } while (0)
-        const bool plain = epi.mode == SD_EPI_PLAIN && epi.red == 0 && !epi.acc && epi.hscale == 1.0;
+        const bool plain = epi.mode == SD_EPI_PLAIN && epi.red == 0 && !epi.acc && epi.hscale == 1.0 && !epi.hscale_dev;
         if (nc == 1 && T == 5) SD_LAUNCH_TILE(1, 5);
         else if (nc == 2 && T == 4) SD_LAUNCH_TILE(2, 4);
         else if (nc == 1 && T == 4) SD_LAUNCH_TILE(1, 4);
@@ -1779,6 +1781,93 @@ static int sd_normalised_copy(sd_vec *dst, const sd_vec *src, double *norm_out) 
     return sd_divide_impl(dst, src, sd_host_scalar(nrm, 0));
 }
 
+// One fused 3R+1W pass after an apply (sd_lanczos_update_kernel); ||w||^2 -> d_scal[slot_out + 3] (+ NCCL sum).
+static int sd_lanczos_update(sd_vec *w, const sd_vec *u, const sd_vec *uo, sd_vec *out, const SdLanczosScal &S, int slot_out) {
+    sd_ctx *c = w->model->ctx;
+    SD_TRY(sd_before_write(c, w));
+    if (out) SD_TRY(sd_before_write(c, out));
+    const unsigned g = sd_blas_grid(c, w->local_n);
+    SD_TRY(sd_partials_reserve(c, (size_t)SD_NSLOT * g));
+    if (w->nc == 2)
+        sd_lanczos_update_kernel<2><<<g, SD_BLAS_THREADS, 0, c->stream>>>(w->d, u->d, uo ? uo->d : nullptr, out ? out->d : nullptr, w->local_n, S, c->d_partials, g);
+    else
+        sd_lanczos_update_kernel<1><<<g, SD_BLAS_THREADS, 0, c->stream>>>(w->d, u->d, uo ? uo->d : nullptr, out ? out->d : nullptr, w->local_n, S, c->d_partials, g);
+    SD_TRY(sd_launch_check(c, "sd_lanczos_update_kernel"));
+    return sd_finish_reduce(c, g, 8, slot_out);
+}
+
+// The three-term Lanczos recurrence of Lanczos.jl:27-84 (extremal), :196-246 (tridiag) and of the memory-lean ground
+// state, on three work vectors with DEFERRED NORMALISATION and no host synchronisation inside the recurrence.  The
+// vectors are kept unnormalised, u_1 = v0, u_{j+1} = w_j, v_j = u_j / beta_{j-1}, beta_0 = ||v0||; a step is two kernels:
+//     apply   w = (hsign / beta_{j-1}) H u_j  with the fused dot  d_j = <u_j, w>         (1 / beta from device memory)
+//     update  w -= (alpha_j / beta_{j-1}) u_j + (beta_{j-1} / beta_{j-2}) u_{j-1},  n_j = ||w||^2   (3R + 1W, fused norm)
+// with alpha_j = Re d_j / beta_{j-1}, beta_j = sqrt(n_j); the last step (j = mm) is the apply alone.  The reductions of
+// step j stay on the device in d_scal[SD_HIST + 4 j ..] and are fetched every 16 steps; beta_j < tol then truncates
+// (m_eff = j), which returns exactly what the step-by-step test of the reference returns.
+// Pass 2 (y != NULL, f64 ground state only): alpha / beta are INPUTS; the recurrence is regenerated from them -- every
+// coefficient is an IEEE sqrt / division of the same numbers, so the vectors are bit-identical to pass 1 -- and
+// out = sum_j y_j v_j is accumulated inside the update pass.
+static int sd_lanczos_engine(sd_model *m, const sd_vec *v0, int dtype, int mm, double tol, double hsign,
+                             double *alpha, double *beta, int *m_eff, double *norm0, const double *y, sd_vec *out) {
+    sd_ctx *c = m->ctx;
+    SD_ARG(mm >= 1 && mm <= SD_HIST_MAX, "lanc_m must be in 1 .. %d", SD_HIST_MAX);
+    SdVecGuard G;
+    sd_vec *u, *uo, *w;
+    SD_TRY(G.make(m, dtype, &u)); SD_TRY(G.make(m, dtype, &uo)); SD_TRY(G.make(m, dtype, &w));
+    double *hist = c->d_scal + SD_HIST;                                       // record j: [8 j + 0] = Re d_j (apply), [8 j + 7] = n_j (update: its own
+    //                                                                         4 slots, a cross-rank sum always covers all four); n_0 = ||v0||^2
+    SD_TRY(sd_vec_copy(u, v0));
+    SD_TRY(sd_dot_impl(v0, v0, 1, SD_HIST));                                  // n_0 -> hist[0]
+    SD_CUDA(cudaMemcpyAsync(hist + 7, hist + 0, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    double n0;
+    SD_TRY(sd_fetch(c, SD_HIST, 1, &n0));
+    if (norm0) *norm0 = sqrt(n0);
+    if (n0 == 0.0) return sd_fail(SD_ERR_ZERO_NORM, "starting vector has zero norm");
+    const double beta0 = sqrt(n0);
+    if (y) SD_TRY(sd_vec_zero(out));
+    int eff = mm, fetched = 0;
+    std::vector<double> hh((size_t)8 * (mm + 1), 0.0);
+    const int scratch_slot = SD_HIST + 8 * SD_HIST_MAX;                       // pass 2 does not need its reductions
+    for (int j = 1; j <= mm; ++j) {
+        SdEpi e = sd_epi_plain(hsign);
+        SdLanczosScal S;
+        memset(&S, 0, sizeof(S));
+        if (!y) {                                                             // pass 1: every scalar from device memory
+            e.red = SD_RED_DOT_SELF;
+            e.hscale_dev = hist + 8 * (j - 1) + 7;                            // hsign / sqrt(n_{j-1})
+            S.d_dev = hist + 8 * j + 0; S.n1_dev = hist + 8 * (j - 1) + 7; S.n2_dev = j >= 2 ? hist + 8 * (j - 2) + 7 : nullptr;
+        } else {                                                              // pass 2: the same numbers from alpha / beta
+            S.b1 = j >= 2 ? beta[j - 2] : beta0;
+            S.b2 = j >= 3 ? beta[j - 3] : beta0;
+            S.alpha = alpha[j - 1];
+            S.yj = y[j - 1];
+            e.hscale = hsign / S.b1;
+            if (j == mm) {                                                    // last Ritz term: out += y_m v_m, no further apply
+                SD_TRY(sd_axpy_impl(out, sd_host_scalar(S.yj / S.b1, 0), u, sd_host_scalar(0, 0), nullptr, -1));
+                break;
+            }
+        }
+        const int slot = y ? scratch_slot : SD_HIST + 8 * j;
+        SD_TRY(sd_apply_impl(m, w, u, e, slot));                              // w = H v_j, d_j = <u_j, w>
+        if (j < mm) SD_TRY(sd_lanczos_update(w, u, j >= 2 ? uo : nullptr, y ? out : nullptr, S, slot + 4));
+        if (!y && (j % 16 == 0 || j == mm)) {                                 // block fetch + breakdown test (Lanczos.jl:65-69,148,228-231)
+            SD_TRY(sd_fetch(c, SD_HIST + 8 * fetched, 8 * (j - fetched + 1), hh.data() + 8 * fetched));
+            bool stop = false;
+            for (int t = fetched + 1; t <= j; ++t) {
+                const double b1 = sqrt(hh[8 * (t - 1) + 7]);
+                alpha[t - 1] = hh[8 * t + 0] / b1;
+                if (t < mm) beta[t - 1] = sqrt(hh[8 * t + 7]);
+                if (t < mm && beta[t - 1] < tol) { eff = t; stop = true; break; }
+            }
+            fetched = j;
+            if (stop) break;
+        }
+        sd_vec *t = uo; uo = u; u = w; w = t;                                 // u_{j+1} = w_j
+    }
+    *m_eff = eff;
+    return SD_OK;
+}
+
 int sd_lanczos_extremal(sd_model *m, const sd_vec *v0, int lanc_m, double tol, int negate,
                         double *alpha, double *beta, int *m_eff) {
     SD_ARG(m && v0 && alpha && beta && m_eff, "NULL argument");
@@ -1787,34 +1876,7 @@ int sd_lanczos_extremal(sd_model *m, const sd_vec *v0, int lanc_m, double tol, i
     sd_ctx *c = m->ctx;
     SD_LOCK(c); SD_TRY(sd_use(c));
     const int mm = (int)std::min<uint64_t>((uint64_t)lanc_m, m->N);          // Lanczos.jl:36
-    SdVecGuard G;
-    sd_vec *vp, *vc, *w;
-    SD_TRY(G.make(m, SD_C128, &vp)); SD_TRY(G.make(m, SD_C128, &vc)); SD_TRY(G.make(m, SD_C128, &w));
-    double n0;
-    SD_TRY(sd_normalised_copy(vp, v0, &n0));                                // :39-40
-    if (n0 == 0.0) return sd_fail(SD_ERR_ZERO_NORM, "starting vector has zero norm");
-    int count = 0;
-    for (int j = 1; j <= mm; ++j) {
-        SdEpi e = sd_epi_plain(negate ? -1.0 : 1.0);
-        e.red = SD_RED_DOT_SELF;
-        SD_TRY(sd_apply_impl(m, w, vp, e, 0));                              // :49-50  alpha = Re dot(v, w)
-        // w -= alpha v [+ beta v_old]                                        :53-60
-        SdScalar sa = sd_dev_scalar(c->d_scal + 0, 4);
-        if (j == 1) SD_TRY(sd_axpy_impl(w, sa, vp, sd_host_scalar(0, 0), nullptr, 4));
-        else SD_TRY(sd_axpy_impl(w, sa, vp, sd_host_scalar(-beta[j - 2], 0), vc, 4));
-        double r[8];
-        SD_TRY(sd_fetch(c, 0, 8, r));
-        alpha[j - 1] = r[0];
-        count = j;
-        if (j < mm) {
-            beta[j - 1] = sqrt(r[7]);                                       // :63
-            if (beta[j - 1] < tol) break;                                   // :65-69
-            std::swap(vp, vc);                                              // :71 roles rotate
-            SD_TRY(sd_divide_impl(vp, w, sd_host_scalar(beta[j - 1], 0)));
-        }
-    }
-    *m_eff = count;
-    return SD_OK;
+    return sd_lanczos_engine(m, v0, SD_C128, mm, tol, negate ? -1.0 : 1.0, alpha, beta, m_eff, nullptr, nullptr, nullptr);
 }
 
 int sd_lanczos_tridiag(sd_model *m, const sd_vec *v, int lanc_m, double tol, double *alpha, double *beta,
@@ -1825,37 +1887,7 @@ int sd_lanczos_tridiag(sd_model *m, const sd_vec *v, int lanc_m, double tol, dou
     sd_ctx *c = m->ctx;
     SD_LOCK(c); SD_TRY(sd_use(c));
     const int mm = (int)std::min<uint64_t>((uint64_t)lanc_m, m->N);          // Lanczos.jl:200
-    SdVecGuard G;
-    sd_vec *vj, *vo, *w;
-    SD_TRY(G.make(m, SD_C128, &vj)); SD_TRY(G.make(m, SD_C128, &vo)); SD_TRY(G.make(m, SD_C128, &w));
-    SD_TRY(sd_normalised_copy(vj, v, normv));                               // :209-213
-    if (*normv == 0.0) return sd_fail(SD_ERR_ZERO_NORM, "starting vector has zero norm");
-    int eff = mm;
-    for (int j = 1; j < mm; ++j) {                                          // :216-235
-        SdEpi e = sd_epi_plain(1.0);
-        e.red = SD_RED_DOT_SELF;
-        SD_TRY(sd_apply_impl(m, w, vj, e, 0));
-        SdScalar sa = sd_dev_scalar(c->d_scal + 0, 4);
-        if (j == 1) SD_TRY(sd_axpy_impl(w, sa, vj, sd_host_scalar(0, 0), nullptr, 4));
-        else SD_TRY(sd_axpy_impl(w, sa, vj, sd_host_scalar(-beta[j - 2], 0), vo, 4));
-        double r[8];
-        SD_TRY(sd_fetch(c, 0, 8, r));
-        alpha[j - 1] = r[0];
-        beta[j - 1] = sqrt(r[7]);
-        if (beta[j - 1] < tol) { eff = j; break; }                          // :228-231
-        std::swap(vj, vo);
-        SD_TRY(sd_divide_impl(vj, w, sd_host_scalar(beta[j - 1], 0)));
-    }
-    if (eff == mm) {                                                        // :237-239
-        SdEpi e = sd_epi_plain(1.0);
-        e.red = SD_RED_DOT_SELF;
-        SD_TRY(sd_apply_impl(m, w, vj, e, 0));
-        double r[2];
-        SD_TRY(sd_fetch(c, 0, 2, r));
-        alpha[mm - 1] = r[0];
-    }
-    *m_eff = eff;
-    return SD_OK;
+    return sd_lanczos_engine(m, v, SD_C128, mm, tol, 1.0, alpha, beta, m_eff, normv, nullptr, nullptr);   // :209-239
 }
 
 int sd_lanczos_groundstate(sd_model *m, const sd_vec *v0, int lanc_m, double tol, double orth_tol,
@@ -1970,6 +2002,9 @@ int sd_lanczos_groundstate(sd_model *m, const sd_vec *v0, int lanc_m, double tol
 //       regenerated v_j are bit-identical to pass 1 -- accumulating out = sum_{j < m_eff} y[j] v_j; *norm2 = ||out||^2.
 // Without reorthogonalisation converged Ritz values reappear as copies, which leaves the lowest Ritz value and the
 // direction of V*y alone; callers gate on E0 against the faithful path (tests: 1e-10).
+// Memory-lean ground state: sd_lanczos_engine on three f64 vectors, called twice by the host.  Pass 1
+// (y == NULL) returns alpha / beta; pass 2 (y = the Ritz coefficients, alpha / beta of pass 1 as inputs) accumulates
+// out = sum_j y_j v_j from the regenerated vectors; norm2 = ||out||^2.
 int sd_lanczos_lean(sd_model *m, const sd_vec *v0, int lanc_m, double tol, double *alpha, double *beta, int *m_eff,
                     const double *y, sd_vec *out, double *norm2) {
     SD_ARG(m && v0 && alpha && beta && m_eff, "NULL argument");
@@ -1979,38 +2014,7 @@ int sd_lanczos_lean(sd_model *m, const sd_vec *v0, int lanc_m, double tol, doubl
     sd_ctx *c = m->ctx;
     SD_LOCK(c); SD_TRY(sd_use(c));
     const int mm = (int)std::min<uint64_t>((uint64_t)lanc_m, m->N);
-    SdVecGuard G;
-    sd_vec *vj, *vo, *w;
-    SD_TRY(G.make(m, SD_F64, &vj)); SD_TRY(G.make(m, SD_F64, &vo)); SD_TRY(G.make(m, SD_F64, &w));
-    double n0;
-    SD_TRY(sd_normalised_copy(vj, v0, &n0));
-    if (n0 == 0.0) return sd_fail(SD_ERR_ZERO_NORM, "starting vector has zero norm");
-    if (y) {
-        SD_TRY(sd_vec_zero(out));
-        SD_TRY(sd_axpy_impl(out, sd_host_scalar(y[0], 0), vj, sd_host_scalar(0, 0), nullptr, -1));
-    }
-    int eff = mm;
-    for (int j = 1; j <= mm; ++j) {
-        if (y && j == mm) break;                                             // pass 2 needs v_1 .. v_mm only
-        SdEpi e = sd_epi_plain(1.0);
-        e.red = SD_RED_DOT_SELF;
-        SD_TRY(sd_apply_impl(m, w, vj, e, 0));                               // w = H v_j, <v_j, w> -> d_scal[0]
-        const SdScalar sa = y ? sd_host_scalar(-alpha[j - 1], 0) : sd_dev_scalar(c->d_scal + 0, 4);
-        if (j == 1) SD_TRY(sd_axpy_impl(w, sa, vj, sd_host_scalar(0, 0), nullptr, 4));
-        else SD_TRY(sd_axpy_impl(w, sa, vj, sd_host_scalar(-beta[j - 2], 0), vo, 4));
-        if (!y) {
-            double r[8];
-            SD_TRY(sd_fetch(c, 0, 8, r));
-            alpha[j - 1] = r[0];
-            if (j == mm) break;
-            beta[j - 1] = sqrt(r[7]);
-            if (beta[j - 1] < tol) { eff = j; break; }
-        }
-        std::swap(vj, vo);
-        SD_TRY(sd_divide_impl(vj, w, sd_host_scalar(beta[j - 1], 0)));       // v_{j+1} = w / beta_j
-        if (y) SD_TRY(sd_axpy_impl(out, sd_host_scalar(y[j], 0), vj, sd_host_scalar(0, 0), nullptr, -1));
-    }
-    *m_eff = eff;
+    SD_TRY(sd_lanczos_engine(m, v0, SD_F64, mm, tol, 1.0, alpha, beta, m_eff, nullptr, y, out));
     if (y) {
         SD_TRY(sd_dot_impl(out, out, 1, 0));
         double r[2];

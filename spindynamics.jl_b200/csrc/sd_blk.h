@@ -122,7 +122,6 @@ struct alignas(16) SdBlkHdr {
     int js, jsx;                         // suffix popcount of the tile / of the crossing partner tile
     int valid;                           // 1: tile, -1: end of this CTA's tile list
     int nnb, nfar;                       // active prefix-internal bonds; the first nfar are beyond L2 reach
-    int nloc;                            // entries [0, nloc) are local tiles, [nloc, nnb) tiles on other GPUs
     int ntot;                            // nnb + 1 if the prefix|mid crossing bond is active: entry nnb of nb[]
     int bP;                              // last prefix bit
     unsigned next_unit;                  // work counter of the consumer warps
@@ -149,8 +148,6 @@ struct SdBlkHdrLane {
     double d;                    // diagonal contribution of site q and bond (q, q+1)
     int bit;
     bool act;                    // bond (q, q+1) is an active prefix-internal hop
-    uint64_t nbase;              // stored base of the bond partner tile (sd_blk_hdr_nb, once the tile base is known)
-    bool rem;                    // ... which another rank owns
 };
 SD_HD SdBlkHdrLane sd_blk_hdr_lane(const SdBlkParams &P, const uint64_t *W, uint64_t Pb, int q) {
     const int A = P.A;
@@ -171,32 +168,24 @@ SD_HD SdBlkHdrLane sd_blk_hdr_lane(const SdBlkParams &P, const uint64_t *W, uint
     }
     return l;
 }
-// after the warp-wide sum base = sum(term): the lane's bond partner tile and whether a peer owns it
-SD_HD void sd_blk_hdr_nb(const SdBlkParams &P, SdBlkHdrLane &l, uint64_t base) {
-    l.nbase = 0; l.rem = false;
-    if (l.act) {
-        // (1,0) -> (0,1): + (W[q][below] - W[q+1][below+1]);  (0,1) -> (1,0): the negative
-        const uint64_t dl = l.wq - l.wn;
-        l.nbase = l.bit ? base + dl : base - dl;
-        l.rem = sd_blk_owner(P.shards, l.nbase) != P.shards.rank;
-    }
-}
-// second half, after the warp-wide sums base = sum(term), dpre = sum(d), actmask = ballot(act), remmask = ballot(rem).
-// Entry order: local partner tiles first (those beyond L2 reach, q < qfar, before the near ones), then the tiles on
-// other GPUs: their loads take ~3 us over NVLink, so the item body prefetches them first and consumes them last.
+// second half, after the warp-wide sums base = sum(term), dpre = sum(d), actmask = ballot(act).
+// Entry order: partner tiles beyond L2 reach (q < qfar; on other GPUs when sharded) before the near ones.
+// (Round 2 tried the remote tiles last with an L1 prefetch at the start of the item: peer-memory prefetches are
+// pathologically slow -- 237 ms per L = 32 apply on 2 GPUs instead of 3.4 -- so remote tiles are plain .cg loads.)
 template <int NC, class HDR = SdBlkHdr>
 SD_HD void sd_blk_hdr_fill(const SdBlkParams &P, const SdBlkHdrLane &l, uint64_t Pb, uint64_t key, uint64_t base, double dpre,
-                           unsigned actmask, unsigned remmask, int qfar, int q, HDR &H, const SdVecView &psi) {
+                           unsigned actmask, int qfar, int q, HDR &H, const SdVecView &psi) {
     const int A = P.A, js = P.k - SD_POPC64(Pb);
     const int bit = l.bit;
     const unsigned farmask = (qfar >= 32) ? 0xffffffffu : ((1u << qfar) - 1u);
-    const unsigned locmask = actmask & ~remmask;
-    const int nfar = SD_POPC32(locmask & farmask);
+    const int nfar = SD_POPC32(actmask & farmask);
     if (l.act) {
+        // (1,0) -> (0,1): + (W[q][below] - W[q+1][below+1]);  (0,1) -> (1,0): the negative
+        const uint64_t dl = l.wq - l.wn;
+        const uint64_t nbase = bit ? base + dl : base - dl;
         const unsigned lt = (1u << q) - 1u;
-        const int slot = l.rem ? SD_POPC32(locmask) + SD_POPC32(remmask & lt)
-                               : (((farmask >> q) & 1u) ? SD_POPC32(locmask & farmask & lt) : nfar + SD_POPC32(locmask & ~farmask & lt));
-        H.nb[slot].p = psi.base[sd_blk_owner(P.shards, l.nbase)] + (size_t)NC * l.nbase;
+        const int slot = ((farmask >> q) & 1u) ? SD_POPC32(actmask & farmask & lt) : nfar + SD_POPC32(actmask & ~farmask & lt);
+        H.nb[slot].p = psi.base[sd_blk_owner(P.shards, nbase)] + (size_t)NC * nbase;
         H.nb[slot].J = P.Jhop[q];
     }
     if (q == A - 1) {                                             // prefix|mid crossing bond
@@ -222,7 +211,6 @@ SD_HD void sd_blk_hdr_fill(const SdBlkParams &P, const SdBlkHdrLane &l, uint64_t
         H.js = js;
         H.valid = 1;
         H.nnb = SD_POPC32(actmask);
-        H.nloc = SD_POPC32(locmask);
         H.nfar = nfar;
         {
             const int bl = (int)((Pb >> (A - 1)) & 1ULL), jsx = bl ? js + 1 : js - 1;
@@ -248,9 +236,7 @@ __device__ __forceinline__ void sd_blk_make_hdr(const SdBlkParams &P, const uint
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dpre += __shfl_xor_sync(0xffffffffu, dpre, o);
     const unsigned actmask = __ballot_sync(0xffffffffu, l.act);
-    sd_blk_hdr_nb(P, l, base);
-    const unsigned remmask = __ballot_sync(0xffffffffu, l.rem);
-    sd_blk_hdr_fill<NC, HDR>(P, l, Pb, key, base, dpre, actmask, remmask, qfar, (int)lane, H, psi);
+    sd_blk_hdr_fill<NC, HDR>(P, l, Pb, key, base, dpre, actmask, qfar, (int)lane, H, psi);
 }
 #endif
 // the same header on the host (tests/emul, sd_halo_host.h): the 32 "lanes" in a loop
@@ -260,18 +246,14 @@ inline void sd_blk_hdr_host(const SdBlkParams &P, const uint64_t *W, uint64_t ke
     SdBlkHdrLane lanes[32];
     uint64_t base = 0;
     double dpre = 0.0;
-    unsigned actmask = 0, remmask = 0;
+    unsigned actmask = 0;
     for (int q = 0; q < 32; ++q) {
         lanes[q] = sd_blk_hdr_lane(P, W, Pb, q);
         base += lanes[q].term;
         dpre += lanes[q].d;
         if (lanes[q].act) actmask |= 1u << q;
     }
-    for (int q = 0; q < 32; ++q) {
-        sd_blk_hdr_nb(P, lanes[q], base);
-        if (lanes[q].rem) remmask |= 1u << q;
-    }
-    for (int q = 0; q < 32; ++q) sd_blk_hdr_fill<NC>(P, lanes[q], Pb, key, base, dpre, actmask, remmask, qfar, q, H, psi);
+    for (int q = 0; q < 32; ++q) sd_blk_hdr_fill<NC>(P, lanes[q], Pb, key, base, dpre, actmask, qfar, q, H, psi);
 }
 
 // ------------------------------------------------------------------ per-item body
@@ -293,34 +275,6 @@ SD_HD double2 sd_blk_ldg(const double *p) {
 #else
     v.x = p[0]; v.y = p[1];
 #endif
-    return v;
-}
-// tiles on another GPU: peer memory is cached in L1 only (the local L2 is bypassed), so the item body prefetches the
-// lines into L1 at its start and reads them with .ca at its end
-SD_HD void sd_blk_prefetch_l1(const double *p) {
-#if defined(__CUDA_ARCH__)
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-#else
-    (void)p;
-#endif
-}
-SD_HD double2 sd_blk_ldg_ca(const double *p) {
-    double2 v;
-#if defined(__CUDA_ARCH__)
-    asm("ld.global.ca.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-#else
-    v.x = p[0]; v.y = p[1];
-#endif
-    return v;
-}
-SD_HD double2 sd_blk_ldg_ca_half(const double *p) {
-    double2 v;
-#if defined(__CUDA_ARCH__)
-    asm("ld.global.ca.f64 %0, [%1];" : "=d"(v.x) : "l"(p));
-#else
-    v.x = p[0];
-#endif
-    v.y = 0.0;
     return v;
 }
 SD_HD double2 sd_blk_ldg_half(const double *p) {

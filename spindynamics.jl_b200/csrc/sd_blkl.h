@@ -47,6 +47,7 @@ static SdBlkShared sd_blkl_sh;
 // fills the context part of SD_SH (device: one thread, before the CTA barrier; host: the emulation)
 SD_BLKL_FN void sd_blkl_ctx_init(const SdBlkParams &P, double *out_local, const SdEpi &epi) {
     SD_SH.epi = epi;
+    if (epi.hscale_dev) { SD_SH.epi.hscale = epi.hscale / sqrt(*epi.hscale_dev); SD_SH.epi.hscale_dev = nullptr; }
     SD_SH.out_local = out_local;
     SD_SH.pstart_local = P.shards.pstart[P.shards.rank];
     SD_SH.items = P.items;
@@ -79,13 +80,6 @@ SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdBlkHdr &H, const doub
         _Pragma("unroll") for (int s = 0; s < EC; ++s)                                        \
             t_[s] = (HALF && s == EC - 1) ? sd_blk_ldg_half(q_ + o[s]) : sd_blk_ldg(q_ + o[s]); \
     } while (0)
-#define SD_LEAN_LOAD_R(t_, p_)        /* tile on another GPU (prefetched into L1 above) */      \
-    do {                                                                                      \
-        const double *q_ = (p_);                                                              \
-        _Pragma("unroll") for (int s = 0; s < EC; ++s)                                        \
-            t_[s] = (HALF && s == EC - 1) ? sd_blk_ldg_ca_half(q_ + o[s]) : sd_blk_ldg_ca(q_ + o[s]); \
-    } while (0)
-#define SD_LEAN_LOADN(t_, p_, n_) do { if ((n_) < nloc) SD_LEAN_LOAD(t_, p_); else SD_LEAN_LOAD_R(t_, p_); } while (0)
 #define SD_LEAN_FMA(t_, J_)                                                                   \
     do {                                                                                      \
         const double j_ = (J_);                                                               \
@@ -94,12 +88,7 @@ SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdBlkHdr &H, const doub
     // ---- prefix|mid crossing bond: partner tile with js +- 1, same class, uniform block shift; only the lanes whose
     // first mid bit differs from the last prefix bit
     const bool c0 = u < cls.n1;                                      // first mid bit (blocks with it set come first)
-    const int nnb = H.nnb, nloc = H.nloc;
-    for (int n = nloc; n < nnb; ++n) {                                // sharded runs only: NVLink latency starts now
-        const double *q_ = H.nb[n].p;
-#pragma unroll
-        for (int s = 0; s < EC; ++s) sd_blk_prefetch_l1(q_ + o[s]);
-    }
+    const int nnb = H.nnb;
     bool xl = false;
     if (H.xptr != nullptr) {
         xl = c0 != (bool)H.bP;
@@ -115,22 +104,20 @@ SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdBlkHdr &H, const doub
     }
     // ---- prefix-internal bonds: whole neighbour tiles in the same element order
     SdBlkEnt e0 = H.nb[0], e1;                                       // {tile base, J}: one LDS.128 per entry
-    if (nnb > 0) SD_LEAN_LOADN(t0, e0.p, 0);
+    if (nnb > 0) SD_LEAN_LOAD(t0, e0.p);
     if (xl) SD_LEAN_FMA(t1, H.Jx);
     int n = 0;
 #pragma unroll 1
     while (n + 1 < nnb) {
         e1 = H.nb[n + 1];
-        SD_LEAN_LOADN(t1, e1.p, n + 1);
+        SD_LEAN_LOAD(t1, e1.p);
         SD_LEAN_FMA(t0, e0.J);
-        if (n + 2 < nnb) { e0 = H.nb[n + 2]; SD_LEAN_LOADN(t0, e0.p, n + 2); }
+        if (n + 2 < nnb) { e0 = H.nb[n + 2]; SD_LEAN_LOAD(t0, e0.p); }
         SD_LEAN_FMA(t1, e1.J);
         n += 2;
     }
     if (n < nnb) SD_LEAN_FMA(t0, e0.J);
 #undef SD_LEAN_LOAD
-#undef SD_LEAN_LOAD_R
-#undef SD_LEAN_LOADN
 #undef SD_LEAN_FMA
     // ---- own block: diagonal + tail-internal hops (registers, compile-time permutation)
     const uint4 it = sd_blk_ld_item(SD_SH.items + cls.item_off + u);     // x,y,z = nb[12]; w = c | u2x << 16

@@ -11,6 +11,7 @@
 // Nothing here stores states[] or a Dict (Basis.jl:49-52 is replaced).
 #pragma once
 #include <stdint.h>
+#include <math.h>
 
 #if defined(__CUDACC__)
 #define SD_HD __host__ __device__ __forceinline__
@@ -149,6 +150,8 @@ struct SdEpi {
     int mode;
     int red;                 // bitmask of SD_RED_*
     double hscale, a, b;
+    const double *hscale_dev; // non-null: hscale / sqrt(*hscale_dev) is used  (deferred normalisation of the Lanczos vectors:
+                              // *hscale_dev = ||u_j||^2 from the previous fused reduction, no host round trip)
     double ck_re, ck_im;
     const double *vprev;     // mode 2
     const double *phi;       // SD_RED_DOT_PHI
@@ -169,9 +172,10 @@ template <int NC>
 SD_HD SdVal<NC> sd_epilogue(const SdEpi &e, SdVal<NC> h, SdVal<NC> p, uint64_t li,
                             double (&red)[SD_NSLOT]) {
     SdVal<NC> o;
+    const double hs = e.hscale_dev ? e.hscale / sqrt(*e.hscale_dev) : e.hscale;   // (the block kernel resolves the pointer once per CTA)
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-        double v = e.hscale * h.c[c];
+        double v = hs * h.c[c];
         if (e.mode != SD_EPI_PLAIN) {
             v = (v - e.b * p.c[c]) / e.a;
             if (e.mode == SD_EPI_CHEB) v = 2.0 * v - e.vprev[li * NC + c];

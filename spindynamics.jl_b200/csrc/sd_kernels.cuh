@@ -320,30 +320,50 @@ __device__ __forceinline__ void sd_load_scalar(const SdScalar &s, double &re, do
     }
 }
 
+// ---- streaming BLAS-1 kernels.  All of them move 16-byte units (double2: one c128 element or two f64 elements),
+// four units per thread and loop trip with the loads issued before the first store, grid-stride over the vector; an
+// odd f64 tail element is handled by one thread.  n = elements, units = n * NC / 2.
+#define SD_BLAS_UNROLL 4
+__device__ __forceinline__ double2 sd_ld2(const double *p, uint64_t unit) { return *(const double2 *)(p + 2 * unit); }
+__device__ __forceinline__ void sd_st2(double *p, uint64_t unit, double2 v) { *(double2 *)(p + 2 * unit) = v; }
+
 // x *= s
 template <int NC>
-__global__ void sd_scale_kernel(double *x, uint64_t n, const __grid_constant__ SdScalar s) {
+__global__ void __launch_bounds__(SD_BLAS_THREADS) sd_scale_kernel(double *x, uint64_t n, const __grid_constant__ SdScalar s) {
     double sr, si;
     sd_load_scalar(s, sr, si);
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (uint64_t)gridDim.x * blockDim.x) {
-        if (NC == 2) {
-            const double a = x[2 * i], b = x[2 * i + 1];
-            x[2 * i] = sr * a - si * b; x[2 * i + 1] = sr * b + si * a;
-        } else x[i] *= sr;
+    const uint64_t units = n * NC / 2, stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < units; i0 += SD_BLAS_UNROLL * stride) {
+        double2 v[SD_BLAS_UNROLL];
+#pragma unroll
+        for (int k = 0; k < SD_BLAS_UNROLL; ++k) if (i0 + k * stride < units) v[k] = sd_ld2(x, i0 + k * stride);
+#pragma unroll
+        for (int k = 0; k < SD_BLAS_UNROLL; ++k) {
+            if (i0 + k * stride >= units) continue;
+            const double2 a = v[k];
+            sd_st2(x, i0 + k * stride, NC == 2 ? make_double2(sr * a.x - si * a.y, sr * a.y + si * a.x) : make_double2(sr * a.x, sr * a.y));
+        }
     }
+    if (NC == 1 && (n & 1) && blockIdx.x == 0 && threadIdx.x == 0) x[n - 1] *= sr;
 }
-// x = x / s (true division by a real scalar, as `w / beta` in Lanczos.jl:71,155,233)
+// y = x / s (true division by a real scalar, as `w / beta` in Lanczos.jl:71,155,233)
 template <int NC>
-__global__ void sd_divide_kernel(double *y, const double *x, uint64_t n, const __grid_constant__ SdScalar s) {
+__global__ void __launch_bounds__(SD_BLAS_THREADS) sd_divide_kernel(double *y, const double *x, uint64_t n, const __grid_constant__ SdScalar s) {
     double sr, si;
     sd_load_scalar(s, sr, si);
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * NC;
-         i += (uint64_t)gridDim.x * blockDim.x)
-        y[i] = x[i] / sr;
+    const uint64_t units = n * NC / 2, stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < units; i0 += SD_BLAS_UNROLL * stride) {
+        double2 v[SD_BLAS_UNROLL];
+#pragma unroll
+        for (int k = 0; k < SD_BLAS_UNROLL; ++k) if (i0 + k * stride < units) v[k] = sd_ld2(x, i0 + k * stride);
+#pragma unroll
+        for (int k = 0; k < SD_BLAS_UNROLL; ++k)
+            if (i0 + k * stride < units) sd_st2(y, i0 + k * stride, make_double2(v[k].x / sr, v[k].y / sr));
+    }
+    if (NC == 1 && (n & 1) && blockIdx.x == 0 && threadIdx.x == 0) y[n - 1] = x[n - 1] / sr;
 }
 
-// y += a x  [+ b z]; optionally ||y||^2 (slot 3) and dot(x, y_new) (slots 0,1)
+// y += a x  [+ b z]; optionally ||y||^2 (slot 3)
 template <int NC>
 __global__ void __launch_bounds__(SD_BLAS_THREADS)
 sd_axpy_kernel(double *y, uint64_t n, const __grid_constant__ SdScalar a, const double *x,
@@ -353,24 +373,38 @@ sd_axpy_kernel(double *y, uint64_t n, const __grid_constant__ SdScalar a, const 
     double ar, ai, br = 0.0, bi = 0.0;
     sd_load_scalar(a, ar, ai);
     if (z) sd_load_scalar(b, br, bi);
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (uint64_t)gridDim.x * blockDim.x) {
-        if (NC == 2) {
-            double yr = y[2 * i], yi = y[2 * i + 1];
-            const double xr = x[2 * i], xi = x[2 * i + 1];
-            yr += ar * xr - ai * xi; yi += ar * xi + ai * xr;
-            if (z) {
-                const double zr = z[2 * i], zi = z[2 * i + 1];
-                yr += br * zr - bi * zi; yi += br * zi + bi * zr;
-            }
-            y[2 * i] = yr; y[2 * i + 1] = yi;
-            red[3] += yr * yr + yi * yi;
-        } else {
-            double yr = y[i] + ar * x[i];
-            if (z) yr += br * z[i];
-            y[i] = yr;
-            red[3] += yr * yr;
+    const uint64_t units = n * NC / 2, stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < units; i0 += SD_BLAS_UNROLL * stride) {
+        double2 vy[SD_BLAS_UNROLL], vx[SD_BLAS_UNROLL], vz[SD_BLAS_UNROLL];
+#pragma unroll
+        for (int k = 0; k < SD_BLAS_UNROLL; ++k) {
+            const uint64_t i = i0 + k * stride;
+            vy[k] = vx[k] = vz[k] = make_double2(0.0, 0.0);
+            if (i >= units) continue;
+            vy[k] = sd_ld2(y, i); vx[k] = sd_ld2(x, i);
+            if (z) vz[k] = sd_ld2(z, i);
         }
+#pragma unroll
+        for (int k = 0; k < SD_BLAS_UNROLL; ++k) {
+            const uint64_t i = i0 + k * stride;
+            if (i >= units) continue;
+            double2 r = vy[k];
+            if (NC == 2) {
+                r.x += ar * vx[k].x - ai * vx[k].y; r.y += ar * vx[k].y + ai * vx[k].x;
+                if (z) { r.x += br * vz[k].x - bi * vz[k].y; r.y += br * vz[k].y + bi * vz[k].x; }
+            } else {
+                r.x += ar * vx[k].x; r.y += ar * vx[k].y;
+                if (z) { r.x += br * vz[k].x; r.y += br * vz[k].y; }
+            }
+            sd_st2(y, i, r);
+            red[3] += r.x * r.x + r.y * r.y;
+        }
+    }
+    if (NC == 1 && (n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        double r = y[n - 1] + ar * x[n - 1];
+        if (z) r += br * z[n - 1];
+        y[n - 1] = r;
+        red[3] += r * r;
     }
     if (partials) sd_block_reduce_store(red, 8, scratch, partials, nparts, blockIdx.x);
 }
@@ -381,17 +415,87 @@ __global__ void __launch_bounds__(SD_BLAS_THREADS)
 sd_dot_kernel(const double *x, const double *y, uint64_t n, int conj, double *partials, unsigned nparts) {
     __shared__ double scratch[SD_NSLOT][16];
     double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (uint64_t)gridDim.x * blockDim.x) {
-        if (NC == 2) {
-            const double xr = x[2 * i], xi = conj ? x[2 * i + 1] : -x[2 * i + 1];
-            const double yr = y[2 * i], yi = y[2 * i + 1];
-            red[0] += xr * yr + xi * yi;
-            red[1] += xr * yi - xi * yr;
-        } else red[0] += x[i] * y[i];
+    const uint64_t units = n * NC / 2, stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < units; i0 += SD_BLAS_UNROLL * stride) {
+        double2 vx[SD_BLAS_UNROLL], vy[SD_BLAS_UNROLL];
+#pragma unroll
+        for (int k = 0; k < SD_BLAS_UNROLL; ++k) {
+            vx[k] = vy[k] = make_double2(0.0, 0.0);
+            if (i0 + k * stride < units) { vx[k] = sd_ld2(x, i0 + k * stride); vy[k] = sd_ld2(y, i0 + k * stride); }
+        }
+#pragma unroll
+        for (int k = 0; k < SD_BLAS_UNROLL; ++k) {
+            if (NC == 2) {
+                const double xi = conj ? vx[k].y : -vx[k].y;
+                red[0] += vx[k].x * vy[k].x + xi * vy[k].y;
+                red[1] += vx[k].x * vy[k].y - xi * vy[k].x;
+            } else red[0] += vx[k].x * vy[k].x + vx[k].y * vy[k].y;
+        }
     }
+    if (NC == 1 && (n & 1) && blockIdx.x == 0 && threadIdx.x == 0) red[0] += x[n - 1] * y[n - 1];
     sd_block_reduce_store(red, 3, scratch, partials, nparts, blockIdx.x);
 }
+
+// Fused tail of a Lanczos step with deferred normalisation (Lanczos.jl:52-65,124-155,219-233 in one 3R+1W pass, no
+// `w / beta` pass).  The vectors are kept UNNORMALISED: u_1 = v0, u_{j+1} = w_j, v_j = u_j / beta_{j-1} with
+// beta_0 = ||v0||.  The apply before this kernel wrote  w = H v_j = (1 / beta_{j-1}) H u_j  (epilogue hscale) and
+// d = <u_j, w>; here
+//     alpha_j = d / beta_{j-1},   w -= (alpha_j / beta_{j-1}) u_j + (beta_{j-1} / beta_{j-2}) u_{j-1},   n_j = ||w||^2
+// and, for the second pass of the memory-lean ground state, out += (y_j / beta_{j-1}) u_j.
+// beta = sqrt(n), the divisions and the sqrt are IEEE operations, so a host that recomputes alpha and beta from the
+// fetched (d, n) gets the same bits and pass 2 (host scalars) regenerates the vectors of pass 1 (device scalars) exactly.
+struct SdLanczosScal {
+    const double *d_dev, *n1_dev, *n2_dev;   // device: <u_j, w>, ||u_j||^2 = beta_{j-1}^2, ||u_{j-1}||^2; d_dev null -> host values:
+    double alpha, b1, b2;                     // alpha_j, beta_{j-1}, beta_{j-2}
+    double yj;                                // pass 2: Ritz coefficient of v_j (0: no accumulation)
+};
+template <int NC>
+__global__ void __launch_bounds__(SD_BLAS_THREADS)
+sd_lanczos_update_kernel(double *w, const double *u, const double *uo, double *out, uint64_t n,
+                         const __grid_constant__ SdLanczosScal S, double *partials, unsigned nparts) {
+    __shared__ double scratch[SD_NSLOT][16];
+    double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
+    double alpha = S.alpha, b1 = S.b1, b2 = S.b2;
+    if (S.d_dev) {
+        b1 = sqrt(*S.n1_dev);
+        alpha = *S.d_dev / b1;
+        if (uo) b2 = sqrt(*S.n2_dev);
+    }
+    const double ca = alpha / b1, cb = uo ? b1 / b2 : 0.0, co = S.yj / b1;
+    const uint64_t units = n * NC / 2, stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < units; i0 += SD_BLAS_UNROLL * stride) {
+        double2 vw[SD_BLAS_UNROLL], vu[SD_BLAS_UNROLL], vo[SD_BLAS_UNROLL], va[SD_BLAS_UNROLL];
+#pragma unroll
+        for (int k = 0; k < SD_BLAS_UNROLL; ++k) {
+            const uint64_t i = i0 + k * stride;
+            vw[k] = vu[k] = vo[k] = va[k] = make_double2(0.0, 0.0);
+            if (i >= units) continue;
+            vw[k] = sd_ld2(w, i); vu[k] = sd_ld2(u, i);
+            if (uo) vo[k] = sd_ld2(uo, i);
+            if (out) va[k] = sd_ld2(out, i);
+        }
+#pragma unroll
+        for (int k = 0; k < SD_BLAS_UNROLL; ++k) {
+            const uint64_t i = i0 + k * stride;
+            if (i >= units) continue;
+            double2 r = vw[k];
+            r.x -= ca * vu[k].x; r.y -= ca * vu[k].y;
+            if (uo) { r.x -= cb * vo[k].x; r.y -= cb * vo[k].y; }
+            sd_st2(w, i, r);
+            red[3] += r.x * r.x + r.y * r.y;
+            if (out) sd_st2(out, i, make_double2(va[k].x + co * vu[k].x, va[k].y + co * vu[k].y));
+        }
+    }
+    if (NC == 1 && (n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        double r = w[n - 1] - ca * u[n - 1];
+        if (uo) r -= cb * uo[n - 1];
+        w[n - 1] = r;
+        red[3] += r * r;
+        if (out) out[n - 1] += co * u[n - 1];
+    }
+    sd_block_reduce_store(red, 8, scratch, partials, nparts, blockIdx.x);
+}
+
 
 // block dot: c[j] = dot(V_j, w) for j < m (full reorthogonalisation, Lanczos.jl:116-122
 // computes these one at a time; the block form reads w once).  partials: [m][nparts].

@@ -68,3 +68,47 @@ def test_lean_breakdown_on_an_invariant_start_vector():
     _, gs = orc.lanczos_groundstate(orc.apply_H_, m, lanc_m=70, v0=np.random.default_rng(0).standard_normal(len(m)))
     E, psi, k = lean_groundstate(m, gs, 40, tol=1e-8)
     assert k < 40 and abs(E - (-3.374932598687896)) < 1e-10 and abs(abs(psi @ gs) - 1) < 1e-10
+
+
+def deferred_recurrence(m, v0, steps, hsign=1.0):
+    """Mirror of sd_lanczos_engine (pass 1): unnormalised vectors u_1 = v0, u_{j+1} = w_j, v_j = u_j / beta_{j-1};
+    apply w = (hsign / beta_{j-1}) H u_j with d_j = <u_j, w>; update w -= (alpha_j / beta_{j-1}) u_j +
+    (beta_{j-1} / beta_{j-2}) u_{j-1}; alpha_j = d_j / beta_{j-1}, beta_j = ||w||.  No vector is ever divided."""
+    N = len(m)
+    u, uo, w = v0.copy(), np.zeros(N), np.empty(N)
+    n = [float(v0 @ v0)]
+    alpha, beta = [], []
+    for j in range(1, steps + 1):
+        b1 = np.sqrt(n[j - 1])
+        orc.apply_H_(w, u, m)
+        w *= hsign / b1
+        d = float(u @ w)
+        al = d / b1
+        alpha.append(al)
+        if j == steps:
+            break
+        w -= (al / b1) * u
+        if j >= 2:
+            w -= (b1 / np.sqrt(n[j - 2])) * uo
+        n.append(float(w @ w))
+        beta.append(np.sqrt(n[j]))
+        uo, u, w = u, w, uo
+    return np.array(alpha), np.array(beta)
+
+
+@pytest.mark.parametrize("L,nup,steps", [(8, 4, 20), (10, 5, 40), (12, 6, 60)])
+def test_deferred_normalisation_gives_the_same_tridiagonal_matrix(L, nup, steps):
+    """The fused recurrence of sd_lanczos_engine against the textbook one (oracle lanczos_tridiag, Lanczos.jl:196-246)."""
+    m = orc.XXZChain(L, Jxy=1.0, Jz=1.0, nup=nup)
+    rng = np.random.default_rng(L)
+    v0 = 3.7 * rng.standard_normal(len(m))                                       # not normalised on purpose
+    a, b = deferred_recurrence(m, v0, steps)
+    ar, br, nv = orc.lanczos_tridiag(orc.apply_H_, m, v0.astype(np.complex128), lanc_m=steps)
+    assert abs(nv - np.linalg.norm(v0)) < 1e-12
+    k = min(len(a), len(ar), 15)              # before rounding noise separates two unorthogonalised recurrences
+    assert np.allclose(a[:k], ar[:k], atol=1e-9) and np.allclose(b[:k - 1], br[:k - 1], atol=1e-9)
+    ev = eigh_tridiagonal(a, b, eigvals_only=True)
+    evr = eigh_tridiagonal(np.asarray(ar), np.asarray(br), eigvals_only=True)
+    assert abs(ev[0] - evr[0]) < 1e-10 and abs(ev[-1] - evr[-1]) < 1e-10
+    an, bn = deferred_recurrence(m, v0, steps, hsign=-1.0)                       # -H (estimate_energy_bounds, Lanczos.jl:261-265)
+    assert abs(eigh_tridiagonal(an, bn, eigvals_only=True)[0] + ev[-1]) < 1e-10
