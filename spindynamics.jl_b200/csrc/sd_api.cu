@@ -25,6 +25,7 @@
 #include "sd_blk_host.h"
 #include "sd_blkl.h"
 #include "sd_obs.h"
+#include "sd_blkv.h"
 #include "sd_bdot.cuh"
 #include "sd_halo_host.h"
 #include <cuda.h>          // driver-API types only; the functions are resolved with dlopen (virtual memory management of the halo mirror)
@@ -1595,6 +1596,33 @@ int sd_szq(sd_model *m, sd_vec *phi, const sd_vec *psi0, double q, double *norm2
     sd_ctx *c = m->ctx;
     SD_LOCK(c); SD_TRY(sd_use(c));
     SD_TRY(sd_before_write(c, phi));
+    if (phi->layout) {                               // block layout: the state of an element is known from its position (sd_blkv.h)
+        SD_ARG(psi0->layout, "vectors differ in layout");
+        SdBlkParams P = sd_blk_params(m, 2);
+        SdBlkSzq ZB;
+        ZB.normfact = 1.0 / sqrt((double)m->L);
+        for (int r = 0; r <= SD_MAX_L; ++r) { ZB.ph_re[r] = r < m->L ? cos(q * (double)r) : 0.0; ZB.ph_im[r] = r < m->L ? sin(q * (double)r) : 0.0; }
+        const uint64_t nkeys = P.key_hi - P.key_lo;
+        const unsigned g = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(nkeys, (uint64_t)c->sm_count * 16));
+        double *partials = nullptr;
+        if (norm2) {
+            SD_TRY(sd_partials_reserve(c, (size_t)SD_NSLOT * g));
+            partials = c->d_partials;
+            if (nkeys == 0) SD_CUDA(cudaMemsetAsync(partials, 0, (size_t)SD_NSLOT * g * sizeof(double), c->stream));
+        }
+        if (nkeys > 0) {
+            if (psi0->nc == 2) sd_blk_szq_kernel<2><<<g, 256, 0, c->stream>>>(P, ZB, psi0->d, phi->d, partials, g);
+            else sd_blk_szq_kernel<1><<<g, 256, 0, c->stream>>>(P, ZB, psi0->d, phi->d, partials, g);
+            SD_TRY(sd_launch_check(c, "sd_blk_szq_kernel"));
+        }
+        if (norm2) {
+            SD_TRY(sd_finish_reduce(c, g, 8, 0));
+            double r[4];
+            SD_TRY(sd_fetch(c, 0, 4, r));
+            *norm2 = r[3];
+        }
+        return SD_OK;
+    }
     SdSzqParams Z;
     Z.L = m->L; Z.k = m->k; Z.normfact = 1.0 / sqrt((double)m->L); Z.binom = c->d_binom;
     for (int r = 0; r < m->L; ++r) { Z.ph_re[r] = cos(q * (double)r); Z.ph_im[r] = sin(q * (double)r); }
@@ -1602,25 +1630,12 @@ int sd_szq(sd_model *m, sd_vec *phi, const sd_vec *psi0, double q, double *norm2
     double *partials = nullptr;
     if (norm2) { SD_TRY(sd_partials_reserve(c, (size_t)SD_NSLOT * g)); partials = c->d_partials; }
     const uint64_t ls = m->shards.start[c->rank];
-    const double *src = psi0->d;
-    double *dst = phi->d;
-    if (phi->layout) {                               // block layout: the state of an element comes from its rank,
-        double *s0 = nullptr, *s1 = nullptr;         // so run on rank-ordered staging copies (not a hot path)
-        SD_TRY(sd_scratch(c, 0, sd_vec_logical_bytes(psi0) + 16, &s0));
-        SD_TRY(sd_scratch(c, 1, sd_vec_logical_bytes(phi) + 16, &s1));
-        SD_TRY(sd_blk_permute(psi0, s0, psi0->nc, 1, 0, 0, 0.0));
-        src = s0; dst = s1;
-    }
     if (phi->logical_n > 0) {
-        if (psi0->nc == 2) sd_szq_kernel<2><<<g, SD_BLAS_THREADS, 0, c->stream>>>(Z, ls, phi->logical_n, src, dst, partials, g);
-        else sd_szq_kernel<1><<<g, SD_BLAS_THREADS, 0, c->stream>>>(Z, ls, phi->logical_n, src, dst, partials, g);
+        if (psi0->nc == 2) sd_szq_kernel<2><<<g, SD_BLAS_THREADS, 0, c->stream>>>(Z, ls, phi->logical_n, psi0->d, phi->d, partials, g);
+        else sd_szq_kernel<1><<<g, SD_BLAS_THREADS, 0, c->stream>>>(Z, ls, phi->logical_n, psi0->d, phi->d, partials, g);
         SD_TRY(sd_launch_check(c, "sd_szq_kernel"));
     } else if (partials) {                           // empty shard: contribute zeros to the cross-rank sum
         SD_CUDA(cudaMemsetAsync(partials, 0, (size_t)SD_NSLOT * g * sizeof(double), c->stream));
-    }
-    if (phi->layout) {
-        SD_TRY(sd_blk_permute(phi, dst, 2, 0, 0, 0, 0.0));
-        sd_scratch_release(c);
     }
     if (norm2) {
         SD_TRY(sd_finish_reduce(c, g, 8, 0));
@@ -1638,27 +1653,31 @@ int sd_vec_observables(const sd_vec *psi, double *mags, double *zz) {
     sd_ctx *c = m->ctx;
     SD_ARG(m->L <= 63, "L must be at most 63");
     SD_LOCK(c); SD_TRY(sd_use(c));
-    const double *src = psi->d;
-    if (psi->layout) {                               // block layout: run on a rank-ordered staging copy (not a hot path)
-        double *s0 = nullptr;
-        SD_TRY(sd_scratch(c, 0, sd_vec_logical_bytes(psi) + 16, &s0));
-        SD_TRY(sd_blk_permute(psi, s0, psi->nc, 1, 0, 0, 0.0));
-        src = s0;
+    unsigned nwarps;
+    if (psi->layout) {                               // block layout: states from the element positions (sd_blkv.h)
+        SdBlkParams P = sd_blk_params(m, psi->nc);
+        const uint64_t nkeys = P.key_hi - P.key_lo;
+        const unsigned g = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(nkeys, (uint64_t)c->sm_count * 8));
+        nwarps = g * (256 / 32);
+        SD_TRY(sd_partials_reserve(c, (size_t)nwarps * 128));
+        if (psi->nc == 2) sd_blk_obs_kernel<2><<<g, 256, 0, c->stream>>>(P, psi->d, c->d_partials);
+        else sd_blk_obs_kernel<1><<<g, 256, 0, c->stream>>>(P, psi->d, c->d_partials);
+        SD_TRY(sd_launch_check(c, "sd_blk_obs_kernel"));
+    } else {
+        const unsigned g = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((psi->logical_n + 255) / 256, (uint64_t)c->sm_count * 4));
+        nwarps = g * (256 / 32);
+        SD_TRY(sd_partials_reserve(c, (size_t)nwarps * 128));
+        const uint64_t ls = m->shards.start[c->rank];
+        if (psi->nc == 2) sd_obs_kernel<2><<<g, 256, 0, c->stream>>>(m->L, m->k, c->d_binom, ls, psi->logical_n, psi->d, c->d_partials);
+        else sd_obs_kernel<1><<<g, 256, 0, c->stream>>>(m->L, m->k, c->d_binom, ls, psi->logical_n, psi->d, c->d_partials);
+        SD_TRY(sd_launch_check(c, "sd_obs_kernel"));
     }
-    const unsigned g = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((psi->logical_n + 255) / 256, (uint64_t)c->sm_count * 4));
-    const unsigned nwarps = g * (256 / 32);
-    SD_TRY(sd_partials_reserve(c, (size_t)nwarps * 128));
-    const uint64_t ls = m->shards.start[c->rank];
-    if (psi->nc == 2) sd_obs_kernel<2><<<g, 256, 0, c->stream>>>(m->L, m->k, c->d_binom, ls, psi->logical_n, src, c->d_partials);
-    else sd_obs_kernel<1><<<g, 256, 0, c->stream>>>(m->L, m->k, c->d_binom, ls, psi->logical_n, src, c->d_partials);
-    SD_TRY(sd_launch_check(c, "sd_obs_kernel"));
     sd_obs_reduce_kernel<<<1, 128, 0, c->stream>>>(c->d_partials, nwarps, c->d_scal + SD_OBS_SLOT);
     SD_TRY(sd_launch_check(c, "sd_obs_reduce_kernel"));
     if (c->world > 1)
         { SD_NCCL(g_nccl.AllReduce(c->d_scal + SD_OBS_SLOT, c->d_scal + SD_OBS_SLOT, 128, ncclFloat64_, ncclSum_, c->comm, c->stream)); sd_collective_done(c); }
     double r[128];
     SD_TRY(sd_fetch(c, SD_OBS_SLOT, 128, r));
-    if (psi->layout) sd_scratch_release(c);
     for (int i = 0; i < m->L; ++i) { mags[i] = r[i]; zz[i] = r[64 + i]; }
     return SD_OK;
 }

@@ -25,15 +25,11 @@ struct SdBlkShared {
     SdBlkJs js[SD_BLK_B + 1];
     uint16_t units[(SD_BLK_B + 1) * SD_BLK_MAXUNITS];
     double dmid[1 << SD_BLK_M];  // diagonal of the mid sites, in item order: lanes = consecutive u read consecutive entries
-    // per-launch context
-    SdEpi epi;
-    double *out_local;          // local shard of out, component 0 of stored element 0
-    uint64_t pstart_local;      // stored-element offset of the local shard
-    const SdBlkItem *items;
+    double hs;                   // hscale of the epilogue, resolved once per CTA (SdEpi::hscale_dev)
 };
-// Model constants that are the same for every lane of a warp (mid / tail hop coefficients, tail diagonal, qx) are NOT in
-// shared memory: they are members of the __grid_constant__ kernel parameter P and reach the FP64 pipe as constant-bank
-// operands.  A warp-uniform LDS costs a full 128-byte wavefront of the LSU data pipe, which is this kernel's scarcest
+// Everything that is the same for every lane of a warp and fixed for the launch (mid / tail hop coefficients, tail
+// diagonal, qx, the epilogue's mode / coefficients / pointers, the out pointer) is NOT in shared memory: it is read from
+// the __grid_constant__ kernel parameters P / epi, i.e. from the constant bank.  A warp-uniform LDS costs a full 128-byte wavefront of the LSU data pipe, which is this kernel's scarcest
 // resource (profiles/round2_b_apply_full.txt: 71 % busy, 12 % of it uniform table reads).
 #if defined(__CUDACC__)
 __shared__ SdBlkShared sd_blkl_sh;
@@ -44,17 +40,14 @@ static SdBlkShared sd_blkl_sh;
 #define SD_SH sd_blkl_sh
 #define SD_BLKL_FN inline
 #endif
-// fills the context part of SD_SH (device: one thread, before the CTA barrier; host: the emulation)
-SD_BLKL_FN void sd_blkl_ctx_init(const SdBlkParams &P, double *out_local, const SdEpi &epi) {
-    SD_SH.epi = epi;
-    if (epi.hscale_dev) { SD_SH.epi.hscale = epi.hscale / sqrt(*epi.hscale_dev); SD_SH.epi.hscale_dev = nullptr; }
-    SD_SH.out_local = out_local;
-    SD_SH.pstart_local = P.shards.pstart[P.shards.rank];
-    SD_SH.items = P.items;
+// resolves the epilogue's hscale (device: one thread, before the CTA barrier; host: the emulation)
+SD_BLKL_FN void sd_blkl_ctx_init(const SdEpi &epi) {
+    SD_SH.hs = epi.hscale_dev ? epi.hscale / sqrt(*epi.hscale_dev) : epi.hscale;
 }
 
 template <int NC, int JT, int S0, bool PLAIN>
-SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdBlkHdr &H, const double *tb, uint32_t u, double (&red)[SD_NSLOT]) {
+SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdEpi &E, double *out_local, const SdBlkHdr &H, const double *tb, uint32_t u,
+                             double (&red)[SD_NSLOT]) {
     constexpr int T = SD_BLK_T, M = SD_BLK_M;
     constexpr int NT = sd_cbinom(T, JT);
     constexpr int NO = NC == 1 ? (NT + 1) / 2 : NT;                  // slots of the whole block
@@ -120,7 +113,7 @@ SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdBlkHdr &H, const doub
 #undef SD_LEAN_LOAD
 #undef SD_LEAN_FMA
     // ---- own block: diagonal + tail-internal hops (registers, compile-time permutation)
-    const uint4 it = sd_blk_ld_item(SD_SH.items + cls.item_off + u);     // x,y,z = nb[12]; w = c | u2x << 16
+    const uint4 it = sd_blk_ld_item(P.items + cls.item_off + u);     // x,y,z = nb[12]; w = c | u2x << 16
     const unsigned cmid = it.w & ((1u << M) - 1u);
     const bool clast = (cmid >> (M - 1)) & 1u;
     sd_blk_tail<NC, JT, E0, NE, EC>(acc, tb + off0, ss, u, P.Jtail, P.dtail, H.dP[c0 ? 1 : 0] + SD_SH.dmid[cls.item_off + u],
@@ -187,8 +180,8 @@ SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdBlkHdr &H, const doub
 #undef SD_LEAN_CROSS
     }
     // ---- epilogue + store
-    const uint64_t ld0 = (H.base - SD_SH.pstart_local) * NC;              // doubles from the start of the local shard
-    double *ob = SD_SH.out_local + ld0;
+    const uint64_t ld0 = (H.base - P.shards.pstart[P.shards.rank]) * NC;  // doubles from the start of the local shard
+    double *ob = out_local + ld0;
     if (PLAIN) {
 #pragma unroll
         for (int s = 0; s < EC; ++s) {
@@ -196,14 +189,14 @@ SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdBlkHdr &H, const doub
             else sd_blk_stg(ob + o[s], acc[s]);
         }
     } else {
-        const SdEpi &E = SD_SH.epi;
+        const double hs = SD_SH.hs;
 #pragma unroll
         for (int s = 0; s < EC; ++s) {
             const uint64_t ld = ld0 + o[s];
             if (HALF && s == EC - 1) {
                 SdVal<1> hh, pp;
                 hh.c[0] = acc[s].x; pp.c[0] = tb[o[s]];
-                const SdVal<1> r0 = sd_epilogue<1>(E, hh, pp, ld, red);
+                const SdVal<1> r0 = sd_epilogue_hs<1>(E, hs, hh, pp, ld, red);
                 ob[o[s]] = r0.c[0];
                 continue;
             }
@@ -212,14 +205,14 @@ SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdBlkHdr &H, const doub
             if (NC == 2) {
                 SdVal<2> hh, pp;
                 hh.c[0] = acc[s].x; hh.c[1] = acc[s].y; pp.c[0] = p.x; pp.c[1] = p.y;
-                const SdVal<2> rr = sd_epilogue<2>(E, hh, pp, ld / 2, red);
+                const SdVal<2> rr = sd_epilogue_hs<2>(E, hs, hh, pp, ld / 2, red);
                 r = make_double2(rr.c[0], rr.c[1]);
             } else {
                 SdVal<1> hh, pp;
                 hh.c[0] = acc[s].x; pp.c[0] = p.x;
-                const SdVal<1> r0 = sd_epilogue<1>(E, hh, pp, ld, red);
+                const SdVal<1> r0 = sd_epilogue_hs<1>(E, hs, hh, pp, ld, red);
                 hh.c[0] = acc[s].y; pp.c[0] = p.y;
-                const SdVal<1> r1 = sd_epilogue<1>(E, hh, pp, ld + 1, red);
+                const SdVal<1> r1 = sd_epilogue_hs<1>(E, hs, hh, pp, ld + 1, red);
                 r = make_double2(r0.c[0], r1.c[0]);
             }
             *(double2 *)(ob + o[s]) = r;
@@ -227,21 +220,21 @@ SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdBlkHdr &H, const doub
     }
 }
 template <int NC, bool PLAIN>
-SD_BLKL_FN void sd_blkl_dispatch(const SdBlkParams &P, const SdBlkHdr &H, const double *tb, unsigned code, uint32_t u,
+SD_BLKL_FN void sd_blkl_dispatch(const SdBlkParams &P, const SdEpi &E, double *out_local, const SdBlkHdr &H, const double *tb, unsigned code, uint32_t u,
                                 double (&red)[SD_NSLOT]) {
     const int jt = (int)(code >> 12);
     const bool hi = ((code >> 8) & 0xFu) != 0;                       // c128, classes of 10: second chunk of five
     switch (jt) {
-        case 0: sd_blkl_item<NC, 0, 0, PLAIN>(P, H, tb, u, red); break;
-        case 1: sd_blkl_item<NC, 1, 0, PLAIN>(P, H, tb, u, red); break;
+        case 0: sd_blkl_item<NC, 0, 0, PLAIN>(P, E, out_local, H, tb, u, red); break;
+        case 1: sd_blkl_item<NC, 1, 0, PLAIN>(P, E, out_local, H, tb, u, red); break;
         case 2:
-            if constexpr (NC == 2) { if (hi) { sd_blkl_item<NC, 2, 5, PLAIN>(P, H, tb, u, red); break; } }
-            sd_blkl_item<NC, 2, 0, PLAIN>(P, H, tb, u, red); break;
+            if constexpr (NC == 2) { if (hi) { sd_blkl_item<NC, 2, 5, PLAIN>(P, E, out_local, H, tb, u, red); break; } }
+            sd_blkl_item<NC, 2, 0, PLAIN>(P, E, out_local, H, tb, u, red); break;
         case 3:
-            if constexpr (NC == 2) { if (hi) { sd_blkl_item<NC, 3, 5, PLAIN>(P, H, tb, u, red); break; } }
-            sd_blkl_item<NC, 3, 0, PLAIN>(P, H, tb, u, red); break;
-        case 4: sd_blkl_item<NC, 4, 0, PLAIN>(P, H, tb, u, red); break;
-        default: sd_blkl_item<NC, 5, 0, PLAIN>(P, H, tb, u, red); break;
+            if constexpr (NC == 2) { if (hi) { sd_blkl_item<NC, 3, 5, PLAIN>(P, E, out_local, H, tb, u, red); break; } }
+            sd_blkl_item<NC, 3, 0, PLAIN>(P, E, out_local, H, tb, u, red); break;
+        case 4: sd_blkl_item<NC, 4, 0, PLAIN>(P, E, out_local, H, tb, u, red); break;
+        default: sd_blkl_item<NC, 5, 0, PLAIN>(P, E, out_local, H, tb, u, red); break;
     }
 }
 
@@ -266,7 +259,7 @@ sd_blkl_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constan
         SD_SH.units[i] = P.units[(NC - 1) * (SD_BLK_B + 1) * SD_BLK_MAXUNITS + i];
     for (int i = (int)tid; i < (1 << SD_BLK_M); i += NTHR) SD_SH.dmid[i] = P.dmid[i];
     if (tid == 0) {
-        sd_blkl_ctx_init(P, out_local, epi);
+        sd_blkl_ctx_init(epi);
         for (unsigned b = 0; b < nbuf; ++b) { sd_mbar_init(&SD_SH.full[b], 1); sd_mbar_init(&SD_SH.empty[b], NCONS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -294,7 +287,7 @@ sd_blkl_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constan
                 const unsigned code = SD_SH.units[H.js * SD_BLK_MAXUNITS + un];
                 const uint32_t u = (code & 0xFFu) * 32u + lane;      // the lane's mid configuration
                 double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
-                sd_blkl_dispatch<NC, PLAIN>(P, H, tb, code, u, red);
+                sd_blkl_dispatch<NC, PLAIN>(P, epi, out_local, H, tb, code, u, red);
                 if (!PLAIN && slotmask) sd_blk_item_reduce(H, epi, slotmask, un, nunits, red, lane);
             }
             __syncwarp();

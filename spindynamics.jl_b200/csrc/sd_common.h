@@ -165,14 +165,13 @@ struct SdVal {
     double c[NC];
 };
 
-// Applies the epilogue to one element.  `h` is H psi (before hscale), `p` is
+// Applies the epilogue to one element.  `h` is H psi (before hscale `hs`), `p` is
 // psi at the same index, `li` the local element index.  Accumulates the
 // requested reductions into red[SD_NSLOT].
 template <int NC>
-SD_HD SdVal<NC> sd_epilogue(const SdEpi &e, SdVal<NC> h, SdVal<NC> p, uint64_t li,
-                            double (&red)[SD_NSLOT]) {
+SD_HD SdVal<NC> sd_epilogue_hs(const SdEpi &e, double hs, SdVal<NC> h, SdVal<NC> p, uint64_t li,
+                               double (&red)[SD_NSLOT]) {
     SdVal<NC> o;
-    const double hs = e.hscale_dev ? e.hscale / sqrt(*e.hscale_dev) : e.hscale;   // (the block kernel resolves the pointer once per CTA)
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
         double v = hs * h.c[c];
@@ -207,4 +206,9 @@ SD_HD SdVal<NC> sd_epilogue(const SdEpi &e, SdVal<NC> h, SdVal<NC> p, uint64_t l
         for (int c = 0; c < NC; ++c) red[3] += o.c[c] * o.c[c];
     }
     return o;
+}
+// hscale resolved per call (tiled / generic kernels); the block kernel resolves it once per CTA and calls sd_epilogue_hs
+template <int NC>
+SD_HD SdVal<NC> sd_epilogue(const SdEpi &e, SdVal<NC> h, SdVal<NC> p, uint64_t li, double (&red)[SD_NSLOT]) {
+    return sd_epilogue_hs<NC>(e, e.hscale_dev ? e.hscale / sqrt(*e.hscale_dev) : e.hscale, h, p, li, red);
 }

@@ -40,7 +40,7 @@ void run_tiles(const SdBlkHost &bh, const SdBlkParams &P, const SdVecView &psi, 
     // tables + context of the kernel's static shared-memory block SD_SH
     std::memcpy(SD_SH.js, bh.js.data(), sizeof(SdBlkJs) * (SD_BLK_B + 1));
     std::memcpy(SD_SH.dmid, bh.dmid.data(), sizeof(double) << SD_BLK_M);
-    sd_blkl_ctx_init(P, out_local, epi);
+    sd_blkl_ctx_init(epi);
     for (uint64_t key = P.key_lo; key < P.key_hi; ++key) {
         const uint64_t Pb = sd_blk_key_prefix(key, P.A);
         const int js = P.k - SD_POPC64(Pb);
@@ -63,7 +63,7 @@ void run_tiles(const SdBlkHost &bh, const SdBlkParams &P, const SdVecView &psi, 
             for (unsigned lane = 0; lane < 32; ++lane) {
                 const uint32_t u = (code & 0xFFu) * 32u + lane;
                 double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
-                sd_blkl_dispatch<NC, PLAIN>(P, H, tile.p, code, u, red);
+                sd_blkl_dispatch<NC, PLAIN>(P, epi, out_local, H, tile.p, code, u, red);
                 for (int s = 0; s < SD_NSLOT; ++s) red_total[s] += red[s];
             }
         }
