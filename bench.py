@@ -354,7 +354,7 @@ def main():
 
     # end to end through the host-buffer entry points (pinned host memory)
     e2e = None
-    if not args.no_e2e and 2 * count * esz > (24 << 30):
+    if not args.no_e2e and 2 * count * esz > (10 << 30):
         e2e = {"skipped": f"2 x {count * esz / 1e9:.1f} GB of pinned host memory per rank"}
     elif not args.no_e2e:
         hin = sd.PinnedBuffer(count, dtype)

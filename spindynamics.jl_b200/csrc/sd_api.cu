@@ -200,6 +200,7 @@ struct SdBlkDev {
     int nbuf[2] = {0, 0};
     size_t smem[2] = {0, 0};
     int qfar[2] = {0, 0};
+    int nofence = 0;                // A/B knob (SD_BLK_NOFENCE)
     int threads = 640;              // CTA size of sd_blkl_apply_kernel (SD_BLKL_THREADS = 512 | 640 | 768, read once at model creation)
     uint32_t *d_order = nullptr;    // breadth-first tile order of this rank's shard (vectors larger than the L2)
     uint32_t norder = 0;
@@ -537,6 +538,7 @@ static int sd_blk_setup(sd_model *m) {
     for (size_t i = 0; i < m->hop_a.size(); ++i) Jhop[m->hop_a[i]] += m->hop_J[i];
     for (size_t i = 0; i < m->zz_a.size(); ++i) Jz[m->zz_a[i]] += m->zz_J[i];
     if (!sd_blk_build(L, m->k, Jhop.data(), Jz.data(), m->field.data(), b.host)) return SD_OK;
+    b.nofence = sd_env_int("SD_BLK_NOFENCE", 0);
     b.threads = sd_env_int("SD_BLKL_THREADS", 640);
     if (b.threads != 512 && b.threads != 768) b.threads = 640;
     for (int w = 0; w < 2; ++w) {
@@ -1461,6 +1463,7 @@ static int sd_apply_impl(sd_model *m, sd_vec *out, const sd_vec *psi, SdEpi epi,
         }
         epi.partials = c->d_partials;
         epi.nparts = (unsigned)nkeys;
+        epi.dbg_nofence = m->blk.nofence;
         const bool plain = epi.mode == SD_EPI_PLAIN && epi.red == 0 && !epi.acc && epi.hscale == 1.0 && !epi.hscale_dev;
         SD_TRY(sd_blk_launch_range(m, nc, P, psi->view, out->d, epi, plain));
         if (slotmask) SD_TRY(sd_finish_reduce(c, (unsigned)nkeys, slotmask, slot_out));

@@ -464,10 +464,10 @@ __device__ __forceinline__ void sd_blk_item_reduce(SdBlkHdr &H, const SdEpi &epi
         if (lane == 0) H.usum[s][un] = w;
     }
     if (lane == 0) {
-        __threadfence_block();
+        if (!epi.dbg_nofence) __threadfence_block();
         const unsigned done = atomicAdd(&H.done_units, 1u);
         if (done + 1 == nunits) {                              // last item of the tile: ordered sum
-            __threadfence_block();
+            if (!epi.dbg_nofence) __threadfence_block();
             for (int s = 0; s < SD_NSLOT; ++s) {
                 if (!((slotmask >> s) & 1)) continue;
                 double t = 0.0;

@@ -197,7 +197,7 @@ SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdEpi &E, double *out_l
                 SdVal<1> hh, pp;
                 hh.c[0] = acc[s].x; pp.c[0] = tb[o[s]];
                 const SdVal<1> r0 = sd_epilogue_hs<1>(E, hs, hh, pp, ld, red);
-                ob[o[s]] = r0.c[0];
+                sd_blk_stg_half(ob + o[s], r0.c[0]);
                 continue;
             }
             const double2 p = *(const double2 *)(tb + o[s]);
@@ -215,7 +215,7 @@ SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdEpi &E, double *out_l
                 const SdVal<1> r1 = sd_epilogue_hs<1>(E, hs, hh, pp, ld + 1, red);
                 r = make_double2(r0.c[0], r1.c[0]);
             }
-            *(double2 *)(ob + o[s]) = r;
+            sd_blk_stg(ob + o[s], r);                                 // evict-first like the plain path: out must not displace psi in L2
         }
     }
 }
