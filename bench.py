@@ -203,6 +203,75 @@ def sampled_row_parity(model, out, scale, first, count, nrows, rank, cplx=False)
     return {"rows": int(len(rows)), "max_rel_err": worst, "what": "sampled rows of H.psi vs oracle row formula"}
 
 
+def run_configs(args):
+    """--configs-only: BASELINE.json configs 1 and 3 end to end through the public API on one GPU, with the CPU port of
+    the same calls timed in the same run (config 3: a bounded CPU sample).  Prints {"configs": {...}}."""
+    import spindyn as sd
+    from oracle import oracle as orc
+    orc.lib().orc_set_num_threads(host_threads())
+    ctx = sd.Context(0)
+    sd.set_default_context(ctx)
+    res = {}
+    # ---- config 1: XXZChain L=16 nup=8, groundstate(lanc_m=100) + lanczos_sqw(q = momenta, w = range(0,5,100), lanc_m=100, eta=0.05)
+    L = 16
+    rng = np.random.default_rng(SEED)
+    wr = np.linspace(0.0, 5.0, 100)
+
+    def config1(lib_, model):
+        v0 = rng.standard_normal(len(model) if hasattr(model, "__len__") else model.dim)
+        E0, psi = lib_.groundstate(model, lanc_m=100, v0=v0)
+        S = lib_.lanczos_sqw(psi, model, lib_.momenta(model), wr, lanc_m=100, eta=0.05)
+        return E0, np.asarray(S)
+
+    m = sd.XXZChain(L, Jxy=1.0, Jz=1.0, hz=0.0, nup=L // 2, ctx=ctx)
+    rng = np.random.default_rng(SEED)
+    config1(sd, m)                                              # warm-up: module load, table uploads
+    ctx.sync()
+    l0 = ctx.launch_count()
+    rng = np.random.default_rng(SEED)
+    t0 = time.perf_counter()
+    E_g, S_g = config1(sd, m)
+    ctx.sync()
+    t_gpu = time.perf_counter() - t0
+    launches = ctx.launch_count() - l0
+    om = orc.XXZChain(L, Jxy=1.0, Jz=1.0, hz=0.0, nup=L // 2)
+    rng = np.random.default_rng(SEED)
+    t0 = time.perf_counter()
+    E_c, S_c = config1(orc, om)
+    t_cpu = time.perf_counter() - t0
+    res["config1"] = {"what": "XXZChain L=16 nup=8: groundstate(lanc_m=100) + lanczos_sqw(16 momenta, 100 frequencies, lanc_m=100, eta=0.05)",
+                      "gpu_s": t_gpu, "cpu_port_s": t_cpu, "cpu_threads": host_threads(), "gpu_launches": int(launches),
+                      "E0_gpu": float(E_g), "E0_cpu": float(E_c), "E0_abs_diff": abs(float(E_g) - float(E_c)),
+                      "Sqw_rel_l2_diff": float(np.linalg.norm(S_g - S_c) / max(np.linalg.norm(S_c), 1e-300)),
+                      "note": "S(q,w) from 100 unreorthogonalised Lanczos steps is ill-conditioned in the last Ritz values: see tests/test_gpu_sqw_tolerance.py for the tolerance"}
+    del m
+    # ---- config 3: XXZChain L=28 nup=14, KPM S(q,w) with 1024 Chebyshev moments (fused moment dots)
+    L, M = 28, 1024
+    m = sd.XXZChain(L, Jxy=1.0, Jz=1.0, hz=0.0, nup=L // 2, ctx=ctx)
+    psi0 = m.vector(np.float64).fill_seeded(SEED, 1.0 / np.sqrt(m.dim / 3.0))
+    Eb = (-0.4432 * L - 0.5, (L - 1) / 4 + 0.25)
+    a, b = (Eb[1] - Eb[0]) / (2 * 0.99), (Eb[1] + Eb[0]) / 2
+    q = np.array([np.pi])
+    w3 = np.linspace(0.0, 4.0, 200)
+    sd.kpm_sqw(psi0, m, q, w3, a=a, b=b, kpm_m=8)               # warm-up
+    ctx.sync()
+    t0 = time.perf_counter()
+    S3 = sd.kpm_sqw(psi0, m, q, w3, a=a, b=b, kpm_m=M)
+    ctx.sync()
+    t_gpu3 = time.perf_counter() - t0
+    om = orc.XXZChain(L, Jxy=1.0, Jz=1.0, hz=0.0, nup=L // 2)
+    phi = orc.Sz_q_vector(om, orc.fill_seeded(len(om), SEED) * (1.0 / np.sqrt(len(om) / 3.0)), float(np.pi))
+    Mc = 5
+    t0 = time.perf_counter()
+    orc.compute_chebyshev_moments(orc.apply_H_, phi, Mc, a, b, om)
+    t_cpu3 = time.perf_counter() - t0
+    res["config3"] = {"what": f"XXZChain L=28 nup=14: kpm_sqw, one momentum (q = pi), {M} Chebyshev moments, fused moment dots, c128",
+                      "gpu_s": t_gpu3, "gpu_ms_per_moment": t_gpu3 * 1e3 / (M - 1),
+                      "cpu_port_ms_per_moment": t_cpu3 * 1e3 / (Mc - 1), "cpu_sample": f"{Mc} moments of the same recurrence on {host_threads()} threads",
+                      "cpu_port_s_extrapolated": t_cpu3 / (Mc - 1) * (M - 1), "sum_S_dw": float(np.sum(S3) * (w3[1] - w3[0]))}
+    print(json.dumps({"configs": res}), flush=True)
+
+
 def run_solve(args):
     """--solve-only: end-to-end solve on one GPU, everything device-resident; prints {"solve": {...}}."""
     import spindyn as sd
@@ -274,6 +343,8 @@ def main():
     ap.add_argument("--no-solve", action="store_true", help="skip the end-to-end Lanczos solve leg")
     ap.add_argument("--solve-m", type=int, default=30)
     ap.add_argument("--solve-only", action="store_true", help="(internal) run only the solve leg and print {\"solve\": ...}")
+    ap.add_argument("--configs-only", action="store_true", help="(internal) BASELINE.json configs 1 and 3 end to end, GPU vs CPU port; prints {\"configs\": ...}")
+    ap.add_argument("--no-configs", action="store_true", help="skip the config 1 / config 3 legs")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--path", default=None, choices=[None, "block", "tiled", "generic"])
     args = ap.parse_args()
@@ -281,6 +352,8 @@ def main():
         return run_reference(args)
     if args.solve_only:
         return run_solve(args)
+    if args.configs_only:
+        return run_configs(args)
 
     import spindyn as sd
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -354,6 +427,7 @@ def main():
 
     # end to end through the host-buffer entry points (pinned host memory)
     e2e = None
+    checksum = None
     if not args.no_e2e and 2 * count * esz > (10 << 30):
         e2e = {"skipped": f"2 x {count * esz / 1e9:.1f} GB of pinned host memory per rank"}
     elif not args.no_e2e:
@@ -409,6 +483,15 @@ def main():
             solve = json.loads(last[-1])["solve"] if (cp.returncode == 0 and last) else {"error": (cp.stderr or cp.stdout)[-300:]}
         except Exception as exc:                                   # noqa: BLE001
             solve = {"error": repr(exc)[:300]}
+    configs = None
+    if not args.no_configs and not args.no_cpu and not args.no_e2e and args.dtype == "f64" and world == 1:
+        import subprocess
+        try:
+            cp = subprocess.run([sys.executable, os.path.abspath(__file__), "--configs-only"], capture_output=True, text=True, timeout=300)
+            last = [ln for ln in cp.stdout.splitlines() if ln.startswith("{")]
+            configs = json.loads(last[-1])["configs"] if (cp.returncode == 0 and last) else {"error": (cp.stderr or cp.stdout)[-300:]}
+        except Exception as exc:                                   # noqa: BLE001
+            configs = {"error": repr(exc)[:300]}
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -444,7 +527,7 @@ def main():
                            "kernel_path": model.info["kernel_path"], "tile_sites": model.info["tile_sites"],
                            **({"env_knobs": knobs} if knobs else {})},
                 "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-                "parity": parity, "cpu_baseline": cpu, "checksum": checksum, "solve": solve}
+                "parity": parity, "cpu_baseline": cpu, "checksum": checksum, "solve": solve, "configs": configs}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

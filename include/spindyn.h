@@ -181,6 +181,10 @@ int sd_cheb_step(sd_model *model, sd_vec *vnext, const sd_vec *v, const sd_vec *
 /* Sz_q_vector: phi = L^-1/2 sum_r e^{iqr} s_r psi0 (phi C128, psi0 F64 or C128),
  * *norm2 = ||phi||^2 if non-NULL               Hamiltonian.jl:307-337 */
 int sd_szq(sd_model *model, sd_vec *phi, const sd_vec *psi0, double q, double *norm2);
+/* phi (SD_C128) = (sum_r w[r] s_r(state)) * ComplexF64(psi0) with complex per-site weights w[L] (site r = bit r, 0-based):
+ * the single-site S^z_i that TimeEvolution/KPM.jl:197-213 builds with create_spin_operator(i, :z) is w = delta_{r,i};
+ * Sz_q_vector is w[r] = e^{iqr} / sqrt(L).  norm2 (optional) receives ||phi||^2. */
+int sd_apply_sz_weights(sd_model *model, sd_vec *phi, const sd_vec *psi0, const sd_complex *w, double *norm2);
 /* Observables.jl:14-109 on a device-resident vector, summed over ranks:
  *   mags[i] = sum |psi|^2 s_i                      magnetization_per_site (:14-37)
  *   zz[r]   = sum_i sum |psi|^2 s_i s_{(i+r) mod L}  the cyclic diagonals of SzSz (:48-93); the caller forms

@@ -27,8 +27,7 @@
 #include "sd_obs.h"
 #include "sd_blkv.h"
 #include "sd_bdot.cuh"
-#include "sd_halo_host.h"
-#include <cuda.h>          // driver-API types only; the functions are resolved with dlopen (virtual memory management of the halo mirror)
+#include "sd_shard_host.h"
 
 #define SD_VERSION 100
 
@@ -109,46 +108,6 @@ static int sd_nccl_load() {
 #define SD_NSCAL 4096
 #define SD_HIST 4096                  // d_scal[SD_HIST + 8 j ..]: reductions of Lanczos step j (kept on the device, fetched in blocks)
 #define SD_HIST_MAX 4096             // steps
-// ----------------------------------------------------------------- CUDA driver API (dlopen, only for SD_HALO=1)
-struct SdDrv {
-    void *h = nullptr;
-    CUresult (*MemGetAllocationGranularity)(size_t *, const CUmemAllocationProp *, CUmemAllocationGranularity_flags) = nullptr;
-    CUresult (*MemAddressReserve)(CUdeviceptr *, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
-    CUresult (*MemAddressFree)(CUdeviceptr, size_t) = nullptr;
-    CUresult (*MemCreate)(CUmemGenericAllocationHandle *, size_t, const CUmemAllocationProp *, unsigned long long) = nullptr;
-    CUresult (*MemRelease)(CUmemGenericAllocationHandle) = nullptr;
-    CUresult (*MemMap)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
-    CUresult (*MemUnmap)(CUdeviceptr, size_t) = nullptr;
-    CUresult (*MemSetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc *, size_t) = nullptr;
-};
-static SdDrv g_drv;
-static int sd_drv_load() {
-    std::lock_guard<std::mutex> lk(g_nccl_mu);
-    if (g_drv.h) return SD_OK;
-    void *h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
-    if (!h) return sd_fail(SD_ERR_CUDA, "cannot dlopen libcuda.so.1: %s", dlerror());
-#define SD_SYM(field, name)                                                   \
-    *(void **)(&g_drv.field) = dlsym(h, name);                                \
-    if (!g_drv.field) return sd_fail(SD_ERR_CUDA, "libcuda lacks %s", name);
-    SD_SYM(MemGetAllocationGranularity, "cuMemGetAllocationGranularity")
-    SD_SYM(MemAddressReserve, "cuMemAddressReserve")
-    SD_SYM(MemAddressFree, "cuMemAddressFree")
-    SD_SYM(MemCreate, "cuMemCreate")
-    SD_SYM(MemRelease, "cuMemRelease")
-    SD_SYM(MemMap, "cuMemMap")
-    SD_SYM(MemUnmap, "cuMemUnmap")
-    SD_SYM(MemSetAccess, "cuMemSetAccess")
-#undef SD_SYM
-    g_drv.h = h;
-    return SD_OK;
-}
-#define SD_DRV(call)                                                                        \
-    do {                                                                                    \
-        CUresult e_ = (call);                                                               \
-        if (e_ != CUDA_SUCCESS)                                                             \
-            return sd_fail(e_ == CUDA_ERROR_OUT_OF_MEMORY ? SD_ERR_NOMEM : SD_ERR_CUDA, "%s failed: CUresult %d (%s:%d)", #call, (int)e_, __FILE__, __LINE__); \
-    } while (0)
-
 struct sd_ctx {
     // Threading contract: calls on one context serialise.  Every entry point that touches the context's
     // stream or scratch state takes this lock (recursive: entry points call each other), so the reference's
@@ -204,22 +163,6 @@ struct SdBlkDev {
     int threads = 640;              // CTA size of sd_blkl_apply_kernel (SD_BLKL_THREADS = 512 | 640 | 768, read once at model creation)
     uint32_t *d_order = nullptr;    // breadth-first tile order of this rank's shard (vectors larger than the L2)
     uint32_t norder = 0;
-    // halo mirror of sharded applies (SD_HALO=1, sd_halo_host.h): chunked copy-engine prefetch of the peer ranges the
-    // tile headers point at into a sparse local mapping with the peers' own offsets
-    struct Halo {
-        bool on = false;
-        SdHaloPlan plan;
-        struct Mirror {
-            bool built = false;
-            CUdeviceptr va[SD_MAX_WORLD] = {0};
-            size_t va_size[SD_MAX_WORLD] = {0};
-            struct Map { CUdeviceptr at; size_t size; CUmemGenericAllocationHandle h; };
-            std::vector<Map> maps;
-        } mir[2];                   // [0]: f64 byte offsets, [1]: c128
-        cudaStream_t copy_stream = nullptr;
-        cudaEvent_t ev_ready = nullptr;
-        std::vector<cudaEvent_t> ev;
-    } halo;
 };
 
 struct SdTileDev {
@@ -576,8 +519,6 @@ static SdBlkParams sd_blk_params(const sd_model *m, int nc) {
     return P;
 }
 
-static int sd_halo_setup(sd_model *m);
-static void sd_halo_free(sd_model *m);
 
 int sd_model_create(sd_ctx *ctx, int L, int nup, const sd_bond *hop, int nhop, const sd_bond *zz, int nzz,
                     const double *field, sd_model **model) {
@@ -674,12 +615,14 @@ int sd_model_create(sd_ctx *ctx, int L, int nup, const sd_bond *hop, int nhop, c
     uint64_t bounds[SD_MAX_WORLD + 1];
     if (m->tile_capable) {
         sd_tile_shard_bounds(m->tile[0].host, ctx->world, bounds, m->tile[0].keys);
-        if (m->blk.ok && ctx->world > 1 && sd_env_int("SD_SHARD_BALANCE", 0)) {
-            // experimental: shards weighted by their remote volume (sd_halo_balance; meant for SD_HALO=1, where transfers
-            // overlap compute).  SD_SHARD_REMOTE_COST (percent): NVLink time per remote element / compute time per local one.
+        if (m->blk.ok && ctx->world > 2 && sd_env_int("SD_SHARD_BALANCE", 1)) {
+            // Shards weighted by their remote volume (sd_shard_balance): with equal rank ranges the ranks whose top prefix
+            // bits are 101 / 010 gather 2.5 shards' worth over NVLink, the edge ranks 0.5; measured at L = 32 on 8 GPUs:
+            // 2.62 ms per apply with equal shards, 1.81 ms weighted (profiles/round2_e_8gpu.txt).  SD_SHARD_REMOTE_COST
+            // (percent): NVLink time per remote element / compute time per local one.  SD_SHARD_BALANCE=0: equal shards.
             double cost[2] = {0.0, 0.0};
             uint64_t wb[SD_MAX_WORLD + 1], wk[SD_MAX_WORLD + 1];
-            if (sd_halo_balance(m->blk.host, m->tile[0].host, ctx->world, m->blk.qfar[0], sd_env_int("SD_SHARD_REMOTE_COST", 70) / 100.0,
+            if (sd_shard_balance(m->blk.host, m->tile[0].host, ctx->world, m->blk.qfar[0], sd_env_int("SD_SHARD_REMOTE_COST", 130) / 100.0,
                                 std::max(1, std::min(20, sd_env_int("SD_SHARD_BALANCE_ITERS", 6))), wb, wk, cost)) {
                 for (int g = 0; g <= ctx->world; ++g) { bounds[g] = wb[g]; m->tile[0].keys[g] = wk[g]; }
             }
@@ -708,10 +651,6 @@ int sd_model_create(sd_ctx *ctx, int L, int nup, const sd_bond *hop, int nhop, c
             m->blk.norder = (uint32_t)ord.size();
         }
     }
-    if (m->blk.ok && ctx->world > 1 && sd_env_int("SD_HALO", 0)) {   // experimental: halo mirror for sharded applies
-        int rc = sd_halo_setup(m);
-        if (rc != SD_OK) { sd_model_free(m); return rc; }
-    }
     *model = m;
     return SD_OK;
 }
@@ -733,7 +672,6 @@ int sd_model_free(sd_model *m) {
         SdTileDev &t = m->tile[w];
         cudaFree(t.d_perm); cudaFree(t.d_items); cudaFree(t.d_binomM);
     }
-    if (m->blk.halo.on || m->blk.halo.copy_stream) sd_halo_free(m);
     cudaFree(m->blk.d_order);
     cudaFree(m->blk.d_W); cudaFree(m->blk.d_js); cudaFree(m->blk.d_units); cudaFree(m->blk.d_items); cudaFree(m->blk.d_dmid);
     delete m;
@@ -1287,79 +1225,6 @@ static int sd_empty_shard_reduce(sd_ctx *c, int slotmask, int slot_out) {
     }
     return SD_OK;
 }
-// ----------------------------------------------------------------- halo mirror (SD_HALO=1; sd_halo_host.h)
-static int sd_halo_setup(sd_model *m) {
-    sd_ctx *c = m->ctx;
-    SdBlkDev::Halo &H = m->blk.halo;
-    H.on = false;
-    if (c->world <= 1 || !m->blk.ok) return SD_OK;
-    SdBlkParams P = sd_blk_params(m, 1);
-    const SdBlkHost &bh = m->blk.host;
-    P.W = bh.W.data(); P.js = bh.js.data(); P.units = bh.units.data(); P.items = bh.items.data(); P.dmid = bh.dmid.data();
-    P.order = nullptr; P.norder = 0;
-    const int nchunks = std::max(1, std::min(64, sd_env_int("SD_HALO_CHUNKS", 8)));
-    if (!sd_halo_plan(bh, P, nchunks, m->blk.qfar[0], H.plan))
-        return sd_fail(SD_ERR_UNSUPPORTED, "internal: halo plan failed (a partner tile straddles two shards)");
-    SD_TRY(sd_drv_load());
-    SD_CUDA(cudaStreamCreateWithFlags(&H.copy_stream, cudaStreamNonBlocking));
-    SD_CUDA(cudaEventCreateWithFlags(&H.ev_ready, cudaEventDisableTiming));
-    H.ev.resize(nchunks);
-    for (cudaEvent_t &e : H.ev) SD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    H.on = true;
-    return SD_OK;
-}
-// Sparse local mapping of the peer shards for vectors of nc components: one virtual range per peer as large as the
-// peer's shard, physical memory only under the ranges the plan needs (rounded out to the allocation granularity).
-static int sd_halo_mirror(sd_model *m, int nc) {
-    sd_ctx *c = m->ctx;
-    SdBlkDev::Halo &H = m->blk.halo;
-    SdBlkDev::Halo::Mirror &M = H.mir[nc - 1];
-    if (M.built) return SD_OK;
-    CUmemAllocationProp prop;
-    memset(&prop, 0, sizeof(prop));
-    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
-    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
-    prop.location.id = c->device;
-    size_t gran = 0;
-    SD_DRV(g_drv.MemGetAllocationGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM));
-    if (gran == 0) gran = (size_t)2 << 20;
-    CUmemAccessDesc acc;
-    memset(&acc, 0, sizeof(acc));
-    acc.location = prop.location;
-    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
-    const size_t esz = (size_t)nc * sizeof(double);
-    for (int g = 0; g < c->world; ++g) {
-        if (g == c->rank || H.plan.need[g].empty()) continue;
-        size_t vsz = 0;
-        std::vector<std::pair<uint64_t, uint64_t>> runs;               // byte ranges, granularity aligned (sd_halo_mirror_runs)
-        sd_halo_mirror_runs(H.plan, m->blk.pstart, g, esz, gran, &vsz, runs);
-        SD_DRV(g_drv.MemAddressReserve(&M.va[g], vsz, gran, 0, 0));
-        M.va_size[g] = vsz;
-        for (auto [b0, b1] : runs) {
-            CUmemGenericAllocationHandle h;
-            SD_DRV(g_drv.MemCreate(&h, (size_t)(b1 - b0), &prop, 0));
-            M.maps.push_back({M.va[g] + b0, (size_t)(b1 - b0), h});
-            SD_DRV(g_drv.MemMap(M.va[g] + b0, (size_t)(b1 - b0), 0, h, 0));
-            SD_DRV(g_drv.MemSetAccess(M.va[g] + b0, (size_t)(b1 - b0), &acc, 1));
-        }
-    }
-    M.built = true;
-    return SD_OK;
-}
-static void sd_halo_free(sd_model *m) {
-    SdBlkDev::Halo &H = m->blk.halo;
-    for (int w = 0; w < 2; ++w) {
-        for (auto &mp : H.mir[w].maps) { g_drv.MemUnmap(mp.at, mp.size); g_drv.MemRelease(mp.h); }
-        for (int g = 0; g < SD_MAX_WORLD; ++g)
-            if (H.mir[w].va[g]) g_drv.MemAddressFree(H.mir[w].va[g], H.mir[w].va_size[g]);
-        H.mir[w] = SdBlkDev::Halo::Mirror();
-    }
-    for (cudaEvent_t e : H.ev) cudaEventDestroy(e);
-    H.ev.clear();
-    if (H.ev_ready) cudaEventDestroy(H.ev_ready);
-    if (H.copy_stream) cudaStreamDestroy(H.copy_stream);
-    H.ev_ready = nullptr; H.copy_stream = nullptr; H.on = false;
-}
 // one launch of the block-layout apply over the tile keys [P.key_lo, P.key_hi) (or P.order)
 static int sd_blk_launch_range(sd_model *m, int nc, const SdBlkParams &P, const SdVecView &view, double *out_local,
                                const SdEpi &epi, bool plain) {
@@ -1388,54 +1253,6 @@ static int sd_blk_launch_range(sd_model *m, int nc, const SdBlkParams &P, const 
 #undef SD_HL
     return sd_launch_check(c, "sd_blkl_apply_kernel");
 }
-// Sharded block-layout apply through the halo mirror: the copy engines bring the peer ranges of chunk j into the
-// mirror while the kernel of chunk j-1 runs; every kernel read is local.  The caller has issued the rank barrier, so the
-// peers' shards of psi are complete; the copies are finished before the last chunk's kernel starts, i.e. before this
-// rank joins the next collective, which is what allows a peer to overwrite psi afterwards.
-static int sd_apply_blk_halo(sd_model *m, sd_vec *out, const sd_vec *psi, SdEpi epi, int slotmask, int slot_out) {
-    sd_ctx *c = m->ctx;
-    SdBlkDev::Halo &H = m->blk.halo;
-    const int nc = psi->nc;
-    SD_TRY(sd_halo_mirror(m, nc));
-    const SdBlkDev::Halo::Mirror &M = H.mir[nc - 1];
-    SdBlkParams P = sd_blk_params(m, nc);
-    P.order = nullptr; P.norder = 0;                                  // the chunks are key ranges
-    const uint64_t klo = P.key_lo, nkeys = P.key_hi - P.key_lo;
-    if (nkeys == 0) return sd_empty_shard_reduce(c, slotmask, slot_out);
-    SD_ARG(nkeys < 0x7fffffffULL, "too many tiles for one launch");
-    if (slotmask) {
-        SD_TRY(sd_partials_reserve(c, (size_t)SD_NSLOT * nkeys));
-        SD_CUDA(cudaMemsetAsync(c->d_partials, 0, (size_t)SD_NSLOT * nkeys * sizeof(double), c->stream));
-    }
-    const bool plain = epi.mode == SD_EPI_PLAIN && epi.red == 0 && !epi.acc && epi.hscale == 1.0 && !epi.hscale_dev;
-    SdVecView view = psi->view;
-    for (int g = 0; g < c->world; ++g)
-        if (g != c->rank && M.va[g]) view.base[g] = (const double *)M.va[g] - (int64_t)m->blk.pstart[g] * nc;
-    const size_t esz = (size_t)nc * sizeof(double);
-    const int K = (int)H.plan.segs.size();
-    SD_CUDA(cudaEventRecord(H.ev_ready, c->stream));
-    SD_CUDA(cudaStreamWaitEvent(H.copy_stream, H.ev_ready, 0));
-    for (int j = 0; j < K; ++j) {
-        for (const SdHaloSeg &sg : H.plan.segs[j]) {
-            const char *src = (const char *)psi->view.base[sg.peer] + sg.lo * esz;
-            char *dst = (char *)view.base[sg.peer] + sg.lo * esz;
-            SD_CUDA(cudaMemcpyAsync(dst, src, (size_t)(sg.hi - sg.lo) * esz, cudaMemcpyDeviceToDevice, H.copy_stream));
-        }
-        SD_CUDA(cudaEventRecord(H.ev[j], H.copy_stream));
-    }
-    for (int j = 0; j < K; ++j) {
-        SdBlkParams Pj = P;
-        Pj.key_lo = H.plan.chunk_key[j]; Pj.key_hi = H.plan.chunk_key[j + 1];
-        SD_CUDA(cudaStreamWaitEvent(c->stream, H.ev[j], 0));
-        SdEpi ej = epi;
-        ej.partials = c->d_partials + (Pj.key_lo - klo);             // slot-major [slot * nparts + tile]: same row pitch, shifted start
-        ej.nparts = (unsigned)nkeys;
-        SD_TRY(sd_blk_launch_range(m, nc, Pj, view, out->d, ej, plain));
-    }
-    if (slotmask) SD_TRY(sd_finish_reduce(c, (unsigned)nkeys, slotmask, slot_out));
-    return SD_OK;
-}
-
 // Launches one apply kernel with the given epilogue; reductions (if any) land
 // in d_scal[slot_out .. slot_out+3].
 static int sd_apply_impl(sd_model *m, sd_vec *out, const sd_vec *psi, SdEpi epi, int slot_out, const sd_vec *acc = nullptr) {
@@ -1450,7 +1267,6 @@ static int sd_apply_impl(sd_model *m, sd_vec *out, const sd_vec *psi, SdEpi epi,
     const int slotmask = sd_epi_slotmask(epi.red);
     SD_ARG(out->layout == psi->layout && psi->layout == (m->path == SD_PATH_BLOCK ? 1 : 0),
            "vector layout does not match the model's kernel path");
-    if (m->path == SD_PATH_BLOCK && m->blk.halo.on) return sd_apply_blk_halo(m, out, psi, epi, slotmask, slot_out);
     if (m->path == SD_PATH_BLOCK) {
         SdBlkParams P = sd_blk_params(m, nc);
         const uint64_t nkeys = P.key_hi - P.key_lo;
@@ -1591,8 +1407,22 @@ int sd_cheb_step(sd_model *m, sd_vec *vnext, const sd_vec *v, const sd_vec *vpre
     }
     return SD_OK;
 }
+// phi = (sum_r w_r s_r(state)) * ComplexF64(psi0) with complex per-site weights w[L]: Sz_q_vector is w_r = e^{iqr} / sqrt(L)
+// (Hamiltonian.jl:307-337), the single-site S^z_i of the site-resolved KPM (TimeEvolution/KPM.jl:197-213) is w = delta_{r,i}.
+static int sd_sz_weights_impl(sd_model *m, sd_vec *phi, const sd_vec *psi0, const double *wre, const double *wim, double normfact, double *norm2);
+int sd_apply_sz_weights(sd_model *m, sd_vec *phi, const sd_vec *psi0, const sd_complex *w, double *norm2) {
+    SD_ARG(m && phi && psi0 && w, "NULL argument");
+    double wre[SD_MAX_L + 1], wim[SD_MAX_L + 1];
+    for (int r = 0; r <= SD_MAX_L; ++r) { wre[r] = r < m->L ? w[r].re : 0.0; wim[r] = r < m->L ? w[r].im : 0.0; }
+    return sd_sz_weights_impl(m, phi, psi0, wre, wim, 1.0, norm2);
+}
 int sd_szq(sd_model *m, sd_vec *phi, const sd_vec *psi0, double q, double *norm2) {
     SD_ARG(m && phi && psi0, "NULL argument");
+    double wre[SD_MAX_L + 1], wim[SD_MAX_L + 1];
+    for (int r = 0; r <= SD_MAX_L; ++r) { wre[r] = r < m->L ? cos(q * (double)r) : 0.0; wim[r] = r < m->L ? sin(q * (double)r) : 0.0; }
+    return sd_sz_weights_impl(m, phi, psi0, wre, wim, 1.0 / sqrt((double)m->L), norm2);
+}
+static int sd_sz_weights_impl(sd_model *m, sd_vec *phi, const sd_vec *psi0, const double *wre, const double *wim, double normfact, double *norm2) {
     SD_ARG(phi->model == m && psi0->model == m, "vector does not belong to this model");
     SD_ARG(phi->dtype == SD_C128, "phi must be SD_C128");
     SD_ARG(phi->d != psi0->d, "phi must not alias psi0");
@@ -1603,8 +1433,8 @@ int sd_szq(sd_model *m, sd_vec *phi, const sd_vec *psi0, double q, double *norm2
         SD_ARG(psi0->layout, "vectors differ in layout");
         SdBlkParams P = sd_blk_params(m, 2);
         SdBlkSzq ZB;
-        ZB.normfact = 1.0 / sqrt((double)m->L);
-        for (int r = 0; r <= SD_MAX_L; ++r) { ZB.ph_re[r] = r < m->L ? cos(q * (double)r) : 0.0; ZB.ph_im[r] = r < m->L ? sin(q * (double)r) : 0.0; }
+        ZB.normfact = normfact;
+        for (int r = 0; r <= SD_MAX_L; ++r) { ZB.ph_re[r] = wre[r]; ZB.ph_im[r] = wim[r]; }
         const uint64_t nkeys = P.key_hi - P.key_lo;
         const unsigned g = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(nkeys, (uint64_t)c->sm_count * 16));
         double *partials = nullptr;
@@ -1627,8 +1457,8 @@ int sd_szq(sd_model *m, sd_vec *phi, const sd_vec *psi0, double q, double *norm2
         return SD_OK;
     }
     SdSzqParams Z;
-    Z.L = m->L; Z.k = m->k; Z.normfact = 1.0 / sqrt((double)m->L); Z.binom = c->d_binom;
-    for (int r = 0; r < m->L; ++r) { Z.ph_re[r] = cos(q * (double)r); Z.ph_im[r] = sin(q * (double)r); }
+    Z.L = m->L; Z.k = m->k; Z.normfact = normfact; Z.binom = c->d_binom;
+    for (int r = 0; r < m->L; ++r) { Z.ph_re[r] = wre[r]; Z.ph_im[r] = wim[r]; }
     const unsigned g = sd_blas_grid(c, phi->logical_n);
     double *partials = nullptr;
     if (norm2) { SD_TRY(sd_partials_reserve(c, (size_t)SD_NSLOT * g)); partials = c->d_partials; }

@@ -1,16 +1,14 @@
-// sd_halo_host.h -- host-side plan of the "halo mirror" for sharded block-layout applies (SD_HALO=1).
+// sd_shard_host.h -- host-side model of a sharded block-layout apply's NVLink traffic, and shards weighted by it.
 //
-// Without it a sharded apply reads the partner tiles of the cut prefix bonds straight from peer HBM inside the kernel
-// (lane loads or TMA over NVLink), and every warp / ring slot runs at the pace of its slowest remote tile.  With it
-// the rank's tile range is cut into K chunks; the copy engines pull, chunk by chunk, exactly the peer ranges the
-// chunk's tile headers point at into a LOCAL mirror of the peer shards (a sparse virtual-memory mapping with the peer's
-// own offsets, so the kernels run unchanged on mirror base pointers), and the apply kernel of chunk j starts when the
-// copies of chunk j have landed while those of chunk j+1 are in flight.  All kernel reads are local; NVLink moves
-// large contiguous segments at copy-engine speed, overlapped with compute.
-//
-// This file computes, from the same tile-header code the kernel runs (sd_blk_hdr_lane / sd_blk_hdr_fill), which peer
-// ranges each chunk needs.  Pure C++ (no CUDA); checked on the CPU by tests/emul (every remote pointer of every header
-// lies inside the segments of its chunk or of an earlier one).
+// A sharded apply reads the partner tiles of the cut prefix bonds straight from peer HBM inside the kernel (plain 16-byte
+// loads through CUDA-IPC mappings).  With equal rank ranges the inbound volume is very uneven: at 8 ranks the ranks whose
+// top prefix bits are 101 / 010 gather 2.5 shards' worth, the edge ranks 0.5.  This file computes, from the
+// same tile-header code the kernel runs (sd_blk_hdr_host), which peer ranges a rank's tiles point at, and moves the cut
+// positions until the slowest rank's modelled time stops improving (sd_shard_balance).  Measured at L = 32 on 8 B200:
+// 2.62 ms per apply with equal shards, 1.81 ms weighted (profiles/round2_e_8gpu.txt).
+// (Round 2 also measured the copy-engine "halo mirror" this plan was first written for -- chunked cudaMemcpyAsync of the
+// peer ranges into a local sparse mapping, kernels on local pointers only: 4.47 ms against 3.43 ms for direct peer loads
+// at 2 ranks, so it was removed.)  Pure C++ (no CUDA); checked on the CPU by tests/emul.
 #pragma once
 #include <algorithm>
 #include <cmath>
@@ -20,21 +18,21 @@
 #include "sd_blk_host.h"
 #include "sd_tile_host.h"
 
-struct SdHaloSeg {
+struct SdShardSeg {
     int peer;
     uint64_t lo, hi;                 // stored elements [lo, hi), global offsets (all shards)
 };
-struct SdHaloPlan {
+struct SdShardPlan {
     std::vector<uint64_t> chunk_key;                                    // K + 1 tile-key bounds of the rank's range
-    std::vector<std::vector<SdHaloSeg>> segs;                           // per chunk: ranges not yet copied by earlier chunks
+    std::vector<std::vector<SdShardSeg>> segs;                           // per chunk: ranges not yet copied by earlier chunks
     std::vector<std::pair<uint64_t, uint64_t>> need[SD_MAX_WORLD];      // per peer: union of all ranges, merged, sorted
     uint64_t remote_elems = 0;                                          // sum of the ranges (stored elements)
 };
 
 // the remote partner tiles of tile `key`: (peer, [lo, hi)) appended to out.  Runs the kernel's header code with base
 // pointers that encode the owner in the top byte, so the owner / offset of every entry is exactly what the kernel derefs.
-static inline void sd_halo_tile_remotes(const SdBlkHost &bh, const SdBlkParams &P, uint64_t key, int qfar,
-                                        std::vector<SdHaloSeg> &out) {
+static inline void sd_shard_tile_remotes(const SdBlkHost &bh, const SdBlkParams &P, uint64_t key, int qfar,
+                                        std::vector<SdShardSeg> &out) {
     const uint64_t Pb = sd_blk_key_prefix(key, P.A);
     const int js = P.k - SD_POPC64(Pb);
     if (js < 0 || js > SD_BLK_B) return;
@@ -53,7 +51,7 @@ static inline void sd_halo_tile_remotes(const SdBlkHost &bh, const SdBlkParams &
     }
 }
 
-static inline void sd_halo_merge(std::vector<std::pair<uint64_t, uint64_t>> &v) {
+static inline void sd_shard_merge(std::vector<std::pair<uint64_t, uint64_t>> &v) {
     std::sort(v.begin(), v.end());
     size_t w = 0;
     for (size_t i = 0; i < v.size(); ++i) {
@@ -63,7 +61,7 @@ static inline void sd_halo_merge(std::vector<std::pair<uint64_t, uint64_t>> &v) 
     v.resize(w);
 }
 // a minus b (both merged and sorted)
-static inline std::vector<std::pair<uint64_t, uint64_t>> sd_halo_subtract(const std::vector<std::pair<uint64_t, uint64_t>> &a,
+static inline std::vector<std::pair<uint64_t, uint64_t>> sd_shard_subtract(const std::vector<std::pair<uint64_t, uint64_t>> &a,
                                                                          const std::vector<std::pair<uint64_t, uint64_t>> &b) {
     std::vector<std::pair<uint64_t, uint64_t>> r;
     size_t j = 0;
@@ -81,8 +79,8 @@ static inline std::vector<std::pair<uint64_t, uint64_t>> sd_halo_subtract(const 
 }
 
 // P: the rank's launch parameters (shards, key_lo / key_hi, host table pointers set).  nchunks >= 1.
-static inline bool sd_halo_plan(const SdBlkHost &bh, const SdBlkParams &P, int nchunks, int qfar, SdHaloPlan &out) {
-    out = SdHaloPlan();
+static inline bool sd_shard_plan(const SdBlkHost &bh, const SdBlkParams &P, int nchunks, int qfar, SdShardPlan &out) {
+    out = SdShardPlan();
     if (nchunks < 1) nchunks = 1;
     const uint64_t klo = P.key_lo, khi = P.key_hi;
     // chunk bounds: equal shares of the rank's stored elements, moved to tile keys (the stored base is monotone in the key)
@@ -100,50 +98,36 @@ static inline bool sd_halo_plan(const SdBlkHost &bh, const SdBlkParams &P, int n
     }
     out.segs.assign(nchunks, {});
     std::vector<std::pair<uint64_t, uint64_t>> have[SD_MAX_WORLD];
-    std::vector<SdHaloSeg> raw;
+    std::vector<SdShardSeg> raw;
     for (int j = 0; j < nchunks; ++j) {
         raw.clear();
-        for (uint64_t key = out.chunk_key[j]; key < out.chunk_key[j + 1]; ++key) sd_halo_tile_remotes(bh, P, key, qfar, raw);
+        for (uint64_t key = out.chunk_key[j]; key < out.chunk_key[j + 1]; ++key) sd_shard_tile_remotes(bh, P, key, qfar, raw);
         for (int g = 0; g < P.shards.world; ++g) {
             std::vector<std::pair<uint64_t, uint64_t>> want;
-            for (const SdHaloSeg &s : raw) if (s.peer == g) want.push_back({s.lo, s.hi});
+            for (const SdShardSeg &s : raw) if (s.peer == g) want.push_back({s.lo, s.hi});
             if (want.empty()) continue;
-            sd_halo_merge(want);
-            for (auto [lo, hi] : sd_halo_subtract(want, have[g])) {
+            sd_shard_merge(want);
+            for (auto [lo, hi] : sd_shard_subtract(want, have[g])) {
                 if (lo < P.shards.pstart[g] || hi > P.shards.pstart[g + 1]) return false;   // a tile never straddles shards
                 out.segs[j].push_back({g, lo, hi});
                 out.remote_elems += hi - lo;
             }
             have[g].insert(have[g].end(), want.begin(), want.end());
-            sd_halo_merge(have[g]);
+            sd_shard_merge(have[g]);
         }
     }
     for (int g = 0; g < SD_MAX_WORLD; ++g) out.need[g] = have[g];
     return true;
 }
 
-// Byte layout of the mirror of peer g (sd_halo_mirror in sd_api.cu): the virtual range covers the peer's whole shard
-// (vsz bytes, a multiple of the allocation granularity), physical memory is mapped under `runs` only: the needed element
-// ranges converted to bytes (esz = bytes per element) and rounded out to the granularity, merged.
-static inline void sd_halo_mirror_runs(const SdHaloPlan &plan, const uint64_t *pstart, int g, size_t esz, size_t gran,
-                                       size_t *vsz, std::vector<std::pair<uint64_t, uint64_t>> &runs) {
-    const uint64_t p0 = pstart[g], p1 = pstart[g + 1];
-    *vsz = (((size_t)(p1 - p0 + 2) * esz + gran - 1) / gran) * gran;
-    runs.clear();
-    for (auto [lo, hi] : plan.need[g])
-        runs.push_back({((lo - p0) * esz / gran) * gran, std::min<uint64_t>(*vsz, (((hi - p0) * esz + gran - 1) / gran) * gran)});
-    sd_halo_merge(runs);
-}
-
-// ---- shards weighted by their remote volume (SD_SHARD_BALANCE=1)
-// Equal rank ranges leave the ranks whose top prefix bits are 101 / 010 with 2.5 shards of inbound NVLink traffic at 8
-// ranks while the edge ranks pull 0.5.  With transfers overlapped (halo mirror) a rank's apply time is
-// about max(local elements, remote_cost * remote elements): remote_cost = time to receive one element over NVLink in
-// units of the time to process one local element (0.7 for f64 with the round-1 kernel: 8 B / 900 GB/s against 12.5 ps).
+// ---- shards weighted by their remote volume (default for more than two ranks; SD_SHARD_BALANCE=0 switches it off)
+// A rank's apply time is modelled as max(local elements, remote_cost * remote elements): remote_cost = time to receive
+// one element over NVLink in units of the time to process one local element (default 1.3: 8 B at ~750 GB/s against
+// ~8 ps per local state).
 // This fixed-point iteration moves the cut positions until the largest such time stops improving; every rank runs
 // it on the same inputs, so all ranks arrive at the same bounds.  cost[0] = largest time with equal shards,
 // cost[1] = with the returned bounds (both in local-element units).
-static inline bool sd_halo_rank_cost(const SdBlkHost &bh, const uint64_t *keys, int world, int qfar, double remote_cost,
+static inline bool sd_shard_rank_cost(const SdBlkHost &bh, const uint64_t *keys, int world, int qfar, double remote_cost,
                                      double *tmax, std::vector<double> *per_rank) {
     SdBlkParams P = bh.P;
     P.W = bh.W.data(); P.js = bh.js.data(); P.units = bh.units.data(); P.items = bh.items.data(); P.dmid = bh.dmid.data();
@@ -153,8 +137,8 @@ static inline bool sd_halo_rank_cost(const SdBlkHost &bh, const uint64_t *keys, 
     if (per_rank) per_rank->assign(world, 0.0);
     for (int r = 0; r < world; ++r) {
         P.shards.rank = r; P.key_lo = keys[r]; P.key_hi = keys[r + 1];
-        SdHaloPlan plan;
-        if (!sd_halo_plan(bh, P, 1, qfar, plan)) return false;
+        SdShardPlan plan;
+        if (!sd_shard_plan(bh, P, 1, qfar, plan)) return false;
         const double local = (double)(P.shards.pstart[r + 1] - P.shards.pstart[r]);
         const double t = std::max(local, remote_cost * (double)plan.remote_elems);
         if (per_rank) (*per_rank)[r] = t;
@@ -162,7 +146,7 @@ static inline bool sd_halo_rank_cost(const SdBlkHost &bh, const uint64_t *keys, 
     }
     return true;
 }
-static inline bool sd_halo_balance(const SdBlkHost &bh, const SdTileHost &th, int world, int qfar, double remote_cost, int iters,
+static inline bool sd_shard_balance(const SdBlkHost &bh, const SdTileHost &th, int world, int qfar, double remote_cost, int iters,
                                    uint64_t *bounds, uint64_t *keys, double *cost) {
     const uint64_t N = th.binom[(size_t)th.P.L * SD_BINOM_DIM + th.P.k];
     std::vector<double> frac(world, 1.0 / world), t(world);
@@ -175,7 +159,7 @@ static inline bool sd_halo_balance(const SdBlkHost &bh, const SdTileHost &th, in
         cum[world] = N;
         sd_tile_shard_bounds_at(th, world, cum.data(), b.data(), kk.data());
         double tmax = 0.0;
-        if (!sd_halo_rank_cost(bh, kk.data(), world, qfar, remote_cost, &tmax, &t)) return false;
+        if (!sd_shard_rank_cost(bh, kk.data(), world, qfar, remote_cost, &tmax, &t)) return false;
         if (it == 0) cost[0] = tmax;
         if (best < 0.0 || tmax < best) {
             best = tmax;

@@ -90,6 +90,7 @@ SIGNATURES = {
     "sd_apply_rescaled_H": [_vp, _vp, _vp, _d, _d],
     "sd_cheb_step": [_vp, _vp, _vp, _vp, _d, _d, _vp, _P(_d), _P(_d), _vp, SdComplex],
     "sd_szq": [_vp, _vp, _vp, _d, _P(_d)],
+    "sd_apply_sz_weights": [_vp, _vp, _vp, _vp, _P(ctypes.c_double)],
     "sd_apply_H_host": [_vp, _i, _vp, _vp],
     "sd_vec_observables": [_vp, _vp, _vp],
     "sd_vecset_free": [_vp],

@@ -687,6 +687,120 @@ def chebyshev_time_evolve(psi0, dt: float, applyH_, model: Model, cheb_n: int = 
     return out if (device or _is_dev(psi0)) else out.to_host()
 
 
+# ------------------------------------------------- TimeEvolution/KPM.jl (site-resolved KPM)
+
+def site_sz_operator(i: int):
+    """The operator `create_spin_operator(i, :z)` that kpm_correlation_matrix builds (TimeEvolution/KPM.jl:205-206),
+    restricted to what the hot path covers: S^z on 1-based site i, psi -> S^z_i psi (complex result, like every other
+    operator output of the reference).  Device in, device out; host in, host out."""
+    def op(psi, model: Model):
+        if not 1 <= i <= model.L:
+            raise ValueError("site index out of range")
+        w = (SdComplex * model.L)()
+        w[i - 1].re = 1.0
+        d = _up(model, psi)
+        out = model.vector(np.complex128)
+        check(lib().sd_apply_sz_weights(model._h, out._h, d._h, ctypes.cast(w, ctypes.c_void_p), None))
+        return out if _is_dev(psi) else out.to_host()
+    return op
+
+
+def kpm_get_rescaling_params(applyH_, model: Model, lanc_m: int = 80, rng=None):
+    """TimeEvolution/KPM.jl:45-49 -- note the factor: a = (Emax - Emin) / 2 * 0.9 (NOT / 0.99 as in KPM_Sqw.jl:13-17)."""
+    E_min, E_max = estimate_energy_bounds(applyH_, model, lanc_m=lanc_m, rng=rng)
+    return float((E_max - E_min) / 2 * 0.9), float((E_max + E_min) / 2)
+
+
+def get_jackson_kernel(n: int):
+    """TimeEvolution/KPM.jl:170-177."""
+    k = np.arange(n)
+    d = np.pi / (n + 1)
+    return ((n - k + 1) * np.cos(d * k) + np.sin(d * k) / np.tan(d)) / (n + 1)
+
+
+def evaluate_chebyshev_series(mu, x: float, a: float) -> float:
+    """TimeEvolution/KPM.jl:184-206: 0 outside (-1, 1); sum_k mu_k T_k(x) / (pi sqrt(1 - x^2)) * (2 / a) (no factor 2 on k >= 1)."""
+    if abs(x) >= 1.0:
+        return 0.0
+    n = len(mu)
+    total = mu[0]
+    if n > 1:
+        total += mu[1] * x
+    Tp, Tc = 1.0, x
+    for k in range(2, n):
+        Tn = 2 * x * Tc - Tp
+        total += mu[k] * Tn
+        Tp, Tc = Tc, Tn
+    return float(total / (np.pi * np.sqrt(1 - x * x)) * (2 / a))
+
+
+def compute_cross_chebyshev_moments(chi, phi, n: int, a: float, b: float, applyH_, model: Model):
+    """TimeEvolution/KPM.jl:121-165: mu_k = <chi| T_k(H~) |phi> with phi normalised first and `dot(conj(chi), .)`, i.e.
+    the UNCONJUGATED product sum_i chi_i phi_i (sd_vec_dotu).  The recurrence runs on the device: one fused Chebyshev
+    step per moment (sd_cheb_step: 2 (H v - b v) / a - v_prev in the apply kernel's epilogue) plus one dotu pass."""
+    _require_builtin(applyH_)
+    n = int(n)
+    dchi = _up(model, chi, np.complex128)
+    dphi = _up(model, phi, np.complex128)
+    norm_phi = dphi.norm()
+    prev = model.vector(np.complex128).copy_from(dphi)
+    prev.scale(1.0 / norm_phi)
+    curr = model.vector(np.complex128)
+    check(lib().sd_apply_rescaled_H(model._h, curr._h, prev._h, float(a), float(b)))
+    mom = np.zeros(n)
+
+    def real_or_inexact(z):
+        if abs(z.imag) > 0.0 and abs(z.imag) > 1e-300:
+            raise TypeError("InexactError: complex moment assigned to a Float64 array")   # moments[1] = dot(...) :147-148
+        return z.real
+
+    mom[0] = real_or_inexact(dchi.dotu(prev) * norm_phi)
+    if n > 1:
+        mom[1] = real_or_inexact(dchi.dotu(curr) * norm_phi)
+    zero = SdComplex(0.0, 0.0)
+    for k in range(2, n):
+        # phi_next = 2 H~ phi_curr - phi_prev, written over phi_prev (same element, read before it is written)
+        check(lib().sd_cheb_step(model._h, prev._h, curr._h, prev._h, float(a), float(b), None, None, None, None, zero))
+        prev, curr = curr, prev
+        mom[k] = (dchi.dotu(curr)).real * norm_phi
+    return mom
+
+
+def kpm_dynamical_correlation(psi, operator_A, operator_B, w_range, applyH_, model: Model, n: int = 300, eps: float = 0.1,
+                              a=None, b=None):
+    """TimeEvolution/KPM.jl:74-118: S(w) = <psi| A^dag delta(w - H) B |psi> from n Jackson-damped cross moments; x = (w - b) / a
+    (no E0 shift, as in the reference); negative values clipped to 0."""
+    if a is None or b is None:
+        a, b = kpm_get_rescaling_params(applyH_, model, lanc_m=n)
+    phi = operator_B(psi, model)
+    chi = operator_A(psi, model)
+    mu = compute_cross_chebyshev_moments(chi, phi, n, a, b, applyH_, model) * get_jackson_kernel(n)
+    S = np.array([evaluate_chebyshev_series(mu, (w - b) / a, a) for w in np.asarray(w_range, dtype=np.float64)])
+    return np.maximum(S, 0.0)
+
+
+def kpm_correlation_matrix(psi, w_range, applyH_, model: Model, n: int = 300, eps: float = 0.1):
+    """TimeEvolution/KPM.jl:211-232 with opA = opB = S^z: C[i, j, :] = |S_ij(w)|, rescaling parameters computed once."""
+    L = model.L
+    w_range = np.asarray(w_range, dtype=np.float64)
+    C = np.zeros((L, L, len(w_range)))
+    a, b = kpm_get_rescaling_params(applyH_, model)
+    dpsi = _up(model, psi)
+    for i in range(1, L + 1):
+        for j in range(1, L + 1):
+            C[i - 1, j - 1, :] = np.abs(kpm_dynamical_correlation(dpsi, site_sz_operator(i), site_sz_operator(j), w_range,
+                                                                 applyH_, model, n=n, eps=eps, a=a, b=b))
+    return C
+
+
+def Sqw(C, q: float, positions):
+    """TimeEvolution/KPM.jl:236-246: S(q, w) = (1/N) sum_ij Re(e^{-iq (r_i - r_j)} C_ij(w))."""
+    positions = np.asarray(positions, dtype=np.float64)
+    N = len(positions)
+    ph = np.exp(-1j * q * (positions[:, None] - positions[None, :]))
+    return np.einsum("ij,ijw->w", ph.real, C) / N
+
+
 # -------------------------------------------------------------- PublicAPI.jl
 
 def groundstate(model: Model, method="lanczos", **kw):

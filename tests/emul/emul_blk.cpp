@@ -15,7 +15,7 @@
 #include "../../spindynamics.jl_b200/csrc/sd_tile_host.h"
 #include "../../spindynamics.jl_b200/csrc/sd_blk_host.h"
 #include "../../spindynamics.jl_b200/csrc/sd_blkl.h"
-#include "../../spindynamics.jl_b200/csrc/sd_halo_host.h"
+#include "../../spindynamics.jl_b200/csrc/sd_shard_host.h"
 
 namespace {
 
@@ -93,13 +93,13 @@ int emul_blk_apply(int L, int k, const double *Jhop, const double *Jz, const dou
     sd_tile_shard_bounds(th, world, bounds, keys);
     if (variant & 512) {
         double cost[2];
-        if (!sd_halo_balance(bh, th, world, sd_tile_qfar(L, bh.P.A, bh.binom.data(), far_bytes, 8 * NC), 0.7, 5, bounds, keys, cost)) return -9;
+        if (!sd_shard_balance(bh, th, world, sd_tile_qfar(L, bh.P.A, bh.binom.data(), far_bytes, 8 * NC), 0.7, 5, bounds, keys, cost)) return -9;
     }
     SdBlkParams P = bh.P;
     P.W = bh.W.data(); P.js = bh.js.data(); P.units = bh.units.data(); P.items = bh.items.data(); P.dmid = bh.dmid.data();
     P.nbuf = 3;
-    const bool halo = (variant & 256) != 0;                          // + 256: through the halo mirror (sd_halo_host.h), 3 chunks
-    // + 512: remote-volume-weighted shard bounds (sd_halo_balance), applied above where the bounds are computed
+    const bool halo = (variant & 256) != 0;                          // + 256: through the halo mirror (sd_shard_host.h), 3 chunks
+    // + 512: remote-volume-weighted shard bounds (sd_shard_balance), applied above where the bounds are computed
     P.key_lo = keys[rank]; P.key_hi = keys[rank + 1];
     P.shards.world = world; P.shards.rank = rank;
     uint64_t pstart[SD_MAX_WORLD + 1];
@@ -152,12 +152,12 @@ int emul_blk_apply(int L, int k, const double *Jhop, const double *Jz, const dou
 #define RUN(NC_, PLAIN_) run_tiles<NC_, PLAIN_>(bh, P, view, o.p, epi, qfar, red)
     // halo mirror: the peers' shards are replaced by NaN-filled mirrors that only hold what the plan copies, chunk by
     // chunk, before the tiles of that chunk run (what sd_apply_blk_halo does with the copy engines and one event per chunk)
-    SdHaloPlan plan;
+    SdShardPlan plan;
     std::vector<AlignedBuf> mirror(world);
     int nchunks = 1;
     if (halo && world > 1) {
         nchunks = 3;
-        if (!sd_halo_plan(bh, P, nchunks, qfar, plan)) return -9;
+        if (!sd_shard_plan(bh, P, nchunks, qfar, plan)) return -9;
         for (int g = 0; g < world; ++g) {
             if (g == rank) continue;
             mirror[g].alloc((size_t)(pstart[g + 1] - pstart[g]) * NC, NAN);
@@ -167,7 +167,7 @@ int emul_blk_apply(int L, int k, const double *Jhop, const double *Jz, const dou
     const uint64_t klo_all = P.key_lo, khi_all = P.key_hi;
     for (int j = 0; j < nchunks; ++j) {
         if (halo && world > 1) {
-            for (const SdHaloSeg &sg : plan.segs[j])
+            for (const SdShardSeg &sg : plan.segs[j])
                 std::memcpy(mirror[sg.peer].p + (sg.lo - pstart[sg.peer]) * NC, s_psi[sg.peer].p + (sg.lo - pstart[sg.peer]) * NC,
                             (size_t)(sg.hi - sg.lo) * NC * sizeof(double));
             P.key_lo = plan.chunk_key[j]; P.key_hi = plan.chunk_key[j + 1];
@@ -215,7 +215,7 @@ int emul_blk_plan(int L, int k, int world, uint64_t *bounds, uint64_t *pstart, u
     return 0;
 }
 
-// Halo-mirror plan of rank `rank` (sd_halo_host.h) at any size, checked: every remote partner tile of every tile header
+// Halo-mirror plan of rank `rank` (sd_shard_host.h) at any size, checked: every remote partner tile of every tile header
 // of chunk j lies inside the segments of chunks 0..j; segments are disjoint, inside their peer's shard and tile aligned
 // (multiples of 16 elements).  stats: [0] segments, [1] remote stored elements, [2] local stored elements, [3] peers used,
 // [4] largest number of segments in one chunk.  Returns 0, -1 (model), -2 (plan failed), -3 (coverage), -4 (segment shape).
@@ -233,25 +233,25 @@ int emul_halo_plan(int L, int k, int world, int rank, int nchunks, uint64_t *sta
     P.shards.world = world; P.shards.rank = rank;
     for (int g = 0; g <= SD_MAX_WORLD; ++g) P.shards.pstart[g] = sd_blk_key_base(bh, keys[g < world ? g : world]);
     const int qfar = sd_tile_qfar(L, P.A, bh.binom.data(), (uint64_t)100 << 20, 8);
-    SdHaloPlan plan;
-    if (!sd_halo_plan(bh, P, nchunks, qfar, plan)) return -2;
+    SdShardPlan plan;
+    if (!sd_shard_plan(bh, P, nchunks, qfar, plan)) return -2;
     if ((int)plan.chunk_key.size() != nchunks + 1 || plan.chunk_key.front() != P.key_lo || plan.chunk_key.back() != P.key_hi) return -2;
     std::vector<std::pair<uint64_t, uint64_t>> have[SD_MAX_WORLD];
     uint64_t nseg = 0, maxseg = 0, total = 0;
     for (int j = 0; j < nchunks; ++j) {
         if (plan.chunk_key[j] > plan.chunk_key[j + 1]) return -2;
         maxseg = std::max<uint64_t>(maxseg, plan.segs[j].size());
-        for (const SdHaloSeg &s : plan.segs[j]) {
+        for (const SdShardSeg &s : plan.segs[j]) {
             if (s.peer == rank || s.peer < 0 || s.peer >= world || s.lo >= s.hi || (s.lo & 15u) || (s.hi & 15u)) return -4;
             if (s.lo < P.shards.pstart[s.peer] || s.hi > P.shards.pstart[s.peer + 1]) return -4;
             for (auto [lo, hi] : have[s.peer]) if (s.lo < hi && lo < s.hi) return -4;             // disjoint from everything before
             have[s.peer].push_back({s.lo, s.hi});
             ++nseg; total += s.hi - s.lo;
         }
-        for (int g = 0; g < world; ++g) sd_halo_merge(have[g]);
-        std::vector<SdHaloSeg> raw;
-        for (uint64_t key = plan.chunk_key[j]; key < plan.chunk_key[j + 1]; ++key) sd_halo_tile_remotes(bh, P, key, qfar, raw);
-        for (const SdHaloSeg &r : raw) {
+        for (int g = 0; g < world; ++g) sd_shard_merge(have[g]);
+        std::vector<SdShardSeg> raw;
+        for (uint64_t key = plan.chunk_key[j]; key < plan.chunk_key[j + 1]; ++key) sd_shard_tile_remotes(bh, P, key, qfar, raw);
+        for (const SdShardSeg &r : raw) {
             bool ok = false;
             for (auto [lo, hi] : have[r.peer]) if (lo <= r.lo && r.hi <= hi) { ok = true; break; }
             if (!ok) return -3;
@@ -264,36 +264,11 @@ int emul_halo_plan(int L, int k, int world, int rank, int nchunks, uint64_t *sta
         if (!have[g].empty()) ++peers;
     }
     stats[0] = nseg; stats[1] = total; stats[2] = P.shards.pstart[rank + 1] - P.shards.pstart[rank]; stats[3] = peers; stats[4] = maxseg;
-    // mirror mapping (sd_halo_mirror_runs): every segment's bytes lie inside one mapped, granularity-aligned run of its peer
-    uint64_t mapped = 0;
-    for (int nc = 1; nc <= 2; ++nc) {
-        const size_t esz = (size_t)nc * 8, gran = (size_t)2 << 20;
-        for (int g = 0; g < world; ++g) {
-            if (g == rank || plan.need[g].empty()) continue;
-            size_t vsz = 0;
-            std::vector<std::pair<uint64_t, uint64_t>> runs;
-            sd_halo_mirror_runs(plan, P.shards.pstart, g, esz, gran, &vsz, runs);
-            if (vsz % gran || vsz < (P.shards.pstart[g + 1] - P.shards.pstart[g]) * esz) return -5;
-            for (size_t i = 0; i < runs.size(); ++i) {
-                if (runs[i].first % gran || runs[i].second % gran || runs[i].first >= runs[i].second || runs[i].second > vsz) return -5;
-                if (i && runs[i].first <= runs[i - 1].second) return -5;                            // merged
-                if (nc == 1) mapped += runs[i].second - runs[i].first;
-            }
-            for (int j = 0; j < nchunks; ++j)
-                for (const SdHaloSeg &sg : plan.segs[j]) {
-                    if (sg.peer != g) continue;
-                    const uint64_t b0 = (sg.lo - P.shards.pstart[g]) * esz, b1 = (sg.hi - P.shards.pstart[g]) * esz;
-                    bool ok = false;
-                    for (auto [r0, r1] : runs) if (r0 <= b0 && b1 <= r1) { ok = true; break; }
-                    if (!ok) return -5;
-                }
-        }
-    }
-    stats[5] = mapped;                                                 // bytes of physical mirror memory for f64 vectors
+    stats[5] = 0;
     return 0;
 }
 
-// Remote-volume-weighted shard bounds (sd_halo_balance): bounds / keys [world + 1], cost[2] (largest per-rank time with
+// Remote-volume-weighted shard bounds (sd_shard_balance): bounds / keys [world + 1], cost[2] (largest per-rank time with
 // equal shards / with the returned bounds, in local-element units), per_rank[world] times at the returned bounds.
 int emul_halo_balance(int L, int k, int world, double remote_cost, int iters, uint64_t *bounds, uint64_t *keys, double *cost, double *per_rank) {
     SdBlkHost bh;
@@ -302,10 +277,10 @@ int emul_halo_balance(int L, int k, int world, double remote_cost, int iters, ui
     SdTileHost th;
     if (!sd_tile_build(L, k, SD_BLK_B, 5, J.data(), Jz.data(), h.data(), th)) return -1;
     const int qfar = sd_tile_qfar(L, bh.P.A, bh.binom.data(), (uint64_t)100 << 20, 8);
-    if (!sd_halo_balance(bh, th, world, qfar, remote_cost, iters, bounds, keys, cost)) return -2;
+    if (!sd_shard_balance(bh, th, world, qfar, remote_cost, iters, bounds, keys, cost)) return -2;
     double tmax = 0.0;
     std::vector<double> t;
-    if (!sd_halo_rank_cost(bh, keys, world, qfar, remote_cost, &tmax, &t)) return -2;
+    if (!sd_shard_rank_cost(bh, keys, world, qfar, remote_cost, &tmax, &t)) return -2;
     for (int g = 0; g < world; ++g) per_rank[g] = t[g];
     return 0;
 }
