@@ -796,6 +796,92 @@ def chebyshev_time_evolve(psi0, dt, applyH_, model, cheb_n=100, Ebounds=(-1.0, 1
     return psi_t.copy()
 
 
+# ------------------------------------------- TimeEvolution/KPM.jl (site-resolved KPM)
+
+def site_sz_operator(i: int):
+    """create_spin_operator(i, :z) as TimeEvolution/KPM.jl:205-206 uses it: psi -> S^z_i psi (1-based site i).  The
+    reference builds it in Operators.jl (out of the hot-path scope); S^z is diagonal: s_i(state) * psi."""
+    def op(psi, model):
+        st = np.array(model.states, dtype=np.uint64)
+        s = np.where((st >> np.uint64(i - 1)) & np.uint64(1) == np.uint64(1), 0.5, -0.5)
+        return (s * np.asarray(psi)).astype(np.complex128)
+    return op
+
+
+def kpm_get_rescaling_params(applyH_, model, lanc_m=80, rng=None):
+    """TimeEvolution/KPM.jl:45-49: a = (E_max - E_min) / 2 * 0.9, b = (E_max + E_min) / 2."""
+    E_min, E_max = estimate_energy_bounds(applyH_, model, lanc_m=lanc_m, rng=rng)
+    return (E_max - E_min) / 2 * 0.9, (E_max + E_min) / 2
+
+
+def get_jackson_kernel(n: int):
+    """TimeEvolution/KPM.jl:170-177."""
+    g = np.zeros(n)
+    for k in range(n):
+        d = np.pi / (n + 1)
+        g[k] = ((n - k + 1) * np.cos(d * k) + np.sin(d * k) / np.tan(d)) / (n + 1)
+    return g
+
+
+def evaluate_chebyshev_series(mu, x, a):
+    """TimeEvolution/KPM.jl:184-206."""
+    n = len(mu)
+    if abs(x) >= 1.0:
+        return 0.0
+    total = mu[0] * 1.0
+    if n > 1:
+        total += mu[1] * x
+    T_prev, T_curr = 1.0, x
+    for k in range(2, n):
+        T_next = 2 * x * T_curr - T_prev
+        total += mu[k] * T_next
+        T_prev, T_curr = T_curr, T_next
+    return total / (np.pi * np.sqrt(1 - x ** 2)) * (2 / a)
+
+
+def compute_cross_chebyshev_moments(chi, phi, n, a, b, applyH_, model):
+    """TimeEvolution/KPM.jl:121-165.  `dot(conj(chi), x)` = sum_i chi_i x_i (Julia's dot conjugates its first argument)."""
+    moments = np.zeros(n)
+    phi = np.asarray(phi)
+    chi = np.asarray(chi)
+    phi_prev = phi.copy()
+    norm_phi = np.linalg.norm(phi)
+    phi_prev = phi_prev / norm_phi
+    phi_curr = np.empty_like(phi_prev)
+    temp = np.empty_like(phi_prev)
+    apply_rescaled_H_(phi_curr, phi_prev, applyH_, model, a, b)
+
+    def to_real(z):                                                   # assignment of a Complex to a Float64 slot
+        z = complex(z)
+        if z.imag != 0.0:
+            raise TypeError("InexactError")
+        return z.real
+
+    moments[0] = to_real(np.sum(chi * phi_prev) * norm_phi)
+    if n > 1:
+        moments[1] = to_real(np.sum(chi * phi_curr) * norm_phi)
+    for k in range(2, n):
+        apply_rescaled_H_(temp, phi_curr, applyH_, model, a, b)
+        phi_next = 2 * temp - phi_prev
+        moments[k] = np.real(np.sum(chi * phi_next)) * norm_phi
+        phi_prev, phi_curr = phi_curr, phi_next
+    return moments
+
+
+def kpm_dynamical_correlation(psi, operator_A, operator_B, w_range, applyH_, model, n=300, eps=0.1, a=None, b=None):
+    """TimeEvolution/KPM.jl:74-118."""
+    if a is None or b is None:
+        a, b = kpm_get_rescaling_params(applyH_, model, lanc_m=n)
+    phi = operator_B(psi, model)
+    chi = operator_A(psi, model)
+    mu = compute_cross_chebyshev_moments(chi, phi, n, a, b, applyH_, model)
+    mu = mu * get_jackson_kernel(n)
+    S = np.zeros(len(w_range))
+    for i, w in enumerate(w_range):
+        S[i] = evaluate_chebyshev_series(mu, (w - b) / a, a)
+    return np.maximum(S, 0.0)
+
+
 # -------------------------------------------------------------- PublicAPI.jl
 
 def groundstate(model, method="lanczos", **kw):

@@ -160,6 +160,7 @@ struct SdBlkDev {
     size_t smem[2] = {0, 0};
     int qfar[2] = {0, 0};
     int nofence = 0;                // A/B knob (SD_BLK_NOFENCE)
+    int prefetch = 0;               // A/B knob (SD_BLK_PREFETCH): first stream entry the item body prefetches into L2 (0: none)
     int threads = 640;              // CTA size of sd_blkl_apply_kernel (SD_BLKL_THREADS = 512 | 640 | 768, read once at model creation)
     uint32_t *d_order = nullptr;    // breadth-first tile order of this rank's shard (vectors larger than the L2)
     uint32_t norder = 0;
@@ -482,6 +483,7 @@ static int sd_blk_setup(sd_model *m) {
     for (size_t i = 0; i < m->zz_a.size(); ++i) Jz[m->zz_a[i]] += m->zz_J[i];
     if (!sd_blk_build(L, m->k, Jhop.data(), Jz.data(), m->field.data(), b.host)) return SD_OK;
     b.nofence = sd_env_int("SD_BLK_NOFENCE", 0);
+    b.prefetch = sd_env_int("SD_BLK_PREFETCH", 0);
     b.threads = sd_env_int("SD_BLKL_THREADS", 640);
     if (b.threads != 512 && b.threads != 768) b.threads = 640;
     for (int w = 0; w < 2; ++w) {
@@ -511,6 +513,7 @@ static SdBlkParams sd_blk_params(const sd_model *m, int nc) {
     SdBlkParams P = m->blk.host.P;
     const sd_ctx *c = m->ctx;
     P.nbuf = m->blk.nbuf[nc - 1];
+    P.prefetch = m->blk.prefetch;
     P.order = m->blk.d_order; P.norder = m->blk.norder;
     P.key_lo = m->tile[0].keys[c->rank];
     P.key_hi = m->tile[0].keys[c->rank + 1];

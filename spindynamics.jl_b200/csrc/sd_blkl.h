@@ -82,6 +82,15 @@ SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdEpi &E, double *out_l
     // first mid bit differs from the last prefix bit
     const bool c0 = u < cls.n1;                                      // first mid bit (blocks with it set come first)
     const int nnb = H.nnb;
+    if (P.prefetch > 0) {                                            // later entries: DRAM -> L2 while the first ones stream
+        const unsigned long long rem = H.remote;
+        for (int n = P.prefetch; n < nnb; ++n) {
+            if ((rem >> n) & 1ULL) continue;
+            const double *q_ = H.nb[n].p;
+#pragma unroll
+            for (int s = 0; s < EC; ++s) sd_blk_prefetch_l2(q_ + o[s]);
+        }
+    }
     bool xl = false;
     if (H.xptr != nullptr) {
         xl = c0 != (bool)H.bP;
