@@ -159,8 +159,6 @@ struct SdBlkDev {
     int nbuf[2] = {0, 0};
     size_t smem[2] = {0, 0};
     int qfar[2] = {0, 0};
-    int nofence = 0;                // A/B knob (SD_BLK_NOFENCE)
-    int prefetch = 0;               // A/B knob (SD_BLK_PREFETCH): first stream entry the item body prefetches into L2 (0: none)
     int threads = 640;              // CTA size of sd_blkl_apply_kernel (SD_BLKL_THREADS = 512 | 640 | 768, read once at model creation)
     uint32_t *d_order = nullptr;    // breadth-first tile order of this rank's shard (vectors larger than the L2)
     uint32_t norder = 0;
@@ -194,6 +192,7 @@ struct sd_model {
     SdBlkDev blk;                   // block-layout kernel (sd_blk.h)
     bool blk_layout = false;        // vectors of this model are stored in block layout
     int live_vecs = 0;
+    std::vector<sd_vec *> pool;     // idle work vectors of the recurrences (SdVecGuard)
     bool free_pending = false;      // sd_model_free was called while vectors were alive
 };
 
@@ -482,8 +481,6 @@ static int sd_blk_setup(sd_model *m) {
     for (size_t i = 0; i < m->hop_a.size(); ++i) Jhop[m->hop_a[i]] += m->hop_J[i];
     for (size_t i = 0; i < m->zz_a.size(); ++i) Jz[m->zz_a[i]] += m->zz_J[i];
     if (!sd_blk_build(L, m->k, Jhop.data(), Jz.data(), m->field.data(), b.host)) return SD_OK;
-    b.nofence = sd_env_int("SD_BLK_NOFENCE", 0);
-    b.prefetch = sd_env_int("SD_BLK_PREFETCH", 0);
     b.threads = sd_env_int("SD_BLKL_THREADS", 640);
     if (b.threads != 512 && b.threads != 768) b.threads = 640;
     for (int w = 0; w < 2; ++w) {
@@ -513,7 +510,6 @@ static SdBlkParams sd_blk_params(const sd_model *m, int nc) {
     SdBlkParams P = m->blk.host.P;
     const sd_ctx *c = m->ctx;
     P.nbuf = m->blk.nbuf[nc - 1];
-    P.prefetch = m->blk.prefetch;
     P.order = m->blk.d_order; P.norder = m->blk.norder;
     P.key_lo = m->tile[0].keys[c->rank];
     P.key_hi = m->tile[0].keys[c->rank + 1];
@@ -658,12 +654,18 @@ int sd_model_create(sd_ctx *ctx, int L, int nup, const sd_bond *hop, int nhop, c
     return SD_OK;
 }
 
+static void sd_pool_drain(sd_model *m) {
+    std::vector<sd_vec *> p;
+    p.swap(m->pool);
+    for (sd_vec *v : p) { m->live_vecs++; sd_vec_free(v); }
+}
 // Finalizer order is unspecified (Julia, Python shutdown): a model that still has live vectors is only marked and
 // released by the sd_vec_free of its last vector.
 int sd_model_free(sd_model *m) {
     if (!m) return SD_OK;
     {
         SD_LOCK(m->ctx);
+        sd_pool_drain(m);
         if (m->live_vecs > 0) { m->free_pending = true; return SD_OK; }
     }
     cudaSetDevice(m->ctx->device);
@@ -836,6 +838,11 @@ int sd_vec_alloc(sd_model *m, int dtype, sd_vec **vec) {
     // +2 elements of slack so 16-byte vector accesses at the ends stay inside the allocation
     const size_t bytes = (size_t)(v->local_n + 2) * v->nc * sizeof(double);
     cudaError_t e = cudaMalloc(&v->d, bytes);
+    if (e != cudaSuccess && !m->pool.empty() && c->world == 1) {     // idle work vectors are the first thing to give back
+        cudaGetLastError();
+        sd_pool_drain(m);
+        e = cudaMalloc(&v->d, bytes);
+    }
     if (e != cudaSuccess) {
         delete v;
         return sd_fail(SD_ERR_NOMEM, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
@@ -1282,7 +1289,6 @@ static int sd_apply_impl(sd_model *m, sd_vec *out, const sd_vec *psi, SdEpi epi,
         }
         epi.partials = c->d_partials;
         epi.nparts = (unsigned)nkeys;
-        epi.dbg_nofence = m->blk.nofence;
         const bool plain = epi.mode == SD_EPI_PLAIN && epi.red == 0 && !epi.acc && epi.hscale == 1.0 && !epi.hscale_dev;
         SD_TRY(sd_blk_launch_range(m, nc, P, psi->view, out->d, epi, plain));
         if (slotmask) SD_TRY(sd_finish_reduce(c, (unsigned)nkeys, slotmask, slot_out));
@@ -1613,10 +1619,29 @@ int sd_lincomb(sd_vecset *s, const sd_complex *y, int mcount, sd_vec *out, doubl
     return SD_OK;
 }
 
-struct SdVecGuard {          // frees temporaries on every exit path
+// Work vectors of the recurrences.  They come from a small per-model pool and go back to it on every exit path: a
+// solver call at L = 32 otherwise spends more time in cudaMalloc / cudaFree of its 4.8 GB temporaries (and, sharded, in
+// the collective handle exchange of sd_vec_alloc) than in its kernels.  The pool holds at most SD_POOL_MAX vectors, is
+// emptied by sd_model_free and by an allocation that runs out of memory.  Pooled vectors do not count as live.
+#define SD_POOL_MAX 6
+struct SdVecGuard {
     std::vector<sd_vec *> v;
-    ~SdVecGuard() { for (sd_vec *p : v) sd_vec_free(p); }
+    ~SdVecGuard() {
+        for (sd_vec *p : v) {
+            sd_model *m = p->model;
+            if ((int)m->pool.size() < SD_POOL_MAX) { m->pool.push_back(p); m->live_vecs--; }
+            else sd_vec_free(p);
+        }
+    }
     int make(sd_model *m, int dtype, sd_vec **out) {
+        for (size_t i = 0; i < m->pool.size(); ++i)
+            if (m->pool[i]->dtype == dtype) {
+                *out = m->pool[i];
+                m->pool.erase(m->pool.begin() + i);
+                m->live_vecs++;
+                v.push_back(*out);
+                return SD_OK;
+            }
         int rc = sd_vec_alloc(m, dtype, out);
         if (rc == SD_OK) v.push_back(*out);
         return rc;

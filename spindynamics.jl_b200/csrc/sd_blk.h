@@ -84,7 +84,6 @@ struct SdBlkParams {
     const SdBlkItem *items;
     const double *dmid;              // [1 << M] diag of the mid sites + mid-internal zz, in ITEM order (same index as items[])
     uint32_t cap;                    // largest size_pad
-    int prefetch;                    // > 0: the item body prefetches its stream entries from entry `prefetch` on into L2 (local tiles only)
     const uint32_t *order;           // optional tile order of this shard (keys, norder of them); nullptr: rank order
     uint32_t norder;
     SdBlkShards shards;
@@ -124,7 +123,6 @@ struct alignas(16) SdBlkHdr {
     int valid;                           // 1: tile, -1: end of this CTA's tile list
     int nnb, nfar;                       // active prefix-internal bonds; the first nfar are beyond L2 reach
     int ntot;                            // nnb + 1 if the prefix|mid crossing bond is active: entry nnb of nb[]
-    unsigned long long remote;           // bit n: entry n of nb[] is a tile on another GPU (never prefetched)
     int bP;                              // last prefix bit
     unsigned next_unit;                  // work counter of the consumer warps
     unsigned done_units;                 // finished units (the warp that finishes the last one sums usum[] in order)
@@ -173,7 +171,8 @@ SD_HD SdBlkHdrLane sd_blk_hdr_lane(const SdBlkParams &P, const uint64_t *W, uint
 // second half, after the warp-wide sums base = sum(term), dpre = sum(d), actmask = ballot(act).
 // Entry order: partner tiles beyond L2 reach (q < qfar; on other GPUs when sharded) before the near ones.
 // (Round 2 tried the remote tiles last with an L1 prefetch at the start of the item: peer-memory prefetches are
-// pathologically slow -- 237 ms per L = 32 apply on 2 GPUs instead of 3.4 -- so remote tiles are plain .cg loads.)
+// pathologically slow -- 237 ms per L = 32 apply on 2 GPUs instead of 3.4 -- so remote tiles are plain .cg loads; an
+// L2 prefetch of the later LOCAL entries at the start of the item cost 10 % too: profiles/round2_h_ab.txt.)
 template <int NC, class HDR = SdBlkHdr>
 SD_HD void sd_blk_hdr_fill(const SdBlkParams &P, const SdBlkHdrLane &l, uint64_t Pb, uint64_t key, uint64_t base, double dpre,
                            unsigned actmask, int qfar, int q, HDR &H, const SdVecView &psi) {
@@ -187,16 +186,8 @@ SD_HD void sd_blk_hdr_fill(const SdBlkParams &P, const SdBlkHdrLane &l, uint64_t
         const uint64_t nbase = bit ? base + dl : base - dl;
         const unsigned lt = (1u << q) - 1u;
         const int slot = ((farmask >> q) & 1u) ? SD_POPC32(actmask & farmask & lt) : nfar + SD_POPC32(actmask & ~farmask & lt);
-        const int own = sd_blk_owner(P.shards, nbase);
-        H.nb[slot].p = psi.base[own] + (size_t)NC * nbase;
+        H.nb[slot].p = psi.base[sd_blk_owner(P.shards, nbase)] + (size_t)NC * nbase;
         H.nb[slot].J = P.Jhop[q];
-        if (own != P.shards.rank) {
-#if defined(__CUDA_ARCH__)
-            atomicOr(&H.remote, 1ULL << slot);
-#else
-            H.remote |= 1ULL << slot;
-#endif
-        }
     }
     if (q == A - 1) {                                             // prefix|mid crossing bond
         const int jsx = bit ? js + 1 : js - 1;
@@ -246,8 +237,6 @@ __device__ __forceinline__ void sd_blk_make_hdr(const SdBlkParams &P, const uint
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dpre += __shfl_xor_sync(0xffffffffu, dpre, o);
     const unsigned actmask = __ballot_sync(0xffffffffu, l.act);
-    if (lane == 0) H.remote = 0ULL;
-    __syncwarp();
     sd_blk_hdr_fill<NC, HDR>(P, l, Pb, key, base, dpre, actmask, qfar, (int)lane, H, psi);
 }
 #endif
@@ -265,7 +254,6 @@ inline void sd_blk_hdr_host(const SdBlkParams &P, const uint64_t *W, uint64_t ke
         dpre += lanes[q].d;
         if (lanes[q].act) actmask |= 1u << q;
     }
-    H.remote = 0ULL;
     for (int q = 0; q < 32; ++q) sd_blk_hdr_fill<NC>(P, lanes[q], Pb, key, base, dpre, actmask, qfar, q, H, psi);
 }
 
@@ -289,13 +277,6 @@ SD_HD double2 sd_blk_ldg(const double *p) {
     v.x = p[0]; v.y = p[1];
 #endif
     return v;
-}
-SD_HD void sd_blk_prefetch_l2(const double *p) {
-#if defined(__CUDA_ARCH__)
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-#else
-    (void)p;
-#endif
 }
 SD_HD double2 sd_blk_ldg_half(const double *p) {
     double2 v;
@@ -484,10 +465,10 @@ __device__ __forceinline__ void sd_blk_item_reduce(SdBlkHdr &H, const SdEpi &epi
         if (lane == 0) H.usum[s][un] = w;
     }
     if (lane == 0) {
-        if (!epi.dbg_nofence) __threadfence_block();
+        __threadfence_block();
         const unsigned done = atomicAdd(&H.done_units, 1u);
         if (done + 1 == nunits) {                              // last item of the tile: ordered sum
-            if (!epi.dbg_nofence) __threadfence_block();
+            __threadfence_block();
             for (int s = 0; s < SD_NSLOT; ++s) {
                 if (!((slotmask >> s) & 1)) continue;
                 double t = 0.0;

@@ -158,7 +158,6 @@ struct SdEpi {
     double *acc;             // optional psi_t accumulation
     double *partials;        // [SD_NSLOT * nparts]
     unsigned nparts;
-    int dbg_nofence;         // (A/B knob SD_BLK_NOFENCE, to be removed) skip the CTA fences of the per-item reduction protocol
 };
 
 template <int NC>
