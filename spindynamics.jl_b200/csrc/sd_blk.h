@@ -125,7 +125,6 @@ struct alignas(16) SdBlkHdr {
     int ntot;                            // nnb + 1 if the prefix|mid crossing bond is active: entry nnb of nb[]
     int bP;                              // last prefix bit
     unsigned next_unit;                  // work counter of the consumer warps
-    unsigned done_units;                 // finished units (the warp that finishes the last one sums usum[] in order)
     unsigned tile_index;                 // key - key_lo (slot of the per-tile partial sums)
     double dP[2];                        // prefix diag + prefix|mid zz, by first mid bit
     double Jx;                           // hop coefficient of the prefix|mid bond (0: none)
@@ -220,7 +219,6 @@ SD_HD void sd_blk_hdr_fill(const SdBlkParams &P, const SdBlkHdrLane &l, uint64_t
             H.ntot = ntot;
         }
         H.next_unit = 0;
-        H.done_units = 0;
         H.tile_index = (unsigned)(key - P.key_lo);
     }
 }
@@ -409,10 +407,25 @@ __device__ __forceinline__ void sd_bulk_g2s(void *dst, const void *src, unsigned
                  ::"r"(sd_smem_u32(dst)), "l"(src), "r"(bytes), "r"(sd_smem_u32(bar)) : "memory");
 }
 // ------------------------------------------------------------------ producer warp and reduction tail (kernel: sd_blkl.h)
+// Fused reductions, deterministic and without fences in the consumer warps: lane 0 of a consumer warp leaves the warp sum
+// of each item in the tile header (usum[slot][item]) and releases the buffer with its usual mbarrier arrive (release
+// semantics); the producer warp, which acquires the buffer through the same mbarrier before it reuses it, adds the item
+// sums in item order and writes the tile's partial sums.  (Round 2: a __threadfence_block + atomic counter per item in
+// the consumers cost 22 % of a Lanczos step -- the fence waits for the item's global stores.)
+template <int NC>
+__device__ __forceinline__ void sd_blk_flush_sums(const SdBlkSmem &S, SdBlkHdr &H, const SdEpi &epi, int slotmask, unsigned lane) {
+    if (H.valid == 1 && lane < SD_NSLOT && ((slotmask >> lane) & 1)) {
+        const unsigned nunits = S.js[H.js].nunits[NC - 1];
+        double t = 0.0;
+        for (unsigned j = 0; j < nunits; ++j) t += ((volatile double *)H.usum[lane])[j];
+        epi.partials[(size_t)lane * epi.nparts + H.tile_index] = t;
+    }
+    __syncwarp();
+}
 // producer warp: tile keys from the global counter, tile headers, TMA of the own tiles
 template <int NC>
 __device__ __forceinline__ void sd_blk_producer(const SdBlkParams &P, const SdBlkSmem &S, const SdVecView &psi, int qfar,
-                                                unsigned long long *tile_ctr, unsigned lane) {
+                                                unsigned long long *tile_ctr, unsigned lane, const SdEpi &epi, int slotmask) {
     const int nbuf = P.nbuf;
     const size_t tile_doubles = (size_t)P.cap * NC;
     for (unsigned i = 0;; ++i) {
@@ -435,10 +448,19 @@ __device__ __forceinline__ void sd_blk_producer(const SdBlkParams &P, const SdBl
         }
         sd_mbar_wait(&S.empty[b], (round & 1u) ^ 1u);          // consumers released this buffer
         SdBlkHdr &H = S.hdr[b];
+        if (slotmask && i >= (unsigned)nbuf) sd_blk_flush_sums<NC>(S, H, epi, slotmask, lane);   // of the tile that used this buffer
         if (key >= P.key_hi) {
             if (lane == 0) { H.valid = -1; }
             __syncwarp();
             if (lane == 0) sd_mbar_arrive(&S.full[b]);
+            // the tiles still in the other buffers: wait until their consumers are done, then their sums
+            for (unsigned k = 1; slotmask && k < (unsigned)nbuf; ++k) {
+                const unsigned ii = i + k;
+                if (ii < (unsigned)nbuf) continue;                 // that buffer never held a tile
+                const int bb = (int)(ii % (unsigned)nbuf);
+                sd_mbar_wait(&S.empty[bb], ((ii / (unsigned)nbuf) & 1u) ^ 1u);
+                sd_blk_flush_sums<NC>(S, S.hdr[bb], epi, slotmask, lane);
+            }
             break;
         }
         sd_blk_make_hdr<NC>(P, S.W, key, H, psi, qfar, lane);
@@ -453,9 +475,8 @@ __device__ __forceinline__ void sd_blk_producer(const SdBlkParams &P, const SdBl
             sd_bulk_g2s(dst + o, src + o, (bytes - o < CH) ? bytes - o : CH, &S.full[b]);
     }
 }
-// per-item tail of a consumer warp: warp sums of the fused reductions, ordered per-tile sum by the last item
-__device__ __forceinline__ void sd_blk_item_reduce(SdBlkHdr &H, const SdEpi &epi, int slotmask, unsigned un, unsigned nunits,
-                                                   const double (&red)[SD_NSLOT], unsigned lane) {
+// per-item tail of a consumer warp: warp sums of the fused reductions into the tile header (see sd_blk_flush_sums)
+__device__ __forceinline__ void sd_blk_item_reduce(SdBlkHdr &H, int slotmask, unsigned un, const double (&red)[SD_NSLOT], unsigned lane) {
 #pragma unroll
     for (int s = 0; s < SD_NSLOT; ++s) {
         if (!((slotmask >> s) & 1)) continue;
@@ -463,19 +484,6 @@ __device__ __forceinline__ void sd_blk_item_reduce(SdBlkHdr &H, const SdEpi &epi
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) w += __shfl_down_sync(0xffffffffu, w, o);
         if (lane == 0) H.usum[s][un] = w;
-    }
-    if (lane == 0) {
-        __threadfence_block();
-        const unsigned done = atomicAdd(&H.done_units, 1u);
-        if (done + 1 == nunits) {                              // last item of the tile: ordered sum
-            __threadfence_block();
-            for (int s = 0; s < SD_NSLOT; ++s) {
-                if (!((slotmask >> s) & 1)) continue;
-                double t = 0.0;
-                for (unsigned j = 0; j < nunits; ++j) t += ((volatile double *)H.usum[s])[j];
-                epi.partials[(size_t)s * epi.nparts + H.tile_index] = t;
-            }
-        }
     }
 }
 

@@ -45,13 +45,9 @@ SD_BLKL_FN void sd_blkl_ctx_init(const SdEpi &epi) {
     SD_SH.hs = epi.hscale_dev ? epi.hscale / sqrt(*epi.hscale_dev) : epi.hscale;
 }
 
-// AFTER: called by ALL 32 lanes of the warp (converged) between the epilogue arithmetic and the stores of the fused
-// (non-PLAIN) variants: the kernel's per-item reduction protocol (warp shuffles + shared-memory bookkeeping with CTA
-// fences) runs there, i.e. BEFORE this item's global stores are issued -- a fence behind them waits for the stores
-// (measured: 1300 -> 1018 ms for a 20-step L = 32 ground state).
-template <int NC, int JT, int S0, bool PLAIN, class AFTER>
+template <int NC, int JT, int S0, bool PLAIN>
 SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdEpi &E, double *out_local, const SdBlkHdr &H, const double *tb, uint32_t u,
-                             double (&red)[SD_NSLOT], AFTER &&after) {
+                             double (&red)[SD_NSLOT]) {
     constexpr int T = SD_BLK_T, M = SD_BLK_M;
     constexpr int NT = sd_cbinom(T, JT);
     constexpr int NO = NC == 1 ? (NT + 1) / 2 : NT;                  // slots of the whole block
@@ -62,8 +58,7 @@ SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdEpi &E, double *out_l
     static_assert(SD_BLK_T == 5 && (NC == 2 || S0 == 0) && (S0 == 0 || (S0 == 5 && NT == 10)), "chunking is written for T = 5");
     const SdBlkJs &I = SD_SH.js[H.js];
     const SdBlkCls cls = I.cls[JT];
-    const bool live = u < cls.nblk;                                  // lanes beyond the class's last mid configuration idle
-    if (PLAIN && !live) return;
+    if (u >= cls.nblk) return;
     const uint32_t ss = 2u * cls.pitch;                              // doubles between slots (both dtypes)
     const uint32_t off0 = cls.cb * NC + 2u * u;                      // doubles, slot 0 of the block
     uint32_t o[EC];                                                  // doubles, slot s of the chunk (half slot: its plain row)
@@ -72,9 +67,6 @@ SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdEpi &E, double *out_l
     double2 acc[EC], t0[EC], t1[EC];
 #pragma unroll
     for (int s = 0; s < EC; ++s) acc[s] = t0[s] = t1[s] = make_double2(0.0, 0.0);   // t0/t1: conditionally loaded below; left undefined they end up on the stack
-    const uint64_t ld0 = (H.base - P.shards.pstart[P.shards.rank]) * NC;  // doubles from the start of the local shard
-    double *ob = out_local + ld0;
-    if (live) {
 #define SD_LEAN_LOAD(t_, p_)                                                                  \
     do {                                                                                      \
         const double *q_ = (p_);                                                              \
@@ -187,8 +179,16 @@ SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdEpi &E, double *out_l
         }
 #undef SD_LEAN_CROSS
     }
-    // ---- epilogue (fused variants: results back into acc, reductions into red)
-    if (!PLAIN) {
+    // ---- epilogue + store
+    const uint64_t ld0 = (H.base - P.shards.pstart[P.shards.rank]) * NC;  // doubles from the start of the local shard
+    double *ob = out_local + ld0;
+    if (PLAIN) {
+#pragma unroll
+        for (int s = 0; s < EC; ++s) {
+            if (HALF && s == EC - 1) sd_blk_stg_half(ob + o[s], acc[s].x);
+            else sd_blk_stg(ob + o[s], acc[s]);
+        }
+    } else {
         const double hs = SD_SH.hs;
 #pragma unroll
         for (int s = 0; s < EC; ++s) {
@@ -196,52 +196,45 @@ SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdEpi &E, double *out_l
             if (HALF && s == EC - 1) {
                 SdVal<1> hh, pp;
                 hh.c[0] = acc[s].x; pp.c[0] = tb[o[s]];
-                acc[s].x = sd_epilogue_hs<1>(E, hs, hh, pp, ld, red).c[0];
+                const SdVal<1> r0 = sd_epilogue_hs<1>(E, hs, hh, pp, ld, red);
+                sd_blk_stg_half(ob + o[s], r0.c[0]);
                 continue;
             }
             const double2 p = *(const double2 *)(tb + o[s]);
+            double2 r;
             if (NC == 2) {
                 SdVal<2> hh, pp;
                 hh.c[0] = acc[s].x; hh.c[1] = acc[s].y; pp.c[0] = p.x; pp.c[1] = p.y;
                 const SdVal<2> rr = sd_epilogue_hs<2>(E, hs, hh, pp, ld / 2, red);
-                acc[s] = make_double2(rr.c[0], rr.c[1]);
+                r = make_double2(rr.c[0], rr.c[1]);
             } else {
                 SdVal<1> hh, pp;
                 hh.c[0] = acc[s].x; pp.c[0] = p.x;
                 const SdVal<1> r0 = sd_epilogue_hs<1>(E, hs, hh, pp, ld, red);
                 hh.c[0] = acc[s].y; pp.c[0] = p.y;
                 const SdVal<1> r1 = sd_epilogue_hs<1>(E, hs, hh, pp, ld + 1, red);
-                acc[s] = make_double2(r0.c[0], r1.c[0]);
+                r = make_double2(r0.c[0], r1.c[0]);
             }
-        }
-    }
-    }   // if (live)
-    if (!PLAIN) after(red);                                          // all lanes, converged; before the stores
-    // ---- store (evict-first: out must not displace psi in L2)
-    if (live) {
-#pragma unroll
-        for (int s = 0; s < EC; ++s) {
-            if (HALF && s == EC - 1) sd_blk_stg_half(ob + o[s], acc[s].x);
-            else sd_blk_stg(ob + o[s], acc[s]);
+            sd_blk_stg(ob + o[s], r);                                 // evict-first like the plain path: out must not displace psi in L2
         }
     }
 }
-template <int NC, bool PLAIN, class AFTER>
+template <int NC, bool PLAIN>
 SD_BLKL_FN void sd_blkl_dispatch(const SdBlkParams &P, const SdEpi &E, double *out_local, const SdBlkHdr &H, const double *tb, unsigned code, uint32_t u,
-                                double (&red)[SD_NSLOT], AFTER &&after) {
+                                double (&red)[SD_NSLOT]) {
     const int jt = (int)(code >> 12);
     const bool hi = ((code >> 8) & 0xFu) != 0;                       // c128, classes of 10: second chunk of five
     switch (jt) {
-        case 0: sd_blkl_item<NC, 0, 0, PLAIN>(P, E, out_local, H, tb, u, red, after); break;
-        case 1: sd_blkl_item<NC, 1, 0, PLAIN>(P, E, out_local, H, tb, u, red, after); break;
+        case 0: sd_blkl_item<NC, 0, 0, PLAIN>(P, E, out_local, H, tb, u, red); break;
+        case 1: sd_blkl_item<NC, 1, 0, PLAIN>(P, E, out_local, H, tb, u, red); break;
         case 2:
-            if constexpr (NC == 2) { if (hi) { sd_blkl_item<NC, 2, 5, PLAIN>(P, E, out_local, H, tb, u, red, after); break; } }
-            sd_blkl_item<NC, 2, 0, PLAIN>(P, E, out_local, H, tb, u, red, after); break;
+            if constexpr (NC == 2) { if (hi) { sd_blkl_item<NC, 2, 5, PLAIN>(P, E, out_local, H, tb, u, red); break; } }
+            sd_blkl_item<NC, 2, 0, PLAIN>(P, E, out_local, H, tb, u, red); break;
         case 3:
-            if constexpr (NC == 2) { if (hi) { sd_blkl_item<NC, 3, 5, PLAIN>(P, E, out_local, H, tb, u, red, after); break; } }
-            sd_blkl_item<NC, 3, 0, PLAIN>(P, E, out_local, H, tb, u, red, after); break;
-        case 4: sd_blkl_item<NC, 4, 0, PLAIN>(P, E, out_local, H, tb, u, red, after); break;
-        default: sd_blkl_item<NC, 5, 0, PLAIN>(P, E, out_local, H, tb, u, red, after); break;
+            if constexpr (NC == 2) { if (hi) { sd_blkl_item<NC, 3, 5, PLAIN>(P, E, out_local, H, tb, u, red); break; } }
+            sd_blkl_item<NC, 3, 0, PLAIN>(P, E, out_local, H, tb, u, red); break;
+        case 4: sd_blkl_item<NC, 4, 0, PLAIN>(P, E, out_local, H, tb, u, red); break;
+        default: sd_blkl_item<NC, 5, 0, PLAIN>(P, E, out_local, H, tb, u, red); break;
     }
 }
 
@@ -276,7 +269,7 @@ sd_blkl_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constan
         SdBlkSmem S;
         S.full = SD_SH.full; S.empty = SD_SH.empty; S.hdr = SD_SH.hdr; S.W = P.W; S.js = SD_SH.js;
         S.tiles = (double *)sd_blk_smem;
-        sd_blk_producer<NC>(P, S, psi, qfar, tile_ctr, lane);
+        sd_blk_producer<NC>(P, S, psi, qfar, tile_ctr, lane, epi, PLAIN ? 0 : sd_epi_slotmask(epi.red));
     } else {
         const int slotmask = PLAIN ? 0 : sd_epi_slotmask(epi.red);
         unsigned b = 0, phase = 0;
@@ -294,8 +287,8 @@ sd_blkl_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constan
                 const unsigned code = SD_SH.units[H.js * SD_BLK_MAXUNITS + un];
                 const uint32_t u = (code & 0xFFu) * 32u + lane;      // the lane's mid configuration
                 double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
-                sd_blkl_dispatch<NC, PLAIN>(P, epi, out_local, H, tb, code, u, red,
-                                            [&](const double (&r)[SD_NSLOT]) { if (slotmask) sd_blk_item_reduce(H, epi, slotmask, un, nunits, r, lane); });
+                sd_blkl_dispatch<NC, PLAIN>(P, epi, out_local, H, tb, code, u, red);
+                if (!PLAIN && slotmask) sd_blk_item_reduce(H, slotmask, un, red, lane);
             }
             __syncwarp();
             if (lane == 0) sd_mbar_arrive(&SD_SH.empty[b]);

@@ -46,9 +46,12 @@ def test_config1_sqw_within_the_oracles_own_rounding_envelope():
         assert np.allclose(a_gpu, a_ref, rtol=1e-9, atol=1e-10) and np.allclose(b_gpu, b_ref, rtol=1e-9, atol=1e-10), (a_gpu - a_ref, b_gpu - b_ref)
 
 
-@pytest.mark.parametrize("lanc_m", [20])
+@pytest.mark.parametrize("lanc_m", [10])
 def test_sqw_tight_parity_below_the_noise_threshold(lanc_m):
-    """Before Ritz values converge the recurrence is well conditioned: 1e-9 relative, the north-star figure."""
+    """Before Ritz values converge the recurrence is well conditioned: 1e-9 relative, the north-star figure.  The oracle's
+    own sensitivity to 1e-16 input noise for this very setup (ground-state-derived start vectors converge fast) is
+    4e-14 / 9e-14 / 2e-12 / 4e-10 / 3e-8 at lanc_m = 8 / 10 / 12 / 16 / 20 and ~5e-5 at 100, so the tight bar is asserted
+    at lanc_m = 10 and the measured envelope above takes over beyond."""
     L, nup = 16, 8
     w = np.linspace(0.0, 5.0, 100)
     om = orc.XXZChain(L, nup=nup)
