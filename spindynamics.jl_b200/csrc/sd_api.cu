@@ -1251,14 +1251,16 @@ static int sd_blk_launch_range(sd_model *m, int nc, const SdBlkParams &P, const 
         SD_CUDA(cudaFuncSetAttribute(KERNEL_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
         KERNEL_<<<grid, THREADS_, smem, c->stream>>>(P, view, out_local, epi, qfar, c->d_tilectr);           \
     } while (0)
-#define SD_HL_LEAN(NC_, PLAIN_)                                                                              \
+#define SD_HL_LEAN(NC_, EK_)                                                                                 \
     do {                                                                                                     \
-        if (m->blk.threads == 512) SD_HL((sd_blkl_apply_kernel<NC_, PLAIN_, 512>), 512);                     \
-        else if (m->blk.threads == 768) SD_HL((sd_blkl_apply_kernel<NC_, PLAIN_, 768>), 768);                \
-        else SD_HL((sd_blkl_apply_kernel<NC_, PLAIN_, 640>), 640);                                           \
+        if (m->blk.threads == 512) SD_HL((sd_blkl_apply_kernel<NC_, EK_, 512>), 512);                        \
+        else if (m->blk.threads == 768) SD_HL((sd_blkl_apply_kernel<NC_, EK_, 768>), 768);                   \
+        else SD_HL((sd_blkl_apply_kernel<NC_, EK_, 640>), 640);                                              \
     } while (0)
-    if (nc == 1) { if (plain) SD_HL_LEAN(1, true); else SD_HL_LEAN(1, false); }
-    else { if (plain) SD_HL_LEAN(2, true); else SD_HL_LEAN(2, false); }
+    // epilogue kind (sd_blkl.h): 0 plain, 1 Lanczos (hscale + fused <psi, out>), 2 generic
+    const int ek = plain ? 0 : ((epi.mode == SD_EPI_PLAIN && epi.red == SD_RED_DOT_SELF && !epi.acc) ? 1 : 2);
+    if (nc == 1) { if (ek == 0) SD_HL_LEAN(1, 0); else if (ek == 1) SD_HL_LEAN(1, 1); else SD_HL_LEAN(1, 2); }
+    else { if (ek == 0) SD_HL_LEAN(2, 0); else if (ek == 1) SD_HL_LEAN(2, 1); else SD_HL_LEAN(2, 2); }
 #undef SD_HL_LEAN
 #undef SD_HL
     return sd_launch_check(c, "sd_blkl_apply_kernel");
@@ -1928,14 +1930,50 @@ int sd_kpm_moments(sd_model *m, const sd_vec *phi, int M, double a, double b, do
         SD_TRY(sd_fetch(c, 0, 4, r));
         mu[1] = r[2];
     }
-    for (int n = 2; n < M; ++n) {                                           // :109-126
-        sd_complex zero = {0, 0};
-        SD_TRY(sd_cheb_step_impl(m, vp, vc, vp, a, b, phi, nullptr, zero, 0));   // v_next overwrites v_prev
-        SD_TRY(sd_fetch(c, 0, 4, r));
-        mu[n] = r[2];
-        const double nv = sqrt(r[3]);
-        if (nv > 1e3) SD_TRY(sd_divide_impl(vp, vp, sd_host_scalar(nv, 0)));   // :118-121
-        std::swap(vp, vc);
+    // :109-126.  The reductions of moment n stay on the device (d_scal[SD_HIST + 8 (n mod SD_HIST_MAX) ..]) and are fetched
+    // 32 moments at a time: no host synchronisation per moment.  The reference renormalises v_next when ||v_next|| > 1e3
+    // (:117-121), which only happens with wrong rescaling bounds; the norms arrive with the same block, and the first
+    // one above the threshold sends the rest of the loop down the step-by-step path from the vectors of that moment --
+    // which are gone by then, so the speculative block is re-run from a checkpoint taken at its start.
+    SdVecGuard CK;
+    sd_vec *cp = nullptr, *cc = nullptr;                                    // checkpoint of (v_prev, v_curr) at the block start
+    const int BLK = 32;
+    int n = 2;
+    bool careful = false;
+    while (n < M) {
+        const int n1 = std::min(M, n + BLK);
+        if (!careful) {
+            if (!cp) { SD_TRY(CK.make(m, SD_C128, &cp)); SD_TRY(CK.make(m, SD_C128, &cc)); }
+            SD_TRY(sd_vec_copy(cp, vp)); SD_TRY(sd_vec_copy(cc, vc));
+            sd_vec *p0 = vp, *c0 = vc;
+            for (int t = n; t < n1; ++t) {
+                sd_complex zero = {0, 0};
+                SD_TRY(sd_cheb_step_impl(m, vp, vc, vp, a, b, phi, nullptr, zero, SD_HIST + 8 * (t - n)));   // v_next overwrites v_prev
+                std::swap(vp, vc);
+            }
+            std::vector<double> hh((size_t)8 * (n1 - n));
+            SD_TRY(sd_fetch(c, SD_HIST, 8 * (n1 - n), hh.data()));
+            bool blown = false;
+            for (int t = n; t < n1; ++t) if (sqrt(hh[8 * (t - n) + 3]) > 1e3) blown = true;
+            if (!blown) {
+                for (int t = n; t < n1; ++t) mu[t] = hh[8 * (t - n) + 2];
+                n = n1;
+                continue;
+            }
+            vp = p0; vc = c0;                                               // restore and redo this block step by step
+            SD_TRY(sd_vec_copy(vp, cp)); SD_TRY(sd_vec_copy(vc, cc));
+            careful = true;
+        }
+        for (int t = n; t < n1; ++t) {
+            sd_complex zero = {0, 0};
+            SD_TRY(sd_cheb_step_impl(m, vp, vc, vp, a, b, phi, nullptr, zero, 0));
+            SD_TRY(sd_fetch(c, 0, 4, r));
+            mu[t] = r[2];
+            const double nv = sqrt(r[3]);
+            if (nv > 1e3) SD_TRY(sd_divide_impl(vp, vp, sd_host_scalar(nv, 0)));   // :118-121
+            std::swap(vp, vc);
+        }
+        n = n1;
     }
     return SD_OK;
 }

@@ -45,9 +45,13 @@ SD_BLKL_FN void sd_blkl_ctx_init(const SdEpi &epi) {
     SD_SH.hs = epi.hscale_dev ? epi.hscale / sqrt(*epi.hscale_dev) : epi.hscale;
 }
 
-template <int NC, int JT, int S0, bool PLAIN>
+// EK: epilogue kind, compile-time so that each instantiation only carries the code it runs (the kernel is instruction-
+// cache sensitive): 0 plain out = H psi; 1 Lanczos: out = hs * H psi with the fused <psi, out> (every Lanczos flavour);
+// 2 generic (rescaled / Chebyshev step, psi_t accumulation, phi dot, norm: sd_epilogue_hs).
+template <int NC, int JT, int S0, int EK>
 SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdEpi &E, double *out_local, const SdBlkHdr &H, const double *tb, uint32_t u,
                              double (&red)[SD_NSLOT]) {
+    constexpr bool PLAIN = EK == 0;
     constexpr int T = SD_BLK_T, M = SD_BLK_M;
     constexpr int NT = sd_cbinom(T, JT);
     constexpr int NO = NC == 1 ? (NT + 1) / 2 : NT;                  // slots of the whole block
@@ -121,9 +125,15 @@ SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdEpi &E, double *out_l
     // ---- mid-internal hops: the whole block moves to block nb[pm] of the same class
     {
         const double *cbp = tb + cls.cb * NC + (uint32_t)S0 * ss;
-#pragma unroll
-        for (int pm = 0; pm + 1 < M; ++pm) {                          // fully unrolled: byte extract and J are compile-time selected
-            const unsigned nbu = ((pm < 4 ? it.x : (pm < 8 ? it.y : it.z)) >> (8 * (pm & 3))) & 0xFFu;
+        // a loop, not unrolled: nine unrolled copies in each of the six class bodies are 20 KB of code, and the kernel is
+        // instruction-cache sensitive (round 2: 54 KB plain / 99 KB fused -> "no instruction" was the top stall of the fused one)
+        uint64_t lo = (uint64_t)it.x | ((uint64_t)it.y << 32);
+        uint32_t hi = it.z;
+#pragma unroll 1
+        for (int pm = 0; pm + 1 < M; ++pm) {
+            const unsigned nbu = (unsigned)(lo & 0xFFu);
+            lo = (lo >> 8) | ((uint64_t)hi << 56);
+            hi >>= 8;
             if (nbu != 0xFFu) {
                 const double J = P.Jmid[pm];
                 const double *sp = cbp + 2u * nbu;
@@ -188,6 +198,22 @@ SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdEpi &E, double *out_l
             if (HALF && s == EC - 1) sd_blk_stg_half(ob + o[s], acc[s].x);
             else sd_blk_stg(ob + o[s], acc[s]);
         }
+    } else if (EK == 1) {                                            // out = hs * H psi, red[0..1] += conj(psi) out
+        const double hs = SD_SH.hs;
+#pragma unroll
+        for (int s = 0; s < EC; ++s) {
+            if (HALF && s == EC - 1) {
+                const double r = hs * acc[s].x;
+                red[0] += tb[o[s]] * r;
+                sd_blk_stg_half(ob + o[s], r);
+                continue;
+            }
+            const double2 p = *(const double2 *)(tb + o[s]);
+            const double2 r = make_double2(hs * acc[s].x, hs * acc[s].y);
+            if (NC == 2) { red[0] += p.x * r.x + p.y * r.y; red[1] += p.x * r.y - p.y * r.x; }
+            else red[0] += p.x * r.x + p.y * r.y;
+            sd_blk_stg(ob + o[s], r);
+        }
     } else {
         const double hs = SD_SH.hs;
 #pragma unroll
@@ -219,22 +245,22 @@ SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdEpi &E, double *out_l
         }
     }
 }
-template <int NC, bool PLAIN>
+template <int NC, int EK>
 SD_BLKL_FN void sd_blkl_dispatch(const SdBlkParams &P, const SdEpi &E, double *out_local, const SdBlkHdr &H, const double *tb, unsigned code, uint32_t u,
                                 double (&red)[SD_NSLOT]) {
     const int jt = (int)(code >> 12);
     const bool hi = ((code >> 8) & 0xFu) != 0;                       // c128, classes of 10: second chunk of five
     switch (jt) {
-        case 0: sd_blkl_item<NC, 0, 0, PLAIN>(P, E, out_local, H, tb, u, red); break;
-        case 1: sd_blkl_item<NC, 1, 0, PLAIN>(P, E, out_local, H, tb, u, red); break;
+        case 0: sd_blkl_item<NC, 0, 0, EK>(P, E, out_local, H, tb, u, red); break;
+        case 1: sd_blkl_item<NC, 1, 0, EK>(P, E, out_local, H, tb, u, red); break;
         case 2:
-            if constexpr (NC == 2) { if (hi) { sd_blkl_item<NC, 2, 5, PLAIN>(P, E, out_local, H, tb, u, red); break; } }
-            sd_blkl_item<NC, 2, 0, PLAIN>(P, E, out_local, H, tb, u, red); break;
+            if constexpr (NC == 2) { if (hi) { sd_blkl_item<NC, 2, 5, EK>(P, E, out_local, H, tb, u, red); break; } }
+            sd_blkl_item<NC, 2, 0, EK>(P, E, out_local, H, tb, u, red); break;
         case 3:
-            if constexpr (NC == 2) { if (hi) { sd_blkl_item<NC, 3, 5, PLAIN>(P, E, out_local, H, tb, u, red); break; } }
-            sd_blkl_item<NC, 3, 0, PLAIN>(P, E, out_local, H, tb, u, red); break;
-        case 4: sd_blkl_item<NC, 4, 0, PLAIN>(P, E, out_local, H, tb, u, red); break;
-        default: sd_blkl_item<NC, 5, 0, PLAIN>(P, E, out_local, H, tb, u, red); break;
+            if constexpr (NC == 2) { if (hi) { sd_blkl_item<NC, 3, 5, EK>(P, E, out_local, H, tb, u, red); break; } }
+            sd_blkl_item<NC, 3, 0, EK>(P, E, out_local, H, tb, u, red); break;
+        case 4: sd_blkl_item<NC, 4, 0, EK>(P, E, out_local, H, tb, u, red); break;
+        default: sd_blkl_item<NC, 5, 0, EK>(P, E, out_local, H, tb, u, red); break;
     }
 }
 
@@ -242,11 +268,12 @@ SD_BLKL_FN void sd_blkl_dispatch(const SdBlkParams &P, const SdEpi &E, double *o
 #if defined(__CUDACC__)
 // grid = one persistent CTA per SM of NTHR threads; the last warp is the producer (sd_blk_producer: tile keys from the global
 // counter or the order table, headers, TMA of the own tiles), the others pull (tile, unit) items.
-template <int NC, bool PLAIN, int NTHR>
+template <int NC, int EK, int NTHR>
 __global__ void __launch_bounds__(NTHR, 1)
 sd_blkl_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constant__ SdVecView psi, double *out_local,
                      const __grid_constant__ SdEpi epi, int qfar, unsigned long long *tile_ctr) {
     extern __shared__ __align__(128) unsigned char sd_blk_smem[];    // [nbuf][cap * NC] doubles: the tile buffers
+    constexpr bool PLAIN = EK == 0;
     const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
     const unsigned nbuf = (unsigned)P.nbuf;
     constexpr unsigned NCONS = NTHR / 32 - 1;                        // consumer warps; the last warp is the producer
@@ -287,7 +314,7 @@ sd_blkl_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constan
                 const unsigned code = SD_SH.units[H.js * SD_BLK_MAXUNITS + un];
                 const uint32_t u = (code & 0xFFu) * 32u + lane;      // the lane's mid configuration
                 double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
-                sd_blkl_dispatch<NC, PLAIN>(P, epi, out_local, H, tb, code, u, red);
+                sd_blkl_dispatch<NC, EK>(P, epi, out_local, H, tb, code, u, red);
                 if (!PLAIN && slotmask) sd_blk_item_reduce(H, slotmask, un, red, lane);
             }
             __syncwarp();

@@ -168,18 +168,30 @@ struct SdVal {
 // Applies the epilogue to one element.  `h` is H psi (before hscale `hs`), `p` is
 // psi at the same index, `li` the local element index.  Accumulates the
 // requested reductions into red[SD_NSLOT].
+// The value part of the epilogue for one real component (mode arithmetic incl. the true division of
+// Hamiltonian.jl:296-298): NOT inlined on the device -- sixty inlined copies of the FP64 division sequence made the
+// fused block kernel twice the size of the plain one and instruction-fetch bound.
+#if defined(__CUDACC__)
+#define SD_EPI_VALUE_FN __device__ __noinline__
+#else
+#define SD_EPI_VALUE_FN inline
+#endif
+static SD_EPI_VALUE_FN double sd_epi_value(int mode, double hs, double a, double b, double h, double p, double vprev) {
+    double v = hs * h;
+    if (mode != SD_EPI_PLAIN) {
+        v = (v - b * p) / a;
+        if (mode == SD_EPI_CHEB) v = 2.0 * v - vprev;
+    }
+    return v;
+}
 template <int NC>
 SD_HD SdVal<NC> sd_epilogue_hs(const SdEpi &e, double hs, SdVal<NC> h, SdVal<NC> p, uint64_t li,
                                double (&red)[SD_NSLOT]) {
     SdVal<NC> o;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-        double v = hs * h.c[c];
-        if (e.mode != SD_EPI_PLAIN) {
-            v = (v - e.b * p.c[c]) / e.a;
-            if (e.mode == SD_EPI_CHEB) v = 2.0 * v - e.vprev[li * NC + c];
-        }
-        o.c[c] = v;
+        if (e.mode == SD_EPI_PLAIN) o.c[c] = hs * h.c[c];
+        else o.c[c] = sd_epi_value(e.mode, hs, e.a, e.b, h.c[c], p.c[c], e.mode == SD_EPI_CHEB ? e.vprev[li * NC + c] : 0.0);
     }
     if (e.acc) {
         if (NC == 2) {

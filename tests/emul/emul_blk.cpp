@@ -32,7 +32,7 @@ struct AlignedBuf {                      // 128-byte aligned doubles (the kernel
     ~AlignedBuf() { free(p); }
 };
 
-template <int NC, bool PLAIN>
+template <int NC, int EK>
 void run_tiles(const SdBlkHost &bh, const SdBlkParams &P, const SdVecView &psi, double *out_local, const SdEpi &epi,
                int qfar, double *red_total) {
     AlignedBuf tile;
@@ -63,7 +63,7 @@ void run_tiles(const SdBlkHost &bh, const SdBlkParams &P, const SdVecView &psi, 
             for (unsigned lane = 0; lane < 32; ++lane) {
                 const uint32_t u = (code & 0xFFu) * 32u + lane;
                 double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
-                sd_blkl_dispatch<NC, PLAIN>(P, epi, out_local, H, tile.p, code, u, red);
+                sd_blkl_dispatch<NC, EK>(P, epi, out_local, H, tile.p, code, u, red);
                 for (int s = 0; s < SD_NSLOT; ++s) red_total[s] += red[s];
             }
         }
@@ -149,7 +149,7 @@ int emul_blk_apply(int L, int k, const double *Jhop, const double *Jz, const dou
     if (acc) { to_blk(acc, s_acc, nullptr); epi.acc = s_acc[rank].p; }
     double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
     const bool plain = epi.mode == SD_EPI_PLAIN && epi.red == 0 && !epi.acc && epi.hscale == 1.0;
-#define RUN(NC_, PLAIN_) run_tiles<NC_, PLAIN_>(bh, P, view, o.p, epi, qfar, red)
+#define RUN(NC_, EK_) run_tiles<NC_, EK_>(bh, P, view, o.p, epi, qfar, red)
     // halo mirror: the peers' shards are replaced by NaN-filled mirrors that only hold what the plan copies, chunk by
     // chunk, before the tiles of that chunk run (what sd_apply_blk_halo does with the copy engines and one event per chunk)
     SdShardPlan plan;
@@ -172,8 +172,9 @@ int emul_blk_apply(int L, int k, const double *Jhop, const double *Jz, const dou
                             (size_t)(sg.hi - sg.lo) * NC * sizeof(double));
             P.key_lo = plan.chunk_key[j]; P.key_hi = plan.chunk_key[j + 1];
         }
-        if (NC == 1) { if (plain) RUN(1, true); else RUN(1, false); }
-        else { if (plain) RUN(2, true); else RUN(2, false); }
+        const int ek = plain ? 0 : ((epi.mode == SD_EPI_PLAIN && epi.red == SD_RED_DOT_SELF && !epi.acc) ? 1 : 2);   // as sd_blk_launch_range
+        if (NC == 1) { if (ek == 0) RUN(1, 0); else if (ek == 1) RUN(1, 1); else RUN(1, 2); }
+        else { if (ek == 0) RUN(2, 0); else if (ek == 1) RUN(2, 1); else RUN(2, 2); }
     }
     P.key_lo = klo_all; P.key_hi = khi_all;
 #undef RUN
