@@ -1258,7 +1258,7 @@ static int sd_blk_launch_range(sd_model *m, int nc, const SdBlkParams &P, const 
         else SD_HL((sd_blkl_apply_kernel<NC_, EK_, 640>), 640);                                              \
     } while (0)
     // epilogue kind (sd_blkl.h): 0 plain, 1 Lanczos (hscale + fused <psi, out>), 2 generic
-    const int ek = plain ? 0 : ((epi.mode == SD_EPI_PLAIN && epi.red == SD_RED_DOT_SELF && !epi.acc) ? 1 : 2);
+    const int ek = plain ? 0 : ((epi.mode == SD_EPI_PLAIN && (epi.red == SD_RED_DOT_SELF || epi.red == 0) && !epi.acc) ? 1 : 2);
     if (nc == 1) { if (ek == 0) SD_HL_LEAN(1, 0); else if (ek == 1) SD_HL_LEAN(1, 1); else SD_HL_LEAN(1, 2); }
     else { if (ek == 0) SD_HL_LEAN(2, 0); else if (ek == 1) SD_HL_LEAN(2, 1); else SD_HL_LEAN(2, 2); }
 #undef SD_HL_LEAN

@@ -172,7 +172,7 @@ int emul_blk_apply(int L, int k, const double *Jhop, const double *Jz, const dou
                             (size_t)(sg.hi - sg.lo) * NC * sizeof(double));
             P.key_lo = plan.chunk_key[j]; P.key_hi = plan.chunk_key[j + 1];
         }
-        const int ek = plain ? 0 : ((epi.mode == SD_EPI_PLAIN && epi.red == SD_RED_DOT_SELF && !epi.acc) ? 1 : 2);   // as sd_blk_launch_range
+        const int ek = plain ? 0 : ((epi.mode == SD_EPI_PLAIN && (epi.red == SD_RED_DOT_SELF || epi.red == 0) && !epi.acc) ? 1 : 2);   // as sd_blk_launch_range
         if (NC == 1) { if (ek == 0) RUN(1, 0); else if (ek == 1) RUN(1, 1); else RUN(1, 2); }
         else { if (ek == 0) RUN(2, 0); else if (ek == 1) RUN(2, 1); else RUN(2, 2); }
     }
