@@ -159,6 +159,8 @@ struct SdBlkDev {
     int nbuf[2] = {0, 0};
     size_t smem[2] = {0, 0};
     int qfar[2] = {0, 0};
+    int pfp = 0;                    // SD_BLK_PFP (experiment, SdBlkParams::pfp)
+    int depth = 2;                  // SD_BLKL_DEPTH (experiment, see sd_blk_launch_range)
     int threads = 640;              // CTA size of sd_blkl_apply_kernel (SD_BLKL_THREADS = 512 | 640 | 768, read once at model creation)
     uint32_t *d_order = nullptr;    // breadth-first tile order of this rank's shard (vectors larger than the L2)
     uint32_t norder = 0;
@@ -482,6 +484,8 @@ static int sd_blk_setup(sd_model *m) {
     for (size_t i = 0; i < m->zz_a.size(); ++i) Jz[m->zz_a[i]] += m->zz_J[i];
     if (!sd_blk_build(L, m->k, Jhop.data(), Jz.data(), m->field.data(), b.host)) return SD_OK;
     b.threads = sd_env_int("SD_BLKL_THREADS", 640);
+    b.depth = sd_env_int("SD_BLKL_DEPTH", 2);
+    b.pfp = sd_env_int("SD_BLK_PFP", 0);
     if (b.threads != 512 && b.threads != 768) b.threads = 640;
     for (int w = 0; w < 2; ++w) {
         const int nc = w + 1;
@@ -510,6 +514,7 @@ static SdBlkParams sd_blk_params(const sd_model *m, int nc) {
     SdBlkParams P = m->blk.host.P;
     const sd_ctx *c = m->ctx;
     P.nbuf = m->blk.nbuf[nc - 1];
+    P.pfp = m->blk.pfp;
     P.order = m->blk.d_order; P.norder = m->blk.norder;
     P.key_lo = m->tile[0].keys[c->rank];
     P.key_hi = m->tile[0].keys[c->rank + 1];
@@ -1259,6 +1264,10 @@ static int sd_blk_launch_range(sd_model *m, int nc, const SdBlkParams &P, const 
     } while (0)
     // epilogue kind (sd_blkl.h): 0 plain, 1 Lanczos (hscale + fused <psi, out>), 2 generic
     const int ek = plain ? 0 : ((epi.mode == SD_EPI_PLAIN && (epi.red == SD_RED_DOT_SELF || epi.red == 0) && !epi.acc) ? 1 : 2);
+    // experiment (SD_BLKL_DEPTH = 3 | 4, f64 plain apply only): neighbour streams three / four entries deep on fewer warps
+    if (nc == 1 && ek == 0 && m->blk.depth == 3) SD_HL((sd_blkl_apply_kernel<1, 0, 512, 3>), 512);
+    else if (nc == 1 && ek == 0 && m->blk.depth == 4) SD_HL((sd_blkl_apply_kernel<1, 0, 512, 4>), 512);
+    else
     if (nc == 1) { if (ek == 0) SD_HL_LEAN(1, 0); else if (ek == 1) SD_HL_LEAN(1, 1); else SD_HL_LEAN(1, 2); }
     else { if (ek == 0) SD_HL_LEAN(2, 0); else if (ek == 1) SD_HL_LEAN(2, 1); else SD_HL_LEAN(2, 2); }
 #undef SD_HL_LEAN

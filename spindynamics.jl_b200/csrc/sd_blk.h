@@ -70,6 +70,7 @@ struct SdBlkShards {
 struct SdBlkParams {
     int L, k, A;
     int nbuf;                        // tile buffers in shared memory
+    int pfp;                         // producer L2 prefetch of partner tiles (experiment): bit 0 on, bit 1 one tile late, bit 2 all prefix entries (else the far ones)
     uint64_t key_lo, key_hi;         // tile keys of this launch (this shard)
     double Jhop[SD_MAX_L + 1];       // hop coefficient of bond p (positions p, p+1)
     double Jz[SD_MAX_L + 1];
@@ -473,6 +474,15 @@ __device__ __forceinline__ void sd_blk_producer(const SdBlkParams &P, const SdBl
         constexpr uint32_t CH = 8192;
         for (uint32_t o = lane * CH; o < bytes; o += 32 * CH)
             sd_bulk_g2s(dst + o, src + o, (bytes - o < CH) ? bytes - o : CH, &S.full[b]);
+        if ((P.pfp & 1) && P.shards.world == 1) {              // partner tiles of the prefix bonds have the tile's own js, i.e. its size
+            const SdBlkHdr &Hp = (P.pfp & 2) ? S.hdr[(b + nbuf - 1) % nbuf] : H;
+            if (!(P.pfp & 2) || i > 0) {
+                const int cnt = (P.pfp & 4) ? Hp.nnb : Hp.nfar;
+                const uint32_t pb = S.js[Hp.js].size_pad * (uint32_t)(NC * 8);
+                if ((int)lane < cnt)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(Hp.nb[lane].p), "r"(pb) : "memory");
+            }
+        }
     }
 }
 // per-item tail of a consumer warp: warp sums of the fused reductions into the tile header (see sd_blk_flush_sums)
