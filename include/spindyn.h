@@ -228,6 +228,26 @@ int sd_lanczos_lean(sd_model *model, const sd_vec *v0_f64, int lanc_m, double to
                     int *m_eff, const double *y, sd_vec *out, double *norm2);
 /* compute_chebyshev_moments (KPM_Sqw.jl:95-128): mu[M], phi C128. */
 int sd_kpm_moments(sd_model *model, const sd_vec *phi, int M, double a, double b, double *mu);
+/* q-batched S(q,w) recurrences: the bodies of the Threads.@threads q-loops of lanczos_sqw
+ * (LanczosSqw.jl:65-77) and kpm_sqw (KPM_Sqw.jl:218-253) for nq momenta at once, on one interleaved [state][q]
+ * multi-vector: phi_q = Sz_q_vector(model, psi0, q) (Hamiltonian.jl:307-337) for every q, then ONE fused kernel pair
+ * per Lanczos step (one per Chebyshev moment) for all momenta, per-momentum scalars kept on the device.  psi0 F64 or
+ * C128; 1 <= nq <= 128; single-GPU contexts (SD_ERR_ARG otherwise: loop over q with sd_szq + sd_lanczos_tridiag).
+ * Any model (full / sector basis, arbitrary bond lists).  Needs 3 * 16 * nq' * N bytes of device memory, nq' = nq
+ * rounded up to 2, 3 or 4 times a power of two (SD_ERR_NOMEM if that does not fit: pass fewer momenta per call).
+ *   sd_lanczos_tridiag_szq_batch: lanczos_tridiag (Lanczos.jl:196-246) per momentum.  alpha[c * lanc_m + t],
+ *     beta[c * lanc_m + t] (both nq * lanc_m doubles), m_eff[c] valid entries (0: norm(phi_c) == 0, the reference's
+ *     `continue`), norm_phi[c].
+ *   sd_kpm_moments_szq_batch: compute_chebyshev_moments (KPM_Sqw.jl:95-128) of phi_c / norm(phi_c) per momentum.
+ *     mu[c * M + n]; norm_phi[c] (0: row of zeros).  *blown = 1 if some ||v_next|| exceeded 1e3, where the reference
+ *     renormalises (:117-121, only with wrong rescaling bounds): the moments are then not the reference's -- use the
+ *     per-momentum sd_kpm_moments. */
+int sd_lanczos_tridiag_szq_batch(sd_model *model, const sd_vec *psi0, const double *q, int nq, int lanc_m, double tol,
+                                 double *alpha, double *beta, int *m_eff, double *norm_phi);
+int sd_kpm_moments_szq_batch(sd_model *model, const sd_vec *psi0, const double *q, int nq, int M, double a, double b,
+                             double *mu, double *norm_phi, int *blown);
+/* Free and total device memory of the context's GPU in bytes (sizing the momenta per batch). */
+int sd_ctx_mem_info(sd_ctx *ctx, uint64_t *free_bytes, uint64_t *total_bytes);
 /* krylov_time_evolve's basis build (Krylov.jl:136-173): alpha complex (the
  * reference keeps dot(V_j, w) complex, :155), beta real; host does the small
  * eigen problem and calls sd_lincomb. */

@@ -29,53 +29,20 @@
 #include "sd_bdot.cuh"
 #include "sd_shard_host.h"
 
-#define SD_VERSION 100
+#include "sd_handles.h"
 
 // ----------------------------------------------------------------- errors
 static thread_local char g_err[512] = "";
-static int sd_fail(int code, const char *fmt, ...) {
+int sd_fail(int code, const char *fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
     return code;
 }
-#define SD_CUDA(call)                                                                       \
-    do {                                                                                    \
-        cudaError_t e_ = (call);                                                            \
-        if (e_ != cudaSuccess)                                                              \
-            return sd_fail(e_ == cudaErrorMemoryAllocation ? SD_ERR_NOMEM : SD_ERR_CUDA,    \
-                           "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-    } while (0)
-#define SD_TRY(call)              \
-    do {                          \
-        int r_ = (call);          \
-        if (r_ != SD_OK) return r_; \
-    } while (0)
-#define SD_LOCK(ctxptr) std::lock_guard<std::recursive_mutex> sd_ctx_lock_((ctxptr)->mu)
-#define SD_ARG(cond, ...)                                  \
-    do {                                                   \
-        if (!(cond)) return sd_fail(SD_ERR_ARG, __VA_ARGS__); \
-    } while (0)
-
-// ----------------------------------------------------------------- NCCL (dlopen, only when world > 1)
-typedef struct ncclComm *ncclComm_t;
-typedef struct { char internal[128]; } ncclUniqueId;
-enum { ncclSuccess_ = 0 };
-enum { ncclUint8_ = 1, ncclFloat64_ = 8 };   // ncclDataType_t values (nccl.h)
-enum { ncclSum_ = 0 };
-struct SdNccl {
-    void *h = nullptr;
-    int (*GetUniqueId)(ncclUniqueId *) = nullptr;
-    int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
-    int (*CommDestroy)(ncclComm_t) = nullptr;
-    int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
-    int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
-    const char *(*GetErrorString)(int) = nullptr;
-};
-static SdNccl g_nccl;
+SdNccl g_nccl;
 static std::mutex g_nccl_mu;
-static int sd_nccl_load() {
+int sd_nccl_load() {
     std::lock_guard<std::mutex> lk(g_nccl_mu);
     if (g_nccl.h) return SD_OK;
     const char *names[] = {"libnccl.so.2", "libnccl.so"};
@@ -98,122 +65,6 @@ static int sd_nccl_load() {
     g_nccl.h = h;
     return SD_OK;
 }
-#define SD_NCCL(call)                                                                      \
-    do {                                                                                   \
-        int e_ = (call);                                                                   \
-        if (e_ != 0) return sd_fail(SD_ERR_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString(e_)); \
-    } while (0)
-
-// ----------------------------------------------------------------- handles
-#define SD_NSCAL 4096
-#define SD_HIST 4096                  // d_scal[SD_HIST + 8 j ..]: reductions of Lanczos step j (kept on the device, fetched in blocks)
-#define SD_HIST_MAX 4096             // steps
-struct sd_ctx {
-    // Threading contract: calls on one context serialise.  Every entry point that touches the context's
-    // stream or scratch state takes this lock (recursive: entry points call each other), so the reference's
-    // Threads.@threads q-loops stay correct when they share a context -- they become sequential device work; for
-    // concurrency use one context per host thread (spindyn's q_threads).
-    mutable std::recursive_mutex mu;
-    int device = 0;
-    int rank = 0, world = 1;
-    int sm_count = 148;
-    cudaStream_t stream = nullptr;
-    ncclComm_t comm = nullptr;
-    uint64_t *d_binom = nullptr;
-    double *d_scal = nullptr;       // device scalars [SD_NSCAL]
-    double *h_scal = nullptr;       // pinned mirror
-    double *d_partials = nullptr;
-    size_t partials_cap = 0;        // doubles
-    unsigned char *d_ipc = nullptr; // [(world + 1) * 128] exchange buffer of sd_exchange
-    std::vector<unsigned char> h_ipc;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    uint64_t launches = 0;
-    std::vector<uint64_t> binom;
-    unsigned long long *d_tilectr = nullptr;  // tile counter of the block kernel's dynamic scheduler
-    void *scratch[2] = {nullptr, nullptr};   // rank-ordered staging of block-layout vectors (upload/download/szq)
-    size_t scratch_cap[2] = {0, 0};
-    // ---- cross-rank ordering of sharded vectors (world > 1).  Every rank makes the same API calls in the same order
-    // (SPMD), vector ids are handed out by the collective sd_vec_alloc, so these sets evolve identically on all ranks and
-    // the barriers they trigger pair up.  Both are emptied by every collective (all ranks' earlier kernels have finished).
-    std::vector<uint64_t> dirty_ids;         // vectors written since the last collective: peers must not gather them yet
-    std::vector<uint64_t> read_ids;          // vectors an apply gathered from since the last collective: peers may still read the local shard
-    uint64_t next_vec_id = 1;
-    // ---- deferred release of IPC-exported shards (world > 1): sd_vec_free is LOCAL (finalizers run at different times
-    // on different ranks); a shard is cudaFree'd once every rank has announced the free of that vector id, which the
-    // ranks tell each other inside the next collective sd_vec_alloc / sd_ctx_collect.
-    struct Dead { uint64_t id; double *d; };
-    std::vector<Dead> dead;                  // local shards waiting for the peers to unmap them
-    std::vector<uint64_t> outbox;            // locally freed ids not yet announced
-    std::vector<std::pair<uint64_t, int>> freed_count;   // id -> ranks that announced it
-};
-
-struct SdBlkDev {
-    bool ok = false;
-    SdBlkHost host;
-    uint64_t *d_W = nullptr;
-    SdBlkJs *d_js = nullptr;
-    uint16_t *d_units = nullptr;
-    SdBlkItem *d_items = nullptr;
-    double *d_dmid = nullptr;
-    uint64_t pstart[SD_MAX_WORLD + 1];
-    int nbuf[2] = {0, 0};
-    size_t smem[2] = {0, 0};
-    int qfar[2] = {0, 0};
-    int pfp = 0;                    // SD_BLK_PFP (experiment, SdBlkParams::pfp)
-    int depth = 2;                  // SD_BLKL_DEPTH (experiment, see sd_blk_launch_range)
-    int threads = 640;              // CTA size of sd_blkl_apply_kernel (SD_BLKL_THREADS = 512 | 640 | 768, read once at model creation)
-    uint32_t *d_order = nullptr;    // breadth-first tile order of this rank's shard (vectors larger than the L2)
-    uint32_t norder = 0;
-};
-
-struct SdTileDev {
-    bool ok = false;
-    SdTileHost host;
-    uint32_t cap = 0;
-    size_t smem = 0;
-    void *d_perm = nullptr, *d_items = nullptr, *d_binomM = nullptr;
-    uint64_t keys[SD_MAX_WORLD + 1];
-};
-
-struct sd_model {
-    sd_ctx *ctx = nullptr;
-    int L = 0, k = -1;
-    uint64_t N = 0;
-    std::vector<int> hop_a, hop_b, zz_a, zz_b;
-    std::vector<double> hop_J, zz_J, field;
-    int *d_hop_a = nullptr, *d_hop_b = nullptr, *d_zz_a = nullptr, *d_zz_b = nullptr;
-    double *d_hop_J = nullptr, *d_zz_J = nullptr, *d_field = nullptr;
-    uint64_t *d_linA = nullptr, *d_linB = nullptr;
-    int lin_h = 0;
-    int path = SD_PATH_GENERIC;
-    bool tile_capable = false;
-    int tile_T[2] = {5, 4};
-    int tile_threads = 512;
-    SdTileDev tile[2];              // [0]: F64, [1]: C128
-    SdShardMap shards;
-    SdBlkDev blk;                   // block-layout kernel (sd_blk.h)
-    bool blk_layout = false;        // vectors of this model are stored in block layout
-    int live_vecs = 0;
-    std::vector<sd_vec *> pool;     // idle work vectors of the recurrences (SdVecGuard)
-    bool free_pending = false;      // sd_model_free was called while vectors were alive
-};
-
-struct sd_vec {
-    sd_model *model = nullptr;
-    int dtype = SD_F64, nc = 1;
-    uint64_t local_n = 0;           // STORED elements of the local shard (block layout: padded)
-    uint64_t logical_n = 0;         // basis states of the local shard
-    int layout = 0;                 // 0: rank order, 1: block layout
-    uint64_t id = 0;                // collective allocation number (same on every rank)
-    double *d = nullptr;
-    SdVecView view;
-    void *peer[SD_MAX_WORLD];
-    bool owned = true;
-};
-
-struct sd_vecset {
-    std::vector<sd_vec *> v;
-};
 
 static inline unsigned sd_blas_grid(const sd_ctx *c, uint64_t n) {
     uint64_t g = (n + SD_BLAS_THREADS - 1) / SD_BLAS_THREADS;
@@ -222,17 +73,17 @@ static inline unsigned sd_blas_grid(const sd_ctx *c, uint64_t n) {
     if (g < 1) g = 1;
     return (unsigned)g;
 }
-static int sd_launch_check(sd_ctx *c, const char *what) {
+int sd_launch_check(sd_ctx *c, const char *what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return sd_fail(SD_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
     c->launches++;
     return SD_OK;
 }
-static int sd_use(const sd_ctx *c) {
+int sd_use(const sd_ctx *c) {
     SD_CUDA(cudaSetDevice(c->device));
     return SD_OK;
 }
-static int sd_partials_reserve(sd_ctx *c, size_t doubles) {
+int sd_partials_reserve(sd_ctx *c, size_t doubles) {
     if (doubles <= c->partials_cap) return SD_OK;
     if (c->d_partials) { SD_CUDA(cudaStreamSynchronize(c->stream)); SD_CUDA(cudaFree(c->d_partials)); c->d_partials = nullptr; }
     size_t cap = std::max(doubles, (size_t)1 << 16);
@@ -252,7 +103,7 @@ static int sd_finish_reduce(sd_ctx *c, unsigned nparts, int slotmask, int slot_o
     }
     return SD_OK;
 }
-static int sd_fetch(sd_ctx *c, int slot, int n, double *out) {
+int sd_fetch(sd_ctx *c, int slot, int n, double *out) {
     SD_CUDA(cudaMemcpyAsync(c->h_scal + slot, c->d_scal + slot, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     SD_CUDA(cudaStreamSynchronize(c->stream));
     for (int i = 0; i < n; ++i) out[i] = c->h_scal[slot + i];
@@ -362,6 +213,7 @@ int sd_ctx_free(sd_ctx *c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm) g_nccl.CommDestroy(c->comm);
+    cudaFree(c->d_vtab); cudaFree(c->d_rth_partials);
     cudaFree(c->d_binom); cudaFree(c->d_scal); cudaFreeHost(c->h_scal); cudaFree(c->d_partials); cudaFree(c->d_ipc);
     cudaFree(c->scratch[0]); cudaFree(c->scratch[1]); cudaFree(c->d_tilectr);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -423,7 +275,7 @@ static int sd_to_device(T **dst, const std::vector<T> &src) {
     return SD_OK;
 }
 
-static int sd_env_int(const char *name, int dflt) {
+int sd_env_int(const char *name, int dflt) {
     const char *s = getenv(name);
     return (s && *s) ? atoi(s) : dflt;
 }
@@ -455,7 +307,7 @@ static int sd_tile_setup(sd_model *m, int which, int B) {
     return SD_OK;
 }
 
-static int sd_scratch(sd_ctx *c, int which, size_t bytes, double **p) {
+int sd_scratch(sd_ctx *c, int which, size_t bytes, double **p) {
     if (bytes > c->scratch_cap[which]) {
         if (c->scratch[which]) { SD_CUDA(cudaStreamSynchronize(c->stream)); SD_CUDA(cudaFree(c->scratch[which])); c->scratch[which] = nullptr; c->scratch_cap[which] = 0; }
         cudaError_t e = cudaMalloc(&c->scratch[which], bytes);
@@ -465,7 +317,7 @@ static int sd_scratch(sd_ctx *c, int which, size_t bytes, double **p) {
     *p = (double *)c->scratch[which];
     return SD_OK;
 }
-static void sd_scratch_release(sd_ctx *c) {          // staging is only kept while it is small
+void sd_scratch_release(sd_ctx *c) {          // staging is only kept while it is small
     for (int w = 0; w < 2; ++w)
         if (c->scratch_cap[w] > ((size_t)256 << 20)) {
             cudaStreamSynchronize(c->stream);
@@ -929,7 +781,7 @@ int sd_vec_local_len(const sd_vec *v, uint64_t *n) {
 static inline size_t sd_vec_bytes(const sd_vec *v) { return (size_t)v->local_n * v->nc * sizeof(double); }
 static inline size_t sd_vec_logical_bytes(const sd_vec *v) { return (size_t)v->logical_n * v->nc * sizeof(double); }
 // block layout <-> rank order on the local shard.  dir 0: blk := rank-ordered (or seeded values), 1: rank-ordered := blk
-static int sd_blk_permute(const sd_vec *v, double *rank_local, int nc_rank, int dir, int seeded, uint64_t seed, double scale) {
+int sd_blk_permute(const sd_vec *v, double *rank_local, int nc_rank, int dir, int seeded, uint64_t seed, double scale) {
     sd_model *m = v->model;
     sd_ctx *c = m->ctx;
     SdBlkParams P = sd_blk_params(m, v->nc);
@@ -1806,7 +1658,24 @@ int sd_lanczos_groundstate(sd_model *m, const sd_vec *v0, int lanc_m, double tol
     }
     int mact = mm;
     const bool batch_check = sd_env_int("SD_BATCH_CHECK", 0) != 0;
-    for (int j = 1; j <= mm; ++j) {
+    // Single GPU: everything behind the apply is one cooperative kernel per step (sd_reorth.cuh) and one 3-double fetch.
+    // SD_REORTH_FUSED=0 keeps the one-call-per-BLAS-operation path below (the only one for sharded models).
+    const bool fused = c->world == 1 && sd_env_int("SD_REORTH_FUSED", 1) != 0;
+    for (int j = 1; fused && j <= mm; ++j) {
+        sd_vec *vj = S->v[j - 1];
+        SD_TRY(sd_apply_impl(m, w, vj, sd_epi_plain(1.0), 0));              // :113
+        sd_vec *vn = nullptr;
+        if (j < mm) { SD_TRY(sd_vec_alloc(m, SD_F64, &vn)); S->v.push_back(vn); }
+        double r[3];
+        SD_TRY(sd_reorth_step(c, w, S->v.data(), j, vn, j >= 2 ? beta[j - 2] : 0.0, tol, orth_tol, r));
+        alpha[j - 1] = r[0];
+        if (j < mm) {
+            beta[j - 1] = r[1];
+            if (r[2] == 1.0) { mact = j; sd_vec_free(vn); S->v.pop_back(); break; }   // :136-139
+            if (r[2] == 2.0) mact = j;                                      // :148-151 leaves the check pass only
+        }
+    }
+    for (int j = 1; !fused && j <= mm; ++j) {
         sd_vec *vj = S->v[j - 1];
         SD_TRY(sd_apply_impl(m, w, vj, sd_epi_plain(1.0), 0));              // :113
         for (int k = 1; k < j; ++k) {                                       // :116-122 sequential MGS

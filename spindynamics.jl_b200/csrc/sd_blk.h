@@ -510,6 +510,7 @@ struct SdBlkPermute {
     uint64_t rstart;             // first rank of the local shard
     const uint64_t *binom;       // [65*65]
 };
+#if !defined(SD_NO_KERNELS)   // a second translation unit (sd_batch.cu) includes this header for the types only
 __global__ void __launch_bounds__(256) sd_blk_permute_kernel(const __grid_constant__ SdBlkParams P, SdBlkPermute Q,
                                                              double *blk_local, double *rank_local) {
     __shared__ uint64_t s_base[2];
@@ -577,4 +578,5 @@ __global__ void __launch_bounds__(256) sd_blk_permute_kernel(const __grid_consta
         }
     }
 }
+#endif  // SD_NO_KERNELS
 #endif  // __CUDACC__

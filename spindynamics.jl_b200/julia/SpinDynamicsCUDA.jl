@@ -244,12 +244,29 @@ function spectral_from_tridiagonal(α, β, norm_phi, E0, ω; eta=0.05, broaden=:
     error("unknown broadening: $broaden")
 end
 
+# q_batch: all momenta as one interleaved [state][q] multi-vector (sd_lanczos_tridiag_szq_batch, at most 128 per call):
+# the reference's Threads.@threads q-loop as data parallelism, two fused kernels per Lanczos step for ALL momenta.
 function lanczos_sqw(ψ0, m::GPUModel, q_list::AbstractVector{Float64}, ω::AbstractVector{Float64};
-                     lanc_m::Int=200, eta::Float64=0.05, broaden::Symbol=:lorentz)
+                     lanc_m::Int=200, eta::Float64=0.05, broaden::Symbol=:lorentz, q_batch::Bool=length(q_list) >= 2)
     ψc = tocomplex(m, ψ0); tmp = GPUVector{ComplexF64}(m); apply_H!(tmp, ψc, m)
     r = Ref{SdComplex}(); check(ccall((:sd_vec_dotu, lib), Cint, (Handle, Handle, Ref{SdComplex}), ψc.h, tmp.h, r))
     E0 = r[].re                                                               # LanczosSqw.jl:59
-    S = zeros(length(q_list), length(ω)); ϕ = GPUVector{ComplexF64}(m)
+    S = zeros(length(q_list), length(ω))
+    if q_batch
+        for lo in 1:128:length(q_list)
+            qs = collect(q_list[lo:min(lo + 127, end)]); n = length(qs)
+            α = zeros(lanc_m, n); β = zeros(lanc_m, n); meff = zeros(Cint, n); nϕ = zeros(n)    # column c = momentum c
+            check(ccall((:sd_lanczos_tridiag_szq_batch, lib), Cint,
+                (Handle, Handle, Ptr{Float64}, Cint, Cint, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Cint}, Ptr{Float64}),
+                m.h, ψc.h, qs, n, lanc_m, 1e-12, α, β, meff, nϕ))
+            for c in 1:n
+                k = meff[c]; k == 0 && continue                               # LanczosSqw.jl:69-72
+                S[lo + c - 1, :] .= spectral_from_tridiagonal(α[1:k, c], β[1:k-1, c], nϕ[c], E0, ω; eta=eta, broaden=broaden)
+            end
+        end
+        return S
+    end
+    ϕ = GPUVector{ComplexF64}(m)
     for (iq, q) in enumerate(q_list)                                          # sequential device work
         n2 = Ref{Float64}()
         check(ccall((:sd_szq, lib), Cint, (Handle, Handle, Handle, Float64, Ref{Float64}), m.h, ϕ.h, ψc.h, q, n2))
@@ -269,7 +286,7 @@ function compute_chebyshev_moments(::typeof(apply_H!), ϕ::GPUVector{ComplexF64}
     check(ccall((:sd_kpm_moments, lib), Cint, (Handle, Handle, Cint, Float64, Float64, Ptr{Float64}), m.h, ϕ.h, M, a, b, μ)); μ
 end
 function kpm_sqw(ψ0, m::GPUModel, q_list::AbstractVector{Float64}, ω::AbstractVector{Float64};
-                 a=nothing, b=nothing, kpm_m::Int=200, kernel::Symbol=:jackson)
+                 a=nothing, b=nothing, kpm_m::Int=200, kernel::Symbol=:jackson, q_batch::Bool=length(q_list) >= 2)
     ψc = tocomplex(m, ψ0); tmp = GPUVector{ComplexF64}(m); r = Ref{SdComplex}()
     check(ccall((:sd_apply_H_dot, lib), Cint, (Handle, Handle, Handle, Ref{SdComplex}), m.h, tmp.h, ψc.h, r))
     E0 = r[].re
@@ -277,14 +294,9 @@ function kpm_sqw(ψ0, m::GPUModel, q_list::AbstractVector{Float64}, ω::Abstract
         a, b = rescaling_from_bounds(estimate_energy_bounds(apply_H!, m)...)
     end
     g = kernel == :jackson ? jackson(kpm_m) : kernel == :lorentz ? [sinh(3.0 * (1 - n / kpm_m)) / sinh(3.0) for n in 0:kpm_m-1] : ones(kpm_m)
-    S = zeros(length(q_list), length(ω)); ϕ = GPUVector{ComplexF64}(m)
-    for (iq, q) in enumerate(q_list)
-        n2 = Ref{Float64}()
-        check(ccall((:sd_szq, lib), Cint, (Handle, Handle, Handle, Float64, Ref{Float64}), m.h, ϕ.h, ψc.h, q, n2))
-        nϕ = sqrt(n2[]); nϕ == 0 && continue
-        scale!(ϕ, 1 / nϕ)
-        μ = compute_chebyshev_moments(apply_H!, ϕ, kpm_m, a, b, m) .* g
-        for (iw, w) in enumerate(ω)                                           # KPM_Sqw.jl:58-90
+    S = zeros(length(q_list), length(ω))
+    function reconstruct!(iq, μ, nϕ)                                          # KPM_Sqw.jl:58-90
+        for (iw, w) in enumerate(ω)
             x = (w + E0 - b) / a
             abs(x) >= 1 && continue
             Tm2, Tm1 = 1.0, x; s = μ[1] + (kpm_m >= 2 ? 2μ[2] * x : 0.0)
@@ -293,6 +305,32 @@ function kpm_sqw(ψ0, m::GPUModel, q_list::AbstractVector{Float64}, ω::Abstract
             end
             S[iq, iw] = nϕ^2 * max(0.0, s / (a * pi * sqrt(1 - x^2)))
         end
+    end
+    batched = q_batch
+    if q_batch                                                                # sd_kpm_moments_szq_batch, at most 128 momenta per call
+        for lo in 1:128:length(q_list)
+            qs = collect(q_list[lo:min(lo + 127, end)]); n = length(qs)
+            μ = zeros(kpm_m, n); nϕ = zeros(n); blown = Ref{Cint}(0)
+            check(ccall((:sd_kpm_moments_szq_batch, lib), Cint,
+                (Handle, Handle, Ptr{Float64}, Cint, Cint, Float64, Float64, Ptr{Float64}, Ptr{Float64}, Ref{Cint}),
+                m.h, ψc.h, qs, n, kpm_m, a, b, μ, nϕ, blown))
+            if blown[] != 0                                                   # KPM_Sqw.jl:117-121 applies: per-momentum path
+                batched = false; fill!(S, 0.0); break
+            end
+            for c in 1:n
+                nϕ[c] == 0 && continue
+                reconstruct!(lo + c - 1, μ[:, c] .* g, nϕ[c])
+            end
+        end
+    end
+    batched && return S
+    ϕ = GPUVector{ComplexF64}(m)
+    for (iq, q) in enumerate(q_list)
+        n2 = Ref{Float64}()
+        check(ccall((:sd_szq, lib), Cint, (Handle, Handle, Handle, Float64, Ref{Float64}), m.h, ϕ.h, ψc.h, q, n2))
+        nϕ = sqrt(n2[]); nϕ == 0 && continue
+        scale!(ϕ, 1 / nϕ)
+        reconstruct!(iq, compute_chebyshev_moments(apply_H!, ϕ, kpm_m, a, b, m) .* g, nϕ)
     end
     S
 end

@@ -102,6 +102,9 @@ SIGNATURES = {
     "sd_lanczos_tridiag": [_vp, _vp, _i, _d, _vp, _vp, _P(_i), _P(_d)],
     "sd_lanczos_lean": [_vp, _vp, _i, _d, _vp, _vp, _P(_i), _vp, _vp, _P(_d)],
     "sd_kpm_moments": [_vp, _vp, _i, _d, _d, _vp],
+    "sd_lanczos_tridiag_szq_batch": [_vp, _vp, _vp, _i, _i, _d, _vp, _vp, _vp, _vp],
+    "sd_kpm_moments_szq_batch": [_vp, _vp, _vp, _i, _i, _d, _d, _vp, _vp, _P(_i)],
+    "sd_ctx_mem_info": [_vp, _P(_u64), _P(_u64)],
     "sd_krylov_basis": [_vp, _vp, _i, _vp, _vp, _P(_i), _P(_d), _P(_vp)],
     "sd_chebyshev_evolve": [_vp, _vp, _vp, _i, _d, _d, _vp],
 }

@@ -469,15 +469,68 @@ def _q_parallel(fn, psi0, model: Model, q_list, q_threads: int, **kw):
     return np.concatenate(parts, axis=0)
 
 
-def lanczos_sqw(psi0, model: Model, q_list, w_range, lanc_m=200, eta=0.05, broaden="lorentz", q_threads: int = 1):
-    """LanczosSqw.jl:49-80.  q_threads > 1: the q-loop on that many host threads / contexts (see _q_parallel)."""
-    if q_threads > 1 and len(q_list) > 1:
-        return _q_parallel(lanczos_sqw, psi0, model, q_list, q_threads, w_range=w_range, lanc_m=lanc_m, eta=eta, broaden=broaden)
+def _q_batches(model: Model, nq: int):
+    """Momenta per call of the q-batched entry points: at most 128, and three [state][q] multi-vectors (16 B per state
+    and padded column each) must fit in 80 % of the free device memory.  Returns [] when not even two columns fit."""
+    free = ctypes.c_uint64()
+    total = ctypes.c_uint64()
+    check(lib().sd_ctx_mem_info(model.ctx._h, ctypes.byref(free), ctypes.byref(total)))
+    fit = int(0.8 * free.value // (3 * 16 * max(model.dim, 1)))
+    sizes = [n for n in (2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64, 96, 128) if n <= fit]     # the padded column counts
+    if not sizes:
+        return []
+    cap = sizes[-1]
+    out, i = [], 0
+    while i < nq:
+        out.append((i, min(nq, i + cap)))
+        i += cap
+    return out
+
+
+def _use_q_batch(model: Model, q_list, q_threads, q_batch):
+    if q_batch is None:
+        q_batch = model.ctx.world == 1 and len(q_list) >= 2 and q_threads <= 1
+    if q_batch and model.ctx.world != 1:
+        raise ValueError("q_batch needs a single-GPU context")
+    return bool(q_batch)
+
+
+def lanczos_sqw(psi0, model: Model, q_list, w_range, lanc_m=200, eta=0.05, broaden="lorentz", q_threads: int = 1,
+                q_batch: Optional[bool] = None):
+    """LanczosSqw.jl:49-80.  q_batch (default on a single GPU with >= 2 momenta): all momenta as one interleaved
+    [state][q] multi-vector, two fused kernels per Lanczos step for ALL of them (sd_lanczos_tridiag_szq_batch) -- the
+    reference's Threads.@threads q-loop as data parallelism.  q_batch=False: one momentum after the other; q_threads > 1:
+    that loop on several host threads / contexts (see _q_parallel)."""
+    if q_threads > 1 and len(q_list) > 1 and not q_batch:
+        return _q_parallel(lanczos_sqw, psi0, model, q_list, q_threads, w_range=w_range, lanc_m=lanc_m, eta=eta, broaden=broaden,
+                           q_batch=False)
     psi0c = _up(model, psi0, np.complex128)
     tmp = model.vector(np.complex128)
     check(lib().sd_apply_H(model._h, tmp._h, psi0c._h))
     E0 = psi0c.dotu(tmp).real                                      # :59 dot(conj(psi0c), tmp)
     S = np.zeros((len(q_list), len(w_range)))
+    if _use_q_batch(model, q_list, q_threads, q_batch):
+        del tmp
+        batches = _q_batches(model, len(q_list))
+        if batches:
+            qs = np.ascontiguousarray(q_list, dtype=np.float64)
+            lm = int(lanc_m)
+            for lo, hi in batches:
+                n = hi - lo
+                qb = qs[lo:hi].copy()
+                alpha = np.zeros((n, lm))
+                beta = np.zeros((n, lm))
+                meff = np.zeros(n, dtype=np.int32)
+                nphi = np.zeros(n)
+                check(lib().sd_lanczos_tridiag_szq_batch(model._h, psi0c._h, _ptr(qb), n, lm, 1e-12,
+                                                         _ptr(alpha), _ptr(beta), _ptr(meff), _ptr(nphi)))
+                for c in range(n):
+                    k = int(meff[c])
+                    if k == 0:                                      # :69-72 norm(phi) == 0
+                        continue
+                    S[lo + c, :] = spectral_from_tridiagonal(alpha[c, :k], beta[c, :k - 1], float(nphi[c]), E0, w_range,
+                                                             eta=eta, broaden=broaden)
+            return S
     phi = model.vector(np.complex128)
     for iq, q in enumerate(q_list):                                 # :65 (the reference threads over q)
         n2 = ctypes.c_double()
@@ -528,6 +581,11 @@ def get_kernel(M: int, kernel: str):
 def kpm_sw(phi, applyH_, model: Model, w_range, a, b, E0, kpm_m=200, kernel="jackson"):
     """KPM_Sqw.jl:34-93."""
     mu = compute_chebyshev_moments(applyH_, phi, kpm_m, a, b, model)
+    return _kpm_reconstruct(mu, w_range, a, b, E0, kpm_m, kernel)
+
+
+def _kpm_reconstruct(mu, w_range, a, b, E0, kpm_m, kernel):
+    """KPM_Sqw.jl:48-92: kernel-damped Chebyshev series on the frequency grid."""
     mu = mu * get_kernel(kpm_m, kernel)
     w_range = np.asarray(w_range, dtype=np.float64)
     x = (w_range + E0 - b) / a
@@ -547,12 +605,47 @@ def kpm_sw(phi, applyH_, model: Model, w_range, a, b, E0, kpm_m=200, kernel="jac
     return S
 
 
-def kpm_sqw(psi0, model: Model, q_list, w_range, a=None, b=None, kpm_m=200, kernel="jackson", rng=None, q_threads: int = 1):
-    """KPM_Sqw.jl:191-256.  q_threads > 1: the q-loop on that many host threads / contexts (see _q_parallel)."""
-    if q_threads > 1 and len(q_list) > 1:
+def kpm_sqw(psi0, model: Model, q_list, w_range, a=None, b=None, kpm_m=200, kernel="jackson", rng=None, q_threads: int = 1,
+            q_batch: Optional[bool] = None):
+    """KPM_Sqw.jl:191-256.  q_batch (default on a single GPU with >= 2 momenta): the moments of all momenta from one
+    interleaved [state][q] multi-vector, one fused kernel per moment for ALL of them (sd_kpm_moments_szq_batch);
+    q_batch=False: one momentum after the other; q_threads > 1: that loop on several host threads / contexts."""
+    if q_threads > 1 and len(q_list) > 1 and not q_batch:
         if a is None or b is None:                                  # :211-215 once, not per thread
             a, b = get_rescaling_params(apply_H_, model, rng=rng)
-        return _q_parallel(kpm_sqw, psi0, model, q_list, q_threads, w_range=w_range, a=a, b=b, kpm_m=kpm_m, kernel=kernel)
+        return _q_parallel(kpm_sqw, psi0, model, q_list, q_threads, w_range=w_range, a=a, b=b, kpm_m=kpm_m, kernel=kernel,
+                           q_batch=False)
+    if _use_q_batch(model, q_list, q_threads, q_batch):
+        psi0c = _up(model, psi0, np.complex128)
+        tmp = model.vector(np.complex128)
+        r = SdComplex()
+        check(lib().sd_apply_H_dot(model._h, tmp._h, psi0c._h, ctypes.byref(r)))    # :207-209 fused E0
+        E0 = float(r.re)
+        del tmp
+        if a is None or b is None:
+            a, b = get_rescaling_params(apply_H_, model, rng=rng)
+        batches = _q_batches(model, len(q_list))
+        S = np.zeros((len(q_list), len(w_range)))
+        qs = np.ascontiguousarray(q_list, dtype=np.float64)
+        ok = bool(batches)
+        for lo, hi in batches:
+            n = hi - lo
+            qb = qs[lo:hi].copy()
+            mu = np.zeros((n, int(kpm_m)))
+            nphi = np.zeros(n)
+            blown = ctypes.c_int()
+            check(lib().sd_kpm_moments_szq_batch(model._h, psi0c._h, _ptr(qb), n, int(kpm_m), float(a), float(b),
+                                                 _ptr(mu), _ptr(nphi), ctypes.byref(blown)))
+            if blown.value:                                         # :117-121 renormalisation needed: per-momentum path
+                ok = False
+                break
+            for c in range(n):
+                if nphi[c] == 0:                                    # :226-229
+                    continue
+                S[lo + c, :] = nphi[c] ** 2 * _kpm_reconstruct(mu[c], w_range, a, b, E0, int(kpm_m), kernel)
+        if ok:
+            return S
+        del psi0c
     psi0c = _up(model, psi0, np.complex128)
     S = np.zeros((len(q_list), len(w_range)))
     tmp = model.vector(np.complex128)
