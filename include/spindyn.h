@@ -134,6 +134,12 @@ int sd_vec_dtype(const sd_vec *vec, int *dtype);
 int sd_vec_local_len(const sd_vec *vec, uint64_t *n);
 int sd_vec_upload(sd_vec *vec, const void *host);       /* local shard, synchronous   */
 int sd_vec_download(sd_vec *vec, void *host);
+/* Asynchronous copies between a PINNED host buffer (sd_host_alloc) and the local shard.  They return at once; the
+ * library orders them against its own kernels.  Block-layout vectors go through the copy engine: two dedicated copy
+ * streams, the transfer cut into chunks whose layout permutes overlap the next chunk's transfer, and an upload issued
+ * after a download runs concurrently with it (both PCIe directions busy).  A downloaded buffer is valid after
+ * sd_ctx_sync (or sd_timer_stop, whose stopwatch covers the copy streams); the host buffer of an upload must stay
+ * untouched until then as well. */
 int sd_vec_upload_async(sd_vec *vec, const void *pinned_host);
 int sd_vec_download_async(sd_vec *vec, void *pinned_host);
 int sd_vec_zero(sd_vec *vec);

@@ -31,6 +31,8 @@
 
 #include "sd_handles.h"
 
+static int sd_copy_join(sd_ctx *c);                               // copy engine (below): compute stream waits for the copy streams
+
 // ----------------------------------------------------------------- errors
 static thread_local char g_err[512] = "";
 int sd_fail(int code, const char *fmt, ...) {
@@ -218,6 +220,9 @@ int sd_ctx_free(sd_ctx *c) {
     cudaFree(c->scratch[0]); cudaFree(c->scratch[1]); cudaFree(c->d_tilectr);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    for (cudaEvent_t e : c->ev_copy) if (e) cudaEventDestroy(e);
+    if (c->h2d) cudaStreamDestroy(c->h2d);
+    if (c->d2h) cudaStreamDestroy(c->d2h);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return SD_OK;
@@ -225,6 +230,7 @@ int sd_ctx_free(sd_ctx *c) {
 int sd_ctx_sync(sd_ctx *c) {
     SD_ARG(c, "ctx is NULL");
     SD_LOCK(c); SD_TRY(sd_use(c));
+    SD_TRY(sd_copy_join(c));                                        // asynchronous uploads / downloads included
     SD_CUDA(cudaStreamSynchronize(c->stream));
     return SD_OK;
 }
@@ -243,6 +249,7 @@ int sd_timer_start(sd_ctx *c) {
 int sd_timer_stop(sd_ctx *c, float *ms) {
     SD_ARG(c && ms, "NULL argument");
     SD_LOCK(c); SD_TRY(sd_use(c));
+    SD_TRY(sd_copy_join(c));                                        // the stopwatch covers the copy streams too
     SD_CUDA(cudaEventRecord(c->ev1, c->stream));
     SD_CUDA(cudaEventSynchronize(c->ev1));
     SD_CUDA(cudaEventElapsedTime(ms, c->ev0, c->ev1));
@@ -307,8 +314,32 @@ static int sd_tile_setup(sd_model *m, int which, int B) {
     return SD_OK;
 }
 
+// The compute stream waits for everything the copy streams have been given so far (no host synchronisation).
+static int sd_copy_join(sd_ctx *c) {
+    if (!c->copy_pending) return SD_OK;
+    const size_t e = 2 * SD_COPY_CHUNKS;
+    SD_CUDA(cudaEventRecord(c->ev_copy[e + 1], c->h2d)); SD_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy[e + 1], 0));
+    SD_CUDA(cudaEventRecord(c->ev_copy[e + 2], c->d2h)); SD_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy[e + 2], 0));
+    c->copy_pending = false; c->d2h_pending = false;
+    return SD_OK;
+}
+static int sd_copy_init(sd_ctx *c) {
+    if (c->h2d) return SD_OK;
+    SD_CUDA(cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
+    SD_CUDA(cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking));
+    c->ev_copy.assign(2 * SD_COPY_CHUNKS + 4, nullptr);
+    for (cudaEvent_t &e : c->ev_copy) SD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return SD_OK;
+}
+static int sd_scratch_raw(sd_ctx *c, int which, size_t bytes, double **p);
+// staging buffer for work on the compute stream: whatever the copy streams still do with it comes first
 int sd_scratch(sd_ctx *c, int which, size_t bytes, double **p) {
+    SD_TRY(sd_copy_join(c));
+    return sd_scratch_raw(c, which, bytes, p);
+}
+static int sd_scratch_raw(sd_ctx *c, int which, size_t bytes, double **p) {
     if (bytes > c->scratch_cap[which]) {
+        SD_TRY(sd_copy_join(c));
         if (c->scratch[which]) { SD_CUDA(cudaStreamSynchronize(c->stream)); SD_CUDA(cudaFree(c->scratch[which])); c->scratch[which] = nullptr; c->scratch_cap[which] = 0; }
         cudaError_t e = cudaMalloc(&c->scratch[which], bytes);
         if (e != cudaSuccess) return sd_fail(SD_ERR_NOMEM, "cudaMalloc of %zu staging bytes failed: %s", bytes, cudaGetErrorString(e));
@@ -320,6 +351,7 @@ int sd_scratch(sd_ctx *c, int which, size_t bytes, double **p) {
 void sd_scratch_release(sd_ctx *c) {          // staging is only kept while it is small
     for (int w = 0; w < 2; ++w)
         if (c->scratch_cap[w] > ((size_t)256 << 20)) {
+            sd_copy_join(c);
             cudaStreamSynchronize(c->stream);
             cudaFree(c->scratch[w]); c->scratch[w] = nullptr; c->scratch_cap[w] = 0;
         }
@@ -336,7 +368,6 @@ static int sd_blk_setup(sd_model *m) {
     for (size_t i = 0; i < m->zz_a.size(); ++i) Jz[m->zz_a[i]] += m->zz_J[i];
     if (!sd_blk_build(L, m->k, Jhop.data(), Jz.data(), m->field.data(), b.host)) return SD_OK;
     b.threads = sd_env_int("SD_BLKL_THREADS", 640);
-    b.depth = sd_env_int("SD_BLKL_DEPTH", 2);
     b.pfp = sd_env_int("SD_BLK_PFP", 0);
     if (b.threads != 512 && b.threads != 768) b.threads = 640;
     for (int w = 0; w < 2; ++w) {
@@ -796,6 +827,37 @@ int sd_blk_permute(const sd_vec *v, double *rank_local, int nc_rank, int dir, in
     return sd_launch_check(c, "sd_blk_permute_kernel");
 }
 
+static int sd_blk_permute_range(const sd_vec *v, double *rank_local, int nc_rank, int dir, uint64_t key_lo, uint64_t key_hi) {
+    sd_model *m = v->model;
+    sd_ctx *c = m->ctx;
+    SdBlkParams P = sd_blk_params(m, v->nc);
+    P.key_lo = key_lo; P.key_hi = key_hi;
+    if (key_hi <= key_lo) return SD_OK;
+    SdBlkPermute Q;
+    Q.dir = dir; Q.nc_blk = v->nc; Q.nc_rank = nc_rank; Q.seeded = 0; Q.seed = 0; Q.scale = 0.0;
+    Q.rstart = m->shards.start[c->rank];
+    Q.binom = c->d_binom;
+    const unsigned grid = (unsigned)std::min<uint64_t>(key_hi - key_lo, (uint64_t)c->sm_count * 16);
+    sd_blk_permute_kernel<<<grid, 256, 0, c->stream>>>(P, Q, v->d, rank_local);
+    return sd_launch_check(c, "sd_blk_permute_kernel");
+}
+// chunk boundaries of the copy engine on this rank's shard: tile keys and the basis ranks (relative to the shard) they start at
+static void sd_copy_chunks(sd_model *m) {
+    if (!m->cp_keys.empty()) return;
+    const sd_ctx *c = m->ctx;
+    const uint64_t r0 = m->shards.start[c->rank], r1 = m->shards.start[c->rank + 1];
+    const uint64_t k0 = m->tile[0].keys[c->rank], k1 = m->tile[0].keys[c->rank + 1];
+    const int K = (r1 - r0) * sizeof(double) < ((uint64_t)64 << 20) ? 1 : SD_COPY_CHUNKS;
+    m->cp_keys.assign(1, k0); m->cp_ranks.assign(1, 0);
+    for (int i = 1; i < K; ++i) {
+        uint64_t base = 0;
+        const uint64_t key = sd_tile_key_of_rank(m->tile[0].host, r0 + (uint64_t)(((unsigned __int128)(r1 - r0) * i) / K), &base);
+        if (key <= m->cp_keys.back() || key >= k1) continue;
+        m->cp_keys.push_back(key); m->cp_ranks.push_back(base - r0);
+    }
+    m->cp_keys.push_back(k1); m->cp_ranks.push_back(r1 - r0);
+}
+
 int sd_vec_upload(sd_vec *v, const void *host) {
     SD_ARG(v && host, "NULL argument");
     sd_ctx *c = v->model->ctx;
@@ -837,10 +899,25 @@ int sd_vec_upload_async(sd_vec *v, const void *host) {
     SD_LOCK(c); SD_TRY(sd_use(c));
     SD_TRY(sd_before_write(c, v));
     if (v->layout) {
+        // pinned host -> rank-ordered staging on the h2d stream, chunk by chunk; the permute of chunk i into block layout
+        // runs on the compute stream while chunk i + 1 is on the wire.  The h2d stream starts when the compute stream
+        // has finished what was enqueued before this call (the permutes of the previous upload read the same staging).
+        sd_model *m = v->model;
+        SD_TRY(sd_copy_init(c));
+        sd_copy_chunks(m);
         double *st = nullptr;
-        SD_TRY(sd_scratch(c, 0, sd_vec_logical_bytes(v) + 16, &st));
-        SD_CUDA(cudaMemcpyAsync(st, host, sd_vec_logical_bytes(v), cudaMemcpyHostToDevice, c->stream));
-        return sd_blk_permute(v, st, v->nc, 0, 0, 0, 0.0);
+        SD_TRY(sd_scratch_raw(c, 0, sd_vec_logical_bytes(v) + 16, &st));
+        const size_t e = 2 * SD_COPY_CHUNKS, esz = (size_t)v->nc * sizeof(double);
+        SD_CUDA(cudaEventRecord(c->ev_copy[e], c->stream));
+        SD_CUDA(cudaStreamWaitEvent(c->h2d, c->ev_copy[e], 0));
+        for (size_t i = 0; i + 1 < m->cp_keys.size(); ++i) {
+            const size_t off = m->cp_ranks[i] * esz, len = (m->cp_ranks[i + 1] - m->cp_ranks[i]) * esz;
+            if (len) SD_CUDA(cudaMemcpyAsync((char *)st + off, (const char *)host + off, len, cudaMemcpyHostToDevice, c->h2d));
+            SD_CUDA(cudaEventRecord(c->ev_copy[i], c->h2d));
+            SD_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy[i], 0));
+            SD_TRY(sd_blk_permute_range(v, st, v->nc, 0, m->cp_keys[i], m->cp_keys[i + 1]));
+        }
+        return SD_OK;                                               // the compute stream has waited for every chunk: nothing pending
     }
     SD_CUDA(cudaMemcpyAsync(v->d, host, sd_vec_bytes(v), cudaMemcpyHostToDevice, c->stream));
     return SD_OK;
@@ -850,10 +927,27 @@ int sd_vec_download_async(sd_vec *v, void *host) {
     sd_ctx *c = v->model->ctx;
     SD_LOCK(c); SD_TRY(sd_use(c));
     if (v->layout) {
+        // permute of chunk i into the rank-ordered staging on the compute stream, its copy to the pinned host buffer on
+        // the d2h stream.  v itself is free again when the permutes are done (stream order); the staging buffer is not
+        // until the copies are, so the next download's permutes wait for this one's last copy (d2h_pending) -- an upload
+        // issued in between does not, which is what lets both PCIe directions run at once.  The data is on the host
+        // after sd_ctx_sync (or sd_timer_stop).
+        sd_model *m = v->model;
+        SD_TRY(sd_copy_init(c));
+        sd_copy_chunks(m);
         double *st = nullptr;
-        SD_TRY(sd_scratch(c, 1, sd_vec_logical_bytes(v) + 16, &st));
-        SD_TRY(sd_blk_permute(v, st, v->nc, 1, 0, 0, 0.0));
-        SD_CUDA(cudaMemcpyAsync(host, st, sd_vec_logical_bytes(v), cudaMemcpyDeviceToHost, c->stream));
+        SD_TRY(sd_scratch_raw(c, 1, sd_vec_logical_bytes(v) + 16, &st));
+        const size_t e = 2 * SD_COPY_CHUNKS, esz = (size_t)v->nc * sizeof(double);
+        if (c->d2h_pending) SD_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy[e + 3], 0));
+        for (size_t i = 0; i + 1 < m->cp_keys.size(); ++i) {
+            const size_t off = m->cp_ranks[i] * esz, len = (m->cp_ranks[i + 1] - m->cp_ranks[i]) * esz;
+            SD_TRY(sd_blk_permute_range(v, st, v->nc, 1, m->cp_keys[i], m->cp_keys[i + 1]));
+            SD_CUDA(cudaEventRecord(c->ev_copy[SD_COPY_CHUNKS + i], c->stream));
+            SD_CUDA(cudaStreamWaitEvent(c->d2h, c->ev_copy[SD_COPY_CHUNKS + i], 0));
+            if (len) SD_CUDA(cudaMemcpyAsync((char *)host + off, (const char *)st + off, len, cudaMemcpyDeviceToHost, c->d2h));
+        }
+        SD_CUDA(cudaEventRecord(c->ev_copy[e + 3], c->d2h));
+        c->d2h_pending = true; c->copy_pending = true;
         return SD_OK;
     }
     SD_CUDA(cudaMemcpyAsync(host, v->d, sd_vec_bytes(v), cudaMemcpyDeviceToHost, c->stream));
@@ -1116,10 +1210,6 @@ static int sd_blk_launch_range(sd_model *m, int nc, const SdBlkParams &P, const 
     } while (0)
     // epilogue kind (sd_blkl.h): 0 plain, 1 Lanczos (hscale + fused <psi, out>), 2 generic
     const int ek = plain ? 0 : ((epi.mode == SD_EPI_PLAIN && (epi.red == SD_RED_DOT_SELF || epi.red == 0) && !epi.acc) ? 1 : 2);
-    // experiment (SD_BLKL_DEPTH = 3 | 4, f64 plain apply only): neighbour streams three / four entries deep on fewer warps
-    if (nc == 1 && ek == 0 && m->blk.depth == 3) SD_HL((sd_blkl_apply_kernel<1, 0, 512, 3>), 512);
-    else if (nc == 1 && ek == 0 && m->blk.depth == 4) SD_HL((sd_blkl_apply_kernel<1, 0, 512, 4>), 512);
-    else
     if (nc == 1) { if (ek == 0) SD_HL_LEAN(1, 0); else if (ek == 1) SD_HL_LEAN(1, 1); else SD_HL_LEAN(1, 2); }
     else { if (ek == 0) SD_HL_LEAN(2, 0); else if (ek == 1) SD_HL_LEAN(2, 1); else SD_HL_LEAN(2, 2); }
 #undef SD_HL_LEAN
@@ -1395,7 +1485,8 @@ int sd_apply_H_host(sd_model *m, int dtype, void *out, const void *psi) {
     if (rc == SD_OK) rc = sd_vec_alloc(m, dtype, &vo);
     if (rc == SD_OK) rc = sd_vec_upload_async(vi, psi);
     if (rc == SD_OK) rc = sd_apply_H(m, vo, vi);
-    if (rc == SD_OK) rc = sd_vec_download(vo, out);
+    if (rc == SD_OK) rc = sd_vec_download_async(vo, out);
+    if (rc == SD_OK) rc = sd_ctx_sync(m->ctx);
     sd_vec_free(vi); sd_vec_free(vo);
     return rc;
 }

@@ -70,7 +70,7 @@ struct SdBlkShards {
 struct SdBlkParams {
     int L, k, A;
     int nbuf;                        // tile buffers in shared memory
-    int pfp;                         // producer L2 prefetch of partner tiles (experiment): bit 0 on, bit 1 one tile late, bit 2 all prefix entries (else the far ones)
+    int pfp;                         // producer L2 prefetch of partner tiles: bit 0 on, bit 1 one tile late, bit 3 two tiles late, bit 2 all prefix entries (else the far ones), bit 4 + the crossing partner
     uint64_t key_lo, key_hi;         // tile keys of this launch (this shard)
     double Jhop[SD_MAX_L + 1];       // hop coefficient of bond p (positions p, p+1)
     double Jz[SD_MAX_L + 1];
@@ -474,13 +474,23 @@ __device__ __forceinline__ void sd_blk_producer(const SdBlkParams &P, const SdBl
         constexpr uint32_t CH = 8192;
         for (uint32_t o = lane * CH; o < bytes; o += 32 * CH)
             sd_bulk_g2s(dst + o, src + o, (bytes - o < CH) ? bytes - o : CH, &S.full[b]);
+        // L2 bulk prefetch of the partner tiles by the producer (no consumer instruction).  Measured at L = 32
+        // (profiles/round2_n_ab.txt): issued for the tile just handed to the consumers' queue it thrashes (all entries:
+        // 20.9 GB of DRAM reads, 5.91 ms); one tile later -- for the tile the consumers reach next -- it lifts the L2 hit
+        // rate from 53 to 62 % at 15.3 GB and takes 5.77 -> 5.40 ms.  Peer memory is never prefetched (pathologically slow).
         if ((P.pfp & 1) && P.shards.world == 1) {              // partner tiles of the prefix bonds have the tile's own js, i.e. its size
-            const SdBlkHdr &Hp = (P.pfp & 2) ? S.hdr[(b + nbuf - 1) % nbuf] : H;
-            if (!(P.pfp & 2) || i > 0) {
+            unsigned late = (P.pfp & 8) ? 2u : ((P.pfp & 2) ? 1u : 0u);
+            if (late > (unsigned)nbuf - 1u) late = (unsigned)nbuf - 1u;   // the header of that tile must still be in its buffer
+            if (i >= late) {
+                const SdBlkHdr &Hp = S.hdr[((unsigned)b + (unsigned)nbuf - late) % (unsigned)nbuf];
                 const int cnt = (P.pfp & 4) ? Hp.nnb : Hp.nfar;
-                const uint32_t pb = S.js[Hp.js].size_pad * (uint32_t)(NC * 8);
-                if ((int)lane < cnt)
+                if ((int)lane < cnt) {
+                    const uint32_t pb = S.js[Hp.js].size_pad * (uint32_t)(NC * 8);
                     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(Hp.nb[lane].p), "r"(pb) : "memory");
+                } else if ((P.pfp & 16) && (int)lane == cnt && Hp.xptr != nullptr) {   // the prefix|mid crossing partner (its own js)
+                    const uint32_t pb = S.js[Hp.jsx].size_pad * (uint32_t)(NC * 8);
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(Hp.xptr), "r"(pb) : "memory");
+                }
             }
         }
     }

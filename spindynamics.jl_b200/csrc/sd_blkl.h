@@ -15,7 +15,6 @@
 // The body compiles for the host too (tests/emul runs it lane by lane against the oracle): there SD_SH is a plain
 // static object.
 #pragma once
-#include <type_traits>
 #include "sd_blk.h"
 
 #define SD_BLKL_NBUF 3           // tile buffers (f64); c128 uses 2
@@ -41,11 +40,6 @@ static SdBlkShared sd_blkl_sh;
 #define SD_SH sd_blkl_sh
 #define SD_BLKL_FN inline
 #endif
-// compile-time loop: f(std::integral_constant<int, 0>) ... f(std::integral_constant<int, N - 1>)
-template <int N, int I = 0, class F>
-SD_BLKL_FN void sd_static_for(F &&f) {
-    if constexpr (I < N) { f(std::integral_constant<int, I>{}); sd_static_for<N, I + 1>(f); }
-}
 // resolves the epilogue's hscale (device: one thread, before the CTA barrier; host: the emulation)
 SD_BLKL_FN void sd_blkl_ctx_init(const SdEpi &epi) {
     SD_SH.hs = epi.hscale_dev ? epi.hscale / sqrt(*epi.hscale_dev) : epi.hscale;
@@ -54,7 +48,7 @@ SD_BLKL_FN void sd_blkl_ctx_init(const SdEpi &epi) {
 // EK: epilogue kind, compile-time so that each instantiation only carries the code it runs (the kernel is instruction-
 // cache sensitive): 0 plain out = H psi; 1 Lanczos: out = hs * H psi with the fused <psi, out> (every Lanczos flavour);
 // 2 generic (rescaled / Chebyshev step, psi_t accumulation, phi dot, norm: sd_epilogue_hs).
-template <int NC, int JT, int S0, int EK, int DEPTH = 2>
+template <int NC, int JT, int S0, int EK>
 SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdEpi &E, double *out_local, const SdBlkHdr &H, const double *tb, uint32_t u,
                              double (&red)[SD_NSLOT]) {
     constexpr bool PLAIN = EK == 0;
@@ -74,14 +68,9 @@ SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdEpi &E, double *out_l
     uint32_t o[EC];                                                  // doubles, slot s of the chunk (half slot: its plain row)
 #pragma unroll
     for (int s = 0; s < EC; ++s) o[s] = off0 + (uint32_t)(S0 + s) * ss - ((HALF && s == EC - 1) ? u : 0u);
-    double2 acc[EC], tt[DEPTH][EC];
-    double2 (&t0)[EC] = tt[0], (&t1)[EC] = tt[DEPTH - 1];            // t1: also the landing stage of the crossing partner
+    double2 acc[EC], t0[EC], t1[EC];
 #pragma unroll
-    for (int s = 0; s < EC; ++s) {
-        acc[s] = make_double2(0.0, 0.0);
-#pragma unroll
-        for (int d = 0; d < DEPTH; ++d) tt[d][s] = make_double2(0.0, 0.0);   // conditionally loaded below; left undefined they end up on the stack
-    }
+    for (int s = 0; s < EC; ++s) acc[s] = t0[s] = t1[s] = make_double2(0.0, 0.0);   // t0/t1: conditionally loaded below; left undefined they end up on the stack
 #define SD_LEAN_LOAD(t_, p_)                                                                  \
     do {                                                                                      \
         const double *q_ = (p_);                                                              \
@@ -111,41 +100,22 @@ SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdEpi &E, double *out_l
         }
     }
     // ---- prefix-internal bonds: whole neighbour tiles in the same element order
-    if constexpr (DEPTH == 2) {
-        SdBlkEnt e0 = H.nb[0], e1;                                   // {tile base, J}: one LDS.128 per entry
-        if (nnb > 0) SD_LEAN_LOAD(t0, e0.p);
-        if (xl) SD_LEAN_FMA(t1, H.Jx);
-        int n = 0;
+    // (Three / four entries in flight per lane on 512 threads were measured slower, 7.3 / 8.9 ms against 5.8 at two entries
+    // on 640 threads: profiles/round2_n_ab.txt.)
+    SdBlkEnt e0 = H.nb[0], e1;                                       // {tile base, J}: one LDS.128 per entry
+    if (nnb > 0) SD_LEAN_LOAD(t0, e0.p);
+    if (xl) SD_LEAN_FMA(t1, H.Jx);
+    int n = 0;
 #pragma unroll 1
-        while (n + 1 < nnb) {
-            e1 = H.nb[n + 1];
-            SD_LEAN_LOAD(t1, e1.p);
-            SD_LEAN_FMA(t0, e0.J);
-            if (n + 2 < nnb) { e0 = H.nb[n + 2]; SD_LEAN_LOAD(t0, e0.p); }
-            SD_LEAN_FMA(t1, e1.J);
-            n += 2;
-        }
-        if (n < nnb) SD_LEAN_FMA(t0, e0.J);
-    } else {
-        // DEPTH entries in flight per lane (experiment: fewer, deeper warps).  Stage d of the rotation holds entry
-        // n + d; the crossing partner sits in the last stage until the first DEPTH - 1 stream loads are issued.
-        double Jq[DEPTH];
-        sd_static_for<DEPTH - 1>([&](auto dc) {
-            constexpr int d = decltype(dc)::value;
-            if (d < nnb) { const SdBlkEnt e = H.nb[d]; Jq[d] = e.J; SD_LEAN_LOAD(tt[d], e.p); }
-        });
-        if (xl) SD_LEAN_FMA(t1, H.Jx);
-        int n = 0;
-#pragma unroll 1
-        while (n < nnb) {
-            sd_static_for<DEPTH>([&](auto dc) {
-                constexpr int d = decltype(dc)::value, dn = (d + DEPTH - 1) % DEPTH;
-                if (n + d + DEPTH - 1 < nnb) { const SdBlkEnt e = H.nb[n + d + DEPTH - 1]; Jq[dn] = e.J; SD_LEAN_LOAD(tt[dn], e.p); }
-                if (n + d < nnb) SD_LEAN_FMA(tt[d], Jq[d]);
-            });
-            n += DEPTH;
-        }
+    while (n + 1 < nnb) {
+        e1 = H.nb[n + 1];
+        SD_LEAN_LOAD(t1, e1.p);
+        SD_LEAN_FMA(t0, e0.J);
+        if (n + 2 < nnb) { e0 = H.nb[n + 2]; SD_LEAN_LOAD(t0, e0.p); }
+        SD_LEAN_FMA(t1, e1.J);
+        n += 2;
     }
+    if (n < nnb) SD_LEAN_FMA(t0, e0.J);
 #undef SD_LEAN_LOAD
 #undef SD_LEAN_FMA
     // ---- own block: diagonal + tail-internal hops (registers, compile-time permutation)
@@ -284,22 +254,22 @@ SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdEpi &E, double *out_l
         }
     }
 }
-template <int NC, int EK, int DEPTH = 2>
+template <int NC, int EK>
 SD_BLKL_FN void sd_blkl_dispatch(const SdBlkParams &P, const SdEpi &E, double *out_local, const SdBlkHdr &H, const double *tb, unsigned code, uint32_t u,
                                 double (&red)[SD_NSLOT]) {
     const int jt = (int)(code >> 12);
     const bool hi = ((code >> 8) & 0xFu) != 0;                       // c128, classes of 10: second chunk of five
     switch (jt) {
-        case 0: sd_blkl_item<NC, 0, 0, EK, DEPTH>(P, E, out_local, H, tb, u, red); break;
-        case 1: sd_blkl_item<NC, 1, 0, EK, DEPTH>(P, E, out_local, H, tb, u, red); break;
+        case 0: sd_blkl_item<NC, 0, 0, EK>(P, E, out_local, H, tb, u, red); break;
+        case 1: sd_blkl_item<NC, 1, 0, EK>(P, E, out_local, H, tb, u, red); break;
         case 2:
-            if constexpr (NC == 2) { if (hi) { sd_blkl_item<NC, 2, 5, EK, DEPTH>(P, E, out_local, H, tb, u, red); break; } }
-            sd_blkl_item<NC, 2, 0, EK, DEPTH>(P, E, out_local, H, tb, u, red); break;
+            if constexpr (NC == 2) { if (hi) { sd_blkl_item<NC, 2, 5, EK>(P, E, out_local, H, tb, u, red); break; } }
+            sd_blkl_item<NC, 2, 0, EK>(P, E, out_local, H, tb, u, red); break;
         case 3:
-            if constexpr (NC == 2) { if (hi) { sd_blkl_item<NC, 3, 5, EK, DEPTH>(P, E, out_local, H, tb, u, red); break; } }
-            sd_blkl_item<NC, 3, 0, EK, DEPTH>(P, E, out_local, H, tb, u, red); break;
-        case 4: sd_blkl_item<NC, 4, 0, EK, DEPTH>(P, E, out_local, H, tb, u, red); break;
-        default: sd_blkl_item<NC, 5, 0, EK, DEPTH>(P, E, out_local, H, tb, u, red); break;
+            if constexpr (NC == 2) { if (hi) { sd_blkl_item<NC, 3, 5, EK>(P, E, out_local, H, tb, u, red); break; } }
+            sd_blkl_item<NC, 3, 0, EK>(P, E, out_local, H, tb, u, red); break;
+        case 4: sd_blkl_item<NC, 4, 0, EK>(P, E, out_local, H, tb, u, red); break;
+        default: sd_blkl_item<NC, 5, 0, EK>(P, E, out_local, H, tb, u, red); break;
     }
 }
 
@@ -307,7 +277,7 @@ SD_BLKL_FN void sd_blkl_dispatch(const SdBlkParams &P, const SdEpi &E, double *o
 #if defined(__CUDACC__)
 // grid = one persistent CTA per SM of NTHR threads; the last warp is the producer (sd_blk_producer: tile keys from the global
 // counter or the order table, headers, TMA of the own tiles), the others pull (tile, unit) items.
-template <int NC, int EK, int NTHR, int DEPTH = 2>
+template <int NC, int EK, int NTHR>
 __global__ void __launch_bounds__(NTHR, 1)
 sd_blkl_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constant__ SdVecView psi, double *out_local,
                      const __grid_constant__ SdEpi epi, int qfar, unsigned long long *tile_ctr) {
@@ -353,7 +323,7 @@ sd_blkl_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constan
                 const unsigned code = SD_SH.units[H.js * SD_BLK_MAXUNITS + un];
                 const uint32_t u = (code & 0xFFu) * 32u + lane;      // the lane's mid configuration
                 double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
-                sd_blkl_dispatch<NC, EK, DEPTH>(P, epi, out_local, H, tb, code, u, red);
+                sd_blkl_dispatch<NC, EK>(P, epi, out_local, H, tb, code, u, red);
                 if (!PLAIN && slotmask) sd_blk_item_reduce(H, slotmask, un, red, lane);
             }
             __syncwarp();

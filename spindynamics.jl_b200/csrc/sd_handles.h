@@ -91,6 +91,13 @@ struct sd_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint64_t launches = 0;
     std::vector<uint64_t> binom;
+    // ---- copy engine of sd_vec_upload_async / sd_vec_download_async on block-layout vectors (sd_api.cu): pinned host
+    // <-> rank-ordered staging on two copy streams, chunk by chunk, the layout permute of chunk i on the compute stream
+    // while chunk i + 1 is on the wire; an upload and a download run concurrently (both PCIe directions).
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    std::vector<cudaEvent_t> ev_copy;         // [2 * SD_COPY_CHUNKS + 4]: per-chunk events up / down, fork, joins, d2h done
+    bool copy_pending = false;                // work may still be running on h2d / d2h that the compute stream has not waited for
+    bool d2h_pending = false;                 // the download staging buffer is still being read by the d2h stream
     const double **d_vtab = nullptr;          // sd_reorth_step: device table of the basis vectors' pointers (+ host mirror)
     std::vector<const double *> h_vtab;
     int vtab_count = 0;
@@ -127,7 +134,6 @@ struct SdBlkDev {
     size_t smem[2] = {0, 0};
     int qfar[2] = {0, 0};
     int pfp = 0;                    // SD_BLK_PFP (experiment, SdBlkParams::pfp)
-    int depth = 2;                  // SD_BLKL_DEPTH (experiment, see sd_blk_launch_range)
     int threads = 640;              // CTA size of sd_blkl_apply_kernel (SD_BLKL_THREADS = 512 | 640 | 768, read once at model creation)
     uint32_t *d_order = nullptr;    // breadth-first tile order of this rank's shard (vectors larger than the L2)
     uint32_t norder = 0;
@@ -142,8 +148,10 @@ struct SdTileDev {
     uint64_t keys[SD_MAX_WORLD + 1];
 };
 
+#define SD_COPY_CHUNKS 8
 struct sd_model {
     sd_ctx *ctx = nullptr;
+    std::vector<uint64_t> cp_keys, cp_ranks;  // chunk boundaries of the copy engine: tile keys / local basis ranks, [chunks + 1]
     int L = 0, k = -1;
     uint64_t N = 0;
     std::vector<int> hop_a, hop_b, zz_a, zz_b;

@@ -399,18 +399,3 @@ def test_sharded_apply_with_planned_peer_ranges_and_weighted_shards(variant, L, 
         assert abs(complex(red[0], red[1]) - np.vdot(cplx(psi), cplx(nxt))) < 1e-9
         assert abs(red[2] - np.vdot(cplx(phi), cplx(nxt)).real) < 1e-9 and abs(red[3] - nxt @ nxt) < 1e-8
 
-
-@pytest.mark.parametrize("depth", [3, 4])
-@pytest.mark.parametrize("NC", [1, 2])
-@pytest.mark.parametrize("L,k", [(16, 8), (17, 3), (18, 9)])
-def test_deeper_stream_pipeline_is_bit_identical(emul, L, k, NC, depth):
-    """sd_blkl_item<.., DEPTH>: the neighbour-tile entries are consumed in the same order whatever the number of register
-    stages, so the result equals the two-stage default bit for bit."""
-    rng = np.random.default_rng(77 + L + NC)
-    Jhop, Jz, h = model_lists(L, rng)
-    m = oracle_model(L, k, Jhop, Jz, h)
-    states = np.ascontiguousarray(m.states, dtype=np.uint64)
-    psi = rng.standard_normal(len(states) * NC)
-    ref, _, _, _ = run(emul, L, k, NC, 1, states, psi, Jhop, Jz, h, variant=0)
-    got, _, _, _ = run(emul, L, k, NC, 1, states, psi, Jhop, Jz, h, variant=depth - 2)
-    assert np.array_equal(ref, got)
