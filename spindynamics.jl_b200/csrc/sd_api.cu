@@ -292,8 +292,8 @@ static int sd_tile_setup(sd_model *m, int which, int B) {
     t.ok = false;
     const int L = m->L;
     std::vector<double> Jhop(L, 0.0), Jz(L, 0.0);
-    for (size_t b = 0; b < m->hop_a.size(); ++b) Jhop[m->hop_a[b]] += m->hop_J[b];
-    for (size_t b = 0; b < m->zz_a.size(); ++b) Jz[m->zz_a[b]] += m->zz_J[b];
+    for (size_t b = 0; b < m->hop_a.size(); ++b) if (m->hop_b[b] == m->hop_a[b] + 1) Jhop[m->hop_a[b]] += m->hop_J[b];   // not the wrap bond
+    for (size_t b = 0; b < m->zz_a.size(); ++b) if (m->zz_b[b] == m->zz_a[b] + 1) Jz[m->zz_a[b]] += m->zz_J[b];
     if (!sd_tile_build(L, m->k, B, m->tile_T[which], Jhop.data(), Jz.data(), m->field.data(), t.host)) return SD_OK;
     const int nc = which + 1;
     t.cap = t.host.cap_max;
@@ -364,8 +364,8 @@ static int sd_blk_setup(sd_model *m) {
     const int L = m->L;
     if (!m->tile_capable || m->tile[0].host.P.B != SD_BLK_B || L - SD_BLK_B < 1) return SD_OK;
     std::vector<double> Jhop(L + 1, 0.0), Jz(L + 1, 0.0);
-    for (size_t i = 0; i < m->hop_a.size(); ++i) Jhop[m->hop_a[i]] += m->hop_J[i];
-    for (size_t i = 0; i < m->zz_a.size(); ++i) Jz[m->zz_a[i]] += m->zz_J[i];
+    for (size_t i = 0; i < m->hop_a.size(); ++i) if (m->hop_b[i] == m->hop_a[i] + 1) Jhop[m->hop_a[i]] += m->hop_J[i];   // not the wrap bond
+    for (size_t i = 0; i < m->zz_a.size(); ++i) if (m->zz_b[i] == m->zz_a[i] + 1) Jz[m->zz_a[i]] += m->zz_J[i];
     if (!sd_blk_build(L, m->k, Jhop.data(), Jz.data(), m->field.data(), b.host)) return SD_OK;
     b.threads = sd_env_int("SD_BLKL_THREADS", 640);
     b.pfp = sd_env_int("SD_BLK_PFP", 0);
@@ -421,21 +421,23 @@ int sd_model_create(sd_ctx *ctx, int L, int nup, const sd_bond *hop, int nhop, c
     if (!m) return sd_fail(SD_ERR_NOMEM, "out of host memory");
     m->ctx = ctx; m->L = L; m->k = nup;
     m->N = nup < 0 ? (1ULL << L) : ctx->binom[L * SD_BINOM_DIM + nup];
-    bool all_nn = true;
+    bool all_nn = true, wrap = false;                               // every bond nearest-neighbour, except possibly the wrap bond
     for (int b = 0; b < nhop; ++b) {
         const int64_t i = hop[b].i, j = hop[b].j;
         if (i < 1 || i > L || j < 1 || j > L) { delete m; return sd_fail(SD_ERR_ARG, "hopping site outside 1..L"); }
         if (i == j) continue;                       // bits never differ: the reference skips it
         const int a = (int)std::min(i, j) - 1, c = (int)std::max(i, j) - 1;
         m->hop_a.push_back(a); m->hop_b.push_back(c); m->hop_J.push_back(hop[b].J);
-        if (c != a + 1) all_nn = false;
+        if (a == 0 && c == L - 1 && L > 2) { wrap = true; m->wrap_hop += hop[b].J; }   // SpinModel.jl:71-78 periodic chain
+        else if (c != a + 1) all_nn = false;
     }
     for (int b = 0; b < nzz; ++b) {
         const int64_t i = zz[b].i, j = zz[b].j;
         if (i < 1 || i > L || j < 1 || j > L) { delete m; return sd_fail(SD_ERR_ARG, "zz site outside 1..L"); }
         const int a = (int)std::min(i, j) - 1, c = (int)std::max(i, j) - 1;
         m->zz_a.push_back(a); m->zz_b.push_back(c); m->zz_J.push_back(zz[b].J);
-        if (c != a + 1) all_nn = false;
+        if (a == 0 && c == L - 1 && L > 2) { wrap = true; m->wrap_zz += zz[b].J; }
+        else if (c != a + 1) all_nn = false;
     }
     m->field.assign(field, field + L);
     SD_TRY(sd_to_device(&m->d_hop_a, m->hop_a));
@@ -489,6 +491,7 @@ int sd_model_create(sd_ctx *ctx, int L, int nup, const sd_bond *hop, int nhop, c
         SD_TRY(sd_tile_setup(m, 1, std::min(B1, B2)));
         m->tile_capable = m->tile[0].ok && m->tile[1].ok;
     }
+    m->has_wrap = wrap && all_nn;
     m->path = m->tile_capable ? SD_PATH_TILED : SD_PATH_GENERIC;
     if (m->tile_capable && sd_env_int("SD_BLK", 1)) {
         SD_TRY(sd_blk_setup(m));
@@ -498,6 +501,8 @@ int sd_model_create(sd_ctx *ctx, int L, int nup, const sd_bond *hop, int nhop, c
         const int min_tiles = sd_env_int("SD_BLK_MIN_TILES", 0);
         if (m->blk.ok && min_tiles > 0 && (1ULL << m->blk.host.P.A) < (uint64_t)min_tiles) m->path = SD_PATH_GENERIC;
     }
+    // a periodic chain runs on the block kernel (wrap pass + add-in) or on the generic one; the tiled kernel has no wrap bond
+    if (m->has_wrap && m->path == SD_PATH_TILED) m->path = SD_PATH_GENERIC;
     // shards: tile-aligned to the coarser (F64) tiling when tiled, plain equal split otherwise
     uint64_t bounds[SD_MAX_WORLD + 1];
     if (m->tile_capable) {
@@ -565,7 +570,7 @@ int sd_model_free(sd_model *m) {
         SdTileDev &t = m->tile[w];
         cudaFree(t.d_perm); cudaFree(t.d_items); cudaFree(t.d_binomM);
     }
-    cudaFree(m->blk.d_order);
+    cudaFree(m->blk.d_order); cudaFree(m->d_wrap[0]); cudaFree(m->d_wrap[1]);
     cudaFree(m->blk.d_W); cudaFree(m->blk.d_js); cudaFree(m->blk.d_units); cudaFree(m->blk.d_items); cudaFree(m->blk.d_dmid);
     delete m;
     return SD_OK;
@@ -609,8 +614,8 @@ int sd_model_set_path(sd_model *m, int kernel_path) {
         return sd_fail(SD_ERR_UNSUPPORTED, "cannot switch between the block kernel and the rank-ordered kernels while %d vectors of the model are alive", m->live_vecs);
     if (kernel_path == SD_PATH_GENERIC) { m->path = SD_PATH_GENERIC; m->blk_layout = false; return SD_OK; }
     if (kernel_path == SD_PATH_TILED) {
-        if (!m->tile_capable)
-            return sd_fail(SD_ERR_UNSUPPORTED, "model does not qualify for the tiled kernel (sector basis, nearest-neighbour bonds, L >= 10)");
+        if (!m->tile_capable || m->has_wrap)
+            return sd_fail(SD_ERR_UNSUPPORTED, "model does not qualify for the tiled kernel (sector basis, open chain of nearest-neighbour bonds, L >= 10)");
         m->path = SD_PATH_TILED; m->blk_layout = false;
         return SD_OK;
     }
@@ -1243,6 +1248,20 @@ static int sd_apply_impl(sd_model *m, sd_vec *out, const sd_vec *psi, SdEpi epi,
         epi.partials = c->d_partials;
         epi.nparts = (unsigned)nkeys;
         const bool plain = epi.mode == SD_EPI_PLAIN && epi.red == 0 && !epi.acc && epi.hscale == 1.0 && !epi.hscale_dev;
+        if (m->has_wrap) {                                          // periodic chain: the wrap bond's terms first (sd_blk.h)
+            double *&wv = m->d_wrap[nc - 1];
+            if (!wv) {
+                SD_CUDA(cudaMalloc(&wv, sd_vec_bytes(psi)));
+                SD_CUDA(cudaMemsetAsync(wv, 0, sd_vec_bytes(psi), c->stream));   // padding stays zero: the pass writes real elements only
+            }
+            SdBlkWrap Wp;
+            Wp.J = m->wrap_hop; Wp.Jz4 = 0.25 * m->wrap_zz;
+            const unsigned wg = (unsigned)std::min<uint64_t>(nkeys, (uint64_t)c->sm_count * 8);
+            if (nc == 2) sd_blk_wrap_kernel<2><<<wg, 256, 0, c->stream>>>(P, Wp, psi->view, wv);
+            else sd_blk_wrap_kernel<1><<<wg, 256, 0, c->stream>>>(P, Wp, psi->view, wv);
+            SD_TRY(sd_launch_check(c, "sd_blk_wrap_kernel"));
+            P.addin = wv;
+        }
         SD_TRY(sd_blk_launch_range(m, nc, P, psi->view, out->d, epi, plain));
         if (slotmask) SD_TRY(sd_finish_reduce(c, (unsigned)nkeys, slotmask, slot_out));
     } else if (m->path == SD_PATH_TILED) {

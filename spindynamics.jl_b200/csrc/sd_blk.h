@@ -85,6 +85,7 @@ struct SdBlkParams {
     const SdBlkItem *items;
     const double *dmid;              // [1 << M] diag of the mid sites + mid-internal zz, in ITEM order (same index as items[])
     uint32_t cap;                    // largest size_pad
+    const double *addin;             // optional: local shard of a block-layout vector added to H psi before the epilogue (the periodic wrap bond's terms, sd_blk_wrap_*)
     const uint32_t *order;           // optional tile order of this shard (keys, norder of them); nullptr: rank order
     uint32_t norder;
     SdBlkShards shards;
@@ -112,6 +113,113 @@ struct alignas(16) double2 { double x, y; };
 struct alignas(16) uint4 { unsigned x, y, z, w; };
 static inline double2 make_double2(double x, double y) { double2 v; v.x = x; v.y = y; return v; }
 #endif
+
+
+// ------------------------------------------------------------------ stored position <-> (class, tail configuration, mid configuration)
+// Stored position p of a tile with class table I, for a vector of nc components -> (jt, e, u); false for padding.
+SD_HD bool sd_blk_decode(const SdBlkJs &I, int nc, uint32_t p, int &jt, uint32_t &e, uint32_t &u) {
+    jt = -1;
+    uint32_t rel = 0;
+#pragma unroll
+    for (int j = 0; j < SD_BLK_NCLS; ++j) {
+        const uint32_t len = I.cls[j].pitch * (uint32_t)sd_cbinom(SD_BLK_T, j);
+        if (jt < 0 && p >= I.cls[j].cb && p < I.cls[j].cb + len) { jt = j; rel = p - I.cls[j].cb; }
+    }
+    if (jt < 0) return false;
+    const uint32_t pitch = I.cls[jt].pitch;
+    const uint32_t nt = (uint32_t)sd_cbinom(SD_BLK_T, jt);
+    if (nc == 1 && (nt & 1u) && rel >= (nt - 1u) * pitch) {        // f64, odd class: last row is plain
+        e = nt - 1u; u = rel - (nt - 1u) * pitch;
+    } else if (nc == 1) {                                          // f64: pair rows (2s, 2s+1) of double2 per block
+        const uint32_t pr = rel / (2u * pitch), r2 = rel % (2u * pitch);
+        u = r2 >> 1; e = 2u * pr + (r2 & 1u);
+    } else {                                                       // c128: one row per tail configuration
+        e = rel / pitch; u = rel % pitch;
+    }
+    return u < I.cls[jt].nblk && e < nt;
+}
+// position of (jt, e, u) inside the tile for a vector of nc components (inverse of sd_blk_decode)
+SD_HD uint32_t sd_blk_encode(const SdBlkJs &I, int nc, int jt, uint32_t e, uint32_t u) {
+    const SdBlkCls &c = I.cls[jt];
+    const uint32_t nt = (uint32_t)sd_cbinom(SD_BLK_T, jt);
+    if (nc == 1 && (nt & 1u) && e == nt - 1u) return c.cb + e * c.pitch + u;
+    if (nc == 1) return c.cb + (e >> 1) * 2u * c.pitch + 2u * u + (e & 1u);
+    return c.cb + e * c.pitch + u;
+}
+
+
+// ------------------------------------------------------------------ periodic wrap bond (sites L-1 and 0; SpinModel.jl:71-78)
+// The bond between the last tail site and the first prefix site is the one bond of a periodic chain that is neither
+// inside a tile nor between two tiles of equal shape: flipping prefix bit 0 changes the prefix popcount, so the partner
+// tile has suffix popcount js +- 1, and flipping tail bit T-1 moves the element to tail class jt +- 1 -- the mid
+// configuration keeps its popcount, hence its index u in the class (item lists are shared by mid popcount).  It is
+// handled by a pass of its own BEFORE the block kernel: wrap[p] = Jz/4 * (+-1) psi[p] + J * psi[partner(p)] for every
+// stored element, which the block kernel then adds to H psi in front of its fused epilogue (SdBlkParams::addin).
+// One extra read of psi and of the partner halves, one write and one read of the wrap vector: the periodic chain costs
+// ~1.5x the open one instead of falling to the one-thread-per-state kernel (10x).
+struct SdBlkWrap {
+    double J;                            // hop coefficient of the wrap bond (0: none)
+    double Jz4;                          // Jz / 4 of the wrap bond
+};
+struct SdBlkWrapTile {
+    uint64_t base, pbase;                // stored-element offsets (global) of the tile and of its wrap partner tile
+    int js, jsp;                         // suffix popcounts
+    int b0;                              // prefix bit 0 (site 0)
+    bool pvalid;                         // the partner tile exists (0 <= jsp <= B)
+};
+SD_HD SdBlkWrapTile sd_blk_wrap_tile(const SdBlkParams &P, const uint64_t *W, uint64_t Pb) {
+    SdBlkWrapTile t;
+    const int A = P.A;
+    const uint64_t Pp = Pb ^ 1ULL;
+    t.b0 = (int)(Pb & 1ULL);
+    t.js = P.k - SD_POPC64(Pb);
+    t.jsp = P.k - SD_POPC64(Pp);
+    t.pvalid = t.jsp >= 0 && t.jsp <= SD_BLK_B;
+    t.base = 0; t.pbase = 0;
+    for (int q = 0; q < A; ++q) {
+        if (!((Pb >> q) & 1ULL)) t.base += W[q * (A + 1) + SD_POPC64(Pb & ((1ULL << q) - 1ULL))];
+        if (t.pvalid && !((Pp >> q) & 1ULL)) t.pbase += W[q * (A + 1) + SD_POPC64(Pp & ((1ULL << q) - 1ULL))];
+    }
+    return t;
+}
+// Row r = 0 .. 2^T - 1 of a tile is one (tail class jt, tail configuration e); the lanes of a warp walk its mid
+// configurations u.  own / part point at component 0 of the tile's / the partner tile's first stored element, out at the
+// tile's first element of the wrap vector.  Padding elements are never written: the wrap vector is zeroed once.
+struct SdBlkWrapRow {
+    int jt, jt2;                         // class of the row / of the partner row (-1: the bond does not act on this row)
+    uint32_t e, e2, nblk;
+    double d;                            // diagonal coefficient of the wrap bond on this row
+};
+SD_HD SdBlkWrapRow sd_blk_wrap_row(const SdBlkWrap &Wp, const SdBlkWrapTile &t, const SdBlkJs &I, int r) {
+    SdBlkWrapRow R;
+    int jt = 0, first = 0;
+    while (r >= first + sd_cbinom(SD_BLK_T, jt)) { first += sd_cbinom(SD_BLK_T, jt); ++jt; }
+    R.jt = jt; R.e = (uint32_t)(r - first); R.nblk = I.cls[jt].nblk;
+    const unsigned tau = sd_tail_cfg(SD_BLK_T, jt, (int)R.e);
+    const int tb = (int)((tau >> (SD_BLK_T - 1)) & 1u);
+    R.d = (tb == t.b0) ? Wp.Jz4 : -Wp.Jz4;
+    R.jt2 = -1; R.e2 = 0;
+    if (tb != t.b0 && Wp.J != 0.0 && t.pvalid) {
+        R.jt2 = tb ? jt - 1 : jt + 1;
+        R.e2 = (uint32_t)sd_tail_rank(SD_BLK_T, R.jt2, tau ^ (1u << (SD_BLK_T - 1)));
+    }
+    return R;
+}
+template <int NC>
+SD_HD void sd_blk_wrap_elem(const SdBlkWrap &Wp, const SdBlkWrapRow &R, const SdBlkJs &I, const SdBlkJs &Ip, uint32_t u,
+                            const double *own, const double *part, double *out) {
+    const size_t p = sd_blk_encode(I, NC, R.jt, R.e, u);
+    double v[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) v[c] = R.d * own[p * NC + c];
+    if (R.jt2 >= 0) {
+        const size_t p2 = sd_blk_encode(Ip, NC, R.jt2, R.e2, u);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) v[c] += Wp.J * part[p2 * NC + c];
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) out[p * NC + c] = v[c];
+}
 
 // ------------------------------------------------------------------ tile header
 struct alignas(16) SdBlkEnt {

@@ -71,6 +71,14 @@ SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdEpi &E, double *out_l
     double2 acc[EC], t0[EC], t1[EC];
 #pragma unroll
     for (int s = 0; s < EC; ++s) acc[s] = t0[s] = t1[s] = make_double2(0.0, 0.0);   // t0/t1: conditionally loaded below; left undefined they end up on the stack
+    if (P.addin != nullptr) {                                        // periodic chain: the wrap bond's terms (sd_blk_wrap_kernel)
+        const double *ap = P.addin + (H.base - P.shards.pstart[P.shards.rank]) * NC;
+#pragma unroll
+        for (int s = 0; s < EC; ++s) {
+            if (HALF && s == EC - 1) acc[s].x = ap[o[s]];
+            else acc[s] = *(const double2 *)(ap + o[s]);
+        }
+    }
 #define SD_LEAN_LOAD(t_, p_)                                                                  \
     do {                                                                                      \
         const double *q_ = (p_);                                                              \

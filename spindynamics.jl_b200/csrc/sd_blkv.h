@@ -9,37 +9,6 @@
 #include "sd_obs.h"
 
 #if defined(__CUDACC__)
-// Stored position p of a tile with class table I, for a vector of nc components -> (jt, e, u); false for padding.
-__device__ __forceinline__ bool sd_blk_decode(const SdBlkJs &I, int nc, uint32_t p, int &jt, uint32_t &e, uint32_t &u) {
-    jt = -1;
-    uint32_t rel = 0;
-#pragma unroll
-    for (int j = 0; j < SD_BLK_NCLS; ++j) {
-        const uint32_t len = I.cls[j].pitch * (uint32_t)sd_cbinom(SD_BLK_T, j);
-        if (jt < 0 && p >= I.cls[j].cb && p < I.cls[j].cb + len) { jt = j; rel = p - I.cls[j].cb; }
-    }
-    if (jt < 0) return false;
-    const uint32_t pitch = I.cls[jt].pitch;
-    const uint32_t nt = (uint32_t)sd_cbinom(SD_BLK_T, jt);
-    if (nc == 1 && (nt & 1u) && rel >= (nt - 1u) * pitch) {        // f64, odd class: last row is plain
-        e = nt - 1u; u = rel - (nt - 1u) * pitch;
-    } else if (nc == 1) {                                          // f64: pair rows (2s, 2s+1) of double2 per block
-        const uint32_t pr = rel / (2u * pitch), r2 = rel % (2u * pitch);
-        u = r2 >> 1; e = 2u * pr + (r2 & 1u);
-    } else {                                                       // c128: one row per tail configuration
-        e = rel / pitch; u = rel % pitch;
-    }
-    return u < I.cls[jt].nblk && e < nt;
-}
-// position of (jt, e, u) inside the tile for a vector of nc components (inverse of sd_blk_decode)
-__device__ __forceinline__ uint32_t sd_blk_encode(const SdBlkJs &I, int nc, int jt, uint32_t e, uint32_t u) {
-    const SdBlkCls &c = I.cls[jt];
-    const uint32_t nt = (uint32_t)sd_cbinom(SD_BLK_T, jt);
-    if (nc == 1 && (nt & 1u) && e == nt - 1u) return c.cb + e * c.pitch + u;
-    if (nc == 1) return c.cb + (e >> 1) * 2u * c.pitch + 2u * u + (e & 1u);
-    return c.cb + e * c.pitch + u;
-}
-
 struct SdBlkSzq {
     double ph_re[SD_MAX_L + 1], ph_im[SD_MAX_L + 1];   // e^{i q r}
     double normfact;                                    // L^-1/2
@@ -139,5 +108,31 @@ __global__ void __launch_bounds__(256) sd_blk_obs_kernel(const __grid_constant__
     }
     double *o = partials + ((size_t)blockIdx.x * nwarp + warp) * 128;
     o[lane] = mag[0]; o[32 + lane] = mag[1]; o[64 + lane] = zz[0]; o[96 + lane] = zz[1];
+}
+
+// The periodic wrap bond's terms for every stored element of the shard (sd_blk.h, "periodic wrap bond"): one CTA per tile
+// (grid-stride over the keys), a warp per (tail class, tail configuration) row, lanes = mid configurations.
+template <int NC>
+__global__ void __launch_bounds__(256) sd_blk_wrap_kernel(const __grid_constant__ SdBlkParams P, const __grid_constant__ SdBlkWrap Wp,
+                                                          const __grid_constant__ SdVecView psi, double *wrap_local) {
+    __shared__ SdBlkWrapTile s_t;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (uint64_t key = P.key_lo + blockIdx.x; key < P.key_hi; key += gridDim.x) {
+        const uint64_t Pb = __brevll(~key) >> (64 - P.A);
+        const int js = P.k - __popcll(Pb);
+        if (js < 0 || js > SD_BLK_B) continue;                         // uniform over the CTA
+        __syncthreads();
+        if (threadIdx.x == 0) s_t = sd_blk_wrap_tile(P, P.W, Pb);
+        __syncthreads();
+        const SdBlkWrapTile t = s_t;
+        const SdBlkJs &I = P.js[t.js], &Ip = P.js[t.pvalid ? t.jsp : t.js];
+        const double *own = psi.base[P.shards.rank] + (size_t)NC * t.base;
+        const double *part = t.pvalid ? psi.base[sd_blk_owner(P.shards, t.pbase)] + (size_t)NC * t.pbase : own;
+        double *out = wrap_local + (size_t)NC * (t.base - P.shards.pstart[P.shards.rank]);
+        for (int r = (int)warp; r < (1 << SD_BLK_T); r += (int)nwarp) {
+            const SdBlkWrapRow R = sd_blk_wrap_row(Wp, t, I, r);
+            for (uint32_t u = lane; u < R.nblk; u += 32u) sd_blk_wrap_elem<NC>(Wp, R, I, Ip, u, own, part, out);
+        }
+    }
 }
 #endif

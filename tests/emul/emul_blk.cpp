@@ -72,7 +72,12 @@ void run_tiles(const SdBlkHost &bh, const SdBlkParams &P, const SdVecView &psi, 
 
 }  // namespace
 
+static double g_wrap_J = 0.0, g_wrap_Jz = 0.0;                      // periodic wrap bond of the next emul_blk_apply calls
+
 extern "C" {
+
+// hop coefficient and Jz of the wrap bond (sites L-1, 0); (0, 0) = open chain
+void emul_blk_set_wrap(double J, double Jz) { g_wrap_J = J; g_wrap_Jz = Jz; }
 
 // Runs rank `rank` of `world` of the block kernel over full-length RANK-ORDERED host vectors (the
 // layout conversion the library does in sd_vec_upload/download is done here with sd_blk_pos_of_state).
@@ -163,6 +168,32 @@ int emul_blk_apply(int L, int k, const double *Jhop, const double *Jz, const dou
             mirror[g].alloc((size_t)(pstart[g + 1] - pstart[g]) * NC, NAN);
             view.base[g] = mirror[g].p - (int64_t)pstart[g] * NC;
         }
+    }
+    // periodic chain: the wrap pass of sd_blk_wrap_kernel (one "warp" per row, lanes = mid configurations) into a zeroed
+    // vector, which the item body adds in front of the epilogue
+    AlignedBuf wv;
+    if (g_wrap_J != 0.0 || g_wrap_Jz != 0.0) {
+        wv.alloc(nloc, 0.0);
+        SdBlkWrap Wp;
+        Wp.J = g_wrap_J; Wp.Jz4 = 0.25 * g_wrap_Jz;
+        for (uint64_t key = P.key_lo; key < P.key_hi; ++key) {
+            const uint64_t Pb = sd_blk_key_prefix(key, P.A);
+            const int js = P.k - SD_POPC64(Pb);
+            if (js < 0 || js > SD_BLK_B) continue;
+            const SdBlkWrapTile t = sd_blk_wrap_tile(P, P.W, Pb);
+            const SdBlkJs &I = P.js[t.js], &Ip = P.js[t.pvalid ? t.jsp : t.js];
+            const double *own = view.base[rank] + (size_t)NC * t.base;
+            const double *part = t.pvalid ? view.base[sd_blk_owner(P.shards, t.pbase)] + (size_t)NC * t.pbase : own;
+            double *wo = wv.p + (size_t)NC * (t.base - pstart[rank]);
+            for (int r = 0; r < (1 << SD_BLK_T); ++r) {
+                const SdBlkWrapRow R = sd_blk_wrap_row(Wp, t, I, r);
+                for (uint32_t u = 0; u < R.nblk; ++u) {
+                    if (NC == 2) sd_blk_wrap_elem<2>(Wp, R, I, Ip, u, own, part, wo);
+                    else sd_blk_wrap_elem<1>(Wp, R, I, Ip, u, own, part, wo);
+                }
+            }
+        }
+        P.addin = wv.p;
     }
     const uint64_t klo_all = P.key_lo, khi_all = P.key_hi;
     for (int j = 0; j < nchunks; ++j) {

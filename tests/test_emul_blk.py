@@ -399,3 +399,37 @@ def test_sharded_apply_with_planned_peer_ranges_and_weighted_shards(variant, L, 
         assert abs(complex(red[0], red[1]) - np.vdot(cplx(psi), cplx(nxt))) < 1e-9
         assert abs(red[2] - np.vdot(cplx(phi), cplx(nxt)).real) < 1e-9 and abs(red[3] - nxt @ nxt) < 1e-8
 
+
+
+@pytest.mark.parametrize("NC", [1, 2])
+@pytest.mark.parametrize("L,k", [(16, 8), (16, 3), (17, 9), (18, 9), (20, 10), (16, 16), (16, 1)])
+def test_periodic_wrap_bond_pass_and_add_in(emul, L, k, NC):
+    """XXZChain(boundary=:periodic) (SpinModel.jl:71-78) on the block path: the wrap pass (sd_blk_wrap_tile / _row / _elem,
+    the code of sd_blk_wrap_kernel) followed by the item body with the add-in, every epilogue, 1 .. 3 ranks -- against the
+    oracle's apply_H! on the model with the (L, 1) bonds."""
+    rng = np.random.default_rng(500 + L * 10 + k + NC)
+    Jhop, Jz, h = model_lists(L, rng)
+    Jw, Jzw = float(rng.uniform(0.3, 1.5)), float(rng.uniform(-1, 1))
+    hop = [(i + 1, i + 2, Jhop[i]) for i in range(L - 1)] + [(L, 1, Jw)]
+    zz = [(i + 1, i + 2, Jz[i]) for i in range(L - 1)] + [(L, 1, Jzw)]
+    m = orc.build_model(L, nup=k, hopping=hop, onsite_field=h, zz=zz)
+    states = np.ascontiguousarray(m.states, dtype=np.uint64)
+    N = len(states)
+    psi = rng.standard_normal(N * NC)
+    ref = oracle_apply(m, psi, NC)
+    emul.emul_blk_set_wrap.argtypes = [ctypes.c_double, ctypes.c_double]
+    emul.emul_blk_set_wrap.restype = None
+    emul.emul_blk_set_wrap(Jw, Jzw)
+    try:
+        for world in (1, 2, 3):
+            out, _, _, _ = run(emul, L, k, NC, world, states, psi, Jhop, Jz, h)
+            assert np.linalg.norm(out - ref) <= 1e-14 * max(1.0, np.linalg.norm(ref)), world
+        # fused epilogue on top of the add-in: (H psi - b psi) / a with the dot <psi, out>
+        a, b = 3.0, -0.4
+        out, red, _, _ = run(emul, L, k, NC, 1, states, psi, Jhop, Jz, h, mode=1, red=1, a=a, b=b)
+        want = (ref - b * psi) / a
+        assert np.linalg.norm(out - want) <= 1e-14 * max(1.0, np.linalg.norm(want))
+        if NC == 1:
+            assert abs(red[0] - float(psi @ want)) <= 1e-12 * max(1.0, abs(float(psi @ want)))
+    finally:
+        emul.emul_blk_set_wrap(0.0, 0.0)

@@ -107,6 +107,7 @@ CASES = [
     (10, 5, "open"), (12, 6, "open"), (12, 3, "open"), (13, 6, "open"), (14, 7, "open"), (14, 7, "periodic"),
     (16, 8, "open"), (16, 2, "open"), (16, 14, "open"), (18, 9, "open"), (20, 10, "open"), (15, 0, "open"),
     (15, 15, "open"), (12, None, "open"),
+    (16, 8, "periodic"), (17, 5, "periodic"), (18, 9, "periodic"), (16, 15, "periodic"),   # block kernel + wrap pass
 ]
 
 
@@ -131,7 +132,9 @@ def test_tiled_path_selected_for_open_chain():
     assert paths_of(sd.XXZChain(20, nup=10)) == ["block", "tiled", "generic"]
     with pytest.raises(NotImplementedError):
         sd.XXZChain(14, nup=7).set_path("block")
-    assert sd.XXZChain(16, nup=8, boundary="periodic").info["kernel_path"] == "generic"
+    assert sd.XXZChain(16, nup=8, boundary="periodic").info["kernel_path"] == "block"    # wrap pass + block kernel
+    assert paths_of(sd.XXZChain(16, nup=8, boundary="periodic")) == ["block", "generic"]    # the tiled kernel has no wrap bond
+    assert sd.XXZChain(14, nup=7, boundary="periodic").info["kernel_path"] == "generic"
     assert sd.XXZChain(12).info["kernel_path"] == "generic"
     with pytest.raises(NotImplementedError):
         sd.XXZChain(12).set_path("tiled")

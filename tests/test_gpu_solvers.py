@@ -87,7 +87,7 @@ def test_zero_start_vector_error():
 
 # ------------------------------------------------------------ vs the oracle
 
-@pytest.mark.parametrize("L,nup,boundary", [(12, 6, "open"), (16, 8, "open"), (10, 5, "periodic"), (10, None, "open")])
+@pytest.mark.parametrize("L,nup,boundary", [(12, 6, "open"), (16, 8, "open"), (10, 5, "periodic"), (10, None, "open"), (16, 8, "periodic")])
 def test_recurrences_match_oracle(L, nup, boundary):
     m = sd.XXZChain(L, Jxy=1.0, Jz=0.8, hz=0.05, nup=nup, boundary=boundary)
     om = orc.XXZChain(L, Jxy=1.0, Jz=0.8, hz=0.05, nup=nup, boundary=boundary)
