@@ -178,7 +178,7 @@ def cpu_reference(L_sample, reps, L_target=32, ranked=True, warm=True):
     return res, times
 
 
-def sampled_row_parity(model, out, scale, first, count, nrows, rank, cplx=False):
+def sampled_row_parity(model, out, scale, first, count, nrows, rank, cplx=False, periodic=False):
     """max over sampled rows r of this rank's shard of |out[r] - (H psi)[r]| / max(|(H psi)[r]|, scale), with (H psi)[r]
     from the oracle's row formula (oracle.c orc_row_seeded_f64 restates Hamiltonian.jl:223-269 for one state and
     regenerates psi from the counter).  Checker only: nothing here is timed."""
@@ -193,6 +193,9 @@ def sampled_row_parity(model, out, scale, first, count, nrows, rank, cplx=False)
     assert present.all()
     hop = [(i, i + 1, 0.5) for i in range(1, L)]
     zz = [(i, i + 1, 1.0) for i in range(1, L)]
+    if periodic:                                                 # SpinModel.jl:71-78
+        hop.append((L, 1, 0.5))
+        zz.append((L, 1, 1.0))
     worst = 0.0
     for r, g in zip(rows, got):
         state = int(model.unrank(int(r), 1)[0])
@@ -352,6 +355,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--L", type=int, default=32, help="chain length (default: the metric's L=32)")
     ap.add_argument("--dtype", default="f64", choices=["f64", "c128"])
+    ap.add_argument("--boundary", default="open", choices=["open", "periodic"], help="periodic: the wrap-bond pass + block kernel (not the headline metric)")
     ap.add_argument("--cpu-L", type=int, default=28, help="chain length of the bounded cpu_baseline sample of the GPU arm")
     ap.add_argument("--cpu-L-ref", type=int, default=0, help="--impl reference: force the chain length (default: L itself if the host has the memory)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
@@ -393,7 +397,7 @@ def main():
     L, nup = args.L, args.L // 2
     dtype = np.float64 if args.dtype == "f64" else np.complex128
     esz = 8 if args.dtype == "f64" else 16
-    model = sd.XXZChain(L, Jxy=1.0, Jz=1.0, hz=0.0, nup=nup, ctx=ctx)
+    model = sd.XXZChain(L, Jxy=1.0, Jz=1.0, hz=0.0, nup=nup, boundary=args.boundary, ctx=ctx)
     if args.path:
         model.set_path(args.path)
     N = model.dim
@@ -433,7 +437,8 @@ def main():
     # oracle regenerates the counter-based psi, so this works at sizes no host can hold).  Outside the timed region.
     parity = None
     if not args.no_parity:
-        parity = sampled_row_parity(model, out, psi_scale, first, count, args.parity_rows, rank, args.dtype == "c128")
+        parity = sampled_row_parity(model, out, psi_scale, first, count, args.parity_rows, rank, args.dtype == "c128",
+                                    args.boundary == "periodic")
         if dist is not None:
             import torch
             t = torch.tensor([parity["max_rel_err"]], device="cuda", dtype=torch.float64)
@@ -545,7 +550,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": args.dtype, "data": "synthetic (counter-based seeded psi, splitmix64)",
-                "config": {"workload": f"XXZChain L={L} nup={nup} open Jxy=Jz=1 hz=0, {args.dtype} H.psi, N={N} states "
+                "config": {"workload": f"XXZChain L={L} nup={nup} {args.boundary} Jxy=Jz=1 hz=0, {args.dtype} H.psi, N={N} states "
                                        f"({N * esz / 1e9:.2f} GB per vector)",
                            "l2": "inputs >> 126 MB L2, no flush needed" if N * esz > 1e9 else "WARNING: fits L2",
                            "sharding": f"{world} contiguous rank ranges, NVLink peer reads" if world > 1 else "single GPU",
