@@ -171,6 +171,7 @@ static int sd_ctx_init(int device, int rank, int world, const void *id128, sd_ct
     SD_ARG(device >= 0 && device < ndev, "device %d out of range (0..%d)", device, ndev - 1);
     sd_ctx *c = new (std::nothrow) sd_ctx;
     if (!c) return sd_fail(SD_ERR_NOMEM, "out of host memory");
+    struct Guard { sd_ctx *c; ~Guard() { if (c) sd_ctx_free(c); } } guard{c};   // early returns below release what was allocated
     c->device = device; c->rank = rank; c->world = world;
     SD_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
@@ -195,6 +196,7 @@ static int sd_ctx_init(int device, int rank, int world, const void *id128, sd_ct
         SD_NCCL(g_nccl.CommInitRank(&c->comm, world, id, rank));
         SD_CUDA(cudaMalloc(&c->d_ipc, (size_t)(world + 1) * 128));
     }
+    guard.c = nullptr;
     *out = c;
     return SD_OK;
 }
@@ -419,12 +421,13 @@ int sd_model_create(sd_ctx *ctx, int L, int nup, const sd_bond *hop, int nhop, c
     SD_LOCK(ctx); SD_TRY(sd_use(ctx));
     sd_model *m = new (std::nothrow) sd_model;
     if (!m) return sd_fail(SD_ERR_NOMEM, "out of host memory");
+    struct Guard { sd_model *m; ~Guard() { if (m) sd_model_free(m); } } guard{m};   // early returns below release the model and its device tables
     m->ctx = ctx; m->L = L; m->k = nup;
     m->N = nup < 0 ? (1ULL << L) : ctx->binom[L * SD_BINOM_DIM + nup];
     bool all_nn = true, wrap = false;                               // every bond nearest-neighbour, except possibly the wrap bond
     for (int b = 0; b < nhop; ++b) {
         const int64_t i = hop[b].i, j = hop[b].j;
-        if (i < 1 || i > L || j < 1 || j > L) { delete m; return sd_fail(SD_ERR_ARG, "hopping site outside 1..L"); }
+        if (i < 1 || i > L || j < 1 || j > L) return sd_fail(SD_ERR_ARG, "hopping site outside 1..L");
         if (i == j) continue;                       // bits never differ: the reference skips it
         const int a = (int)std::min(i, j) - 1, c = (int)std::max(i, j) - 1;
         m->hop_a.push_back(a); m->hop_b.push_back(c); m->hop_J.push_back(hop[b].J);
@@ -433,7 +436,7 @@ int sd_model_create(sd_ctx *ctx, int L, int nup, const sd_bond *hop, int nhop, c
     }
     for (int b = 0; b < nzz; ++b) {
         const int64_t i = zz[b].i, j = zz[b].j;
-        if (i < 1 || i > L || j < 1 || j > L) { delete m; return sd_fail(SD_ERR_ARG, "zz site outside 1..L"); }
+        if (i < 1 || i > L || j < 1 || j > L) return sd_fail(SD_ERR_ARG, "zz site outside 1..L");
         const int a = (int)std::min(i, j) - 1, c = (int)std::max(i, j) - 1;
         m->zz_a.push_back(a); m->zz_b.push_back(c); m->zz_J.push_back(zz[b].J);
         if (a == 0 && c == L - 1 && L > 2) { wrap = true; m->wrap_zz += zz[b].J; }
@@ -522,7 +525,7 @@ int sd_model_create(sd_ctx *ctx, int L, int nup, const sd_bond *hop, int nhop, c
         for (int g = 0; g <= ctx->world; ++g) {
             uint64_t base = 0;
             m->tile[1].keys[g] = sd_tile_key_of_rank(m->tile[1].host, bounds[g], &base);
-            if (base != bounds[g]) { delete m; return sd_fail(SD_ERR_UNSUPPORTED, "internal: shard bound not tile aligned"); }
+            if (base != bounds[g]) return sd_fail(SD_ERR_UNSUPPORTED, "internal: shard bound not tile aligned");
         }
     } else {
         for (int g = 0; g <= ctx->world; ++g)
@@ -543,6 +546,7 @@ int sd_model_create(sd_ctx *ctx, int L, int nup, const sd_bond *hop, int nhop, c
             m->blk.norder = (uint32_t)ord.size();
         }
     }
+    guard.m = nullptr;
     *model = m;
     return SD_OK;
 }
@@ -1281,11 +1285,8 @@ static int sd_apply_impl(sd_model *m, sd_vec *out, const sd_vec *psi, SdEpi epi,
         const int T = m->tile_T[nc - 1];
 #define SD_LAUNCH_TILE3(NC_, T_, PLAIN_, NTHR_)                                                             \
     do {                                                                                                    \
-        static size_t set_smem = 0;                                                                         \
-        if (t.smem > set_smem) {                                                                            \
-            SD_CUDA(cudaFuncSetAttribute(sd_tile_apply_kernel<NC_, T_, PLAIN_, NTHR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem)); \
-            set_smem = t.smem;                                                                              \
-        }                                                                                                   \
+        /* per device and cheap: set on every launch, no process-global cache (several contexts / GPUs per process) */ \
+        SD_CUDA(cudaFuncSetAttribute(sd_tile_apply_kernel<NC_, T_, PLAIN_, NTHR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem)); \
         sd_tile_apply_kernel<NC_, T_, PLAIN_, NTHR_><<<grid, NTHR_, t.smem, c->stream>>>(P, psi->view, out_vbase, epi, t.cap); \
     } while (0)
 #define SD_LAUNCH_TILE2(NC_, T_, PLAIN_)                                                                    \
