@@ -49,7 +49,7 @@ def report(name, err, tol):
         print(f"[world={world}] {name}: err={e:.2e} tol={tol:.0e} {'OK' if good else 'FAIL'}", flush=True)
 
 
-cases = [(16, 8, "open"), (18, 9, "open"), (20, 10, "open"), (20, 7, "open"), (17, 8, "open"), (16, 8, "periodic"), (12, None, "open")]
+cases = [(16, 8, "open"), (18, 9, "open"), (20, 10, "open"), (20, 7, "open"), (17, 8, "open"), (16, 8, "periodic"), (18, 7, "periodic"), (12, None, "open")]
 for (L, nup, bc) in cases:
     for dtype in (np.float64, np.complex128):
         kw = dict(Jxy=0.7, Jz=1.3, hz=0.2, nup=nup, boundary=bc)

@@ -370,7 +370,7 @@ static int sd_blk_setup(sd_model *m) {
     for (size_t i = 0; i < m->zz_a.size(); ++i) if (m->zz_b[i] == m->zz_a[i] + 1) Jz[m->zz_a[i]] += m->zz_J[i];
     if (!sd_blk_build(L, m->k, Jhop.data(), Jz.data(), m->field.data(), b.host)) return SD_OK;
     b.threads = sd_env_int("SD_BLKL_THREADS", 640);
-    b.pfp = sd_env_int("SD_BLK_PFP", 0);
+    b.pfp = sd_env_int("SD_BLK_PFP", 7);      // all prefix partners of the tile the consumers reach next (profiles/round2_n_ab.txt, round2_o_blkenv.txt)
     if (b.threads != 512 && b.threads != 768) b.threads = 640;
     for (int w = 0; w < 2; ++w) {
         const int nc = w + 1;

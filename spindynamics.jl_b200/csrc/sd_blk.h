@@ -220,6 +220,47 @@ SD_HD void sd_blk_wrap_elem(const SdBlkWrap &Wp, const SdBlkWrapRow &R, const Sd
 #pragma unroll
     for (int c = 0; c < NC; ++c) out[p * NC + c] = v[c];
 }
+// A work unit of the wrap pass = what one warp walks with its lanes over the mid configurations u: for c128 one row
+// (32 per tile), for f64 one PAIR row (tail configurations 2s, 2s+1 of a class share 16-byte slots: own value and result
+// move as double2, coalesced; 18 per tile) or the plain last row of an odd class.
+SD_HDC int sd_blk_wrap_units(int nc) { return nc == 2 ? (1 << SD_BLK_T) : 18; }
+static_assert(SD_BLK_T == 5, "18 pair rows: sum over jt of ceil(C(5, jt) / 2)");
+template <int NC>
+struct SdBlkWrapUnit {
+    SdBlkWrapRow r0, r1;                 // f64: rows 2s and 2s+1 (r1.nblk = 0: plain last row); c128: r0 only
+    uint32_t nblk;
+};
+template <int NC>
+SD_HD SdBlkWrapUnit<NC> sd_blk_wrap_unit(const SdBlkWrap &Wp, const SdBlkWrapTile &t, const SdBlkJs &I, int unit) {
+    SdBlkWrapUnit<NC> U;
+    if (NC == 2) {
+        U.r0 = sd_blk_wrap_row(Wp, t, I, unit);
+        U.r1 = U.r0; U.r1.nblk = 0;
+        U.nblk = U.r0.nblk;
+        return U;
+    }
+    int jt = 0, first_unit = 0, first_row = 0;
+    while (unit >= first_unit + (sd_cbinom(SD_BLK_T, jt) + 1) / 2) {
+        first_unit += (sd_cbinom(SD_BLK_T, jt) + 1) / 2; first_row += sd_cbinom(SD_BLK_T, jt); ++jt;
+    }
+    const int s = unit - first_unit, nt = sd_cbinom(SD_BLK_T, jt);
+    U.r0 = sd_blk_wrap_row(Wp, t, I, first_row + 2 * s);
+    if (2 * s + 1 < nt) U.r1 = sd_blk_wrap_row(Wp, t, I, first_row + 2 * s + 1);
+    else { U.r1 = U.r0; U.r1.nblk = 0; }
+    U.nblk = U.r0.nblk;
+    return U;
+}
+template <int NC>
+SD_HD void sd_blk_wrap_apply(const SdBlkWrap &Wp, const SdBlkWrapUnit<NC> &U, const SdBlkJs &I, const SdBlkJs &Ip, uint32_t u,
+                             const double *own, const double *part, double *out) {
+    if (NC == 2 || U.r1.nblk == 0) { sd_blk_wrap_elem<NC>(Wp, U.r0, I, Ip, u, own, part, out); return; }
+    const size_t p = sd_blk_encode(I, 1, U.r0.jt, U.r0.e, u);      // even tail configuration of the pair: 16-byte aligned slot
+    const double2 o = *(const double2 *)(own + p);
+    double2 v = make_double2(U.r0.d * o.x, U.r1.d * o.y);
+    if (U.r0.jt2 >= 0) v.x += Wp.J * part[sd_blk_encode(Ip, 1, U.r0.jt2, U.r0.e2, u)];
+    if (U.r1.jt2 >= 0) v.y += Wp.J * part[sd_blk_encode(Ip, 1, U.r1.jt2, U.r1.e2, u)];
+    *(double2 *)(out + p) = v;
+}
 
 // ------------------------------------------------------------------ tile header
 struct alignas(16) SdBlkEnt {

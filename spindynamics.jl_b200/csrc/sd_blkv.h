@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) sd_blk_obs_kernel(const __grid_constant__
 }
 
 // The periodic wrap bond's terms for every stored element of the shard (sd_blk.h, "periodic wrap bond"): one CTA per tile
-// (grid-stride over the keys), a warp per (tail class, tail configuration) row, lanes = mid configurations.
+// (grid-stride over the keys), a warp per work unit (c128: one row; f64: one pair row), lanes = mid configurations.
 template <int NC>
 __global__ void __launch_bounds__(256) sd_blk_wrap_kernel(const __grid_constant__ SdBlkParams P, const __grid_constant__ SdBlkWrap Wp,
                                                           const __grid_constant__ SdVecView psi, double *wrap_local) {
@@ -129,9 +129,9 @@ __global__ void __launch_bounds__(256) sd_blk_wrap_kernel(const __grid_constant_
         const double *own = psi.base[P.shards.rank] + (size_t)NC * t.base;
         const double *part = t.pvalid ? psi.base[sd_blk_owner(P.shards, t.pbase)] + (size_t)NC * t.pbase : own;
         double *out = wrap_local + (size_t)NC * (t.base - P.shards.pstart[P.shards.rank]);
-        for (int r = (int)warp; r < (1 << SD_BLK_T); r += (int)nwarp) {
-            const SdBlkWrapRow R = sd_blk_wrap_row(Wp, t, I, r);
-            for (uint32_t u = lane; u < R.nblk; u += 32u) sd_blk_wrap_elem<NC>(Wp, R, I, Ip, u, own, part, out);
+        for (int unit = (int)warp; unit < sd_blk_wrap_units(NC); unit += (int)nwarp) {
+            const SdBlkWrapUnit<NC> U = sd_blk_wrap_unit<NC>(Wp, t, I, unit);
+            for (uint32_t u = lane; u < U.nblk; u += 32u) sd_blk_wrap_apply<NC>(Wp, U, I, Ip, u, own, part, out);
         }
     }
 }
