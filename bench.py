@@ -279,6 +279,28 @@ def run_configs(args):
                       "gpu_s": t_gpu3, "gpu_ms_per_moment": t_gpu3 * 1e3 / (M - 1),
                       "cpu_port_ms_per_moment": t_cpu3 * 1e3 / (Mc - 1), "cpu_sample": f"{Mc} moments of the same recurrence on {host_threads()} threads",
                       "cpu_port_s_extrapolated": t_cpu3 / (Mc - 1) * (M - 1), "sum_S_dw": float(np.sum(S3) * (w3[1] - w3[0]))}
+    # ---- config 3 as BASELINE.json states it: q = momenta(model) (28 of them).  The q-batched path (one [state][q] multi-vector,
+    # one fused kernel per moment for all momenta) against the per-momentum loop, on a reduced moment count so that the leg
+    # stays within seconds; both scale linearly in the number of moments.
+    try:
+        qs = sd.momenta(m)
+        Mq = 48
+        sd.kpm_sqw(psi0, m, qs, w3, a=a, b=b, kpm_m=4, q_batch=True)             # warm-up
+        ctx.sync()
+        t0 = time.perf_counter()
+        Sb = sd.kpm_sqw(psi0, m, qs, w3, a=a, b=b, kpm_m=Mq, q_batch=True)
+        ctx.sync()
+        t_b = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        Sl = sd.kpm_sqw(psi0, m, qs[:4], w3, a=a, b=b, kpm_m=Mq, q_batch=False)
+        ctx.sync()
+        t_l = (time.perf_counter() - t0) * len(qs) / 4
+        res["config3_all_momenta"] = {"what": f"XXZChain L=28 nup=14: kpm_sqw over the {len(qs)} momenta, {Mq} moments (timing sample; linear in the moments)",
+                                      "batched_s": t_b, "batched_ms_per_moment_and_momentum": t_b * 1e3 / ((Mq - 1) * len(qs)),
+                                      "q_loop_s_extrapolated_from_4_momenta": t_l, "q_loop_ms_per_moment_and_momentum": t_l * 1e3 / ((Mq - 1) * len(qs)),
+                                      "batched_vs_loop_rel_l2": float(np.linalg.norm(Sb[:4] - Sl) / max(np.linalg.norm(Sl), 1e-300))}
+    except Exception as exc:                                         # noqa: BLE001  (a newer leg must not cost the others)
+        res["config3_all_momenta"] = {"error": repr(exc)[:300]}
     print(json.dumps({"configs": res}), flush=True)
 
 
