@@ -280,6 +280,7 @@ struct alignas(16) SdBlkHdr {
     double Jx;                           // hop coefficient of the prefix|mid bond (0: none)
     const double *xptr;                  // stored base of the crossing partner tile (component 0)
     SdBlkEnt nb[SD_BLK_MAXA + 1];        // neighbour tiles of the active prefix bonds (one LDS.128 per entry); entry nnb: the crossing bond (if active)
+    unsigned char nbloc[SD_BLK_MAXA + 3];   // entry lives in this rank's shard (the producer's L2 prefetch skips peer memory); [nnb]: the crossing partner
     double usum[SD_NSLOT][SD_BLK_MAXUNITS];   // per-unit reduction results (deterministic: summed in unit order)
 };
 
@@ -335,8 +336,10 @@ SD_HD void sd_blk_hdr_fill(const SdBlkParams &P, const SdBlkHdrLane &l, uint64_t
         const uint64_t nbase = bit ? base + dl : base - dl;
         const unsigned lt = (1u << q) - 1u;
         const int slot = ((farmask >> q) & 1u) ? SD_POPC32(actmask & farmask & lt) : nfar + SD_POPC32(actmask & ~farmask & lt);
-        H.nb[slot].p = psi.base[sd_blk_owner(P.shards, nbase)] + (size_t)NC * nbase;
+        const int owner = sd_blk_owner(P.shards, nbase);
+        H.nb[slot].p = psi.base[owner] + (size_t)NC * nbase;
         H.nb[slot].J = P.Jhop[q];
+        H.nbloc[slot] = owner == P.shards.rank ? 1 : 0;
     }
     if (q == A - 1) {                                             // prefix|mid crossing bond
         const int jsx = bit ? js + 1 : js - 1;
@@ -345,11 +348,13 @@ SD_HD void sd_blk_hdr_fill(const SdBlkParams &P, const SdBlkHdrLane &l, uint64_t
         const uint64_t nbase = bit ? base + l.wq : base - l.wq;
         H.jsx = jsx;
         H.Jx = ok ? J : 0.0;
-        H.xptr = ok ? psi.base[sd_blk_owner(P.shards, nbase)] + (size_t)NC * nbase : nullptr;
+        const int xowner = ok ? sd_blk_owner(P.shards, nbase) : P.shards.rank;
+        H.xptr = ok ? psi.base[xowner] + (size_t)NC * nbase : nullptr;
         if (ok) {                                                 // the crossing bond as entry nnb of the stream list
             const int nnb = SD_POPC32(actmask);
             H.nb[nnb].p = H.xptr;
             H.nb[nnb].J = J;
+            H.nbloc[nnb] = xowner == P.shards.rank ? 1 : 0;
         }
         H.bP = bit;
         const double sl = bit ? 0.5 : -0.5;
@@ -626,17 +631,19 @@ __device__ __forceinline__ void sd_blk_producer(const SdBlkParams &P, const SdBl
         // L2 bulk prefetch of the partner tiles by the producer (no consumer instruction).  Measured at L = 32
         // (profiles/round2_n_ab.txt): issued for the tile just handed to the consumers' queue it thrashes (all entries:
         // 20.9 GB of DRAM reads, 5.91 ms); one tile later -- for the tile the consumers reach next -- it lifts the L2 hit
-        // rate from 53 to 62 % at 15.3 GB and takes 5.77 -> 5.40 ms.  Peer memory is never prefetched (pathologically slow).
-        if ((P.pfp & 1) && P.shards.world == 1) {              // partner tiles of the prefix bonds have the tile's own js, i.e. its size
+        // rate from 53 to 62 % at 15.3 GB and takes 5.77 -> 5.40 ms.  Peer memory is never prefetched (pathologically slow): sharded, only the partner tiles in
+        // this rank's own shard are (nbloc).
+        if (P.pfp & 1) {                                       // partner tiles of the prefix bonds have the tile's own js, i.e. its size
             unsigned late = (P.pfp & 8) ? 2u : ((P.pfp & 2) ? 1u : 0u);
             if (late > (unsigned)nbuf - 1u) late = (unsigned)nbuf - 1u;   // the header of that tile must still be in its buffer
             if (i >= late) {
                 const SdBlkHdr &Hp = S.hdr[((unsigned)b + (unsigned)nbuf - late) % (unsigned)nbuf];
                 const int cnt = (P.pfp & 4) ? Hp.nnb : Hp.nfar;
                 if ((int)lane < cnt) {
-                    const uint32_t pb = S.js[Hp.js].size_pad * (uint32_t)(NC * 8);
+                    const uint32_t pb = Hp.nbloc[lane] ? S.js[Hp.js].size_pad * (uint32_t)(NC * 8) : 0u;   // local tiles only
+                    if (pb)
                     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(Hp.nb[lane].p), "r"(pb) : "memory");
-                } else if ((P.pfp & 16) && (int)lane == cnt && Hp.xptr != nullptr) {   // the prefix|mid crossing partner (its own js)
+                } else if ((P.pfp & 16) && (int)lane == cnt && Hp.xptr != nullptr && Hp.nbloc[Hp.nnb]) {   // the prefix|mid crossing partner (its own js)
                     const uint32_t pb = S.js[Hp.jsx].size_pad * (uint32_t)(NC * 8);
                     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(Hp.xptr), "r"(pb) : "memory");
                 }
