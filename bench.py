@@ -383,7 +383,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the sampled-row check of H.psi against the oracle")
-    ap.add_argument("--parity-rows", type=int, default=48, help="sampled rows per rank")
+    ap.add_argument("--parity-rows", type=int, default=256, help="sampled rows per rank")
     ap.add_argument("--no-solve", action="store_true", help="skip the end-to-end Lanczos solve leg")
     ap.add_argument("--solve-m", type=int, default=30)
     ap.add_argument("--solve-only", action="store_true", help="(internal) run only the solve leg and print {\"solve\": ...}")

@@ -337,6 +337,7 @@ static int sd_scratch_raw(sd_ctx *c, int which, size_t bytes, double **p);
 // staging buffer for work on the compute stream: whatever the copy streams still do with it comes first
 int sd_scratch(sd_ctx *c, int which, size_t bytes, double **p) {
     SD_TRY(sd_copy_join(c));
+    c->stage_touched[which] = true;
     return sd_scratch_raw(c, which, bytes, p);
 }
 static int sd_scratch_raw(sd_ctx *c, int which, size_t bytes, double **p) {
@@ -614,6 +615,7 @@ int sd_model_set_path(sd_model *m, int kernel_path) {
     // the block kernel works on block-layout vectors, the other two on rank-ordered ones: the
     // layout can only change while no vector of the model is alive
     const bool want_blk = kernel_path == SD_PATH_BLOCK;
+    if (want_blk != m->blk_layout) { SD_LOCK(m->ctx); sd_pool_drain(m); }   // idle work vectors have the old layout
     if (want_blk != m->blk_layout && m->live_vecs > 0)
         return sd_fail(SD_ERR_UNSUPPORTED, "cannot switch between the block kernel and the rank-ordered kernels while %d vectors of the model are alive", m->live_vecs);
     if (kernel_path == SD_PATH_GENERIC) { m->path = SD_PATH_GENERIC; m->blk_layout = false; return SD_OK; }
@@ -909,15 +911,17 @@ int sd_vec_upload_async(sd_vec *v, const void *host) {
     SD_TRY(sd_before_write(c, v));
     if (v->layout) {
         // pinned host -> rank-ordered staging on the h2d stream, chunk by chunk; the permute of chunk i into block layout
-        // runs on the compute stream while chunk i + 1 is on the wire.  The h2d stream starts when the compute stream
-        // has finished what was enqueued before this call (the permutes of the previous upload read the same staging).
+        // runs on the compute stream while chunk i + 1 is on the wire.
         sd_model *m = v->model;
         SD_TRY(sd_copy_init(c));
         sd_copy_chunks(m);
         double *st = nullptr;
         SD_TRY(sd_scratch_raw(c, 0, sd_vec_logical_bytes(v) + 16, &st));
         const size_t e = 2 * SD_COPY_CHUNKS, esz = (size_t)v->nc * sizeof(double);
-        SD_CUDA(cudaEventRecord(c->ev_copy[e], c->stream));
+        // the staging buffer is free once the permutes of the previous upload are done: wait for exactly that, not for the
+        // whole compute stream (which may be parked behind a download), so uploads run one step ahead of the kernels
+        if (c->stage_touched[0] || !c->up_event) SD_CUDA(cudaEventRecord(c->ev_copy[e], c->stream));
+        c->stage_touched[0] = false;
         SD_CUDA(cudaStreamWaitEvent(c->h2d, c->ev_copy[e], 0));
         for (size_t i = 0; i + 1 < m->cp_keys.size(); ++i) {
             const size_t off = m->cp_ranks[i] * esz, len = (m->cp_ranks[i + 1] - m->cp_ranks[i]) * esz;
@@ -926,6 +930,8 @@ int sd_vec_upload_async(sd_vec *v, const void *host) {
             SD_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy[i], 0));
             SD_TRY(sd_blk_permute_range(v, st, v->nc, 0, m->cp_keys[i], m->cp_keys[i + 1]));
         }
+        SD_CUDA(cudaEventRecord(c->ev_copy[e], c->stream));         // staging free again
+        c->up_event = true;
         return SD_OK;                                               // the compute stream has waited for every chunk: nothing pending
     }
     SD_CUDA(cudaMemcpyAsync(v->d, host, sd_vec_bytes(v), cudaMemcpyHostToDevice, c->stream));

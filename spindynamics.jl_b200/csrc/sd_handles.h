@@ -98,6 +98,8 @@ struct sd_ctx {
     std::vector<cudaEvent_t> ev_copy;         // [2 * SD_COPY_CHUNKS + 4]: per-chunk events up / down, fork, joins, d2h done
     bool copy_pending = false;                // work may still be running on h2d / d2h that the compute stream has not waited for
     bool d2h_pending = false;                 // the download staging buffer is still being read by the d2h stream
+    bool up_event = false;                    // ev_copy[fork] marks the end of the previous upload's permutes (the upload staging buffer is free after it)
+    bool stage_touched[2] = {false, false};   // a compute-stream user (sd_scratch) has had the staging buffer since the last asynchronous copy
     const double **d_vtab = nullptr;          // sd_reorth_step: device table of the basis vectors' pointers (+ host mirror)
     std::vector<const double *> h_vtab;
     int vtab_count = 0;
