@@ -553,9 +553,7 @@ def main():
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         knobs = {k: v for k, v in os.environ.items() if k.startswith(("SD_BLK", "SD_HALO", "SD_SHARD")) or k in ("SD_FAR_MB", "SD_FORCE_GENERIC")}
-        kname = {"block": "sd_blk_apply_kernel", "tiled": "sd_tile_apply_kernel"}.get(model.info["kernel_path"], "sd_generic_apply_kernel")
-        if kname == "sd_blk_apply_kernel" and args.dtype == "f64" and knobs.get("SD_BLK_RING", "0") not in ("0", ""):
-            kname = "sd_blkr_apply_kernel"                   # experimental ring variant (sd_blkr.h)
+        kname = {"block": "sd_blkl_apply_kernel", "tiled": "sd_tile_apply_kernel"}.get(model.info["kernel_path"], "sd_generic_apply_kernel")
         if os.path.exists(tpath) and world == 1 and not knobs:   # the ncu capture is of the default single-GPU launch
             try:
                 with open(tpath) as f:

@@ -1266,9 +1266,9 @@ static int sd_apply_impl(sd_model *m, sd_vec *out, const sd_vec *psi, SdEpi epi,
             }
             SdBlkWrap Wp;
             Wp.J = m->wrap_hop; Wp.Jz4 = 0.25 * m->wrap_zz;
-            const unsigned wg = (unsigned)std::min<uint64_t>(nkeys, (uint64_t)c->sm_count * 8);
-            if (nc == 2) sd_blk_wrap_kernel<2><<<wg, 256, 0, c->stream>>>(P, Wp, psi->view, wv);
-            else sd_blk_wrap_kernel<1><<<wg, 256, 0, c->stream>>>(P, Wp, psi->view, wv);
+            const unsigned wg = (unsigned)std::min<uint64_t>(nkeys, (uint64_t)c->sm_count * 16);
+            if (nc == 2) sd_blk_wrap_kernel<2><<<wg, SD_WRAP_THREADS, 0, c->stream>>>(P, Wp, psi->view, wv);
+            else sd_blk_wrap_kernel<1><<<wg, SD_WRAP_THREADS, 0, c->stream>>>(P, Wp, psi->view, wv);
             SD_TRY(sd_launch_check(c, "sd_blk_wrap_kernel"));
             P.addin = wv;
         }

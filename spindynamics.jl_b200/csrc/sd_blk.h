@@ -190,19 +190,26 @@ struct SdBlkWrapRow {
     uint32_t e, e2, nblk;
     double d;                            // diagonal coefficient of the wrap bond on this row
 };
-SD_HD SdBlkWrapRow sd_blk_wrap_row(const SdBlkWrap &Wp, const SdBlkWrapTile &t, const SdBlkJs &I, int r) {
-    SdBlkWrapRow R;
+// what a row is, independent of the tile (the kernel keeps the 2^T of them in shared memory)
+struct SdBlkWrapStatic {
+    signed char jt, e, tb, e2;           // class, tail configuration in the class, tail bit T-1, index of the configuration with that bit flipped in class jt -+ 1
+};
+SD_HD SdBlkWrapStatic sd_blk_wrap_static(int r) {
+    SdBlkWrapStatic S;
     int jt = 0, first = 0;
     while (r >= first + sd_cbinom(SD_BLK_T, jt)) { first += sd_cbinom(SD_BLK_T, jt); ++jt; }
-    R.jt = jt; R.e = (uint32_t)(r - first); R.nblk = I.cls[jt].nblk;
-    const unsigned tau = sd_tail_cfg(SD_BLK_T, jt, (int)R.e);
+    const unsigned tau = sd_tail_cfg(SD_BLK_T, jt, r - first);
     const int tb = (int)((tau >> (SD_BLK_T - 1)) & 1u);
-    R.d = (tb == t.b0) ? Wp.Jz4 : -Wp.Jz4;
+    S.jt = (signed char)jt; S.e = (signed char)(r - first); S.tb = (signed char)tb;
+    S.e2 = (signed char)sd_tail_rank(SD_BLK_T, tb ? jt - 1 : jt + 1, tau ^ (1u << (SD_BLK_T - 1)));
+    return S;
+}
+SD_HD SdBlkWrapRow sd_blk_wrap_row(const SdBlkWrap &Wp, const SdBlkWrapTile &t, const SdBlkJs &I, const SdBlkWrapStatic &S) {
+    SdBlkWrapRow R;
+    R.jt = S.jt; R.e = (uint32_t)S.e; R.nblk = I.cls[S.jt].nblk;
+    R.d = (S.tb == t.b0) ? Wp.Jz4 : -Wp.Jz4;
     R.jt2 = -1; R.e2 = 0;
-    if (tb != t.b0 && Wp.J != 0.0 && t.pvalid) {
-        R.jt2 = tb ? jt - 1 : jt + 1;
-        R.e2 = (uint32_t)sd_tail_rank(SD_BLK_T, R.jt2, tau ^ (1u << (SD_BLK_T - 1)));
-    }
+    if (S.tb != t.b0 && Wp.J != 0.0 && t.pvalid) { R.jt2 = S.tb ? S.jt - 1 : S.jt + 1; R.e2 = (uint32_t)S.e2; }
     return R;
 }
 template <int NC>
@@ -230,22 +237,23 @@ struct SdBlkWrapUnit {
     SdBlkWrapRow r0, r1;                 // f64: rows 2s and 2s+1 (r1.nblk = 0: plain last row); c128: r0 only
     uint32_t nblk;
 };
-template <int NC>
-SD_HD SdBlkWrapUnit<NC> sd_blk_wrap_unit(const SdBlkWrap &Wp, const SdBlkWrapTile &t, const SdBlkJs &I, int unit) {
-    SdBlkWrapUnit<NC> U;
-    if (NC == 2) {
-        U.r0 = sd_blk_wrap_row(Wp, t, I, unit);
-        U.r1 = U.r0; U.r1.nblk = 0;
-        U.nblk = U.r0.nblk;
-        return U;
-    }
+// rows of work unit `unit`: rows[0] and rows[1] (-1: none)
+SD_HD void sd_blk_wrap_unit_rows(int nc, int unit, int &r0, int &r1) {
+    if (nc == 2) { r0 = unit; r1 = -1; return; }
     int jt = 0, first_unit = 0, first_row = 0;
     while (unit >= first_unit + (sd_cbinom(SD_BLK_T, jt) + 1) / 2) {
         first_unit += (sd_cbinom(SD_BLK_T, jt) + 1) / 2; first_row += sd_cbinom(SD_BLK_T, jt); ++jt;
     }
     const int s = unit - first_unit, nt = sd_cbinom(SD_BLK_T, jt);
-    U.r0 = sd_blk_wrap_row(Wp, t, I, first_row + 2 * s);
-    if (2 * s + 1 < nt) U.r1 = sd_blk_wrap_row(Wp, t, I, first_row + 2 * s + 1);
+    r0 = first_row + 2 * s;
+    r1 = (2 * s + 1 < nt) ? r0 + 1 : -1;
+}
+// rows: the 2^T static row descriptors (sd_blk_wrap_static), r0 / r1 from sd_blk_wrap_unit_rows
+template <int NC>
+SD_HD SdBlkWrapUnit<NC> sd_blk_wrap_unit(const SdBlkWrap &Wp, const SdBlkWrapTile &t, const SdBlkJs &I, const SdBlkWrapStatic *rows, int r0, int r1) {
+    SdBlkWrapUnit<NC> U;
+    U.r0 = sd_blk_wrap_row(Wp, t, I, rows[r0]);
+    if (r1 >= 0) U.r1 = sd_blk_wrap_row(Wp, t, I, rows[r1]);
     else { U.r1 = U.r0; U.r1.nblk = 0; }
     U.nblk = U.r0.nblk;
     return U;

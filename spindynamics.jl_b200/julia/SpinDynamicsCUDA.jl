@@ -244,10 +244,13 @@ function spectral_from_tridiagonal(α, β, norm_phi, E0, ω; eta=0.05, broaden=:
     error("unknown broadening: $broaden")
 end
 
+# The multi-vector kernel wins where one vector cannot fill the GPU (L = 16) and loses to the block kernel once that is
+# bandwidth-bound (L = 28): the automatic choice batches small bases only.
+const Q_BATCH_AUTO_MAX_DIM = 1 << 20
 # q_batch: all momenta as one interleaved [state][q] multi-vector (sd_lanczos_tridiag_szq_batch, at most 128 per call):
 # the reference's Threads.@threads q-loop as data parallelism, two fused kernels per Lanczos step for ALL momenta.
 function lanczos_sqw(ψ0, m::GPUModel, q_list::AbstractVector{Float64}, ω::AbstractVector{Float64};
-                     lanc_m::Int=200, eta::Float64=0.05, broaden::Symbol=:lorentz, q_batch::Bool=length(q_list) >= 2)
+                     lanc_m::Int=200, eta::Float64=0.05, broaden::Symbol=:lorentz, q_batch::Bool=length(q_list) >= 2 && m.dim <= Q_BATCH_AUTO_MAX_DIM)
     ψc = tocomplex(m, ψ0); tmp = GPUVector{ComplexF64}(m); apply_H!(tmp, ψc, m)
     r = Ref{SdComplex}(); check(ccall((:sd_vec_dotu, lib), Cint, (Handle, Handle, Ref{SdComplex}), ψc.h, tmp.h, r))
     E0 = r[].re                                                               # LanczosSqw.jl:59
@@ -286,7 +289,7 @@ function compute_chebyshev_moments(::typeof(apply_H!), ϕ::GPUVector{ComplexF64}
     check(ccall((:sd_kpm_moments, lib), Cint, (Handle, Handle, Cint, Float64, Float64, Ptr{Float64}), m.h, ϕ.h, M, a, b, μ)); μ
 end
 function kpm_sqw(ψ0, m::GPUModel, q_list::AbstractVector{Float64}, ω::AbstractVector{Float64};
-                 a=nothing, b=nothing, kpm_m::Int=200, kernel::Symbol=:jackson, q_batch::Bool=length(q_list) >= 2)
+                 a=nothing, b=nothing, kpm_m::Int=200, kernel::Symbol=:jackson, q_batch::Bool=length(q_list) >= 2 && m.dim <= Q_BATCH_AUTO_MAX_DIM)
     ψc = tocomplex(m, ψ0); tmp = GPUVector{ComplexF64}(m); r = Ref{SdComplex}()
     check(ccall((:sd_apply_H_dot, lib), Cint, (Handle, Handle, Handle, Ref{SdComplex}), m.h, tmp.h, ψc.h, r))
     E0 = r[].re

@@ -487,9 +487,16 @@ def _q_batches(model: Model, nq: int):
     return out
 
 
+# The multi-vector kernel is the one-thread-group-per-state gather: it wins where a single vector cannot fill the GPU
+# (config 1, L = 16: 16 momenta in 2 launches per step instead of 48) and loses to the block kernel once that one is
+# bandwidth-bound (L = 28: 3.7 ms per moment and momentum batched against 1.7 ms looped, profiles/round2_q_bench.json), so
+# the automatic choice batches small bases only; q_batch=True / False overrides it.
+Q_BATCH_AUTO_MAX_DIM = 1 << 20
+
+
 def _use_q_batch(model: Model, q_list, q_threads, q_batch):
     if q_batch is None:
-        q_batch = model.ctx.world == 1 and len(q_list) >= 2 and q_threads <= 1
+        q_batch = model.ctx.world == 1 and len(q_list) >= 2 and q_threads <= 1 and model.dim <= Q_BATCH_AUTO_MAX_DIM
     if q_batch and model.ctx.world != 1:
         raise ValueError("q_batch needs a single-GPU context")
     return bool(q_batch)
@@ -497,7 +504,7 @@ def _use_q_batch(model: Model, q_list, q_threads, q_batch):
 
 def lanczos_sqw(psi0, model: Model, q_list, w_range, lanc_m=200, eta=0.05, broaden="lorentz", q_threads: int = 1,
                 q_batch: Optional[bool] = None):
-    """LanczosSqw.jl:49-80.  q_batch (default on a single GPU with >= 2 momenta): all momenta as one interleaved
+    """LanczosSqw.jl:49-80.  q_batch (default on a single GPU with >= 2 momenta and at most Q_BATCH_AUTO_MAX_DIM states): all momenta as one interleaved
     [state][q] multi-vector, two fused kernels per Lanczos step for ALL of them (sd_lanczos_tridiag_szq_batch) -- the
     reference's Threads.@threads q-loop as data parallelism.  q_batch=False: one momentum after the other; q_threads > 1:
     that loop on several host threads / contexts (see _q_parallel)."""
@@ -607,7 +614,7 @@ def _kpm_reconstruct(mu, w_range, a, b, E0, kpm_m, kernel):
 
 def kpm_sqw(psi0, model: Model, q_list, w_range, a=None, b=None, kpm_m=200, kernel="jackson", rng=None, q_threads: int = 1,
             q_batch: Optional[bool] = None):
-    """KPM_Sqw.jl:191-256.  q_batch (default on a single GPU with >= 2 momenta): the moments of all momenta from one
+    """KPM_Sqw.jl:191-256.  q_batch (default on a single GPU with >= 2 momenta and at most Q_BATCH_AUTO_MAX_DIM states): the moments of all momenta from one
     interleaved [state][q] multi-vector, one fused kernel per moment for ALL of them (sd_kpm_moments_szq_batch);
     q_batch=False: one momentum after the other; q_threads > 1: that loop on several host threads / contexts."""
     if q_threads > 1 and len(q_list) > 1 and not q_batch:

@@ -185,12 +185,16 @@ int emul_blk_apply(int L, int k, const double *Jhop, const double *Jz, const dou
             const double *own = view.base[rank] + (size_t)NC * t.base;
             const double *part = t.pvalid ? view.base[sd_blk_owner(P.shards, t.pbase)] + (size_t)NC * t.pbase : own;
             double *wo = wv.p + (size_t)NC * (t.base - pstart[rank]);
+            SdBlkWrapStatic rows[1 << SD_BLK_T];                     // the kernel's shared-memory tables
+            for (int r = 0; r < (1 << SD_BLK_T); ++r) rows[r] = sd_blk_wrap_static(r);
             for (int unit = 0; unit < sd_blk_wrap_units(NC); ++unit) {
+                int r0, r1;
+                sd_blk_wrap_unit_rows(NC, unit, r0, r1);
                 if (NC == 2) {
-                    const SdBlkWrapUnit<2> U = sd_blk_wrap_unit<2>(Wp, t, I, unit);
+                    const SdBlkWrapUnit<2> U = sd_blk_wrap_unit<2>(Wp, t, I, rows, r0, r1);
                     for (uint32_t u = 0; u < U.nblk; ++u) sd_blk_wrap_apply<2>(Wp, U, I, Ip, u, own, part, wo);
                 } else {
-                    const SdBlkWrapUnit<1> U = sd_blk_wrap_unit<1>(Wp, t, I, unit);
+                    const SdBlkWrapUnit<1> U = sd_blk_wrap_unit<1>(Wp, t, I, rows, r0, r1);
                     for (uint32_t u = 0; u < U.nblk; ++u) sd_blk_wrap_apply<1>(Wp, U, I, Ip, u, own, part, wo);
                 }
             }
