@@ -121,10 +121,8 @@ static inline bool sd_blk_build(int L, int k, const double *Jhop, const double *
             std::vector<std::pair<int, uint16_t>> list;       // (-NT, code): heavy classes first
             for (int jt = 0; jt <= T; ++jt) {
                 const SdBlkCls &c = I.cls[jt];
+                const uint32_t nu = (c.pitch + uw - 1) / uw;
                 const int nt = (int)C[T * SD_BINOM_DIM + jt];
-                // f64 classes with one tail configuration: a lane owns four mid configurations (sd_blkl_item_x4)
-                const uint32_t per_unit = (w == 0 && nt == 1) ? 4u * uw : uw;
-                const uint32_t nu = (c.pitch + per_unit - 1) / per_unit;
                 const int nchunk = (w == 1 && nt > 5) ? 2 : 1;    // sd_blk_dispatch: c128, NT = 10 -> two chunks of 5
                 for (uint32_t j = 0; j < nu; ++j)
                     for (int ch = 0; ch < nchunk; ++ch)

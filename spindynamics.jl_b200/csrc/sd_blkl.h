@@ -262,141 +262,13 @@ SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdEpi &E, double *out_l
         }
     }
 }
-// ---- classes with ONE tail configuration (JT = 0: tail all down, JT = T: all up) of an f64 vector.  Their row is plain
-// (element (0, u) at cb + u), so a lane owns FOUR consecutive mid configurations: 32 contiguous bytes per neighbour-tile
-// entry (two LDG.128) instead of one 8-byte load.  The kernel is latency-bound -- an item costs its number of dependent
-// load rounds whatever it carries -- and these classes are 19 % of a tile's work items for 2.6 % of its states at one
-// configuration per lane (js = 8: 6 of 32 units); at four per lane they are 2 of 28.
-template <int JT, int EK>
-SD_BLKL_FN void sd_blkl_item_x4(const SdBlkParams &P, const SdEpi &E, double *out_local, const SdBlkHdr &H, const double *tb, uint32_t u0,
-                                double (&red)[SD_NSLOT]) {
-    static_assert(JT == 0 || JT == SD_BLK_T, "classes with a single tail configuration");
-    constexpr int M = SD_BLK_M, T = SD_BLK_T;
-    constexpr unsigned cfg = JT == 0 ? 0u : (1u << T) - 1u;           // the tail bits
-    const SdBlkJs &I = SD_SH.js[H.js];
-    const SdBlkCls cls = I.cls[JT];
-    if (u0 >= cls.nblk) return;
-    const uint32_t off0 = cls.cb + u0;                               // doubles; 32-byte aligned (cb and u0 are multiples of 4)
-    // elements u0 + k >= nblk are row padding: zero in every vector, so everything below leaves them exactly zero
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    if (P.addin != nullptr) {                                        // periodic chain: the wrap bond's terms
-        const double *ap = P.addin + (H.base - P.shards.pstart[P.shards.rank]) + off0;
-        const double2 a0 = *(const double2 *)ap, a1 = *(const double2 *)(ap + 2);
-        acc[0] = a0.x; acc[1] = a0.y; acc[2] = a1.x; acc[3] = a1.y;
-    }
-    double2 t0[2], t1[2];
-    t0[0] = t0[1] = t1[0] = t1[1] = make_double2(0.0, 0.0);
-#define SD_X4_LOAD(t_, p_)                                            \
-    do {                                                              \
-        const double *q_ = (p_) + off0;                               \
-        t_[0] = sd_blk_ldg(q_); t_[1] = sd_blk_ldg(q_ + 2);           \
-    } while (0)
-#define SD_X4_FMA(t_, J_)                                             \
-    do {                                                              \
-        const double j_ = (J_);                                       \
-        acc[0] += j_ * t_[0].x; acc[1] += j_ * t_[0].y; acc[2] += j_ * t_[1].x; acc[3] += j_ * t_[1].y; \
-    } while (0)
-    // ---- prefix|mid crossing bond, per element (the four may straddle the first-mid-bit boundary n1)
-    double tx[4] = {0.0, 0.0, 0.0, 0.0};
-    const int nnb = H.nnb;
-    if (H.xptr != nullptr) {
-        const SdBlkCls cx = SD_SH.js[H.jsx].cls[JT];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t u = u0 + (uint32_t)k;
-            if (u < cls.nblk && (u < cls.n1) != (bool)H.bP) {
-                const uint32_t xu = H.bP ? u - cls.n1 : cx.n1 + u;
-                tx[k] = sd_blk_ldg_half(H.xptr + cx.cb + xu).x;
-            }
-        }
-    }
-    // ---- prefix-internal bonds
-    SdBlkEnt e0 = H.nb[0], e1;
-    if (nnb > 0) SD_X4_LOAD(t0, e0.p);
-    if (H.xptr != nullptr) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) acc[k] += H.Jx * tx[k];
-    }
-    int n = 0;
-#pragma unroll 1
-    while (n + 1 < nnb) {
-        e1 = H.nb[n + 1];
-        SD_X4_LOAD(t1, e1.p);
-        SD_X4_FMA(t0, e0.J);
-        if (n + 2 < nnb) { e0 = H.nb[n + 2]; SD_X4_LOAD(t0, e0.p); }
-        SD_X4_FMA(t1, e1.J);
-        n += 2;
-    }
-    if (n < nnb) SD_X4_FMA(t0, e0.J);
-#undef SD_X4_LOAD
-#undef SD_X4_FMA
-    // ---- own value: diagonal, mid-internal hops, mid|tail crossing (no tail-internal hop: all tail bits are equal)
-    const double2 o0 = *(const double2 *)(tb + off0), o1 = *(const double2 *)(tb + off0 + 2);
-    const double own[4] = {o0.x, o0.y, o1.x, o1.y};
-    const double *row = tb + cls.cb;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const uint32_t u = u0 + (uint32_t)k;
-        if (u >= cls.nblk) continue;
-        const uint4 it = sd_blk_ld_item(P.items + cls.item_off + u);
-        const unsigned cmid = it.w & ((1u << M) - 1u);
-        const bool clast = (cmid >> (M - 1)) & 1u;
-        const double dx = clast ? P.qx : -P.qx;
-        const double d = H.dP[u < cls.n1 ? 1 : 0] + SD_SH.dmid[cls.item_off + u] + (P.dtail[cfg] + ((cfg & 1u) ? dx : -dx));
-        double a = acc[k] + d * own[k];
-        uint64_t lo = (uint64_t)it.x | ((uint64_t)it.y << 32);
-        uint32_t hi = it.z;
-#pragma unroll 1
-        for (int pm = 0; pm + 1 < M; ++pm) {
-            const unsigned nbu = (unsigned)(lo & 0xFFu);
-            lo = (lo >> 8) | ((uint64_t)hi << 56);
-            hi >>= 8;
-            if (nbu != 0xFFu) a += P.Jmid[pm] * row[nbu];
-        }
-        const uint32_t u2x = it.w >> 16;
-        if (JT == 0) {                                               // last mid bit set & tail bit 0 clear -> class 1, its configuration 0
-            if (clast) a += P.Jmid[M - 1] * tb[I.cls[1].cb + 2u * u2x];
-        } else {                                                     // last mid bit clear & tail bit 0 set -> class T-1, its last (plain-row) configuration
-            if (!clast) a += P.Jmid[M - 1] * tb[I.cls[T - 1].cb + (uint32_t)(T - 1) * I.cls[T - 1].pitch + u2x];
-        }
-        acc[k] = a;
-    }
-    // ---- epilogue + store (a pair is stored when its first element is real; a padding partner is exactly zero)
-    const uint64_t ld0 = (H.base - P.shards.pstart[P.shards.rank]) + off0;
-    double *ob = out_local + ld0;
-    double r[4];
-    if (EK == 0) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) r[k] = acc[k];
-    } else if (EK == 1) {
-        const double hs = SD_SH.hs;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { r[k] = hs * acc[k]; red[0] += own[k] * r[k]; }
-    } else {
-        const double hs = SD_SH.hs;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            r[k] = 0.0;
-            if (u0 + (uint32_t)k >= cls.nblk) continue;              // the generic epilogue reads vprev / phi / acc at this element
-            SdVal<1> hh, pp;
-            hh.c[0] = acc[k]; pp.c[0] = own[k];
-            r[k] = sd_epilogue_hs<1>(E, hs, hh, pp, ld0 + (uint64_t)k, red).c[0];
-        }
-    }
-    sd_blk_stg(ob, make_double2(r[0], r[1]));
-    if (u0 + 2u < cls.nblk) sd_blk_stg(ob + 2, make_double2(r[2], r[3]));
-}
 template <int NC, int EK>
-SD_BLKL_FN void sd_blkl_dispatch(const SdBlkParams &P, const SdEpi &E, double *out_local, const SdBlkHdr &H, const double *tb, unsigned code, unsigned lane,
+SD_BLKL_FN void sd_blkl_dispatch(const SdBlkParams &P, const SdEpi &E, double *out_local, const SdBlkHdr &H, const double *tb, unsigned code, uint32_t u,
                                 double (&red)[SD_NSLOT]) {
     const int jt = (int)(code >> 12);
     const bool hi = ((code >> 8) & 0xFu) != 0;                       // c128, classes of 10: second chunk of five
-    const uint32_t unit = code & 0xFFu;
-    const uint32_t u = unit * 32u + lane;                            // the lane's mid configuration
     switch (jt) {
-        case 0:
-            if constexpr (NC == 1) { sd_blkl_item_x4<0, EK>(P, E, out_local, H, tb, unit * (4u * 32u) + 4u * lane, red); break; }
-            sd_blkl_item<NC, 0, 0, EK>(P, E, out_local, H, tb, u, red); break;
+        case 0: sd_blkl_item<NC, 0, 0, EK>(P, E, out_local, H, tb, u, red); break;
         case 1: sd_blkl_item<NC, 1, 0, EK>(P, E, out_local, H, tb, u, red); break;
         case 2:
             if constexpr (NC == 2) { if (hi) { sd_blkl_item<NC, 2, 5, EK>(P, E, out_local, H, tb, u, red); break; } }
@@ -405,9 +277,7 @@ SD_BLKL_FN void sd_blkl_dispatch(const SdBlkParams &P, const SdEpi &E, double *o
             if constexpr (NC == 2) { if (hi) { sd_blkl_item<NC, 3, 5, EK>(P, E, out_local, H, tb, u, red); break; } }
             sd_blkl_item<NC, 3, 0, EK>(P, E, out_local, H, tb, u, red); break;
         case 4: sd_blkl_item<NC, 4, 0, EK>(P, E, out_local, H, tb, u, red); break;
-        default:
-            if constexpr (NC == 1) { sd_blkl_item_x4<SD_BLK_T, EK>(P, E, out_local, H, tb, unit * (4u * 32u) + 4u * lane, red); break; }
-            sd_blkl_item<NC, 5, 0, EK>(P, E, out_local, H, tb, u, red); break;
+        default: sd_blkl_item<NC, 5, 0, EK>(P, E, out_local, H, tb, u, red); break;
     }
 }
 
@@ -459,8 +329,9 @@ sd_blkl_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constan
                 const unsigned nunits = SD_SH.js[H.js].nunits[NC - 1];
                 if (un >= nunits) break;
                 const unsigned code = SD_SH.units[H.js * SD_BLK_MAXUNITS + un];
+                const uint32_t u = (code & 0xFFu) * 32u + lane;      // the lane's mid configuration
                 double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
-                sd_blkl_dispatch<NC, EK>(P, epi, out_local, H, tb, code, lane, red);
+                sd_blkl_dispatch<NC, EK>(P, epi, out_local, H, tb, code, u, red);
                 if (!PLAIN && slotmask) sd_blk_item_reduce(H, slotmask, un, red, lane);
             }
             __syncwarp();

@@ -61,8 +61,9 @@ void run_tiles(const SdBlkHost &bh, const SdBlkParams &P, const SdVecView &psi, 
         for (unsigned un = 0; un < nunits; ++un) {
             const unsigned code = ut[un];
             for (unsigned lane = 0; lane < 32; ++lane) {
+                const uint32_t u = (code & 0xFFu) * 32u + lane;
                 double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
-                sd_blkl_dispatch<NC, EK>(P, epi, out_local, H, tile.p, code, lane, red);
+                sd_blkl_dispatch<NC, EK>(P, epi, out_local, H, tile.p, code, u, red);
                 for (int s = 0; s < SD_NSLOT; ++s) red_total[s] += red[s];
             }
         }
