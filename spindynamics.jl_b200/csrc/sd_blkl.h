@@ -14,6 +14,10 @@
 //     SD_BLKL_THREADS exceed 512.
 // The body compiles for the host too (tests/emul runs it lane by lane against the oracle): there SD_SH is a plain
 // static object.
+// Tried and dropped (profiles/round2_s_x4_*.txt): a separate body for the f64 classes with ONE tail configuration in which a
+// lane owns four mid configurations (32-byte stream loads; 28 instead of 32 work items per tile).  Correct, but 5.94 ms
+// against 5.52: four item-table reads and four serial mid-hop loops per lane cost more than the saved load rounds, and
+// the extra code hurts a kernel that is instruction-cache sensitive.
 #pragma once
 #include "sd_blk.h"
 
