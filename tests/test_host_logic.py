@@ -92,3 +92,44 @@ def test_threaded_q_loop_partitions_q_in_order(monkeypatch):
         if e == "close":
             assert "model_del" in events[:i]
     assert api._q_parallel(fn, np.zeros(3), m, [5], 8, x=2).ravel().tolist() == [52]
+
+
+@pytest.mark.parametrize("kernel", ["jackson", "lorentz", "none"])
+def test_kpm_reconstruction_equals_the_oracles(kernel):
+    """The host half of kpm_sw / kpm_sqw (KPM_Sqw.jl:48-92: kernel damping, x = (w + E0 - b) / a, the Chebyshev series,
+    1 / (a pi sqrt(1 - x^2)), max(0, .)) shared by the per-momentum and the q-batched paths, against the oracle's loop on
+    the same moments -- including frequencies outside the rescaled band (S = 0)."""
+    import oracle.oracle as orc
+    om = orc.XXZChain(8, nup=4)
+    rng = np.random.default_rng(11)
+    phi = rng.standard_normal(len(om)) + 1j * rng.standard_normal(len(om))
+    phi /= np.linalg.norm(phi)
+    a, b, E0, M = 2.9, -0.3, -3.1, 37
+    w = np.linspace(-1.0, 7.0, 41)
+    mu = orc.compute_chebyshev_moments(orc.apply_H_, phi, M, a, b, om)
+    want = orc.kpm_sw(phi, orc.apply_H_, om, w, a, b, E0, kpm_m=M, kernel=kernel)
+    got = api._kpm_reconstruct(np.asarray(mu), w, a, b, E0, M, kernel)
+    assert np.any(want == 0.0) and np.any(want > 0.0)
+    assert np.allclose(got, want, rtol=1e-12, atol=1e-14)
+
+
+def test_q_batch_automatic_choice():
+    """q_batch=None batches small bases on a single GPU only (the multi-vector kernel loses to the block kernel at large N)."""
+    class Ctx:
+        world = 1
+
+    class Mdl:
+        ctx = Ctx()
+        dim = 12870
+
+    m = Mdl()
+    assert api._use_q_batch(m, [0.0, 1.0], 1, None) is True
+    assert api._use_q_batch(m, [0.0], 1, None) is False                 # one momentum: nothing to batch
+    assert api._use_q_batch(m, [0.0, 1.0], 4, None) is False            # q_threads asks for the threaded loop
+    m.dim = api.Q_BATCH_AUTO_MAX_DIM + 1
+    assert api._use_q_batch(m, [0.0, 1.0], 1, None) is False
+    assert api._use_q_batch(m, [0.0, 1.0], 1, True) is True             # explicit request wins
+    m.ctx.world = 2
+    assert api._use_q_batch(m, [0.0, 1.0], 1, None) is False
+    with pytest.raises(ValueError):
+        api._use_q_batch(m, [0.0, 1.0], 1, True)
