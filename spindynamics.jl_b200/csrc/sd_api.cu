@@ -1775,22 +1775,39 @@ int sd_lanczos_groundstate(sd_model *m, const sd_vec *v0, int lanc_m, double tol
     }
     int mact = mm;
     const bool batch_check = sd_env_int("SD_BATCH_CHECK", 0) != 0;
-    // Single GPU: everything behind the apply is one cooperative kernel per step (sd_reorth.cuh) and one 3-double fetch.
+    // Single GPU: everything behind the apply is one cooperative kernel per step (sd_reorth.cuh), scalars fetched once at the end.
     // SD_REORTH_FUSED=0 keeps the one-call-per-BLAS-operation path below (the only one for sharded models).
     const bool fused = c->world == 1 && sd_env_int("SD_REORTH_FUSED", 1) != 0;
-    for (int j = 1; fused && j <= mm; ++j) {
-        sd_vec *vj = S->v[j - 1];
-        SD_TRY(sd_apply_impl(m, w, vj, sd_epi_plain(1.0), 0));              // :113
-        sd_vec *vn = nullptr;
-        if (j < mm) { SD_TRY(sd_vec_alloc(m, SD_F64, &vn)); S->v.push_back(vn); }
-        double r[3];
-        SD_TRY(sd_reorth_step(c, w, S->v.data(), j, vn, j >= 2 ? beta[j - 2] : 0.0, tol, orth_tol, r));
-        alpha[j - 1] = r[0];
-        if (j < mm) {
-            beta[j - 1] = r[1];
-            if (r[2] == 1.0) { mact = j; sd_vec_free(vn); S->v.pop_back(); break; }   // :136-139
-            if (r[2] == 2.0) mact = j;                                      // :148-151 leaves the check pass only
+    if (fused) {
+        // all steps enqueued back to back: apply, cooperative step kernel, no host synchronisation in between (the next
+        // basis vector is allocated while the device works); the scalars of all steps come back in one fetch.  A step behind
+        // the reference's `break` (:136-139) returns at once, so what it leaves in its vectors is never looked at.
+        SD_TRY(sd_reorth_begin(c, mm));
+        for (int j = 1; j <= mm; ++j) {
+            sd_vec *vj = S->v[j - 1];
+            SD_TRY(sd_apply_impl(m, w, vj, sd_epi_plain(1.0), 0));          // :113
+            sd_vec *vn = nullptr;
+            if (j < mm) { SD_TRY(sd_vec_alloc(m, SD_F64, &vn)); S->v.push_back(vn); }
+            SD_TRY(sd_reorth_step(c, w, S->v.data(), j, vn, tol, orth_tol));
+            if (j % 16 == 0 && j < mm) {                                    // bound the work (and the vectors) behind a break
+                double stop = 0.0;
+                SD_TRY(sd_fetch(c, 3712 /* SD_RTH_SLOT */, 1, &stop));
+                if (stop != 0.0) break;
+            }
         }
+        std::vector<double> rec((size_t)8 * (mm + 1), 0.0);
+        SD_TRY(sd_reorth_finish(c, mm, rec.data()));
+        for (int j = 1; j <= mm; ++j) {
+            const double *r = rec.data() + 8 * j;
+            if (r[3] != 1.0) break;                                         // behind a break: did not run
+            alpha[j - 1] = r[0];
+            if (j < mm) {
+                beta[j - 1] = r[1];
+                if (r[2] == 1.0) { mact = j; break; }                       // :136-139
+                if (r[2] == 2.0) mact = j;                                  // :148-151 leaves the check pass only
+            }
+        }
+        while ((int)S->v.size() > std::max(mact, 1)) { sd_vec_free(S->v.back()); S->v.pop_back(); }   // vectors behind m_actual
     }
     for (int j = 1; !fused && j <= mm; ++j) {
         sd_vec *vj = S->v[j - 1];

@@ -6,11 +6,20 @@
 #include "sd_handles.h"
 #include "sd_reorth.cuh"
 
-#define SD_RTH_SLOT 3712                                              // d_scal[3712 .. 3714]: alpha_j, beta_j, flag
+#define SD_RTH_SLOT 3712                                              // d_scal[3712]: the stop flag of the running solve
 
 // One step of Lanczos.jl:116-155 behind the apply (see sd_reorth.cuh).  V[0 .. j-1] are v_1 .. v_j, w = H v_j on entry;
-// vnext (j < m) receives v_{j+1}.  res[0] = alpha_j, res[1] = beta_j, res[2] = breakdown flag.  Single GPU.
-int sd_reorth_step(sd_ctx *c, sd_vec *w, sd_vec *const *V, int j, sd_vec *vnext, double beta_prev, double tol, double orth_tol, double *res) {
+// vnext (j < m) receives v_{j+1}.  Nothing is fetched: the step's scalars (alpha_j, beta_j, breakdown flag, "ran") stay in
+// d_scal[SD_HIST + 8 j ..], beta_{j-1} is read from the previous step's record, and sd_reorth_finish returns them all at
+// once -- a solve is m applies and m cooperative launches enqueued back to back.  Single GPU.
+int sd_reorth_begin(sd_ctx *c, int mm) {
+    SD_ARG(c->world == 1, "the fused reorthogonalisation is single-GPU");
+    SD_ARG(mm >= 1 && mm <= SD_HIST_MAX, "lanc_m must be in 1 .. %d", SD_HIST_MAX);
+    SD_CUDA(cudaMemsetAsync(c->d_scal + SD_RTH_SLOT, 0, sizeof(double), c->stream));
+    SD_CUDA(cudaMemsetAsync(c->d_scal + SD_HIST, 0, (size_t)8 * (mm + 1) * sizeof(double), c->stream));
+    return SD_OK;
+}
+int sd_reorth_step(sd_ctx *c, sd_vec *w, sd_vec *const *V, int j, sd_vec *vnext, double tol, double orth_tol) {
     SD_ARG(c->world == 1, "sd_reorth_step is single-GPU");
     SD_ARG(j >= 1 && j <= SD_HIST_MAX, "too many basis vectors");
     if (!c->d_vtab) {
@@ -32,14 +41,19 @@ int sd_reorth_step(sd_ctx *c, sd_vec *w, sd_vec *const *V, int j, sd_vec *vnext,
     }
     SdReorthArgs A;
     A.w = w->d; A.V = c->d_vtab; A.vnext = vnext ? vnext->d : nullptr; A.j = j; A.n = w->local_n;
-    A.beta_prev = beta_prev; A.tol = tol; A.orth_tol = orth_tol;
-    A.partials = c->d_rth_partials; A.out = c->d_scal + SD_RTH_SLOT;
+    A.beta_prev = j >= 2 ? c->d_scal + SD_HIST + 8 * (j - 1) + 1 : nullptr;
+    A.stop = c->d_scal + SD_RTH_SLOT;
+    A.tol = tol; A.orth_tol = orth_tol;
+    A.partials = c->d_rth_partials; A.out = c->d_scal + SD_HIST + 8 * j;
     const uint64_t want = (A.n + SD_RTH_THREADS - 1) / SD_RTH_THREADS;
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, c->rth_grid_max));
     void *args[] = {&A};
     SD_CUDA(cudaLaunchCooperativeKernel((const void *)sd_reorth_step_kernel, dim3(grid), dim3(SD_RTH_THREADS), args, 0, c->stream));
-    SD_TRY(sd_launch_check(c, "sd_reorth_step_kernel"));
-    return sd_fetch(c, SD_RTH_SLOT, 3, res);
+    return sd_launch_check(c, "sd_reorth_step_kernel");
+}
+// records of steps 1 .. mm: rec[8 j + 0..3] = alpha_j, beta_j, flag, ran (one fetch, one synchronisation)
+int sd_reorth_finish(sd_ctx *c, int mm, double *rec) {
+    return sd_fetch(c, SD_HIST, 8 * (mm + 1), rec);
 }
 
 // =====================================================================================================================

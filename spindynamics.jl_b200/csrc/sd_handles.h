@@ -206,4 +206,6 @@ void sd_scratch_release(sd_ctx *c);
 int sd_blk_permute(const sd_vec *v, double *rank_local, int nc_rank, int dir, int seeded, uint64_t seed, double scale);
 
 // ----------------------------------------------------------------- sd_batch.cu
-int sd_reorth_step(sd_ctx *c, sd_vec *w, sd_vec *const *V, int j, sd_vec *vnext, double beta_prev, double tol, double orth_tol, double *res);
+int sd_reorth_begin(sd_ctx *c, int mm);
+int sd_reorth_step(sd_ctx *c, sd_vec *w, sd_vec *const *V, int j, sd_vec *vnext, double tol, double orth_tol);
+int sd_reorth_finish(sd_ctx *c, int mm, double *rec);

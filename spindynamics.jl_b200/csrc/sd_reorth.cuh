@@ -23,10 +23,11 @@ struct SdReorthArgs {
     double *vnext;                      // out: V_{j+1} = w / beta_j (nullptr: last step, j = m)
     int j;
     uint64_t n;
-    double beta_prev;                   // beta_{j-1} (unused for j = 1)
+    const double *beta_prev;            // device: beta_{j-1}, the out[1] of the previous step (nullptr for j = 1)
+    double *stop;                       // device flag: set by the step that hits the breakdown test at :136; later steps return at once
     double tol, orth_tol;
     double *partials;                   // [2][SD_RCHK][gridDim.x]
-    double *out;                        // out[0] = alpha_j, out[1] = beta_j, out[2] = 1: beta_j < tol at :136 (stop), 2: inside the check pass (m_actual = j, go on)
+    double *out;                        // out[0] = alpha_j, out[1] = beta_j, out[2] = 1: beta_j < tol at :136 (stop), 2: inside the check pass (m_actual = j, go on), out[3] = 1
 };
 
 namespace sd_rth {
@@ -72,6 +73,10 @@ __global__ void __launch_bounds__(SD_RTH_THREADS) sd_reorth_step_kernel(const __
     __shared__ double scratch[SD_RCHK][SD_RTH_THREADS / 32];
     __shared__ double total[SD_RCHK];
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // A solve enqueues all its steps without waiting for their scalars; once a step has met the reference's `break` the
+    // remaining ones do nothing.  Every CTA reads the flag before the first grid barrier, the flag is written behind the
+    // last one, so all CTAs of a launch see the same value.
+    if (*A.stop != 0.0) return;
     double *w = A.w;
     const int j = A.j;
     const size_t pstride = (size_t)SD_RCHK * gridDim.x;
@@ -106,7 +111,7 @@ __global__ void __launch_bounds__(SD_RTH_THREADS) sd_reorth_step_kernel(const __
     double beta;
     {
         const double *vj = A.V[j - 1], *vp = j >= 2 ? A.V[j - 2] : nullptr;
-        const double bp = A.beta_prev;
+        const double bp = vp ? *A.beta_prev : 0.0;
         double r[1] = {0.0};
         for (uint64_t i = i0; i < A.n; i += stride) {
             double x = w[i] - alpha * vj[i];
@@ -168,5 +173,8 @@ __global__ void __launch_bounds__(SD_RTH_THREADS) sd_reorth_step_kernel(const __
             for (uint64_t i = i0; i < A.n; i += stride) vn[i] = w[i] / beta;
         }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { A.out[0] = alpha; A.out[1] = beta; A.out[2] = flag; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        A.out[0] = alpha; A.out[1] = beta; A.out[2] = flag; A.out[3] = 1.0;   // [3]: this step ran
+        if (flag == 1.0) *A.stop = 1.0;
+    }
 }
