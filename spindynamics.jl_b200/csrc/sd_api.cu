@@ -1219,7 +1219,8 @@ static int sd_blk_launch_range(sd_model *m, int nc, const SdBlkParams &P, const 
     } while (0)
 #define SD_HL_LEAN(NC_, EK_)                                                                                 \
     do {                                                                                                     \
-        if (m->blk.threads == 512) SD_HL((sd_blkl_apply_kernel<NC_, EK_, 512>), 512);                        \
+        if (P.addin != nullptr) SD_HL((sd_blkl_apply_kernel<NC_, EK_, 640, true>), 640);   /* periodic chain */ \
+        else if (m->blk.threads == 512) SD_HL((sd_blkl_apply_kernel<NC_, EK_, 512>), 512);                   \
         else if (m->blk.threads == 768) SD_HL((sd_blkl_apply_kernel<NC_, EK_, 768>), 768);                   \
         else SD_HL((sd_blkl_apply_kernel<NC_, EK_, 640>), 640);                                              \
     } while (0)

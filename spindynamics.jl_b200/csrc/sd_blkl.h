@@ -52,7 +52,7 @@ SD_BLKL_FN void sd_blkl_ctx_init(const SdEpi &epi) {
 // EK: epilogue kind, compile-time so that each instantiation only carries the code it runs (the kernel is instruction-
 // cache sensitive): 0 plain out = H psi; 1 Lanczos: out = hs * H psi with the fused <psi, out> (every Lanczos flavour);
 // 2 generic (rescaled / Chebyshev step, psi_t accumulation, phi dot, norm: sd_epilogue_hs).
-template <int NC, int JT, int S0, int EK>
+template <int NC, int JT, int S0, int EK, bool ADDIN = false>
 SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdEpi &E, double *out_local, const SdBlkHdr &H, const double *tb, uint32_t u,
                              double (&red)[SD_NSLOT]) {
     constexpr bool PLAIN = EK == 0;
@@ -75,7 +75,8 @@ SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdEpi &E, double *out_l
     double2 acc[EC], t0[EC], t1[EC];
 #pragma unroll
     for (int s = 0; s < EC; ++s) acc[s] = t0[s] = t1[s] = make_double2(0.0, 0.0);   // t0/t1: conditionally loaded below; left undefined they end up on the stack
-    if (P.addin != nullptr) {                                        // periodic chain: the wrap bond's terms (sd_blk_wrap_kernel)
+    if constexpr (ADDIN) {                                           // periodic chain: the wrap bond's terms (sd_blk_wrap_kernel); a kernel of its own, so that
+                                                                     // the open chain's instruction-cache-sensitive body does not carry the code
         const double *ap = P.addin + (H.base - P.shards.pstart[P.shards.rank]) * NC;
 #pragma unroll
         for (int s = 0; s < EC; ++s) {
@@ -266,22 +267,22 @@ SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdEpi &E, double *out_l
         }
     }
 }
-template <int NC, int EK>
+template <int NC, int EK, bool ADDIN = false>
 SD_BLKL_FN void sd_blkl_dispatch(const SdBlkParams &P, const SdEpi &E, double *out_local, const SdBlkHdr &H, const double *tb, unsigned code, uint32_t u,
                                 double (&red)[SD_NSLOT]) {
     const int jt = (int)(code >> 12);
     const bool hi = ((code >> 8) & 0xFu) != 0;                       // c128, classes of 10: second chunk of five
     switch (jt) {
-        case 0: sd_blkl_item<NC, 0, 0, EK>(P, E, out_local, H, tb, u, red); break;
-        case 1: sd_blkl_item<NC, 1, 0, EK>(P, E, out_local, H, tb, u, red); break;
+        case 0: sd_blkl_item<NC, 0, 0, EK, ADDIN>(P, E, out_local, H, tb, u, red); break;
+        case 1: sd_blkl_item<NC, 1, 0, EK, ADDIN>(P, E, out_local, H, tb, u, red); break;
         case 2:
-            if constexpr (NC == 2) { if (hi) { sd_blkl_item<NC, 2, 5, EK>(P, E, out_local, H, tb, u, red); break; } }
-            sd_blkl_item<NC, 2, 0, EK>(P, E, out_local, H, tb, u, red); break;
+            if constexpr (NC == 2) { if (hi) { sd_blkl_item<NC, 2, 5, EK, ADDIN>(P, E, out_local, H, tb, u, red); break; } }
+            sd_blkl_item<NC, 2, 0, EK, ADDIN>(P, E, out_local, H, tb, u, red); break;
         case 3:
-            if constexpr (NC == 2) { if (hi) { sd_blkl_item<NC, 3, 5, EK>(P, E, out_local, H, tb, u, red); break; } }
-            sd_blkl_item<NC, 3, 0, EK>(P, E, out_local, H, tb, u, red); break;
-        case 4: sd_blkl_item<NC, 4, 0, EK>(P, E, out_local, H, tb, u, red); break;
-        default: sd_blkl_item<NC, 5, 0, EK>(P, E, out_local, H, tb, u, red); break;
+            if constexpr (NC == 2) { if (hi) { sd_blkl_item<NC, 3, 5, EK, ADDIN>(P, E, out_local, H, tb, u, red); break; } }
+            sd_blkl_item<NC, 3, 0, EK, ADDIN>(P, E, out_local, H, tb, u, red); break;
+        case 4: sd_blkl_item<NC, 4, 0, EK, ADDIN>(P, E, out_local, H, tb, u, red); break;
+        default: sd_blkl_item<NC, 5, 0, EK, ADDIN>(P, E, out_local, H, tb, u, red); break;
     }
 }
 
@@ -289,7 +290,7 @@ SD_BLKL_FN void sd_blkl_dispatch(const SdBlkParams &P, const SdEpi &E, double *o
 #if defined(__CUDACC__)
 // grid = one persistent CTA per SM of NTHR threads; the last warp is the producer (sd_blk_producer: tile keys from the global
 // counter or the order table, headers, TMA of the own tiles), the others pull (tile, unit) items.
-template <int NC, int EK, int NTHR>
+template <int NC, int EK, int NTHR, bool ADDIN = false>
 __global__ void __launch_bounds__(NTHR, 1)
 sd_blkl_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constant__ SdVecView psi, double *out_local,
                      const __grid_constant__ SdEpi epi, int qfar, unsigned long long *tile_ctr) {
@@ -335,7 +336,7 @@ sd_blkl_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constan
                 const unsigned code = SD_SH.units[H.js * SD_BLK_MAXUNITS + un];
                 const uint32_t u = (code & 0xFFu) * 32u + lane;      // the lane's mid configuration
                 double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
-                sd_blkl_dispatch<NC, EK>(P, epi, out_local, H, tb, code, u, red);
+                sd_blkl_dispatch<NC, EK, ADDIN>(P, epi, out_local, H, tb, code, u, red);
                 if (!PLAIN && slotmask) sd_blk_item_reduce(H, slotmask, un, red, lane);
             }
             __syncwarp();

@@ -32,7 +32,7 @@ struct AlignedBuf {                      // 128-byte aligned doubles (the kernel
     ~AlignedBuf() { free(p); }
 };
 
-template <int NC, int EK>
+template <int NC, int EK, bool ADDIN = false>
 void run_tiles(const SdBlkHost &bh, const SdBlkParams &P, const SdVecView &psi, double *out_local, const SdEpi &epi,
                int qfar, double *red_total) {
     AlignedBuf tile;
@@ -63,7 +63,7 @@ void run_tiles(const SdBlkHost &bh, const SdBlkParams &P, const SdVecView &psi, 
             for (unsigned lane = 0; lane < 32; ++lane) {
                 const uint32_t u = (code & 0xFFu) * 32u + lane;
                 double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
-                sd_blkl_dispatch<NC, EK>(P, epi, out_local, H, tile.p, code, u, red);
+                sd_blkl_dispatch<NC, EK, ADDIN>(P, epi, out_local, H, tile.p, code, u, red);
                 for (int s = 0; s < SD_NSLOT; ++s) red_total[s] += red[s];
             }
         }
@@ -154,7 +154,11 @@ int emul_blk_apply(int L, int k, const double *Jhop, const double *Jz, const dou
     if (acc) { to_blk(acc, s_acc, nullptr); epi.acc = s_acc[rank].p; }
     double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
     const bool plain = epi.mode == SD_EPI_PLAIN && epi.red == 0 && !epi.acc && epi.hscale == 1.0;
-#define RUN(NC_, EK_) run_tiles<NC_, EK_>(bh, P, view, o.p, epi, qfar, red)
+#define RUN(NC_, EK_)                                                                         \
+    do {                                                                                      \
+        if (P.addin != nullptr) run_tiles<NC_, EK_, true>(bh, P, view, o.p, epi, qfar, red);   /* as sd_blk_launch_range */ \
+        else run_tiles<NC_, EK_>(bh, P, view, o.p, epi, qfar, red);                           \
+    } while (0)
     // halo mirror: the peers' shards are replaced by NaN-filled mirrors that only hold what the plan copies, chunk by
     // chunk, before the tiles of that chunk run (what sd_apply_blk_halo does with the copy engines and one event per chunk)
     SdShardPlan plan;
