@@ -401,6 +401,7 @@ static SdBlkParams sd_blk_params(const sd_model *m, int nc) {
     const sd_ctx *c = m->ctx;
     P.nbuf = m->blk.nbuf[nc - 1];
     P.pfp = m->blk.pfp;
+    P.wrap_on = m->has_wrap ? 1 : 0; P.wrapJ = m->wrap_hop; P.wrapJz4 = 0.25 * m->wrap_zz;
     P.order = m->blk.d_order; P.norder = m->blk.norder;
     P.key_lo = m->tile[0].keys[c->rank];
     P.key_hi = m->tile[0].keys[c->rank + 1];
@@ -505,7 +506,7 @@ int sd_model_create(sd_ctx *ctx, int L, int nup, const sd_bond *hop, int nhop, c
         const int min_tiles = sd_env_int("SD_BLK_MIN_TILES", 0);
         if (m->blk.ok && min_tiles > 0 && (1ULL << m->blk.host.P.A) < (uint64_t)min_tiles) m->path = SD_PATH_GENERIC;
     }
-    // a periodic chain runs on the block kernel (wrap pass + add-in) or on the generic one; the tiled kernel has no wrap bond
+    // a periodic chain runs on the block kernel (WRAP variant) or on the generic one; the tiled kernel has no wrap bond
     if (m->has_wrap && m->path == SD_PATH_TILED) m->path = SD_PATH_GENERIC;
     // shards: tile-aligned to the coarser (F64) tiling when tiled, plain equal split otherwise
     uint64_t bounds[SD_MAX_WORLD + 1];
@@ -575,7 +576,7 @@ int sd_model_free(sd_model *m) {
         SdTileDev &t = m->tile[w];
         cudaFree(t.d_perm); cudaFree(t.d_items); cudaFree(t.d_binomM);
     }
-    cudaFree(m->blk.d_order); cudaFree(m->d_wrap[0]); cudaFree(m->d_wrap[1]);
+    cudaFree(m->blk.d_order);
     cudaFree(m->blk.d_W); cudaFree(m->blk.d_js); cudaFree(m->blk.d_units); cudaFree(m->blk.d_items); cudaFree(m->blk.d_dmid);
     delete m;
     return SD_OK;
@@ -1219,7 +1220,7 @@ static int sd_blk_launch_range(sd_model *m, int nc, const SdBlkParams &P, const 
     } while (0)
 #define SD_HL_LEAN(NC_, EK_)                                                                                 \
     do {                                                                                                     \
-        if (P.addin != nullptr) SD_HL((sd_blkl_apply_kernel<NC_, EK_, 640, true>), 640);   /* periodic chain */ \
+        if (P.wrap_on) SD_HL((sd_blkl_apply_kernel<NC_, EK_, 640, true>), 640);   /* periodic chain: WRAP variant */ \
         else if (m->blk.threads == 512) SD_HL((sd_blkl_apply_kernel<NC_, EK_, 512>), 512);                   \
         else if (m->blk.threads == 768) SD_HL((sd_blkl_apply_kernel<NC_, EK_, 768>), 768);                   \
         else SD_HL((sd_blkl_apply_kernel<NC_, EK_, 640>), 640);                                              \
@@ -1259,20 +1260,6 @@ static int sd_apply_impl(sd_model *m, sd_vec *out, const sd_vec *psi, SdEpi epi,
         epi.partials = c->d_partials;
         epi.nparts = (unsigned)nkeys;
         const bool plain = epi.mode == SD_EPI_PLAIN && epi.red == 0 && !epi.acc && epi.hscale == 1.0 && !epi.hscale_dev;
-        if (m->has_wrap) {                                          // periodic chain: the wrap bond's terms first (sd_blk.h)
-            double *&wv = m->d_wrap[nc - 1];
-            if (!wv) {
-                SD_CUDA(cudaMalloc(&wv, sd_vec_bytes(psi)));
-                SD_CUDA(cudaMemsetAsync(wv, 0, sd_vec_bytes(psi), c->stream));   // padding stays zero: the pass writes real elements only
-            }
-            SdBlkWrap Wp;
-            Wp.J = m->wrap_hop; Wp.Jz4 = 0.25 * m->wrap_zz;
-            const unsigned wg = (unsigned)std::min<uint64_t>(nkeys, (uint64_t)c->sm_count * 16);
-            if (nc == 2) sd_blk_wrap_kernel<2><<<wg, SD_WRAP_THREADS, 0, c->stream>>>(P, Wp, psi->view, wv);
-            else sd_blk_wrap_kernel<1><<<wg, SD_WRAP_THREADS, 0, c->stream>>>(P, Wp, psi->view, wv);
-            SD_TRY(sd_launch_check(c, "sd_blk_wrap_kernel"));
-            P.addin = wv;
-        }
         SD_TRY(sd_blk_launch_range(m, nc, P, psi->view, out->d, epi, plain));
         if (slotmask) SD_TRY(sd_finish_reduce(c, (unsigned)nkeys, slotmask, slot_out));
     } else if (m->path == SD_PATH_TILED) {

@@ -85,7 +85,8 @@ struct SdBlkParams {
     const SdBlkItem *items;
     const double *dmid;              // [1 << M] diag of the mid sites + mid-internal zz, in ITEM order (same index as items[])
     uint32_t cap;                    // largest size_pad
-    const double *addin;             // optional: local shard of a block-layout vector added to H psi before the epilogue (the periodic wrap bond's terms, sd_blk_wrap_*)
+    int wrap_on;                     // periodic chain (SpinModel.jl:71-78): the bond between sites L-1 and 0 is present
+    double wrapJ, wrapJz4;           // its hop coefficient and Jz / 4
     const uint32_t *order;           // optional tile order of this shard (keys, norder of them); nullptr: rank order
     uint32_t norder;
     SdBlkShards shards;
@@ -152,123 +153,10 @@ SD_HD uint32_t sd_blk_encode(const SdBlkJs &I, int nc, int jt, uint32_t e, uint3
 // The bond between the last tail site and the first prefix site is the one bond of a periodic chain that is neither
 // inside a tile nor between two tiles of equal shape: flipping prefix bit 0 changes the prefix popcount, so the partner
 // tile has suffix popcount js +- 1, and flipping tail bit T-1 moves the element to tail class jt +- 1 -- the mid
-// configuration keeps its popcount, hence its index u in the class (item lists are shared by mid popcount).  It is
-// handled by a pass of its own BEFORE the block kernel: wrap[p] = Jz/4 * (+-1) psi[p] + J * psi[partner(p)] for every
-// stored element, which the block kernel then adds to H psi in front of its fused epilogue (SdBlkParams::addin).
-// One extra read of psi and of the partner halves, one write and one read of the wrap vector: the periodic chain costs
-// ~1.5x the open one instead of falling to the one-thread-per-state kernel (10x).
-struct SdBlkWrap {
-    double J;                            // hop coefficient of the wrap bond (0: none)
-    double Jz4;                          // Jz / 4 of the wrap bond
-};
-struct SdBlkWrapTile {
-    uint64_t base, pbase;                // stored-element offsets (global) of the tile and of its wrap partner tile
-    int js, jsp;                         // suffix popcounts
-    int b0;                              // prefix bit 0 (site 0)
-    bool pvalid;                         // the partner tile exists (0 <= jsp <= B)
-};
-SD_HD SdBlkWrapTile sd_blk_wrap_tile(const SdBlkParams &P, const uint64_t *W, uint64_t Pb) {
-    SdBlkWrapTile t;
-    const int A = P.A;
-    const uint64_t Pp = Pb ^ 1ULL;
-    t.b0 = (int)(Pb & 1ULL);
-    t.js = P.k - SD_POPC64(Pb);
-    t.jsp = P.k - SD_POPC64(Pp);
-    t.pvalid = t.jsp >= 0 && t.jsp <= SD_BLK_B;
-    t.base = 0; t.pbase = 0;
-    for (int q = 0; q < A; ++q) {
-        if (!((Pb >> q) & 1ULL)) t.base += W[q * (A + 1) + SD_POPC64(Pb & ((1ULL << q) - 1ULL))];
-        if (t.pvalid && !((Pp >> q) & 1ULL)) t.pbase += W[q * (A + 1) + SD_POPC64(Pp & ((1ULL << q) - 1ULL))];
-    }
-    return t;
-}
-// Row r = 0 .. 2^T - 1 of a tile is one (tail class jt, tail configuration e); the lanes of a warp walk its mid
-// configurations u.  own / part point at component 0 of the tile's / the partner tile's first stored element, out at the
-// tile's first element of the wrap vector.  Padding elements are never written: the wrap vector is zeroed once.
-struct SdBlkWrapRow {
-    int jt, jt2;                         // class of the row / of the partner row (-1: the bond does not act on this row)
-    uint32_t e, e2, nblk;
-    double d;                            // diagonal coefficient of the wrap bond on this row
-};
-// what a row is, independent of the tile (the kernel keeps the 2^T of them in shared memory)
-struct SdBlkWrapStatic {
-    signed char jt, e, tb, e2;           // class, tail configuration in the class, tail bit T-1, index of the configuration with that bit flipped in class jt -+ 1
-};
-SD_HD SdBlkWrapStatic sd_blk_wrap_static(int r) {
-    SdBlkWrapStatic S;
-    int jt = 0, first = 0;
-    while (r >= first + sd_cbinom(SD_BLK_T, jt)) { first += sd_cbinom(SD_BLK_T, jt); ++jt; }
-    const unsigned tau = sd_tail_cfg(SD_BLK_T, jt, r - first);
-    const int tb = (int)((tau >> (SD_BLK_T - 1)) & 1u);
-    S.jt = (signed char)jt; S.e = (signed char)(r - first); S.tb = (signed char)tb;
-    S.e2 = (signed char)sd_tail_rank(SD_BLK_T, tb ? jt - 1 : jt + 1, tau ^ (1u << (SD_BLK_T - 1)));
-    return S;
-}
-SD_HD SdBlkWrapRow sd_blk_wrap_row(const SdBlkWrap &Wp, const SdBlkWrapTile &t, const SdBlkJs &I, const SdBlkWrapStatic &S) {
-    SdBlkWrapRow R;
-    R.jt = S.jt; R.e = (uint32_t)S.e; R.nblk = I.cls[S.jt].nblk;
-    R.d = (S.tb == t.b0) ? Wp.Jz4 : -Wp.Jz4;
-    R.jt2 = -1; R.e2 = 0;
-    if (S.tb != t.b0 && Wp.J != 0.0 && t.pvalid) { R.jt2 = S.tb ? S.jt - 1 : S.jt + 1; R.e2 = (uint32_t)S.e2; }
-    return R;
-}
-template <int NC>
-SD_HD void sd_blk_wrap_elem(const SdBlkWrap &Wp, const SdBlkWrapRow &R, const SdBlkJs &I, const SdBlkJs &Ip, uint32_t u,
-                            const double *own, const double *part, double *out) {
-    const size_t p = sd_blk_encode(I, NC, R.jt, R.e, u);
-    double v[NC];
-#pragma unroll
-    for (int c = 0; c < NC; ++c) v[c] = R.d * own[p * NC + c];
-    if (R.jt2 >= 0) {
-        const size_t p2 = sd_blk_encode(Ip, NC, R.jt2, R.e2, u);
-#pragma unroll
-        for (int c = 0; c < NC; ++c) v[c] += Wp.J * part[p2 * NC + c];
-    }
-#pragma unroll
-    for (int c = 0; c < NC; ++c) out[p * NC + c] = v[c];
-}
-// A work unit of the wrap pass = what one warp walks with its lanes over the mid configurations u: for c128 one row
-// (32 per tile), for f64 one PAIR row (tail configurations 2s, 2s+1 of a class share 16-byte slots: own value and result
-// move as double2, coalesced; 18 per tile) or the plain last row of an odd class.
-SD_HDC int sd_blk_wrap_units(int nc) { return nc == 2 ? (1 << SD_BLK_T) : 18; }
-static_assert(SD_BLK_T == 5, "18 pair rows: sum over jt of ceil(C(5, jt) / 2)");
-template <int NC>
-struct SdBlkWrapUnit {
-    SdBlkWrapRow r0, r1;                 // f64: rows 2s and 2s+1 (r1.nblk = 0: plain last row); c128: r0 only
-    uint32_t nblk;
-};
-// rows of work unit `unit`: rows[0] and rows[1] (-1: none)
-SD_HD void sd_blk_wrap_unit_rows(int nc, int unit, int &r0, int &r1) {
-    if (nc == 2) { r0 = unit; r1 = -1; return; }
-    int jt = 0, first_unit = 0, first_row = 0;
-    while (unit >= first_unit + (sd_cbinom(SD_BLK_T, jt) + 1) / 2) {
-        first_unit += (sd_cbinom(SD_BLK_T, jt) + 1) / 2; first_row += sd_cbinom(SD_BLK_T, jt); ++jt;
-    }
-    const int s = unit - first_unit, nt = sd_cbinom(SD_BLK_T, jt);
-    r0 = first_row + 2 * s;
-    r1 = (2 * s + 1 < nt) ? r0 + 1 : -1;
-}
-// rows: the 2^T static row descriptors (sd_blk_wrap_static), r0 / r1 from sd_blk_wrap_unit_rows
-template <int NC>
-SD_HD SdBlkWrapUnit<NC> sd_blk_wrap_unit(const SdBlkWrap &Wp, const SdBlkWrapTile &t, const SdBlkJs &I, const SdBlkWrapStatic *rows, int r0, int r1) {
-    SdBlkWrapUnit<NC> U;
-    U.r0 = sd_blk_wrap_row(Wp, t, I, rows[r0]);
-    if (r1 >= 0) U.r1 = sd_blk_wrap_row(Wp, t, I, rows[r1]);
-    else { U.r1 = U.r0; U.r1.nblk = 0; }
-    U.nblk = U.r0.nblk;
-    return U;
-}
-template <int NC>
-SD_HD void sd_blk_wrap_apply(const SdBlkWrap &Wp, const SdBlkWrapUnit<NC> &U, const SdBlkJs &I, const SdBlkJs &Ip, uint32_t u,
-                             const double *own, const double *part, double *out) {
-    if (NC == 2 || U.r1.nblk == 0) { sd_blk_wrap_elem<NC>(Wp, U.r0, I, Ip, u, own, part, out); return; }
-    const size_t p = sd_blk_encode(I, 1, U.r0.jt, U.r0.e, u);      // even tail configuration of the pair: 16-byte aligned slot
-    const double2 o = *(const double2 *)(own + p);
-    double2 v = make_double2(U.r0.d * o.x, U.r1.d * o.y);
-    if (U.r0.jt2 >= 0) v.x += Wp.J * part[sd_blk_encode(Ip, 1, U.r0.jt2, U.r0.e2, u)];
-    if (U.r1.jt2 >= 0) v.y += Wp.J * part[sd_blk_encode(Ip, 1, U.r1.jt2, U.r1.e2, u)];
-    *(double2 *)(out + p) = v;
-}
+// configuration keeps its popcount, hence its index u in the class (item lists are shared by mid popcount).  The tile
+// header carries the partner tile (wptr, jsw) and prefix bit 0; the item body of the WRAP kernel variant (sd_blkl.h) adds,
+// per tail configuration whose last bit differs from prefix bit 0, one element of the partner tile, and +-Jz/4 on the
+// diagonal.  The open chain's kernels are separate instantiations and carry none of it.
 
 // ------------------------------------------------------------------ tile header
 struct alignas(16) SdBlkEnt {
@@ -287,6 +175,9 @@ struct alignas(16) SdBlkHdr {
     double dP[2];                        // prefix diag + prefix|mid zz, by first mid bit
     double Jx;                           // hop coefficient of the prefix|mid bond (0: none)
     const double *xptr;                  // stored base of the crossing partner tile (component 0)
+    const double *wptr;                  // periodic chain: stored base of the wrap partner tile (prefix bit 0 flipped), nullptr: none / no hop
+    int jsw, b0;                         // its suffix popcount; prefix bit 0 of this tile
+    int wloc;                            // the wrap partner tile lives in this rank's shard
     SdBlkEnt nb[SD_BLK_MAXA + 1];        // neighbour tiles of the active prefix bonds (one LDS.128 per entry); entry nnb: the crossing bond (if active)
     unsigned char nbloc[SD_BLK_MAXA + 3];   // entry lives in this rank's shard (the producer's L2 prefetch skips peer memory); [nnb]: the crossing partner
     double usum[SD_NSLOT][SD_BLK_MAXUNITS];   // per-unit reduction results (deterministic: summed in unit order)
@@ -303,17 +194,23 @@ SD_HD uint64_t sd_blk_key_prefix(uint64_t key, int A) {
 }
 struct SdBlkHdrLane {
     uint64_t term, wq, wn;       // rank-base contribution; W of this site / of the bond partner
+    uint64_t wterm;              // periodic chain: rank-base contribution of this site in the wrap partner tile (prefix bit 0 flipped)
     double d;                    // diagonal contribution of site q and bond (q, q+1)
     int bit;
     bool act;                    // bond (q, q+1) is an active prefix-internal hop
 };
+template <bool WRAP = false>
 SD_HD SdBlkHdrLane sd_blk_hdr_lane(const SdBlkParams &P, const uint64_t *W, uint64_t Pb, int q) {
     const int A = P.A;
     SdBlkHdrLane l;
     const int bit = (int)((Pb >> q) & 1ULL), bn = (int)((Pb >> (q + 1)) & 1ULL);
     const int below = SD_POPC64(Pb & ((1ULL << q) - 1ULL));
-    l.term = 0; l.wq = 0; l.wn = 0; l.d = 0.0; l.act = false; l.bit = bit;
+    l.term = 0; l.wq = 0; l.wn = 0; l.d = 0.0; l.act = false; l.bit = bit; l.wterm = 0;
     if (q < A) {
+        if constexpr (WRAP) {
+            const uint64_t Pw = Pb ^ 1ULL;
+            if (!((Pw >> q) & 1ULL)) l.wterm = W[q * (A + 1) + SD_POPC64(Pw & ((1ULL << q) - 1ULL))];
+        }
         l.wq = W[q * (A + 1) + below];
         if (!bit) l.term = l.wq;
         const double sq = bit ? 0.5 : -0.5;
@@ -331,9 +228,9 @@ SD_HD SdBlkHdrLane sd_blk_hdr_lane(const SdBlkParams &P, const uint64_t *W, uint
 // (Round 2 tried the remote tiles last with an L1 prefetch at the start of the item: peer-memory prefetches are
 // pathologically slow -- 237 ms per L = 32 apply on 2 GPUs instead of 3.4 -- so remote tiles are plain .cg loads; an
 // L2 prefetch of the later LOCAL entries at the start of the item cost 10 % too: profiles/round2_h_ab.txt.)
-template <int NC, class HDR = SdBlkHdr>
+template <int NC, class HDR = SdBlkHdr, bool WRAP = false>
 SD_HD void sd_blk_hdr_fill(const SdBlkParams &P, const SdBlkHdrLane &l, uint64_t Pb, uint64_t key, uint64_t base, double dpre,
-                           unsigned actmask, int qfar, int q, HDR &H, const SdVecView &psi) {
+                           unsigned actmask, int qfar, int q, HDR &H, const SdVecView &psi, uint64_t wbase = 0) {
     const int A = P.A, js = P.k - SD_POPC64(Pb);
     const int bit = l.bit;
     const unsigned farmask = (qfar >= 32) ? 0xffffffffu : ((1u << qfar) - 1u);
@@ -370,6 +267,16 @@ SD_HD void sd_blk_hdr_fill(const SdBlkParams &P, const SdBlkHdrLane &l, uint64_t
         H.dP[1] = dpre + P.Jz[q] * sl * (0.5);
     }
     if (q == 0) {
+        if constexpr (WRAP) {
+            H.wptr = nullptr; H.jsw = js; H.b0 = (int)(Pb & 1ULL); H.wloc = 0;
+            const int jsw = P.k - SD_POPC64(Pb ^ 1ULL);
+            if (P.wrapJ != 0.0 && jsw >= 0 && jsw <= SD_BLK_B) {
+                const int wowner = sd_blk_owner(P.shards, wbase);
+                H.wptr = psi.base[wowner] + (size_t)NC * wbase;
+                H.jsw = jsw;
+                H.wloc = wowner == P.shards.rank ? 1 : 0;
+            }
+        }
         H.base = base;
         H.js = js;
         H.valid = 1;
@@ -386,11 +293,11 @@ SD_HD void sd_blk_hdr_fill(const SdBlkParams &P, const SdBlkHdrLane &l, uint64_t
     }
 }
 #if defined(__CUDACC__)
-template <int NC, class HDR = SdBlkHdr>
+template <int NC, class HDR = SdBlkHdr, bool WRAP = false>
 __device__ __forceinline__ void sd_blk_make_hdr(const SdBlkParams &P, const uint64_t *W, uint64_t key, HDR &H,
                                                 const SdVecView &psi, int qfar, unsigned lane) {
     const uint64_t Pb = sd_blk_key_prefix(key, P.A);
-    SdBlkHdrLane l = sd_blk_hdr_lane(P, W, Pb, (int)lane);
+    SdBlkHdrLane l = sd_blk_hdr_lane<WRAP>(P, W, Pb, (int)lane);
     uint64_t base = l.term;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) base += __shfl_xor_sync(0xffffffffu, base, o);
@@ -398,24 +305,30 @@ __device__ __forceinline__ void sd_blk_make_hdr(const SdBlkParams &P, const uint
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dpre += __shfl_xor_sync(0xffffffffu, dpre, o);
     const unsigned actmask = __ballot_sync(0xffffffffu, l.act);
-    sd_blk_hdr_fill<NC, HDR>(P, l, Pb, key, base, dpre, actmask, qfar, (int)lane, H, psi);
+    uint64_t wbase = l.wterm;
+    if constexpr (WRAP) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wbase += __shfl_xor_sync(0xffffffffu, wbase, o);
+    }
+    sd_blk_hdr_fill<NC, HDR, WRAP>(P, l, Pb, key, base, dpre, actmask, qfar, (int)lane, H, psi, wbase);
 }
 #endif
 // the same header on the host (tests/emul, sd_halo_host.h): the 32 "lanes" in a loop
-template <int NC>
+template <int NC, bool WRAP = false>
 inline void sd_blk_hdr_host(const SdBlkParams &P, const uint64_t *W, uint64_t key, int qfar, const SdVecView &psi, SdBlkHdr &H) {
     const uint64_t Pb = sd_blk_prefix_bits(key, P.A);
     SdBlkHdrLane lanes[32];
-    uint64_t base = 0;
+    uint64_t base = 0, wbase = 0;
     double dpre = 0.0;
     unsigned actmask = 0;
     for (int q = 0; q < 32; ++q) {
-        lanes[q] = sd_blk_hdr_lane(P, W, Pb, q);
+        lanes[q] = sd_blk_hdr_lane<WRAP>(P, W, Pb, q);
         base += lanes[q].term;
+        wbase += lanes[q].wterm;
         dpre += lanes[q].d;
         if (lanes[q].act) actmask |= 1u << q;
     }
-    for (int q = 0; q < 32; ++q) sd_blk_hdr_fill<NC>(P, lanes[q], Pb, key, base, dpre, actmask, qfar, q, H, psi);
+    for (int q = 0; q < 32; ++q) sd_blk_hdr_fill<NC, SdBlkHdr, WRAP>(P, lanes[q], Pb, key, base, dpre, actmask, qfar, q, H, psi, wbase);
 }
 
 // ------------------------------------------------------------------ per-item body
@@ -586,7 +499,7 @@ __device__ __forceinline__ void sd_blk_flush_sums(const SdBlkSmem &S, SdBlkHdr &
     __syncwarp();
 }
 // producer warp: tile keys from the global counter, tile headers, TMA of the own tiles
-template <int NC>
+template <int NC, bool WRAP = false>
 __device__ __forceinline__ void sd_blk_producer(const SdBlkParams &P, const SdBlkSmem &S, const SdVecView &psi, int qfar,
                                                 unsigned long long *tile_ctr, unsigned lane, const SdEpi &epi, int slotmask) {
     const int nbuf = P.nbuf;
@@ -626,7 +539,7 @@ __device__ __forceinline__ void sd_blk_producer(const SdBlkParams &P, const SdBl
             }
             break;
         }
-        sd_blk_make_hdr<NC>(P, S.W, key, H, psi, qfar, lane);
+        sd_blk_make_hdr<NC, SdBlkHdr, WRAP>(P, S.W, key, H, psi, qfar, lane);
         __syncwarp();
         const uint32_t bytes = S.js[H.js].size_pad * (uint32_t)(NC * 8);
         const char *src = (const char *)(psi.base[P.shards.rank] + (size_t)NC * H.base);
@@ -651,6 +564,9 @@ __device__ __forceinline__ void sd_blk_producer(const SdBlkParams &P, const SdBl
                     const uint32_t pb = Hp.nbloc[lane] ? S.js[Hp.js].size_pad * (uint32_t)(NC * 8) : 0u;   // local tiles only
                     if (pb)
                     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(Hp.nb[lane].p), "r"(pb) : "memory");
+                } else if (WRAP && (int)lane == cnt + 1 && Hp.wptr != nullptr && Hp.wloc) {     // periodic chain: the wrap partner tile (its own js)
+                    const uint32_t pb = S.js[Hp.jsw].size_pad * (uint32_t)(NC * 8);
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(Hp.wptr), "r"(pb) : "memory");
                 } else if ((P.pfp & 16) && (int)lane == cnt && Hp.xptr != nullptr && Hp.nbloc[Hp.nnb]) {   // the prefix|mid crossing partner (its own js)
                     const uint32_t pb = S.js[Hp.jsx].size_pad * (uint32_t)(NC * 8);
                     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(Hp.xptr), "r"(pb) : "memory");

@@ -19,6 +19,7 @@
 // against 5.52: four item-table reads and four serial mid-hop loops per lane cost more than the saved load rounds, and
 // the extra code hurts a kernel that is instruction-cache sensitive.
 #pragma once
+#include <type_traits>
 #include "sd_blk.h"
 
 #define SD_BLKL_NBUF 3           // tile buffers (f64); c128 uses 2
@@ -44,6 +45,11 @@ static SdBlkShared sd_blkl_sh;
 #define SD_SH sd_blkl_sh
 #define SD_BLKL_FN inline
 #endif
+// compile-time loop: f(std::integral_constant<int, 0>) ... f(std::integral_constant<int, N - 1>)
+template <int N, int I = 0, class F>
+SD_BLKL_FN void sd_static_for(F &&f) {
+    if constexpr (I < N) { f(std::integral_constant<int, I>{}); sd_static_for<N, I + 1>(f); }
+}
 // resolves the epilogue's hscale (device: one thread, before the CTA barrier; host: the emulation)
 SD_BLKL_FN void sd_blkl_ctx_init(const SdEpi &epi) {
     SD_SH.hs = epi.hscale_dev ? epi.hscale / sqrt(*epi.hscale_dev) : epi.hscale;
@@ -52,7 +58,7 @@ SD_BLKL_FN void sd_blkl_ctx_init(const SdEpi &epi) {
 // EK: epilogue kind, compile-time so that each instantiation only carries the code it runs (the kernel is instruction-
 // cache sensitive): 0 plain out = H psi; 1 Lanczos: out = hs * H psi with the fused <psi, out> (every Lanczos flavour);
 // 2 generic (rescaled / Chebyshev step, psi_t accumulation, phi dot, norm: sd_epilogue_hs).
-template <int NC, int JT, int S0, int EK, bool ADDIN = false>
+template <int NC, int JT, int S0, int EK, bool WRAP = false>
 SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdEpi &E, double *out_local, const SdBlkHdr &H, const double *tb, uint32_t u,
                              double (&red)[SD_NSLOT]) {
     constexpr bool PLAIN = EK == 0;
@@ -75,15 +81,6 @@ SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdEpi &E, double *out_l
     double2 acc[EC], t0[EC], t1[EC];
 #pragma unroll
     for (int s = 0; s < EC; ++s) acc[s] = t0[s] = t1[s] = make_double2(0.0, 0.0);   // t0/t1: conditionally loaded below; left undefined they end up on the stack
-    if constexpr (ADDIN) {                                           // periodic chain: the wrap bond's terms (sd_blk_wrap_kernel); a kernel of its own, so that
-                                                                     // the open chain's instruction-cache-sensitive body does not carry the code
-        const double *ap = P.addin + (H.base - P.shards.pstart[P.shards.rank]) * NC;
-#pragma unroll
-        for (int s = 0; s < EC; ++s) {
-            if (HALF && s == EC - 1) acc[s].x = ap[o[s]];
-            else acc[s] = *(const double2 *)(ap + o[s]);
-        }
-    }
 #define SD_LEAN_LOAD(t_, p_)                                                                  \
     do {                                                                                      \
         const double *q_ = (p_);                                                              \
@@ -131,6 +128,48 @@ SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdEpi &E, double *out_l
     if (n < nnb) SD_LEAN_FMA(t0, e0.J);
 #undef SD_LEAN_LOAD
 #undef SD_LEAN_FMA
+    // ---- periodic chain (WRAP variant): the bond between tail site T-1 and prefix site 0.  +-Jz/4 on the diagonal of every
+    // element; the hop acts on the tail configurations whose last bit differs from prefix bit 0 (tile-uniform) and reads one
+    // element of the wrap partner tile: class jt -+ 1, the configuration with the last bit flipped, the same u.  The loads
+    // come after the streams, when the stream registers are free again.
+    if constexpr (WRAP) {
+        const int b0 = H.b0;
+        const double dw = b0 ? P.wrapJz4 : -P.wrapJz4;
+        const double *wp = H.wptr;
+        const SdBlkJs &Iw = SD_SH.js[H.jsw];
+        sd_static_for<NE>([&](auto tc) {
+            constexpr int t = decltype(tc)::value;
+            constexpr unsigned cfgt = sd_tail_cfg(T, JT, E0 + t);
+            constexpr int tbit = (int)((cfgt >> (T - 1)) & 1u);
+            constexpr int jt2 = tbit ? JT - 1 : JT + 1;
+            double wr = 0.0, wi = 0.0;
+            if constexpr (jt2 >= 0 && jt2 <= T) {
+                if (wp != nullptr && tbit != b0) {
+                    constexpr int e2 = sd_tail_rank(T, jt2, cfgt ^ (1u << (T - 1)));
+                    constexpr int NT2 = sd_cbinom(T, jt2);
+                    const SdBlkCls c2 = Iw.cls[jt2];
+                    if (NC == 1) {
+                        const uint32_t p2 = ((NT2 & 1) && e2 == NT2 - 1) ? c2.cb + (uint32_t)e2 * c2.pitch + u
+                                                                         : c2.cb + (uint32_t)(e2 >> 1) * 2u * c2.pitch + 2u * u + (uint32_t)(e2 & 1);
+                        wr = P.wrapJ * sd_blk_ldg_half(wp + p2).x;
+                    } else {
+                        const double2 v = sd_blk_ldg(wp + 2u * (c2.cb + (uint32_t)e2 * c2.pitch + u));
+                        wr = P.wrapJ * v.x; wi = P.wrapJ * v.y;
+                    }
+                }
+            }
+            const double dsg = tbit ? dw : -dw;
+            if (NC == 1) {
+                constexpr int sl = (E0 + t) >> 1;
+                const double ownv = (HALF && sl == EC - 1) ? tb[o[sl]] : tb[o[sl] + (uint32_t)((E0 + t) & 1)];
+                SD_BLK_EL(acc, t, 1) += wr + dsg * ownv;
+            } else {
+                const double2 ownv = *(const double2 *)(tb + o[t]);
+                acc[t].x += wr + dsg * ownv.x;
+                acc[t].y += wi + dsg * ownv.y;
+            }
+        });
+    }
     // ---- own block: diagonal + tail-internal hops (registers, compile-time permutation)
     const uint4 it = sd_blk_ld_item(P.items + cls.item_off + u);     // x,y,z = nb[12]; w = c | u2x << 16
     const unsigned cmid = it.w & ((1u << M) - 1u);
@@ -267,22 +306,22 @@ SD_BLKL_FN void sd_blkl_item(const SdBlkParams &P, const SdEpi &E, double *out_l
         }
     }
 }
-template <int NC, int EK, bool ADDIN = false>
+template <int NC, int EK, bool WRAP = false>
 SD_BLKL_FN void sd_blkl_dispatch(const SdBlkParams &P, const SdEpi &E, double *out_local, const SdBlkHdr &H, const double *tb, unsigned code, uint32_t u,
                                 double (&red)[SD_NSLOT]) {
     const int jt = (int)(code >> 12);
     const bool hi = ((code >> 8) & 0xFu) != 0;                       // c128, classes of 10: second chunk of five
     switch (jt) {
-        case 0: sd_blkl_item<NC, 0, 0, EK, ADDIN>(P, E, out_local, H, tb, u, red); break;
-        case 1: sd_blkl_item<NC, 1, 0, EK, ADDIN>(P, E, out_local, H, tb, u, red); break;
+        case 0: sd_blkl_item<NC, 0, 0, EK, WRAP>(P, E, out_local, H, tb, u, red); break;
+        case 1: sd_blkl_item<NC, 1, 0, EK, WRAP>(P, E, out_local, H, tb, u, red); break;
         case 2:
-            if constexpr (NC == 2) { if (hi) { sd_blkl_item<NC, 2, 5, EK, ADDIN>(P, E, out_local, H, tb, u, red); break; } }
-            sd_blkl_item<NC, 2, 0, EK, ADDIN>(P, E, out_local, H, tb, u, red); break;
+            if constexpr (NC == 2) { if (hi) { sd_blkl_item<NC, 2, 5, EK, WRAP>(P, E, out_local, H, tb, u, red); break; } }
+            sd_blkl_item<NC, 2, 0, EK, WRAP>(P, E, out_local, H, tb, u, red); break;
         case 3:
-            if constexpr (NC == 2) { if (hi) { sd_blkl_item<NC, 3, 5, EK, ADDIN>(P, E, out_local, H, tb, u, red); break; } }
-            sd_blkl_item<NC, 3, 0, EK, ADDIN>(P, E, out_local, H, tb, u, red); break;
-        case 4: sd_blkl_item<NC, 4, 0, EK, ADDIN>(P, E, out_local, H, tb, u, red); break;
-        default: sd_blkl_item<NC, 5, 0, EK, ADDIN>(P, E, out_local, H, tb, u, red); break;
+            if constexpr (NC == 2) { if (hi) { sd_blkl_item<NC, 3, 5, EK, WRAP>(P, E, out_local, H, tb, u, red); break; } }
+            sd_blkl_item<NC, 3, 0, EK, WRAP>(P, E, out_local, H, tb, u, red); break;
+        case 4: sd_blkl_item<NC, 4, 0, EK, WRAP>(P, E, out_local, H, tb, u, red); break;
+        default: sd_blkl_item<NC, 5, 0, EK, WRAP>(P, E, out_local, H, tb, u, red); break;
     }
 }
 
@@ -290,7 +329,7 @@ SD_BLKL_FN void sd_blkl_dispatch(const SdBlkParams &P, const SdEpi &E, double *o
 #if defined(__CUDACC__)
 // grid = one persistent CTA per SM of NTHR threads; the last warp is the producer (sd_blk_producer: tile keys from the global
 // counter or the order table, headers, TMA of the own tiles), the others pull (tile, unit) items.
-template <int NC, int EK, int NTHR, bool ADDIN = false>
+template <int NC, int EK, int NTHR, bool WRAP = false>
 __global__ void __launch_bounds__(NTHR, 1)
 sd_blkl_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constant__ SdVecView psi, double *out_local,
                      const __grid_constant__ SdEpi epi, int qfar, unsigned long long *tile_ctr) {
@@ -318,7 +357,7 @@ sd_blkl_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constan
         SdBlkSmem S;
         S.full = SD_SH.full; S.empty = SD_SH.empty; S.hdr = SD_SH.hdr; S.W = P.W; S.js = SD_SH.js;
         S.tiles = (double *)sd_blk_smem;
-        sd_blk_producer<NC>(P, S, psi, qfar, tile_ctr, lane, epi, PLAIN ? 0 : sd_epi_slotmask(epi.red));
+        sd_blk_producer<NC, WRAP>(P, S, psi, qfar, tile_ctr, lane, epi, PLAIN ? 0 : sd_epi_slotmask(epi.red));
     } else {
         const int slotmask = PLAIN ? 0 : sd_epi_slotmask(epi.red);
         unsigned b = 0, phase = 0;
@@ -336,7 +375,7 @@ sd_blkl_apply_kernel(const __grid_constant__ SdBlkParams P, const __grid_constan
                 const unsigned code = SD_SH.units[H.js * SD_BLK_MAXUNITS + un];
                 const uint32_t u = (code & 0xFFu) * 32u + lane;      // the lane's mid configuration
                 double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
-                sd_blkl_dispatch<NC, EK, ADDIN>(P, epi, out_local, H, tb, code, u, red);
+                sd_blkl_dispatch<NC, EK, WRAP>(P, epi, out_local, H, tb, code, u, red);
                 if (!PLAIN && slotmask) sd_blk_item_reduce(H, slotmask, un, red, lane);
             }
             __syncwarp();

@@ -110,40 +110,4 @@ __global__ void __launch_bounds__(256) sd_blk_obs_kernel(const __grid_constant__
     o[lane] = mag[0]; o[32 + lane] = mag[1]; o[64 + lane] = zz[0]; o[96 + lane] = zz[1];
 }
 
-// The periodic wrap bond's terms for every stored element of the shard (sd_blk.h, "periodic wrap bond"): one CTA per tile
-// (grid-stride over the keys), a warp per work unit (c128: one row; f64: one pair row), lanes = mid configurations.
-#define SD_WRAP_THREADS 128             // small CTAs, many per SM: the per-tile header (one thread) of one CTA hides behind the rows of the others
-template <int NC>
-__global__ void __launch_bounds__(SD_WRAP_THREADS) sd_blk_wrap_kernel(const __grid_constant__ SdBlkParams P, const __grid_constant__ SdBlkWrap Wp,
-                                                                      const __grid_constant__ SdVecView psi, double *wrap_local) {
-    __shared__ SdBlkWrapTile s_t;
-    __shared__ SdBlkWrapStatic s_rows[1 << SD_BLK_T];
-    __shared__ signed char s_unit[1 << SD_BLK_T][2];
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    if (threadIdx.x < (1u << SD_BLK_T)) {
-        s_rows[threadIdx.x] = sd_blk_wrap_static((int)threadIdx.x);
-        if ((int)threadIdx.x < sd_blk_wrap_units(NC)) {
-            int r0, r1;
-            sd_blk_wrap_unit_rows(NC, (int)threadIdx.x, r0, r1);
-            s_unit[threadIdx.x][0] = (signed char)r0; s_unit[threadIdx.x][1] = (signed char)r1;
-        }
-    }
-    for (uint64_t key = P.key_lo + blockIdx.x; key < P.key_hi; key += gridDim.x) {
-        const uint64_t Pb = __brevll(~key) >> (64 - P.A);
-        const int js = P.k - __popcll(Pb);
-        if (js < 0 || js > SD_BLK_B) continue;                         // uniform over the CTA
-        __syncthreads();
-        if (threadIdx.x == 0) s_t = sd_blk_wrap_tile(P, P.W, Pb);
-        __syncthreads();
-        const SdBlkWrapTile t = s_t;
-        const SdBlkJs &I = P.js[t.js], &Ip = P.js[t.pvalid ? t.jsp : t.js];
-        const double *own = psi.base[P.shards.rank] + (size_t)NC * t.base;
-        const double *part = t.pvalid ? psi.base[sd_blk_owner(P.shards, t.pbase)] + (size_t)NC * t.pbase : own;
-        double *out = wrap_local + (size_t)NC * (t.base - P.shards.pstart[P.shards.rank]);
-        for (int unit = (int)warp; unit < sd_blk_wrap_units(NC); unit += (int)nwarp) {
-            const SdBlkWrapUnit<NC> U = sd_blk_wrap_unit<NC>(Wp, t, I, s_rows, s_unit[unit][0], s_unit[unit][1]);
-            for (uint32_t u = lane; u < U.nblk; u += 32u) sd_blk_wrap_apply<NC>(Wp, U, I, Ip, u, own, part, out);
-        }
-    }
-}
 #endif

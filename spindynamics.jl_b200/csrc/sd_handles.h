@@ -171,8 +171,7 @@ struct sd_model {
     SdBlkDev blk;                   // block-layout kernel (sd_blk.h)
     bool blk_layout = false;        // vectors of this model are stored in block layout
     bool has_wrap = false;          // periodic chain: nearest-neighbour bonds plus the wrap bond (sites L-1, 0)
-    double wrap_hop = 0.0, wrap_zz = 0.0;   // its hop coefficient and Jz; handled by sd_blk_wrap_kernel in front of the block kernel
-    double *d_wrap[2] = {nullptr, nullptr};  // the wrap terms of the current apply ([0]: f64, [1]: c128), local shard, allocated on first use
+    double wrap_hop = 0.0, wrap_zz = 0.0;   // its hop coefficient and Jz (the WRAP variant of the block kernel, sd_blkl.h)
     int live_vecs = 0;
     std::vector<sd_vec *> pool;     // idle work vectors of the recurrences (SdVecGuard)
     bool free_pending = false;      // sd_model_free was called while vectors were alive

@@ -32,7 +32,7 @@ struct AlignedBuf {                      // 128-byte aligned doubles (the kernel
     ~AlignedBuf() { free(p); }
 };
 
-template <int NC, int EK, bool ADDIN = false>
+template <int NC, int EK, bool WRAP = false>
 void run_tiles(const SdBlkHost &bh, const SdBlkParams &P, const SdVecView &psi, double *out_local, const SdEpi &epi,
                int qfar, double *red_total) {
     AlignedBuf tile;
@@ -49,7 +49,7 @@ void run_tiles(const SdBlkHost &bh, const SdBlkParams &P, const SdVecView &psi, 
         SdBlkHdr H;
         std::memset(&H, 0, sizeof(H));
         for (SdBlkEnt &e : H.nb) { e.p = nullptr; e.J = NAN; }       // entries the header does not write must never be used
-        sd_blk_hdr_host<NC>(P, bh.W.data(), key, qfar, psi, H);
+        sd_blk_hdr_host<NC, WRAP>(P, bh.W.data(), key, qfar, psi, H);
         // pipeline overrun entries: valid pointer, J = 0 (the kernel never dereferences them: ok_ is false)
         // ---- own tile -> "shared memory" (the TMA bulk copy); the rest of the buffer stays NaN
         const uint32_t size_pad = bh.js[H.js].size_pad;
@@ -63,7 +63,7 @@ void run_tiles(const SdBlkHost &bh, const SdBlkParams &P, const SdVecView &psi, 
             for (unsigned lane = 0; lane < 32; ++lane) {
                 const uint32_t u = (code & 0xFFu) * 32u + lane;
                 double red[SD_NSLOT] = {0.0, 0.0, 0.0, 0.0};
-                sd_blkl_dispatch<NC, EK, ADDIN>(P, epi, out_local, H, tile.p, code, u, red);
+                sd_blkl_dispatch<NC, EK, WRAP>(P, epi, out_local, H, tile.p, code, u, red);
                 for (int s = 0; s < SD_NSLOT; ++s) red_total[s] += red[s];
             }
         }
@@ -156,7 +156,7 @@ int emul_blk_apply(int L, int k, const double *Jhop, const double *Jz, const dou
     const bool plain = epi.mode == SD_EPI_PLAIN && epi.red == 0 && !epi.acc && epi.hscale == 1.0;
 #define RUN(NC_, EK_)                                                                         \
     do {                                                                                      \
-        if (P.addin != nullptr) run_tiles<NC_, EK_, true>(bh, P, view, o.p, epi, qfar, red);   /* as sd_blk_launch_range */ \
+        if (P.wrap_on) run_tiles<NC_, EK_, true>(bh, P, view, o.p, epi, qfar, red);   /* as sd_blk_launch_range */ \
         else run_tiles<NC_, EK_>(bh, P, view, o.p, epi, qfar, red);                           \
     } while (0)
     // halo mirror: the peers' shards are replaced by NaN-filled mirrors that only hold what the plan copies, chunk by
@@ -173,38 +173,8 @@ int emul_blk_apply(int L, int k, const double *Jhop, const double *Jz, const dou
             view.base[g] = mirror[g].p - (int64_t)pstart[g] * NC;
         }
     }
-    // periodic chain: the wrap pass of sd_blk_wrap_kernel (one "warp" per row, lanes = mid configurations) into a zeroed
-    // vector, which the item body adds in front of the epilogue
-    AlignedBuf wv;
-    if (g_wrap_J != 0.0 || g_wrap_Jz != 0.0) {
-        wv.alloc(nloc, 0.0);
-        SdBlkWrap Wp;
-        Wp.J = g_wrap_J; Wp.Jz4 = 0.25 * g_wrap_Jz;
-        for (uint64_t key = P.key_lo; key < P.key_hi; ++key) {
-            const uint64_t Pb = sd_blk_key_prefix(key, P.A);
-            const int js = P.k - SD_POPC64(Pb);
-            if (js < 0 || js > SD_BLK_B) continue;
-            const SdBlkWrapTile t = sd_blk_wrap_tile(P, P.W, Pb);
-            const SdBlkJs &I = P.js[t.js], &Ip = P.js[t.pvalid ? t.jsp : t.js];
-            const double *own = view.base[rank] + (size_t)NC * t.base;
-            const double *part = t.pvalid ? view.base[sd_blk_owner(P.shards, t.pbase)] + (size_t)NC * t.pbase : own;
-            double *wo = wv.p + (size_t)NC * (t.base - pstart[rank]);
-            SdBlkWrapStatic rows[1 << SD_BLK_T];                     // the kernel's shared-memory tables
-            for (int r = 0; r < (1 << SD_BLK_T); ++r) rows[r] = sd_blk_wrap_static(r);
-            for (int unit = 0; unit < sd_blk_wrap_units(NC); ++unit) {
-                int r0, r1;
-                sd_blk_wrap_unit_rows(NC, unit, r0, r1);
-                if (NC == 2) {
-                    const SdBlkWrapUnit<2> U = sd_blk_wrap_unit<2>(Wp, t, I, rows, r0, r1);
-                    for (uint32_t u = 0; u < U.nblk; ++u) sd_blk_wrap_apply<2>(Wp, U, I, Ip, u, own, part, wo);
-                } else {
-                    const SdBlkWrapUnit<1> U = sd_blk_wrap_unit<1>(Wp, t, I, rows, r0, r1);
-                    for (uint32_t u = 0; u < U.nblk; ++u) sd_blk_wrap_apply<1>(Wp, U, I, Ip, u, own, part, wo);
-                }
-            }
-        }
-        P.addin = wv.p;
-    }
+    // periodic chain: the WRAP variant of the item body; the header carries the wrap partner tile
+    if (g_wrap_J != 0.0 || g_wrap_Jz != 0.0) { P.wrap_on = 1; P.wrapJ = g_wrap_J; P.wrapJz4 = 0.25 * g_wrap_Jz; }
     const uint64_t klo_all = P.key_lo, khi_all = P.key_hi;
     for (int j = 0; j < nchunks; ++j) {
         if (halo && world > 1) {

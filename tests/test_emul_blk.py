@@ -403,10 +403,10 @@ def test_sharded_apply_with_planned_peer_ranges_and_weighted_shards(variant, L, 
 
 @pytest.mark.parametrize("NC", [1, 2])
 @pytest.mark.parametrize("L,k", [(16, 8), (16, 3), (17, 9), (18, 9), (20, 10), (16, 16), (16, 1)])
-def test_periodic_wrap_bond_pass_and_add_in(emul, L, k, NC):
-    """XXZChain(boundary=:periodic) (SpinModel.jl:71-78) on the block path: the wrap pass (sd_blk_wrap_tile / _row / _elem,
-    the code of sd_blk_wrap_kernel) followed by the item body with the add-in, every epilogue, 1 .. 3 ranks -- against the
-    oracle's apply_H! on the model with the (L, 1) bonds."""
+def test_periodic_wrap_bond_variant(emul, L, k, NC):
+    """XXZChain(boundary=:periodic) (SpinModel.jl:71-78) on the block path: the WRAP variant of the item body (the tile
+    header carries the wrap partner tile; the bond between tail site T-1 and prefix site 0 is one more element read per
+    tail configuration), every epilogue, 1 .. 3 ranks -- against the oracle's apply_H! on the model with the (L, 1) bonds."""
     rng = np.random.default_rng(500 + L * 10 + k + NC)
     Jhop, Jz, h = model_lists(L, rng)
     Jw, Jzw = float(rng.uniform(0.3, 1.5)), float(rng.uniform(-1, 1))
